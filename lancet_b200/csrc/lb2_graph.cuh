@@ -1,0 +1,536 @@
+// lb2_graph.cuh -- the order-sensitive graph stages, executed in the reference's own sweep order
+// by one lane of the window's CTA (the graphs are ~600 -> ~10 nodes; throughput comes from the
+// hundreds of windows resident on the GPU).
+//
+//   libstdc++ unordered_map iteration order      SURVEY.md Appendix D  (hashtable.h / hashtable_policy.h)
+//   Graph_t::removeLowCov / removeNode / cleanDead   src/Graph.cc:2790-2827, 2768-2784, 2737-2762
+//   Graph_t::markConnectedComponents             src/Graph.cc:2252-2336
+//   Graph_t::markRefEnds                         src/Graph.cc:2028-2228
+//   Graph_t::hasCycle / hasCycleRec              src/Graph.cc:593-681
+//   Graph_t::compress / compressNode             src/Graph.cc:2712-2732, 2486-2706
+//   Graph_t::removeTips / removeShortLinks       src/Graph.cc:2885-2926, 2833-2880
+//   findTandems                                  src/util.cc:574-758
+#ifndef LB2_GRAPH_CUH
+#define LB2_GRAPH_CUH
+
+#include "lb2_build.cuh"
+
+// ---- edge direction algebra (src/Edge.hh:62-110, src/Edge.cc:25-30) ----------------------------
+LB2_DEV int  lb2_dir_start(int d) { return (d == LB2_FF || d == LB2_FR) ? 0 : 1; }   // 0=F 1=R
+LB2_DEV int  lb2_dir_dest(int d)  { return (d == LB2_FF || d == LB2_RF) ? 0 : 1; }
+LB2_DEV bool lb2_is_dir(int d, int ori) { return lb2_dir_start(d) == ori; }
+LB2_DEV int  lb2_flipme(int d)   { return d == LB2_FF ? LB2_RF : d == LB2_FR ? LB2_RR : d == LB2_RF ? LB2_FF : LB2_FR; }
+LB2_DEV int  lb2_fliplink(int d) { return d == LB2_FF ? LB2_RR : d == LB2_FR ? LB2_FR : d == LB2_RF ? LB2_RF : LB2_FF; }
+
+// ---- node accessors ------------------------------------------------------------------------------
+LB2_DEV bool lb2_special(lb2_win &W, uint32_t id) { return (W.ws.d_flags[id] & LB2_NF_SPECIAL) != 0; }
+LB2_DEV uint32_t lb2_strlen(lb2_win &W, uint32_t id) { return lb2_special(W, id) ? 0u : W.ws.d_len[id]; }   // Node_t::strlen src/Node.cc:340-345
+
+LB2_DEV char lb2_node_char(lb2_win &W, uint32_t id, uint32_t i) {
+	lb2_ws &ws = W.ws;
+	if (ws.d_str[id] == LB2_NIL) {
+		uint32_t rep = ws.d_rep[id], g = rep >> 1; int K = W.sh->K;
+		if (rep & 1) { return lb2_base(3 - lb2_getbase(W.bits, g + K - 1 - i)); }
+		return lb2_base(lb2_getbase(W.bits, g + i));
+	}
+	return (char)ws.arena[ws.d_str[id] + i];
+}
+LB2_DEV lb2_cov lb2_node_cov(lb2_win &W, uint32_t id, uint32_t i, int sample /*0=T 1=N*/) {
+	lb2_ws &ws = W.ws; lb2_cov c;
+	if (ws.d_cd[id] == LB2_NIL) {
+		uint32_t f = ws.d_cnt[id * 4 + sample * 2], r = ws.d_cnt[id * 4 + sample * 2 + 1];
+		uint32_t df = 0, dr = 0;
+		if (W.sh->has_lowq) {
+			uint32_t v = ((const uint32_t *)ws.deficit)[((size_t)id * W.sh->K + i) * 2 + sample];
+			df = v & 0xFFFF; dr = v >> 16;
+		}
+		c.fwd = (uint16_t)f; c.rev = (uint16_t)r; c.mqf = (uint16_t)(f - df); c.mqr = (uint16_t)(r - dr);
+		return c;
+	}
+	const lb2_cov *a = (const lb2_cov *)(ws.arena + ws.d_cd[id]);
+	return a[(size_t)sample * ws.d_len[id] + i];
+}
+LB2_DEV float lb2_totcov(lb2_win &W, uint32_t id) {   // Node_t::getTotCov (src/Node.hh:151), same association order
+	float *c = W.ws.d_cov + id * 4; return c[0] + c[1] + c[2] + c[3];
+}
+LB2_DEV uint32_t lb2_arena_alloc(lb2_win &W, uint32_t bytes) {
+	uint32_t o = (W.sh->arena_used + 7u) & ~7u;
+	if (o + bytes > W.C->arena_bytes) { W.sh->err |= 1u << LB2_D_ARENA; return 0; }
+	W.sh->arena_used = o + bytes; return o;
+}
+
+// ---- libstdc++ _Hashtable order emulation -----------------------------------------------------------
+LB2_DEV uint32_t lb2_oe_next(lb2_win &W, uint32_t x) { return x == LB2_SENT ? W.sh->lhead : W.ws.d_lnext[x]; }
+LB2_DEV void lb2_oe_setnext(lb2_win &W, uint32_t x, uint32_t v) { if (x == LB2_SENT) { W.sh->lhead = v; } else { W.ws.d_lnext[x] = v; } }
+LB2_DEV uint32_t lb2_oe_next_bkt(uint32_t x) {
+	const uint32_t chain[] = { 13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753, 42043, 85229, 172933 };
+	for (int i = 0; i < 14; ++i) { if (chain[i] >= x) { return chain[i]; } }
+	return 0;
+}
+LB2_DEV void lb2_oe_reset(lb2_win &W) {
+	lb2_sh *sh = W.sh; sh->bkt_count = 1; sh->elem_count = 0; sh->next_resize = 0; sh->lhead = LB2_NIL;
+	W.ws.buckets[0] = LB2_NIL;
+}
+LB2_DEV void lb2_oe_rehash(lb2_win &W, uint32_t nb) {   // _M_rehash_aux (unique keys)
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	for (uint32_t b = 0; b < nb; ++b) { ws.buckets[b] = LB2_NIL; }
+	uint32_t p = sh->lhead; sh->lhead = LB2_NIL; uint32_t bbegin = 0;
+	while (p != LB2_NIL) {
+		uint32_t nx = ws.d_lnext[p];
+		uint32_t b = (uint32_t)(ws.d_hash[p] % nb);
+		if (ws.buckets[b] == LB2_NIL) {
+			ws.d_lnext[p] = sh->lhead; sh->lhead = p; ws.buckets[b] = LB2_SENT;
+			if (ws.d_lnext[p] != LB2_NIL) { ws.buckets[bbegin] = p; }
+			bbegin = b;
+		} else {
+			uint32_t before = ws.buckets[b];
+			ws.d_lnext[p] = lb2_oe_next(W, before); lb2_oe_setnext(W, before, p);
+		}
+		p = nx;
+	}
+	sh->bkt_count = nb;
+}
+LB2_DEV void lb2_oe_insert(lb2_win &W, uint32_t id) {   // _M_insert_unique_node + _Prime_rehash_policy::_M_need_rehash
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	uint32_t n = sh->elem_count;
+	if (n + 1 > sh->next_resize) {
+		uint32_t min_bkts = n + 1; if (!sh->next_resize && min_bkts < 11) { min_bkts = 11; }
+		if (min_bkts >= sh->bkt_count) {
+			uint32_t want = min_bkts + 1; if (want < sh->bkt_count * 2) { want = sh->bkt_count * 2; }
+			uint32_t nb = lb2_oe_next_bkt(want);
+			if (nb == 0 || nb > W.C->bucket_cap) { sh->err |= 1u << LB2_D_BUCKETS; return; }
+			sh->next_resize = nb;
+			lb2_oe_rehash(W, nb);
+		} else { sh->next_resize = sh->bkt_count; }
+	}
+	uint32_t b = (uint32_t)(ws.d_hash[id] % sh->bkt_count);
+	if (ws.buckets[b] != LB2_NIL) {
+		uint32_t before = ws.buckets[b];
+		ws.d_lnext[id] = lb2_oe_next(W, before); lb2_oe_setnext(W, before, id);
+	} else {
+		ws.d_lnext[id] = sh->lhead; sh->lhead = id;
+		if (ws.d_lnext[id] != LB2_NIL) { ws.buckets[(uint32_t)(ws.d_hash[ws.d_lnext[id]] % sh->bkt_count)] = id; }
+		ws.buckets[b] = LB2_SENT;
+	}
+	sh->elem_count = n + 1;
+}
+LB2_DEV void lb2_oe_erase(lb2_win &W, uint32_t id) {    // _M_erase(bkt, prev, n)
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	uint32_t B = sh->bkt_count, b = (uint32_t)(ws.d_hash[id] % B);
+	uint32_t prev = ws.buckets[b];
+	while (lb2_oe_next(W, prev) != id) { prev = lb2_oe_next(W, prev); }
+	uint32_t nx = ws.d_lnext[id];
+	if (prev == ws.buckets[b]) {
+		uint32_t nb = (nx != LB2_NIL) ? (uint32_t)(ws.d_hash[nx] % B) : 0;
+		if (nx == LB2_NIL || nb != b) {
+			if (nx != LB2_NIL) { ws.buckets[nb] = ws.buckets[b]; }
+			ws.buckets[b] = LB2_NIL;   // (before_begin.next is updated by the unlink below)
+		}
+	} else if (nx != LB2_NIL) {
+		uint32_t nb = (uint32_t)(ws.d_hash[nx] % B);
+		if (nb != b) { ws.buckets[nb] = prev; }
+	}
+	lb2_oe_setnext(W, prev, nx);
+	sh->elem_count -= 1;
+	ws.d_flags[id] |= LB2_NF_GONE;
+}
+
+// ---- edge helpers (Node_t::removeEdge / updateEdge, src/Node.cc:177-233) ------------------------------
+LB2_DEV void lb2_remove_edge(lb2_win &W, uint32_t id, uint32_t to, int dir) {
+	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	for (int i = 0; i < ne; ++i) {
+		if (e[i].to == to && e[i].dir == dir) {
+			for (int j = i; j + 1 < ne; ++j) { e[j] = e[j + 1]; }
+			ws.d_ne[id] = (uint8_t)(ne - 1); return;
+		}
+	}
+	W.sh->err |= 1u << LB2_D_EDGES;   // the reference would assert here
+}
+LB2_DEV void lb2_update_edge(lb2_win &W, uint32_t id, uint32_t oldto, int olddir, uint32_t newto, int newdir) {
+	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	for (int i = 0; i < ne; ++i) {
+		if (e[i].to == oldto && e[i].dir == olddir) { e[i].to = newto; e[i].dir = (uint8_t)newdir; return; }
+	}
+	W.sh->err |= 1u << LB2_D_EDGES;
+}
+LB2_DEV void lb2_push_edge(lb2_win &W, uint32_t id, uint32_t to, int dir, int flag) {
+	lb2_ws &ws = W.ws; int ne = ws.d_ne[id];
+	if (ne >= LB2_ECAP) { W.sh->err |= 1u << LB2_D_EDGES; return; }
+	lb2_edge ed; ed.to = to; ed.dir = (uint8_t)dir; ed.flag = (uint8_t)flag; ed.pad = 0;
+	ws.d_edge[(size_t)id * LB2_ECAP + ne] = ed; ws.d_ne[id] = (uint8_t)(ne + 1);
+}
+LB2_DEV void lb2_add_edge_node(lb2_win &W, uint32_t id, uint32_t to, int dir) {   // Node_t::addEdge without read ids
+	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	for (int i = 0; i < ne; ++i) { if (e[i].to == to && e[i].dir == dir) { return; } }
+	lb2_push_edge(W, id, to, dir, 0);
+}
+LB2_DEV void lb2_remove_node(lb2_win &W, uint32_t id) {   // Graph_t::removeNode
+	lb2_ws &ws = W.ws; ws.d_flags[id] |= LB2_NF_DEAD;
+	lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	for (int i = 0; i < ne; ++i) { if (e[i].to != id) { lb2_remove_edge(W, e[i].to, id, lb2_fliplink(e[i].dir)); } }
+}
+LB2_DEV void lb2_clean_dead(lb2_win &W) {                 // Graph_t::cleanDead
+	lb2_ws &ws = W.ws;
+	uint32_t p = W.sh->lhead;
+	while (p != LB2_NIL) { uint32_t nx = ws.d_lnext[p]; if (ws.d_flags[p] & LB2_NF_DEAD) { lb2_oe_erase(W, p); } p = nx; }
+}
+LB2_DEV bool lb2_is_tandem(lb2_win &W, uint32_t id) {     // Node_t::isTandem
+	lb2_edge *e = W.ws.d_edge + (size_t)id * LB2_ECAP; int ne = W.ws.d_ne[id];
+	for (int i = 0; i < ne; ++i) { if (e[i].to == id) { return true; } }
+	return false;
+}
+LB2_DEV int lb2_get_buddy(lb2_win &W, uint32_t id, int ori) {   // Node_t::getBuddy
+	if (lb2_special(W, id)) { return -1; }
+	lb2_edge *e = W.ws.d_edge + (size_t)id * LB2_ECAP; int ne = W.ws.d_ne[id]; int r = -1;
+	for (int i = 0; i < ne; ++i) { if (lb2_is_dir(e[i].dir, ori)) { if (r != -1) { return -1; } r = i; } }
+	if (r != -1 && e[r].to == id) { return -1; }
+	return r;
+}
+
+// ---- findTandems (src/util.cc:574-758); seq given through an accessor; returns ans, LEN, motif appended ----
+template <class GetC>
+LB2_DEV bool lb2_find_tandems(GetC getc, uint32_t slen, const lb2_params *P, int pos, int &len, char *motif, uint32_t &mlen, uint32_t mcap, bool &movf)
+{
+	bool ans = false;
+	const uint32_t MAXU = (uint32_t)P->max_unit_len;
+	int offsets[17][17];
+	for (uint32_t m = 1; m <= MAXU && m <= 16; ++m) { for (uint32_t ph = 0; ph < m; ++ph) { offsets[m][ph] = (int)ph; } }
+	const int delta = P->dist_from_str;
+	for (uint32_t i = 0; i < slen; ++i) {
+		for (uint32_t merlen = 1; merlen <= MAXU && merlen <= 16; ++merlen) {
+			int phase = (int)(i % merlen);
+			int offset = offsets[merlen][phase];
+			uint32_t j = 0;
+			while (j < merlen && i + j < slen && getc(i + j) == getc((uint32_t)offset + j)) { ++j; }
+			if (j != merlen || (i + j + 1 == slen)) {
+				// seq[offset-1] at offset 0 reads the byte before the buffer: 0 in practice
+				char left = (offset >= 1) ? getc((uint32_t)offset - 1) : (char)0;
+				if (left != getc((uint32_t)offset + merlen - 1)) {
+					if (((i - (uint32_t)offset) / merlen >= (uint32_t)P->min_report_units) && (i - (uint32_t)offset >= (uint32_t)P->min_report_len)) {
+						uint32_t ml = 1;
+						while (ml < merlen) {
+							uint32_t units = (i - (uint32_t)offset + j) / ml;
+							int allmatch = 1;
+							for (uint32_t index = 1; allmatch && index < units; ++index) {
+								for (uint32_t m = 0; m < ml; ++m) {
+									if (getc((uint32_t)offset + m) != getc((uint32_t)offset + index * ml + m)) { allmatch = 0; break; }
+								}
+							}
+							if (!allmatch) { ++ml; } else { break; }
+						}
+						if (ml == merlen) {
+							int start = offset, end = (int)(i + j), LL = (int)(i + j) - offset;
+							if (pos >= start - delta && pos <= end + delta) {
+								ans = true; len = LL;
+								for (uint32_t z = 0; z < merlen; ++z) {
+									if (mlen < mcap) { motif[mlen++] = getc((uint32_t)offset + z); } else { movf = true; }
+								}
+							}
+						}
+					}
+				}
+				offsets[merlen][phase] = (int)i;
+			}
+		}
+	}
+	return ans;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sequential stages (lane 0)
+// ---------------------------------------------------------------------------------------------------
+LB2_DEVNI void lb2_order_nodes(lb2_win &W) {
+	lb2_oe_reset(W);
+	for (uint32_t j = 0; j < W.sh->n_nodes; ++j) { lb2_oe_insert(W, j); if (W.sh->err) { return; } }
+}
+
+// removeLowCov(docompression=false path and the sweep part) src/Graph.cc:2790-2827
+LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
+	double thr = W.P->min_cov_ratio * avgcov;
+	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+		if (ws.d_comp[p] != compid) { continue; }
+		if (lb2_special(W, p)) { continue; }
+		int mq = ws.d_mincovqv[p];
+		float tt = ws.d_cov[p * 4 + 0] + ws.d_cov[p * 4 + 1], tn = ws.d_cov[p * 4 + 2] + ws.d_cov[p * 4 + 3];
+		if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { lb2_remove_node(W, p); }
+	}
+	lb2_clean_dead(W);
+}
+
+LB2_DEVNI int lb2_mark_components(lb2_win &W) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) { ws.d_comp[p] = 0; }
+	int comp = 0; uint32_t *Q = ws.stack;   // FIFO; every edge is pushed at most once per labelled node
+	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+		if (ws.d_comp[p] != 0) { continue; }
+		++comp;
+		uint32_t qh = 0, qt = 0; Q[qt++] = p; ws.d_comp[p] = comp;
+		while (qh < qt) {   // labels depend only on connectivity and on which node opens the component
+			uint32_t cur = Q[qh++];
+			lb2_edge *e = ws.d_edge + (size_t)cur * LB2_ECAP; int ne = ws.d_ne[cur];
+			for (int i = 0; i < ne; ++i) { if (ws.d_comp[e[i].to] == 0) { ws.d_comp[e[i].to] = comp; Q[qt++] = e[i].to; } }
+		}
+	}
+	return comp;
+}
+
+// special node creation: key string "source<c>" / "sink<c>" hashed like any other map key
+LB2_DEV uint32_t lb2_new_special(lb2_win &W, bool source, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	if (sh->n_spec >= LB2_MAX_SPECIAL) { sh->err |= 1u << LB2_D_SPECIAL; return LB2_NIL; }
+	uint32_t id = W.C->max_nodes + sh->n_spec++;
+	char buf[24]; int n = 0;
+	const char *pre = source ? "source" : "sink";
+	while (*pre) { buf[n++] = *pre++; }
+	char dig[12]; int nd = 0; int c = compid; do { dig[nd++] = (char)('0' + c % 10); c /= 10; } while (c);
+	while (nd) { buf[n++] = dig[--nd]; }
+	ws.d_hash[id] = lb2_stdhash_bytes(buf, (uint32_t)n);
+	ws.d_flags[id] = source ? LB2_NF_SOURCE : LB2_NF_SINK;
+	ws.d_comp[id] = compid; ws.d_ne[id] = 0; ws.d_len[id] = 0; ws.d_str[id] = LB2_NIL; ws.d_cd[id] = LB2_NIL;
+	for (int k = 0; k < 4; ++k) { ws.d_cov[id * 4 + k] = 0; ws.d_cnt[id * 4 + k] = 0; }
+	ws.d_stn[id] = 0; ws.d_stT[id] = 0; ws.d_color[id] = 0; ws.d_mincov[id] = 0; ws.d_mincovqv[id] = 0;
+	return id;
+}
+
+// markRefEnds src/Graph.cc:2028-2228.  The reference looks every window k-mer up in the map; here the
+// dense node of the reference k-mer at each offset was recorded at build time (ws.refnode).
+LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const int L = (int)sh->L;
+	sh->trim5 = 0xFFFF; sh->trim3 = 0xFFFF; sh->source = LB2_NIL; sh->sink = LB2_NIL;
+	uint32_t src = LB2_NIL, snk = LB2_NIL; int src_off = -1, snk_off = -1;
+	const float thr = (float)W.P->cov_threshold;
+	for (int off = 0; off + K <= L; ++off) {
+		uint32_t nd = ws.refnode[off];
+		if (nd == LB2_NIL || (ws.d_flags[nd] & LB2_NF_GONE)) { continue; }
+		if (lb2_totcov(W, nd) >= thr && ws.d_comp[nd] == compid) {
+			if (src == LB2_NIL) { src = nd; src_off = off; }
+			else if (src == nd) { return; }   // ambiguous match
+		}
+	}
+	if (src == LB2_NIL) { return; }
+	for (int off = L - K; off >= 0; --off) {
+		uint32_t nd = ws.refnode[off];
+		if (nd == LB2_NIL || (ws.d_flags[nd] & LB2_NF_GONE)) { continue; }
+		if (lb2_totcov(W, nd) >= thr && ws.d_comp[nd] == compid) {
+			if (snk == LB2_NIL) { snk = nd; snk_off = off; }
+			else if (snk == nd) { return; }
+		}
+	}
+	if (snk == LB2_NIL) { return; }
+	int ref_dist = snk_off - src_off + K;
+	// std::string::substr(pos, n) clamps n; a negative n (sink left of source) becomes npos => to the end
+	sh->seq_off = (uint32_t)src_off;
+	sh->seq_len = (ref_dist < 0) ? (uint32_t)(L - src_off) : (uint32_t)((src_off + ref_dist > L) ? (L - src_off) : ref_dist);
+	sh->trim5 = (uint32_t)src_off & 0xFFFF; sh->trim3 = (uint32_t)(L - snk_off - K) & 0xFFFF;
+	// orientation of the anchor k-mers in the reference: F iff the reference spelling is the canonical one
+	auto ref_ori = [&](int off) -> int {
+		lb2_kmer f, rc; lb2_extract(W.bits, sh->ref_g + (uint32_t)off, K, f); lb2_revcomp(f, K, rc);
+		return lb2_less(f, rc, sh->nw) ? 0 : 1;
+	};
+	int sori = ref_ori(src_off), kori = ref_ori(snk_off);
+	uint32_t ns = lb2_new_special(W, true, compid); if (ns == LB2_NIL) { return; }
+	int sourcedir = sori ? LB2_FR : LB2_FF;
+	{
+		lb2_edge *e = ws.d_edge + (size_t)src * LB2_ECAP;
+		for (int i = (int)ws.d_ne[src] - 1; i >= 0; --i) {
+			if (lb2_dir_start(e[i].dir) == (sori ^ 1)) {
+				uint32_t other = e[i].to;
+				if (other != src) {
+					lb2_remove_edge(W, other, src, lb2_fliplink(e[i].dir));
+					int ne = ws.d_ne[src]; for (int j = i; j + 1 < ne; ++j) { e[j] = e[j + 1]; } ws.d_ne[src] = (uint8_t)(ne - 1);
+				}
+			}
+		}
+	}
+	lb2_add_edge_node(W, ns, src, sourcedir);
+	lb2_add_edge_node(W, src, ns, lb2_fliplink(sourcedir));
+	lb2_oe_insert(W, ns);
+	uint32_t nk = lb2_new_special(W, false, compid); if (nk == LB2_NIL) { return; }
+	int sinkdir = kori ? LB2_FF : LB2_RR;
+	{
+		lb2_edge *e = ws.d_edge + (size_t)snk * LB2_ECAP;
+		for (int i = (int)ws.d_ne[snk] - 1; i >= 0; --i) {
+			if (lb2_dir_start(e[i].dir) == kori) {
+				uint32_t other = e[i].to;
+				if (other != snk) {
+					lb2_remove_edge(W, other, snk, lb2_fliplink(e[i].dir));
+					int ne = ws.d_ne[snk]; for (int j = i; j + 1 < ne; ++j) { e[j] = e[j + 1]; } ws.d_ne[snk] = (uint8_t)(ne - 1);
+				}
+			}
+		}
+	}
+	lb2_add_edge_node(W, nk, snk, sinkdir);
+	lb2_add_edge_node(W, snk, nk, lb2_fliplink(sinkdir));
+	lb2_oe_insert(W, nk);
+	sh->source = ns; sh->sink = nk;
+}
+
+// hasCycle / hasCycleRec with an explicit stack (node, incoming orientation, next edge index)
+LB2_DEV bool lb2_cycle_from(lb2_win &W, uint32_t start, int ori) {
+	lb2_ws &ws = W.ws; uint32_t *st = ws.stack; uint32_t sp = 0; bool ans = false;
+	const uint32_t cap = (W.C->max_nodes + LB2_MAX_SPECIAL) * 2;
+	ws.d_color[start] = 2; st[sp++] = start; st[sp++] = ((uint32_t)ori << 16) | 0u;
+	while (sp) {
+		uint32_t node = st[sp - 2]; uint32_t v = st[sp - 1]; int o = (int)(v >> 16); int i = (int)(v & 0xFFFF);
+		if (ans || i >= (int)ws.d_ne[node]) { ws.d_color[node] = 3; sp -= 2; continue; }
+		st[sp - 1] = ((uint32_t)o << 16) | (uint32_t)(i + 1);
+		lb2_edge ed = ws.d_edge[(size_t)node * LB2_ECAP + i];
+		if (!lb2_is_dir(ed.dir, o)) { continue; }
+		uint32_t other = ed.to;
+		if (lb2_special(W, other)) { continue; }
+		if (ws.d_color[other] == 2) { ans = true; st[sp - 1] = ((uint32_t)o << 16) | 0xFFFFu; continue; }   // break out of this node's loop
+		if (ws.d_color[other] == 1) {
+			if (sp + 2 > cap) { W.sh->err |= 1u << LB2_D_STACK; return true; }
+			ws.d_color[other] = 2; st[sp++] = other; st[sp++] = ((uint32_t)lb2_dir_dest(ed.dir) << 16) | 0u;
+		}
+	}
+	return ans;
+}
+LB2_DEVNI bool lb2_has_cycle(lb2_win &W) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	if (sh->source == LB2_NIL || sh->sink == LB2_NIL) { return false; }
+	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) { if (!lb2_special(W, p)) { ws.d_color[p] = 1; } }
+	bool a1 = lb2_cycle_from(W, sh->source, 0);
+	bool a2 = lb2_cycle_from(W, sh->source, 1);
+	return a1 || a2;
+}
+
+// ---- compressNode: walk one direction, literal edge surgery + float averages; bases/coverage of the
+//      absorbed nodes are laid out afterwards in one pass (see lb2_compress_one) ----------------------
+// chain entry: node id | flip<<31 (flip: buddy is reverse-complemented in the seed's frame)
+LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *chain, uint32_t nchain, uint32_t &curlen) {
+	lb2_ws &ws = W.ws; const int K = W.sh->K;
+	while (true) {
+		int uid = lb2_get_buddy(W, node, dir);
+		if (uid == -1) { break; }
+		if (lb2_is_tandem(W, node)) { break; }
+		lb2_edge *ne_ = ws.d_edge + (size_t)node * LB2_ECAP;
+		int edir = ne_[uid].dir;
+		int bdir = (edir == LB2_FF || edir == LB2_RF) ? 1 : 0;
+		uint32_t buddy = ne_[uid].to;
+		if (lb2_is_tandem(W, buddy)) { break; }
+		int buid = lb2_get_buddy(W, buddy, bdir);
+		if (buid == -1) { break; }
+		// orientation of the buddy in the seed's frame
+		int dest_r = lb2_dir_dest(edir);               // 1 => buddy string is reverse-complemented in the walking frame
+		uint32_t flip = (dir == 0) ? (uint32_t)dest_r : (uint32_t)(dest_r ^ 1);
+		chain[nchain++] = buddy | (flip << 31);
+		// float coverage, same expression order as src/Graph.cc:2631-2636
+		int amerlen = (int)curlen - K + 1, bmerlen = (int)ws.d_len[buddy] - K + 1;
+		for (int c = 0; c < 4; ++c) {
+			float nc = ws.d_cov[node * 4 + c], cc = ws.d_cov[buddy * 4 + c];
+			ws.d_cov[node * 4 + c] = ((nc * amerlen) + (cc * bmerlen)) / (amerlen + bmerlen);
+		}
+		curlen += (uint32_t)bmerlen;
+		ws.d_stn[node] += ws.d_stn[buddy]; ws.d_stT[node] += ws.d_stT[buddy];
+		ws.d_flags[buddy] |= LB2_NF_DEAD;
+		// node edges: erase the buddy edge, move over the buddy's other edges
+		{ int ne = ws.d_ne[node]; for (int j = uid; j + 1 < ne; ++j) { ne_[j] = ne_[j + 1]; } ws.d_ne[node] = (uint8_t)(ne - 1); }
+		lb2_edge *be = ws.d_edge + (size_t)buddy * LB2_ECAP; int bne = ws.d_ne[buddy];
+		for (int i = 0; i < bne; ++i) {
+			if (i == buid) { continue; }
+			int nd = be[i].dir; if (edir == LB2_FR || edir == LB2_RF) { nd = lb2_flipme(nd); }
+			uint32_t other = be[i].to;
+			if (other == buddy) { lb2_push_edge(W, node, node, nd, be[i].flag); }   // "circle to buddy"
+			else {
+				lb2_push_edge(W, node, other, nd, be[i].flag);
+				lb2_update_edge(W, other, buddy, lb2_fliplink(be[i].dir), node, lb2_fliplink(nd));
+			}
+		}
+		if (W.sh->err) { break; }
+	}
+	return nchain;
+}
+
+LB2_DEVNI void lb2_compress_one(lb2_win &W, uint32_t node) {
+	lb2_ws &ws = W.ws; const int K = W.sh->K;
+	uint32_t *chain = ws.chain;
+	uint32_t len0 = ws.d_len[node], curlen = len0;
+	uint32_t nF = lb2_compress_dir(W, node, 0, chain, 0, curlen);
+	uint32_t nAll = lb2_compress_dir(W, node, 1, chain, nF, curlen);
+	if (nAll == 0 || W.sh->err) { return; }
+	// layout: [R-chain, last absorbed first] seed [F-chain]
+	uint32_t so = lb2_arena_alloc(W, curlen); uint32_t co = lb2_arena_alloc(W, curlen * 2 * (uint32_t)sizeof(lb2_cov));
+	if (W.sh->err) { return; }
+	char *S = (char *)ws.arena + so; lb2_cov *CT = (lb2_cov *)(ws.arena + co); lb2_cov *CN = CT + curlen;
+	uint32_t leftlen = 0;
+	for (uint32_t c = nF; c < nAll; ++c) { leftlen += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
+	// seed
+	for (uint32_t i = 0; i < len0; ++i) { S[leftlen + i] = lb2_node_char(W, node, i); CT[leftlen + i] = lb2_node_cov(W, node, i, 0); CN[leftlen + i] = lb2_node_cov(W, node, i, 1); }
+	// F chain: append oriented[K-1..]
+	uint32_t pos = leftlen + len0;
+	for (uint32_t c = 0; c < nF; ++c) {
+		uint32_t b = chain[c] & 0x7FFFFFFFu; bool flip = (chain[c] >> 31) != 0; uint32_t bl = ws.d_len[b];
+		for (uint32_t i = (uint32_t)K - 1; i < bl; ++i, ++pos) {
+			uint32_t src = flip ? (bl - 1 - i) : i;
+			char ch = lb2_node_char(W, b, src); S[pos] = flip ? lb2_comp(ch) : ch;
+			CT[pos] = lb2_node_cov(W, b, src, 0); CN[pos] = lb2_node_cov(W, b, src, 1);
+		}
+	}
+	// R chain: the c-th absorbed node sits left of everything absorbed before it; it contributes frame[0 .. bl-K]
+	pos = leftlen;
+	for (uint32_t c = nF; c < nAll; ++c) {
+		uint32_t b = chain[c] & 0x7FFFFFFFu; bool flip = (chain[c] >> 31) != 0; uint32_t bl = ws.d_len[b];
+		uint32_t cntb = bl - K + 1; pos -= cntb;
+		for (uint32_t i = 0; i < cntb; ++i) {
+			uint32_t src = flip ? (bl - 1 - i) : i;
+			char ch = lb2_node_char(W, b, src); S[pos + i] = flip ? lb2_comp(ch) : ch;
+			CT[pos + i] = lb2_node_cov(W, b, src, 0); CN[pos + i] = lb2_node_cov(W, b, src, 1);
+		}
+	}
+	ws.d_str[node] = so; ws.d_cd[node] = co; ws.d_len[node] = curlen;
+	// Node_t::computeMinCov (src/Node.cc:600-615)
+	int mn = 10000000, mnq = 10000000;
+	for (uint32_t i = 0; i < curlen; ++i) {
+		int t = CT[i].fwd + CT[i].rev + CN[i].fwd + CN[i].rev, q = CT[i].mqf + CT[i].mqr + CN[i].mqf + CN[i].mqr;
+		if (t < mn) { mn = t; } if (q < mnq) { mnq = q; }
+	}
+	ws.d_mincov[node] = mn; ws.d_mincovqv[node] = mnq;
+}
+
+LB2_DEVNI void lb2_compress(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws;
+	for (uint32_t p = W.sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+		if (ws.d_comp[p] != compid) { continue; }
+		if (ws.d_flags[p] & LB2_NF_DEAD) { continue; }
+		if (lb2_special(W, p)) { continue; }
+		lb2_compress_one(W, p);
+		if (W.sh->err) { return; }
+	}
+	lb2_clean_dead(W);
+}
+
+LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; const int K = W.sh->K; int tips;
+	do {
+		tips = 0;
+		for (uint32_t p = W.sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+			if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
+			int deg = ws.d_ne[p]; int len = (int)lb2_strlen(W, p) - K + 1;
+			if (deg <= 1 && len < W.P->max_tip_len) { lb2_remove_node(W, p); ++tips; }
+		}
+		if (tips) { lb2_compress(W, compid); }
+	} while (tips && !W.sh->err);
+}
+
+LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; const int K = W.sh->K; int links = 0;
+	double avgcov = ((double)(int)W.sh->totalreadbp) / ((double)W.sh->L);
+	const int max_link = (int)floor((double)K / 2.0);
+	const double lim = floor(sqrt(avgcov));
+	for (uint32_t p = W.sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+		if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
+		int deg = ws.d_ne[p]; int len = (int)ws.d_len[p] - K + 1;
+		if (deg >= 2 && len < max_link && (double)ws.d_mincov[p] <= lim) {
+			int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false;
+			uint32_t id = p;
+			lb2_find_tandems([&](uint32_t i) -> char { return lb2_node_char(W, id, i); }, ws.d_len[p], W.P, K - 1, LEN, motif, ml, 0, ov);
+			if (LEN == 0) { lb2_remove_node(W, p); ++links; }
+		}
+	}
+	if (links) { lb2_compress(W, compid); }
+}
+
+#endif

@@ -1,0 +1,138 @@
+// lb2_kmer.cuh -- 2-bit packed k-mers (k <= 128), canonical form, table hash, libstdc++ string hash.
+//
+// Layout: base i of a k-mer lives at bits [2i,2i+1] of a little-endian 2k-bit integer held in
+// NW = ceil(k/32) 64-bit words (word 0 = first 32 bases).  Codes A=0 C=1 G=2 T=3, so that the
+// reference's std::string comparison (src/Mer.hh:57-71, 'A'<'C'<'G'<'T') is a comparison of the
+// first differing 2-bit group.
+#ifndef LB2_KMER_CUH
+#define LB2_KMER_CUH
+
+#include "lb2_prims.cuh"
+
+#define LB2_MAXW 4
+
+struct lb2_kmer { uint64_t w[LB2_MAXW]; };
+
+LB2_DEV int lb2_nw(int K) { return (K + 31) >> 5; }
+
+LB2_DEV int lb2_code(char c) {   // ACGT -> 0..3, anything else -> -1
+	switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; }
+	return -1;
+}
+LB2_DEV char lb2_base(int code) { return (char)((0x54474341u >> (8 * code)) & 0xFF); }
+LB2_DEV char lb2_comp(char c) { // rrc() of reference src/util.cc:246-258 for upper-case input
+	switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; case 'N': return 'N'; }
+	return 0;
+}
+
+// read base g of a packed 2-bit array
+LB2_DEV int lb2_getbase(const uint32_t *bits, uint32_t g) { return (bits[g >> 4] >> ((g & 15) << 1)) & 3; }
+LB2_DEV int lb2_getbit(const uint32_t *mask, uint32_t g) { return (mask[g >> 5] >> (g & 31)) & 1; }
+
+// extract K bases starting at base g (little-endian words)
+LB2_DEV void lb2_extract(const uint32_t *bits, uint32_t g, int K, lb2_kmer &out) {
+	int nw = lb2_nw(K);
+	uint32_t bitpos = g << 1;
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		if (j < nw) {
+			uint32_t bp = bitpos + (uint32_t)j * 64;
+			uint32_t wi = bp >> 5, sh = bp & 31;
+			uint64_t lo = bits[wi], mid = bits[wi + 1], hi = bits[wi + 2];
+			uint64_t v = (lo >> sh) | (mid << (32 - sh));
+			if (sh) { v |= hi << (64 - sh); }
+			out.w[j] = v;
+		} else { out.w[j] = 0; }
+	}
+	int rem = (K & 31);
+	if (rem) { out.w[nw - 1] &= (~0ull) >> (64 - 2 * rem); }
+}
+
+// rolling update: drop first base, append code c at position K-1
+LB2_DEV void lb2_roll_fwd(lb2_kmer &f, int K, int c) {
+	int nw = lb2_nw(K);
+	for (int j = 0; j < LB2_MAXW - 1; ++j) { if (j < nw - 1) { f.w[j] = (f.w[j] >> 2) | (f.w[j + 1] << 62); } }
+	f.w[nw - 1] >>= 2;
+	f.w[(K - 1) >> 5] |= (uint64_t)c << (((K - 1) & 31) << 1);
+}
+// reverse complement rolling update: prepend complement of c, drop last base
+LB2_DEV void lb2_roll_rc(lb2_kmer &r, int K, int c) {
+	int nw = lb2_nw(K);
+	for (int j = LB2_MAXW - 1; j > 0; --j) { if (j < nw) { r.w[j] = (r.w[j] << 2) | (r.w[j - 1] >> 62); } }
+	r.w[0] = (r.w[0] << 2) | (uint64_t)(3 - c);
+	int rem = (K & 31);
+	if (rem) { r.w[nw - 1] &= (~0ull) >> (64 - 2 * rem); }
+}
+
+// lexicographic a < b  (std::string operator<, equal -> false)
+LB2_DEV bool lb2_less(const lb2_kmer &a, const lb2_kmer &b, int nw) {
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		if (j < nw) {
+			uint64_t x = a.w[j] ^ b.w[j];
+			if (x) {
+				int pos = lb2_ctz64(x) & ~1;
+				return ((a.w[j] >> pos) & 3) < ((b.w[j] >> pos) & 3);
+			}
+		}
+	}
+	return false;
+}
+LB2_DEV bool lb2_equal(const lb2_kmer &a, const lb2_kmer &b, int nw) {
+	bool eq = true;
+	for (int j = 0; j < LB2_MAXW; ++j) { if (j < nw && a.w[j] != b.w[j]) { eq = false; } }
+	return eq;
+}
+
+// table hash (not semantically significant -- only spreads keys over the open-addressing table)
+LB2_DEV uint64_t lb2_mix64(uint64_t x) {
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+LB2_DEV uint64_t lb2_table_hash(const lb2_kmer &k, int nw) {
+	uint64_t h = 0x9E3779B97F4A7C15ull;
+	for (int j = 0; j < LB2_MAXW; ++j) { if (j < nw) { h = lb2_mix64(h ^ k.w[j]) + 0x632BE59BD9B4E019ull; } }
+	return h;
+}
+
+// ---- libstdc++ std::hash<std::string> == _Hash_bytes(p, len, 0xc70f6907) (64-bit murmur2 variant)
+// (libstdc++-v3/libsupc++/hash_bytes.cc).  Semantically significant: it
+// fixes the iteration order of the reference's unordered_map<string,Node_t*> (src/Graph.hh:68).
+LB2_DEV uint64_t lb2_shift_mix(uint64_t v) { return v ^ (v >> 47); }
+
+struct lb2_stdhash {
+	uint64_t h; uint64_t acc; int nacc;
+};
+LB2_DEV void lb2_sh_init(lb2_stdhash &s, uint32_t len) {
+	const uint64_t mul = 0xc6a4a7935bd1e995ull;
+	s.h = 0xc70f6907ull ^ ((uint64_t)len * mul); s.acc = 0; s.nacc = 0;
+}
+LB2_DEV void lb2_sh_byte(lb2_stdhash &s, unsigned char c) {
+	const uint64_t mul = 0xc6a4a7935bd1e995ull;
+	s.acc |= (uint64_t)c << (8 * s.nacc);
+	if (++s.nacc == 8) {
+		uint64_t d = lb2_shift_mix(s.acc * mul) * mul;
+		s.h ^= d; s.h *= mul; s.acc = 0; s.nacc = 0;
+	}
+}
+LB2_DEV uint64_t lb2_sh_final(lb2_stdhash &s) {
+	const uint64_t mul = 0xc6a4a7935bd1e995ull;
+	if (s.nacc) { s.h ^= s.acc; s.h *= mul; }
+	s.h = lb2_shift_mix(s.h) * mul;
+	s.h = lb2_shift_mix(s.h);
+	return s.h;
+}
+LB2_DEV uint64_t lb2_stdhash_bytes(const char *p, uint32_t len) {
+	lb2_stdhash s; lb2_sh_init(s, len);
+	for (uint32_t i = 0; i < len; ++i) { lb2_sh_byte(s, (unsigned char)p[i]); }
+	return lb2_sh_final(s);
+}
+// hash of the ASCII spelling of a packed k-mer
+LB2_DEV uint64_t lb2_stdhash_kmer(const lb2_kmer &k, int K) {
+	lb2_stdhash s; lb2_sh_init(s, (uint32_t)K);
+	for (int i = 0; i < K; ++i) {
+		int code = (int)((k.w[i >> 5] >> ((i & 31) << 1)) & 3);
+		lb2_sh_byte(s, (unsigned char)lb2_base(code));
+	}
+	return lb2_sh_final(s);
+}
+
+#endif

@@ -1,0 +1,348 @@
+// lb2_paths.cuh -- source->sink path enumeration, contig/reference alignment, variant extraction.
+//
+//   Graph_t::bfs / eka                      src/Graph.cc:1299-1425, 1430-1501
+//   Graph_t::findRepeatsInGraphPaths        src/Graph.cc:686-730
+//   Path_t::str / covDistr / pathcontig     src/Path.cc:69-108, 110-180, 291-314
+//   Graph_t::processPath                    src/Graph.cc:788-1220
+//   global_align_aff                        src/align.cc:235-364   (full-matrix Gotoh, CTA-wide wavefront)
+//   Transcript_t / computeStats             src/Transcript.hh:79-226
+//   isRepeat / isAlmostRepeat / kMismatch   src/util.cc:295-360
+#ifndef LB2_PATHS_CUH
+#define LB2_PATHS_CUH
+
+#include "lb2_graph.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// repeat predicates over a character string, CTA-wide.  Results: sh->flag_a (exact K-mer repeat among
+// offsets < len-K), sh->flag_b (two offsets whose (K+1)-mers differ in <= maxmm positions).
+// ---------------------------------------------------------------------------------------------------
+LB2_DEVNI void lb2_pair_scan(lb2_win &W, const char *s, int len, int K, int maxmm, bool want_almost)
+{
+	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	if (tid == 0) { sh->flag_a = 0; sh->flag_b = 0; }
+	lb2_sync();
+	const int end = len - K;               // offsets s0 in [0,end), partner i in (s0, end)
+	for (int s0 = (int)tid; s0 < end; s0 += (int)nt) {
+		if (lb2_ld32(&sh->flag_a) && (!want_almost || lb2_ld32(&sh->flag_b))) { break; }
+		for (int i = s0 + 1; i < end; ++i) {
+			int mm = 0, j = 0; bool exact = true;
+			// first K columns decide the exact repeat, K+1 columns the near repeat
+			for (; j < K; ++j) {
+				if (s[s0 + j] != s[i + j]) { ++mm; exact = false; if (mm > maxmm || !want_almost) { break; } }
+			}
+			if (j == K) {
+				if (exact) { sh->flag_a = 1; }
+				if (want_almost) {
+					if (s[s0 + K] != s[i + K]) { ++mm; }
+					if (mm <= maxmm) { sh->flag_b = 1; }
+				}
+			}
+		}
+	}
+	lb2_sync();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bfs: best = first complete path (dequeue order) with the most not-yet-flagged edges
+// ---------------------------------------------------------------------------------------------------
+LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	lb2_qent *Q = ws.queue; const uint32_t cap = W.C->queue_cap;
+	const int reflen = (int)sh->seq_len;
+	uint32_t qh = 0, qt = 0; int visit = 0; uint32_t best = LB2_NIL; int bestscore = 0;
+	lb2_qent root; root.parent = LB2_NIL; root.node = sh->source; root.len = K; root.score = 0; root.eidx = 0; root.dirflag = 2;   // dir F, flag 1
+	Q[qt++] = root;
+	while (qh < qt) {
+		++visit;
+		if (W.P->dfs_limit && visit > W.P->dfs_limit) { break; }
+		uint32_t idx = qh++; lb2_qent e = Q[idx];
+		uint32_t cur = e.node; int pdir = e.dirflag & 1; int pflag = (e.dirflag >> 1) & 1;
+		if (cur == sh->sink && pflag == 0) {
+			if (best == LB2_NIL || (int)e.score > bestscore) { best = idx; bestscore = e.score; }
+		} else if (e.len > reflen + W.P->max_indel_len) {
+		} else {
+			lb2_edge *ed = ws.d_edge + (size_t)cur * LB2_ECAP; int ne = ws.d_ne[cur];
+			for (int i = 0; i < ne; ++i) {
+				if (!lb2_is_dir(ed[i].dir, pdir)) { continue; }
+				uint32_t other = ed[i].to;
+				if (qt >= cap) { sh->err |= 1u << LB2_D_QUEUE; return LB2_NIL; }
+				lb2_qent c; c.parent = idx; c.node = other; c.eidx = (uint8_t)i;
+				c.len = e.len + (int)lb2_strlen(W, other) - K + 1;
+				int nflag = pflag * (int)ed[i].flag;
+				c.score = (uint16_t)(e.score + (ed[i].flag == 0 ? 1 : 0));
+				c.dirflag = (uint8_t)(lb2_dir_dest(ed[i].dir) | (nflag << 1));
+				Q[qt++] = c;
+			}
+		}
+	}
+	return best;
+}
+
+// materialise the chosen path: node list, string, per-base tumour/normal coverage
+LB2_DEVNI void lb2_load_path(lb2_win &W, uint32_t best)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; lb2_qent *Q = ws.queue;
+	uint32_t n = 0;
+	for (uint32_t x = best; x != LB2_NIL; x = Q[x].parent) { ++n; }
+	if (n > LB2_MAX_PNODES) { sh->err |= 1u << LB2_D_PATH; return; }
+	uint32_t k = n;
+	for (uint32_t x = best; x != LB2_NIL; x = Q[x].parent) { --k; ws.pnodes[k] = Q[x].node; ws.peidx[k] = Q[x].eidx; }
+	sh->pn = n;
+	for (uint32_t i = 1; i < n; ++i) { ws.pdirs[i - 1] = ws.d_edge[(size_t)ws.pnodes[i - 1] * LB2_ECAP + ws.peidx[i]].dir; }
+	// Path_t::str / covDistr
+	int dir = lb2_dir_start(ws.pdirs[0]);
+	uint32_t plen = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		uint32_t nd = ws.pnodes[i];
+		if (!lb2_special(W, nd)) {
+			uint32_t bl = ws.d_len[nd]; uint32_t from = plen ? (uint32_t)K - 1 : 0;
+			if (plen + (bl - from) > LB2_MAX_PATH) { sh->err |= 1u << LB2_D_PATH; return; }
+			for (uint32_t j = from; j < bl; ++j, ++plen) {
+				uint32_t src = dir ? (bl - 1 - j) : j;
+				char ch = lb2_node_char(W, nd, src);
+				ws.pathseq[plen] = dir ? lb2_comp(ch) : ch;
+				ws.pcovT[plen] = lb2_node_cov(W, nd, src, 0); ws.pcovN[plen] = lb2_node_cov(W, nd, src, 1);
+			}
+		}
+		if (i + 1 < n) { dir = lb2_dir_dest(ws.pdirs[i]); }
+	}
+	sh->plen = plen;
+}
+
+LB2_DEV uint32_t lb2_pathcontig(lb2_win &W, int pos) {   // Path_t::pathcontig
+	lb2_ws &ws = W.ws; const int K = W.sh->K; int curpos = 0;
+	for (uint32_t i = 0; i < W.sh->pn; ++i) {
+		uint32_t nd = ws.pnodes[i];
+		if (!lb2_special(W, nd)) {
+			int span = (int)ws.d_len[nd];
+			if (curpos + span >= pos) { return nd; }
+			curpos += span - K + 1;
+		}
+	}
+	return LB2_NIL;
+}
+LB2_DEV bool lb2_status_T(lb2_win &W, uint32_t nd) {     // Node_t::isStatusCnt('T') src/Node.cc:423-440
+	double prc = (double)(int)W.ws.d_stT[nd] / (double)W.ws.d_stn[nd];
+	return prc > 0.8;
+}
+LB2_DEV void lb2_flag_path(lb2_win &W, int flag) {
+	lb2_ws &ws = W.ws;
+	for (uint32_t i = 1; i < W.sh->pn; ++i) { ws.d_edge[(size_t)ws.pnodes[i - 1] * LB2_ECAP + ws.peidx[i]].flag = (uint8_t)flag; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// global_align_aff(S = trimmed reference, T = path): anti-diagonal wavefront over the CTA.
+// tb byte per cell: M.tb (0 '\\', 1 '<', 2 '^', 3 '*') | X.tb<<2 (0 '<', 1 '-', 2 other) | Y.tb<<4 (0 '^', 1 '|', 2 other)
+// ---------------------------------------------------------------------------------------------------
+LB2_DEVNI void lb2_align_fill(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const int n = (int)sh->seq_len, m = (int)sh->plen;
+	const char *S = W.ref_raw + sh->seq_off; const char *T = ws.pathseq;
+	const int stride = LB2_MAX_REF + 2;
+	int32_t *Mb = ws.dp, *Xb = ws.dp + 3 * stride, *Yb = ws.dp + 5 * stride;
+	const size_t row = (size_t)n + 1;
+	for (int d = 0; d <= n + m; ++d) {
+		int32_t *M0 = Mb + (d % 3) * stride, *M1 = Mb + ((d + 2) % 3) * stride, *M2 = Mb + ((d + 1) % 3) * stride;
+		int32_t *X0 = Xb + (d & 1) * stride, *X1 = Xb + ((d + 1) & 1) * stride;
+		int32_t *Y0 = Yb + (d & 1) * stride, *Y1 = Yb + ((d + 1) & 1) * stride;
+		int lo = d - m; if (lo < 0) { lo = 0; } int hi = d < n ? d : n;
+		for (int i = lo + (int)tid; i <= hi; i += (int)nt) {
+			int j = d - i; uint8_t tb;
+			if (i == 0 && j == 0) { M0[0] = 0; X0[0] = -8; Y0[0] = -8; tb = 3 | (2 << 2) | (2 << 4); }
+			else if (i == 0) { M0[0] = -8 - j; X0[0] = -8 - j; Y0[0] = 0; tb = 2 | (2 << 2) | (2 << 4); }
+			else if (j == 0) { M0[i] = -8 - i; Y0[i] = -8 - i; X0[i] = 0; tb = 1 | (2 << 2) | (2 << 4); }
+			else {
+				int xe = X1[i - 1] - 1, xo = M1[i - 1] - 8; int x, xt; if (xe > xo) { x = xe; xt = 1; } else { x = xo; xt = 0; }
+				int ye = Y1[i] - 1, yo = M1[i] - 8; int y, yt; if (ye > yo) { y = ye; yt = 1; } else { y = yo; yt = 0; }
+				int z = M2[i - 1] + ((S[i - 1] == T[j - 1]) ? 2 : -4); int mt = 0;
+				if (x > z) { z = x; mt = 1; }
+				if (y > z) { z = y; mt = 2; }
+				M0[i] = z; X0[i] = x; Y0[i] = y; tb = (uint8_t)(mt | (xt << 2) | (yt << 4));
+			}
+			ws.tb[(size_t)j * row + i] = tb;
+		}
+		lb2_sync();
+	}
+}
+
+LB2_DEVNI void lb2_align_trace(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	const int n = (int)sh->seq_len, m = (int)sh->plen; const size_t row = (size_t)n + 1;
+	const char *S = W.ref_raw + sh->seq_off; const char *T = ws.pathseq;
+	int i = n, j = m; bool forcex = false, forcey = false; uint32_t L = 0;
+	while (i > 0 || j > 0) {
+		uint8_t tb = ws.tb[(size_t)j * row + i]; int t = tb & 3, x = (tb >> 2) & 3, y = (tb >> 4) & 3;
+		char a, b;
+		if (t == 3) { break; }
+		else if (forcex) { if (i <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = S[i - 1]; b = '-'; if (x == 0) { forcex = false; } --i; }
+		else if (t == 1) { if (i <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = S[i - 1]; b = '-'; if (x == 1) { forcex = true; } --i; }
+		else if (forcey) { if (j <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = '-'; b = T[j - 1]; if (y == 0) { forcey = false; } --j; }
+		else if (t == 2) { if (j <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = '-'; b = T[j - 1]; if (y == 1) { forcey = true; } --j; }
+		else { a = S[i - 1]; b = T[j - 1]; --i; --j; }
+		ws.aln_ref[L] = a; ws.aln_path[L] = b; ++L;
+	}
+	for (uint32_t k = 0; k < L / 2; ++k) {
+		char c = ws.aln_ref[k]; ws.aln_ref[k] = ws.aln_ref[L - 1 - k]; ws.aln_ref[L - 1 - k] = c;
+		c = ws.aln_path[k]; ws.aln_path[k] = ws.aln_path[L - 1 - k]; ws.aln_path[L - 1 - k] = c;
+	}
+	sh->aln_len = L;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// transcripts
+// ---------------------------------------------------------------------------------------------------
+LB2_DEV void lb2_tr_add(lb2_trans &t, int list, lb2_cov c) {
+	uint16_t v[4] = { c.fwd, c.rev, c.mqf, c.mqr };
+	if (t.n[list] == 0) { for (int k = 0; k < 4; ++k) { t.mn[list][k] = v[k]; t.mn0[list][k] = v[k]; } t.sum[list][0] = 0; t.sum[list][1] = 0; }
+	t.n[list] += 1;
+	t.sum[list][0] = (uint16_t)(t.sum[list][0] + c.fwd); t.sum[list][1] = (uint16_t)(t.sum[list][1] + c.rev);
+	for (int k = 0; k < 4; ++k) {
+		if (v[k] < t.mn[list][k]) { t.mn[list][k] = v[k]; }
+		if (v[k] < t.mn0[list][k] && v[k] != 0) { t.mn0[list][k] = v[k]; }
+	}
+}
+LB2_DEV lb2_cov lb2_refcov_at(lb2_win &W, uint32_t pos, int sample) {   // Ref_t::getCovStructAt: only fwd/rev are ever set
+	lb2_cov c; c.fwd = 0; c.rev = 0; c.mqf = 0; c.mqr = 0;
+	if (pos < W.sh->L) { c.fwd = W.ws.refcov[((size_t)sample * LB2_MAX_REF + pos) * 2]; c.rev = W.ws.refcov[((size_t)sample * LB2_MAX_REF + pos) * 2 + 1]; }
+	return c;
+}
+LB2_DEV bool lb2_isACGT(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// column scan + stats + emission (lane 0).  aligned strings are in ws.aln_ref / ws.aln_path.
+LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	const char *ra = ws.aln_ref, *pa = ws.aln_path; const uint32_t alen = sh->aln_len;
+	const uint32_t plen = sh->plen;
+	lb2_trans *tr = ws.trans; uint32_t ts = 0;
+	char *poolR = ws.tstr, *poolQ = ws.tstr + (LB2_MAX_PATH + LB2_MAX_REF + 8); uint32_t usedR = 0, usedQ = 0;
+	uint32_t pos_in_ref = 0, refpos = 0, pathpos = 0; char code = '?', prev_code = '?';
+	const uint32_t trim5 = sh->trim5;
+	for (uint32_t i = 0; i < alen; ++i) {
+		prev_code = code;
+		if (ra[i] == '-') { code = '^'; pos_in_ref = refpos; ++pathpos; }
+		else if (pa[i] == '-') { code = 'v'; pos_in_ref = refpos; ++refpos; }
+		else { code = (ra[i] != pa[i]) ? 'x' : '='; pos_in_ref = refpos; ++refpos; ++pathpos; }
+		if (code == '=') { continue; }   // (the spanner lookup of '=' columns has no side effect)
+		uint32_t spanner = lb2_pathcontig(W, (int)pathpos);
+		if (spanner == LB2_NIL) { break; }
+		bool within_tumor = lb2_status_T(W, spanner);
+		if (pathpos == 0 || pathpos > plen || i == 0) { sh->err |= 1u << LB2_D_ALIGN; return; }   // reference: UB / assert
+		int P = (int)pathpos - 1;
+		lb2_cov COVn = ws.pcovN[P], COVt = ws.pcovT[P];
+		lb2_cov REFn = lb2_refcov_at(W, pos_in_ref + trim5, 1), REFt = lb2_refcov_at(W, pos_in_ref + trim5, 0);
+		uint32_t rrpos = pos_in_ref + (uint32_t)sh->ref_start + trim5;
+		int pr = (int)i - 1, pq = (int)i - 1;
+		while (pr >= 0 && !lb2_isACGT(ra[pr])) { --pr; }
+		while (pq >= 0 && !lb2_isACGT(pa[pq])) { --pq; }
+		if (pr < 0 || pq < 0) { sh->err |= 1u << LB2_D_ALIGN; return; }
+		if (ts > 0 && prev_code != '=') {
+			lb2_trans &t = tr[ts - 1];
+			if (within_tumor) { t.isSomatic = 1; }
+			if (usedR >= LB2_MAX_PATH + LB2_MAX_REF || usedQ >= LB2_MAX_PATH + LB2_MAX_REF) { sh->err |= 1u << LB2_D_TRANS; return; }
+			poolR[usedR++] = ra[i]; t.ref_len++; poolQ[usedQ++] = pa[i]; t.qry_len++;
+			t.end_pos = (uint32_t)P; t.ref_end_pos = pos_in_ref;
+			if (code == '^' && t.code == code && t.pos == rrpos) { lb2_tr_add(t, 0, COVn); lb2_tr_add(t, 1, COVt); }
+			else if (code == 'v' && t.code == code && (t.pos + t.ref_len) == rrpos) { lb2_tr_add(t, 2, REFn); lb2_tr_add(t, 3, REFt); }
+			else if (code == 'x' || t.code != code) {
+				t.code = 'c';
+				lb2_tr_add(t, 0, COVn); lb2_tr_add(t, 1, COVt); lb2_tr_add(t, 2, REFn); lb2_tr_add(t, 3, REFt);
+			}
+		} else {
+			if (ts >= LB2_MAX_TRANS) { sh->err |= 1u << LB2_D_TRANS; return; }
+			lb2_trans &t = tr[ts++];
+			t.pos = rrpos; t.ref_pos = pos_in_ref; t.start_pos = (uint32_t)P + 1; t.code = (uint8_t)code;
+			t.end_pos = (uint32_t)P; t.ref_end_pos = pos_in_ref; t.isSomatic = within_tumor ? 1 : 0;
+			t.prev_bp_ref = (uint8_t)ra[pr]; t.prev_bp_alt = (uint8_t)pa[pq];
+			t.ref_off = usedR; t.qry_off = usedQ; t.ref_len = 1; t.qry_len = 1;
+			poolR[usedR++] = ra[i]; poolQ[usedQ++] = pa[i];
+			for (int l = 0; l < 4; ++l) { t.n[l] = 0; }
+			lb2_tr_add(t, 0, COVn); lb2_tr_add(t, 1, COVt); lb2_tr_add(t, 2, REFn); lb2_tr_add(t, 3, REFt);
+		}
+	}
+	// trailing columns, stats, emission (src/Graph.cc:1036-1190)
+	for (uint32_t ti = 0; ti < ts; ++ti) {
+		lb2_trans &t = tr[ti];
+		if (t.code != 'x') {
+			for (int j = 0; j <= K; ++j) {
+				uint32_t idx1 = t.end_pos + (uint32_t)j;
+				if (idx1 < plen) {
+					uint32_t sp = lb2_pathcontig(W, (int)idx1);
+					if (sp == LB2_NIL) { break; }
+					if (lb2_status_T(W, sp)) { t.isSomatic = 1; }
+					lb2_tr_add(t, 0, ws.pcovN[idx1]); lb2_tr_add(t, 1, ws.pcovT[idx1]);
+				}
+				uint32_t idx2 = t.ref_end_pos + trim5 + (uint32_t)j;
+				lb2_tr_add(t, 2, lb2_refcov_at(W, idx2, 1)); lb2_tr_add(t, 3, lb2_refcov_at(W, idx2, 0));
+			}
+		}
+		const bool snv = (t.code == 'x');
+		uint16_t RCNF = t.mn[2][0], RCNR = t.mn[2][1], RCTF = t.mn[3][0], RCTR = t.mn[3][1];
+		uint16_t ACNF = snv ? t.mn[0][2] : t.mn[0][0], ACNR = snv ? t.mn[0][3] : t.mn[0][1];
+		if (!snv) { ACNF = t.mn0[0][0]; ACNR = t.mn0[0][1]; }
+		uint16_t ACTF = snv ? t.mn[1][2] : t.mn[1][0], ACTR = snv ? t.mn[1][3] : t.mn[1][1];
+		if (t.isSomatic) {
+			// mean = (float)sum/(float)n stored into an unsigned short (src/Transcript.hh:201-203)
+			RCNF = (uint16_t)((float)t.sum[2][0] / (float)t.n[2]); RCNR = (uint16_t)((float)t.sum[2][1] / (float)t.n[2]);
+			RCTF = (uint16_t)((float)t.sum[3][0] / (float)t.n[3]); RCTR = (uint16_t)((float)t.sum[3][1] / (float)t.n[3]);
+			ACNF = 0; ACNR = 0;
+		}
+		if (ACNF > 0 || ACNR > 0 || ACTF > 0 || ACTR > 0) {
+			const lb2_dev_out *O = W.O; uint32_t w = sh->w;
+			if (sh->n_var >= W.C->max_var) { sh->err |= 1u << LB2_D_VARIANTS; return; }
+			uint32_t need = t.ref_len + t.qry_len;
+			char *spool = O->strings + (size_t)w * W.C->str_bytes;
+			if (sh->str_used + need + 64 > W.C->str_bytes) { sh->err |= 1u << LB2_D_STRINGS; return; }
+			lb2_variant v;
+			v.window = w; v.pos = (int32_t)t.pos - 1; v.str_off = sh->str_used;
+			v.ref_len = (uint16_t)t.ref_len; v.alt_len = (uint16_t)t.qry_len;
+			char *dst = spool + sh->str_used;
+			for (uint32_t k = 0; k < t.ref_len; ++k) { dst[k] = poolR[t.ref_off + k]; }
+			for (uint32_t k = 0; k < t.qry_len; ++k) { dst[t.ref_len + k] = poolQ[t.qry_off + k]; }
+			int LEN = 0; uint32_t ml = 0; bool movf = false;
+			const char *ps = ws.pathseq;
+			bool ans = lb2_find_tandems([&](uint32_t q) -> char { return ps[q]; }, plen, W.P, (int)t.start_pos, LEN, dst + need, ml, 64, movf);
+			if (movf) { sh->err |= 1u << LB2_D_MOTIF; return; }
+			v.motif_len = (uint16_t)(ans ? ml : 0); v.str_len = (uint16_t)(ans ? LEN : 0);
+			sh->str_used += need + v.motif_len;
+			v.rcn_fwd = RCNF; v.rcn_rev = RCNR; v.rct_fwd = RCTF; v.rct_rev = RCTR;
+			v.acn_fwd = ACNF; v.acn_rev = ACNR; v.act_fwd = ACTF; v.act_rev = ACTR;
+			v.code = t.code; v.prev_bp_ref = t.prev_bp_ref; v.prev_bp_alt = t.prev_bp_alt; v.kmer = (uint8_t)K;
+			O->variants[(size_t)w * W.C->max_var + sh->n_var] = v;
+			sh->n_var += 1;
+		}
+	}
+}
+
+// processPath for the path loaded in ws.pathseq (all lanes: the alignment is CTA-wide)
+LB2_DEVNI void lb2_process_path(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	if (lb2_tid() == 0) {
+		// HammingDistance cut-off (src/Graph.cc:818-826)
+		int hd = -1;
+		if (sh->seq_len == sh->plen) {
+			hd = 0; const char *S = W.ref_raw + sh->seq_off;
+			for (uint32_t i = 0; i < sh->plen; ++i) { if (S[i] != ws.pathseq[i]) { ++hd; } }
+		}
+		sh->need_align = (hd == -1 || hd > 5) ? 1u : 0u;
+		if (!sh->need_align) {
+			const char *S = W.ref_raw + sh->seq_off;
+			for (uint32_t i = 0; i < sh->plen; ++i) { ws.aln_ref[i] = S[i]; ws.aln_path[i] = ws.pathseq[i]; }
+			sh->aln_len = sh->plen;
+		}
+	}
+	lb2_sync();
+	if (sh->need_align) {
+		lb2_align_fill(W);
+		if (lb2_tid() == 0) { lb2_align_trace(W); }
+		lb2_sync();
+	}
+	if (lb2_tid() == 0 && !sh->err) { lb2_scan_alignment(W); }
+	lb2_sync();
+}
+
+#endif

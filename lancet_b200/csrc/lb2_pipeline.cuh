@@ -1,0 +1,192 @@
+// lb2_pipeline.cuh -- one window through the whole micro-assembly: the k sweep of
+// Microassembler::processGraph (reference src/Microassembler.cc:73-249) on one CTA.
+#ifndef LB2_PIPELINE_CUH
+#define LB2_PIPELINE_CUH
+
+#include "lb2_paths.cuh"
+
+// byte layout of one CTA's workspace slab; the same function runs on host (sizing) and device (pointers)
+#ifdef __CUDACC__
+#define LB2_HD __host__ __device__ inline
+#else
+#define LB2_HD static inline
+#endif
+
+LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
+{
+	size_t off = 0;
+#define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
+	const size_t HC = c.hash_cap, MN = (size_t)c.max_nodes + LB2_MAX_SPECIAL, MR = (size_t)c.max_reads + 2;
+	size_t n2 = 1; while (n2 < c.max_nodes) { n2 <<= 1; }
+	LB2_TAKE(slots, uint64_t, HC); LB2_TAKE(occ, uint32_t, HC); LB2_TAKE(cnt, uint32_t, HC * 4); LB2_TAKE(sflags, uint32_t, HC);
+	LB2_TAKE(ekey, uint32_t, HC * LB2_ECAP); LB2_TAKE(eseq, uint32_t, HC * LB2_ECAP);
+	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(slot2id, uint32_t, HC); LB2_TAKE(sortk, uint64_t, n2);
+	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
+	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR);
+	LB2_TAKE(d_rep, uint32_t, MN); LB2_TAKE(d_hash, uint64_t, MN); LB2_TAKE(d_cov, float, MN * 4); LB2_TAKE(d_cnt, uint32_t, MN * 4);
+	LB2_TAKE(d_stn, uint32_t, MN); LB2_TAKE(d_stT, uint32_t, MN); LB2_TAKE(d_mincov, int32_t, MN); LB2_TAKE(d_mincovqv, int32_t, MN);
+	LB2_TAKE(d_ne, uint8_t, MN); LB2_TAKE(d_edge, lb2_edge, MN * LB2_ECAP); LB2_TAKE(d_flags, uint8_t, MN);
+	LB2_TAKE(d_comp, int32_t, MN); LB2_TAKE(d_color, uint8_t, MN); LB2_TAKE(d_lnext, uint32_t, MN);
+	LB2_TAKE(d_str, uint32_t, MN); LB2_TAKE(d_len, uint32_t, MN); LB2_TAKE(d_cd, uint32_t, MN);
+	LB2_TAKE(deficit, uint16_t, c.deficit_bytes / 2); LB2_TAKE(buckets, uint32_t, c.bucket_cap);
+	LB2_TAKE(refnode, uint32_t, LB2_MAX_REF); LB2_TAKE(refcov, uint16_t, 2 * LB2_MAX_REF * 2);
+	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(queue, lb2_qent, c.queue_cap);
+	LB2_TAKE(stack, uint32_t, MN * 2 + 16); LB2_TAKE(chain, uint32_t, MN + 16);
+	LB2_TAKE(pathseq, char, LB2_MAX_PATH + 16); LB2_TAKE(pcovN, lb2_cov, LB2_MAX_PATH + 16); LB2_TAKE(pcovT, lb2_cov, LB2_MAX_PATH + 16);
+	LB2_TAKE(pnodes, uint32_t, LB2_MAX_PNODES); LB2_TAKE(pdirs, uint8_t, LB2_MAX_PNODES); LB2_TAKE(peidx, uint8_t, LB2_MAX_PNODES);
+	LB2_TAKE(aln_ref, char, LB2_MAX_PATH + LB2_MAX_REF + 16); LB2_TAKE(aln_path, char, LB2_MAX_PATH + LB2_MAX_REF + 16);
+	LB2_TAKE(dp, int32_t, 7 * (LB2_MAX_REF + 2)); LB2_TAKE(tb, uint8_t, (size_t)(LB2_MAX_REF + 1) * (LB2_MAX_PATH + 1));
+	LB2_TAKE(trans, lb2_trans, LB2_MAX_TRANS); LB2_TAKE(tstr, char, 2 * (LB2_MAX_PATH + LB2_MAX_REF + 8));
+#undef LB2_TAKE
+	return (off + 255) & ~(size_t)255;
+}
+
+// shared-memory layout: lb2_sh | ref_raw[LB2_MAX_REF] | bits[max_bp/16 + 4] | lowq[max_bp/32 + 4]
+LB2_HD size_t lb2_smem_bytes(uint32_t max_bp) {
+	return ((sizeof(lb2_sh) + 15) & ~(size_t)15) + LB2_MAX_REF + ((size_t)max_bp / 16 + 4) * 4 + ((size_t)max_bp / 32 + 4) * 4;
+}
+
+LB2_DEV uint32_t lb2_first_err(uint32_t e) { for (uint32_t b = 0; b < 32; ++b) { if (e & (1u << b)) { return b; } } return 0; }
+
+// reference k-mer coverage tracks (Ref_t::indexMers/updateCoverage/computeCoverage, src/Ref.cc:40-64,128-149,173-250)
+LB2_DEVNI void lb2_ref_coverage(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t L = sh->L;
+	for (uint32_t i = tid; i < 2 * LB2_MAX_REF * 2; i += nt) { ws.refcov[i] = 0; }
+	// mers indexed from the (possibly already trimmed) ref->seq: offsets i with i + K < seq.length()
+	for (uint32_t i = tid; i + K < sh->seq_len; i += nt) {
+		uint32_t nd = ws.refnode[sh->seq_off + i];
+		if (nd != LB2_NIL) { ws.d_color[nd] = 9; }
+	}
+	lb2_sync();
+	for (uint32_t i = tid; i + K < L; i += nt) {
+		uint32_t nd = ws.refnode[i];
+		uint16_t v[4] = { 0, 0, 0, 0 };
+		if (nd != LB2_NIL && ws.d_color[nd] == 9) { for (int c = 0; c < 4; ++c) { v[c] = (uint16_t)ws.d_cnt[nd * 4 + c]; } }
+		for (int s = 0; s < 2; ++s) {
+			uint16_t *rc = ws.refcov + (size_t)s * LB2_MAX_REF * 2;
+			if (i == 0) { for (int j = 0; j < K; ++j) { rc[j * 2] = v[s * 2]; rc[j * 2 + 1] = v[s * 2 + 1]; } }
+			else { rc[(i + K - 1) * 2] = v[s * 2]; rc[(i + K - 1) * 2 + 1] = v[s * 2 + 1]; }
+		}
+	}
+	lb2_sync();
+}
+
+LB2_DEVNI void lb2_clear_table_full(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; const unsigned tid = lb2_tid(), nt = lb2_nthr(); const uint32_t HC = W.C->hash_cap;
+	for (uint32_t s = tid; s < HC; s += nt) {
+		ws.slots[s] = 0; ws.occ[s] = 0; ws.sflags[s] = 0;
+		for (int c = 0; c < 4; ++c) { ws.cnt[s * 4 + c] = 0; }
+		for (int e = 0; e < LB2_ECAP; ++e) { ws.ekey[(size_t)s * LB2_ECAP + e] = 0; ws.eseq[(size_t)s * LB2_ECAP + e] = 0; }
+	}
+	lb2_sync();
+}
+
+LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
+{
+	lb2_sh *sh = W.sh; const lb2_params *P = W.P; const unsigned tid = lb2_tid();
+	lb2_stage_window(W, w);
+	if (sh->status == LB2_WIN_OK) {
+		if (P->max_unit_len > 16 || P->max_k > (int32_t)W.C->max_k) { if (tid == 0) { sh->status = LB2_WIN_UNSUPPORTED; sh->detail = LB2_D_KMAX; } lb2_sync(); }
+	}
+	if (sh->status == LB2_WIN_OK) {
+		// window pre-skip: isRepeat(rawseq, maxK)  (src/Microassembler.cc:800)
+		lb2_pair_scan(W, W.ref_raw, (int)sh->L, P->max_k, 0, false);
+		if (sh->flag_a) { if (tid == 0) { sh->status = LB2_WIN_SKIP_REPEAT; } lb2_sync(); }
+	}
+	if (sh->status == LB2_WIN_OK) {
+		bool ref_passed = false;
+		for (int k = P->min_k; k <= P->max_k; k += 2) {
+			if (!ref_passed) {
+				// isRepeat / isAlmostRepeat on the window reference; both are monotone in k
+				lb2_pair_scan(W, W.ref_raw, (int)sh->L, k, P->max_mismatch, true);
+				if (sh->flag_a || sh->flag_b) { continue; }
+				ref_passed = true;
+			}
+			lb2_build_graph(W, k);
+			if (tid == 0) { sh->n_k_tried += 1; sh->final_k = (uint32_t)k; }
+			lb2_sync();
+			if (sh->err) { lb2_clear_table_full(W); break; }
+			lb2_ref_coverage(W);
+			if (tid == 0) {
+				sh->arena_used = 8; sh->flag_c = 0;
+				lb2_order_nodes(W);
+				if (!sh->err) { lb2_remove_lowcov(W, 0); sh->numcomp = lb2_mark_components(W); }
+			}
+			lb2_sync();
+			if (sh->err) { break; }
+			bool retry = false;
+			const int numcomp = sh->numcomp;
+			for (int c = 1; c <= numcomp; ++c) {
+				if (tid == 0) {
+					lb2_mark_ref_ends(W, c);
+					bool cyc = !sh->err && lb2_has_cycle(W);
+					if (!cyc && !sh->err) {
+						lb2_compress(W, c);
+						if (!sh->err) { lb2_remove_lowcov(W, c); lb2_compress(W, c); }
+						if (!sh->err) { lb2_remove_tips(W, c); }
+						if (!sh->err) { lb2_remove_short_links(W, c); }
+						if (!sh->err) { cyc = lb2_has_cycle(W); }
+					}
+					sh->flag_c = cyc ? 1u : 0u;
+				}
+				lb2_sync();
+				if (sh->err) { break; }
+				if (sh->flag_c) { retry = true; break; }
+				if (sh->source == LB2_NIL || sh->sink == LB2_NIL) { continue; }
+				// ---- findRepeatsInGraphPaths: enumerate the covering paths, near-repeat test on each
+				bool rpt = false; uint32_t nflag = 0;
+				while (true) {
+					if (tid == 0) {
+						uint32_t best = lb2_bfs(W);
+						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
+						if (sh->path_found) { lb2_load_path(W, best); }
+					}
+					lb2_sync();
+					if (sh->err || !sh->path_found) { break; }
+					lb2_pair_scan(W, W.ws.pathseq, (int)sh->plen, k, P->max_mismatch, true);
+					if (sh->flag_b) { rpt = true; break; }
+					if (tid == 0) { lb2_flag_path(W, 1); }
+					++nflag;
+					lb2_sync();
+				}
+				if (sh->err) { break; }
+				if (tid == 0) {   // clear the edge flags again (all flags of this component were 0 before)
+					for (uint32_t p = sh->lhead; p != LB2_NIL; p = W.ws.d_lnext[p]) {
+						if (W.ws.d_comp[p] == c) { for (int e = 0; e < (int)W.ws.d_ne[p]; ++e) { W.ws.d_edge[(size_t)p * LB2_ECAP + e].flag = 0; } }
+					}
+				}
+				lb2_sync();
+				if (rpt) { retry = true; break; }
+				// ---- eka: repeat { best path; processPath; flag its edges }
+				while (true) {
+					if (tid == 0) {
+						uint32_t best = lb2_bfs(W);
+						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
+						if (sh->path_found) { lb2_load_path(W, best); }
+					}
+					lb2_sync();
+					if (sh->err || !sh->path_found) { break; }
+					lb2_process_path(W);
+					if (sh->err) { break; }
+					if (tid == 0) { lb2_flag_path(W, 1); }
+					lb2_sync();
+				}
+				if (sh->err) { break; }
+			}
+			if (sh->err) { break; }
+			if (!retry) { break; }
+		}
+		if (sh->err) { if (tid == 0) { sh->status = LB2_WIN_OVERFLOW; sh->detail = lb2_first_err(sh->err); } lb2_sync(); }
+	}
+	if (tid == 0) {
+		lb2_window_info wi; wi.status = (uint8_t)sh->status; wi.final_k = (uint8_t)sh->final_k; wi.n_k_tried = (uint16_t)sh->n_k_tried;
+		wi.n_variants = (sh->status == LB2_WIN_OK) ? sh->n_var : 0; wi.n_nodes = sh->last_nodes; wi.detail = sh->detail;
+		W.O->info[w] = wi; W.O->str_used[w] = sh->str_used;
+	}
+	lb2_sync();
+}
+
+#endif

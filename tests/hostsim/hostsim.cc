@@ -1,0 +1,78 @@
+// DEBUG-ONLY single-thread simulation of the device pipeline (LB2_HOSTSIM): the same
+// lancet_b200/csrc/*.cuh sources compiled by g++ with a ONE-thread "CTA".  It exists because the
+// development container has no GPU; it is not shipped, not imported by the package, is not the
+// oracle, and no test asserts product behaviour through it (tests/ compare the CUDA path with
+// oracle/_ref).  Usage: hostsim batch.lb2b [--min-k a --max-k b] [--out f.tsv] [--first i --count n]
+#define LB2_HOSTSIM 1
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../lancet_b200/csrc/lb2_pipeline.cuh"
+
+template <class T> static void rd(FILE *f, std::vector<T> &v, size_t n) { v.resize(n); if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
+
+int main(int argc, char **argv)
+{
+	const char *fn = NULL, *out = NULL; int first = 0, count = -1;
+	lb2_params P; P.min_k = 11; P.max_k = 101; P.min_qual_trim = 43; P.min_qual_call = 50; P.cov_threshold = 5;
+	P.low_cov_threshold = 1; P.max_tip_len = 11; P.dfs_limit = 1000000; P.max_indel_len = 500; P.max_mismatch = 2;
+	P.max_unit_len = 4; P.min_report_units = 3; P.min_report_len = 7; P.dist_from_str = 1; P.min_cov_ratio = 0.01;
+	for (int i = 1; i < argc; ++i) {
+		std::string a = argv[i];
+		if (a == "--min-k") P.min_k = atoi(argv[++i]); else if (a == "--max-k") P.max_k = atoi(argv[++i]);
+		else if (a == "--out") out = argv[++i]; else if (a == "--first") first = atoi(argv[++i]);
+		else if (a == "--count") count = atoi(argv[++i]); else if (a == "--dfs-limit") P.dfs_limit = atoi(argv[++i]);
+		else fn = argv[i];
+	}
+	FILE *f = fopen(fn, "rb"); if (!f) { perror(fn); return 2; }
+	char magic[4]; uint32_t ver, W, R, nwr; uint64_t nref, nbase;
+	if (fread(magic, 1, 4, f) != 4 || fread(&ver, 4, 1, f) != 1 || fread(&W, 4, 1, f) != 1 || fread(&R, 4, 1, f) != 1 || fread(&nwr, 4, 1, f) != 1 ||
+	    fread(&nref, 8, 1, f) != 1 || fread(&nbase, 8, 1, f) != 1) return 2;
+	std::vector<uint32_t> ref_off, chr_id, wr_off, wr_idx, name_rank; std::vector<int32_t> ref_start; std::vector<uint64_t> base_off;
+	std::vector<uint8_t> flags; std::vector<char> ref_seq, seq, qual;
+	rd(f, ref_off, W + 1); rd(f, ref_start, W); rd(f, chr_id, W); rd(f, wr_off, W + 1); rd(f, wr_idx, nwr); rd(f, base_off, R + 1);
+	rd(f, flags, R); rd(f, name_rank, R); rd(f, ref_seq, nref); rd(f, seq, nbase); rd(f, qual, nbase); fclose(f);
+
+	lb2_cfg C; memset(&C, 0, sizeof C);
+	C.hash_cap = 16384; C.max_nodes = 8000; C.max_reads = 8192; C.max_bp = 1 << 20; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
+	C.queue_cap = 1 << 18; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
+	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
+	B.base_off = base_off.data(); B.flags = flags.data(); B.name_rank = name_rank.data(); B.ref_seq = ref_seq.data(); B.seq = seq.data(); B.qual = qual.data();
+	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
+	lb2_dev_out O; O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
+	size_t wsb = lb2_ws_layout(C, NULL, NULL);
+	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp), 0);
+	lb2_win Wn; Wn.P = &P; Wn.C = &C; Wn.B = &B; Wn.O = &O;
+	lb2_ws_layout(C, slab.data(), &Wn.ws);
+	Wn.sh = (lb2_sh *)smem.data();
+	Wn.ref_raw = (char *)smem.data() + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
+	Wn.bits = (uint32_t *)(Wn.ref_raw + LB2_MAX_REF);
+	Wn.lowq = Wn.bits + (C.max_bp / 16 + 4);
+	int w1 = count < 0 ? (int)W : std::min((int)W, first + count);
+	FILE *fo = out ? fopen(out, "w") : stdout;
+	for (int w = first; w < w1; ++w) {
+		lb2_process_window(Wn, (uint32_t)w);
+		const lb2_window_info &wi = info[w];
+		if (wi.status != LB2_WIN_OK) { fprintf(stderr, "window %d status %d detail %u\n", w, wi.status, wi.detail); }
+		for (uint32_t v = 0; v < wi.n_variants; ++v) {
+			const lb2_variant &x = vars[(size_t)w * C.max_var + v]; const char *sp = strs.data() + (size_t)w * C.str_bytes + x.str_off;
+			std::string ref(sp, x.ref_len), alt(sp + x.ref_len, x.alt_len), motif(sp + x.ref_len + x.alt_len, x.motif_len);
+			// Variant_t constructor normalisation (reference src/Variant.hh:133-153) -- test-side only
+			int pos = x.pos; char type = '?'; int len = 0;
+			if (x.code == '^') { type = 'I'; ref = ""; len = (int)alt.size(); }
+			if (x.code == 'v') { type = 'D'; alt = ""; len = (int)ref.size(); }
+			if (x.code == 'x') { type = 'S'; pos++; }
+			if (x.code == 'c') { type = 'C'; ref.erase(std::remove(ref.begin(), ref.end(), '-'), ref.end()); alt.erase(std::remove(alt.begin(), alt.end(), '-'), alt.end());
+				int rl = (int)ref.size(), al = (int)alt.size(); len = (rl == al) ? al : (rl > al ? rl - al : al - rl); }
+			if (type != 'S') { ref = std::string(1, (char)x.prev_bp_alt) + ref; alt = std::string(1, (char)x.prev_bp_alt) + alt; } else { len = 1; }
+			std::string str = x.str_len ? std::to_string(x.str_len) + motif : std::string(".");
+			fprintf(fo, "%d\t%d\t%c\t%d\t%s\t%s\t%d\t%s\t%u,%u,%u,%u,%u,%u,%u,%u\t%c\t%c\n", w, pos, type, len, ref.c_str(), alt.c_str(), x.kmer, str.c_str(),
+				x.rcn_fwd, x.rcn_rev, x.rct_fwd, x.rct_rev, x.acn_fwd, x.acn_rev, x.act_fwd, x.act_rev, x.prev_bp_ref, x.prev_bp_alt);
+		}
+	}
+	if (fo != stdout) fclose(fo);
+	return 0;
+}
