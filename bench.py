@@ -1,0 +1,223 @@
+#!/usr/bin/env python
+"""bench.py -- micro-assembly windows/sec of the Lancet hot path on B200 (BASELINE.json metric).
+
+A "step" = one pass of the per-window micro-assembly pipeline over one batch of synthetic windows:
+the configuration BASELINE.json quotes the metric on (configs[1]: a 1 Mb region, synthetic 60x/60x
+tumour/normal, 100 bp reads, default k-sweep 11..101) -> ~10 000 windows of 600 bp, ~1.2 M reads.
+
+  value  : windows/s, whole job, batch already resident in HBM when the timed region starts
+  e2e    : windows/s through the C ABI call lb2_process() with HOST (pinned) buffers: H2D + kernels + D2H
+  roofline / cpu_baseline : see DESIGN.md
+  --impl reference : the reference's own CPU implementation (oracle/_ref/ref_windows = unmodified
+                     nygenome/lancet sources behind the same window-batch boundary), all host threads
+
+N > 1: one process per GPU (torchrun), windows are independent => no data-path collective; every rank
+assembles its own 1 Mb region (weak scaling); timing = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+
+REGION = int(os.environ.get("LB2_BENCH_REGION", 1_000_000))
+METRIC = "microassembly windows/sec (whole box)"
+WORKLOAD = f"configs[1]: chr22 {REGION // 1000} kb region, synthetic 60x/60x T/N, 100 bp reads, err 0.1%, default k-sweep 11..101, 600 bp windows / 100 bp stride"
+
+
+def make_workload(rank: int):
+    from lancet_b200.synth import make_batch
+    return make_batch(seed=1000 + rank, region_len=REGION, region_start=1_000_001, var_every=5000)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.rows = []; self._stop_ev = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_ev.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def summary(self):
+        self._stop_ev.set(); self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def reference_arm(args, rank):
+    """CPU reference: unmodified lancet sources (oracle/_ref/ref_windows), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import run_ref
+    cores = os.cpu_count() or 1
+    if not run_ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_windows not built (needs /root/reference at build time)"}))
+        return
+    batch = make_workload(0)
+    path = "/tmp/lb2_bench_ref.lb2b"
+    # bounded sample: the first `count` windows of the workload (~1 s per step per 16 windows/thread)
+    count = min(batch.n_windows, int(os.environ.get("LB2_REF_SAMPLE", 24 * cores)))
+    batch.subset(np.arange(count)).save(path)
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, t = run_ref.run(path=path, threads=cores, want_records=False)
+        if i >= args.warmup:
+            times.append(t["best_s"])
+    sec = sum(times) / len(times)
+    val = count / sec
+    sample = f"first {count} of {batch.n_windows} windows of the workload, {cores} threads, per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the lancet_b200 hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from lancet_b200.api import Context
+
+    batch = make_workload(rank)
+    # pinned host staging so that the e2e leg measures PCIe, not pageable-memory bounce buffers
+    for name in ("ref_off", "ref_start", "chr_id", "wr_off", "wr_idx", "base_off", "flags", "name_rank", "ref_seq", "seq", "qual"):
+        a = getattr(batch, name)
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        v = t.numpy()[:a.nbytes].view(a.dtype); v[...] = a
+        setattr(batch, name, v); batch.__dict__.setdefault("_pins", []).append(t)
+    ctx = Context(device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-in-HBM leg -------------------------------------------------------------------
+    ctx.upload(batch)
+    for _ in range(args.warmup):
+        ctx.run(); ctx.wait()
+    res = ctx.download()
+    n_var = len(res.variants); st = res.windows["status"]
+    n_ok = int((st == 0).sum()); n_fail = int((st >= 3).sum())
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.run(); ctx.wait(); dev_ms += ctx.last_kernel_ms       # CUDA events on the launching stream
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.kernel_launches - launches0
+    ms_step = dev_ms / args.steps
+    # ---- end-to-end leg: host buffers -> H2D -> kernels -> D2H, through lb2_process ---------------
+    for _ in range(1):
+        ctx.process(batch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ctx.process(batch)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    h2d, d2h = ctx.last_h2d_bytes, ctx.last_d2h_bytes
+    clocks = sampler.summary()
+
+    tms = torch.tensor([ms_step, e2e_s * 1e3, wall * 1e3 / args.steps], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([batch.n_windows, n_ok, n_fail, n_var], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, e2e_ms, wall_ms = [float(x) for x in tms.tolist()]
+    total_windows, n_ok_all, n_fail_all, n_var_all = [int(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peak, how = peak_hbm()
+        alg_bytes = batch.algorithmic_bytes(n_var)                  # this rank's launch (B_win summed)
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        out = {
+            "metric": METRIC, "value": total_windows / (ms_step * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "windows_per_gpu": batch.n_windows, "reads_per_gpu": batch.n_reads,
+                       "windows_ok": n_ok_all, "windows_failed": n_fail_all, "variant_records": n_var_all,
+                       "l2": f"inputs ({(batch.seq.nbytes * 2) >> 20} MiB per step) larger than L2", "parallelism": f"window-sharded x{world}, no collective",
+                       "resident_ctas": ctx.resident_ctas, "smem_per_cta": ctx.smem_per_cta, "wall_ms_per_step": wall_ms},
+            "e2e": {"value": total_windows / (e2e_ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "kernel": "lb2_window_kernel"},
+        }
+        if world == 1 and os.environ.get("LB2_SKIP_CPU_BASELINE") is None:
+            import run_ref
+            cores = os.cpu_count() or 1
+            if run_ref.available():
+                count = min(batch.n_windows, int(os.environ.get("LB2_REF_SAMPLE", 24 * cores)))
+                path = "/tmp/lb2_bench_cpu.lb2b"
+                batch.subset(np.arange(count)).save(path)
+                _, t = run_ref.run(path=path, threads=cores, want_records=False)
+                out["cpu_baseline"] = {"value": count / t["best_s"], "unit": "windows/s", "cores": cores, "kind": "reference",
+                                       "sample": f"first {count} of {batch.n_windows} windows, {cores} threads, {t['best_s']:.1f} s"}
+            else:
+                out["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,329 @@
+// lb2_cuda.cu -- the sm_100a kernels and the extern "C" boundary declared in include/lancet_b200.h.
+//
+// One persistent CTA per resident slot; each CTA pulls window indices from a global counter and runs
+// the whole micro-assembly of that window (lb2_process_window) out of its own workspace slab, with the
+// window's reads staged 2-bit-packed in shared memory.  No CPU fallback exists in this file: every
+// entry point fails with LB2_ERR_CUDA when there is no usable device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+
+#include "lb2_pipeline.cuh"
+
+struct lb2_launch {
+	lb2_params P; lb2_cfg C; lb2_dev_batch B; lb2_dev_out O;
+	uint8_t *ws_base; size_t ws_stride; uint32_t *counter;
+	// compaction outputs
+	uint32_t *var_off; uint32_t *str_off; uint32_t *totals; lb2_variant *cvars; char *cstr;
+};
+
+__global__ void __launch_bounds__(LB2_THREADS)
+lb2_window_kernel(const lb2_launch *Lp)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	__shared__ uint32_t s_next;
+	lb2_win W;
+	W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O;
+	lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws);
+	W.sh = (lb2_sh *)smem;
+	W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
+	W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);
+	W.lowq = W.bits + (Lp->C.max_bp / 16 + 4);
+	const uint32_t nwin = Lp->B.n_windows;
+	while (true) {
+		if (threadIdx.x == 0) { s_next = atomicAdd(Lp->counter, 1u); }
+		__syncthreads();
+		uint32_t w = s_next;
+		__syncthreads();
+		if (w >= nwin) { break; }
+		lb2_process_window(W, w);
+	}
+}
+
+// exclusive scans of per-window variant counts and string bytes (one block)
+__global__ void lb2_scan_kernel(const lb2_launch *Lp)
+{
+	__shared__ uint32_t pv[1024], ps[1024];
+	const uint32_t n = Lp->B.n_windows, t = threadIdx.x, nt = blockDim.x;
+	const uint32_t chunk = (n + nt - 1) / nt, lo = t * chunk, hi = min(n, lo + chunk);
+	uint32_t sv = 0, ss = 0;
+	for (uint32_t w = lo; w < hi; ++w) { sv += Lp->O.info[w].n_variants; ss += (Lp->O.info[w].n_variants ? Lp->O.str_used[w] : 0); }
+	pv[t] = sv; ps[t] = ss; __syncthreads();
+	if (t == 0) {
+		uint32_t av = 0, as = 0;
+		for (uint32_t i = 0; i < nt; ++i) { uint32_t v = pv[i], s = ps[i]; pv[i] = av; ps[i] = as; av += v; as += s; }
+		Lp->totals[0] = av; Lp->totals[1] = as;
+	}
+	__syncthreads();
+	uint32_t av = pv[t], as = ps[t];
+	for (uint32_t w = lo; w < hi; ++w) {
+		Lp->var_off[w] = av; Lp->str_off[w] = as;
+		uint32_t nv = Lp->O.info[w].n_variants; av += nv; as += (nv ? Lp->O.str_used[w] : 0);
+	}
+}
+
+// gather the per-window slabs into dense arrays (one block per window)
+__global__ void lb2_gather_kernel(const lb2_launch *Lp)
+{
+	const uint32_t w = blockIdx.x; const uint32_t nv = Lp->O.info[w].n_variants;
+	if (!nv) { return; }
+	const uint32_t vo = Lp->var_off[w], so = Lp->str_off[w], sb = Lp->O.str_used[w];
+	for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+		lb2_variant v = Lp->O.variants[(size_t)w * Lp->C.max_var + i]; v.str_off += so; Lp->cvars[vo + i] = v;
+	}
+	const char *src = Lp->O.strings + (size_t)w * Lp->C.str_bytes;
+	for (uint32_t i = threadIdx.x; i < sb; i += blockDim.x) { Lp->cstr[so + i] = src[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct lb2_ctx {
+	int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
+	lb2_params P; lb2_cfg C;
+	int sm_count;
+	std::string err;
+	// device buffers of the resident batch
+	struct Buf { void *p = nullptr; size_t cap = 0; };
+	Buf d_ref_off, d_ref_start, d_wr_off, d_wr_idx, d_base_off, d_flags, d_name_rank, d_ref_seq, d_seq, d_qual;
+	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws;
+	uint32_t *d_counter = nullptr, *d_totals = nullptr; lb2_launch *d_launch = nullptr;
+	lb2_launch L;
+	uint32_t n_windows = 0; bool resident = false, ran = false;
+	size_t ws_stride = 0; uint32_t ws_slots = 0;
+	uint64_t launches = 0;
+	float kernel_ms = 0;
+	// host result
+	std::vector<lb2_window_info> h_info; std::vector<lb2_variant> h_vars; std::vector<char> h_str;
+	uint64_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+#define LB2_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return LB2_ERR_CUDA; } } while (0)
+
+static int lb2_reserve(lb2_ctx *ctx, lb2_ctx::Buf &b, size_t bytes, bool zero = false)
+{
+	if (bytes <= b.cap && b.p) { return LB2_OK; }
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	size_t cap = bytes + bytes / 4 + 256;
+	LB2_CK(cudaMalloc(&b.p, cap));
+	b.cap = cap;
+	if (zero) { LB2_CK(cudaMemsetAsync(b.p, 0, cap, ctx->stream)); }
+	return LB2_OK;
+}
+
+extern "C" void lb2_default_params(lb2_params *p)
+{
+	// reference src/Lancet.hh:33-79
+	p->min_k = 11; p->max_k = 101; p->min_qual_trim = 10 + 33; p->min_qual_call = 17 + 33; p->cov_threshold = 5;
+	p->low_cov_threshold = 1; p->max_tip_len = 11; p->dfs_limit = 1000000; p->max_indel_len = 500; p->max_mismatch = 2;
+	p->max_unit_len = 4; p->min_report_units = 3; p->min_report_len = 7; p->dist_from_str = 1; p->min_cov_ratio = 0.01;
+}
+
+extern "C" const char *lb2_strerror(const lb2_ctx *ctx, int code)
+{
+	switch (code) {
+		case LB2_OK: return "ok";
+		case LB2_ERR_CUDA: return (ctx && !ctx->err.empty()) ? ctx->err.c_str() : "CUDA error / no sm_100 device (this library has no CPU fallback)";
+		case LB2_ERR_ARG: return "invalid argument";
+		case LB2_ERR_NOMEM: return "out of memory";
+		case LB2_ERR_STATE: return "call sequence error (upload -> run -> download)";
+	}
+	return "unknown error";
+}
+
+static uint32_t env_u32(const char *name, uint32_t dflt) { const char *s = getenv(name); return s ? (uint32_t)strtoul(s, nullptr, 10) : dflt; }
+
+extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
+{
+	if (!out || !params) { return LB2_ERR_ARG; }
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { return LB2_ERR_CUDA; }
+	lb2_ctx *ctx = new lb2_ctx();
+	ctx->device = device; ctx->P = *params;
+	cudaDeviceProp prop;
+	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
+	if (prop.major < 10) { delete ctx; return LB2_ERR_CUDA; }
+	ctx->sm_count = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
+	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
+	C.hash_cap = env_u32("LB2_HASH_CAP", 8192); C.max_nodes = env_u32("LB2_MAX_NODES", C.hash_cap / 2 - 64);
+	C.max_reads = 4096; C.max_bp = 0;
+	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
+	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
+	C.bucket_cap = 10273; C.max_k = 127;
+	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
+		delete ctx; return LB2_ERR_CUDA;
+	}
+	*out = ctx;
+	return LB2_OK;
+}
+
+extern "C" void lb2_destroy(lb2_ctx *ctx)
+{
+	if (!ctx) { return; }
+	cudaSetDevice(ctx->device);
+	lb2_ctx::Buf *bufs[] = { &ctx->d_ref_off, &ctx->d_ref_start, &ctx->d_wr_off, &ctx->d_wr_idx, &ctx->d_base_off, &ctx->d_flags, &ctx->d_name_rank,
+		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used, &ctx->d_var_off, &ctx->d_str_off,
+		&ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws };
+	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
+	cudaFree(ctx->d_counter); cudaFree(ctx->d_totals); cudaFree(ctx->d_launch);
+	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" uint64_t lb2_kernel_launches(const lb2_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
+{
+	if (!ctx || !b) { return LB2_ERR_ARG; }
+	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
+	ctx->resident = false; ctx->ran = false;
+	const uint32_t W = b->n_windows, R = b->n_reads;
+	// staging bound: every read rounded up to 32 bases + reference + padding (untrimmed lengths)
+	uint32_t max_bp = 0, max_reads = 0;
+	for (uint32_t w = 0; w < W; ++w) {
+		uint64_t bp = 0;
+		for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
+			uint32_t r = b->wr_idx[x]; if (r >= R) { return LB2_ERR_ARG; }
+			bp += ((b->base_off[r + 1] - b->base_off[r]) + 31) & ~31ull;
+		}
+		bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; bp += 128;
+		if (bp > max_bp) { max_bp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
+		max_reads = std::max(max_reads, b->wr_off[w + 1] - b->wr_off[w]);
+	}
+	max_bp = (max_bp + 1023) & ~1023u;
+	const uint32_t smem_cap = 200u << 10;
+	while (lb2_smem_bytes(max_bp) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
+	lb2_cfg &C = ctx->C;
+	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp); C.max_reads = std::max(max_reads + 2, 64u);
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem_bytes));
+	int occ = 0;
+	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, LB2_THREADS, C.smem_bytes));
+	if (occ < 1) { ctx->err = "kernel does not fit on an SM"; return LB2_ERR_CUDA; }
+	uint32_t max_occ = env_u32("LB2_MAX_CTAS_PER_SM", 16);
+	C.n_slots = (uint32_t)ctx->sm_count * std::min<uint32_t>((uint32_t)occ, max_occ);
+	if (C.n_slots > std::max(W, 1u)) { C.n_slots = std::max(W, 1u); }
+	size_t stride = lb2_ws_layout(C, nullptr, nullptr);
+	if (stride != ctx->ws_stride || C.n_slots > ctx->ws_slots) {
+		if (ctx->d_ws.p) { cudaFree(ctx->d_ws.p); ctx->d_ws.p = nullptr; ctx->d_ws.cap = 0; }
+		size_t bytes = stride * C.n_slots;
+		LB2_CK(cudaMalloc(&ctx->d_ws.p, bytes)); ctx->d_ws.cap = bytes;
+		LB2_CK(cudaMemsetAsync(ctx->d_ws.p, 0, bytes, ctx->stream));   // the hash table must start all-zero
+		ctx->ws_stride = stride; ctx->ws_slots = C.n_slots;
+	}
+	uint64_t h2d = 0;
+#define LB2_UP(buf, ptr, bytes) do { int rc_ = lb2_reserve(ctx, ctx->buf, (bytes)); if (rc_) return rc_; \
+		LB2_CK(cudaMemcpyAsync(ctx->buf.p, (ptr), (bytes), cudaMemcpyHostToDevice, ctx->stream)); h2d += (bytes); } while (0)
+	LB2_UP(d_ref_off, b->ref_off, sizeof(uint32_t) * (size_t)(W + 1));
+	LB2_UP(d_ref_start, b->ref_start, sizeof(int32_t) * (size_t)W);
+	LB2_UP(d_wr_off, b->wr_off, sizeof(uint32_t) * (size_t)(W + 1));
+	LB2_UP(d_wr_idx, b->wr_idx, sizeof(uint32_t) * (size_t)b->n_wr);
+	LB2_UP(d_base_off, b->base_off, sizeof(uint64_t) * (size_t)(R + 1));
+	LB2_UP(d_flags, b->flags, (size_t)R);
+	LB2_UP(d_name_rank, b->name_rank, sizeof(uint32_t) * (size_t)R);
+	LB2_UP(d_ref_seq, b->ref_seq, (size_t)b->n_ref_bytes);
+	LB2_UP(d_seq, b->seq, (size_t)b->n_base_bytes);
+	LB2_UP(d_qual, b->qual, (size_t)b->n_base_bytes);
+#undef LB2_UP
+	ctx->h2d_bytes = h2d;
+	int rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_info, sizeof(lb2_window_info) * (size_t)W))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_vars, sizeof(lb2_variant) * (size_t)W * C.max_var))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_strs, (size_t)W * C.str_bytes))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_str_used, sizeof(uint32_t) * (size_t)W))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_var_off, sizeof(uint32_t) * (size_t)W))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_str_off, sizeof(uint32_t) * (size_t)W))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_cvars, sizeof(lb2_variant) * (size_t)W * C.max_var))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_cstr, (size_t)W * C.str_bytes))) return rc;
+	lb2_launch &L = ctx->L;
+	L.P = ctx->P; L.C = C;
+	L.B.n_windows = W; L.B.ref_off = (const uint32_t *)ctx->d_ref_off.p; L.B.ref_start = (const int32_t *)ctx->d_ref_start.p;
+	L.B.wr_off = (const uint32_t *)ctx->d_wr_off.p; L.B.wr_idx = (const uint32_t *)ctx->d_wr_idx.p;
+	L.B.base_off = (const uint64_t *)ctx->d_base_off.p; L.B.flags = (const uint8_t *)ctx->d_flags.p;
+	L.B.name_rank = (const uint32_t *)ctx->d_name_rank.p; L.B.ref_seq = (const char *)ctx->d_ref_seq.p;
+	L.B.seq = (const char *)ctx->d_seq.p; L.B.qual = (const char *)ctx->d_qual.p;
+	L.O.info = (lb2_window_info *)ctx->d_info.p; L.O.variants = (lb2_variant *)ctx->d_vars.p; L.O.strings = (char *)ctx->d_strs.p;
+	L.O.str_used = (uint32_t *)ctx->d_str_used.p;
+	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
+	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_totals;
+	L.cvars = (lb2_variant *)ctx->d_cvars.p; L.cstr = (char *)ctx->d_cstr.p;
+	LB2_CK(cudaMemcpyAsync(ctx->d_launch, &L, sizeof L, cudaMemcpyHostToDevice, ctx->stream));
+	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	ctx->n_windows = W; ctx->resident = true;
+	return LB2_OK;
+}
+
+extern "C" int lb2_run(lb2_ctx *ctx)
+{
+	if (!ctx) { return LB2_ERR_ARG; }
+	if (!ctx->resident) { return LB2_ERR_STATE; }
+	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
+	const uint32_t W = ctx->n_windows;
+	LB2_CK(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
+	LB2_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (W) {
+		lb2_window_kernel<<<ctx->C.n_slots, LB2_THREADS, ctx->C.smem_bytes, ctx->stream>>>(ctx->d_launch);
+		lb2_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_launch);
+		lb2_gather_kernel<<<W, 64, 0, ctx->stream>>>(ctx->d_launch);
+		ctx->launches += 3;
+	}
+	LB2_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+	LB2_CK(cudaGetLastError());
+	ctx->ran = true;
+	return LB2_OK;
+}
+
+extern "C" int lb2_download(lb2_ctx *ctx, lb2_result *res)
+{
+	if (!ctx || !res) { return LB2_ERR_ARG; }
+	if (!ctx->ran) { return LB2_ERR_STATE; }
+	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
+	const uint32_t W = ctx->n_windows;
+	uint32_t totals[2] = { 0, 0 };
+	ctx->h_info.resize(W);
+	if (W) {
+		LB2_CK(cudaMemcpyAsync(totals, ctx->d_totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		LB2_CK(cudaMemcpyAsync(ctx->h_info.data(), ctx->d_info.p, sizeof(lb2_window_info) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	ctx->h_vars.resize(totals[0]); ctx->h_str.resize(totals[1]);
+	if (totals[0]) { LB2_CK(cudaMemcpyAsync(ctx->h_vars.data(), ctx->d_cvars.p, sizeof(lb2_variant) * (size_t)totals[0], cudaMemcpyDeviceToHost, ctx->stream)); }
+	if (totals[1]) { LB2_CK(cudaMemcpyAsync(ctx->h_str.data(), ctx->d_cstr.p, totals[1], cudaMemcpyDeviceToHost, ctx->stream)); }
+	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->kernel_ms = ms;
+	ctx->d2h_bytes = 8 + sizeof(lb2_window_info) * (size_t)W + sizeof(lb2_variant) * (size_t)totals[0] + totals[1];
+	res->n_windows = W; res->n_variants = totals[0]; res->windows = ctx->h_info.data(); res->variants = ctx->h_vars.data();
+	res->strings = ctx->h_str.data(); res->n_string_bytes = totals[1]; res->kernel_ms = ms;
+	return LB2_OK;
+}
+
+extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *result)
+{
+	int rc = lb2_upload(ctx, batch); if (rc) { return rc; }
+	rc = lb2_run(ctx); if (rc) { return rc; }
+	return lb2_download(ctx, result);
+}
+
+extern "C" uint64_t lb2_last_h2d_bytes(const lb2_ctx *ctx) { return ctx ? ctx->h2d_bytes : 0; }
+extern "C" uint64_t lb2_last_d2h_bytes(const lb2_ctx *ctx) { return ctx ? ctx->d2h_bytes : 0; }
+extern "C" uint32_t lb2_resident_ctas(const lb2_ctx *ctx) { return ctx ? ctx->C.n_slots : 0; }
+extern "C" uint32_t lb2_smem_per_cta(const lb2_ctx *ctx) { return ctx ? ctx->C.smem_bytes : 0; }
+extern "C" int lb2_wait(lb2_ctx *ctx) { if (!ctx) return LB2_ERR_ARG; LB2_CK(cudaStreamSynchronize(ctx->stream)); return LB2_OK; }
+extern "C" float lb2_last_kernel_ms(lb2_ctx *ctx) { if (!ctx) return 0; float ms = 0; cudaEventSynchronize(ctx->ev1); cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); return ms; }
+
+extern "C" int lb2_rank_names(const char *const *names, uint32_t n, uint32_t *rank_out)
+{
+	if (!names || !rank_out) { return LB2_ERR_ARG; }
+	std::vector<uint32_t> idx(n); std::iota(idx.begin(), idx.end(), 0u);
+	std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return strcmp(names[a], names[b]) < 0; });
+	uint32_t r = 0;
+	for (uint32_t i = 0; i < n; ++i) { if (i && strcmp(names[idx[i]], names[idx[i - 1]]) != 0) { ++r; } rank_out[idx[i]] = r; }
+	return LB2_OK;
+}
