@@ -72,6 +72,7 @@ for _n in ("lb2_last_h2d_bytes", "lb2_last_d2h_bytes"):
 for _n in ("lb2_resident_ctas", "lb2_smem_per_cta"):
     getattr(_lib, _n).argtypes = [ctypes.c_void_p]
     getattr(_lib, _n).restype = ctypes.c_uint32
+_lib.lb2_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 _lib.lb2_last_kernel_ms.argtypes = [ctypes.c_void_p]
 _lib.lb2_last_kernel_ms.restype = ctypes.c_float
 
@@ -151,6 +152,16 @@ class Context:
     resident_ctas = property(lambda self: int(_lib.lb2_resident_ctas(self._h)))
     smem_per_cta = property(lambda self: int(_lib.lb2_smem_per_cta(self._h)))
     last_kernel_ms = property(lambda self: float(_lib.lb2_last_kernel_ms(self._h)))
+
+    PHASES = ("stage", "prescan_maxk", "ref_repeat_scan", "kmer_walk", "compact_sort", "mate_replay", "lowq_deficits",
+              "table_clear", "ref_coverage", "order_emulation", "lowcov_components", "component_sequential", "bfs_loadpath",
+              "path_repeat_scan", "align", "column_scan_emit", "other")
+
+    def phase_cycles(self, reset: bool = True) -> dict:
+        """lane-0 cycles per pipeline phase, summed over windows since the last reset (debugging aid)."""
+        buf = (ctypes.c_ulonglong * 24)()
+        self._ck(_lib.lb2_phase_cycles(self._h, buf, 1 if reset else 0))
+        return {n: int(buf[i]) for i, n in enumerate(self.PHASES)}
 
     def close(self):
         if self._h:

@@ -23,6 +23,13 @@ struct lb2_win {
 	char     *ref_raw;   // smem: window reference, ASCII
 };
 
+LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2);
+
+// attribute the cycles since the previous mark to phase ph (lane 0 only)
+LB2_DEV void lb2_mark(lb2_win &W, int ph) {
+	if (lb2_tid() == 0) { unsigned long long t = lb2_clock(); W.sh->prof[ph] += t - W.sh->t_last; W.sh->t_last = t; }
+}
+
 LB2_DEV void lb2_fail(lb2_win &W, uint32_t status, uint32_t detail) {
 	if (lb2_cas32(&W.sh->status, LB2_WIN_OK, status) == LB2_WIN_OK) { W.sh->detail = detail; }
 }
@@ -89,6 +96,21 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 	}
 	lb2_sync();
 	if (sh->status != LB2_WIN_OK) { return; }
+	{	// does any query name occur with both mate orders?  (otherwise hasOverlappingMate can never fire)
+		uint32_t r2 = 1; while (r2 < R) { r2 <<= 1; }
+		for (uint32_t r = tid; r < r2; r += nt) {
+			uint64_t k = ~0ull;
+			if (r < R) { uint32_t mate = (ws.rd_info[r] >> 2) & 3u; if (mate == 1 || mate == 2) { k = ((uint64_t)ws.rd_rank[r] << 2) | mate; } }
+			ws.sortk[r] = k;
+		}
+		lb2_sync();
+		lb2_sort64(ws.sortk, r2);
+		for (uint32_t r = tid + 1; r < r2; r += nt) {
+			uint64_t a = ws.sortk[r - 1], b = ws.sortk[r];
+			if (b != ~0ull && (a >> 2) == (b >> 2) && (a & 3) != (b & 3)) { sh->has_pairs = 1; }
+		}
+		lb2_sync();
+	}
 	const int qcall = W.P->min_qual_call;
 	for (uint32_t r = tid; r < R; r += nt) {
 		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
@@ -192,10 +214,12 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 	uint32_t su = lb2_find_or_insert(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
 	lb2_max32(&ws.occ[su], 0xFFFFFFFFu - (kbase + o_begin));
+	const bool rec = !isref && sh->has_pairs;
 	if (isref) { ws.refnode[o_begin] = su; }
 	else if (o_begin == 0) {
 		lb2_add32(&ws.cnt[su * 4 + cls], 1u);
 		if (normal) { lb2_or32(&ws.sflags[su], 1u); }
+		if (rec) { ws.inst[kbase] = su; }
 	}
 	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
 		if ((g & 15) == 0) { wordbuf = W.bits[g >> 4]; }
@@ -210,6 +234,7 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 		else {
 			lb2_add32(&ws.cnt[sv * 4 + cls], 1u);
 			if (normal) { lb2_or32(&ws.sflags[sv], 1u); }
+			if (rec) { ws.inst[kbase + o + 1] = sv; }
 			if (tumor) {
 				bool clean = true;
 				if (track_q) {
@@ -277,9 +302,11 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		sh->n_used = 0; sh->err = 0; sh->n_spec = 0;
 		sh->K = K; sh->nw = nw;
 		if (cum + L >= 0x7FFFFFF0u) { sh->err |= 1u << LB2_D_READS; }
+		if (sh->has_pairs && cum > W.C->max_inst) { sh->err |= 1u << LB2_D_READS; }
 	}
 	for (uint32_t i = tid; i < LB2_MAX_REF; i += nt) { ws.refnode[i] = LB2_NIL; }
 	lb2_sync();
+	if (sh->err) { return; }
 	const uint32_t nref_pairs = (L > (uint32_t)K) ? (L - K) : 0;
 	const uint32_t nchunks = (nref_pairs + 63) / 64;
 	for (uint32_t it = tid; it < R + nchunks; it += nt) {
@@ -292,6 +319,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		}
 	}
 	lb2_sync();
+	lb2_mark(W, LB2_PH_WALK);
 	if (sh->err) { return; }
 	// ---- compaction: order used slots by first occurrence = insertion order of the reference map
 	const uint32_t n = sh->n_used;
@@ -337,6 +365,60 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	}
 	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t s = ws.refnode[p]; if (s != LB2_NIL) { ws.refnode[p] = ws.slot2id[s]; } }
 	lb2_sync();
+	lb2_sync();
+	lb2_mark(W, LB2_PH_COMPACT);
+	// ---- overlapping-mate suppression (Node_t::hasOverlappingMate / addMateName, src/Node.cc:638-671;
+	//      call sites src/Graph.cc:232-233, 269, 299): a k-mer occurrence is not counted when std::binary_search
+	//      finds the read's name in the node's list of names of the OTHER mate order -- a list that is in push
+	//      order (unsorted) at that time.  Queries of one read only look at lists fed by reads of
+	//      the other mate order, so per node it suffices to replay its occurrences in read order.
+	if (sh->has_pairs) {
+		const uint32_t total = ws.rd_kbase[R];
+		uint32_t t2 = 1; while (t2 < total) { t2 <<= 1; }
+		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)ws.slot2id[ws.inst[x]] << 32) | x) : ~0ull; }
+		lb2_sync();
+		lb2_sort64(ws.sortk, t2);
+		uint32_t *nstart = ws.stack;
+		for (uint32_t x = tid; x < total; x += nt) {
+			uint32_t nd = (uint32_t)(ws.sortk[x] >> 32);
+			if (x == 0 || (uint32_t)(ws.sortk[x - 1] >> 32) != nd) { nstart[nd] = x; }
+		}
+		lb2_sync();
+		for (uint32_t j = tid; j < n; j += nt) {
+			uint32_t tot = 0; for (int c = 0; c < 4; ++c) { tot += ws.d_cnt[j * 4 + c]; }
+			if (!tot) { continue; }
+			uint32_t b0 = nstart[j];
+			uint32_t *L1 = ws.mates + 2 * (size_t)b0; uint32_t *L2top = ws.mates + 2 * (size_t)b0 + 2 * (size_t)tot - 1;   // list 2 grows downwards
+			uint32_t n1 = 0, n2 = 0;
+			for (uint32_t x = b0; x < b0 + tot; ++x) {
+				uint32_t s_ = (uint32_t)ws.sortk[x];
+				uint32_t lo = 0, hi = R;                       // read of occurrence s_: last r with kbase[r] <= s_
+				while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (ws.rd_kbase[mid] <= s_) { lo = mid; } else { hi = mid; } }
+				uint32_t r = lo, p = s_ - ws.rd_kbase[r];
+				uint32_t info = ws.rd_info[r], mate = (info >> 2) & 3u, cls = info & 3u, name = ws.rd_rank[r];
+				if (mate == 1 || mate == 2) {
+					// std::binary_search(first,last,val) = lower_bound + !(val < *it)   (libstdc++ stl_algo.h)
+					uint32_t len = (mate == 1) ? n2 : n1, first = 0;
+					while (len > 0) {
+						uint32_t half = len >> 1, mid = first + half;
+						uint32_t v = (mate == 1) ? *(L2top - mid) : L1[mid];
+						if (v < name) { first = mid + 1; len = len - half - 1; } else { len = half; }
+					}
+					uint32_t cnt_other = (mate == 1) ? n2 : n1;
+					bool ovl = false;
+					if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
+					if (ovl) { ws.inst[s_] |= 0x80000000u; ws.d_cnt[j * 4 + cls] -= 1; }
+					uint32_t last = ws.rd_len[r] - (uint32_t)K;
+					uint32_t pushes = (p == 0 || p == last) ? 1u : 2u;
+					for (uint32_t q = 0; q < pushes; ++q) { if (mate == 1) { L1[n1++] = name; } else { *(L2top - n2) = name; ++n2; } }
+				}
+			}
+			uint32_t t = 0; for (int c = 0; c < 4; ++c) { uint32_t v = ws.d_cnt[j * 4 + c]; ws.d_cov[j * 4 + c] = (float)v; t += v; }
+			ws.d_mincov[j] = (int32_t)t; ws.d_mincovqv[j] = (int32_t)t;
+		}
+		lb2_sync();
+	}
+	lb2_mark(W, LB2_PH_MATES);
 	// ---- low-quality deficits: minqv_{fwd,rev}[i] = count - deficit[i]   (Node_t::updateCovDistr, src/Node.cc:470-497)
 	if (tid == 0) { sh->n_nodes = n; sh->last_nodes = n; }
 	if (sh->has_lowq) {
@@ -352,6 +434,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					if (!lb2_getbit(W.lowq, g0 + q)) { continue; }
 					uint32_t p0 = (q + 1 > (uint32_t)K) ? (q + 1 - K) : 0, p1 = (q < len - K) ? q : (len - K);
 					for (uint32_t p = p0; p <= p1; ++p) {
+						if (sh->has_pairs && (ws.inst[ws.rd_kbase[r] + p] & 0x80000000u)) { continue; }
 						lb2_kmer f, rc; lb2_extract(W.bits, g0 + p, K, f); lb2_revcomp(f, K, rc);
 						bool fl = lb2_less(f, rc, nw);
 						uint32_t s = lb2_find_or_insert(W, fl ? f : rc, fl ? rc : f, 0, K, nw, false);
@@ -375,9 +458,10 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		}
 	}
 	lb2_sync();
+	lb2_mark(W, LB2_PH_LOWQ);
 	// ---- hand the slots back clean (the table is all-zero between builds)
 	for (uint32_t j = tid; j < n; j += nt) {
-		uint32_t s = (uint32_t)ws.sortk[j];
+		uint32_t s = ws.used[j];
 		ws.slots[s] = 0; ws.occ[s] = 0; ws.sflags[s] = 0;
 		for (int c = 0; c < 4; ++c) { ws.cnt[s * 4 + c] = 0; }
 		for (int e = 0; e < LB2_ECAP; ++e) { ws.ekey[(size_t)s * LB2_ECAP + e] = 0; ws.eseq[(size_t)s * LB2_ECAP + e] = 0; }

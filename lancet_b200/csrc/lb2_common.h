@@ -40,6 +40,7 @@ struct lb2_cfg {
 	uint32_t arena_bytes;   // unitig strings / coverage arrays
 	uint32_t deficit_bytes; // low-quality deficit counters [node][k][4] u16
 	uint32_t queue_cap;     // BFS path-tree entries
+	uint32_t max_inst;      // k-mer occurrences per (window,k) tracked for the overlapping-mate replay
 	uint32_t max_var;       // variant records per window
 	uint32_t str_bytes;     // string pool per window
 	uint32_t bucket_cap;    // buckets for the libstdc++ order emulation (prime >= max_nodes)
@@ -62,6 +63,7 @@ struct lb2_dev_out {
 	lb2_variant     *variants;  // [n_windows * max_var]
 	char            *strings;   // [n_windows * str_bytes]
 	uint32_t        *str_used;  // [n_windows]
+	unsigned long long *prof;   // [24] cycles per pipeline phase summed over windows (lane 0), may be NULL
 };
 
 #endif

@@ -92,7 +92,7 @@ struct lb2_ctx {
 	struct Buf { void *p = nullptr; size_t cap = 0; };
 	Buf d_ref_off, d_ref_start, d_wr_off, d_wr_idx, d_base_off, d_flags, d_name_rank, d_ref_seq, d_seq, d_qual;
 	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws;
-	uint32_t *d_counter = nullptr, *d_totals = nullptr; lb2_launch *d_launch = nullptr;
+	uint32_t *d_counter = nullptr, *d_totals = nullptr; lb2_launch *d_launch = nullptr; unsigned long long *d_prof = nullptr;
 	lb2_launch L;
 	uint32_t n_windows = 0; bool resident = false, ran = false;
 	size_t ws_stride = 0; uint32_t ws_slots = 0;
@@ -153,11 +153,13 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
-	C.hash_cap = env_u32("LB2_HASH_CAP", 8192); C.max_nodes = env_u32("LB2_MAX_NODES", C.hash_cap / 2 - 64);
+	C.hash_cap = env_u32("LB2_HASH_CAP", 16384); C.max_nodes = env_u32("LB2_MAX_NODES", C.hash_cap / 2 - 64);
 	C.max_reads = 4096; C.max_bp = 0;
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
+	C.max_inst = env_u32("LB2_MAX_INST", 1u << 17);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
 	C.bucket_cap = 10273; C.max_k = 127;
+	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
 		delete ctx; return LB2_ERR_CUDA;
 	}
@@ -250,7 +252,7 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	L.B.name_rank = (const uint32_t *)ctx->d_name_rank.p; L.B.ref_seq = (const char *)ctx->d_ref_seq.p;
 	L.B.seq = (const char *)ctx->d_seq.p; L.B.qual = (const char *)ctx->d_qual.p;
 	L.O.info = (lb2_window_info *)ctx->d_info.p; L.O.variants = (lb2_variant *)ctx->d_vars.p; L.O.strings = (char *)ctx->d_strs.p;
-	L.O.str_used = (uint32_t *)ctx->d_str_used.p;
+	L.O.str_used = (uint32_t *)ctx->d_str_used.p; L.O.prof = ctx->d_prof;
 	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
 	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_totals;
 	L.cvars = (lb2_variant *)ctx->d_cvars.p; L.cstr = (char *)ctx->d_cstr.p;
@@ -311,6 +313,14 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	return lb2_download(ctx, result);
 }
 
+// debugging aid: cycles per pipeline phase (lane 0 of every CTA), summed since the context was created
+extern "C" int lb2_phase_cycles(lb2_ctx *ctx, unsigned long long *out24, int reset)
+{
+	if (!ctx || !out24) { return LB2_ERR_ARG; }
+	LB2_CK(cudaMemcpy(out24, ctx->d_prof, 24 * 8, cudaMemcpyDeviceToHost));
+	if (reset) { LB2_CK(cudaMemset(ctx->d_prof, 0, 24 * 8)); }
+	return LB2_OK;
+}
 extern "C" uint64_t lb2_last_h2d_bytes(const lb2_ctx *ctx) { return ctx ? ctx->h2d_bytes : 0; }
 extern "C" uint64_t lb2_last_d2h_bytes(const lb2_ctx *ctx) { return ctx ? ctx->d2h_bytes : 0; }
 extern "C" uint32_t lb2_resident_ctas(const lb2_ctx *ctx) { return ctx ? ctx->C.n_slots : 0; }

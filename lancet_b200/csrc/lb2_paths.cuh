@@ -341,8 +341,10 @@ LB2_DEVNI void lb2_process_path(lb2_win &W)
 		if (lb2_tid() == 0) { lb2_align_trace(W); }
 		lb2_sync();
 	}
+	lb2_mark(W, LB2_PH_ALIGN);
 	if (lb2_tid() == 0 && !sh->err) { lb2_scan_alignment(W); }
 	lb2_sync();
+	lb2_mark(W, LB2_PH_SCAN);
 }
 
 #endif

@@ -17,10 +17,10 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	size_t off = 0;
 #define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
 	const size_t HC = c.hash_cap, MN = (size_t)c.max_nodes + LB2_MAX_SPECIAL, MR = (size_t)c.max_reads + 2;
-	size_t n2 = 1; while (n2 < c.max_nodes) { n2 <<= 1; }
+	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
 	LB2_TAKE(slots, uint64_t, HC); LB2_TAKE(occ, uint32_t, HC); LB2_TAKE(cnt, uint32_t, HC * 4); LB2_TAKE(sflags, uint32_t, HC);
 	LB2_TAKE(ekey, uint32_t, HC * LB2_ECAP); LB2_TAKE(eseq, uint32_t, HC * LB2_ECAP);
-	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(slot2id, uint32_t, HC); LB2_TAKE(sortk, uint64_t, n2);
+	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(slot2id, uint32_t, HC); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
 	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR);
 	LB2_TAKE(d_rep, uint32_t, MN); LB2_TAKE(d_hash, uint64_t, MN); LB2_TAKE(d_cov, float, MN * 4); LB2_TAKE(d_cnt, uint32_t, MN * 4);
@@ -87,7 +87,9 @@ LB2_DEVNI void lb2_clear_table_full(lb2_win &W)
 LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 {
 	lb2_sh *sh = W.sh; const lb2_params *P = W.P; const unsigned tid = lb2_tid();
+	if (tid == 0) { for (int i = 0; i < 24; ++i) { sh->prof[i] = 0; } sh->t_last = lb2_clock(); }
 	lb2_stage_window(W, w);
+	lb2_mark(W, LB2_PH_STAGE);
 	if (sh->status == LB2_WIN_OK) {
 		if (P->max_unit_len > 16 || P->max_k > (int32_t)W.C->max_k) { if (tid == 0) { sh->status = LB2_WIN_UNSUPPORTED; sh->detail = LB2_D_KMAX; } lb2_sync(); }
 	}
@@ -95,6 +97,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		// window pre-skip: isRepeat(rawseq, maxK)  (src/Microassembler.cc:800)
 		lb2_pair_scan(W, W.ref_raw, (int)sh->L, P->max_k, 0, false);
 		if (sh->flag_a) { if (tid == 0) { sh->status = LB2_WIN_SKIP_REPEAT; } lb2_sync(); }
+		lb2_mark(W, LB2_PH_PRESCAN);
 	}
 	if (sh->status == LB2_WIN_OK) {
 		bool ref_passed = false;
@@ -102,18 +105,23 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			if (!ref_passed) {
 				// isRepeat / isAlmostRepeat on the window reference; both are monotone in k
 				lb2_pair_scan(W, W.ref_raw, (int)sh->L, k, P->max_mismatch, true);
+				lb2_mark(W, LB2_PH_REFSCAN);
 				if (sh->flag_a || sh->flag_b) { continue; }
 				ref_passed = true;
 			}
 			lb2_build_graph(W, k);
 			if (tid == 0) { sh->n_k_tried += 1; sh->final_k = (uint32_t)k; }
 			lb2_sync();
+			lb2_mark(W, LB2_PH_CLEAR);
 			if (sh->err) { lb2_clear_table_full(W); break; }
 			lb2_ref_coverage(W);
+			lb2_mark(W, LB2_PH_REFCOV);
 			if (tid == 0) {
 				sh->arena_used = 8; sh->flag_c = 0;
 				lb2_order_nodes(W);
+				lb2_mark(W, LB2_PH_ORDER);
 				if (!sh->err) { lb2_remove_lowcov(W, 0); sh->numcomp = lb2_mark_components(W); }
+				lb2_mark(W, LB2_PH_LOWCOV_CC);
 			}
 			lb2_sync();
 			if (sh->err) { break; }
@@ -131,6 +139,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						if (!sh->err) { cyc = lb2_has_cycle(W); }
 					}
 					sh->flag_c = cyc ? 1u : 0u;
+					lb2_mark(W, LB2_PH_COMP_SEQ);
 				}
 				lb2_sync();
 				if (sh->err) { break; }
@@ -143,10 +152,12 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
 						if (sh->path_found) { lb2_load_path(W, best); }
+						lb2_mark(W, LB2_PH_BFS);
 					}
 					lb2_sync();
 					if (sh->err || !sh->path_found) { break; }
 					lb2_pair_scan(W, W.ws.pathseq, (int)sh->plen, k, P->max_mismatch, true);
+					lb2_mark(W, LB2_PH_PATHSCAN);
 					if (sh->flag_b) { rpt = true; break; }
 					if (tid == 0) { lb2_flag_path(W, 1); }
 					++nflag;
@@ -166,6 +177,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
 						if (sh->path_found) { lb2_load_path(W, best); }
+						lb2_mark(W, LB2_PH_BFS);
 					}
 					lb2_sync();
 					if (sh->err || !sh->path_found) { break; }
@@ -185,6 +197,10 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		lb2_window_info wi; wi.status = (uint8_t)sh->status; wi.final_k = (uint8_t)sh->final_k; wi.n_k_tried = (uint16_t)sh->n_k_tried;
 		wi.n_variants = (sh->status == LB2_WIN_OK) ? sh->n_var : 0; wi.n_nodes = sh->last_nodes; wi.detail = sh->detail;
 		W.O->info[w] = wi; W.O->str_used[w] = sh->str_used;
+		lb2_mark(W, LB2_PH_OTHER);
+#ifndef LB2_HOSTSIM
+		if (W.O->prof) { for (int i = 0; i < LB2_PH_N; ++i) { if (sh->prof[i]) { atomicAdd(&W.O->prof[i], sh->prof[i]); } } }
+#endif
 	}
 	lb2_sync();
 }

@@ -28,6 +28,7 @@ static inline uint64_t lb2_ld64(const uint64_t *p) { return *p; }
 static inline uint32_t lb2_ld32(const uint32_t *p) { return *p; }
 static inline int lb2_ctz64(uint64_t x) { return __builtin_ctzll(x); }
 static inline int lb2_clz32(uint32_t x) { return __builtin_clz(x); }
+static inline unsigned long long lb2_clock() { return 0; }
 #else
 #define LB2_DEV   __device__ __forceinline__
 #define LB2_DEVNI __device__ __noinline__
@@ -45,6 +46,7 @@ LB2_DEV uint64_t lb2_ld64(const uint64_t *p) { return *(const volatile uint64_t 
 LB2_DEV uint32_t lb2_ld32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }
+LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
 #endif
 
 #endif

@@ -41,7 +41,7 @@ struct lb2_trans {                // Transcript_t (reference src/Transcript.hh:3
 struct lb2_ws {
 	// --- build stage, slot indexed ---
 	uint64_t *slots; uint32_t *occ; uint32_t *cnt; uint32_t *sflags; uint32_t *ekey; uint32_t *eseq;
-	uint32_t *used; uint32_t *slot2id; uint64_t *sortk;
+	uint32_t *used; uint32_t *slot2id; uint64_t *sortk; uint32_t *inst; uint32_t *mates;
 	// --- reads ---
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
 	// --- dense nodes ---
@@ -86,6 +86,11 @@ struct lb2_sh {
 	uint32_t n_var, str_used, n_k_tried, final_k, last_nodes;
 	int32_t  numcomp;
 	uint32_t stop_k;
+	unsigned long long prof[24]; unsigned long long t_last;
 };
+
+// phase ids for the optional cycle profile (lb2_dev_out::prof)
+enum { LB2_PH_STAGE = 0, LB2_PH_PRESCAN, LB2_PH_REFSCAN, LB2_PH_WALK, LB2_PH_COMPACT, LB2_PH_MATES, LB2_PH_LOWQ, LB2_PH_CLEAR,
+       LB2_PH_REFCOV, LB2_PH_ORDER, LB2_PH_LOWCOV_CC, LB2_PH_COMP_SEQ, LB2_PH_BFS, LB2_PH_PATHSCAN, LB2_PH_ALIGN, LB2_PH_SCAN, LB2_PH_OTHER, LB2_PH_N };
 
 #endif

@@ -80,12 +80,20 @@ def make_batch(seed: int = 7, region_len: int = 3000, region_start: int = 1001, 
                cov_n: float = 60.0, read_len: int = 100, err: float = 0.001, vaf: float = 0.5,
                var_every: int = 700, window: int = 600, delta: int = 100, paired: bool = False,
                insert_mean: float = 300.0, insert_sd: float = 30.0, chr_id: int = 22, n_in_ref: int = 0,
-               low_qual_frac: float = 0.0, kinds=("snv", "ins", "del"), return_truth: bool = False):
+               low_qual_frac: float = 0.0, kinds=("snv", "ins", "del"), str_every: int = 0,
+               return_truth: bool = False):
     rng = np.random.default_rng(seed)
     margin = 1000
     g0 = max(0, region_start - 1 - margin)           # 0-based genome coordinate of local index 0
     G = region_len + 2 * margin
     ref_codes = rng.integers(0, 4, G).astype(np.uint8)
+    if str_every:   # config 4: STR blocks (unit 1-6 bp x 5-40 copies) every ~str_every bp
+        p = int(rng.integers(0, str_every))
+        while p < G - 300:
+            unit = rng.integers(0, 4, int(rng.integers(1, 7))).astype(np.uint8)
+            blk = np.tile(unit, int(rng.integers(5, 41)))[:250]
+            ref_codes[p:p + len(blk)] = blk
+            p += len(blk) + str_every + int(rng.integers(-str_every // 4, str_every // 4 + 1))
     alt, a_s, a_e, truth = _make_alt(ref_codes, rng, var_every, first=margin // 2 + int(rng.integers(0, 200)), kinds=kinds)
     r_s = np.arange(G, dtype=np.int64)
     r_e = r_s + 1
