@@ -21,6 +21,8 @@ struct lb2_win {
 	uint32_t *bits;      // smem: 2-bit packed trimmed reads, then the window reference
 	uint32_t *lowq;      // smem: 1 bit per staged base: quality < MIN_QUAL_CALL
 	char     *ref_raw;   // smem: window reference, ASCII
+	uint8_t  *treg;      // smem region T: Mer->Node table during the build, graph-stage arrays afterwards
+	uint32_t *t_key, *t_occ, *t_cnt, *t_em;
 };
 
 LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2);
@@ -144,30 +146,38 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 }
 
 // ---------------------------------------------------------------------------------------------
-// hash table: slot word = (fingerprint32 | 0x80000000) << 32 | (g << 1 | ori) where g is the
-// staged base index of one representative occurrence; matches are verified against the bases.
+// Mer -> Node table in SHARED memory (region T), TS = cfg.table_slots slots, per slot:
+//   t_key  u32  0x80000000 | fingerprint12 << 19 | (g << 1 | ori): g = staged base index of one
+//               representative occurrence (matches are verified against the packed bases)
+//   t_occ  u32  0xFFFFFFFF - first occurrence (atomicMax); after the sort: dense node id
+//   t_cnt  2xu32  tumour / normal occurrence counts, fwd in the low half, rev in the high half
+//   t_em   u32  bits 0-7 edge types seen (start orientation*4 + appended base), bit 8 normal,
+//               bit 9 tumour-qualified, bit 10 "branching" (needs first-seen edge order)
 // ---------------------------------------------------------------------------------------------
+#define LB2_EM_NORMAL 0x100u
+#define LB2_EM_TUMOR  0x200u
+#define LB2_EM_BRANCH 0x400u
+
 LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2_kmer &nonc, uint32_t rep, int K, int nw, bool insert)
 {
-	lb2_ws &ws = W.ws; const uint32_t mask = W.C->hash_cap - 1;
+	uint32_t *tk = W.t_key; const uint32_t mask = W.C->table_slots - 1;
 	uint64_t h = lb2_table_hash(canon, nw);
 	uint32_t i = (uint32_t)h & mask;
-	uint64_t fp = (h >> 32) | 0x80000000ull;
+	const uint32_t fp = 0x80000000u | (((uint32_t)(h >> 40) & 0xFFFu) << 19);
 	for (uint32_t probes = 0; probes <= mask; ++probes) {
-		uint64_t cur = lb2_ld64(&ws.slots[i]);
+		uint32_t cur = lb2_ld32(&tk[i]);
 		if (cur == 0) {
 			if (!insert) { return LB2_NIL; }
-			uint64_t mine = (fp << 32) | rep;
-			uint64_t prev = lb2_cas64(&ws.slots[i], 0ull, mine);
+			uint32_t prev = lb2_cas32(&tk[i], 0u, fp | rep);
 			if (prev == 0) {
 				uint32_t u = lb2_add32(&W.sh->n_used, 1u);
-				if (u < W.C->max_nodes) { ws.used[u] = i; } else { lb2_or32(&W.sh->err, 1u << LB2_D_NODES); }
+				if (u < W.C->max_nodes && u < (mask + 1) - ((mask + 1) >> 2)) { W.ws.used[u] = i; } else { lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL); }
 				return i;
 			}
 			cur = prev;
 		}
-		if ((cur >> 32) == fp) {
-			uint32_t r = (uint32_t)cur;
+		if ((cur & 0xFFF80000u) == fp) {
+			uint32_t r = cur & 0x7FFFFu;
 			lb2_kmer o; lb2_extract(W.bits, r >> 1, K, o);
 			if (lb2_equal(o, (r & 1) ? nonc : canon, nw)) { return i; }
 		}
@@ -175,20 +185,6 @@ LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2
 	}
 	lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL);
 	return LB2_NIL;
-}
-
-LB2_DEV void lb2_add_edge(lb2_win &W, uint32_t slot, uint32_t to, uint32_t dir, uint32_t seq)
-{
-	lb2_ws &ws = W.ws;
-	uint32_t key = ((to << 2) | dir) + 1u;
-	uint32_t inv = 0xFFFFFFFFu - seq;
-	uint32_t *ek = ws.ekey + (size_t)slot * LB2_ECAP; uint32_t *es = ws.eseq + (size_t)slot * LB2_ECAP;
-	for (int e = 0; e < LB2_ECAP; ++e) {
-		uint32_t cur = lb2_ld32(&ek[e]);
-		if (cur == 0) { cur = lb2_cas32(&ek[e], 0u, key); if (cur == 0) { cur = key; } }
-		if (cur == key) { lb2_max32(&es[e], inv); return; }
-	}
-	lb2_or32(&W.sh->err, 1u << LB2_D_EDGES);
 }
 
 // one work item: a whole read, or a 64-pair chunk of the reference "read"
@@ -199,42 +195,44 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 	lb2_kmer f, rc;
 	for (int j = 0; j < LB2_MAXW; ++j) { f.w[j] = 0; rc.w[j] = 0; }
 	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
-	// warm-up: first K bases
-	for (int i = 0; i < K; ++i, ++g) {
+	for (int i = 0; i < K; ++i, ++g) {          // warm-up: first K bases
 		if ((g & 15) == 0 || i == 0) { wordbuf = W.bits[g >> 4]; }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
 		lb2_roll_fwd(f, K, c); lb2_roll_rc(rc, K, c);
 	}
 	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
 	const bool track_q = tumor && sh->has_lowq;
+	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u, csel = cls >> 1;
 	int lowcnt = 0;    // low-quality bases in [o, o+K-1]; the pair window adds base o+K
 	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
 	bool fless = lb2_less(f, rc, nw);
 	uint32_t ori_u = fless ? 0u : 1u;
 	uint32_t su = lb2_find_or_insert(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
-	lb2_max32(&ws.occ[su], 0xFFFFFFFFu - (kbase + o_begin));
-	const bool rec = !isref && sh->has_pairs;
+	lb2_max32(&W.t_occ[su], 0xFFFFFFFFu - (kbase + o_begin));
+	ws.inst[kbase + o_begin] = su | (ori_u << 31);
 	if (isref) { ws.refnode[o_begin] = su; }
 	else if (o_begin == 0) {
-		lb2_add32(&ws.cnt[su * 4 + cls], 1u);
-		if (normal) { lb2_or32(&ws.sflags[su], 1u); }
-		if (rec) { ws.inst[kbase] = su; }
+		lb2_add32(&W.t_cnt[su * 2 + csel], cadd);
+		if (normal) { lb2_or32(&W.t_em[su], LB2_EM_NORMAL); }
 	}
 	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
 		if ((g & 15) == 0) { wordbuf = W.bits[g >> 4]; }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
+		int a = lb2_getbase(W.bits, g0 + o);                      // base that leaves the window
 		lb2_roll_fwd(f, K, c); lb2_roll_rc(rc, K, c);
 		fless = lb2_less(f, rc, nw);
 		uint32_t ori_v = fless ? 0u : 1u;
 		uint32_t sv = lb2_find_or_insert(W, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, K, nw, true);
 		if (sv == LB2_NIL) { return; }
-		lb2_max32(&ws.occ[sv], 0xFFFFFFFFu - (kbase + o + 1));
+		lb2_max32(&W.t_occ[sv], 0xFFFFFFFFu - (kbase + o + 1));
+		ws.inst[kbase + o + 1] = sv | (ori_v << 31);
+		uint32_t emu = 1u << (ori_u * 4 + (uint32_t)c);            // u leaves in orientation ori_u appending c
+		uint32_t emv = 1u << ((1u - ori_v) * 4 + (uint32_t)(3 - a)); // v leaves in the flipped orientation appending comp(a)
 		if (isref) { ws.refnode[o + 1] = sv; }
 		else {
-			lb2_add32(&ws.cnt[sv * 4 + cls], 1u);
-			if (normal) { lb2_or32(&ws.sflags[sv], 1u); }
-			if (rec) { ws.inst[kbase + o + 1] = sv; }
+			lb2_add32(&W.t_cnt[sv * 2 + csel], cadd);
+			if (normal) { emv |= LB2_EM_NORMAL; }
 			if (tumor) {
 				bool clean = true;
 				if (track_q) {
@@ -242,23 +240,15 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 					clean = (wl == 0);
 					lowcnt = wl - lb2_getbit(W.lowq, g0 + o);         // slide to [o+1, o+K]
 				}
-				if (clean) { lb2_or32(&ws.sflags[su], 2u); lb2_or32(&ws.sflags[sv], 2u); }
+				if (clean) { emu |= LB2_EM_TUMOR; emv |= LB2_EM_TUMOR; }
 			}
 		}
-		// edge directions (src/Graph.cc:320-326)
-		uint32_t fdir, rdir;
-		if (!ori_u && !ori_v) { fdir = LB2_FF; rdir = LB2_RR; }
-		else if (!ori_u && ori_v) { fdir = LB2_FR; rdir = LB2_FR; }
-		else if (ori_u && !ori_v) { fdir = LB2_RF; rdir = LB2_RF; }
-		else { fdir = LB2_RR; rdir = LB2_FF; }
-		uint32_t es = 2u * (kbase + o);
-		lb2_add_edge(W, su, sv, fdir, es);
-		lb2_add_edge(W, sv, su, rdir, es + 1u);
+		lb2_or32(&W.t_em[su], emu); lb2_or32(&W.t_em[sv], emv);
 		su = sv; ori_u = ori_v;
 	}
 }
 
-// bitonic sort of ws.sortk[0..n2) ascending, n2 a power of two
+// bitonic sort of a[0..n2) ascending, n2 a power of two
 LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2)
 {
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
@@ -285,26 +275,36 @@ LB2_DEV void lb2_revcomp(const lb2_kmer &f, int K, lb2_kmer &rc) {
 		rc.w[t >> 5] |= c << ((t & 31) << 1);
 	}
 }
+// canonical k-mer of a dense node (from its representative occurrence)
+LB2_DEV void lb2_node_kmer(lb2_win &W, uint32_t id, int K, lb2_kmer &km) {
+	uint32_t rep = W.ws.d_rep[id];
+	lb2_extract(W.bits, rep >> 1, K, km);
+	if (rep & 1) { lb2_kmer t; lb2_revcomp(km, K, t); km = t; }
+}
+LB2_DEV void lb2_shift_append(lb2_kmer &k, int K, int c) { lb2_roll_fwd(k, K, c); }
 
 // ---------------------------------------------------------------------------------------------
-// build the graph for k-mer size K; on return the dense node arrays are filled (insertion order)
+// build the graph for k-mer size K.  On return: dense nodes in insertion order (all nodes), the
+// first low-coverage sweep already applied as a per-node predicate (LB2_NF_DEAD), edges of the
+// survivors in the reference's first-seen order.
 // ---------------------------------------------------------------------------------------------
 LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 {
 	lb2_sh *sh = W.sh; lb2_ws &ws = W.ws; const lb2_cfg *C = W.C;
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const int nw = lb2_nw(K);
-	const uint32_t R = sh->R, L = sh->L;
+	const uint32_t R = sh->R, L = sh->L, TS = C->table_slots;
+	W.t_key = (uint32_t *)W.treg; W.t_occ = W.t_key + TS; W.t_cnt = W.t_occ + TS; W.t_em = W.t_cnt + 2 * (size_t)TS;
 	if (tid == 0) {
 		uint32_t cum = 0;
 		for (uint32_t r = 0; r < R; ++r) { ws.rd_kbase[r] = cum; uint32_t n = ws.rd_len[r]; cum += (n > (uint32_t)K) ? (n - K + 1) : 0; }
 		ws.rd_kbase[R] = cum;
-		sh->n_used = 0; sh->err = 0; sh->n_spec = 0;
+		sh->n_used = 0; sh->err = 0; sh->n_spec = 0; sh->flag_a = 0;
 		sh->K = K; sh->nw = nw;
-		if (cum + L >= 0x7FFFFFF0u) { sh->err |= 1u << LB2_D_READS; }
-		if (sh->has_pairs && cum > W.C->max_inst) { sh->err |= 1u << LB2_D_READS; }
+		if (cum + L + 2 > C->max_inst) { sh->err |= 1u << LB2_D_READS; }
 	}
 	for (uint32_t i = tid; i < LB2_MAX_REF; i += nt) { ws.refnode[i] = LB2_NIL; }
+	for (uint32_t i = tid; i < TS * 5; i += nt) { W.t_key[i] = 0; }      // t_key, t_occ, t_cnt, t_em are contiguous
 	lb2_sync();
 	if (sh->err) { return; }
 	const uint32_t nref_pairs = (L > (uint32_t)K) ? (L - K) : 0;
@@ -325,46 +325,30 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	const uint32_t n = sh->n_used;
 	uint32_t n2 = 1; while (n2 < n) { n2 <<= 1; }
 	for (uint32_t j = tid; j < n2; j += nt) {
-		if (j < n) { uint32_t s = ws.used[j]; ws.sortk[j] = ((uint64_t)(0xFFFFFFFFu - ws.occ[s]) << 32) | s; }
+		if (j < n) { uint32_t s = ws.used[j]; ws.sortk[j] = ((uint64_t)(0xFFFFFFFFu - W.t_occ[s]) << 32) | s; }
 		else { ws.sortk[j] = ~0ull; }
 	}
 	lb2_sync();
 	lb2_sort64(ws.sortk, n2);
-	for (uint32_t j = tid; j < n; j += nt) { ws.slot2id[(uint32_t)ws.sortk[j]] = j; }
+	for (uint32_t j = tid; j < n; j += nt) { uint32_t s = (uint32_t)ws.sortk[j]; W.t_occ[s] = j; ws.used[j] = s; }   // t_occ := slot -> dense id, used := dense id -> slot
 	lb2_sync();
 	for (uint32_t j = tid; j < n; j += nt) {
-		uint32_t s = (uint32_t)ws.sortk[j];
-		uint32_t rep = (uint32_t)ws.slots[s];
+		uint32_t s = ws.used[j];
+		uint32_t rep = W.t_key[s] & 0x7FFFFu;
 		ws.d_rep[j] = rep;
-		lb2_kmer km; lb2_extract(W.bits, rep >> 1, K, km);
-		if (rep & 1) { lb2_kmer t; lb2_revcomp(km, K, t); km = t; }
+		lb2_kmer km; lb2_node_kmer(W, j, K, km);
 		ws.d_hash[j] = lb2_stdhash_kmer(km, K);
-		uint32_t tot = 0;
-		for (int c = 0; c < 4; ++c) { uint32_t v = ws.cnt[s * 4 + c]; ws.d_cov[j * 4 + c] = (float)v; ws.d_cnt[j * 4 + c] = v; tot += v; }
-		uint32_t sf = ws.sflags[s];
-		ws.d_stn[j] = 1; ws.d_stT[j] = (sf == 2u) ? 1u : 0u;   // cov_status of the k-mer: 'T' iff tumour-qualified and never normal
+		uint32_t ct = W.t_cnt[s * 2], cn = W.t_cnt[s * 2 + 1];
+		uint32_t v[4] = { ct & 0xFFFFu, ct >> 16, cn & 0xFFFFu, cn >> 16 }, tot = 0;
+		for (int c = 0; c < 4; ++c) { ws.d_cov[j * 4 + c] = (float)v[c]; ws.d_cnt[j * 4 + c] = v[c]; tot += v[c]; }
+		uint32_t em = W.t_em[s];
+		ws.d_stn[j] = 1; ws.d_stT[j] = ((em & (LB2_EM_NORMAL | LB2_EM_TUMOR)) == LB2_EM_TUMOR) ? 1u : 0u;   // cov_status 'T': tumour-qualified, never normal
 		ws.d_mincov[j] = (int32_t)tot; ws.d_mincovqv[j] = (int32_t)tot;
-		ws.d_flags[j] = 0; ws.d_comp[j] = 0; ws.d_color[j] = 0;
+		ws.d_flags[j] = 0; ws.d_comp[j] = 0; ws.d_color[j] = 0; ws.d_ne[j] = 0;
 		ws.d_str[j] = LB2_NIL; ws.d_len[j] = (uint32_t)K; ws.d_cd[j] = LB2_NIL;
-		// edges: sort by first-seen, map targets to dense ids
-		uint32_t ek[LB2_ECAP], es[LB2_ECAP]; int ne = 0;
-		for (int e = 0; e < LB2_ECAP; ++e) {
-			uint32_t k = ws.ekey[(size_t)s * LB2_ECAP + e];
-			if (k) { ek[ne] = k - 1; es[ne] = 0xFFFFFFFFu - ws.eseq[(size_t)s * LB2_ECAP + e]; ++ne; }
-		}
-		for (int a = 1; a < ne; ++a) {
-			uint32_t kk = ek[a], ss = es[a]; int b = a - 1;
-			while (b >= 0 && es[b] > ss) { ek[b + 1] = ek[b]; es[b + 1] = es[b]; --b; }
-			ek[b + 1] = kk; es[b + 1] = ss;
-		}
-		for (int e = 0; e < ne; ++e) {
-			lb2_edge ed; ed.to = ws.slot2id[ek[e] >> 2]; ed.dir = (uint8_t)(ek[e] & 3); ed.flag = 0; ed.pad = 0;
-			ws.d_edge[(size_t)j * LB2_ECAP + e] = ed;
-		}
-		ws.d_ne[j] = (uint8_t)ne;
 	}
-	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t s = ws.refnode[p]; if (s != LB2_NIL) { ws.refnode[p] = ws.slot2id[s]; } }
-	lb2_sync();
+	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t s = ws.refnode[p]; if (s != LB2_NIL) { ws.refnode[p] = W.t_occ[s]; } }
+	if (tid == 0) { sh->n_nodes = n; sh->last_nodes = n; }
 	lb2_sync();
 	lb2_mark(W, LB2_PH_COMPACT);
 	// ---- overlapping-mate suppression (Node_t::hasOverlappingMate / addMateName, src/Node.cc:638-671;
@@ -375,7 +359,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	if (sh->has_pairs) {
 		const uint32_t total = ws.rd_kbase[R];
 		uint32_t t2 = 1; while (t2 < total) { t2 <<= 1; }
-		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)ws.slot2id[ws.inst[x]] << 32) | x) : ~0ull; }
+		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)W.t_occ[ws.inst[x] & 0x3FFFFFFFu] << 32) | x) : ~0ull; }
 		lb2_sync();
 		lb2_sort64(ws.sortk, t2);
 		uint32_t *nstart = ws.stack;
@@ -389,7 +373,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			if (!tot) { continue; }
 			uint32_t b0 = nstart[j];
 			uint32_t *L1 = ws.mates + 2 * (size_t)b0; uint32_t *L2top = ws.mates + 2 * (size_t)b0 + 2 * (size_t)tot - 1;   // list 2 grows downwards
-			uint32_t n1 = 0, n2 = 0;
+			uint32_t n1 = 0, n2_ = 0;
 			for (uint32_t x = b0; x < b0 + tot; ++x) {
 				uint32_t s_ = (uint32_t)ws.sortk[x];
 				uint32_t lo = 0, hi = R;                       // read of occurrence s_: last r with kbase[r] <= s_
@@ -398,19 +382,19 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				uint32_t info = ws.rd_info[r], mate = (info >> 2) & 3u, cls = info & 3u, name = ws.rd_rank[r];
 				if (mate == 1 || mate == 2) {
 					// std::binary_search(first,last,val) = lower_bound + !(val < *it)   (libstdc++ stl_algo.h)
-					uint32_t len = (mate == 1) ? n2 : n1, first = 0;
+					uint32_t len = (mate == 1) ? n2_ : n1, first = 0;
 					while (len > 0) {
 						uint32_t half = len >> 1, mid = first + half;
 						uint32_t v = (mate == 1) ? *(L2top - mid) : L1[mid];
 						if (v < name) { first = mid + 1; len = len - half - 1; } else { len = half; }
 					}
-					uint32_t cnt_other = (mate == 1) ? n2 : n1;
+					uint32_t cnt_other = (mate == 1) ? n2_ : n1;
 					bool ovl = false;
 					if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
-					if (ovl) { ws.inst[s_] |= 0x80000000u; ws.d_cnt[j * 4 + cls] -= 1; }
+					if (ovl) { ws.inst[s_] |= 0x40000000u; ws.d_cnt[j * 4 + cls] -= 1; }
 					uint32_t last = ws.rd_len[r] - (uint32_t)K;
 					uint32_t pushes = (p == 0 || p == last) ? 1u : 2u;
-					for (uint32_t q = 0; q < pushes; ++q) { if (mate == 1) { L1[n1++] = name; } else { *(L2top - n2) = name; ++n2; } }
+					for (uint32_t q = 0; q < pushes; ++q) { if (mate == 1) { L1[n1++] = name; } else { *(L2top - n2_) = name; ++n2_; } }
 				}
 			}
 			uint32_t t = 0; for (int c = 0; c < 4; ++c) { uint32_t v = ws.d_cnt[j * 4 + c]; ws.d_cov[j * 4 + c] = (float)v; t += v; }
@@ -420,7 +404,6 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	}
 	lb2_mark(W, LB2_PH_MATES);
 	// ---- low-quality deficits: minqv_{fwd,rev}[i] = count - deficit[i]   (Node_t::updateCovDistr, src/Node.cc:470-497)
-	if (tid == 0) { sh->n_nodes = n; sh->last_nodes = n; }
 	if (sh->has_lowq) {
 		uint32_t *d32 = (uint32_t *)ws.deficit;
 		if ((size_t)n * K * 8 > (size_t)C->deficit_bytes) { if (tid == 0) { sh->err |= 1u << LB2_D_ARENA; } }
@@ -429,18 +412,15 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			lb2_sync();
 			for (uint32_t r = tid; r < R; r += nt) {
 				uint32_t len = ws.rd_len[r]; if (len <= (uint32_t)K) { continue; }
-				uint32_t g0 = ws.rd_start[r]; uint32_t cls = ws.rd_info[r] & 3u;
+				uint32_t g0 = ws.rd_start[r]; uint32_t cls = ws.rd_info[r] & 3u; uint32_t kb = ws.rd_kbase[r];
 				for (uint32_t q = 0; q < len; ++q) {
 					if (!lb2_getbit(W.lowq, g0 + q)) { continue; }
 					uint32_t p0 = (q + 1 > (uint32_t)K) ? (q + 1 - K) : 0, p1 = (q < len - K) ? q : (len - K);
 					for (uint32_t p = p0; p <= p1; ++p) {
-						if (sh->has_pairs && (ws.inst[ws.rd_kbase[r] + p] & 0x80000000u)) { continue; }
-						lb2_kmer f, rc; lb2_extract(W.bits, g0 + p, K, f); lb2_revcomp(f, K, rc);
-						bool fl = lb2_less(f, rc, nw);
-						uint32_t s = lb2_find_or_insert(W, fl ? f : rc, fl ? rc : f, 0, K, nw, false);
-						if (s == LB2_NIL) { continue; }
-						uint32_t id = ws.slot2id[s];
-						uint32_t i = fl ? (q - p) : ((uint32_t)K - 1 - (q - p));   // qv string is reversed for ori R (src/Graph.cc:148-158)
+						uint32_t iw = ws.inst[kb + p];
+						if (iw & 0x40000000u) { continue; }               // suppressed (overlapping mate)
+						uint32_t id = W.t_occ[iw & 0x3FFFFFFFu];
+						uint32_t i = (iw >> 31) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
 						lb2_add32(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
 					}
 				}
@@ -459,14 +439,79 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	}
 	lb2_sync();
 	lb2_mark(W, LB2_PH_LOWQ);
-	// ---- hand the slots back clean (the table is all-zero between builds)
-	for (uint32_t j = tid; j < n; j += nt) {
-		uint32_t s = ws.used[j];
-		ws.slots[s] = 0; ws.occ[s] = 0; ws.sflags[s] = 0;
-		for (int c = 0; c < 4; ++c) { ws.cnt[s * 4 + c] = 0; }
-		for (int e = 0; e < LB2_ECAP; ++e) { ws.ekey[(size_t)s * LB2_ECAP + e] = 0; ws.eseq[(size_t)s * LB2_ECAP + e] = 0; }
+	if (sh->err) { return; }
+	// ---- first low-coverage sweep, Graph_t::removeLowCov(false,0) (src/Graph.cc:2790-2827): the rule only looks
+	//      at the node itself, so it is a per-node predicate; dead nodes simply never get edges below
+	{
+		double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
+		double thr = W.P->min_cov_ratio * avgcov;
+		for (uint32_t j = tid; j < n; j += nt) {
+			int mq = ws.d_mincovqv[j];
+			float tt = ws.d_cov[j * 4 + 0] + ws.d_cov[j * 4 + 1], tn = ws.d_cov[j * 4 + 2] + ws.d_cov[j * 4 + 3];
+			if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { ws.d_flags[j] = LB2_NF_DEAD; }
+		}
 	}
 	lb2_sync();
+	// ---- edges of the survivors: every edge type (start orientation, appended base) names one neighbour
+	for (uint32_t j = tid; j < n; j += nt) {
+		if (ws.d_flags[j] & LB2_NF_DEAD) { continue; }
+		uint32_t s = ws.used[j]; uint32_t em = W.t_em[s] & 0xFFu;
+		lb2_kmer C0; lb2_node_kmer(W, j, K, C0);
+		lb2_kmer C1; lb2_revcomp(C0, K, C1);
+		int ne = 0, nF = 0, nR = 0;
+		for (int t = 0; t < 8; ++t) {
+			if (!(em & (1u << t))) { continue; }
+			int o = t >> 2, b = t & 3;
+			lb2_kmer V = o ? C1 : C0; lb2_roll_fwd(V, K, b);
+			lb2_kmer Vr; lb2_revcomp(V, K, Vr);
+			bool fl = lb2_less(V, Vr, nw);
+			uint32_t ts = lb2_find_or_insert(W, fl ? V : Vr, fl ? Vr : V, 0, K, nw, false);
+			if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); break; }
+			uint32_t to = W.t_occ[ts];
+			if (ws.d_flags[to] & LB2_NF_DEAD) { continue; }
+			lb2_edge ed; ed.to = to; ed.dir = (uint8_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.pad = (uint16_t)t;
+			ws.d_edge[(size_t)j * LB2_ECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
+		}
+		ws.d_ne[j] = (uint8_t)ne;
+		if (nF > 1 || nR > 1) {   // first-seen order matters only among edges leaving in the same orientation
+			lb2_or32(&W.t_em[s], LB2_EM_BRANCH); sh->flag_a = 1;
+			for (int t = 0; t < 8; ++t) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
+		}
+	}
+	lb2_sync();
+	if (sh->flag_a && !sh->err) {
+		for (uint32_t it = tid; it < R + 1; it += nt) {
+			uint32_t g0, np, kb;
+			if (it < R) { uint32_t n_ = ws.rd_len[it]; if (n_ <= (uint32_t)K) { continue; } g0 = ws.rd_start[it]; np = n_ - K; kb = ws.rd_kbase[it]; }
+			else { g0 = sh->ref_g; np = nref_pairs; kb = ws.rd_kbase[R]; }
+			uint32_t iu = ws.inst[kb];
+			for (uint32_t o = 0; o < np; ++o) {
+				uint32_t iv = ws.inst[kb + o + 1];
+				uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
+				if (W.t_em[su] & LB2_EM_BRANCH) {
+					uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
+					lb2_min32(&ws.bseq[(size_t)W.t_occ[su] * 8 + t], 2 * (kb + o));
+				}
+				if (W.t_em[sv] & LB2_EM_BRANCH) {
+					uint32_t t = (1u - (iv >> 31)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
+					lb2_min32(&ws.bseq[(size_t)W.t_occ[sv] * 8 + t], 2 * (kb + o) + 1);
+				}
+				iu = iv;
+			}
+		}
+		lb2_sync();
+		for (uint32_t j = tid; j < n; j += nt) {
+			if (!(W.t_em[ws.used[j]] & LB2_EM_BRANCH)) { continue; }
+			lb2_edge *e = ws.d_edge + (size_t)j * LB2_ECAP; int ne = ws.d_ne[j];
+			for (int a = 1; a < ne; ++a) {
+				lb2_edge x = e[a]; uint32_t sx = ws.bseq[(size_t)j * 8 + x.pad]; int b = a - 1;
+				while (b >= 0 && ws.bseq[(size_t)j * 8 + e[b].pad] > sx) { e[b + 1] = e[b]; --b; }
+				e[b + 1] = x;
+			}
+		}
+	}
+	lb2_sync();
+	lb2_mark(W, LB2_PH_CLEAR);
 }
 
 #endif

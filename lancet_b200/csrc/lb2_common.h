@@ -33,8 +33,8 @@ enum {
 
 // ---- runtime configuration of the device workspace -----------------------------------------
 struct lb2_cfg {
-	uint32_t hash_cap;      // open-addressing slots (power of two)
-	uint32_t max_nodes;     // dense nodes per (window,k)  (<= hash_cap/2)
+	uint32_t table_slots;   // shared-memory Mer->Node table slots (power of two)
+	uint32_t max_nodes;     // dense nodes per (window,k)  (<= 3/4 table_slots)
 	uint32_t max_reads;     // reads per window (+1 for the reference read)
 	uint32_t max_bp;        // staged (trimmed) read bases per window incl. reference (smem)
 	uint32_t arena_bytes;   // unitig strings / coverage arrays

@@ -34,6 +34,7 @@ lb2_window_kernel(const lb2_launch *Lp)
 	W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
 	W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);
 	W.lowq = W.bits + (Lp->C.max_bp / 16 + 4);
+	W.treg = smem + ((lb2_smem_fixed(Lp->C.max_bp) + 15) & ~(size_t)15);
 	const uint32_t nwin = Lp->B.n_windows;
 	while (true) {
 		if (threadIdx.x == 0) { s_next = atomicAdd(Lp->counter, 1u); }
@@ -153,7 +154,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
-	C.hash_cap = env_u32("LB2_HASH_CAP", 16384); C.max_nodes = env_u32("LB2_MAX_NODES", C.hash_cap / 2 - 64);
+	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096); C.max_nodes = env_u32("LB2_MAX_NODES", C.table_slots - C.table_slots / 4);
 	C.max_reads = 4096; C.max_bp = 0;
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 17);
@@ -201,10 +202,11 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 		max_reads = std::max(max_reads, b->wr_off[w + 1] - b->wr_off[w]);
 	}
 	max_bp = (max_bp + 1023) & ~1023u;
-	const uint32_t smem_cap = 200u << 10;
-	while (lb2_smem_bytes(max_bp) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
+	const uint32_t smem_cap = 220u << 10;
+	if (max_bp > (1u << 18) - 1024) { max_bp = (1u << 18) - 1024; }   // representative base index has 18 bits in the table key
+	while (lb2_smem_bytes(max_bp, ctx->C.table_slots) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
 	lb2_cfg &C = ctx->C;
-	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp); C.max_reads = std::max(max_reads + 2, 64u);
+	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C.table_slots); C.max_reads = std::max(max_reads + 2, 64u);
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem_bytes));
 	int occ = 0;
 	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, LB2_THREADS, C.smem_bytes));

@@ -243,6 +243,8 @@ LB2_DEVNI void lb2_order_nodes(lb2_win &W) {
 	lb2_oe_reset(W);
 	for (uint32_t j = 0; j < W.sh->n_nodes; ++j) { lb2_oe_insert(W, j); if (W.sh->err) { return; } }
 }
+// the nodes condemned by the first low-coverage sweep leave the map (cleanDead of removeLowCov(false,0))
+LB2_DEVNI void lb2_drop_dead(lb2_win &W) { lb2_clean_dead(W); }
 
 // removeLowCov(docompression=false path and the sweep part) src/Graph.cc:2790-2827
 LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {

@@ -13,32 +13,32 @@
 #include "lb2_graph.cuh"
 
 // ---------------------------------------------------------------------------------------------------
-// repeat predicates over a character string, CTA-wide.  Results: sh->flag_a (exact K-mer repeat among
-// offsets < len-K), sh->flag_b (two offsets whose (K+1)-mers differ in <= maxmm positions).
+// repeat predicates over a character string, CTA-wide, for ALL k at once (one lane per diagonal).
+//   isRepeat(seq,K)             (src/util.cc:295-315)  <=>  K   <= sh->scan_emax
+//   isAlmostRepeat(seq,K,max)   (src/util.cc:317-360)  <=>  K+1 <= sh->scan_wmax
+// where, over the diagonals d = i - s0 >= 1 with mismatch bits m_d[p] = (seq[p] != seq[p+d]):
+//   emax = longest run of zeros of m_d restricted to p <= len-2-d   (both offsets must be < len-K)
+//   wmax = longest window of m_d (p <= len-1-d) holding <= max ones  (kMismatch compares K+1 columns)
 // ---------------------------------------------------------------------------------------------------
-LB2_DEVNI void lb2_pair_scan(lb2_win &W, const char *s, int len, int K, int maxmm, bool want_almost)
+LB2_DEVNI void lb2_diag_scan(lb2_win &W, const char *s, int len, int maxmm)
 {
 	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
-	if (tid == 0) { sh->flag_a = 0; sh->flag_b = 0; }
+	if (tid == 0) { sh->scan_emax = 0; sh->scan_wmax = 0; }
 	lb2_sync();
-	const int end = len - K;               // offsets s0 in [0,end), partner i in (s0, end)
-	for (int s0 = (int)tid; s0 < end; s0 += (int)nt) {
-		if (lb2_ld32(&sh->flag_a) && (!want_almost || lb2_ld32(&sh->flag_b))) { break; }
-		for (int i = s0 + 1; i < end; ++i) {
-			int mm = 0, j = 0; bool exact = true;
-			// first K columns decide the exact repeat, K+1 columns the near repeat
-			for (; j < K; ++j) {
-				if (s[s0 + j] != s[i + j]) { ++mm; exact = false; if (mm > maxmm || !want_almost) { break; } }
-			}
-			if (j == K) {
-				if (exact) { sh->flag_a = 1; }
-				if (want_almost) {
-					if (s[s0 + K] != s[i + K]) { ++mm; }
-					if (mm <= maxmm) { sh->flag_b = 1; }
-				}
-			}
+	uint32_t emax = 0, wmax = 0;
+	for (int d = 1 + (int)tid; d < len; d += (int)nt) {
+		const int np = len - d;                 // positions p in [0, np)
+		int run = 0, left = 0, mm = 0;
+		for (int p = 0; p < np; ++p) {
+			int m = (s[p] != s[p + d]) ? 1 : 0;
+			if (p < np - 1) { if (m) { run = 0; } else { ++run; if ((uint32_t)run > emax) { emax = (uint32_t)run; } } }
+			mm += m;
+			while (mm > maxmm) { mm -= (s[left] != s[left + d]) ? 1 : 0; ++left; }
+			if ((uint32_t)(p - left + 1) > wmax) { wmax = (uint32_t)(p - left + 1); }
 		}
 	}
+	if (emax) { lb2_max32(&sh->scan_emax, emax); }
+	if (wmax) { lb2_max32(&sh->scan_wmax, wmax); }
 	lb2_sync();
 }
 

@@ -16,11 +16,9 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 {
 	size_t off = 0;
 #define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
-	const size_t HC = c.hash_cap, MN = (size_t)c.max_nodes + LB2_MAX_SPECIAL, MR = (size_t)c.max_reads + 2;
+	const size_t MN = (size_t)c.max_nodes + LB2_MAX_SPECIAL, MR = (size_t)c.max_reads + 2;
 	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
-	LB2_TAKE(slots, uint64_t, HC); LB2_TAKE(occ, uint32_t, HC); LB2_TAKE(cnt, uint32_t, HC * 4); LB2_TAKE(sflags, uint32_t, HC);
-	LB2_TAKE(ekey, uint32_t, HC * LB2_ECAP); LB2_TAKE(eseq, uint32_t, HC * LB2_ECAP);
-	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(slot2id, uint32_t, HC); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
+	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
 	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR);
 	LB2_TAKE(d_rep, uint32_t, MN); LB2_TAKE(d_hash, uint64_t, MN); LB2_TAKE(d_cov, float, MN * 4); LB2_TAKE(d_cnt, uint32_t, MN * 4);
@@ -41,10 +39,12 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	return (off + 255) & ~(size_t)255;
 }
 
-// shared-memory layout: lb2_sh | ref_raw[LB2_MAX_REF] | bits[max_bp/16 + 4] | lowq[max_bp/32 + 4]
-LB2_HD size_t lb2_smem_bytes(uint32_t max_bp) {
+// shared-memory layout: lb2_sh | ref_raw[LB2_MAX_REF] | bits[max_bp/16 + 4] | lowq[max_bp/32 + 4] | region T
+LB2_HD size_t lb2_smem_fixed(uint32_t max_bp) {
 	return ((sizeof(lb2_sh) + 15) & ~(size_t)15) + LB2_MAX_REF + ((size_t)max_bp / 16 + 4) * 4 + ((size_t)max_bp / 32 + 4) * 4;
 }
+LB2_HD size_t lb2_treg_bytes(uint32_t table_slots) { return (size_t)table_slots * 20; }
+LB2_HD size_t lb2_smem_bytes(uint32_t max_bp, uint32_t table_slots) { return ((lb2_smem_fixed(max_bp) + 15) & ~(size_t)15) + lb2_treg_bytes(table_slots); }
 
 LB2_DEV uint32_t lb2_first_err(uint32_t e) { for (uint32_t b = 0; b < 32; ++b) { if (e & (1u << b)) { return b; } } return 0; }
 
@@ -73,17 +73,6 @@ LB2_DEVNI void lb2_ref_coverage(lb2_win &W)
 	lb2_sync();
 }
 
-LB2_DEVNI void lb2_clear_table_full(lb2_win &W)
-{
-	lb2_ws &ws = W.ws; const unsigned tid = lb2_tid(), nt = lb2_nthr(); const uint32_t HC = W.C->hash_cap;
-	for (uint32_t s = tid; s < HC; s += nt) {
-		ws.slots[s] = 0; ws.occ[s] = 0; ws.sflags[s] = 0;
-		for (int c = 0; c < 4; ++c) { ws.cnt[s * 4 + c] = 0; }
-		for (int e = 0; e < LB2_ECAP; ++e) { ws.ekey[(size_t)s * LB2_ECAP + e] = 0; ws.eseq[(size_t)s * LB2_ECAP + e] = 0; }
-	}
-	lb2_sync();
-}
-
 LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 {
 	lb2_sh *sh = W.sh; const lb2_params *P = W.P; const unsigned tid = lb2_tid();
@@ -94,33 +83,32 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		if (P->max_unit_len > 16 || P->max_k > (int32_t)W.C->max_k) { if (tid == 0) { sh->status = LB2_WIN_UNSUPPORTED; sh->detail = LB2_D_KMAX; } lb2_sync(); }
 	}
 	if (sh->status == LB2_WIN_OK) {
-		// window pre-skip: isRepeat(rawseq, maxK)  (src/Microassembler.cc:800)
-		lb2_pair_scan(W, W.ref_raw, (int)sh->L, P->max_k, 0, false);
-		if (sh->flag_a) { if (tid == 0) { sh->status = LB2_WIN_SKIP_REPEAT; } lb2_sync(); }
-		lb2_mark(W, LB2_PH_PRESCAN);
+		// one pass over the window reference answers isRepeat / isAlmostRepeat for every k
+		lb2_diag_scan(W, W.ref_raw, (int)sh->L, P->max_mismatch);
+		if (tid == 0) {
+			sh->ref_emax = sh->scan_emax; sh->ref_wmax = sh->scan_wmax;
+			// window pre-skip: isRepeat(rawseq, maxK)  (src/Microassembler.cc:800)
+			if ((uint32_t)P->max_k <= sh->ref_emax) { sh->status = LB2_WIN_SKIP_REPEAT; }
+		}
+		lb2_sync();
+		lb2_mark(W, LB2_PH_REFSCAN);
 	}
 	if (sh->status == LB2_WIN_OK) {
-		bool ref_passed = false;
 		for (int k = P->min_k; k <= P->max_k; k += 2) {
-			if (!ref_passed) {
-				// isRepeat / isAlmostRepeat on the window reference; both are monotone in k
-				lb2_pair_scan(W, W.ref_raw, (int)sh->L, k, P->max_mismatch, true);
-				lb2_mark(W, LB2_PH_REFSCAN);
-				if (sh->flag_a || sh->flag_b) { continue; }
-				ref_passed = true;
-			}
+			// isRepeat(rawseq,k) || isAlmostRepeat(rawseq,k,MAX_MISMATCH)  (src/Microassembler.cc:118-131)
+			if ((uint32_t)k <= sh->ref_emax || (uint32_t)k + 1 <= sh->ref_wmax) { continue; }
 			lb2_build_graph(W, k);
 			if (tid == 0) { sh->n_k_tried += 1; sh->final_k = (uint32_t)k; }
 			lb2_sync();
 			lb2_mark(W, LB2_PH_CLEAR);
-			if (sh->err) { lb2_clear_table_full(W); break; }
+			if (sh->err) { break; }
 			lb2_ref_coverage(W);
 			lb2_mark(W, LB2_PH_REFCOV);
 			if (tid == 0) {
 				sh->arena_used = 8; sh->flag_c = 0;
 				lb2_order_nodes(W);
 				lb2_mark(W, LB2_PH_ORDER);
-				if (!sh->err) { lb2_remove_lowcov(W, 0); sh->numcomp = lb2_mark_components(W); }
+				if (!sh->err) { lb2_drop_dead(W); sh->numcomp = lb2_mark_components(W); }
 				lb2_mark(W, LB2_PH_LOWCOV_CC);
 			}
 			lb2_sync();
@@ -156,9 +144,9 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 					}
 					lb2_sync();
 					if (sh->err || !sh->path_found) { break; }
-					lb2_pair_scan(W, W.ws.pathseq, (int)sh->plen, k, P->max_mismatch, true);
+					lb2_diag_scan(W, W.ws.pathseq, (int)sh->plen, P->max_mismatch);
 					lb2_mark(W, LB2_PH_PATHSCAN);
-					if (sh->flag_b) { rpt = true; break; }
+					if ((uint32_t)k + 1 <= sh->scan_wmax) { rpt = true; break; }
 					if (tid == 0) { lb2_flag_path(W, 1); }
 					++nflag;
 					lb2_sync();

@@ -40,8 +40,7 @@ struct lb2_trans {                // Transcript_t (reference src/Transcript.hh:3
 // pointers into this CTA's global-memory slab (identical layout for every CTA)
 struct lb2_ws {
 	// --- build stage, slot indexed ---
-	uint64_t *slots; uint32_t *occ; uint32_t *cnt; uint32_t *sflags; uint32_t *ekey; uint32_t *eseq;
-	uint32_t *used; uint32_t *slot2id; uint64_t *sortk; uint32_t *inst; uint32_t *mates;
+	uint32_t *used; uint64_t *sortk; uint32_t *inst; uint32_t *mates; uint32_t *bseq;
 	// --- reads ---
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
 	// --- dense nodes ---
@@ -72,7 +71,7 @@ struct lb2_sh {
 	int32_t  K, nw;
 	uint32_t n_used, n_nodes, n_spec, err;
 	uint32_t totalreadbp;
-	uint32_t flag_a, flag_b, flag_c;
+	uint32_t flag_a, flag_b, flag_c; uint32_t scan_emax, scan_wmax, ref_emax, ref_wmax;
 	// reference trimming state (Ref_t::seq/trim5/trim3, persists across k: SURVEY B4)
 	uint32_t seq_off, seq_len; uint32_t trim5, trim3;
 	// order emulation

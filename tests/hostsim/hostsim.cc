@@ -37,20 +37,21 @@ int main(int argc, char **argv)
 	rd(f, flags, R); rd(f, name_rank, R); rd(f, ref_seq, nref); rd(f, seq, nbase); rd(f, qual, nbase); fclose(f);
 
 	lb2_cfg C; memset(&C, 0, sizeof C);
-	C.hash_cap = 16384; C.max_nodes = 8000; C.max_reads = 8192; C.max_bp = 1 << 20; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
+	C.table_slots = 16384; C.max_nodes = 12000; C.max_reads = 8192; C.max_bp = (1 << 18) - 1024; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
 	C.queue_cap = 1 << 18; C.max_inst = 1 << 18; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
 	B.base_off = base_off.data(); B.flags = flags.data(); B.name_rank = name_rank.data(); B.ref_seq = ref_seq.data(); B.seq = seq.data(); B.qual = qual.data();
 	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
 	lb2_dev_out O; O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);
-	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp), 0);
+	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp, C.table_slots) + 64, 0);
 	lb2_win Wn; Wn.P = &P; Wn.C = &C; Wn.B = &B; Wn.O = &O;
 	lb2_ws_layout(C, slab.data(), &Wn.ws);
 	Wn.sh = (lb2_sh *)smem.data();
 	Wn.ref_raw = (char *)smem.data() + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
 	Wn.bits = (uint32_t *)(Wn.ref_raw + LB2_MAX_REF);
 	Wn.lowq = Wn.bits + (C.max_bp / 16 + 4);
+	Wn.treg = smem.data() + ((lb2_smem_fixed(C.max_bp) + 15) & ~(size_t)15);
 	int w1 = count < 0 ? (int)W : std::min((int)W, first + count);
 	FILE *fo = out ? fopen(out, "w") : stdout;
 	for (int w = first; w < w1; ++w) {
