@@ -17,7 +17,7 @@
 
 struct lb2_win {
 	const lb2_params *P; const lb2_cfg *C; const lb2_dev_batch *B; const lb2_dev_out *O;
-	lb2_ws ws; lb2_sh *sh;
+	lb2_ws ws, ws0; lb2_sh *sh;
 	uint32_t *bits;      // smem: 2-bit packed trimmed reads, then the window reference
 	uint32_t *lowq;      // smem: 1 bit per staged base: quality < MIN_QUAL_CALL
 	char     *ref_raw;   // smem: window reference, ASCII
@@ -34,6 +34,30 @@ LB2_DEV void lb2_mark(lb2_win &W, int ph) {
 
 LB2_DEV void lb2_fail(lb2_win &W, uint32_t status, uint32_t detail) {
 	if (lb2_cas32(&W.sh->status, LB2_WIN_OK, status) == LB2_WIN_OK) { W.sh->detail = detail; }
+}
+
+// low-quality mask (quality < MIN_QUAL_CALL) of the staged bases.  The mask's shared memory is lent to the
+// graph stage after every build, so it is staged again before the build of a later k.
+LB2_DEVNI void lb2_stage_lowq(lb2_win &W)
+{
+	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
+	const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t R = sh->R; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
+	const int qcall = W.P->min_qual_call;
+	for (uint32_t r = tid; r < R; r += nt) {
+		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
+		const char *q = B->qual + B->base_off[widx[r]] + ws.rd_t5[r];
+		uint32_t g = ws.rd_start[r], anylow = 0;
+		for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+			uint32_t lw = 0, m = (n - b0 < 32) ? (n - b0) : 32;
+			for (uint32_t i = 0; i < m; ++i) { if (q[b0 + i] < qcall) { lw |= 1u << i; } }
+			W.lowq[(g + b0) >> 5] = lw; anylow |= lw;
+		}
+		if (anylow) { lb2_or32(&sh->has_lowq, 1u); }
+	}
+	for (uint32_t b0 = tid * 32; b0 < ((sh->L + 31u) & ~31u) + 64; b0 += nt * 32) { W.lowq[(sh->ref_g + b0) >> 5] = 0; }
+	if (tid == 0) { sh->lowq_live = 1; }
+	lb2_sync();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -113,33 +137,26 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		}
 		lb2_sync();
 	}
-	const int qcall = W.P->min_qual_call;
 	for (uint32_t r = tid; r < R; r += nt) {
 		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
 		uint32_t idx = widx[r];
 		uint64_t o0 = B->base_off[idx] + ws.rd_t5[r];
-		const char *s = B->seq + o0; const char *q = B->qual + o0;
+		const char *s = B->seq + o0;
 		uint32_t g = ws.rd_start[r];
-		uint32_t anylow = 0;
 		for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-			uint64_t bw = 0; uint32_t lw = 0;
+			uint64_t bw = 0;
 			uint32_t m = (n - b0 < 32) ? (n - b0) : 32;
-			for (uint32_t i = 0; i < m; ++i) {
-				bw |= (uint64_t)lb2_code(s[b0 + i]) << (2 * i);
-				if (q[b0 + i] < qcall) { lw |= 1u << i; }
-			}
+			for (uint32_t i = 0; i < m; ++i) { bw |= (uint64_t)lb2_code(s[b0 + i]) << (2 * i); }
 			W.bits[(g + b0) >> 4] = (uint32_t)bw; W.bits[((g + b0) >> 4) + 1] = (uint32_t)(bw >> 32);
-			W.lowq[(g + b0) >> 5] = lw; anylow |= lw;
 		}
-		if (anylow) { lb2_or32(&sh->has_lowq, 1u); }
 	}
+	lb2_stage_lowq(W);
 	{
 		uint32_t g = sh->ref_g;
 		for (uint32_t b0 = tid * 32; b0 < ((L + 31u) & ~31u) + 64; b0 += nt * 32) {
 			uint64_t bw = 0;
 			for (uint32_t i = 0; i < 32 && b0 + i < L; ++i) { bw |= (uint64_t)(lb2_code(W.ref_raw[b0 + i]) & 3) << (2 * i); }
 			W.bits[(g + b0) >> 4] = (uint32_t)bw; W.bits[((g + b0) >> 4) + 1] = (uint32_t)(bw >> 32);
-			W.lowq[(g + b0) >> 5] = 0;
 		}
 	}
 	lb2_sync();
@@ -147,7 +164,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 
 // ---------------------------------------------------------------------------------------------
 // Mer -> Node table in SHARED memory (region T), TS = cfg.table_slots slots, per slot:
-//   t_key  u32  0x80000000 | fingerprint12 << 19 | (g << 1 | ori): g = staged base index of one
+//   t_key  u32  0x80000000 | fingerprint10 << 21 | (g << 1 | ori): g = staged base index of one
 //               representative occurrence (matches are verified against the packed bases)
 //   t_occ  u32  0xFFFFFFFF - first occurrence (atomicMax); after the sort: dense node id
 //   t_cnt  2xu32  tumour / normal occurrence counts, fwd in the low half, rev in the high half
@@ -163,7 +180,7 @@ LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2
 	uint32_t *tk = W.t_key; const uint32_t mask = W.C->table_slots - 1;
 	uint64_t h = lb2_table_hash(canon, nw);
 	uint32_t i = (uint32_t)h & mask;
-	const uint32_t fp = 0x80000000u | (((uint32_t)(h >> 40) & 0xFFFu) << 19);
+	const uint32_t fp = 0x80000000u | (((uint32_t)(h >> 40) & 0x3FFu) << 21);
 	for (uint32_t probes = 0; probes <= mask; ++probes) {
 		uint32_t cur = lb2_ld32(&tk[i]);
 		if (cur == 0) {
@@ -176,8 +193,8 @@ LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2
 			}
 			cur = prev;
 		}
-		if ((cur & 0xFFF80000u) == fp) {
-			uint32_t r = cur & 0x7FFFFu;
+		if ((cur & 0xFFE00000u) == fp) {
+			uint32_t r = cur & 0x1FFFFFu;
 			lb2_kmer o; lb2_extract(W.bits, r >> 1, K, o);
 			if (lb2_equal(o, (r & 1) ? nonc : canon, nw)) { return i; }
 		}
@@ -276,8 +293,7 @@ LB2_DEV void lb2_revcomp(const lb2_kmer &f, int K, lb2_kmer &rc) {
 	}
 }
 // canonical k-mer of a dense node (from its representative occurrence)
-LB2_DEV void lb2_node_kmer(lb2_win &W, uint32_t id, int K, lb2_kmer &km) {
-	uint32_t rep = W.ws.d_rep[id];
+LB2_DEV void lb2_rep_kmer(lb2_win &W, uint32_t rep, int K, lb2_kmer &km) {
 	lb2_extract(W.bits, rep >> 1, K, km);
 	if (rep & 1) { lb2_kmer t; lb2_revcomp(km, K, t); km = t; }
 }
@@ -294,6 +310,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const int nw = lb2_nw(K);
 	const uint32_t R = sh->R, L = sh->L, TS = C->table_slots;
+	if (!sh->lowq_live && sh->has_lowq) { lb2_stage_lowq(W); }
 	W.t_key = (uint32_t *)W.treg; W.t_occ = W.t_key + TS; W.t_cnt = W.t_occ + TS; W.t_em = W.t_cnt + 2 * (size_t)TS;
 	if (tid == 0) {
 		uint32_t cum = 0;
@@ -334,18 +351,17 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	lb2_sync();
 	for (uint32_t j = tid; j < n; j += nt) {
 		uint32_t s = ws.used[j];
-		uint32_t rep = W.t_key[s] & 0x7FFFFu;
-		ws.d_rep[j] = rep;
-		lb2_kmer km; lb2_node_kmer(W, j, K, km);
-		ws.d_hash[j] = lb2_stdhash_kmer(km, K);
+		uint32_t rep = W.t_key[s] & 0x1FFFFFu;
+		ws.b_rep[j] = rep;
+		lb2_kmer km; lb2_rep_kmer(W, rep, K, km);
+		ws.b_hash[j] = lb2_stdhash_kmer(km, K);
 		uint32_t ct = W.t_cnt[s * 2], cn = W.t_cnt[s * 2 + 1];
 		uint32_t v[4] = { ct & 0xFFFFu, ct >> 16, cn & 0xFFFFu, cn >> 16 }, tot = 0;
-		for (int c = 0; c < 4; ++c) { ws.d_cov[j * 4 + c] = (float)v[c]; ws.d_cnt[j * 4 + c] = v[c]; tot += v[c]; }
+		for (int c = 0; c < 4; ++c) { ws.b_cnt[j * 4 + c] = v[c]; tot += v[c]; }
 		uint32_t em = W.t_em[s];
-		ws.d_stn[j] = 1; ws.d_stT[j] = ((em & (LB2_EM_NORMAL | LB2_EM_TUMOR)) == LB2_EM_TUMOR) ? 1u : 0u;   // cov_status 'T': tumour-qualified, never normal
-		ws.d_mincov[j] = (int32_t)tot; ws.d_mincovqv[j] = (int32_t)tot;
-		ws.d_flags[j] = 0; ws.d_comp[j] = 0; ws.d_color[j] = 0; ws.d_ne[j] = 0;
-		ws.d_str[j] = LB2_NIL; ws.d_len[j] = (uint32_t)K; ws.d_cd[j] = LB2_NIL;
+		ws.b_stT[j] = ((em & (LB2_EM_NORMAL | LB2_EM_TUMOR)) == LB2_EM_TUMOR) ? 1u : 0u;   // cov_status 'T': tumour-qualified, never normal
+		ws.b_mincovqv[j] = (int32_t)tot;
+		ws.b_flags[j] = 0; ws.b_ne[j] = 0;
 	}
 	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t s = ws.refnode[p]; if (s != LB2_NIL) { ws.refnode[p] = W.t_occ[s]; } }
 	if (tid == 0) { sh->n_nodes = n; sh->last_nodes = n; }
@@ -362,14 +378,14 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)W.t_occ[ws.inst[x] & 0x3FFFFFFFu] << 32) | x) : ~0ull; }
 		lb2_sync();
 		lb2_sort64(ws.sortk, t2);
-		uint32_t *nstart = ws.stack;
+		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
 		for (uint32_t x = tid; x < total; x += nt) {
 			uint32_t nd = (uint32_t)(ws.sortk[x] >> 32);
 			if (x == 0 || (uint32_t)(ws.sortk[x - 1] >> 32) != nd) { nstart[nd] = x; }
 		}
 		lb2_sync();
 		for (uint32_t j = tid; j < n; j += nt) {
-			uint32_t tot = 0; for (int c = 0; c < 4; ++c) { tot += ws.d_cnt[j * 4 + c]; }
+			uint32_t tot = 0; for (int c = 0; c < 4; ++c) { tot += ws.b_cnt[j * 4 + c]; }
 			if (!tot) { continue; }
 			uint32_t b0 = nstart[j];
 			uint32_t *L1 = ws.mates + 2 * (size_t)b0; uint32_t *L2top = ws.mates + 2 * (size_t)b0 + 2 * (size_t)tot - 1;   // list 2 grows downwards
@@ -391,14 +407,14 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					uint32_t cnt_other = (mate == 1) ? n2_ : n1;
 					bool ovl = false;
 					if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
-					if (ovl) { ws.inst[s_] |= 0x40000000u; ws.d_cnt[j * 4 + cls] -= 1; }
+					if (ovl) { ws.inst[s_] |= 0x40000000u; ws.b_cnt[j * 4 + cls] -= 1; }
 					uint32_t last = ws.rd_len[r] - (uint32_t)K;
 					uint32_t pushes = (p == 0 || p == last) ? 1u : 2u;
 					for (uint32_t q = 0; q < pushes; ++q) { if (mate == 1) { L1[n1++] = name; } else { *(L2top - n2_) = name; ++n2_; } }
 				}
 			}
-			uint32_t t = 0; for (int c = 0; c < 4; ++c) { uint32_t v = ws.d_cnt[j * 4 + c]; ws.d_cov[j * 4 + c] = (float)v; t += v; }
-			ws.d_mincov[j] = (int32_t)t; ws.d_mincovqv[j] = (int32_t)t;
+			uint32_t t = 0; for (int c = 0; c < 4; ++c) { t += ws.b_cnt[j * 4 + c]; }
+			ws.b_mincovqv[j] = (int32_t)t;
 		}
 		lb2_sync();
 	}
@@ -433,7 +449,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					uint32_t t = (a & 0xFFFF) + (a >> 16) + (b & 0xFFFF) + (b >> 16);
 					if (t > mx) { mx = t; }
 				}
-				ws.d_mincovqv[j] -= (int32_t)mx;
+				ws.b_mincovqv[j] -= (int32_t)mx;
 			}
 		}
 	}
@@ -446,17 +462,17 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
 		double thr = W.P->min_cov_ratio * avgcov;
 		for (uint32_t j = tid; j < n; j += nt) {
-			int mq = ws.d_mincovqv[j];
-			float tt = ws.d_cov[j * 4 + 0] + ws.d_cov[j * 4 + 1], tn = ws.d_cov[j * 4 + 2] + ws.d_cov[j * 4 + 3];
-			if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { ws.d_flags[j] = LB2_NF_DEAD; }
+			int mq = ws.b_mincovqv[j];
+			float tt = (float)ws.b_cnt[j * 4 + 0] + (float)ws.b_cnt[j * 4 + 1], tn = (float)ws.b_cnt[j * 4 + 2] + (float)ws.b_cnt[j * 4 + 3];
+			if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { ws.b_flags[j] = LB2_NF_DEAD; }
 		}
 	}
 	lb2_sync();
 	// ---- edges of the survivors: every edge type (start orientation, appended base) names one neighbour
 	for (uint32_t j = tid; j < n; j += nt) {
-		if (ws.d_flags[j] & LB2_NF_DEAD) { continue; }
+		if (ws.b_flags[j] & LB2_NF_DEAD) { continue; }
 		uint32_t s = ws.used[j]; uint32_t em = W.t_em[s] & 0xFFu;
-		lb2_kmer C0; lb2_node_kmer(W, j, K, C0);
+		lb2_kmer C0; lb2_rep_kmer(W, ws.b_rep[j], K, C0);
 		lb2_kmer C1; lb2_revcomp(C0, K, C1);
 		int ne = 0, nF = 0, nR = 0;
 		for (int t = 0; t < 8; ++t) {
@@ -468,11 +484,11 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			uint32_t ts = lb2_find_or_insert(W, fl ? V : Vr, fl ? Vr : V, 0, K, nw, false);
 			if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); break; }
 			uint32_t to = W.t_occ[ts];
-			if (ws.d_flags[to] & LB2_NF_DEAD) { continue; }
-			lb2_edge ed; ed.to = to; ed.dir = (uint8_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.pad = (uint16_t)t;
-			ws.d_edge[(size_t)j * LB2_ECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
+			if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
+			lb2_bedge ed; ed.to = to; ed.dir = (uint32_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.type = (uint32_t)t;
+			ws.b_edge[(size_t)j * LB2_BECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
 		}
-		ws.d_ne[j] = (uint8_t)ne;
+		ws.b_ne[j] = (uint8_t)ne;
 		if (nF > 1 || nR > 1) {   // first-seen order matters only among edges leaving in the same orientation
 			lb2_or32(&W.t_em[s], LB2_EM_BRANCH); sh->flag_a = 1;
 			for (int t = 0; t < 8; ++t) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
@@ -502,10 +518,10 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		lb2_sync();
 		for (uint32_t j = tid; j < n; j += nt) {
 			if (!(W.t_em[ws.used[j]] & LB2_EM_BRANCH)) { continue; }
-			lb2_edge *e = ws.d_edge + (size_t)j * LB2_ECAP; int ne = ws.d_ne[j];
+			lb2_bedge *e = ws.b_edge + (size_t)j * LB2_BECAP; int ne = ws.b_ne[j];
 			for (int a = 1; a < ne; ++a) {
-				lb2_edge x = e[a]; uint32_t sx = ws.bseq[(size_t)j * 8 + x.pad]; int b = a - 1;
-				while (b >= 0 && ws.bseq[(size_t)j * 8 + e[b].pad] > sx) { e[b + 1] = e[b]; --b; }
+				lb2_bedge x = e[a]; uint32_t sx = ws.bseq[(size_t)j * 8 + x.type]; int b = a - 1;
+				while (b >= 0 && ws.bseq[(size_t)j * 8 + e[b].type] > sx) { e[b + 1] = e[b]; --b; }
 				e[b + 1] = x;
 			}
 		}

@@ -10,7 +10,7 @@
 #define LB2_ECAP         12         // half-edges per node (8 possible k-mer neighbours + specials)
 #define LB2_MAX_REF      1024       // max window reference length
 #define LB2_MAX_PATH     2304       // max assembled path length (reflen + MAX_INDEL_LEN + slack)
-#define LB2_MAX_SPECIAL  128        // source/sink nodes per (window,k)
+#define LB2_MAX_SPECIAL  32         // source/sink nodes per (window,k)
 #define LB2_MAX_TRANS    64         // transcripts per path
 #define LB2_MAX_PNODES   512        // nodes per path
 

@@ -29,7 +29,7 @@ lb2_window_kernel(const lb2_launch *Lp)
 	__shared__ uint32_t s_next;
 	lb2_win W;
 	W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O;
-	lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws);
+	lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws); W.ws0 = W.ws;
 	W.sh = (lb2_sh *)smem;
 	W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
 	W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);

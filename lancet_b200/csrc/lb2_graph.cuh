@@ -41,7 +41,7 @@ LB2_DEV lb2_cov lb2_node_cov(lb2_win &W, uint32_t id, uint32_t i, int sample /*0
 		uint32_t f = ws.d_cnt[id * 4 + sample * 2], r = ws.d_cnt[id * 4 + sample * 2 + 1];
 		uint32_t df = 0, dr = 0;
 		if (W.sh->has_lowq) {
-			uint32_t v = ((const uint32_t *)ws.deficit)[((size_t)id * W.sh->K + i) * 2 + sample];
+			uint32_t v = ((const uint32_t *)ws.deficit)[((size_t)ws.d_orig[id] * W.sh->K + i) * 2 + sample];
 			df = v & 0xFFFF; dr = v >> 16;
 		}
 		c.fwd = (uint16_t)f; c.rev = (uint16_t)r; c.mqf = (uint16_t)(f - df); c.mqr = (uint16_t)(r - dr);
@@ -71,13 +71,14 @@ LB2_DEV void lb2_oe_reset(lb2_win &W) {
 	lb2_sh *sh = W.sh; sh->bkt_count = 1; sh->elem_count = 0; sh->next_resize = 0; sh->lhead = LB2_NIL;
 	W.ws.buckets[0] = LB2_NIL;
 }
-LB2_DEV void lb2_oe_rehash(lb2_win &W, uint32_t nb) {   // _M_rehash_aux (unique keys)
+LB2_DEV void lb2_oe_rehash(lb2_win &W, uint32_t nb) {   // _M_rehash_aux (unique keys); rare here (only a source/sink insert can trigger it)
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	if (nb > W.sh->bkt_cap) { sh->err |= 1u << LB2_D_BUCKETS; return; }
 	for (uint32_t b = 0; b < nb; ++b) { ws.buckets[b] = LB2_NIL; }
 	uint32_t p = sh->lhead; sh->lhead = LB2_NIL; uint32_t bbegin = 0;
 	while (p != LB2_NIL) {
 		uint32_t nx = ws.d_lnext[p];
-		uint32_t b = (uint32_t)(ws.d_hash[p] % nb);
+		uint32_t b = (uint32_t)(ws.d_hash[p] % nb); ws.d_bk[p] = b;
 		if (ws.buckets[b] == LB2_NIL) {
 			ws.d_lnext[p] = sh->lhead; sh->lhead = p; ws.buckets[b] = LB2_SENT;
 			if (ws.d_lnext[p] != LB2_NIL) { ws.buckets[bbegin] = p; }
@@ -98,36 +99,37 @@ LB2_DEV void lb2_oe_insert(lb2_win &W, uint32_t id) {   // _M_insert_unique_node
 		if (min_bkts >= sh->bkt_count) {
 			uint32_t want = min_bkts + 1; if (want < sh->bkt_count * 2) { want = sh->bkt_count * 2; }
 			uint32_t nb = lb2_oe_next_bkt(want);
-			if (nb == 0 || nb > W.C->bucket_cap) { sh->err |= 1u << LB2_D_BUCKETS; return; }
+			if (nb == 0) { sh->err |= 1u << LB2_D_BUCKETS; return; }
 			sh->next_resize = nb;
 			lb2_oe_rehash(W, nb);
+			if (sh->err) { return; }
 		} else { sh->next_resize = sh->bkt_count; }
 	}
-	uint32_t b = (uint32_t)(ws.d_hash[id] % sh->bkt_count);
+	uint32_t b = (uint32_t)(ws.d_hash[id] % sh->bkt_count); ws.d_bk[id] = b;
 	if (ws.buckets[b] != LB2_NIL) {
 		uint32_t before = ws.buckets[b];
 		ws.d_lnext[id] = lb2_oe_next(W, before); lb2_oe_setnext(W, before, id);
 	} else {
 		ws.d_lnext[id] = sh->lhead; sh->lhead = id;
-		if (ws.d_lnext[id] != LB2_NIL) { ws.buckets[(uint32_t)(ws.d_hash[ws.d_lnext[id]] % sh->bkt_count)] = id; }
+		if (ws.d_lnext[id] != LB2_NIL) { ws.buckets[ws.d_bk[ws.d_lnext[id]]] = id; }
 		ws.buckets[b] = LB2_SENT;
 	}
 	sh->elem_count = n + 1;
 }
 LB2_DEV void lb2_oe_erase(lb2_win &W, uint32_t id) {    // _M_erase(bkt, prev, n)
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
-	uint32_t B = sh->bkt_count, b = (uint32_t)(ws.d_hash[id] % B);
+	uint32_t b = ws.d_bk[id];
 	uint32_t prev = ws.buckets[b];
 	while (lb2_oe_next(W, prev) != id) { prev = lb2_oe_next(W, prev); }
 	uint32_t nx = ws.d_lnext[id];
 	if (prev == ws.buckets[b]) {
-		uint32_t nb = (nx != LB2_NIL) ? (uint32_t)(ws.d_hash[nx] % B) : 0;
+		uint32_t nb = (nx != LB2_NIL) ? ws.d_bk[nx] : 0;
 		if (nx == LB2_NIL || nb != b) {
 			if (nx != LB2_NIL) { ws.buckets[nb] = ws.buckets[b]; }
 			ws.buckets[b] = LB2_NIL;   // (before_begin.next is updated by the unlink below)
 		}
 	} else if (nx != LB2_NIL) {
-		uint32_t nb = (uint32_t)(ws.d_hash[nx] % B);
+		uint32_t nb = ws.d_bk[nx];
 		if (nb != b) { ws.buckets[nb] = prev; }
 	}
 	lb2_oe_setnext(W, prev, nx);
@@ -149,14 +151,14 @@ LB2_DEV void lb2_remove_edge(lb2_win &W, uint32_t id, uint32_t to, int dir) {
 LB2_DEV void lb2_update_edge(lb2_win &W, uint32_t id, uint32_t oldto, int olddir, uint32_t newto, int newdir) {
 	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) {
-		if (e[i].to == oldto && e[i].dir == olddir) { e[i].to = newto; e[i].dir = (uint8_t)newdir; return; }
+		if (e[i].to == oldto && e[i].dir == olddir) { e[i].to = (uint16_t)newto; e[i].dir = (uint16_t)newdir; return; }
 	}
 	W.sh->err |= 1u << LB2_D_EDGES;
 }
 LB2_DEV void lb2_push_edge(lb2_win &W, uint32_t id, uint32_t to, int dir, int flag) {
 	lb2_ws &ws = W.ws; int ne = ws.d_ne[id];
 	if (ne >= LB2_ECAP) { W.sh->err |= 1u << LB2_D_EDGES; return; }
-	lb2_edge ed; ed.to = to; ed.dir = (uint8_t)dir; ed.flag = (uint8_t)flag; ed.pad = 0;
+	lb2_edge ed; ed.to = (uint16_t)to; ed.dir = (uint16_t)dir; ed.flag = (uint16_t)flag; ed.pad = 0;
 	ws.d_edge[(size_t)id * LB2_ECAP + ne] = ed; ws.d_ne[id] = (uint8_t)(ne + 1);
 }
 LB2_DEV void lb2_add_edge_node(lb2_win &W, uint32_t id, uint32_t to, int dir) {   // Node_t::addEdge without read ids
@@ -239,12 +241,121 @@ LB2_DEV bool lb2_find_tandems(GetC getc, uint32_t slen, const lb2_params *P, int
 // ---------------------------------------------------------------------------------------------------
 // sequential stages (lane 0)
 // ---------------------------------------------------------------------------------------------------
-LB2_DEVNI void lb2_order_nodes(lb2_win &W) {
-	lb2_oe_reset(W);
-	for (uint32_t j = 0; j < W.sh->n_nodes; ++j) { lb2_oe_insert(W, j); if (W.sh->err) { return; } }
+// ---------------------------------------------------------------------------------------------------
+// Iteration order of the reference's unordered_map over ALL nodes (insertion order = dense id), the
+// first low-coverage sweep, and the hand-over to the graph stage:
+//  1. emulate the map in shared memory with 16-bit links.  The bucket count only changes when element
+//     number B+1 arrives (13, 29, 59, ... SURVEY App. D), so the work is done level by level: all lanes
+//     compute hash % B for the level, lane 0 relinks (rehash) and inserts the level's elements;
+//  2. survivors of removeLowCov(false,0) get compact "row" ids; lane 0 walks the emulated list, drops the
+//     dead nodes (unordered_map::erase keeps the relative order) and rebuilds the bucket heads;
+//  3. the hot per-node arrays of the graph stage are laid out in shared memory (the region that held
+//     the low-quality mask and the Mer->Node table) and filled from the build-space arrays.
+// ---------------------------------------------------------------------------------------------------
+LB2_DEV uint32_t lb2_level_bkt(uint32_t n_before) {   // bucket count in force while inserting element index n_before (0-based)
+	const uint32_t chain[] = { 13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753, 42043, 85229, 172933 };
+	for (int i = 0; i < 14; ++i) { if (n_before < chain[i]) { return chain[i]; } }
+	return 0;
 }
-// the nodes condemned by the first low-coverage sweep leave the map (cleanDead of removeLowCov(false,0))
-LB2_DEVNI void lb2_drop_dead(lb2_win &W) { lb2_clean_dead(W); }
+
+LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t n = sh->n_nodes;
+	const uint32_t Bfinal = n ? lb2_level_bkt(n - 1) : 13;
+	// graph region: [low-quality mask | table region], both dead now
+	uint8_t *G = (uint8_t *)W.lowq; const size_t Gbytes = (size_t)(W.treg - (uint8_t *)W.lowq) + lb2_treg_bytes(W.C->table_slots);
+	// all-node emulation arrays sit at the END of the region, row arrays grow from the start
+	const size_t an_bytes = ((size_t)n * 2 * 2 + (size_t)Bfinal * 2 + 15) & ~(size_t)15;
+	if (Bfinal == 0 || n >= 0xFFF0u || an_bytes > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
+	uint16_t *a_next = (uint16_t *)(G + Gbytes - an_bytes), *a_bk = a_next + n, *a_bkt = a_bk + n;
+	const uint16_t NIL16 = 0xFFFF, SENT16 = 0xFFFE;
+	if (tid == 0) { sh->lhead = NIL16; sh->lowq_live = 0; }
+	uint32_t done = 0;
+	while (done < n) {
+		const uint32_t B = lb2_level_bkt(done); uint32_t end = B < n ? B : n;     // elements [done, end) arrive at this bucket count
+		for (uint32_t j = tid; j < end; j += nt) { a_bk[j] = (uint16_t)(ws.b_hash[j] % B); }
+		for (uint32_t b = tid; b < B; b += nt) { a_bkt[b] = NIL16; }
+		lb2_sync();
+		if (tid == 0) {
+			uint32_t head = sh->lhead;
+			// _M_rehash_aux over the current list
+			uint32_t p = head; head = NIL16; uint32_t bbegin = 0;
+			while (p != NIL16) {
+				uint32_t nx = a_next[p], b = a_bk[p];
+				if (a_bkt[b] == NIL16) { a_next[p] = (uint16_t)head; head = p; a_bkt[b] = SENT16; if (a_next[p] != NIL16) { a_bkt[bbegin] = (uint16_t)p; } bbegin = b; }
+				else { uint32_t before = a_bkt[b]; if (before == SENT16) { a_next[p] = (uint16_t)head; head = p; } else { a_next[p] = a_next[before]; a_next[before] = (uint16_t)p; } }
+				p = nx;
+			}
+			// _M_insert_bucket_begin for the new elements
+			for (uint32_t id = done; id < end; ++id) {
+				uint32_t b = a_bk[id];
+				if (a_bkt[b] != NIL16) { uint32_t before = a_bkt[b]; if (before == SENT16) { a_next[id] = (uint16_t)head; head = id; } else { a_next[id] = a_next[before]; a_next[before] = (uint16_t)id; } }
+				else { a_next[id] = (uint16_t)head; head = id; if (a_next[id] != NIL16) { a_bkt[a_bk[a_next[id]]] = (uint16_t)id; } a_bkt[b] = SENT16; }
+			}
+			sh->lhead = head;
+		}
+		done = end;
+		lb2_sync();
+	}
+	lb2_mark(W, LB2_PH_ORDER);
+	// ---- rows for the survivors (dense-id order), layout of the row-space arrays
+	if (tid == 0) {
+		uint32_t r = 0;
+		for (uint32_t j = 0; j < n; ++j) { if (ws.b_flags[j] & LB2_NF_DEAD) { ws.b_row[j] = LB2_NIL; } else { ws.b_row[j] = r++; } }
+		sh->n_rows = r; sh->n_spec = 0;
+	}
+	lb2_sync();
+	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
+	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
+	{
+		size_t off = 0;
+#define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; ws.field = (type *)(G + off); off += sizeof(type) * (size_t)(count); } while (0)
+		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint32_t, bcap);
+		LB2_GT(d_cov, float, NT * 4); LB2_GT(d_len, uint32_t, NT); LB2_GT(d_stn, uint32_t, NT); LB2_GT(d_stT, uint32_t, NT);
+		LB2_GT(d_comp, int32_t, NT); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(d_edge, lb2_edge, NT * LB2_ECAP);
+		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT);
+#undef LB2_GT
+		ws.chain = ws.stack;
+		if (NT > LB2_MAX_ROWS || off + an_bytes > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
+	}
+	if (tid == 0) { sh->bkt_cap = bcap; sh->bkt_count = Bfinal; sh->next_resize = Bfinal; sh->elem_count = NR; }
+	const int K = sh->K;
+	for (uint32_t j = tid; j < n; j += nt) {
+		uint32_t r = ws.b_row[j]; if (r == LB2_NIL) { continue; }
+		ws.d_bk[r] = a_bk[j];
+		uint32_t tot = 0;
+		for (int c = 0; c < 4; ++c) { uint32_t v = ws.b_cnt[j * 4 + c]; ws.d_cov[r * 4 + c] = (float)v; ws.d_cnt[r * 4 + c] = v; tot += v; }
+		ws.d_len[r] = (uint32_t)K; ws.d_stn[r] = 1; ws.d_stT[r] = ws.b_stT[j]; ws.d_comp[r] = 0;
+		ws.d_flags[r] = 0; ws.d_color[r] = 0;
+		ws.d_rep[r] = ws.b_rep[j]; ws.d_hash[r] = ws.b_hash[j]; ws.d_orig[r] = j;
+		ws.d_mincov[r] = (int32_t)tot; ws.d_mincovqv[r] = ws.b_mincovqv[j]; ws.d_str[r] = LB2_NIL; ws.d_cd[r] = LB2_NIL;
+		int ne = ws.b_ne[j];
+		for (int e = 0; e < ne; ++e) {
+			lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e];
+			lb2_edge ed; ed.to = (uint16_t)ws.b_row[be.to]; ed.dir = (uint16_t)be.dir; ed.flag = 0; ed.pad = 0;
+			ws.d_edge[(size_t)r * LB2_ECAP + e] = ed;
+		}
+		ws.d_ne[r] = (uint8_t)ne;
+	}
+	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t j = ws.refnode[p]; if (j != LB2_NIL) { ws.refnode[p] = ws.b_row[j]; } }
+	for (uint32_t b = tid; b < bcap; b += nt) { ws.buckets[b] = LB2_NIL; }
+	lb2_sync();
+	if (tid == 0) {
+		// translate the list to row ids, dropping the dead; rebuild the bucket heads (before-begin pointers)
+		uint32_t prev = LB2_SENT; uint32_t head = LB2_NIL;
+		for (uint32_t p = sh->lhead; p != NIL16; p = a_next[p]) {
+			uint32_t r = ws.b_row[p]; if (r == LB2_NIL) { continue; }
+			if (prev == LB2_SENT) { head = r; } else { ws.d_lnext[prev] = r; }
+			uint32_t b = ws.d_bk[r]; if (ws.buckets[b] == LB2_NIL) { ws.buckets[b] = prev; }
+			prev = r;
+		}
+		if (prev != LB2_SENT) { ws.d_lnext[prev] = LB2_NIL; }
+		sh->lhead = head;
+	}
+	lb2_sync();
+	lb2_mark(W, LB2_PH_LOWCOV_CC);
+}
 
 // removeLowCov(docompression=false path and the sweep part) src/Graph.cc:2790-2827
 LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
@@ -264,7 +375,7 @@ LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
 LB2_DEVNI int lb2_mark_components(lb2_win &W) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) { ws.d_comp[p] = 0; }
-	int comp = 0; uint32_t *Q = ws.stack;   // FIFO; every edge is pushed at most once per labelled node
+	int comp = 0; uint32_t *Q = ws.stack;   // FIFO; every node is pushed once
 	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
 		if (ws.d_comp[p] != 0) { continue; }
 		++comp;
@@ -282,7 +393,7 @@ LB2_DEVNI int lb2_mark_components(lb2_win &W) {
 LB2_DEV uint32_t lb2_new_special(lb2_win &W, bool source, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	if (sh->n_spec >= LB2_MAX_SPECIAL) { sh->err |= 1u << LB2_D_SPECIAL; return LB2_NIL; }
-	uint32_t id = W.C->max_nodes + sh->n_spec++;
+	uint32_t id = sh->n_rows + sh->n_spec++;
 	char buf[24]; int n = 0;
 	const char *pre = source ? "source" : "sink";
 	while (*pre) { buf[n++] = *pre++; }
@@ -290,7 +401,7 @@ LB2_DEV uint32_t lb2_new_special(lb2_win &W, bool source, int compid) {
 	while (nd) { buf[n++] = dig[--nd]; }
 	ws.d_hash[id] = lb2_stdhash_bytes(buf, (uint32_t)n);
 	ws.d_flags[id] = source ? LB2_NF_SOURCE : LB2_NF_SINK;
-	ws.d_comp[id] = compid; ws.d_ne[id] = 0; ws.d_len[id] = 0; ws.d_str[id] = LB2_NIL; ws.d_cd[id] = LB2_NIL;
+	ws.d_comp[id] = compid; ws.d_ne[id] = 0; ws.d_len[id] = 0; ws.d_str[id] = LB2_NIL; ws.d_cd[id] = LB2_NIL; ws.d_orig[id] = 0; ws.d_rep[id] = 0;
 	for (int k = 0; k < 4; ++k) { ws.d_cov[id * 4 + k] = 0; ws.d_cnt[id * 4 + k] = 0; }
 	ws.d_stn[id] = 0; ws.d_stT[id] = 0; ws.d_color[id] = 0; ws.d_mincov[id] = 0; ws.d_mincovqv[id] = 0;
 	return id;
@@ -369,23 +480,23 @@ LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {
 	sh->source = ns; sh->sink = nk;
 }
 
-// hasCycle / hasCycleRec with an explicit stack (node, incoming orientation, next edge index)
+// hasCycle / hasCycleRec with an explicit stack; frame = node << 16 | incoming orientation << 15 | next edge index
 LB2_DEV bool lb2_cycle_from(lb2_win &W, uint32_t start, int ori) {
 	lb2_ws &ws = W.ws; uint32_t *st = ws.stack; uint32_t sp = 0; bool ans = false;
-	const uint32_t cap = (W.C->max_nodes + LB2_MAX_SPECIAL) * 2;
-	ws.d_color[start] = 2; st[sp++] = start; st[sp++] = ((uint32_t)ori << 16) | 0u;
+	const uint32_t cap = W.sh->n_rows + LB2_MAX_SPECIAL;
+	ws.d_color[start] = 2; st[sp++] = (start << 16) | ((uint32_t)ori << 15);
 	while (sp) {
-		uint32_t node = st[sp - 2]; uint32_t v = st[sp - 1]; int o = (int)(v >> 16); int i = (int)(v & 0xFFFF);
-		if (ans || i >= (int)ws.d_ne[node]) { ws.d_color[node] = 3; sp -= 2; continue; }
-		st[sp - 1] = ((uint32_t)o << 16) | (uint32_t)(i + 1);
+		uint32_t v = st[sp - 1]; uint32_t node = v >> 16; int o = (int)((v >> 15) & 1); int i = (int)(v & 0x7FFF);
+		if (ans || i >= (int)ws.d_ne[node]) { ws.d_color[node] = 3; --sp; continue; }
+		st[sp - 1] = v + 1;
 		lb2_edge ed = ws.d_edge[(size_t)node * LB2_ECAP + i];
 		if (!lb2_is_dir(ed.dir, o)) { continue; }
 		uint32_t other = ed.to;
 		if (lb2_special(W, other)) { continue; }
-		if (ws.d_color[other] == 2) { ans = true; st[sp - 1] = ((uint32_t)o << 16) | 0xFFFFu; continue; }   // break out of this node's loop
+		if (ws.d_color[other] == 2) { ans = true; continue; }
 		if (ws.d_color[other] == 1) {
-			if (sp + 2 > cap) { W.sh->err |= 1u << LB2_D_STACK; return true; }
-			ws.d_color[other] = 2; st[sp++] = other; st[sp++] = ((uint32_t)lb2_dir_dest(ed.dir) << 16) | 0u;
+			if (sp + 1 > cap) { W.sh->err |= 1u << LB2_D_STACK; return true; }
+			ws.d_color[other] = 2; st[sp++] = (other << 16) | ((uint32_t)lb2_dir_dest(ed.dir) << 15);
 		}
 	}
 	return ans;

@@ -6,30 +6,23 @@
 #include "lb2_paths.cuh"
 
 // byte layout of one CTA's workspace slab; the same function runs on host (sizing) and device (pointers)
-#ifdef __CUDACC__
-#define LB2_HD __host__ __device__ inline
-#else
-#define LB2_HD static inline
-#endif
 
 LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 {
 	size_t off = 0;
 #define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
-	const size_t MN = (size_t)c.max_nodes + LB2_MAX_SPECIAL, MR = (size_t)c.max_reads + 2;
+	const size_t MN = (size_t)c.max_nodes + 16, MR = (size_t)c.max_reads + 2;
 	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
 	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
 	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR);
-	LB2_TAKE(d_rep, uint32_t, MN); LB2_TAKE(d_hash, uint64_t, MN); LB2_TAKE(d_cov, float, MN * 4); LB2_TAKE(d_cnt, uint32_t, MN * 4);
-	LB2_TAKE(d_stn, uint32_t, MN); LB2_TAKE(d_stT, uint32_t, MN); LB2_TAKE(d_mincov, int32_t, MN); LB2_TAKE(d_mincovqv, int32_t, MN);
-	LB2_TAKE(d_ne, uint8_t, MN); LB2_TAKE(d_edge, lb2_edge, MN * LB2_ECAP); LB2_TAKE(d_flags, uint8_t, MN);
-	LB2_TAKE(d_comp, int32_t, MN); LB2_TAKE(d_color, uint8_t, MN); LB2_TAKE(d_lnext, uint32_t, MN);
-	LB2_TAKE(d_str, uint32_t, MN); LB2_TAKE(d_len, uint32_t, MN); LB2_TAKE(d_cd, uint32_t, MN);
-	LB2_TAKE(deficit, uint16_t, c.deficit_bytes / 2); LB2_TAKE(buckets, uint32_t, c.bucket_cap);
+	LB2_TAKE(b_rep, uint32_t, MN); LB2_TAKE(b_hash, uint64_t, MN); LB2_TAKE(b_cnt, uint32_t, MN * 4); LB2_TAKE(b_mincovqv, int32_t, MN);
+	LB2_TAKE(b_flags, uint8_t, MN); LB2_TAKE(b_stT, uint8_t, MN); LB2_TAKE(b_ne, uint8_t, MN); LB2_TAKE(b_edge, lb2_bedge, MN * LB2_BECAP); LB2_TAKE(b_row, uint32_t, MN);
+	LB2_TAKE(d_rep, uint32_t, LB2_MAX_ROWS); LB2_TAKE(d_hash, uint64_t, LB2_MAX_ROWS); LB2_TAKE(d_cnt, uint32_t, LB2_MAX_ROWS * 4); LB2_TAKE(d_orig, uint32_t, LB2_MAX_ROWS);
+	LB2_TAKE(d_mincov, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_mincovqv, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_str, uint32_t, LB2_MAX_ROWS); LB2_TAKE(d_cd, uint32_t, LB2_MAX_ROWS);
+	LB2_TAKE(deficit, uint16_t, c.deficit_bytes / 2);
 	LB2_TAKE(refnode, uint32_t, LB2_MAX_REF); LB2_TAKE(refcov, uint16_t, 2 * LB2_MAX_REF * 2);
 	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(queue, lb2_qent, c.queue_cap);
-	LB2_TAKE(stack, uint32_t, MN * 2 + 16); LB2_TAKE(chain, uint32_t, MN + 16);
 	LB2_TAKE(pathseq, char, LB2_MAX_PATH + 16); LB2_TAKE(pcovN, lb2_cov, LB2_MAX_PATH + 16); LB2_TAKE(pcovT, lb2_cov, LB2_MAX_PATH + 16);
 	LB2_TAKE(pnodes, uint32_t, LB2_MAX_PNODES); LB2_TAKE(pdirs, uint8_t, LB2_MAX_PNODES); LB2_TAKE(peidx, uint8_t, LB2_MAX_PNODES);
 	LB2_TAKE(aln_ref, char, LB2_MAX_PATH + LB2_MAX_REF + 16); LB2_TAKE(aln_path, char, LB2_MAX_PATH + LB2_MAX_REF + 16);
@@ -38,13 +31,6 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 #undef LB2_TAKE
 	return (off + 255) & ~(size_t)255;
 }
-
-// shared-memory layout: lb2_sh | ref_raw[LB2_MAX_REF] | bits[max_bp/16 + 4] | lowq[max_bp/32 + 4] | region T
-LB2_HD size_t lb2_smem_fixed(uint32_t max_bp) {
-	return ((sizeof(lb2_sh) + 15) & ~(size_t)15) + LB2_MAX_REF + ((size_t)max_bp / 16 + 4) * 4 + ((size_t)max_bp / 32 + 4) * 4;
-}
-LB2_HD size_t lb2_treg_bytes(uint32_t table_slots) { return (size_t)table_slots * 20; }
-LB2_HD size_t lb2_smem_bytes(uint32_t max_bp, uint32_t table_slots) { return ((lb2_smem_fixed(max_bp) + 15) & ~(size_t)15) + lb2_treg_bytes(table_slots); }
 
 LB2_DEV uint32_t lb2_first_err(uint32_t e) { for (uint32_t b = 0; b < 32; ++b) { if (e & (1u << b)) { return b; } } return 0; }
 
@@ -57,13 +43,13 @@ LB2_DEVNI void lb2_ref_coverage(lb2_win &W)
 	// mers indexed from the (possibly already trimmed) ref->seq: offsets i with i + K < seq.length()
 	for (uint32_t i = tid; i + K < sh->seq_len; i += nt) {
 		uint32_t nd = ws.refnode[sh->seq_off + i];
-		if (nd != LB2_NIL) { ws.d_color[nd] = 9; }
+		if (nd != LB2_NIL) { ws.b_flags[nd] |= 0x10; }      // same bit from every writer; the low-coverage bit was set before the barrier
 	}
 	lb2_sync();
 	for (uint32_t i = tid; i + K < L; i += nt) {
 		uint32_t nd = ws.refnode[i];
 		uint16_t v[4] = { 0, 0, 0, 0 };
-		if (nd != LB2_NIL && ws.d_color[nd] == 9) { for (int c = 0; c < 4; ++c) { v[c] = (uint16_t)ws.d_cnt[nd * 4 + c]; } }
+		if (nd != LB2_NIL && (ws.b_flags[nd] & 0x10)) { for (int c = 0; c < 4; ++c) { v[c] = (uint16_t)ws.b_cnt[nd * 4 + c]; } }
 		for (int s = 0; s < 2; ++s) {
 			uint16_t *rc = ws.refcov + (size_t)s * LB2_MAX_REF * 2;
 			if (i == 0) { for (int j = 0; j < K; ++j) { rc[j * 2] = v[s * 2]; rc[j * 2 + 1] = v[s * 2 + 1]; } }
@@ -97,6 +83,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		for (int k = P->min_k; k <= P->max_k; k += 2) {
 			// isRepeat(rawseq,k) || isAlmostRepeat(rawseq,k,MAX_MISMATCH)  (src/Microassembler.cc:118-131)
 			if ((uint32_t)k <= sh->ref_emax || (uint32_t)k + 1 <= sh->ref_wmax) { continue; }
+			W.ws = W.ws0;                         // row-space pointers go back to their global homes
 			lb2_build_graph(W, k);
 			if (tid == 0) { sh->n_k_tried += 1; sh->final_k = (uint32_t)k; }
 			lb2_sync();
@@ -104,11 +91,11 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			if (sh->err) { break; }
 			lb2_ref_coverage(W);
 			lb2_mark(W, LB2_PH_REFCOV);
+			lb2_order_and_pack(W);
+			if (sh->err) { break; }
 			if (tid == 0) {
 				sh->arena_used = 8; sh->flag_c = 0;
-				lb2_order_nodes(W);
-				lb2_mark(W, LB2_PH_ORDER);
-				if (!sh->err) { lb2_drop_dead(W); sh->numcomp = lb2_mark_components(W); }
+				sh->numcomp = lb2_mark_components(W);
 				lb2_mark(W, LB2_PH_LOWCOV_CC);
 			}
 			lb2_sync();

@@ -15,7 +15,12 @@
 #define LB2_NF_GONE    0x08       // erased from the map (cleanDead)
 #define LB2_NF_SPECIAL (LB2_NF_SOURCE | LB2_NF_SINK)
 
-struct lb2_edge { uint32_t to; uint8_t dir; uint8_t flag; uint16_t pad; };
+// build-space half-edge (dense ids over ALL nodes of the map) and row-space half-edge (ids over the
+// survivors of the first low-coverage sweep + source/sink nodes, < 4096)
+struct lb2_bedge { uint32_t to : 24, dir : 2, flag : 1, type : 5; };
+struct lb2_edge  { uint16_t to : 12, dir : 2, flag : 1, pad : 1; };
+#define LB2_BECAP 8               // a k-mer node has at most 8 neighbours (orientation x appended base)
+#define LB2_MAX_ROWS 4096
 
 struct lb2_qent {                 // one partial path of bfs() (reference src/Graph.cc:1299-1425)
 	uint32_t parent;              // queue index of the prefix
@@ -37,24 +42,25 @@ struct lb2_trans {                // Transcript_t (reference src/Transcript.hh:3
 	uint16_t mn0[4][4];
 };
 
-// pointers into this CTA's global-memory slab (identical layout for every CTA)
+// pointers into this CTA's global-memory slab (identical layout for every CTA) and, for the hot
+// graph-stage arrays, into the CTA's shared memory (assigned per (window,k) by lb2_order_and_pack)
 struct lb2_ws {
-	// --- build stage, slot indexed ---
+	// --- build stage ---
 	uint32_t *used; uint64_t *sortk; uint32_t *inst; uint32_t *mates; uint32_t *bseq;
+	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
+	lb2_bedge *b_edge; uint32_t *b_row;
 	// --- reads ---
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
-	// --- dense nodes ---
-	uint32_t *d_rep; uint64_t *d_hash; float *d_cov; uint32_t *d_cnt; uint32_t *d_stn; uint32_t *d_stT;
-	int32_t *d_mincov; int32_t *d_mincovqv; uint8_t *d_ne; lb2_edge *d_edge; uint8_t *d_flags;
-	int32_t *d_comp; uint8_t *d_color; uint32_t *d_lnext; uint32_t *d_str; uint32_t *d_len; uint32_t *d_cd;
-	uint16_t *deficit;            // [node][K][4] low-quality deficits (only when the window has low-qual bases)
-	uint32_t *buckets;
-	uint32_t *refnode;            // [LB2_MAX_REF] dense node of the reference k-mer at each offset
+	// --- graph stage, row space.  hot (shared memory): ---
+	uint32_t *d_lnext; uint32_t *d_bk; uint32_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; int32_t *d_comp;
+	lb2_edge *d_edge; float *d_cov; uint32_t *d_len; uint32_t *d_stn; uint32_t *d_stT; uint32_t *stack; uint32_t *chain;
+	// cold (global):
+	uint32_t *d_rep; uint64_t *d_hash; uint32_t *d_cnt; uint32_t *d_orig; int32_t *d_mincov; int32_t *d_mincovqv; uint32_t *d_str; uint32_t *d_cd;
+	uint16_t *deficit;            // [dense node][K][4] low-quality deficits (only when the window has low-qual bases)
+	uint32_t *refnode;            // [LB2_MAX_REF] node of the reference k-mer at each offset (dense id, then row id)
 	uint16_t *refcov;             // [2 samples][LB2_MAX_REF][2] fwd,rev
 	uint8_t  *arena;
 	lb2_qent *queue;
-	uint32_t *stack;
-	uint32_t *chain;
 	// --- path processing ---
 	char *pathseq; lb2_cov *pcovN; lb2_cov *pcovT; uint32_t *pnodes; uint8_t *pdirs; uint8_t *peidx;
 	char *aln_ref; char *aln_path; int32_t *dp; uint8_t *tb; lb2_trans *trans; char *tstr;
@@ -65,17 +71,17 @@ struct lb2_sizes { size_t total; size_t off[64]; };
 // shared (smem) scalars of one window
 struct lb2_sh {
 	// window
-	uint32_t w, R, L, total_bp, ref_g, has_lowq, has_pairs, mapped, status, detail;
+	uint32_t w, R, L, total_bp, ref_g, has_lowq, lowq_live, has_pairs, mapped, status, detail;
 	int32_t  ref_start;
 	// per k
 	int32_t  K, nw;
-	uint32_t n_used, n_nodes, n_spec, err;
+	uint32_t n_used, n_nodes, n_rows, n_spec, err;
 	uint32_t totalreadbp;
 	uint32_t flag_a, flag_b, flag_c; uint32_t scan_emax, scan_wmax, ref_emax, ref_wmax;
 	// reference trimming state (Ref_t::seq/trim5/trim3, persists across k: SURVEY B4)
 	uint32_t seq_off, seq_len; uint32_t trim5, trim3;
 	// order emulation
-	uint32_t bkt_count, elem_count, next_resize, lhead;
+	uint32_t bkt_count, bkt_cap, elem_count, next_resize, lhead;
 	// anchors
 	uint32_t source, sink;
 	uint32_t arena_used, tstr_used;
@@ -91,5 +97,19 @@ struct lb2_sh {
 // phase ids for the optional cycle profile (lb2_dev_out::prof)
 enum { LB2_PH_STAGE = 0, LB2_PH_PRESCAN, LB2_PH_REFSCAN, LB2_PH_WALK, LB2_PH_COMPACT, LB2_PH_MATES, LB2_PH_LOWQ, LB2_PH_CLEAR,
        LB2_PH_REFCOV, LB2_PH_ORDER, LB2_PH_LOWCOV_CC, LB2_PH_COMP_SEQ, LB2_PH_BFS, LB2_PH_PATHSCAN, LB2_PH_ALIGN, LB2_PH_SCAN, LB2_PH_OTHER, LB2_PH_N };
+
+#ifdef __CUDACC__
+#define LB2_HD __host__ __device__ inline
+#else
+#define LB2_HD static inline
+#endif
+
+// shared-memory layout: lb2_sh | ref_raw[LB2_MAX_REF] | bits[max_bp/16 + 4] | lowq[max_bp/32 + 4] | region T
+LB2_HD size_t lb2_smem_fixed(uint32_t max_bp) {
+	return ((sizeof(lb2_sh) + 15) & ~(size_t)15) + LB2_MAX_REF + ((size_t)max_bp / 16 + 4) * 4 + ((size_t)max_bp / 32 + 4) * 4;
+}
+LB2_HD size_t lb2_treg_bytes(uint32_t table_slots) { return (size_t)table_slots * 20; }
+LB2_HD size_t lb2_smem_bytes(uint32_t max_bp, uint32_t table_slots) { return ((lb2_smem_fixed(max_bp) + 15) & ~(size_t)15) + lb2_treg_bytes(table_slots); }
+
 
 #endif

@@ -46,7 +46,7 @@ int main(int argc, char **argv)
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);
 	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp, C.table_slots) + 64, 0);
 	lb2_win Wn; Wn.P = &P; Wn.C = &C; Wn.B = &B; Wn.O = &O;
-	lb2_ws_layout(C, slab.data(), &Wn.ws);
+	lb2_ws_layout(C, slab.data(), &Wn.ws); Wn.ws0 = Wn.ws;
 	Wn.sh = (lb2_sh *)smem.data();
 	Wn.ref_raw = (char *)smem.data() + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
 	Wn.bits = (uint32_t *)(Wn.ref_raw + LB2_MAX_REF);
