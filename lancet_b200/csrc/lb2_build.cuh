@@ -32,6 +32,25 @@ LB2_DEV void lb2_mark(lb2_win &W, int ph) {
 	if (lb2_tid() == 0) { unsigned long long t = lb2_clock(); W.sh->prof[ph] += t - W.sh->t_last; W.sh->t_last = t; }
 }
 
+// CTA-wide exclusive prefix sum: set(i, sum_{j<i} get(j)); returns the total.  Each lane owns a contiguous chunk.
+template <class Get, class Set>
+LB2_DEV uint32_t lb2_excl_scan(lb2_win &W, uint32_t n, Get get, Set set)
+{
+	const unsigned tid = lb2_tid(), nt = lb2_nthr(); uint32_t *sc = W.sh->scan;
+	const uint32_t chunk = (n + nt - 1) / nt, lo = tid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+	uint32_t sum = 0;
+	for (uint32_t i = lo; i < hi; ++i) { sum += get(i); }
+	sc[tid] = sum;
+	lb2_sync();
+	if (tid == 0) { uint32_t acc = 0; for (unsigned t = 0; t < nt; ++t) { uint32_t v = sc[t]; sc[t] = acc; acc += v; } sc[nt] = acc; }
+	lb2_sync();
+	uint32_t acc = sc[tid];
+	for (uint32_t i = lo; i < hi; ++i) { uint32_t v = get(i); set(i, acc); acc += v; }
+	uint32_t total = sc[nt];
+	lb2_sync();
+	return total;
+}
+
 LB2_DEV void lb2_fail(lb2_win &W, uint32_t status, uint32_t detail) {
 	if (lb2_cas32(&W.sh->status, LB2_WIN_OK, status) == LB2_WIN_OK) { W.sh->detail = detail; }
 }
@@ -44,18 +63,19 @@ LB2_DEVNI void lb2_stage_lowq(lb2_win &W)
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const uint32_t R = sh->R; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
 	const int qcall = W.P->min_qual_call;
+	for (uint32_t i = tid; i < (sh->total_bp >> 5) + 4; i += nt) { W.lowq[i] = 0; }
+	lb2_sync();
 	for (uint32_t r = tid; r < R; r += nt) {
 		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
 		const char *q = B->qual + B->base_off[widx[r]] + ws.rd_t5[r];
-		uint32_t g = ws.rd_start[r], anylow = 0;
-		for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-			uint32_t lw = 0, m = (n - b0 < 32) ? (n - b0) : 32;
+		uint32_t g = ws.rd_start[r], anylow = 0;      // reads start on 16-base boundaries: neighbours may share a mask word
+		for (uint32_t b0 = 0; b0 < n; b0 += 16) {
+			uint32_t lw = 0, m = (n - b0 < 16) ? (n - b0) : 16;
 			for (uint32_t i = 0; i < m; ++i) { if (q[b0 + i] < qcall) { lw |= 1u << i; } }
-			W.lowq[(g + b0) >> 5] = lw; anylow |= lw;
+			if (lw) { lb2_or32(&W.lowq[(g + b0) >> 5], lw << ((g + b0) & 31)); anylow = 1; }
 		}
 		if (anylow) { lb2_or32(&sh->has_lowq, 1u); }
 	}
-	for (uint32_t b0 = tid * 32; b0 < ((sh->L + 31u) & ~31u) + 64; b0 += nt * 32) { W.lowq[(sh->ref_g + b0) >> 5] = 0; }
 	if (tid == 0) { sh->lowq_live = 1; }
 	lb2_sync();
 }
@@ -110,9 +130,9 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		if (n) { lb2_add32(&sh->totalreadbp, (uint32_t)n); }
 	}
 	lb2_sync();
+	uint32_t cum_all = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { return (ws.rd_len[r] + 15u) & ~15u; }, [&](uint32_t r, uint32_t v) { ws.rd_start[r] = v; });
 	if (tid == 0) {
-		uint32_t cum = 0;
-		for (uint32_t r = 0; r < R; ++r) { ws.rd_start[r] = cum; cum += (ws.rd_len[r] + 31u) & ~31u; }
+		uint32_t cum = cum_all;
 		ws.rd_start[R] = cum; sh->ref_g = cum; cum += (L + 31u) & ~31u;
 		sh->total_bp = cum;
 		if (cum + 64 > W.C->max_bp) { lb2_fail(W, LB2_WIN_OVERFLOW, LB2_D_SMEM); }
@@ -143,11 +163,11 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		uint64_t o0 = B->base_off[idx] + ws.rd_t5[r];
 		const char *s = B->seq + o0;
 		uint32_t g = ws.rd_start[r];
-		for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-			uint64_t bw = 0;
-			uint32_t m = (n - b0 < 32) ? (n - b0) : 32;
-			for (uint32_t i = 0; i < m; ++i) { bw |= (uint64_t)lb2_code(s[b0 + i]) << (2 * i); }
-			W.bits[(g + b0) >> 4] = (uint32_t)bw; W.bits[((g + b0) >> 4) + 1] = (uint32_t)(bw >> 32);
+		for (uint32_t b0 = 0; b0 < n; b0 += 16) {
+			uint32_t bw = 0;
+			uint32_t m = (n - b0 < 16) ? (n - b0) : 16;
+			for (uint32_t i = 0; i < m; ++i) { bw |= (uint32_t)lb2_code(s[b0 + i]) << (2 * i); }
+			W.bits[(g + b0) >> 4] = bw;
 		}
 	}
 	lb2_stage_lowq(W);
@@ -312,9 +332,10 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	const uint32_t R = sh->R, L = sh->L, TS = C->table_slots;
 	if (!sh->lowq_live && sh->has_lowq) { lb2_stage_lowq(W); }
 	W.t_key = (uint32_t *)W.treg; W.t_occ = W.t_key + TS; W.t_cnt = W.t_occ + TS; W.t_em = W.t_cnt + 2 * (size_t)TS;
+	uint32_t kcum = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { uint32_t n = ws.rd_len[r]; return (n > (uint32_t)K) ? (n - K + 1) : 0; },
+	                              [&](uint32_t r, uint32_t v) { ws.rd_kbase[r] = v; });
 	if (tid == 0) {
-		uint32_t cum = 0;
-		for (uint32_t r = 0; r < R; ++r) { ws.rd_kbase[r] = cum; uint32_t n = ws.rd_len[r]; cum += (n > (uint32_t)K) ? (n - K + 1) : 0; }
+		uint32_t cum = kcum;
 		ws.rd_kbase[R] = cum;
 		sh->n_used = 0; sh->err = 0; sh->n_spec = 0; sh->flag_a = 0;
 		sh->K = K; sh->nw = nw;

@@ -18,6 +18,8 @@
 struct lb2_launch {
 	lb2_params P; lb2_cfg C; lb2_dev_batch B; lb2_dev_out O;
 	uint8_t *ws_base; size_t ws_stride; uint32_t *counter;
+	const uint32_t *win_list; const uint32_t *n_list;   // escalation pass: indices of the windows to redo (NULL = all windows)
+	uint32_t *retry_list; uint32_t *retry_count;
 	// compaction outputs
 	uint32_t *var_off; uint32_t *str_off; uint32_t *totals; lb2_variant *cvars; char *cstr;
 };
@@ -35,14 +37,32 @@ lb2_window_kernel(const lb2_launch *Lp)
 	W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);
 	W.lowq = W.bits + (Lp->C.max_bp / 16 + 4);
 	W.treg = smem + ((lb2_smem_fixed(Lp->C.max_bp) + 15) & ~(size_t)15);
-	const uint32_t nwin = Lp->B.n_windows;
+	const uint32_t nwin = Lp->win_list ? *Lp->n_list : Lp->B.n_windows;
 	while (true) {
 		if (threadIdx.x == 0) { s_next = atomicAdd(Lp->counter, 1u); }
 		__syncthreads();
 		uint32_t w = s_next;
 		__syncthreads();
 		if (w >= nwin) { break; }
+		if (Lp->win_list) { w = Lp->win_list[w]; }
 		lb2_process_window(W, w);
+	}
+}
+
+// windows that ran out of a per-CTA capacity in the first pass are redone by the escalation pass
+// (same kernel, larger table / arena / BFS queue, one CTA per SM)
+__global__ void lb2_collect_kernel(const lb2_launch *Lp)
+{
+	const uint32_t n = Lp->B.n_windows;
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+		lb2_window_info wi = Lp->O.info[w];
+		if (wi.status == LB2_WIN_OVERFLOW) {
+			uint32_t d = wi.detail;
+			if (d == LB2_D_HASH_FULL || d == LB2_D_NODES || d == LB2_D_ARENA || d == LB2_D_QUEUE || d == LB2_D_SMEM || d == LB2_D_BUCKETS ||
+			    d == LB2_D_STACK || d == LB2_D_EDGES || d == LB2_D_SPECIAL) {
+				Lp->retry_list[atomicAdd(Lp->retry_count, 1u)] = w;
+			}
+		}
 	}
 }
 
@@ -97,6 +117,9 @@ struct lb2_ctx {
 	lb2_launch L;
 	uint32_t n_windows = 0; bool resident = false, ran = false;
 	size_t ws_stride = 0; uint32_t ws_slots = 0;
+	// escalation pass
+	lb2_cfg C2; lb2_launch L2; lb2_launch *d_launch2 = nullptr; Buf d_ws2, d_retry; uint32_t *d_counter2 = nullptr, *d_retry_count = nullptr;
+	size_t ws2_stride = 0; uint32_t ws2_slots = 0; bool escalate = true;
 	uint64_t launches = 0;
 	float kernel_ms = 0;
 	// host result
@@ -154,13 +177,15 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
-	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096); C.max_nodes = env_u32("LB2_MAX_NODES", C.table_slots - C.table_slots / 4);
+	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096); C.max_nodes = C.table_slots - C.table_slots / 4;
 	C.max_reads = 4096; C.max_bp = 0;
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 17);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
 	C.bucket_cap = 10273; C.max_k = 127;
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
+	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
+	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
 	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
 		delete ctx; return LB2_ERR_CUDA;
 	}
@@ -176,6 +201,8 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used, &ctx->d_var_off, &ctx->d_str_off,
 		&ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws };
 	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
+	if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); } if (ctx->d_retry.p) { cudaFree(ctx->d_retry.p); }
+	cudaFree(ctx->d_counter2); cudaFree(ctx->d_retry_count); cudaFree(ctx->d_launch2);
 	cudaFree(ctx->d_counter); cudaFree(ctx->d_totals); cudaFree(ctx->d_launch);
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -195,7 +222,7 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 		uint64_t bp = 0;
 		for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
 			uint32_t r = b->wr_idx[x]; if (r >= R) { return LB2_ERR_ARG; }
-			bp += ((b->base_off[r + 1] - b->base_off[r]) + 31) & ~31ull;
+			bp += ((b->base_off[r + 1] - b->base_off[r]) + 15) & ~15ull;
 		}
 		bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; bp += 128;
 		if (bp > max_bp) { max_bp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
@@ -203,9 +230,12 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	}
 	max_bp = (max_bp + 1023) & ~1023u;
 	const uint32_t smem_cap = 220u << 10;
-	if (max_bp > (1u << 18) - 1024) { max_bp = (1u << 18) - 1024; }   // representative base index has 18 bits in the table key
-	while (lb2_smem_bytes(max_bp, ctx->C.table_slots) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
+	if (max_bp > (1u << 20) - 1024) { max_bp = (1u << 20) - 1024; }   // representative base index has 20 bits in the table key
 	lb2_cfg &C = ctx->C;
+	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096);
+	while (C.table_slots > 1024 && lb2_smem_bytes(max_bp, C.table_slots) > smem_cap) { C.table_slots >>= 1; }
+	while (lb2_smem_bytes(max_bp, C.table_slots) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
+	C.max_nodes = C.table_slots - C.table_slots / 4;
 	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C.table_slots); C.max_reads = std::max(max_reads + 2, 64u);
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem_bytes));
 	int occ = 0;
@@ -256,9 +286,34 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	L.O.info = (lb2_window_info *)ctx->d_info.p; L.O.variants = (lb2_variant *)ctx->d_vars.p; L.O.strings = (char *)ctx->d_strs.p;
 	L.O.str_used = (uint32_t *)ctx->d_str_used.p; L.O.prof = ctx->d_prof;
 	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
+	L.win_list = nullptr; L.n_list = nullptr;
+	if ((rc = lb2_reserve(ctx, ctx->d_retry, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
+	L.retry_list = (uint32_t *)ctx->d_retry.p; L.retry_count = ctx->d_retry_count;
 	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_totals;
 	L.cvars = (lb2_variant *)ctx->d_cvars.p; L.cstr = (char *)ctx->d_cstr.p;
 	LB2_CK(cudaMemcpyAsync(ctx->d_launch, &L, sizeof L, cudaMemcpyHostToDevice, ctx->stream));
+	if (ctx->escalate) {
+		// escalation pass: the largest table that still fits beside the staged reads, big arena / BFS queue, one CTA per SM
+		lb2_cfg &C2 = ctx->C2; C2 = C;
+		C2.table_slots = 8192;
+		while (C2.table_slots > C.table_slots && lb2_smem_bytes(max_bp, C2.table_slots) > smem_cap) { C2.table_slots >>= 1; }
+		C2.max_nodes = C2.table_slots - C2.table_slots / 4;
+		C2.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C2.table_slots);
+		C2.arena_bytes = env_u32("LB2_ARENA_BYTES2", 8u << 20); C2.deficit_bytes = env_u32("LB2_DEFICIT_BYTES2", 16u << 20);
+		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 22); C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20);
+		C2.n_slots = (uint32_t)std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 64));
+		size_t stride2 = lb2_ws_layout(C2, nullptr, nullptr);
+		if (stride2 != ctx->ws2_stride || C2.n_slots > ctx->ws2_slots) {
+			if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); ctx->d_ws2.p = nullptr; }
+			LB2_CK(cudaMalloc(&ctx->d_ws2.p, stride2 * C2.n_slots)); ctx->d_ws2.cap = stride2 * C2.n_slots;
+			ctx->ws2_stride = stride2; ctx->ws2_slots = C2.n_slots;
+		}
+		lb2_launch &L2 = ctx->L2; L2 = L; L2.C = C2;
+		L2.ws_base = (uint8_t *)ctx->d_ws2.p; L2.ws_stride = stride2; L2.counter = ctx->d_counter2;
+		L2.win_list = (const uint32_t *)ctx->d_retry.p; L2.n_list = ctx->d_retry_count;
+		LB2_CK(cudaMemcpyAsync(ctx->d_launch2, &L2, sizeof L2, cudaMemcpyHostToDevice, ctx->stream));
+		LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(C.smem_bytes, C2.smem_bytes)));
+	}
 	LB2_CK(cudaStreamSynchronize(ctx->stream));
 	ctx->n_windows = W; ctx->resident = true;
 	return LB2_OK;
@@ -274,6 +329,12 @@ extern "C" int lb2_run(lb2_ctx *ctx)
 	LB2_CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (W) {
 		lb2_window_kernel<<<ctx->C.n_slots, LB2_THREADS, ctx->C.smem_bytes, ctx->stream>>>(ctx->d_launch);
+		if (ctx->escalate) {
+			LB2_CK(cudaMemsetAsync(ctx->d_counter2, 0, 4, ctx->stream)); LB2_CK(cudaMemsetAsync(ctx->d_retry_count, 0, 4, ctx->stream));
+			lb2_collect_kernel<<<64, 256, 0, ctx->stream>>>(ctx->d_launch);
+			lb2_window_kernel<<<ctx->C2.n_slots, LB2_THREADS, ctx->C2.smem_bytes, ctx->stream>>>(ctx->d_launch2);
+			ctx->launches += 2;
+		}
 		lb2_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_launch);
 		lb2_gather_kernel<<<W, 64, 0, ctx->stream>>>(ctx->d_launch);
 		ctx->launches += 3;

@@ -50,6 +50,35 @@ LB2_DEV lb2_cov lb2_node_cov(lb2_win &W, uint32_t id, uint32_t i, int sample /*0
 	const lb2_cov *a = (const lb2_cov *)(ws.arena + ws.d_cd[id]);
 	return a[(size_t)sample * ws.d_len[id] + i];
 }
+// a node's cold fields loaded once (they live in global memory); element access is then cheap
+struct lb2_nview { uint32_t str, cd, rep, len, orig; uint32_t cnt[4]; };
+LB2_DEV void lb2_view(lb2_win &W, uint32_t id, lb2_nview &v) {
+	lb2_ws &ws = W.ws;
+	v.str = ws.d_str[id]; v.cd = ws.d_cd[id]; v.rep = ws.d_rep[id]; v.len = ws.d_len[id]; v.orig = ws.d_orig[id];
+	for (int c = 0; c < 4; ++c) { v.cnt[c] = ws.d_cnt[id * 4 + c]; }
+}
+LB2_DEV char lb2_vchar(lb2_win &W, const lb2_nview &v, uint32_t i) {
+	if (v.str == LB2_NIL) {
+		uint32_t g = v.rep >> 1; int K = W.sh->K;
+		if (v.rep & 1) { return lb2_base(3 - lb2_getbase(W.bits, g + K - 1 - i)); }
+		return lb2_base(lb2_getbase(W.bits, g + i));
+	}
+	return (char)W.ws.arena[v.str + i];
+}
+LB2_DEV lb2_cov lb2_vcov(lb2_win &W, const lb2_nview &v, uint32_t i, int sample) {
+	lb2_cov c;
+	if (v.cd == LB2_NIL) {
+		uint32_t f = v.cnt[sample * 2], r = v.cnt[sample * 2 + 1], df = 0, dr = 0;
+		if (W.sh->has_lowq) {
+			uint32_t x = ((const uint32_t *)W.ws.deficit)[((size_t)v.orig * W.sh->K + i) * 2 + sample];
+			df = x & 0xFFFF; dr = x >> 16;
+		}
+		c.fwd = (uint16_t)f; c.rev = (uint16_t)r; c.mqf = (uint16_t)(f - df); c.mqr = (uint16_t)(r - dr);
+		return c;
+	}
+	const lb2_cov *a = (const lb2_cov *)(W.ws.arena + v.cd);
+	return a[(size_t)sample * v.len + i];
+}
 LB2_DEV float lb2_totcov(lb2_win &W, uint32_t id) {   // Node_t::getTotCov (src/Node.hh:151), same association order
 	float *c = W.ws.d_cov + id * 4; return c[0] + c[1] + c[2] + c[3];
 }
@@ -300,11 +329,9 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 	}
 	lb2_mark(W, LB2_PH_ORDER);
 	// ---- rows for the survivors (dense-id order), layout of the row-space arrays
-	if (tid == 0) {
-		uint32_t r = 0;
-		for (uint32_t j = 0; j < n; ++j) { if (ws.b_flags[j] & LB2_NF_DEAD) { ws.b_row[j] = LB2_NIL; } else { ws.b_row[j] = r++; } }
-		sh->n_rows = r; sh->n_spec = 0;
-	}
+	uint32_t nrows = lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return (ws.b_flags[j] & LB2_NF_DEAD) ? 0u : 1u; },
+	                               [&](uint32_t j, uint32_t v) { ws.b_row[j] = (ws.b_flags[j] & LB2_NF_DEAD) ? LB2_NIL : v; });
+	if (tid == 0) { sh->n_rows = nrows; sh->n_spec = 0; }
 	lb2_sync();
 	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
 	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
@@ -313,7 +340,7 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 #define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; ws.field = (type *)(G + off); off += sizeof(type) * (size_t)(count); } while (0)
 		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint32_t, bcap);
 		LB2_GT(d_cov, float, NT * 4); LB2_GT(d_len, uint32_t, NT); LB2_GT(d_stn, uint32_t, NT); LB2_GT(d_stT, uint32_t, NT);
-		LB2_GT(d_comp, int32_t, NT); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(d_edge, lb2_edge, NT * LB2_ECAP);
+		LB2_GT(d_comp, int32_t, NT); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8); LB2_GT(d_edge, lb2_edge, NT * LB2_ECAP);
 		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT);
 #undef LB2_GT
 		ws.chain = ws.stack;
@@ -557,93 +584,125 @@ LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *
 	return nchain;
 }
 
-LB2_DEVNI void lb2_compress_one(lb2_win &W, uint32_t node) {
-	lb2_ws &ws = W.ws; const int K = W.sh->K;
-	uint32_t *chain = ws.chain;
-	uint32_t len0 = ws.d_len[node], curlen = len0;
-	uint32_t nF = lb2_compress_dir(W, node, 0, chain, 0, curlen);
-	uint32_t nAll = lb2_compress_dir(W, node, 1, chain, nF, curlen);
-	if (nAll == 0 || W.sh->err) { return; }
-	// layout: [R-chain, last absorbed first] seed [F-chain]
-	uint32_t so = lb2_arena_alloc(W, curlen); uint32_t co = lb2_arena_alloc(W, curlen * 2 * (uint32_t)sizeof(lb2_cov));
-	if (W.sh->err) { return; }
-	char *S = (char *)ws.arena + so; lb2_cov *CT = (lb2_cov *)(ws.arena + co); lb2_cov *CN = CT + curlen;
-	uint32_t leftlen = 0;
-	for (uint32_t c = nF; c < nAll; ++c) { leftlen += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
-	// seed
-	for (uint32_t i = 0; i < len0; ++i) { S[leftlen + i] = lb2_node_char(W, node, i); CT[leftlen + i] = lb2_node_cov(W, node, i, 0); CN[leftlen + i] = lb2_node_cov(W, node, i, 1); }
-	// F chain: append oriented[K-1..]
-	uint32_t pos = leftlen + len0;
-	for (uint32_t c = 0; c < nF; ++c) {
-		uint32_t b = chain[c] & 0x7FFFFFFFu; bool flip = (chain[c] >> 31) != 0; uint32_t bl = ws.d_len[b];
-		for (uint32_t i = (uint32_t)K - 1; i < bl; ++i, ++pos) {
-			uint32_t src = flip ? (bl - 1 - i) : i;
-			char ch = lb2_node_char(W, b, src); S[pos] = flip ? lb2_comp(ch) : ch;
-			CT[pos] = lb2_node_cov(W, b, src, 0); CN[pos] = lb2_node_cov(W, b, src, 1);
-		}
-	}
-	// R chain: the c-th absorbed node sits left of everything absorbed before it; it contributes frame[0 .. bl-K]
-	pos = leftlen;
-	for (uint32_t c = nF; c < nAll; ++c) {
-		uint32_t b = chain[c] & 0x7FFFFFFFu; bool flip = (chain[c] >> 31) != 0; uint32_t bl = ws.d_len[b];
-		uint32_t cntb = bl - K + 1; pos -= cntb;
-		for (uint32_t i = 0; i < cntb; ++i) {
-			uint32_t src = flip ? (bl - 1 - i) : i;
-			char ch = lb2_node_char(W, b, src); S[pos + i] = flip ? lb2_comp(ch) : ch;
-			CT[pos + i] = lb2_node_cov(W, b, src, 0); CN[pos + i] = lb2_node_cov(W, b, src, 1);
-		}
-	}
-	ws.d_str[node] = so; ws.d_cd[node] = co; ws.d_len[node] = curlen;
-	// Node_t::computeMinCov (src/Node.cc:600-615)
-	int mn = 10000000, mnq = 10000000;
-	for (uint32_t i = 0; i < curlen; ++i) {
-		int t = CT[i].fwd + CT[i].rev + CN[i].fwd + CN[i].rev, q = CT[i].mqf + CT[i].mqr + CN[i].mqf + CN[i].mqr;
-		if (t < mn) { mn = t; } if (q < mnq) { mnq = q; }
-	}
-	ws.d_mincov[node] = mn; ws.d_mincovqv[node] = mnq;
-}
+// job record of one compacted unitig (lane 0 writes it during the sweep, all lanes lay the bases out)
+struct lb2_job { uint32_t node, cbeg, nF, nAll, len0, curlen, so, co, leftlen, pad; };
 
-LB2_DEVNI void lb2_compress(lb2_win &W, int compid) {
-	lb2_ws &ws = W.ws;
-	for (uint32_t p = W.sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	uint32_t cused = 0, njobs = 0; const uint32_t ccap = sh->n_rows + LB2_MAX_SPECIAL;
+	lb2_job *jobs = (lb2_job *)ws.jobs;
+	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
 		if (ws.d_comp[p] != compid) { continue; }
 		if (ws.d_flags[p] & LB2_NF_DEAD) { continue; }
 		if (lb2_special(W, p)) { continue; }
-		lb2_compress_one(W, p);
-		if (W.sh->err) { return; }
+		uint32_t *chain = ws.chain + cused;
+		uint32_t len0 = ws.d_len[p], curlen = len0;
+		uint32_t nF = lb2_compress_dir(W, p, 0, chain, 0, curlen);
+		uint32_t nAll = lb2_compress_dir(W, p, 1, chain, nF, curlen);
+		if (sh->err) { break; }
+		if (nAll == 0) { continue; }
+		if (cused + nAll > ccap || njobs >= LB2_MAX_ROWS) { sh->err |= 1u << LB2_D_STACK; break; }
+		lb2_job jb; jb.node = p; jb.cbeg = cused; jb.nF = nF; jb.nAll = nAll; jb.len0 = len0; jb.curlen = curlen; jb.pad = 0;
+		jb.so = lb2_arena_alloc(W, curlen); jb.co = lb2_arena_alloc(W, curlen * 2 * (uint32_t)sizeof(lb2_cov));
+		if (sh->err) { break; }
+		// destination offsets: [R-chain, last absorbed first] seed [F-chain]; chain entries get their start position
+		uint32_t leftlen = 0;
+		for (uint32_t c = nF; c < nAll; ++c) { leftlen += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
+		jb.leftlen = leftlen;
+		uint32_t pos = leftlen + len0;
+		for (uint32_t c = 0; c < nF; ++c) { ws.cpos[cused + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
+		pos = leftlen;
+		for (uint32_t c = nF; c < nAll; ++c) { pos -= ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; ws.cpos[cused + c] = pos; }
+		ws.d_mincov[p] = 10000000; ws.d_mincovqv[p] = 10000000;
+		jobs[njobs++] = jb; cused += nAll;
 	}
-	lb2_clean_dead(W);
+	sh->n_jobs = njobs;
 }
 
-LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {
-	lb2_ws &ws = W.ws; const int K = W.sh->K; int tips;
-	do {
-		tips = 0;
-		for (uint32_t p = W.sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+// lay out bases and per-base coverage of every compacted unitig (all lanes); Node_t::computeMinCov on the fly
+LB2_DEVNI void lb2_materialize(lb2_win &W) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const lb2_job *jobs = (const lb2_job *)ws.jobs;
+	for (uint32_t q = 0; q < sh->n_jobs; ++q) {
+		lb2_job jb = jobs[q];
+		char *S = (char *)ws.arena + jb.so; lb2_cov *CT = (lb2_cov *)(ws.arena + jb.co); lb2_cov *CN = CT + jb.curlen;
+		int mn = 10000000, mnq = 10000000;
+		for (uint32_t m = tid; m <= jb.nAll; m += nt) {
+			uint32_t id, first, count, dst; bool flip;
+			if (m == jb.nAll) { id = jb.node; flip = false; first = 0; count = jb.len0; dst = jb.leftlen; }
+			else {
+				uint32_t ce = ws.chain[jb.cbeg + m]; id = ce & 0x7FFFFFFFu; flip = (ce >> 31) != 0;
+				uint32_t bl = ws.d_len[id]; count = bl - K + 1; dst = ws.cpos[jb.cbeg + m];
+				first = (m < jb.nF) ? (uint32_t)K - 1 : 0;       // F: oriented[K-1..], R: frame[0..bl-K]
+			}
+			lb2_nview v; lb2_view(W, id, v);
+			for (uint32_t i = 0; i < count; ++i) {
+				uint32_t o = first + i, src = flip ? (v.len - 1 - o) : o;
+				char ch = lb2_vchar(W, v, src); S[dst + i] = flip ? lb2_comp(ch) : ch;
+				lb2_cov ct = lb2_vcov(W, v, src, 0), cn = lb2_vcov(W, v, src, 1);
+				CT[dst + i] = ct; CN[dst + i] = cn;
+				int t = ct.fwd + ct.rev + cn.fwd + cn.rev, qq = ct.mqf + ct.mqr + cn.mqf + cn.mqr;
+				if (t < mn) { mn = t; } if (qq < mnq) { mnq = qq; }
+			}
+		}
+		if (mn != 10000000) { lb2_min32((uint32_t *)&ws.d_mincov[jb.node], (uint32_t)mn); lb2_min32((uint32_t *)&ws.d_mincovqv[jb.node], (uint32_t)mnq); }
+	}
+}
+
+// Graph_t::compress (all lanes)
+LB2_DEVNI void lb2_compress(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	if (lb2_tid() == 0) { lb2_compress_sweep(W, compid); }
+	lb2_sync();
+	if (!sh->err) { lb2_materialize(W); }
+	lb2_sync();
+	if (lb2_tid() == 0 && !sh->err) {
+		const lb2_job *jobs = (const lb2_job *)ws.jobs;
+		for (uint32_t q = 0; q < sh->n_jobs; ++q) { const lb2_job &jb = jobs[q]; ws.d_str[jb.node] = jb.so; ws.d_cd[jb.node] = jb.co; ws.d_len[jb.node] = jb.curlen; }
+		lb2_clean_dead(W);
+	}
+	lb2_sync();
+}
+
+LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {      // all lanes
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	while (true) {
+		if (lb2_tid() == 0) {
+			int tips = 0;
+			for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+				if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
+				int deg = ws.d_ne[p]; int len = (int)lb2_strlen(W, p) - K + 1;
+				if (deg <= 1 && len < W.P->max_tip_len) { lb2_remove_node(W, p); ++tips; }
+			}
+			sh->flag_b = (uint32_t)tips;
+		}
+		lb2_sync();
+		if (!sh->flag_b || sh->err) { break; }
+		lb2_compress(W, compid);
+	}
+}
+
+LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {   // all lanes
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	if (lb2_tid() == 0) {
+		int links = 0;
+		double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
+		const int max_link = (int)floor((double)K / 2.0);
+		const double lim = floor(sqrt(avgcov));
+		for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
 			if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
-			int deg = ws.d_ne[p]; int len = (int)lb2_strlen(W, p) - K + 1;
-			if (deg <= 1 && len < W.P->max_tip_len) { lb2_remove_node(W, p); ++tips; }
+			int deg = ws.d_ne[p]; int len = (int)ws.d_len[p] - K + 1;
+			if (deg >= 2 && len < max_link && (double)ws.d_mincov[p] <= lim) {
+				int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false;
+				lb2_nview v; lb2_view(W, p, v);
+				lb2_find_tandems([&](uint32_t i) -> char { return lb2_vchar(W, v, i); }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov);
+				if (LEN == 0) { lb2_remove_node(W, p); ++links; }
+			}
 		}
-		if (tips) { lb2_compress(W, compid); }
-	} while (tips && !W.sh->err);
-}
-
-LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {
-	lb2_ws &ws = W.ws; const int K = W.sh->K; int links = 0;
-	double avgcov = ((double)(int)W.sh->totalreadbp) / ((double)W.sh->L);
-	const int max_link = (int)floor((double)K / 2.0);
-	const double lim = floor(sqrt(avgcov));
-	for (uint32_t p = W.sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
-		if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
-		int deg = ws.d_ne[p]; int len = (int)ws.d_len[p] - K + 1;
-		if (deg >= 2 && len < max_link && (double)ws.d_mincov[p] <= lim) {
-			int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false;
-			uint32_t id = p;
-			lb2_find_tandems([&](uint32_t i) -> char { return lb2_node_char(W, id, i); }, ws.d_len[p], W.P, K - 1, LEN, motif, ml, 0, ov);
-			if (LEN == 0) { lb2_remove_node(W, p); ++links; }
-		}
+		sh->flag_b = (uint32_t)links;
 	}
-	if (links) { lb2_compress(W, compid); }
+	lb2_sync();
+	if (sh->flag_b && !sh->err) { lb2_compress(W, compid); }
 }
 
 #endif

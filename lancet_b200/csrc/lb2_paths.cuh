@@ -20,7 +20,19 @@
 //   emax = longest run of zeros of m_d restricted to p <= len-2-d   (both offsets must be < len-K)
 //   wmax = longest window of m_d (p <= len-1-d) holding <= max ones  (kMismatch compares K+1 columns)
 // ---------------------------------------------------------------------------------------------------
-LB2_DEVNI void lb2_diag_scan(lb2_win &W, const char *s, int len, int maxmm)
+// 16 mismatch flags (bit 2i = base p+i differs from base p+i+d) from the 2-bit packed sequence starting at base g0
+LB2_DEV uint32_t lb2_mm16(const uint32_t *bits, uint32_t g0, uint32_t p, uint32_t d) {
+	uint32_t ia = g0 + p, ib = ia + d;
+	uint32_t a0 = bits[ia >> 4], a1 = bits[(ia >> 4) + 1], sa = (ia & 15) << 1;
+	uint32_t b0 = bits[ib >> 4], b1 = bits[(ib >> 4) + 1], sb = (ib & 15) << 1;
+	uint32_t A = sa ? ((a0 >> sa) | (a1 << (32 - sa))) : a0;
+	uint32_t B = sb ? ((b0 >> sb) | (b1 << (32 - sb))) : b0;
+	uint32_t x = A ^ B;
+	return (x | (x >> 1)) & 0x55555555u;
+}
+
+// the sequence is ACGT only and 2-bit packed at base index g0 of `bits` (two readable words past the end)
+LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int len, int maxmm)
 {
 	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	if (tid == 0) { sh->scan_emax = 0; sh->scan_wmax = 0; }
@@ -29,16 +41,36 @@ LB2_DEVNI void lb2_diag_scan(lb2_win &W, const char *s, int len, int maxmm)
 	for (int d = 1 + (int)tid; d < len; d += (int)nt) {
 		const int np = len - d;                 // positions p in [0, np)
 		int run = 0, left = 0, mm = 0;
-		for (int p = 0; p < np; ++p) {
-			int m = (s[p] != s[p + d]) ? 1 : 0;
-			if (p < np - 1) { if (m) { run = 0; } else { ++run; if ((uint32_t)run > emax) { emax = (uint32_t)run; } } }
-			mm += m;
-			while (mm > maxmm) { mm -= (s[left] != s[left + d]) ? 1 : 0; ++left; }
-			if ((uint32_t)(p - left + 1) > wmax) { wmax = (uint32_t)(p - left + 1); }
+		uint32_t lw = 0; int lbase = -16;       // cached flags of the chunk holding `left`
+		for (int p0 = 0; p0 < np; p0 += 16) {
+			uint32_t fw = lb2_mm16(bits, g0, (uint32_t)p0, (uint32_t)d);
+			int lim = np - p0 < 16 ? np - p0 : 16;
+			for (int i = 0; i < lim; ++i) {
+				int p = p0 + i; int m = (int)((fw >> (2 * i)) & 1u);
+				if (p < np - 1) { if (m) { run = 0; } else { ++run; if ((uint32_t)run > emax) { emax = (uint32_t)run; } } }
+				mm += m;
+				while (mm > maxmm) {
+					if (left - lbase >= 16 || left < lbase) { lbase = left & ~15; lw = lb2_mm16(bits, g0, (uint32_t)lbase, (uint32_t)d); }
+					mm -= (int)((lw >> (2 * (left - lbase))) & 1u); ++left;
+				}
+				if ((uint32_t)(p - left + 1) > wmax) { wmax = (uint32_t)(p - left + 1); }
+			}
 		}
 	}
 	if (emax) { lb2_max32(&sh->scan_emax, emax); }
 	if (wmax) { lb2_max32(&sh->scan_wmax, wmax); }
+	lb2_sync();
+}
+
+// pack the loaded path (ws.pathseq, ACGT) 2-bit into `dst` (all lanes); dst must hold plen/16 + 3 words
+LB2_DEVNI void lb2_pack_path(lb2_win &W, uint32_t *dst)
+{
+	const unsigned tid = lb2_tid(), nt = lb2_nthr(); const uint32_t plen = W.sh->plen; const char *s = W.ws.pathseq;
+	for (uint32_t w = tid; w < (plen >> 4) + 3; w += nt) {
+		uint32_t v = 0;
+		for (uint32_t i = 0; i < 16; ++i) { uint32_t q = w * 16 + i; if (q < plen) { v |= (uint32_t)(lb2_code(s[q]) & 3) << (2 * i); } }
+		dst[w] = v;
+	}
 	lb2_sync();
 }
 
@@ -90,24 +122,42 @@ LB2_DEVNI void lb2_load_path(lb2_win &W, uint32_t best)
 	for (uint32_t x = best; x != LB2_NIL; x = Q[x].parent) { --k; ws.pnodes[k] = Q[x].node; ws.peidx[k] = Q[x].eidx; }
 	sh->pn = n;
 	for (uint32_t i = 1; i < n; ++i) { ws.pdirs[i - 1] = ws.d_edge[(size_t)ws.pnodes[i - 1] * LB2_ECAP + ws.peidx[i]].dir; }
-	// Path_t::str / covDistr
+	// Path_t::str / covDistr: where every node's contribution starts (lane 0); the copy itself is lb2_copy_path
 	int dir = lb2_dir_start(ws.pdirs[0]);
 	uint32_t plen = 0;
 	for (uint32_t i = 0; i < n; ++i) {
 		uint32_t nd = ws.pnodes[i];
+		ws.pstart[i] = plen | ((uint32_t)dir << 31);
 		if (!lb2_special(W, nd)) {
 			uint32_t bl = ws.d_len[nd]; uint32_t from = plen ? (uint32_t)K - 1 : 0;
 			if (plen + (bl - from) > LB2_MAX_PATH) { sh->err |= 1u << LB2_D_PATH; return; }
-			for (uint32_t j = from; j < bl; ++j, ++plen) {
-				uint32_t src = dir ? (bl - 1 - j) : j;
-				char ch = lb2_node_char(W, nd, src);
-				ws.pathseq[plen] = dir ? lb2_comp(ch) : ch;
-				ws.pcovT[plen] = lb2_node_cov(W, nd, src, 0); ws.pcovN[plen] = lb2_node_cov(W, nd, src, 1);
-			}
+			plen += bl - from;
 		}
 		if (i + 1 < n) { dir = lb2_dir_dest(ws.pdirs[i]); }
 	}
+	ws.pstart[n] = plen;
 	sh->plen = plen;
+}
+
+// all lanes: bases and per-base tumour/normal coverage of the loaded path
+LB2_DEVNI void lb2_copy_path(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t n = sh->pn;
+	for (uint32_t i = 0; i < n; ++i) {
+		uint32_t nd = ws.pnodes[i];
+		if (lb2_special(W, nd)) { continue; }
+		uint32_t ps = ws.pstart[i] & 0x7FFFFFFFu; bool dir = (ws.pstart[i] >> 31) != 0;
+		uint32_t from = ps ? (uint32_t)K - 1 : 0;
+		lb2_nview v; lb2_view(W, nd, v);
+		for (uint32_t j = from + tid; j < v.len; j += nt) {
+			uint32_t src = dir ? (v.len - 1 - j) : j, dst = ps + (j - from);
+			char ch = lb2_vchar(W, v, src);
+			ws.pathseq[dst] = dir ? lb2_comp(ch) : ch;
+			ws.pcovT[dst] = lb2_vcov(W, v, src, 0); ws.pcovN[dst] = lb2_vcov(W, v, src, 1);
+		}
+	}
+	lb2_sync();
 }
 
 LB2_DEV uint32_t lb2_pathcontig(lb2_win &W, int pos) {   // Path_t::pathcontig

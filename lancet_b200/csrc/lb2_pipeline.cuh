@@ -22,7 +22,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	LB2_TAKE(d_mincov, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_mincovqv, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_str, uint32_t, LB2_MAX_ROWS); LB2_TAKE(d_cd, uint32_t, LB2_MAX_ROWS);
 	LB2_TAKE(deficit, uint16_t, c.deficit_bytes / 2);
 	LB2_TAKE(refnode, uint32_t, LB2_MAX_REF); LB2_TAKE(refcov, uint16_t, 2 * LB2_MAX_REF * 2);
-	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(queue, lb2_qent, c.queue_cap);
+	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(queue, lb2_qent, c.queue_cap); LB2_TAKE(jobs, uint32_t, LB2_MAX_ROWS * 10); LB2_TAKE(pstart, uint32_t, LB2_MAX_PNODES + 1);
 	LB2_TAKE(pathseq, char, LB2_MAX_PATH + 16); LB2_TAKE(pcovN, lb2_cov, LB2_MAX_PATH + 16); LB2_TAKE(pcovT, lb2_cov, LB2_MAX_PATH + 16);
 	LB2_TAKE(pnodes, uint32_t, LB2_MAX_PNODES); LB2_TAKE(pdirs, uint8_t, LB2_MAX_PNODES); LB2_TAKE(peidx, uint8_t, LB2_MAX_PNODES);
 	LB2_TAKE(aln_ref, char, LB2_MAX_PATH + LB2_MAX_REF + 16); LB2_TAKE(aln_path, char, LB2_MAX_PATH + LB2_MAX_REF + 16);
@@ -70,7 +70,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 	}
 	if (sh->status == LB2_WIN_OK) {
 		// one pass over the window reference answers isRepeat / isAlmostRepeat for every k
-		lb2_diag_scan(W, W.ref_raw, (int)sh->L, P->max_mismatch);
+		lb2_diag_scan(W, W.bits, sh->ref_g, (int)sh->L, P->max_mismatch);
 		if (tid == 0) {
 			sh->ref_emax = sh->scan_emax; sh->ref_wmax = sh->scan_wmax;
 			// window pre-skip: isRepeat(rawseq, maxK)  (src/Microassembler.cc:800)
@@ -105,17 +105,19 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			for (int c = 1; c <= numcomp; ++c) {
 				if (tid == 0) {
 					lb2_mark_ref_ends(W, c);
-					bool cyc = !sh->err && lb2_has_cycle(W);
-					if (!cyc && !sh->err) {
-						lb2_compress(W, c);
-						if (!sh->err) { lb2_remove_lowcov(W, c); lb2_compress(W, c); }
-						if (!sh->err) { lb2_remove_tips(W, c); }
-						if (!sh->err) { lb2_remove_short_links(W, c); }
-						if (!sh->err) { cyc = lb2_has_cycle(W); }
-					}
-					sh->flag_c = cyc ? 1u : 0u;
-					lb2_mark(W, LB2_PH_COMP_SEQ);
+					sh->flag_c = (!sh->err && lb2_has_cycle(W)) ? 1u : 0u;
 				}
+				lb2_sync();
+				if (!sh->flag_c && !sh->err) {
+					lb2_compress(W, c);
+					if (tid == 0 && !sh->err) { lb2_remove_lowcov(W, c); }      // removeLowCov(true,c): sweep, cleanDead, then compress
+					lb2_sync();
+					if (!sh->err) { lb2_compress(W, c); }
+					if (!sh->err) { lb2_remove_tips(W, c); }
+					if (!sh->err) { lb2_remove_short_links(W, c); }
+					if (tid == 0 && !sh->err) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+				}
+				lb2_mark(W, LB2_PH_COMP_SEQ);
 				lb2_sync();
 				if (sh->err) { break; }
 				if (sh->flag_c) { retry = true; break; }
@@ -127,11 +129,13 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
 						if (sh->path_found) { lb2_load_path(W, best); }
-						lb2_mark(W, LB2_PH_BFS);
 					}
 					lb2_sync();
-					if (sh->err || !sh->path_found) { break; }
-					lb2_diag_scan(W, W.ws.pathseq, (int)sh->plen, P->max_mismatch);
+					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
+					lb2_copy_path(W);
+					lb2_mark(W, LB2_PH_BFS);
+					lb2_pack_path(W, W.ws.cpos);               // cpos is idle outside lb2_compress
+					lb2_diag_scan(W, W.ws.cpos, 0, (int)sh->plen, P->max_mismatch);
 					lb2_mark(W, LB2_PH_PATHSCAN);
 					if ((uint32_t)k + 1 <= sh->scan_wmax) { rpt = true; break; }
 					if (tid == 0) { lb2_flag_path(W, 1); }
@@ -152,10 +156,11 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
 						if (sh->path_found) { lb2_load_path(W, best); }
-						lb2_mark(W, LB2_PH_BFS);
 					}
 					lb2_sync();
-					if (sh->err || !sh->path_found) { break; }
+					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
+					lb2_copy_path(W);
+					lb2_mark(W, LB2_PH_BFS);
 					lb2_process_path(W);
 					if (sh->err) { break; }
 					if (tid == 0) { lb2_flag_path(W, 1); }

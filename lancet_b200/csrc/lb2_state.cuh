@@ -53,14 +53,14 @@ struct lb2_ws {
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
 	// --- graph stage, row space.  hot (shared memory): ---
 	uint32_t *d_lnext; uint32_t *d_bk; uint32_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; int32_t *d_comp;
-	lb2_edge *d_edge; float *d_cov; uint32_t *d_len; uint32_t *d_stn; uint32_t *d_stT; uint32_t *stack; uint32_t *chain;
+	lb2_edge *d_edge; float *d_cov; uint32_t *d_len; uint32_t *d_stn; uint32_t *d_stT; uint32_t *stack; uint32_t *chain; uint32_t *cpos;
 	// cold (global):
 	uint32_t *d_rep; uint64_t *d_hash; uint32_t *d_cnt; uint32_t *d_orig; int32_t *d_mincov; int32_t *d_mincovqv; uint32_t *d_str; uint32_t *d_cd;
 	uint16_t *deficit;            // [dense node][K][4] low-quality deficits (only when the window has low-qual bases)
 	uint32_t *refnode;            // [LB2_MAX_REF] node of the reference k-mer at each offset (dense id, then row id)
 	uint16_t *refcov;             // [2 samples][LB2_MAX_REF][2] fwd,rev
 	uint8_t  *arena;
-	lb2_qent *queue;
+	lb2_qent *queue; uint32_t *jobs; uint32_t *pstart;
 	// --- path processing ---
 	char *pathseq; lb2_cov *pcovN; lb2_cov *pcovT; uint32_t *pnodes; uint8_t *pdirs; uint8_t *peidx;
 	char *aln_ref; char *aln_path; int32_t *dp; uint8_t *tb; lb2_trans *trans; char *tstr;
@@ -75,7 +75,7 @@ struct lb2_sh {
 	int32_t  ref_start;
 	// per k
 	int32_t  K, nw;
-	uint32_t n_used, n_nodes, n_rows, n_spec, err;
+	uint32_t n_used, n_nodes, n_rows, n_spec, n_jobs, err;
 	uint32_t totalreadbp;
 	uint32_t flag_a, flag_b, flag_c; uint32_t scan_emax, scan_wmax, ref_emax, ref_wmax;
 	// reference trimming state (Ref_t::seq/trim5/trim3, persists across k: SURVEY B4)
@@ -92,6 +92,7 @@ struct lb2_sh {
 	int32_t  numcomp;
 	uint32_t stop_k;
 	unsigned long long prof[24]; unsigned long long t_last;
+	uint32_t scan[260];           // block-scan partials
 };
 
 // phase ids for the optional cycle profile (lb2_dev_out::prof)
