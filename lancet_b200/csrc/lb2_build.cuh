@@ -233,7 +233,7 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 	for (int j = 0; j < LB2_MAXW; ++j) { f.w[j] = 0; rc.w[j] = 0; }
 	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
 	for (int i = 0; i < K; ++i, ++g) {          // warm-up: first K bases
-		if ((g & 15) == 0 || i == 0) { wordbuf = W.bits[g >> 4]; }
+		if ((g & 15) == 0 || i == 0) { wordbuf = lb2_lds(&W.bits[g >> 4]); }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
 		lb2_roll_fwd(f, K, c); lb2_roll_rc(rc, K, c);
 	}
@@ -254,7 +254,7 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 		if (normal) { lb2_or32(&W.t_em[su], LB2_EM_NORMAL); }
 	}
 	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
-		if ((g & 15) == 0) { wordbuf = W.bits[g >> 4]; }
+		if ((g & 15) == 0) { wordbuf = lb2_lds(&W.bits[g >> 4]); }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
 		int a = lb2_getbase(W.bits, g0 + o);                      // base that leaves the window
 		lb2_roll_fwd(f, K, c); lb2_roll_rc(rc, K, c);
@@ -304,13 +304,35 @@ LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2)
 	}
 }
 
+// reverse complement: complement, reverse the 2-bit groups of the 256-bit integer, shift down to 2K bits
+LB2_DEV uint64_t lb2_rev2(uint64_t x) {
+	x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+	x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+	x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+	x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+	return (x >> 32) | (x << 32);
+}
 LB2_DEV void lb2_revcomp(const lb2_kmer &f, int K, lb2_kmer &rc) {
-	for (int j = 0; j < LB2_MAXW; ++j) { rc.w[j] = 0; }
-	for (int i = 0; i < K; ++i) {
-		uint64_t c = 3 - ((f.w[i >> 5] >> ((i & 31) << 1)) & 3);
-		int t = K - 1 - i;
-		rc.w[t >> 5] |= c << ((t & 31) << 1);
+	const int nw = lb2_nw(K);
+	uint64_t t[LB2_MAXW];
+	// reversed words of the complement, as if the k-mer filled nw*32 bases; word order reversed within the nw words
+#pragma unroll
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		uint64_t v = 0;
+#pragma unroll
+		for (int s = 0; s < LB2_MAXW; ++s) { if (s == nw - 1 - j) { v = lb2_rev2(~f.w[s]); } }
+		t[j] = (j < nw) ? v : 0;
 	}
+	// the (nw*32 - K) pad bases now sit at the low end: shift right by 2*pad bits
+	const int sh = (nw * 32 - K) * 2;
+#pragma unroll
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		uint64_t hi = (j + 1 < LB2_MAXW) ? t[(j + 1 < LB2_MAXW) ? j + 1 : j] : 0;
+		rc.w[j] = sh ? ((t[j] >> sh) | (hi << (64 - sh))) : t[j];
+	}
+	lb2_mask_top(rc, K);
+#pragma unroll
+	for (int j = 0; j < LB2_MAXW; ++j) { if (j >= nw) { rc.w[j] = 0; } }
 }
 // canonical k-mer of a dense node (from its representative occurrence)
 LB2_DEV void lb2_rep_kmer(lb2_win &W, uint32_t rep, int K, lb2_kmer &km) {
@@ -458,7 +480,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 						if (iw & 0x40000000u) { continue; }               // suppressed (overlapping mate)
 						uint32_t id = W.t_occ[iw & 0x3FFFFFFFu];
 						uint32_t i = (iw >> 31) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
-						lb2_add32(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
+						lb2g_add32(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
 					}
 				}
 			}
@@ -527,11 +549,11 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
 				if (W.t_em[su] & LB2_EM_BRANCH) {
 					uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
-					lb2_min32(&ws.bseq[(size_t)W.t_occ[su] * 8 + t], 2 * (kb + o));
+					lb2g_min32(&ws.bseq[(size_t)W.t_occ[su] * 8 + t], 2 * (kb + o));
 				}
 				if (W.t_em[sv] & LB2_EM_BRANCH) {
 					uint32_t t = (1u - (iv >> 31)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
-					lb2_min32(&ws.bseq[(size_t)W.t_occ[sv] * 8 + t], 2 * (kb + o) + 1);
+					lb2g_min32(&ws.bseq[(size_t)W.t_occ[sv] * 8 + t], 2 * (kb + o) + 1);
 				}
 				iu = iv;
 			}

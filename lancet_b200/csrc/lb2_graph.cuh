@@ -645,22 +645,26 @@ LB2_DEVNI void lb2_materialize(lb2_win &W) {
 				if (t < mn) { mn = t; } if (qq < mnq) { mnq = qq; }
 			}
 		}
-		if (mn != 10000000) { lb2_min32((uint32_t *)&ws.d_mincov[jb.node], (uint32_t)mn); lb2_min32((uint32_t *)&ws.d_mincovqv[jb.node], (uint32_t)mnq); }
+		if (mn != 10000000) { lb2g_min32((uint32_t *)&ws.d_mincov[jb.node], (uint32_t)mn); lb2g_min32((uint32_t *)&ws.d_mincovqv[jb.node], (uint32_t)mnq); }
 	}
 }
 
 // Graph_t::compress (all lanes)
 LB2_DEVNI void lb2_compress(lb2_win &W, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	lb2_mark(W, LB2_PH_COMP_SEQ);
 	if (lb2_tid() == 0) { lb2_compress_sweep(W, compid); }
+	lb2_mark(W, LB2_PH_CSWEEP);
 	lb2_sync();
 	if (!sh->err) { lb2_materialize(W); }
 	lb2_sync();
+	lb2_mark(W, LB2_PH_CMAT);
 	if (lb2_tid() == 0 && !sh->err) {
 		const lb2_job *jobs = (const lb2_job *)ws.jobs;
 		for (uint32_t q = 0; q < sh->n_jobs; ++q) { const lb2_job &jb = jobs[q]; ws.d_str[jb.node] = jb.so; ws.d_cd[jb.node] = jb.co; ws.d_len[jb.node] = jb.curlen; }
 		lb2_clean_dead(W);
 	}
+	lb2_mark(W, LB2_PH_CCLEAN);
 	lb2_sync();
 }
 

@@ -26,45 +26,60 @@ LB2_DEV char lb2_comp(char c) { // rrc() of reference src/util.cc:246-258 for up
 }
 
 // read base g of a packed 2-bit array
-LB2_DEV int lb2_getbase(const uint32_t *bits, uint32_t g) { return (bits[g >> 4] >> ((g & 15) << 1)) & 3; }
-LB2_DEV int lb2_getbit(const uint32_t *mask, uint32_t g) { return (mask[g >> 5] >> (g & 31)) & 1; }
+LB2_DEV int lb2_getbase(const uint32_t *bits, uint32_t g) { return (lb2_lds(&bits[g >> 4]) >> ((g & 15) << 1)) & 3; }
+LB2_DEV int lb2_getbit(const uint32_t *mask, uint32_t g) { return (lb2_lds(&mask[g >> 5]) >> (g & 31)) & 1; }
+
+LB2_DEV void lb2_mask_top(struct lb2_kmer &k, int K);
 
 // extract K bases starting at base g (little-endian words)
 LB2_DEV void lb2_extract(const uint32_t *bits, uint32_t g, int K, lb2_kmer &out) {
 	int nw = lb2_nw(K);
 	uint32_t bitpos = g << 1;
+#pragma unroll
 	for (int j = 0; j < LB2_MAXW; ++j) {
 		if (j < nw) {
 			uint32_t bp = bitpos + (uint32_t)j * 64;
 			uint32_t wi = bp >> 5, sh = bp & 31;
-			uint64_t lo = bits[wi], mid = bits[wi + 1], hi = bits[wi + 2];
+			uint64_t lo = lb2_lds(&bits[wi]), mid = lb2_lds(&bits[wi + 1]), hi = lb2_lds(&bits[wi + 2]);
 			uint64_t v = (lo >> sh) | (mid << (32 - sh));
 			if (sh) { v |= hi << (64 - sh); }
 			out.w[j] = v;
 		} else { out.w[j] = 0; }
 	}
-	int rem = (K & 31);
-	if (rem) { out.w[nw - 1] &= (~0ull) >> (64 - 2 * rem); }
+	lb2_mask_top(out, K);
 }
 
+// (all indexing below is static after unrolling, so k-mers stay in registers)
+LB2_DEV void lb2_mask_top(lb2_kmer &k, int K) {
+	const int nw = lb2_nw(K), rem = (K & 31);
+	if (rem) {
+		const uint64_t m = (~0ull) >> (64 - 2 * rem);
+#pragma unroll
+		for (int j = 0; j < LB2_MAXW; ++j) { if (j == nw - 1) { k.w[j] &= m; } }
+	}
+}
 // rolling update: drop first base, append code c at position K-1
 LB2_DEV void lb2_roll_fwd(lb2_kmer &f, int K, int c) {
-	int nw = lb2_nw(K);
-	for (int j = 0; j < LB2_MAXW - 1; ++j) { if (j < nw - 1) { f.w[j] = (f.w[j] >> 2) | (f.w[j + 1] << 62); } }
-	f.w[nw - 1] >>= 2;
-	f.w[(K - 1) >> 5] |= (uint64_t)c << (((K - 1) & 31) << 1);
+	const int top = (K - 1) >> 5; const uint64_t ins = (uint64_t)c << (((K - 1) & 31) << 1);
+#pragma unroll
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		uint64_t nxt = (j + 1 < LB2_MAXW) ? f.w[(j + 1 < LB2_MAXW) ? j + 1 : j] : 0;
+		if (j < top) { f.w[j] = (f.w[j] >> 2) | (nxt << 62); }
+		else if (j == top) { f.w[j] = (f.w[j] >> 2) | ins; }
+	}
 }
 // reverse complement rolling update: prepend complement of c, drop last base
 LB2_DEV void lb2_roll_rc(lb2_kmer &r, int K, int c) {
-	int nw = lb2_nw(K);
+	const int nw = lb2_nw(K);
+#pragma unroll
 	for (int j = LB2_MAXW - 1; j > 0; --j) { if (j < nw) { r.w[j] = (r.w[j] << 2) | (r.w[j - 1] >> 62); } }
 	r.w[0] = (r.w[0] << 2) | (uint64_t)(3 - c);
-	int rem = (K & 31);
-	if (rem) { r.w[nw - 1] &= (~0ull) >> (64 - 2 * rem); }
+	lb2_mask_top(r, K);
 }
 
 // lexicographic a < b  (std::string operator<, equal -> false)
 LB2_DEV bool lb2_less(const lb2_kmer &a, const lb2_kmer &b, int nw) {
+#pragma unroll
 	for (int j = 0; j < LB2_MAXW; ++j) {
 		if (j < nw) {
 			uint64_t x = a.w[j] ^ b.w[j];
@@ -78,6 +93,7 @@ LB2_DEV bool lb2_less(const lb2_kmer &a, const lb2_kmer &b, int nw) {
 }
 LB2_DEV bool lb2_equal(const lb2_kmer &a, const lb2_kmer &b, int nw) {
 	bool eq = true;
+#pragma unroll
 	for (int j = 0; j < LB2_MAXW; ++j) { if (j < nw && a.w[j] != b.w[j]) { eq = false; } }
 	return eq;
 }
@@ -89,6 +105,7 @@ LB2_DEV uint64_t lb2_mix64(uint64_t x) {
 }
 LB2_DEV uint64_t lb2_table_hash(const lb2_kmer &k, int nw) {
 	uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
 	for (int j = 0; j < LB2_MAXW; ++j) { if (j < nw) { h = lb2_mix64(h ^ k.w[j]) + 0x632BE59BD9B4E019ull; } }
 	return h;
 }
@@ -128,9 +145,10 @@ LB2_DEV uint64_t lb2_stdhash_bytes(const char *p, uint32_t len) {
 // hash of the ASCII spelling of a packed k-mer
 LB2_DEV uint64_t lb2_stdhash_kmer(const lb2_kmer &k, int K) {
 	lb2_stdhash s; lb2_sh_init(s, (uint32_t)K);
-	for (int i = 0; i < K; ++i) {
-		int code = (int)((k.w[i >> 5] >> ((i & 31) << 1)) & 3);
-		lb2_sh_byte(s, (unsigned char)lb2_base(code));
+#pragma unroll
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		const uint64_t w = k.w[j];
+		for (int i = 0; i < 32 && j * 32 + i < K; ++i) { lb2_sh_byte(s, (unsigned char)lb2_base((int)((w >> (i << 1)) & 3))); }
 	}
 	return lb2_sh_final(s);
 }

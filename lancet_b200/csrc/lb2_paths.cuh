@@ -23,8 +23,8 @@
 // 16 mismatch flags (bit 2i = base p+i differs from base p+i+d) from the 2-bit packed sequence starting at base g0
 LB2_DEV uint32_t lb2_mm16(const uint32_t *bits, uint32_t g0, uint32_t p, uint32_t d) {
 	uint32_t ia = g0 + p, ib = ia + d;
-	uint32_t a0 = bits[ia >> 4], a1 = bits[(ia >> 4) + 1], sa = (ia & 15) << 1;
-	uint32_t b0 = bits[ib >> 4], b1 = bits[(ib >> 4) + 1], sb = (ib & 15) << 1;
+	uint32_t a0 = lb2_lds(&bits[ia >> 4]), a1 = lb2_lds(&bits[(ia >> 4) + 1]), sa = (ia & 15) << 1;
+	uint32_t b0 = lb2_lds(&bits[ib >> 4]), b1 = lb2_lds(&bits[(ib >> 4) + 1]), sb = (ib & 15) << 1;
 	uint32_t A = sa ? ((a0 >> sa) | (a1 << (32 - sa))) : a0;
 	uint32_t B = sb ? ((b0 >> sb) | (b1 << (32 - sb))) : b0;
 	uint32_t x = A ^ B;

@@ -106,6 +106,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				if (tid == 0) {
 					lb2_mark_ref_ends(W, c);
 					sh->flag_c = (!sh->err && lb2_has_cycle(W)) ? 1u : 0u;
+					lb2_mark(W, LB2_PH_ANCHOR);
 				}
 				lb2_sync();
 				if (!sh->flag_c && !sh->err) {

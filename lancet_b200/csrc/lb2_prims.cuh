@@ -17,15 +17,15 @@
 static inline unsigned lb2_tid()  { return 0; }
 static inline unsigned lb2_nthr() { return 1; }
 static inline void     lb2_sync() {}
-static inline uint64_t lb2_cas64(uint64_t *p, uint64_t cmp, uint64_t val) { uint64_t o = *p; if (o == cmp) *p = val; return o; }
 static inline uint32_t lb2_cas32(uint32_t *p, uint32_t cmp, uint32_t val) { uint32_t o = *p; if (o == cmp) *p = val; return o; }
 static inline uint32_t lb2_add32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
-static inline uint32_t lb2_sub32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o - v; return o; }
-static inline uint32_t lb2_max32(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
-static inline uint32_t lb2_min32(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
-static inline uint32_t lb2_or32 (uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
-static inline uint64_t lb2_ld64(const uint64_t *p) { return *p; }
+static inline void lb2_max32(uint32_t *p, uint32_t v) { if (v > *p) *p = v; }
+static inline void lb2_min32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
+static inline void lb2_or32 (uint32_t *p, uint32_t v) { *p |= v; }
+static inline uint32_t lb2g_add32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t lb2g_min32(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t lb2_ld32(const uint32_t *p) { return *p; }
+static inline uint32_t lb2_lds(const uint32_t *p) { return *p; }
 static inline int lb2_ctz64(uint64_t x) { return __builtin_ctzll(x); }
 static inline int lb2_clz32(uint32_t x) { return __builtin_clz(x); }
 static inline unsigned long long lb2_clock() { return 0; }
@@ -35,15 +35,19 @@ static inline unsigned long long lb2_clock() { return 0; }
 LB2_DEV unsigned lb2_tid()  { return threadIdx.x; }
 LB2_DEV unsigned lb2_nthr() { return blockDim.x; }
 LB2_DEV void     lb2_sync() { __syncthreads(); }
-LB2_DEV uint64_t lb2_cas64(uint64_t *p, uint64_t cmp, uint64_t val) { return atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)val); }
-LB2_DEV uint32_t lb2_cas32(uint32_t *p, uint32_t cmp, uint32_t val) { return atomicCAS(p, cmp, val); }
-LB2_DEV uint32_t lb2_add32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
-LB2_DEV uint32_t lb2_sub32(uint32_t *p, uint32_t v) { return atomicSub(p, v); }
-LB2_DEV uint32_t lb2_max32(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
-LB2_DEV uint32_t lb2_min32(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
-LB2_DEV uint32_t lb2_or32 (uint32_t *p, uint32_t v) { return atomicOr(p, v); }
-LB2_DEV uint64_t lb2_ld64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
-LB2_DEV uint32_t lb2_ld32(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+// lb2_* atomics act on SHARED memory (the Mer->Node table, window state): explicit .shared PTX, because a generic
+// atomic whose address happens to be shared takes the slow path.  lb2g_* are the few global-memory atomics.
+LB2_DEV uint32_t lb2_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LB2_DEV uint32_t lb2_cas32(uint32_t *p, uint32_t cmp, uint32_t val) { uint32_t o; asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(o) : "r"(lb2_saddr(p)), "r"(cmp), "r"(val) : "memory"); return o; }
+LB2_DEV uint32_t lb2_add32(uint32_t *p, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(lb2_saddr(p)), "r"(v) : "memory"); return o; }
+LB2_DEV void     lb2_max32(uint32_t *p, uint32_t v) { asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(lb2_saddr(p)), "r"(v) : "memory"); }
+LB2_DEV void     lb2_min32(uint32_t *p, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(lb2_saddr(p)), "r"(v) : "memory"); }
+LB2_DEV void     lb2_or32 (uint32_t *p, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(lb2_saddr(p)), "r"(v) : "memory"); }
+LB2_DEV uint32_t lb2_ld32(const uint32_t *p) { uint32_t o; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(o) : "r"(lb2_saddr(p)) : "memory"); return o; }
+// read-only shared data (packed bases, quality mask): plain ld.shared, free to be scheduled/merged by the compiler
+LB2_DEV uint32_t lb2_lds(const uint32_t *p) { uint32_t o; asm("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(lb2_saddr(p))); return o; }
+LB2_DEV uint32_t lb2g_add32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+LB2_DEV uint32_t lb2g_min32(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }
 LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
