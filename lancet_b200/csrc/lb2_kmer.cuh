@@ -98,16 +98,20 @@ LB2_DEV bool lb2_equal(const lb2_kmer &a, const lb2_kmer &b, int nw) {
 	return eq;
 }
 
-// table hash (not semantically significant -- only spreads keys over the open-addressing table)
-LB2_DEV uint64_t lb2_mix64(uint64_t x) {
-	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-	return x;
-}
+// table hash (not semantically significant -- only spreads keys over the open-addressing table); 32-bit ops only
 LB2_DEV uint64_t lb2_table_hash(const lb2_kmer &k, int nw) {
-	uint64_t h = 0x9E3779B97F4A7C15ull;
+	uint32_t h = 0x9E3779B9u, g = 0x85EBCA6Bu;
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) { if (j < nw) { h = lb2_mix64(h ^ k.w[j]) + 0x632BE59BD9B4E019ull; } }
-	return h;
+	for (int j = 0; j < LB2_MAXW; ++j) {
+		if (j < nw) {
+			uint32_t lo = (uint32_t)k.w[j], hi = (uint32_t)(k.w[j] >> 32);
+			h = (h ^ lo) * 0xCC9E2D51u; h = (h << 15) | (h >> 17);
+			g = (g ^ hi) * 0x1B873593u; g = (g << 13) | (g >> 19);
+			h += g;
+		}
+	}
+	h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; g ^= h; g *= 0xC2B2AE35u; g ^= g >> 16;
+	return ((uint64_t)g << 32) | h;
 }
 
 // ---- libstdc++ std::hash<std::string> == _Hash_bytes(p, len, 0xc70f6907) (64-bit murmur2 variant)

@@ -31,34 +31,39 @@ LB2_DEV uint32_t lb2_mm16(const uint32_t *bits, uint32_t g0, uint32_t p, uint32_
 	return (x | (x >> 1)) & 0x55555555u;
 }
 
-// the sequence is ACGT only and 2-bit packed at base index g0 of `bits` (two readable words past the end)
+// the sequence is ACGT only and 2-bit packed at base index g0 of `bits` (two readable words past the end).
+// One lane per diagonal walks only the MISMATCH positions q (ffs over 16 flags per XOR): with the previous
+// mismatches m1 > m2 > ... the zero run ending at q-1 has length q-m1-1 and the longest window ending at q-1
+// with <= max mismatches has length q - m_{max+1} - 1.
 LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int len, int maxmm)
 {
 	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	if (tid == 0) { sh->scan_emax = 0; sh->scan_wmax = 0; }
 	lb2_sync();
-	uint32_t emax = 0, wmax = 0;
+	int emax = 0, wmax = 0;
+	if (maxmm > 3) { maxmm = 3; if (tid == 0) { sh->err |= 1u << LB2_D_KMAX; } }
 	for (int d = 1 + (int)tid; d < len; d += (int)nt) {
 		const int np = len - d;                 // positions p in [0, np)
-		int run = 0, left = 0, mm = 0;
-		uint32_t lw = 0; int lbase = -16;       // cached flags of the chunk holding `left`
+		int m1 = -1, m2 = -1, m3 = -1, m4 = -1; // previous mismatch positions (virtual mismatch at -1)
 		for (int p0 = 0; p0 < np; p0 += 16) {
 			uint32_t fw = lb2_mm16(bits, g0, (uint32_t)p0, (uint32_t)d);
-			int lim = np - p0 < 16 ? np - p0 : 16;
-			for (int i = 0; i < lim; ++i) {
-				int p = p0 + i; int m = (int)((fw >> (2 * i)) & 1u);
-				if (p < np - 1) { if (m) { run = 0; } else { ++run; if ((uint32_t)run > emax) { emax = (uint32_t)run; } } }
-				mm += m;
-				while (mm > maxmm) {
-					if (left - lbase >= 16 || left < lbase) { lbase = left & ~15; lw = lb2_mm16(bits, g0, (uint32_t)lbase, (uint32_t)d); }
-					mm -= (int)((lw >> (2 * (left - lbase))) & 1u); ++left;
-				}
-				if ((uint32_t)(p - left + 1) > wmax) { wmax = (uint32_t)(p - left + 1); }
+			if (np - p0 < 16) { fw &= (1u << (2 * (np - p0))) - 1u; }
+			while (fw) {
+				int b = lb2_ctz32(fw); fw &= fw - 1;
+				int q = p0 + (b >> 1);
+				int run = q - m1 - 1; if (q == np - 1) { /* position np-1 is outside the exact-repeat range anyway */ }
+				if (run > emax) { emax = run; }
+				int far = (maxmm == 0) ? m1 : (maxmm == 1) ? m2 : (maxmm == 2) ? m3 : m4;
+				int win = q - far - 1; if (win > wmax) { wmax = win; }
+				m4 = m3; m3 = m2; m2 = m1; m1 = q;
 			}
 		}
+		// end of the diagonal: exact runs may use positions <= np-2, near-repeat windows positions <= np-1
+		{ int run = (np - 1) - m1 - 1; if (run > emax) { emax = run; } }
+		{ int far = (maxmm == 0) ? m1 : (maxmm == 1) ? m2 : (maxmm == 2) ? m3 : m4; int win = np - far - 1; if (win > wmax) { wmax = win; } }
 	}
-	if (emax) { lb2_max32(&sh->scan_emax, emax); }
-	if (wmax) { lb2_max32(&sh->scan_wmax, wmax); }
+	if (emax > 0) { lb2_max32(&sh->scan_emax, (uint32_t)emax); }
+	if (wmax > 0) { lb2_max32(&sh->scan_wmax, (uint32_t)wmax); }
 	lb2_sync();
 }
 

@@ -28,6 +28,7 @@ static inline uint32_t lb2_ld32(const uint32_t *p) { return *p; }
 static inline uint32_t lb2_lds(const uint32_t *p) { return *p; }
 static inline int lb2_ctz64(uint64_t x) { return __builtin_ctzll(x); }
 static inline int lb2_clz32(uint32_t x) { return __builtin_clz(x); }
+static inline int lb2_ctz32(uint32_t x) { return __builtin_ctz(x); }
 static inline unsigned long long lb2_clock() { return 0; }
 #else
 #define LB2_DEV   __device__ __forceinline__
@@ -50,6 +51,7 @@ LB2_DEV uint32_t lb2g_add32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 LB2_DEV uint32_t lb2g_min32(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }
+LB2_DEV int lb2_ctz32(uint32_t x) { return __ffs((int)x) - 1; }
 LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
 #endif
 
