@@ -195,10 +195,10 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 #define LB2_EM_TUMOR  0x200u
 #define LB2_EM_BRANCH 0x400u
 
-LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2_kmer &nonc, uint32_t rep, int K, int nw, bool insert)
+template <int NWT = LB2_MAXW> LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2_kmer &nonc, uint32_t rep, int K, int nw, bool insert)
 {
 	uint32_t *tk = W.t_key; const uint32_t mask = W.C->table_slots - 1;
-	uint64_t h = lb2_table_hash(canon, nw);
+	uint64_t h = lb2_table_hash<NWT>(canon, nw);
 	uint32_t i = (uint32_t)h & mask;
 	const uint32_t fp = 0x80000000u | (((uint32_t)(h >> 40) & 0x3FFu) << 21);
 	for (uint32_t probes = 0; probes <= mask; ++probes) {
@@ -215,8 +215,8 @@ LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2
 		}
 		if ((cur & 0xFFE00000u) == fp) {
 			uint32_t r = cur & 0x1FFFFFu;
-			lb2_kmer o; lb2_extract(W.bits, r >> 1, K, o);
-			if (lb2_equal(o, (r & 1) ? nonc : canon, nw)) { return i; }
+			lb2_kmer o; lb2_extract<NWT>(W.bits, r >> 1, K, o);
+			if (lb2_equal<NWT>(o, (r & 1) ? nonc : canon, nw)) { return i; }
 		}
 		i = (i + 1) & mask;
 	}
@@ -225,7 +225,7 @@ LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2
 }
 
 // one work item: a whole read, or a 64-pair chunk of the reference "read"
-LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uint32_t o_end, uint32_t kbase,
+template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uint32_t o_end, uint32_t kbase,
                       bool isref, uint32_t cls, int K, int nw)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
@@ -235,16 +235,16 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 	for (int i = 0; i < K; ++i, ++g) {          // warm-up: first K bases
 		if ((g & 15) == 0 || i == 0) { wordbuf = lb2_lds(&W.bits[g >> 4]); }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
-		lb2_roll_fwd(f, K, c); lb2_roll_rc(rc, K, c);
+		lb2_roll_fwd<NWT>(f, K, c); lb2_roll_rc<NWT>(rc, K, c);
 	}
 	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
 	const bool track_q = tumor && sh->has_lowq;
 	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u, csel = cls >> 1;
 	int lowcnt = 0;    // low-quality bases in [o, o+K-1]; the pair window adds base o+K
 	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
-	bool fless = lb2_less(f, rc, nw);
+	bool fless = lb2_less<NWT>(f, rc, nw);
 	uint32_t ori_u = fless ? 0u : 1u;
-	uint32_t su = lb2_find_or_insert(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
+	uint32_t su = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
 	lb2_max32(&W.t_occ[su], 0xFFFFFFFFu - (kbase + o_begin));
 	ws.inst[kbase + o_begin] = su | (ori_u << 31);
@@ -257,10 +257,10 @@ LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uin
 		if ((g & 15) == 0) { wordbuf = lb2_lds(&W.bits[g >> 4]); }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
 		int a = lb2_getbase(W.bits, g0 + o);                      // base that leaves the window
-		lb2_roll_fwd(f, K, c); lb2_roll_rc(rc, K, c);
-		fless = lb2_less(f, rc, nw);
+		lb2_roll_fwd<NWT>(f, K, c); lb2_roll_rc<NWT>(rc, K, c);
+		fless = lb2_less<NWT>(f, rc, nw);
 		uint32_t ori_v = fless ? 0u : 1u;
-		uint32_t sv = lb2_find_or_insert(W, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, K, nw, true);
+		uint32_t sv = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, K, nw, true);
 		if (sv == LB2_NIL) { return; }
 		lb2_max32(&W.t_occ[sv], 0xFFFFFFFFu - (kbase + o + 1));
 		ws.inst[kbase + o + 1] = sv | (ori_v << 31);
@@ -372,10 +372,16 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	for (uint32_t it = tid; it < R + nchunks; it += nt) {
 		if (it < R) {
 			uint32_t n = ws.rd_len[it];
-			if (n > (uint32_t)K) { lb2_walk(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
+			if (n > (uint32_t)K) {
+				if (nw == 1) { lb2_walk<1>(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
+				else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
+				else { lb2_walk<LB2_MAXW>(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
+			}
 		} else {
 			uint32_t c = it - R, ob = c * 64, oe = ob + 64; if (oe > nref_pairs) { oe = nref_pairs; }
-			lb2_walk(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw);
+			if (nw == 1) { lb2_walk<1>(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw); }
+			else if (nw == 2) { lb2_walk<2>(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw); }
+			else { lb2_walk<LB2_MAXW>(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw); }
 		}
 	}
 	lb2_sync();

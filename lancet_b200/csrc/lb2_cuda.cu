@@ -24,7 +24,7 @@ struct lb2_launch {
 	uint32_t *var_off; uint32_t *str_off; uint32_t *totals; lb2_variant *cvars; char *cstr;
 };
 
-__global__ void __launch_bounds__(LB2_THREADS)
+__global__ void __launch_bounds__(512)
 lb2_window_kernel(const lb2_launch *Lp)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -59,7 +59,7 @@ __global__ void lb2_collect_kernel(const lb2_launch *Lp)
 		if (wi.status == LB2_WIN_OVERFLOW) {
 			uint32_t d = wi.detail;
 			if (d == LB2_D_HASH_FULL || d == LB2_D_NODES || d == LB2_D_ARENA || d == LB2_D_QUEUE || d == LB2_D_SMEM || d == LB2_D_BUCKETS ||
-			    d == LB2_D_STACK || d == LB2_D_EDGES || d == LB2_D_SPECIAL) {
+			    d == LB2_D_STACK || d == LB2_D_EDGES || d == LB2_D_SPECIAL || d == LB2_D_READS) {
 				Lp->retry_list[atomicAdd(Lp->retry_count, 1u)] = w;
 			}
 		}
@@ -107,7 +107,7 @@ __global__ void lb2_gather_kernel(const lb2_launch *Lp)
 struct lb2_ctx {
 	int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
 	lb2_params P; lb2_cfg C;
-	int sm_count;
+	int sm_count; uint32_t threads = 256;
 	std::string err;
 	// device buffers of the resident batch
 	struct Buf { void *p = nullptr; size_t cap = 0; };
@@ -180,12 +180,13 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096); C.max_nodes = C.table_slots - C.table_slots / 4;
 	C.max_reads = 4096; C.max_bp = 0;
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
-	C.max_inst = env_u32("LB2_MAX_INST", 1u << 17);
+	C.max_inst = env_u32("LB2_MAX_INST", 1u << 18);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
 	C.bucket_cap = 10273; C.max_k = 127;
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
+	ctx->threads = env_u32("LB2_THREADS", 256); if (ctx->threads < 32 || ctx->threads > 512 || (ctx->threads & 31)) { ctx->threads = 256; }
 	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
 		delete ctx; return LB2_ERR_CUDA;
 	}
@@ -239,7 +240,7 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C.table_slots); C.max_reads = std::max(max_reads + 2, 64u);
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem_bytes));
 	int occ = 0;
-	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, LB2_THREADS, C.smem_bytes));
+	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, (int)ctx->threads, C.smem_bytes));
 	if (occ < 1) { ctx->err = "kernel does not fit on an SM"; return LB2_ERR_CUDA; }
 	uint32_t max_occ = env_u32("LB2_MAX_CTAS_PER_SM", 16);
 	C.n_slots = (uint32_t)ctx->sm_count * std::min<uint32_t>((uint32_t)occ, max_occ);
@@ -328,11 +329,11 @@ extern "C" int lb2_run(lb2_ctx *ctx)
 	LB2_CK(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
 	LB2_CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (W) {
-		lb2_window_kernel<<<ctx->C.n_slots, LB2_THREADS, ctx->C.smem_bytes, ctx->stream>>>(ctx->d_launch);
+		lb2_window_kernel<<<ctx->C.n_slots, ctx->threads, ctx->C.smem_bytes, ctx->stream>>>(ctx->d_launch);
 		if (ctx->escalate) {
 			LB2_CK(cudaMemsetAsync(ctx->d_counter2, 0, 4, ctx->stream)); LB2_CK(cudaMemsetAsync(ctx->d_retry_count, 0, 4, ctx->stream));
 			lb2_collect_kernel<<<64, 256, 0, ctx->stream>>>(ctx->d_launch);
-			lb2_window_kernel<<<ctx->C2.n_slots, LB2_THREADS, ctx->C2.smem_bytes, ctx->stream>>>(ctx->d_launch2);
+			lb2_window_kernel<<<ctx->C2.n_slots, ctx->threads, ctx->C2.smem_bytes, ctx->stream>>>(ctx->d_launch2);
 			ctx->launches += 2;
 		}
 		lb2_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_launch);

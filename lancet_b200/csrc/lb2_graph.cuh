@@ -295,9 +295,9 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 	// graph region: [low-quality mask | table region], both dead now
 	uint8_t *G = (uint8_t *)W.lowq; const size_t Gbytes = (size_t)(W.treg - (uint8_t *)W.lowq) + lb2_treg_bytes(W.C->table_slots);
 	// all-node emulation arrays sit at the END of the region, row arrays grow from the start
-	const size_t an_bytes = ((size_t)n * 2 * 2 + (size_t)Bfinal * 2 + 15) & ~(size_t)15;
+	const size_t an_bytes = ((size_t)n * 2 * 3 + (size_t)Bfinal * 2 + 15) & ~(size_t)15;
 	if (Bfinal == 0 || n >= 0xFFF0u || an_bytes > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
-	uint16_t *a_next = (uint16_t *)(G + Gbytes - an_bytes), *a_bk = a_next + n, *a_bkt = a_bk + n;
+	uint16_t *a_next = (uint16_t *)(G + Gbytes - an_bytes), *a_bk = a_next + n, *a_row = a_bk + n, *a_bkt = a_row + n;
 	const uint16_t NIL16 = 0xFFFF, SENT16 = 0xFFFE;
 	if (tid == 0) { sh->lhead = NIL16; sh->lowq_live = 0; }
 	uint32_t done = 0;
@@ -330,7 +330,7 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 	lb2_mark(W, LB2_PH_ORDER);
 	// ---- rows for the survivors (dense-id order), layout of the row-space arrays
 	uint32_t nrows = lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return (ws.b_flags[j] & LB2_NF_DEAD) ? 0u : 1u; },
-	                               [&](uint32_t j, uint32_t v) { ws.b_row[j] = (ws.b_flags[j] & LB2_NF_DEAD) ? LB2_NIL : v; });
+	                               [&](uint32_t j, uint32_t v) { bool dead = (ws.b_flags[j] & LB2_NF_DEAD) != 0; ws.b_row[j] = dead ? LB2_NIL : v; a_row[j] = dead ? NIL16 : (uint16_t)v; });
 	if (tid == 0) { sh->n_rows = nrows; sh->n_spec = 0; }
 	lb2_sync();
 	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
@@ -372,7 +372,7 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		// translate the list to row ids, dropping the dead; rebuild the bucket heads (before-begin pointers)
 		uint32_t prev = LB2_SENT; uint32_t head = LB2_NIL;
 		for (uint32_t p = sh->lhead; p != NIL16; p = a_next[p]) {
-			uint32_t r = ws.b_row[p]; if (r == LB2_NIL) { continue; }
+			uint32_t r = a_row[p]; if (r == NIL16) { continue; }
 			if (prev == LB2_SENT) { head = r; } else { ws.d_lnext[prev] = r; }
 			uint32_t b = ws.d_bk[r]; if (ws.buckets[b] == LB2_NIL) { ws.buckets[b] = prev; }
 			prev = r;
@@ -436,29 +436,39 @@ LB2_DEV uint32_t lb2_new_special(lb2_win &W, bool source, int compid) {
 
 // markRefEnds src/Graph.cc:2028-2228.  The reference looks every window k-mer up in the map; here the
 // dense node of the reference k-mer at each offset was recorded at build time (ws.refnode).
-LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {
+// all lanes: first / last reference offset whose node qualifies as an anchor, and the "same node matched twice" test
+LB2_DEVNI void lb2_find_anchors(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const int L = (int)sh->L;
+	const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const float thr = (float)W.P->cov_threshold;
+	if (tid == 0) { sh->anc_src = LB2_NIL; sh->anc_snk = 0; sh->anc_amb = 0; }
+	lb2_sync();
+	for (int off = (int)tid; off + K <= L; off += (int)nt) {
+		uint32_t nd = ws.refnode[off];
+		if (nd == LB2_NIL || (ws.d_flags[nd] & LB2_NF_GONE)) { continue; }
+		if (lb2_totcov(W, nd) >= thr && ws.d_comp[nd] == compid) { lb2_min32(&sh->anc_src, (uint32_t)off); lb2_max32(&sh->anc_snk, (uint32_t)off + 1u); }
+	}
+	lb2_sync();
+	if (sh->anc_src != LB2_NIL) {
+		const int so = (int)sh->anc_src, ko = (int)sh->anc_snk - 1;
+		const uint32_t sn = ws.refnode[so], kn = ws.refnode[ko];
+		uint32_t amb = 0;
+		for (int off = (int)tid; off + K <= L; off += (int)nt) {
+			uint32_t nd = ws.refnode[off];
+			if (off > so && nd == sn) { amb |= 1u; }
+			if (off < ko && nd == kn) { amb |= 2u; }
+		}
+		if (amb) { lb2_or32(&sh->anc_amb, amb); }
+	}
+	lb2_sync();
+}
+
+LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {   // lane 0, after lb2_find_anchors
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const int L = (int)sh->L;
 	sh->trim5 = 0xFFFF; sh->trim3 = 0xFFFF; sh->source = LB2_NIL; sh->sink = LB2_NIL;
-	uint32_t src = LB2_NIL, snk = LB2_NIL; int src_off = -1, snk_off = -1;
-	const float thr = (float)W.P->cov_threshold;
-	for (int off = 0; off + K <= L; ++off) {
-		uint32_t nd = ws.refnode[off];
-		if (nd == LB2_NIL || (ws.d_flags[nd] & LB2_NF_GONE)) { continue; }
-		if (lb2_totcov(W, nd) >= thr && ws.d_comp[nd] == compid) {
-			if (src == LB2_NIL) { src = nd; src_off = off; }
-			else if (src == nd) { return; }   // ambiguous match
-		}
-	}
-	if (src == LB2_NIL) { return; }
-	for (int off = L - K; off >= 0; --off) {
-		uint32_t nd = ws.refnode[off];
-		if (nd == LB2_NIL || (ws.d_flags[nd] & LB2_NF_GONE)) { continue; }
-		if (lb2_totcov(W, nd) >= thr && ws.d_comp[nd] == compid) {
-			if (snk == LB2_NIL) { snk = nd; snk_off = off; }
-			else if (snk == nd) { return; }
-		}
-	}
-	if (snk == LB2_NIL) { return; }
+	if (sh->anc_src == LB2_NIL || sh->anc_amb) { return; }     // no match / ambiguous match (source first, then sink)
+	const int src_off = (int)sh->anc_src, snk_off = (int)sh->anc_snk - 1;
+	const uint32_t src = ws.refnode[src_off], snk = ws.refnode[snk_off];
 	int ref_dist = snk_off - src_off + K;
 	// std::string::substr(pos, n) clamps n; a negative n (sink left of source) becomes npos => to the end
 	sh->seq_off = (uint32_t)src_off;
@@ -537,49 +547,69 @@ LB2_DEVNI bool lb2_has_cycle(lb2_win &W) {
 	return a1 || a2;
 }
 
-// ---- compressNode: walk one direction, literal edge surgery + float averages; bases/coverage of the
-//      absorbed nodes are laid out afterwards in one pass (see lb2_compress_one) ----------------------
+// ---- compressNode (src/Graph.cc:2486-2706) for one direction.  The reference rewrites the seed's edge vector after
+//      every absorbed buddy; only the last rewrite is observable (each intermediate edge is the unique edge erased by
+//      the next step, and the intermediate updateEdge targets are absorbed next), so the walk keeps the "current edge"
+//      in registers and performs the literal edge surgery once, for the last buddy.  Float averages, status counts and
+//      dead flags are applied per buddy in the reference's order.
 // chain entry: node id | flip<<31 (flip: buddy is reverse-complemented in the seed's frame)
 LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *chain, uint32_t nchain, uint32_t &curlen) {
 	lb2_ws &ws = W.ws; const int K = W.sh->K;
+	lb2_edge *const E = ws.d_edge; uint8_t *const NE = ws.d_ne; uint8_t *const FL = ws.d_flags;
+	float *const COV = ws.d_cov; uint32_t *const LEN = ws.d_len; uint32_t *const STN = ws.d_stn; uint32_t *const STT = ws.d_stT;
+	int uid = lb2_get_buddy(W, node, dir);
+	if (uid == -1) { return nchain; }
+	if (lb2_is_tandem(W, node)) { return nchain; }
+	uint32_t cur_to = E[(size_t)node * LB2_ECAP + uid].to; int cur_dir = E[(size_t)node * LB2_ECAP + uid].dir;
+	uint32_t last = LB2_NIL; int last_buid = -1, last_edir = 0;
+	float c0 = COV[node * 4 + 0], c1 = COV[node * 4 + 1], c2 = COV[node * 4 + 2], c3 = COV[node * 4 + 3];
+	uint32_t stn = STN[node], stt = STT[node];
 	while (true) {
-		int uid = lb2_get_buddy(W, node, dir);
-		if (uid == -1) { break; }
-		if (lb2_is_tandem(W, node)) { break; }
-		lb2_edge *ne_ = ws.d_edge + (size_t)node * LB2_ECAP;
-		int edir = ne_[uid].dir;
-		int bdir = (edir == LB2_FF || edir == LB2_RF) ? 1 : 0;
-		uint32_t buddy = ne_[uid].to;
-		if (lb2_is_tandem(W, buddy)) { break; }
-		int buid = lb2_get_buddy(W, buddy, bdir);
-		if (buid == -1) { break; }
-		// orientation of the buddy in the seed's frame
-		int dest_r = lb2_dir_dest(edir);               // 1 => buddy string is reverse-complemented in the walking frame
-		uint32_t flip = (dir == 0) ? (uint32_t)dest_r : (uint32_t)(dest_r ^ 1);
-		chain[nchain++] = buddy | (flip << 31);
-		// float coverage, same expression order as src/Graph.cc:2631-2636
-		int amerlen = (int)curlen - K + 1, bmerlen = (int)ws.d_len[buddy] - K + 1;
-		for (int c = 0; c < 4; ++c) {
-			float nc = ws.d_cov[node * 4 + c], cc = ws.d_cov[buddy * 4 + c];
-			ws.d_cov[node * 4 + c] = ((nc * amerlen) + (cc * bmerlen)) / (amerlen + bmerlen);
-		}
-		curlen += (uint32_t)bmerlen;
-		ws.d_stn[node] += ws.d_stn[buddy]; ws.d_stT[node] += ws.d_stT[buddy];
-		ws.d_flags[buddy] |= LB2_NF_DEAD;
-		// node edges: erase the buddy edge, move over the buddy's other edges
-		{ int ne = ws.d_ne[node]; for (int j = uid; j + 1 < ne; ++j) { ne_[j] = ne_[j + 1]; } ws.d_ne[node] = (uint8_t)(ne - 1); }
-		lb2_edge *be = ws.d_edge + (size_t)buddy * LB2_ECAP; int bne = ws.d_ne[buddy];
+		const int edir = cur_dir; const uint32_t buddy = cur_to;
+		const int bdir = (edir == LB2_FF || edir == LB2_RF) ? 1 : 0;
+		if (FL[buddy] & LB2_NF_SPECIAL) { break; }                    // getBuddy of a special node is -1
+		const lb2_edge *be = E + (size_t)buddy * LB2_ECAP; const int bne = NE[buddy];
+		int buid = -1, nb = 0; bool tandem = false;
 		for (int i = 0; i < bne; ++i) {
-			if (i == buid) { continue; }
-			int nd = be[i].dir; if (edir == LB2_FR || edir == LB2_RF) { nd = lb2_flipme(nd); }
-			uint32_t other = be[i].to;
-			if (other == buddy) { lb2_push_edge(W, node, node, nd, be[i].flag); }   // "circle to buddy"
-			else {
-				lb2_push_edge(W, node, other, nd, be[i].flag);
-				lb2_update_edge(W, other, buddy, lb2_fliplink(be[i].dir), node, lb2_fliplink(nd));
-			}
+			lb2_edge e = be[i];
+			if (e.to == buddy) { tandem = true; }
+			if (lb2_is_dir(e.dir, bdir)) { ++nb; buid = i; }
 		}
-		if (W.sh->err) { break; }
+		if (tandem || nb != 1) { break; }                              // buddy->isTandem(), buddy->getBuddy(bdir) == -1
+		// absorb the buddy
+		const int dest_r = lb2_dir_dest(edir);
+		const uint32_t flip = (dir == 0) ? (uint32_t)dest_r : (uint32_t)(dest_r ^ 1);
+		chain[nchain++] = buddy | (flip << 31);
+		const int amerlen = (int)curlen - K + 1, bmerlen = (int)LEN[buddy] - K + 1;
+		// same expression order as src/Graph.cc:2631-2636
+		c0 = ((c0 * amerlen) + (COV[buddy * 4 + 0] * bmerlen)) / (amerlen + bmerlen);
+		c1 = ((c1 * amerlen) + (COV[buddy * 4 + 1] * bmerlen)) / (amerlen + bmerlen);
+		c2 = ((c2 * amerlen) + (COV[buddy * 4 + 2] * bmerlen)) / (amerlen + bmerlen);
+		c3 = ((c3 * amerlen) + (COV[buddy * 4 + 3] * bmerlen)) / (amerlen + bmerlen);
+		curlen += (uint32_t)bmerlen; stn += STN[buddy]; stt += STT[buddy];
+		FL[buddy] |= LB2_NF_DEAD;
+		last = buddy; last_buid = buid; last_edir = edir;
+		if (bne - 1 != 1) { break; }                                   // the seed would have 0 or >= 2 edges in `dir`
+		const lb2_edge f = be[buid == 0 ? 1 : 0];
+		int nd = f.dir; if (edir == LB2_FR || edir == LB2_RF) { nd = lb2_flipme(nd); }
+		const uint32_t nto = (f.to == buddy) ? node : f.to;
+		if (nto == node) { break; }                                    // self edge: getBuddy -> -1
+		cur_to = nto; cur_dir = nd;
+	}
+	if (last == LB2_NIL) { return nchain; }
+	COV[node * 4 + 0] = c0; COV[node * 4 + 1] = c1; COV[node * 4 + 2] = c2; COV[node * 4 + 3] = c3; STN[node] = stn; STT[node] = stt;
+	// the literal edge surgery of the last step: erase the seed's edge in `dir`, move over the last buddy's other edges
+	{ lb2_edge *ne_ = E + (size_t)node * LB2_ECAP; int ne = NE[node]; for (int j = uid; j + 1 < ne; ++j) { ne_[j] = ne_[j + 1]; } NE[node] = (uint8_t)(ne - 1); }
+	const lb2_edge *be = E + (size_t)last * LB2_ECAP; const int bne = NE[last];
+	for (int i = 0; i < bne; ++i) {
+		if (i == last_buid) { continue; }
+		int nd = be[i].dir; if (last_edir == LB2_FR || last_edir == LB2_RF) { nd = lb2_flipme(nd); }
+		uint32_t other = be[i].to;
+		if (other == last) { lb2_push_edge(W, node, node, nd, be[i].flag); }   // "circle to buddy"
+		else {
+			lb2_push_edge(W, node, other, nd, be[i].flag);
+			lb2_update_edge(W, other, last, lb2_fliplink(be[i].dir), node, lb2_fliplink(nd));
+		}
 	}
 	return nchain;
 }

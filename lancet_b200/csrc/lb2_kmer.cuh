@@ -29,14 +29,14 @@ LB2_DEV char lb2_comp(char c) { // rrc() of reference src/util.cc:246-258 for up
 LB2_DEV int lb2_getbase(const uint32_t *bits, uint32_t g) { return (lb2_lds(&bits[g >> 4]) >> ((g & 15) << 1)) & 3; }
 LB2_DEV int lb2_getbit(const uint32_t *mask, uint32_t g) { return (lb2_lds(&mask[g >> 5]) >> (g & 31)) & 1; }
 
-LB2_DEV void lb2_mask_top(struct lb2_kmer &k, int K);
+template <int NWT> LB2_DEV void lb2_mask_top(struct lb2_kmer &k, int K);
 
 // extract K bases starting at base g (little-endian words)
-LB2_DEV void lb2_extract(const uint32_t *bits, uint32_t g, int K, lb2_kmer &out) {
+template <int NWT = LB2_MAXW> LB2_DEV void lb2_extract(const uint32_t *bits, uint32_t g, int K, lb2_kmer &out) {
 	int nw = lb2_nw(K);
 	uint32_t bitpos = g << 1;
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
+	for (int j = 0; j < NWT; ++j) {
 		if (j < nw) {
 			uint32_t bp = bitpos + (uint32_t)j * 64;
 			uint32_t wi = bp >> 5, sh = bp & 31;
@@ -46,41 +46,41 @@ LB2_DEV void lb2_extract(const uint32_t *bits, uint32_t g, int K, lb2_kmer &out)
 			out.w[j] = v;
 		} else { out.w[j] = 0; }
 	}
-	lb2_mask_top(out, K);
+	lb2_mask_top<NWT>(out, K);
 }
 
 // (all indexing below is static after unrolling, so k-mers stay in registers)
-LB2_DEV void lb2_mask_top(lb2_kmer &k, int K) {
+template <int NWT = LB2_MAXW> LB2_DEV void lb2_mask_top(lb2_kmer &k, int K) {
 	const int nw = lb2_nw(K), rem = (K & 31);
 	if (rem) {
 		const uint64_t m = (~0ull) >> (64 - 2 * rem);
 #pragma unroll
-		for (int j = 0; j < LB2_MAXW; ++j) { if (j == nw - 1) { k.w[j] &= m; } }
+		for (int j = 0; j < NWT; ++j) { if (j == nw - 1) { k.w[j] &= m; } }
 	}
 }
 // rolling update: drop first base, append code c at position K-1
-LB2_DEV void lb2_roll_fwd(lb2_kmer &f, int K, int c) {
+template <int NWT = LB2_MAXW> LB2_DEV void lb2_roll_fwd(lb2_kmer &f, int K, int c) {
 	const int top = (K - 1) >> 5; const uint64_t ins = (uint64_t)c << (((K - 1) & 31) << 1);
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
-		uint64_t nxt = (j + 1 < LB2_MAXW) ? f.w[(j + 1 < LB2_MAXW) ? j + 1 : j] : 0;
+	for (int j = 0; j < NWT; ++j) {
+		uint64_t nxt = (j + 1 < NWT) ? f.w[(j + 1 < NWT) ? j + 1 : j] : 0;
 		if (j < top) { f.w[j] = (f.w[j] >> 2) | (nxt << 62); }
 		else if (j == top) { f.w[j] = (f.w[j] >> 2) | ins; }
 	}
 }
 // reverse complement rolling update: prepend complement of c, drop last base
-LB2_DEV void lb2_roll_rc(lb2_kmer &r, int K, int c) {
+template <int NWT = LB2_MAXW> LB2_DEV void lb2_roll_rc(lb2_kmer &r, int K, int c) {
 	const int nw = lb2_nw(K);
 #pragma unroll
-	for (int j = LB2_MAXW - 1; j > 0; --j) { if (j < nw) { r.w[j] = (r.w[j] << 2) | (r.w[j - 1] >> 62); } }
+	for (int j = NWT - 1; j > 0; --j) { if (j < nw) { r.w[j] = (r.w[j] << 2) | (r.w[j - 1] >> 62); } }
 	r.w[0] = (r.w[0] << 2) | (uint64_t)(3 - c);
-	lb2_mask_top(r, K);
+	lb2_mask_top<NWT>(r, K);
 }
 
 // lexicographic a < b  (std::string operator<, equal -> false)
-LB2_DEV bool lb2_less(const lb2_kmer &a, const lb2_kmer &b, int nw) {
+template <int NWT = LB2_MAXW> LB2_DEV bool lb2_less(const lb2_kmer &a, const lb2_kmer &b, int nw) {
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
+	for (int j = 0; j < NWT; ++j) {
 		if (j < nw) {
 			uint64_t x = a.w[j] ^ b.w[j];
 			if (x) {
@@ -91,18 +91,18 @@ LB2_DEV bool lb2_less(const lb2_kmer &a, const lb2_kmer &b, int nw) {
 	}
 	return false;
 }
-LB2_DEV bool lb2_equal(const lb2_kmer &a, const lb2_kmer &b, int nw) {
+template <int NWT = LB2_MAXW> LB2_DEV bool lb2_equal(const lb2_kmer &a, const lb2_kmer &b, int nw) {
 	bool eq = true;
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) { if (j < nw && a.w[j] != b.w[j]) { eq = false; } }
+	for (int j = 0; j < NWT; ++j) { if (j < nw && a.w[j] != b.w[j]) { eq = false; } }
 	return eq;
 }
 
 // table hash (not semantically significant -- only spreads keys over the open-addressing table); 32-bit ops only
-LB2_DEV uint64_t lb2_table_hash(const lb2_kmer &k, int nw) {
+template <int NWT = LB2_MAXW> LB2_DEV uint64_t lb2_table_hash(const lb2_kmer &k, int nw) {
 	uint32_t h = 0x9E3779B9u, g = 0x85EBCA6Bu;
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
+	for (int j = 0; j < NWT; ++j) {
 		if (j < nw) {
 			uint32_t lo = (uint32_t)k.w[j], hi = (uint32_t)(k.w[j] >> 32);
 			h = (h ^ lo) * 0xCC9E2D51u; h = (h << 15) | (h >> 17);

@@ -103,6 +103,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			bool retry = false;
 			const int numcomp = sh->numcomp;
 			for (int c = 1; c <= numcomp; ++c) {
+				lb2_find_anchors(W, c);
 				if (tid == 0) {
 					lb2_mark_ref_ends(W, c);
 					sh->flag_c = (!sh->err && lb2_has_cycle(W)) ? 1u : 0u;

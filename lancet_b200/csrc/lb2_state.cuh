@@ -83,7 +83,7 @@ struct lb2_sh {
 	// order emulation
 	uint32_t bkt_count, bkt_cap, elem_count, next_resize, lhead;
 	// anchors
-	uint32_t source, sink;
+	uint32_t source, sink, anc_src, anc_snk, anc_amb;
 	uint32_t arena_used, tstr_used;
 	// path
 	uint32_t plen, pn, need_align, n_trans, path_found, aln_len;
@@ -92,7 +92,7 @@ struct lb2_sh {
 	int32_t  numcomp;
 	uint32_t stop_k;
 	unsigned long long prof[24]; unsigned long long t_last;
-	uint32_t scan[260];           // block-scan partials
+	uint32_t scan[520];           // block-scan partials (<= 512 lanes)
 };
 
 // phase ids for the optional cycle profile (lb2_dev_out::prof)

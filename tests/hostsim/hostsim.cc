@@ -38,7 +38,7 @@ int main(int argc, char **argv)
 
 	lb2_cfg C; memset(&C, 0, sizeof C);
 	C.table_slots = 16384; C.max_nodes = 12000; C.max_reads = 8192; C.max_bp = (1 << 20) - 1024; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
-	C.queue_cap = 1 << 18; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
+	C.queue_cap = 1 << 22; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
 	if (getenv("LB2_SIM_TS")) { C.table_slots = atoi(getenv("LB2_SIM_TS")); C.max_nodes = C.table_slots - C.table_slots / 4; }
 	if (getenv("LB2_SIM_BP")) { C.max_bp = atoi(getenv("LB2_SIM_BP")); }
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
