@@ -22,7 +22,7 @@ struct lb2_win {
 	uint32_t *lowq;      // smem: 1 bit per staged base: quality < MIN_QUAL_CALL
 	char     *ref_raw;   // smem: window reference, ASCII
 	uint8_t  *treg;      // smem region T: Mer->Node table during the build, graph-stage arrays afterwards
-	uint32_t *t_key, *t_occ, *t_cnt, *t_em;
+	uint32_t *t_key; uint16_t *t_id;   // smem: table keys; slot -> dense node id (bit 15: needs first-seen edge order)
 };
 
 LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2);
@@ -53,6 +53,34 @@ LB2_DEV uint32_t lb2_excl_scan(lb2_win &W, uint32_t n, Get get, Set set)
 
 LB2_DEV void lb2_fail(lb2_win &W, uint32_t status, uint32_t detail) {
 	if (lb2_cas32(&W.sh->status, LB2_WIN_OK, status) == LB2_WIN_OK) { W.sh->detail = detail; }
+}
+
+// 2-bit packed bases of the trimmed reads and of the window reference.  The packed bases' shared memory is lent to the
+// order emulation after every build (k-mer strings of the surviving nodes are copied out first), so the bases are
+// staged again before the build of a later k.
+LB2_DEVNI void lb2_stage_bits(lb2_win &W)
+{
+	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
+	const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t R = sh->R, L = sh->L; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
+	for (uint32_t r = tid; r < R; r += nt) {
+		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
+		const char *s = B->seq + B->base_off[widx[r]] + ws.rd_t5[r];
+		uint32_t g = ws.rd_start[r];
+		for (uint32_t b0 = 0; b0 < n; b0 += 16) {
+			uint32_t bw = 0, m = (n - b0 < 16) ? (n - b0) : 16;
+			for (uint32_t i = 0; i < m; ++i) { bw |= (uint32_t)lb2_code(s[b0 + i]) << (2 * i); }
+			W.bits[(g + b0) >> 4] = bw;
+		}
+	}
+	const uint32_t g = sh->ref_g;
+	for (uint32_t b0 = tid * 16; b0 < ((L + 15u) & ~15u) + 64; b0 += nt * 16) {
+		uint32_t bw = 0;
+		for (uint32_t i = 0; i < 16 && b0 + i < L; ++i) { bw |= (uint32_t)(lb2_code(W.ref_raw[b0 + i]) & 3) << (2 * i); }
+		W.bits[(g + b0) >> 4] = bw;
+	}
+	if (tid == 0) { sh->bits_live = 1; }
+	lb2_sync();
 }
 
 // low-quality mask (quality < MIN_QUAL_CALL) of the staged bases.  The mask's shared memory is lent to the
@@ -157,28 +185,8 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		}
 		lb2_sync();
 	}
-	for (uint32_t r = tid; r < R; r += nt) {
-		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
-		uint32_t idx = widx[r];
-		uint64_t o0 = B->base_off[idx] + ws.rd_t5[r];
-		const char *s = B->seq + o0;
-		uint32_t g = ws.rd_start[r];
-		for (uint32_t b0 = 0; b0 < n; b0 += 16) {
-			uint32_t bw = 0;
-			uint32_t m = (n - b0 < 16) ? (n - b0) : 16;
-			for (uint32_t i = 0; i < m; ++i) { bw |= (uint32_t)lb2_code(s[b0 + i]) << (2 * i); }
-			W.bits[(g + b0) >> 4] = bw;
-		}
-	}
+	lb2_stage_bits(W);
 	lb2_stage_lowq(W);
-	{
-		uint32_t g = sh->ref_g;
-		for (uint32_t b0 = tid * 32; b0 < ((L + 31u) & ~31u) + 64; b0 += nt * 32) {
-			uint64_t bw = 0;
-			for (uint32_t i = 0; i < 32 && b0 + i < L; ++i) { bw |= (uint64_t)(lb2_code(W.ref_raw[b0 + i]) & 3) << (2 * i); }
-			W.bits[(g + b0) >> 4] = (uint32_t)bw; W.bits[((g + b0) >> 4) + 1] = (uint32_t)(bw >> 32);
-		}
-	}
 	lb2_sync();
 }
 
@@ -186,14 +194,15 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 // Mer -> Node table in SHARED memory (region T), TS = cfg.table_slots slots, per slot:
 //   t_key  u32  0x80000000 | fingerprint10 << 21 | (g << 1 | ori): g = staged base index of one
 //               representative occurrence (matches are verified against the packed bases)
-//   t_occ  u32  0xFFFFFFFF - first occurrence (atomicMax); after the sort: dense node id
-//   t_cnt  2xu32  tumour / normal occurrence counts, fwd in the low half, rev in the high half
-//   t_em   u32  bits 0-7 edge types seen (start orientation*4 + appended base), bit 8 normal,
-//               bit 9 tumour-qualified, bit 10 "branching" (needs first-seen edge order)
+//   t_id   u16  (after the sort) dense node id, bit 15 = "branching" (needs first-seen edge order)
+// and, in GLOBAL memory, fed by fire-and-forget reductions (nothing on the lane's critical path reads them back):
+//   g_occ  u32  0xFFFFFFFF - first occurrence (max)
+//   g_cnt  2xu32  tumour / normal occurrence counts, fwd in the low half, rev in the high half (add)
+//   g_em   u32  bits 0-7 edge types seen (start orientation*4 + appended base), bit 8 normal, bit 9 tumour-qualified (or)
 // ---------------------------------------------------------------------------------------------
 #define LB2_EM_NORMAL 0x100u
 #define LB2_EM_TUMOR  0x200u
-#define LB2_EM_BRANCH 0x400u
+#define LB2_ID_BRANCH 0x8000u
 
 template <int NWT = LB2_MAXW> LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2_kmer &nonc, uint32_t rep, int K, int nw, bool insert)
 {
@@ -246,12 +255,12 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 	uint32_t ori_u = fless ? 0u : 1u;
 	uint32_t su = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
-	lb2_max32(&W.t_occ[su], 0xFFFFFFFFu - (kbase + o_begin));
+	lb2g_red_max(&ws.g_occ[su], 0xFFFFFFFFu - (kbase + o_begin));
 	ws.inst[kbase + o_begin] = su | (ori_u << 31);
 	if (isref) { ws.refnode[o_begin] = su; }
 	else if (o_begin == 0) {
-		lb2_add32(&W.t_cnt[su * 2 + csel], cadd);
-		if (normal) { lb2_or32(&W.t_em[su], LB2_EM_NORMAL); }
+		lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
+		if (normal) { lb2g_red_or(&ws.g_em[su], LB2_EM_NORMAL); }
 	}
 	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
 		if ((g & 15) == 0) { wordbuf = lb2_lds(&W.bits[g >> 4]); }
@@ -262,13 +271,13 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 		uint32_t ori_v = fless ? 0u : 1u;
 		uint32_t sv = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, K, nw, true);
 		if (sv == LB2_NIL) { return; }
-		lb2_max32(&W.t_occ[sv], 0xFFFFFFFFu - (kbase + o + 1));
+		lb2g_red_max(&ws.g_occ[sv], 0xFFFFFFFFu - (kbase + o + 1));
 		ws.inst[kbase + o + 1] = sv | (ori_v << 31);
 		uint32_t emu = 1u << (ori_u * 4 + (uint32_t)c);            // u leaves in orientation ori_u appending c
 		uint32_t emv = 1u << ((1u - ori_v) * 4 + (uint32_t)(3 - a)); // v leaves in the flipped orientation appending comp(a)
 		if (isref) { ws.refnode[o + 1] = sv; }
 		else {
-			lb2_add32(&W.t_cnt[sv * 2 + csel], cadd);
+			lb2g_red_add(&ws.g_cnt[sv * 2 + csel], cadd);
 			if (normal) { emv |= LB2_EM_NORMAL; }
 			if (tumor) {
 				bool clean = true;
@@ -280,7 +289,7 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 				if (clean) { emu |= LB2_EM_TUMOR; emv |= LB2_EM_TUMOR; }
 			}
 		}
-		lb2_or32(&W.t_em[su], emu); lb2_or32(&W.t_em[sv], emv);
+		lb2g_red_or(&ws.g_em[su], emu); lb2g_red_or(&ws.g_em[sv], emv);
 		su = sv; ori_u = ori_v;
 	}
 }
@@ -352,8 +361,9 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const int nw = lb2_nw(K);
 	const uint32_t R = sh->R, L = sh->L, TS = C->table_slots;
+	if (!sh->bits_live) { lb2_stage_bits(W); }
 	if (!sh->lowq_live && sh->has_lowq) { lb2_stage_lowq(W); }
-	W.t_key = (uint32_t *)W.treg; W.t_occ = W.t_key + TS; W.t_cnt = W.t_occ + TS; W.t_em = W.t_cnt + 2 * (size_t)TS;
+	W.t_key = (uint32_t *)W.treg; W.t_id = (uint16_t *)(W.t_key + TS);
 	uint32_t kcum = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { uint32_t n = ws.rd_len[r]; return (n > (uint32_t)K) ? (n - K + 1) : 0; },
 	                              [&](uint32_t r, uint32_t v) { ws.rd_kbase[r] = v; });
 	if (tid == 0) {
@@ -364,7 +374,8 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		if (cum + L + 2 > C->max_inst) { sh->err |= 1u << LB2_D_READS; }
 	}
 	for (uint32_t i = tid; i < LB2_MAX_REF; i += nt) { ws.refnode[i] = LB2_NIL; }
-	for (uint32_t i = tid; i < TS * 5; i += nt) { W.t_key[i] = 0; }      // t_key, t_occ, t_cnt, t_em are contiguous
+	for (uint32_t i = tid; i < TS; i += nt) { W.t_key[i] = 0; }
+	for (uint32_t i = tid; i < TS * 4; i += nt) { ws.g_occ[i] = 0; }      // g_occ, g_cnt, g_em are contiguous
 	lb2_sync();
 	if (sh->err) { return; }
 	const uint32_t nref_pairs = (L > (uint32_t)K) ? (L - K) : 0;
@@ -391,12 +402,12 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	const uint32_t n = sh->n_used;
 	uint32_t n2 = 1; while (n2 < n) { n2 <<= 1; }
 	for (uint32_t j = tid; j < n2; j += nt) {
-		if (j < n) { uint32_t s = ws.used[j]; ws.sortk[j] = ((uint64_t)(0xFFFFFFFFu - W.t_occ[s]) << 32) | s; }
+		if (j < n) { uint32_t s = ws.used[j]; ws.sortk[j] = ((uint64_t)(0xFFFFFFFFu - ws.g_occ[s]) << 32) | s; }
 		else { ws.sortk[j] = ~0ull; }
 	}
 	lb2_sync();
 	lb2_sort64(ws.sortk, n2);
-	for (uint32_t j = tid; j < n; j += nt) { uint32_t s = (uint32_t)ws.sortk[j]; W.t_occ[s] = j; ws.used[j] = s; }   // t_occ := slot -> dense id, used := dense id -> slot
+	for (uint32_t j = tid; j < n; j += nt) { uint32_t s = (uint32_t)ws.sortk[j]; W.t_id[s] = (uint16_t)j; ws.used[j] = s; }   // slot -> dense id, used := dense id -> slot
 	lb2_sync();
 	for (uint32_t j = tid; j < n; j += nt) {
 		uint32_t s = ws.used[j];
@@ -404,15 +415,15 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		ws.b_rep[j] = rep;
 		lb2_kmer km; lb2_rep_kmer(W, rep, K, km);
 		ws.b_hash[j] = lb2_stdhash_kmer(km, K);
-		uint32_t ct = W.t_cnt[s * 2], cn = W.t_cnt[s * 2 + 1];
+		uint32_t ct = ws.g_cnt[s * 2], cn = ws.g_cnt[s * 2 + 1];
 		uint32_t v[4] = { ct & 0xFFFFu, ct >> 16, cn & 0xFFFFu, cn >> 16 }, tot = 0;
 		for (int c = 0; c < 4; ++c) { ws.b_cnt[j * 4 + c] = v[c]; tot += v[c]; }
-		uint32_t em = W.t_em[s];
+		uint32_t em = ws.g_em[s];
 		ws.b_stT[j] = ((em & (LB2_EM_NORMAL | LB2_EM_TUMOR)) == LB2_EM_TUMOR) ? 1u : 0u;   // cov_status 'T': tumour-qualified, never normal
 		ws.b_mincovqv[j] = (int32_t)tot;
 		ws.b_flags[j] = 0; ws.b_ne[j] = 0;
 	}
-	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t s = ws.refnode[p]; if (s != LB2_NIL) { ws.refnode[p] = W.t_occ[s]; } }
+	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t s = ws.refnode[p]; if (s != LB2_NIL) { ws.refnode[p] = W.t_id[s]; } }
 	if (tid == 0) { sh->n_nodes = n; sh->last_nodes = n; }
 	lb2_sync();
 	lb2_mark(W, LB2_PH_COMPACT);
@@ -424,7 +435,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	if (sh->has_pairs) {
 		const uint32_t total = ws.rd_kbase[R];
 		uint32_t t2 = 1; while (t2 < total) { t2 <<= 1; }
-		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)W.t_occ[ws.inst[x] & 0x3FFFFFFFu] << 32) | x) : ~0ull; }
+		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)W.t_id[ws.inst[x] & 0x3FFFFFFFu] << 32) | x) : ~0ull; }
 		lb2_sync();
 		lb2_sort64(ws.sortk, t2);
 		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
@@ -484,7 +495,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					for (uint32_t p = p0; p <= p1; ++p) {
 						uint32_t iw = ws.inst[kb + p];
 						if (iw & 0x40000000u) { continue; }               // suppressed (overlapping mate)
-						uint32_t id = W.t_occ[iw & 0x3FFFFFFFu];
+						uint32_t id = W.t_id[iw & 0x3FFFFFFFu];
 						uint32_t i = (iw >> 31) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
 						lb2g_add32(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
 					}
@@ -520,7 +531,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	// ---- edges of the survivors: every edge type (start orientation, appended base) names one neighbour
 	for (uint32_t j = tid; j < n; j += nt) {
 		if (ws.b_flags[j] & LB2_NF_DEAD) { continue; }
-		uint32_t s = ws.used[j]; uint32_t em = W.t_em[s] & 0xFFu;
+		uint32_t s = ws.used[j]; uint32_t em = ws.g_em[s] & 0xFFu;
 		lb2_kmer C0; lb2_rep_kmer(W, ws.b_rep[j], K, C0);
 		lb2_kmer C1; lb2_revcomp(C0, K, C1);
 		int ne = 0, nF = 0, nR = 0;
@@ -532,19 +543,21 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			bool fl = lb2_less(V, Vr, nw);
 			uint32_t ts = lb2_find_or_insert(W, fl ? V : Vr, fl ? Vr : V, 0, K, nw, false);
 			if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); break; }
-			uint32_t to = W.t_occ[ts];
+			uint32_t to = W.t_id[ts] & 0x7FFFu;
 			if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
 			lb2_bedge ed; ed.to = to; ed.dir = (uint32_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.type = (uint32_t)t;
 			ws.b_edge[(size_t)j * LB2_BECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
 		}
 		ws.b_ne[j] = (uint8_t)ne;
 		if (nF > 1 || nR > 1) {   // first-seen order matters only among edges leaving in the same orientation
-			lb2_or32(&W.t_em[s], LB2_EM_BRANCH); sh->flag_a = 1;
+			ws.b_flags[j] |= 0x20; sh->flag_a = 1;      // slot's branch bit is set after the barrier (t_id is being read by other lanes)
 			for (int t = 0; t < 8; ++t) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
 		}
 	}
 	lb2_sync();
 	if (sh->flag_a && !sh->err) {
+		for (uint32_t j = tid; j < n; j += nt) { if (ws.b_flags[j] & 0x20) { W.t_id[ws.used[j]] |= LB2_ID_BRANCH; } }
+		lb2_sync();
 		for (uint32_t it = tid; it < R + 1; it += nt) {
 			uint32_t g0, np, kb;
 			if (it < R) { uint32_t n_ = ws.rd_len[it]; if (n_ <= (uint32_t)K) { continue; } g0 = ws.rd_start[it]; np = n_ - K; kb = ws.rd_kbase[it]; }
@@ -553,20 +566,20 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			for (uint32_t o = 0; o < np; ++o) {
 				uint32_t iv = ws.inst[kb + o + 1];
 				uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
-				if (W.t_em[su] & LB2_EM_BRANCH) {
+				if (W.t_id[su] & LB2_ID_BRANCH) {
 					uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
-					lb2g_min32(&ws.bseq[(size_t)W.t_occ[su] * 8 + t], 2 * (kb + o));
+					lb2g_min32(&ws.bseq[(size_t)(W.t_id[su] & 0x7FFFu) * 8 + t], 2 * (kb + o));
 				}
-				if (W.t_em[sv] & LB2_EM_BRANCH) {
+				if (W.t_id[sv] & LB2_ID_BRANCH) {
 					uint32_t t = (1u - (iv >> 31)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
-					lb2g_min32(&ws.bseq[(size_t)W.t_occ[sv] * 8 + t], 2 * (kb + o) + 1);
+					lb2g_min32(&ws.bseq[(size_t)(W.t_id[sv] & 0x7FFFu) * 8 + t], 2 * (kb + o) + 1);
 				}
 				iu = iv;
 			}
 		}
 		lb2_sync();
 		for (uint32_t j = tid; j < n; j += nt) {
-			if (!(W.t_em[ws.used[j]] & LB2_EM_BRANCH)) { continue; }
+			if (!(ws.b_flags[j] & 0x20)) { continue; }
 			lb2_bedge *e = ws.b_edge + (size_t)j * LB2_BECAP; int ne = ws.b_ne[j];
 			for (int a = 1; a < ne; ++a) {
 				lb2_bedge x = e[a]; uint32_t sx = ws.bseq[(size_t)j * 8 + x.type]; int b = a - 1;

@@ -45,6 +45,7 @@ struct lb2_cfg {
 	uint32_t str_bytes;     // string pool per window
 	uint32_t bucket_cap;    // buckets for the libstdc++ order emulation (prime >= max_nodes)
 	uint32_t max_k;         // largest k supported by the per-k dense arrays
+	uint32_t graph_bytes;   // shared memory for the graph-stage arrays (quality-mask bytes included)
 	uint32_t n_slots;       // resident CTAs (workspace slabs)
 	uint32_t smem_bytes;    // dynamic shared memory per CTA
 };

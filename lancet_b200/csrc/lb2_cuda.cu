@@ -182,7 +182,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 18);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
-	C.bucket_cap = 10273; C.max_k = 127;
+	C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
@@ -234,10 +234,10 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	if (max_bp > (1u << 20) - 1024) { max_bp = (1u << 20) - 1024; }   // representative base index has 20 bits in the table key
 	lb2_cfg &C = ctx->C;
 	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096);
-	while (C.table_slots > 1024 && lb2_smem_bytes(max_bp, C.table_slots) > smem_cap) { C.table_slots >>= 1; }
-	while (lb2_smem_bytes(max_bp, C.table_slots) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
+	while (C.table_slots > 1024 && lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes) > smem_cap) { C.table_slots >>= 1; }
+	while (lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
 	C.max_nodes = C.table_slots - C.table_slots / 4;
-	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C.table_slots); C.max_reads = std::max(max_reads + 2, 64u);
+	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes); C.max_reads = std::max(max_reads + 2, 64u);
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem_bytes));
 	int occ = 0;
 	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, (int)ctx->threads, C.smem_bytes));
@@ -296,10 +296,11 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	if (ctx->escalate) {
 		// escalation pass: the largest table that still fits beside the staged reads, big arena / BFS queue, one CTA per SM
 		lb2_cfg &C2 = ctx->C2; C2 = C;
-		C2.table_slots = 8192;
-		while (C2.table_slots > C.table_slots && lb2_smem_bytes(max_bp, C2.table_slots) > smem_cap) { C2.table_slots >>= 1; }
+		C2.table_slots = 8192; C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 150u << 10);
+		while (C2.graph_bytes > C.graph_bytes && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.graph_bytes -= 4096; }
+		while (C2.table_slots > C.table_slots && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.table_slots >>= 1; }
 		C2.max_nodes = C2.table_slots - C2.table_slots / 4;
-		C2.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C2.table_slots);
+		C2.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes);
 		C2.arena_bytes = env_u32("LB2_ARENA_BYTES2", 8u << 20); C2.deficit_bytes = env_u32("LB2_DEFICIT_BYTES2", 16u << 20);
 		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 22); C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20);
 		C2.n_slots = (uint32_t)std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 64));

@@ -22,6 +22,14 @@ LB2_DEV bool lb2_is_dir(int d, int ori) { return lb2_dir_start(d) == ori; }
 LB2_DEV int  lb2_flipme(int d)   { return d == LB2_FF ? LB2_RF : d == LB2_FR ? LB2_RR : d == LB2_RF ? LB2_FF : LB2_FR; }
 LB2_DEV int  lb2_fliplink(int d) { return d == LB2_FF ? LB2_RR : d == LB2_FR ? LB2_FR : d == LB2_RF ? LB2_RF : LB2_FF; }
 
+// ---- edge storage: 4 half-edges inline per row, nodes that need more move to a 12-slot block of a small pool
+#define LB2_EINL 4
+#define LB2_EOV_BLOCKS 96
+LB2_DEV lb2_edge *lb2_edges(lb2_ws &ws, uint32_t id) {
+	uint32_t ov = ws.d_eov[id];
+	return ov ? (ws.e_pool + (size_t)(ov - 1) * LB2_ECAP) : (ws.d_edge + (size_t)id * LB2_EINL);
+}
+
 // ---- node accessors ------------------------------------------------------------------------------
 LB2_DEV bool lb2_special(lb2_win &W, uint32_t id) { return (W.ws.d_flags[id] & LB2_NF_SPECIAL) != 0; }
 LB2_DEV uint32_t lb2_strlen(lb2_win &W, uint32_t id) { return lb2_special(W, id) ? 0u : W.ws.d_len[id]; }   // Node_t::strlen src/Node.cc:340-345
@@ -89,6 +97,8 @@ LB2_DEV uint32_t lb2_arena_alloc(lb2_win &W, uint32_t bytes) {
 }
 
 // ---- libstdc++ _Hashtable order emulation -----------------------------------------------------------
+LB2_DEV uint32_t lb2_bget(lb2_win &W, uint32_t b) { uint32_t v = W.ws.buckets[b]; return v >= 0xFFFEu ? (v | 0xFFFF0000u) : v; }   // 0xFFFF -> LB2_NIL, 0xFFFE -> LB2_SENT
+LB2_DEV void lb2_bset(lb2_win &W, uint32_t b, uint32_t v) { W.ws.buckets[b] = (uint16_t)v; }
 LB2_DEV uint32_t lb2_oe_next(lb2_win &W, uint32_t x) { return x == LB2_SENT ? W.sh->lhead : W.ws.d_lnext[x]; }
 LB2_DEV void lb2_oe_setnext(lb2_win &W, uint32_t x, uint32_t v) { if (x == LB2_SENT) { W.sh->lhead = v; } else { W.ws.d_lnext[x] = v; } }
 LB2_DEV uint32_t lb2_oe_next_bkt(uint32_t x) {
@@ -98,22 +108,22 @@ LB2_DEV uint32_t lb2_oe_next_bkt(uint32_t x) {
 }
 LB2_DEV void lb2_oe_reset(lb2_win &W) {
 	lb2_sh *sh = W.sh; sh->bkt_count = 1; sh->elem_count = 0; sh->next_resize = 0; sh->lhead = LB2_NIL;
-	W.ws.buckets[0] = LB2_NIL;
+	lb2_bset(W, 0, LB2_NIL);
 }
 LB2_DEV void lb2_oe_rehash(lb2_win &W, uint32_t nb) {   // _M_rehash_aux (unique keys); rare here (only a source/sink insert can trigger it)
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	if (nb > W.sh->bkt_cap) { sh->err |= 1u << LB2_D_BUCKETS; return; }
-	for (uint32_t b = 0; b < nb; ++b) { ws.buckets[b] = LB2_NIL; }
+	for (uint32_t b = 0; b < nb; ++b) { lb2_bset(W, b, LB2_NIL); }
 	uint32_t p = sh->lhead; sh->lhead = LB2_NIL; uint32_t bbegin = 0;
 	while (p != LB2_NIL) {
 		uint32_t nx = ws.d_lnext[p];
 		uint32_t b = (uint32_t)(ws.d_hash[p] % nb); ws.d_bk[p] = b;
-		if (ws.buckets[b] == LB2_NIL) {
-			ws.d_lnext[p] = sh->lhead; sh->lhead = p; ws.buckets[b] = LB2_SENT;
-			if (ws.d_lnext[p] != LB2_NIL) { ws.buckets[bbegin] = p; }
+		if (lb2_bget(W, b) == LB2_NIL) {
+			ws.d_lnext[p] = sh->lhead; sh->lhead = p; lb2_bset(W, b, LB2_SENT);
+			if (ws.d_lnext[p] != LB2_NIL) { lb2_bset(W, bbegin, p); }
 			bbegin = b;
 		} else {
-			uint32_t before = ws.buckets[b];
+			uint32_t before = lb2_bget(W, b);
 			ws.d_lnext[p] = lb2_oe_next(W, before); lb2_oe_setnext(W, before, p);
 		}
 		p = nx;
@@ -135,31 +145,31 @@ LB2_DEV void lb2_oe_insert(lb2_win &W, uint32_t id) {   // _M_insert_unique_node
 		} else { sh->next_resize = sh->bkt_count; }
 	}
 	uint32_t b = (uint32_t)(ws.d_hash[id] % sh->bkt_count); ws.d_bk[id] = b;
-	if (ws.buckets[b] != LB2_NIL) {
-		uint32_t before = ws.buckets[b];
+	if (lb2_bget(W, b) != LB2_NIL) {
+		uint32_t before = lb2_bget(W, b);
 		ws.d_lnext[id] = lb2_oe_next(W, before); lb2_oe_setnext(W, before, id);
 	} else {
 		ws.d_lnext[id] = sh->lhead; sh->lhead = id;
-		if (ws.d_lnext[id] != LB2_NIL) { ws.buckets[ws.d_bk[ws.d_lnext[id]]] = id; }
-		ws.buckets[b] = LB2_SENT;
+		if (ws.d_lnext[id] != LB2_NIL) { lb2_bset(W, ws.d_bk[ws.d_lnext[id]], id); }
+		lb2_bset(W, b, LB2_SENT);
 	}
 	sh->elem_count = n + 1;
 }
 LB2_DEV void lb2_oe_erase(lb2_win &W, uint32_t id) {    // _M_erase(bkt, prev, n)
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	uint32_t b = ws.d_bk[id];
-	uint32_t prev = ws.buckets[b];
+	uint32_t prev = lb2_bget(W, b);
 	while (lb2_oe_next(W, prev) != id) { prev = lb2_oe_next(W, prev); }
 	uint32_t nx = ws.d_lnext[id];
-	if (prev == ws.buckets[b]) {
+	if (prev == lb2_bget(W, b)) {
 		uint32_t nb = (nx != LB2_NIL) ? ws.d_bk[nx] : 0;
 		if (nx == LB2_NIL || nb != b) {
-			if (nx != LB2_NIL) { ws.buckets[nb] = ws.buckets[b]; }
-			ws.buckets[b] = LB2_NIL;   // (before_begin.next is updated by the unlink below)
+			if (nx != LB2_NIL) { lb2_bset(W, nb, lb2_bget(W, b)); }
+			lb2_bset(W, b, LB2_NIL);   // (before_begin.next is updated by the unlink below)
 		}
 	} else if (nx != LB2_NIL) {
 		uint32_t nb = ws.d_bk[nx];
-		if (nb != b) { ws.buckets[nb] = prev; }
+		if (nb != b) { lb2_bset(W, nb, prev); }
 	}
 	lb2_oe_setnext(W, prev, nx);
 	sh->elem_count -= 1;
@@ -168,7 +178,7 @@ LB2_DEV void lb2_oe_erase(lb2_win &W, uint32_t id) {    // _M_erase(bkt, prev, n
 
 // ---- edge helpers (Node_t::removeEdge / updateEdge, src/Node.cc:177-233) ------------------------------
 LB2_DEV void lb2_remove_edge(lb2_win &W, uint32_t id, uint32_t to, int dir) {
-	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	lb2_ws &ws = W.ws; lb2_edge *e = lb2_edges(ws, id); int ne = ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) {
 		if (e[i].to == to && e[i].dir == dir) {
 			for (int j = i; j + 1 < ne; ++j) { e[j] = e[j + 1]; }
@@ -178,7 +188,7 @@ LB2_DEV void lb2_remove_edge(lb2_win &W, uint32_t id, uint32_t to, int dir) {
 	W.sh->err |= 1u << LB2_D_EDGES;   // the reference would assert here
 }
 LB2_DEV void lb2_update_edge(lb2_win &W, uint32_t id, uint32_t oldto, int olddir, uint32_t newto, int newdir) {
-	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	lb2_ws &ws = W.ws; lb2_edge *e = lb2_edges(ws, id); int ne = ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) {
 		if (e[i].to == oldto && e[i].dir == olddir) { e[i].to = (uint16_t)newto; e[i].dir = (uint16_t)newdir; return; }
 	}
@@ -187,17 +197,25 @@ LB2_DEV void lb2_update_edge(lb2_win &W, uint32_t id, uint32_t oldto, int olddir
 LB2_DEV void lb2_push_edge(lb2_win &W, uint32_t id, uint32_t to, int dir, int flag) {
 	lb2_ws &ws = W.ws; int ne = ws.d_ne[id];
 	if (ne >= LB2_ECAP) { W.sh->err |= 1u << LB2_D_EDGES; return; }
+	if (ne == LB2_EINL && !ws.d_eov[id]) {          // outgrew the inline slots: move to a pool block
+		uint32_t blk = W.sh->n_eov;
+		if (blk >= LB2_EOV_BLOCKS) { W.sh->err |= 1u << LB2_D_EDGES; return; }
+		W.sh->n_eov = blk + 1;
+		lb2_edge *src = ws.d_edge + (size_t)id * LB2_EINL, *dst = ws.e_pool + (size_t)blk * LB2_ECAP;
+		for (int i = 0; i < LB2_EINL; ++i) { dst[i] = src[i]; }
+		ws.d_eov[id] = (uint8_t)(blk + 1);
+	}
 	lb2_edge ed; ed.to = (uint16_t)to; ed.dir = (uint16_t)dir; ed.flag = (uint16_t)flag; ed.pad = 0;
-	ws.d_edge[(size_t)id * LB2_ECAP + ne] = ed; ws.d_ne[id] = (uint8_t)(ne + 1);
+	lb2_edges(ws, id)[ne] = ed; ws.d_ne[id] = (uint8_t)(ne + 1);
 }
 LB2_DEV void lb2_add_edge_node(lb2_win &W, uint32_t id, uint32_t to, int dir) {   // Node_t::addEdge without read ids
-	lb2_ws &ws = W.ws; lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	lb2_ws &ws = W.ws; lb2_edge *e = lb2_edges(ws, id); int ne = ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) { if (e[i].to == to && e[i].dir == dir) { return; } }
 	lb2_push_edge(W, id, to, dir, 0);
 }
 LB2_DEV void lb2_remove_node(lb2_win &W, uint32_t id) {   // Graph_t::removeNode
 	lb2_ws &ws = W.ws; ws.d_flags[id] |= LB2_NF_DEAD;
-	lb2_edge *e = ws.d_edge + (size_t)id * LB2_ECAP; int ne = ws.d_ne[id];
+	lb2_edge *e = lb2_edges(ws, id); int ne = ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) { if (e[i].to != id) { lb2_remove_edge(W, e[i].to, id, lb2_fliplink(e[i].dir)); } }
 }
 LB2_DEV void lb2_clean_dead(lb2_win &W) {                 // Graph_t::cleanDead
@@ -206,13 +224,13 @@ LB2_DEV void lb2_clean_dead(lb2_win &W) {                 // Graph_t::cleanDead
 	while (p != LB2_NIL) { uint32_t nx = ws.d_lnext[p]; if (ws.d_flags[p] & LB2_NF_DEAD) { lb2_oe_erase(W, p); } p = nx; }
 }
 LB2_DEV bool lb2_is_tandem(lb2_win &W, uint32_t id) {     // Node_t::isTandem
-	lb2_edge *e = W.ws.d_edge + (size_t)id * LB2_ECAP; int ne = W.ws.d_ne[id];
+	lb2_edge *e = lb2_edges(W.ws, id); int ne = W.ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) { if (e[i].to == id) { return true; } }
 	return false;
 }
 LB2_DEV int lb2_get_buddy(lb2_win &W, uint32_t id, int ori) {   // Node_t::getBuddy
 	if (lb2_special(W, id)) { return -1; }
-	lb2_edge *e = W.ws.d_edge + (size_t)id * LB2_ECAP; int ne = W.ws.d_ne[id]; int r = -1;
+	lb2_edge *e = lb2_edges(W.ws, id); int ne = W.ws.d_ne[id]; int r = -1;
 	for (int i = 0; i < ne; ++i) { if (lb2_is_dir(e[i].dir, ori)) { if (r != -1) { return -1; } r = i; } }
 	if (r != -1 && e[r].to == id) { return -1; }
 	return r;
@@ -290,16 +308,35 @@ LB2_DEV uint32_t lb2_level_bkt(uint32_t n_before) {   // bucket count in force w
 LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
-	const uint32_t n = sh->n_nodes;
+	const uint32_t n = sh->n_nodes; const int K = sh->K;
 	const uint32_t Bfinal = n ? lb2_level_bkt(n - 1) : 13;
 	// graph region: [low-quality mask | table region], both dead now
-	uint8_t *G = (uint8_t *)W.lowq; const size_t Gbytes = (size_t)(W.treg - (uint8_t *)W.lowq) + lb2_treg_bytes(W.C->table_slots);
-	// all-node emulation arrays sit at the END of the region, row arrays grow from the start
+	uint8_t *G = (uint8_t *)W.lowq; const size_t Gbytes = (size_t)(W.treg - (uint8_t *)W.lowq) + lb2_treg_bytes(W.C->table_slots, W.C->graph_bytes, W.C->max_bp);
+	// rows for the survivors (dense-id order); their k-mer spellings leave the packed reads for the arena, because the
+	// packed reads' shared memory is about to hold the all-node emulation arrays
+	uint32_t nrows = lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return (ws.b_flags[j] & LB2_NF_DEAD) ? 0u : 1u; },
+	                               [&](uint32_t j, uint32_t v) { ws.b_row[j] = (ws.b_flags[j] & LB2_NF_DEAD) ? LB2_NIL : v; });
+	if (tid == 0) {
+		sh->n_rows = nrows; sh->n_spec = 0; sh->arena_used = 8 + nrows * (uint32_t)K;
+		if (sh->arena_used + 64 > W.C->arena_bytes) { sh->err |= 1u << LB2_D_ARENA; }
+	}
+	lb2_sync();
+	if (sh->err) { return; }
+	for (uint32_t j = tid; j < n; j += nt) {
+		uint32_t r = ws.b_row[j]; if (r == LB2_NIL) { continue; }
+		uint32_t rep = ws.b_rep[j], g0 = rep >> 1; char *dst = (char *)ws.arena + 8 + (size_t)r * K;
+		if (rep & 1) { for (int i = 0; i < K; ++i) { dst[i] = lb2_base(3 - lb2_getbase(W.bits, g0 + K - 1 - i)); } }
+		else { for (int i = 0; i < K; ++i) { dst[i] = lb2_base(lb2_getbase(W.bits, g0 + i)); } }
+	}
+	lb2_sync();
+	// all-node emulation arrays live where the packed reads were
 	const size_t an_bytes = ((size_t)n * 2 * 3 + (size_t)Bfinal * 2 + 15) & ~(size_t)15;
-	if (Bfinal == 0 || n >= 0xFFF0u || an_bytes > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
-	uint16_t *a_next = (uint16_t *)(G + Gbytes - an_bytes), *a_bk = a_next + n, *a_row = a_bk + n, *a_bkt = a_row + n;
+	const size_t bits_bytes = ((size_t)W.C->max_bp / 16 + 4) * 4;
+	if (Bfinal == 0 || n >= 0x7FF0u || an_bytes > bits_bytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
+	uint16_t *a_next = (uint16_t *)W.bits, *a_bk = a_next + n, *a_row = a_bk + n, *a_bkt = a_row + n;
 	const uint16_t NIL16 = 0xFFFF, SENT16 = 0xFFFE;
-	if (tid == 0) { sh->lhead = NIL16; sh->lowq_live = 0; }
+	for (uint32_t j = tid; j < n; j += nt) { uint32_t r = ws.b_row[j]; a_row[j] = (r == LB2_NIL) ? NIL16 : (uint16_t)r; }
+	if (tid == 0) { sh->lhead = NIL16; sh->lowq_live = 0; sh->bits_live = 0; }
 	uint32_t done = 0;
 	while (done < n) {
 		const uint32_t B = lb2_level_bkt(done); uint32_t end = B < n ? B : n;     // elements [done, end) arrive at this bucket count
@@ -328,26 +365,24 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		lb2_sync();
 	}
 	lb2_mark(W, LB2_PH_ORDER);
-	// ---- rows for the survivors (dense-id order), layout of the row-space arrays
-	uint32_t nrows = lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return (ws.b_flags[j] & LB2_NF_DEAD) ? 0u : 1u; },
-	                               [&](uint32_t j, uint32_t v) { bool dead = (ws.b_flags[j] & LB2_NF_DEAD) != 0; ws.b_row[j] = dead ? LB2_NIL : v; a_row[j] = dead ? NIL16 : (uint16_t)v; });
-	if (tid == 0) { sh->n_rows = nrows; sh->n_spec = 0; }
-	lb2_sync();
+	// ---- layout of the row-space arrays
 	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
 	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
 	{
 		size_t off = 0;
 #define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; ws.field = (type *)(G + off); off += sizeof(type) * (size_t)(count); } while (0)
-		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint32_t, bcap);
-		LB2_GT(d_cov, float, NT * 4); LB2_GT(d_len, uint32_t, NT); LB2_GT(d_stn, uint32_t, NT); LB2_GT(d_stT, uint32_t, NT);
-		LB2_GT(d_comp, int32_t, NT); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8); LB2_GT(d_edge, lb2_edge, NT * LB2_ECAP);
-		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT);
+		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint16_t, bcap);
+		LB2_GT(d_cov, float, NT * 4); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8);
+		LB2_GT(d_edge, lb2_edge, NT * LB2_EINL); LB2_GT(e_pool, lb2_edge, LB2_EOV_BLOCKS * LB2_ECAP);
+		LB2_GT(d_len, uint16_t, NT); LB2_GT(d_stn, uint16_t, NT); LB2_GT(d_stT, uint16_t, NT); LB2_GT(d_comp, int16_t, NT);
+		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT); LB2_GT(d_eov, uint8_t, NT);
 #undef LB2_GT
 		ws.chain = ws.stack;
-		if (NT > LB2_MAX_ROWS || off + an_bytes > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
+		if (NT > LB2_MAX_ROWS || off > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
 	}
-	if (tid == 0) { sh->bkt_cap = bcap; sh->bkt_count = Bfinal; sh->next_resize = Bfinal; sh->elem_count = NR; }
-	const int K = sh->K;
+	if (tid == 0) { sh->bkt_cap = bcap; sh->bkt_count = Bfinal; sh->next_resize = Bfinal; sh->elem_count = NR; sh->n_eov = 0; }
+	for (uint32_t r = tid; r < NT; r += nt) { ws.d_eov[r] = 0; ws.d_ne[r] = 0; }
+	lb2_sync();
 	for (uint32_t j = tid; j < n; j += nt) {
 		uint32_t r = ws.b_row[j]; if (r == LB2_NIL) { continue; }
 		ws.d_bk[r] = a_bk[j];
@@ -356,25 +391,32 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		ws.d_len[r] = (uint32_t)K; ws.d_stn[r] = 1; ws.d_stT[r] = ws.b_stT[j]; ws.d_comp[r] = 0;
 		ws.d_flags[r] = 0; ws.d_color[r] = 0;
 		ws.d_rep[r] = ws.b_rep[j]; ws.d_hash[r] = ws.b_hash[j]; ws.d_orig[r] = j;
-		ws.d_mincov[r] = (int32_t)tot; ws.d_mincovqv[r] = ws.b_mincovqv[j]; ws.d_str[r] = LB2_NIL; ws.d_cd[r] = LB2_NIL;
+		ws.d_mincov[r] = (int32_t)tot; ws.d_mincovqv[r] = ws.b_mincovqv[j]; ws.d_str[r] = 8 + r * (uint32_t)K; ws.d_cd[r] = LB2_NIL;
 		int ne = ws.b_ne[j];
-		for (int e = 0; e < ne; ++e) {
-			lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e];
-			lb2_edge ed; ed.to = (uint16_t)ws.b_row[be.to]; ed.dir = (uint16_t)be.dir; ed.flag = 0; ed.pad = 0;
-			ws.d_edge[(size_t)r * LB2_ECAP + e] = ed;
-		}
-		ws.d_ne[r] = (uint8_t)ne;
+		if (ne <= LB2_EINL) {
+			for (int e = 0; e < ne; ++e) {
+				lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e];
+				lb2_edge ed; ed.to = (uint16_t)ws.b_row[be.to]; ed.dir = (uint16_t)be.dir; ed.flag = 0; ed.pad = 0;
+				ws.d_edge[(size_t)r * LB2_EINL + e] = ed;
+			}
+			ws.d_ne[r] = (uint8_t)ne;
+		} else { ws.d_ne[r] = 0xFF; }      // more than the inline slots: lane 0 fills these below (pool allocation is serial)
 	}
 	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t j = ws.refnode[p]; if (j != LB2_NIL) { ws.refnode[p] = ws.b_row[j]; } }
-	for (uint32_t b = tid; b < bcap; b += nt) { ws.buckets[b] = LB2_NIL; }
+	for (uint32_t b = tid; b < bcap; b += nt) { lb2_bset(W, b, LB2_NIL); }
 	lb2_sync();
 	if (tid == 0) {
+		for (uint32_t j = 0; j < n; ++j) {      // (rare) nodes with more than LB2_EINL edges
+			uint32_t r = a_row[j]; if (r == NIL16 || ws.d_ne[r] != 0xFF) { continue; }
+			ws.d_ne[r] = 0; int ne = ws.b_ne[j];
+			for (int e = 0; e < ne; ++e) { lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e]; lb2_push_edge(W, r, ws.b_row[be.to], (int)be.dir, 0); }
+		}
 		// translate the list to row ids, dropping the dead; rebuild the bucket heads (before-begin pointers)
 		uint32_t prev = LB2_SENT; uint32_t head = LB2_NIL;
 		for (uint32_t p = sh->lhead; p != NIL16; p = a_next[p]) {
 			uint32_t r = a_row[p]; if (r == NIL16) { continue; }
 			if (prev == LB2_SENT) { head = r; } else { ws.d_lnext[prev] = r; }
-			uint32_t b = ws.d_bk[r]; if (ws.buckets[b] == LB2_NIL) { ws.buckets[b] = prev; }
+			uint32_t b = ws.d_bk[r]; if (lb2_bget(W, b) == LB2_NIL) { lb2_bset(W, b, prev); }
 			prev = r;
 		}
 		if (prev != LB2_SENT) { ws.d_lnext[prev] = LB2_NIL; }
@@ -409,7 +451,7 @@ LB2_DEVNI int lb2_mark_components(lb2_win &W) {
 		uint32_t qh = 0, qt = 0; Q[qt++] = p; ws.d_comp[p] = comp;
 		while (qh < qt) {   // labels depend only on connectivity and on which node opens the component
 			uint32_t cur = Q[qh++];
-			lb2_edge *e = ws.d_edge + (size_t)cur * LB2_ECAP; int ne = ws.d_ne[cur];
+			lb2_edge *e = lb2_edges(ws, cur); int ne = ws.d_ne[cur];
 			for (int i = 0; i < ne; ++i) { if (ws.d_comp[e[i].to] == 0) { ws.d_comp[e[i].to] = comp; Q[qt++] = e[i].to; } }
 		}
 	}
@@ -428,7 +470,7 @@ LB2_DEV uint32_t lb2_new_special(lb2_win &W, bool source, int compid) {
 	while (nd) { buf[n++] = dig[--nd]; }
 	ws.d_hash[id] = lb2_stdhash_bytes(buf, (uint32_t)n);
 	ws.d_flags[id] = source ? LB2_NF_SOURCE : LB2_NF_SINK;
-	ws.d_comp[id] = compid; ws.d_ne[id] = 0; ws.d_len[id] = 0; ws.d_str[id] = LB2_NIL; ws.d_cd[id] = LB2_NIL; ws.d_orig[id] = 0; ws.d_rep[id] = 0;
+	ws.d_comp[id] = (int16_t)compid; ws.d_ne[id] = 0; ws.d_eov[id] = 0; ws.d_len[id] = 0; ws.d_str[id] = LB2_NIL; ws.d_cd[id] = LB2_NIL; ws.d_orig[id] = 0; ws.d_rep[id] = 0;
 	for (int k = 0; k < 4; ++k) { ws.d_cov[id * 4 + k] = 0; ws.d_cnt[id * 4 + k] = 0; }
 	ws.d_stn[id] = 0; ws.d_stT[id] = 0; ws.d_color[id] = 0; ws.d_mincov[id] = 0; ws.d_mincovqv[id] = 0;
 	return id;
@@ -475,15 +517,16 @@ LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {   // lane 0, after lb
 	sh->seq_len = (ref_dist < 0) ? (uint32_t)(L - src_off) : (uint32_t)((src_off + ref_dist > L) ? (L - src_off) : ref_dist);
 	sh->trim5 = (uint32_t)src_off & 0xFFFF; sh->trim3 = (uint32_t)(L - snk_off - K) & 0xFFFF;
 	// orientation of the anchor k-mers in the reference: F iff the reference spelling is the canonical one
-	auto ref_ori = [&](int off) -> int {
-		lb2_kmer f, rc; lb2_extract(W.bits, sh->ref_g + (uint32_t)off, K, f); lb2_revcomp(f, K, rc);
-		return lb2_less(f, rc, sh->nw) ? 0 : 1;
+	auto ref_ori = [&](int off) -> int {      // CanonicalMer_t::set on the reference spelling (src/Mer.hh:57-71)
+		const char *m = W.ref_raw + off;
+		for (int i = 0; i < K; ++i) { char a = m[i], b = lb2_comp(m[K - 1 - i]); if (a != b) { return a < b ? 0 : 1; } }
+		return 1;
 	};
 	int sori = ref_ori(src_off), kori = ref_ori(snk_off);
 	uint32_t ns = lb2_new_special(W, true, compid); if (ns == LB2_NIL) { return; }
 	int sourcedir = sori ? LB2_FR : LB2_FF;
 	{
-		lb2_edge *e = ws.d_edge + (size_t)src * LB2_ECAP;
+		lb2_edge *e = lb2_edges(ws, src);
 		for (int i = (int)ws.d_ne[src] - 1; i >= 0; --i) {
 			if (lb2_dir_start(e[i].dir) == (sori ^ 1)) {
 				uint32_t other = e[i].to;
@@ -500,7 +543,7 @@ LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {   // lane 0, after lb
 	uint32_t nk = lb2_new_special(W, false, compid); if (nk == LB2_NIL) { return; }
 	int sinkdir = kori ? LB2_FF : LB2_RR;
 	{
-		lb2_edge *e = ws.d_edge + (size_t)snk * LB2_ECAP;
+		lb2_edge *e = lb2_edges(ws, snk);
 		for (int i = (int)ws.d_ne[snk] - 1; i >= 0; --i) {
 			if (lb2_dir_start(e[i].dir) == kori) {
 				uint32_t other = e[i].to;
@@ -526,7 +569,7 @@ LB2_DEV bool lb2_cycle_from(lb2_win &W, uint32_t start, int ori) {
 		uint32_t v = st[sp - 1]; uint32_t node = v >> 16; int o = (int)((v >> 15) & 1); int i = (int)(v & 0x7FFF);
 		if (ans || i >= (int)ws.d_ne[node]) { ws.d_color[node] = 3; --sp; continue; }
 		st[sp - 1] = v + 1;
-		lb2_edge ed = ws.d_edge[(size_t)node * LB2_ECAP + i];
+		lb2_edge ed = lb2_edges(ws, node)[i];
 		if (!lb2_is_dir(ed.dir, o)) { continue; }
 		uint32_t other = ed.to;
 		if (lb2_special(W, other)) { continue; }
@@ -555,12 +598,12 @@ LB2_DEVNI bool lb2_has_cycle(lb2_win &W) {
 // chain entry: node id | flip<<31 (flip: buddy is reverse-complemented in the seed's frame)
 LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *chain, uint32_t nchain, uint32_t &curlen) {
 	lb2_ws &ws = W.ws; const int K = W.sh->K;
-	lb2_edge *const E = ws.d_edge; uint8_t *const NE = ws.d_ne; uint8_t *const FL = ws.d_flags;
-	float *const COV = ws.d_cov; uint32_t *const LEN = ws.d_len; uint32_t *const STN = ws.d_stn; uint32_t *const STT = ws.d_stT;
+	uint8_t *const NE = ws.d_ne; uint8_t *const FL = ws.d_flags;
+	float *const COV = ws.d_cov; uint16_t *const LEN = ws.d_len; uint16_t *const STN = ws.d_stn; uint16_t *const STT = ws.d_stT;
 	int uid = lb2_get_buddy(W, node, dir);
 	if (uid == -1) { return nchain; }
 	if (lb2_is_tandem(W, node)) { return nchain; }
-	uint32_t cur_to = E[(size_t)node * LB2_ECAP + uid].to; int cur_dir = E[(size_t)node * LB2_ECAP + uid].dir;
+	uint32_t cur_to = lb2_edges(ws, node)[uid].to; int cur_dir = lb2_edges(ws, node)[uid].dir;
 	uint32_t last = LB2_NIL; int last_buid = -1, last_edir = 0;
 	float c0 = COV[node * 4 + 0], c1 = COV[node * 4 + 1], c2 = COV[node * 4 + 2], c3 = COV[node * 4 + 3];
 	uint32_t stn = STN[node], stt = STT[node];
@@ -568,7 +611,7 @@ LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *
 		const int edir = cur_dir; const uint32_t buddy = cur_to;
 		const int bdir = (edir == LB2_FF || edir == LB2_RF) ? 1 : 0;
 		if (FL[buddy] & LB2_NF_SPECIAL) { break; }                    // getBuddy of a special node is -1
-		const lb2_edge *be = E + (size_t)buddy * LB2_ECAP; const int bne = NE[buddy];
+		const lb2_edge *be = lb2_edges(ws, buddy); const int bne = NE[buddy];
 		int buid = -1, nb = 0; bool tandem = false;
 		for (int i = 0; i < bne; ++i) {
 			lb2_edge e = be[i];
@@ -599,8 +642,8 @@ LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *
 	if (last == LB2_NIL) { return nchain; }
 	COV[node * 4 + 0] = c0; COV[node * 4 + 1] = c1; COV[node * 4 + 2] = c2; COV[node * 4 + 3] = c3; STN[node] = stn; STT[node] = stt;
 	// the literal edge surgery of the last step: erase the seed's edge in `dir`, move over the last buddy's other edges
-	{ lb2_edge *ne_ = E + (size_t)node * LB2_ECAP; int ne = NE[node]; for (int j = uid; j + 1 < ne; ++j) { ne_[j] = ne_[j + 1]; } NE[node] = (uint8_t)(ne - 1); }
-	const lb2_edge *be = E + (size_t)last * LB2_ECAP; const int bne = NE[last];
+	{ lb2_edge *ne_ = lb2_edges(ws, node); int ne = NE[node]; for (int j = uid; j + 1 < ne; ++j) { ne_[j] = ne_[j + 1]; } NE[node] = (uint8_t)(ne - 1); }
+	const lb2_edge *be = lb2_edges(ws, last); const int bne = NE[last];
 	for (int i = 0; i < bne; ++i) {
 		if (i == last_buid) { continue; }
 		int nd = be[i].dir; if (last_edir == LB2_FR || last_edir == LB2_RF) { nd = lb2_flipme(nd); }

@@ -99,7 +99,7 @@ LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 			if (best == LB2_NIL || (int)e.score > bestscore) { best = idx; bestscore = e.score; }
 		} else if (e.len > reflen + W.P->max_indel_len) {
 		} else {
-			lb2_edge *ed = ws.d_edge + (size_t)cur * LB2_ECAP; int ne = ws.d_ne[cur];
+			lb2_edge *ed = lb2_edges(ws, cur); int ne = ws.d_ne[cur];
 			for (int i = 0; i < ne; ++i) {
 				if (!lb2_is_dir(ed[i].dir, pdir)) { continue; }
 				uint32_t other = ed[i].to;
@@ -126,7 +126,7 @@ LB2_DEVNI void lb2_load_path(lb2_win &W, uint32_t best)
 	uint32_t k = n;
 	for (uint32_t x = best; x != LB2_NIL; x = Q[x].parent) { --k; ws.pnodes[k] = Q[x].node; ws.peidx[k] = Q[x].eidx; }
 	sh->pn = n;
-	for (uint32_t i = 1; i < n; ++i) { ws.pdirs[i - 1] = ws.d_edge[(size_t)ws.pnodes[i - 1] * LB2_ECAP + ws.peidx[i]].dir; }
+	for (uint32_t i = 1; i < n; ++i) { ws.pdirs[i - 1] = lb2_edges(ws, ws.pnodes[i - 1])[ws.peidx[i]].dir; }
 	// Path_t::str / covDistr: where every node's contribution starts (lane 0); the copy itself is lb2_copy_path
 	int dir = lb2_dir_start(ws.pdirs[0]);
 	uint32_t plen = 0;
@@ -183,7 +183,7 @@ LB2_DEV bool lb2_status_T(lb2_win &W, uint32_t nd) {     // Node_t::isStatusCnt(
 }
 LB2_DEV void lb2_flag_path(lb2_win &W, int flag) {
 	lb2_ws &ws = W.ws;
-	for (uint32_t i = 1; i < W.sh->pn; ++i) { ws.d_edge[(size_t)ws.pnodes[i - 1] * LB2_ECAP + ws.peidx[i]].flag = (uint8_t)flag; }
+	for (uint32_t i = 1; i < W.sh->pn; ++i) { lb2_edges(ws, ws.pnodes[i - 1])[ws.peidx[i]].flag = (uint16_t)flag; }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 #define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
 	const size_t MN = (size_t)c.max_nodes + 16, MR = (size_t)c.max_reads + 2;
 	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
-	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
+	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(g_occ, uint32_t, c.table_slots); LB2_TAKE(g_cnt, uint32_t, (size_t)c.table_slots * 2); LB2_TAKE(g_em, uint32_t, c.table_slots); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
 	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR);
 	LB2_TAKE(b_rep, uint32_t, MN); LB2_TAKE(b_hash, uint64_t, MN); LB2_TAKE(b_cnt, uint32_t, MN * 4); LB2_TAKE(b_mincovqv, int32_t, MN);
@@ -94,7 +94,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			lb2_order_and_pack(W);
 			if (sh->err) { break; }
 			if (tid == 0) {
-				sh->arena_used = 8; sh->flag_c = 0;
+				sh->flag_c = 0;
 				sh->numcomp = lb2_mark_components(W);
 				lb2_mark(W, LB2_PH_LOWCOV_CC);
 			}
@@ -127,6 +127,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				// ---- findRepeatsInGraphPaths: enumerate the covering paths, near-repeat test on each
 				bool rpt = false; uint32_t nflag = 0;
 				while (true) {
+					if (nflag > 8 * LB2_MAX_ROWS) { if (tid == 0) { sh->err |= 1u << LB2_D_STACK; } lb2_sync(); break; }   // every round flags >= 1 new edge
 					if (tid == 0) {
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
@@ -147,13 +148,14 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				if (sh->err) { break; }
 				if (tid == 0) {   // clear the edge flags again (all flags of this component were 0 before)
 					for (uint32_t p = sh->lhead; p != LB2_NIL; p = W.ws.d_lnext[p]) {
-						if (W.ws.d_comp[p] == c) { for (int e = 0; e < (int)W.ws.d_ne[p]; ++e) { W.ws.d_edge[(size_t)p * LB2_ECAP + e].flag = 0; } }
+						if (W.ws.d_comp[p] == c) { for (int e = 0; e < (int)W.ws.d_ne[p]; ++e) { lb2_edges(W.ws, p)[e].flag = 0; } }
 					}
 				}
 				lb2_sync();
 				if (rpt) { retry = true; break; }
 				// ---- eka: repeat { best path; processPath; flag its edges }
-				while (true) {
+				for (uint32_t round = 0; ; ++round) {
+					if (round > 8 * LB2_MAX_ROWS) { if (tid == 0) { sh->err |= 1u << LB2_D_STACK; } lb2_sync(); break; }
 					if (tid == 0) {
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;

@@ -23,6 +23,9 @@ static inline void lb2_max32(uint32_t *p, uint32_t v) { if (v > *p) *p = v; }
 static inline void lb2_min32(uint32_t *p, uint32_t v) { if (v < *p) *p = v; }
 static inline void lb2_or32 (uint32_t *p, uint32_t v) { *p |= v; }
 static inline uint32_t lb2g_add32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline void lb2g_red_add(uint32_t *p, uint32_t v) { *p += v; }
+static inline void lb2g_red_max(uint32_t *p, uint32_t v) { if (v > *p) *p = v; }
+static inline void lb2g_red_or(uint32_t *p, uint32_t v) { *p |= v; }
 static inline uint32_t lb2g_min32(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t lb2_ld32(const uint32_t *p) { return *p; }
 static inline uint32_t lb2_lds(const uint32_t *p) { return *p; }
@@ -48,6 +51,10 @@ LB2_DEV uint32_t lb2_ld32(const uint32_t *p) { uint32_t o; asm volatile("ld.vola
 // read-only shared data (packed bases, quality mask): plain ld.shared, free to be scheduled/merged by the compiler
 LB2_DEV uint32_t lb2_lds(const uint32_t *p) { uint32_t o; asm("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(lb2_saddr(p))); return o; }
 LB2_DEV uint32_t lb2g_add32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+// fire-and-forget global reductions (no return value => the lane does not wait for L2)
+LB2_DEV void lb2g_red_add(uint32_t *p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+LB2_DEV void lb2g_red_max(uint32_t *p, uint32_t v) { asm volatile("red.global.max.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+LB2_DEV void lb2g_red_or(uint32_t *p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 LB2_DEV uint32_t lb2g_min32(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }

@@ -47,13 +47,14 @@ struct lb2_trans {                // Transcript_t (reference src/Transcript.hh:3
 struct lb2_ws {
 	// --- build stage ---
 	uint32_t *used; uint64_t *sortk; uint32_t *inst; uint32_t *mates; uint32_t *bseq;
+	uint32_t *g_occ; uint32_t *g_cnt; uint32_t *g_em;   // per-slot accumulators of the build (fed by fire-and-forget reductions)
 	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
 	lb2_bedge *b_edge; uint32_t *b_row;
 	// --- reads ---
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
 	// --- graph stage, row space.  hot (shared memory): ---
-	uint32_t *d_lnext; uint32_t *d_bk; uint32_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; int32_t *d_comp;
-	lb2_edge *d_edge; float *d_cov; uint32_t *d_len; uint32_t *d_stn; uint32_t *d_stT; uint32_t *stack; uint32_t *chain; uint32_t *cpos;
+	uint32_t *d_lnext; uint32_t *d_bk; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
+	lb2_edge *d_edge; lb2_edge *e_pool; float *d_cov; uint16_t *d_len; uint16_t *d_stn; uint16_t *d_stT; uint32_t *stack; uint32_t *chain; uint32_t *cpos;
 	// cold (global):
 	uint32_t *d_rep; uint64_t *d_hash; uint32_t *d_cnt; uint32_t *d_orig; int32_t *d_mincov; int32_t *d_mincovqv; uint32_t *d_str; uint32_t *d_cd;
 	uint16_t *deficit;            // [dense node][K][4] low-quality deficits (only when the window has low-qual bases)
@@ -71,11 +72,11 @@ struct lb2_sizes { size_t total; size_t off[64]; };
 // shared (smem) scalars of one window
 struct lb2_sh {
 	// window
-	uint32_t w, R, L, total_bp, ref_g, has_lowq, lowq_live, has_pairs, mapped, status, detail;
+	uint32_t w, R, L, total_bp, ref_g, has_lowq, lowq_live, bits_live, has_pairs, mapped, status, detail;
 	int32_t  ref_start;
 	// per k
 	int32_t  K, nw;
-	uint32_t n_used, n_nodes, n_rows, n_spec, n_jobs, err;
+	uint32_t n_used, n_nodes, n_rows, n_spec, n_jobs, n_eov, err;
 	uint32_t totalreadbp;
 	uint32_t flag_a, flag_b, flag_c; uint32_t scan_emax, scan_wmax, ref_emax, ref_wmax;
 	// reference trimming state (Ref_t::seq/trim5/trim3, persists across k: SURVEY B4)
@@ -110,8 +111,15 @@ enum { LB2_PH_STAGE = 0, LB2_PH_PRESCAN, LB2_PH_REFSCAN, LB2_PH_WALK, LB2_PH_COM
 LB2_HD size_t lb2_smem_fixed(uint32_t max_bp) {
 	return ((sizeof(lb2_sh) + 15) & ~(size_t)15) + LB2_MAX_REF + ((size_t)max_bp / 16 + 4) * 4 + ((size_t)max_bp / 32 + 4) * 4;
 }
-LB2_HD size_t lb2_treg_bytes(uint32_t table_slots) { return (size_t)table_slots * 20; }
-LB2_HD size_t lb2_smem_bytes(uint32_t max_bp, uint32_t table_slots) { return ((lb2_smem_fixed(max_bp) + 15) & ~(size_t)15) + lb2_treg_bytes(table_slots); }
+// region T follows the quality mask: Mer->Node keys (u32) + slot->node ids (u16) during the build; together with the
+// mask's bytes it must also hold the graph-stage arrays (cfg.graph_bytes)
+LB2_HD size_t lb2_lowq_bytes(uint32_t max_bp) { return ((size_t)max_bp / 32 + 4) * 4; }
+LB2_HD size_t lb2_treg_bytes(uint32_t table_slots, uint32_t graph_bytes, uint32_t max_bp) {
+	size_t t = (size_t)table_slots * 6, lq = lb2_lowq_bytes(max_bp);
+	size_t g = graph_bytes > lq ? graph_bytes - lq : 0;
+	return ((t > g ? t : g) + 15) & ~(size_t)15;
+}
+LB2_HD size_t lb2_smem_bytes(uint32_t max_bp, uint32_t table_slots, uint32_t graph_bytes) { return ((lb2_smem_fixed(max_bp) + 15) & ~(size_t)15) + lb2_treg_bytes(table_slots, graph_bytes, max_bp); }
 
 
 #endif

@@ -38,15 +38,16 @@ int main(int argc, char **argv)
 
 	lb2_cfg C; memset(&C, 0, sizeof C);
 	C.table_slots = 16384; C.max_nodes = 12000; C.max_reads = 8192; C.max_bp = (1 << 20) - 1024; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
-	C.queue_cap = 1 << 22; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
+	C.queue_cap = 1 << 22; C.graph_bytes = 1 << 20; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
 	if (getenv("LB2_SIM_TS")) { C.table_slots = atoi(getenv("LB2_SIM_TS")); C.max_nodes = C.table_slots - C.table_slots / 4; }
 	if (getenv("LB2_SIM_BP")) { C.max_bp = atoi(getenv("LB2_SIM_BP")); }
+	if (getenv("LB2_SIM_GB")) { C.graph_bytes = atoi(getenv("LB2_SIM_GB")); }
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
 	B.base_off = base_off.data(); B.flags = flags.data(); B.name_rank = name_rank.data(); B.ref_seq = ref_seq.data(); B.seq = seq.data(); B.qual = qual.data();
 	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
 	lb2_dev_out O; O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);
-	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp, C.table_slots) + 64, 0);
+	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp, C.table_slots, C.graph_bytes) + 64, 0);
 	lb2_win Wn; Wn.P = &P; Wn.C = &C; Wn.B = &B; Wn.O = &O;
 	lb2_ws_layout(C, slab.data(), &Wn.ws); Wn.ws0 = Wn.ws;
 	Wn.sh = (lb2_sh *)smem.data();
