@@ -24,7 +24,7 @@ struct lb2_launch {
 	uint32_t *var_off; uint32_t *str_off; uint32_t *totals; lb2_variant *cvars; char *cstr;
 };
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, 3)
 lb2_window_kernel(const lb2_launch *Lp)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -186,7 +186,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
-	ctx->threads = env_u32("LB2_THREADS", 256); if (ctx->threads < 32 || ctx->threads > 512 || (ctx->threads & 31)) { ctx->threads = 256; }
+	ctx->threads = env_u32("LB2_THREADS", 256); if (ctx->threads < 32 || ctx->threads > 256 || (ctx->threads & 31)) { ctx->threads = 256; }
 	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
 		delete ctx; return LB2_ERR_CUDA;
 	}
@@ -229,7 +229,7 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 		if (bp > max_bp) { max_bp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
 		max_reads = std::max(max_reads, b->wr_off[w + 1] - b->wr_off[w]);
 	}
-	max_bp = (max_bp + 1023) & ~1023u;
+	max_bp = (max_bp + 1023) & ~1023u; if (max_bp < 32768) { max_bp = 32768; }
 	const uint32_t smem_cap = 220u << 10;
 	if (max_bp > (1u << 20) - 1024) { max_bp = (1u << 20) - 1024; }   // representative base index has 20 bits in the table key
 	lb2_cfg &C = ctx->C;

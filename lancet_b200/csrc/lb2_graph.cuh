@@ -329,11 +329,29 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		else { for (int i = 0; i < K; ++i) { dst[i] = lb2_base(lb2_getbase(W.bits, g0 + i)); } }
 	}
 	lb2_sync();
-	// all-node emulation arrays live where the packed reads were
+	// row-space layout first (its size decides where the all-node emulation arrays can live)
+	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
+	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
+	size_t rows_bytes = 0;
+	{
+		size_t off = 0;
+#define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; ws.field = (type *)(G + off); off += sizeof(type) * (size_t)(count); } while (0)
+		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint16_t, bcap);
+		LB2_GT(d_cov, float, NT * 4); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8);
+		LB2_GT(d_edge, lb2_edge, NT * LB2_EINL); LB2_GT(e_pool, lb2_edge, LB2_EOV_BLOCKS * LB2_ECAP);
+		LB2_GT(d_len, uint16_t, NT); LB2_GT(d_stn, uint16_t, NT); LB2_GT(d_stT, uint16_t, NT); LB2_GT(d_comp, int16_t, NT);
+		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT); LB2_GT(d_eov, uint8_t, NT);
+#undef LB2_GT
+		ws.chain = ws.stack; rows_bytes = (off + 15) & ~(size_t)15;
+	}
+	// all-node emulation arrays: over the packed reads (dead now) or, if those are too small, behind the row arrays
 	const size_t an_bytes = ((size_t)n * 2 * 3 + (size_t)Bfinal * 2 + 15) & ~(size_t)15;
 	const size_t bits_bytes = ((size_t)W.C->max_bp / 16 + 4) * 4;
-	if (Bfinal == 0 || n >= 0x7FF0u || an_bytes > bits_bytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
-	uint16_t *a_next = (uint16_t *)W.bits, *a_bk = a_next + n, *a_row = a_bk + n, *a_bkt = a_row + n;
+	uint16_t *a_next = nullptr;
+	if (an_bytes <= bits_bytes) { a_next = (uint16_t *)W.bits; }
+	else if (rows_bytes + an_bytes <= Gbytes) { a_next = (uint16_t *)(G + rows_bytes); }
+	if (Bfinal == 0 || n >= 0x7FF0u || NT > LB2_MAX_ROWS || rows_bytes > Gbytes || !a_next) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
+	uint16_t *a_bk = a_next + n, *a_row = a_bk + n, *a_bkt = a_row + n;
 	const uint16_t NIL16 = 0xFFFF, SENT16 = 0xFFFE;
 	for (uint32_t j = tid; j < n; j += nt) { uint32_t r = ws.b_row[j]; a_row[j] = (r == LB2_NIL) ? NIL16 : (uint16_t)r; }
 	if (tid == 0) { sh->lhead = NIL16; sh->lowq_live = 0; sh->bits_live = 0; }
@@ -365,21 +383,6 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		lb2_sync();
 	}
 	lb2_mark(W, LB2_PH_ORDER);
-	// ---- layout of the row-space arrays
-	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
-	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
-	{
-		size_t off = 0;
-#define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; ws.field = (type *)(G + off); off += sizeof(type) * (size_t)(count); } while (0)
-		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint16_t, bcap);
-		LB2_GT(d_cov, float, NT * 4); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8);
-		LB2_GT(d_edge, lb2_edge, NT * LB2_EINL); LB2_GT(e_pool, lb2_edge, LB2_EOV_BLOCKS * LB2_ECAP);
-		LB2_GT(d_len, uint16_t, NT); LB2_GT(d_stn, uint16_t, NT); LB2_GT(d_stT, uint16_t, NT); LB2_GT(d_comp, int16_t, NT);
-		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT); LB2_GT(d_eov, uint8_t, NT);
-#undef LB2_GT
-		ws.chain = ws.stack;
-		if (NT > LB2_MAX_ROWS || off > Gbytes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
-	}
 	if (tid == 0) { sh->bkt_cap = bcap; sh->bkt_count = Bfinal; sh->next_resize = Bfinal; sh->elem_count = NR; sh->n_eov = 0; }
 	for (uint32_t r = tid; r < NT; r += nt) { ws.d_eov[r] = 0; ws.d_ne[r] = 0; }
 	lb2_sync();
