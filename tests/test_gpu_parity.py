@@ -51,6 +51,12 @@ def test_golden(name, tmp_path):
     dict(seed=35, region_len=3000, cov_t=150, cov_n=150),
     dict(seed=36, region_len=3000, read_len=150),
     dict(seed=37, region_len=1777),              # short last window (len-offset-1 rule)
+    dict(seed=61, region_len=3000, paired=True),                                   # Variant B: true pairs, names unsorted
+    dict(seed=62, region_len=3000, paired=True, insert_mean=150, insert_sd=20),    # overlapping mates (unsorted binary_search quirk)
+    dict(seed=77, region_len=3000, paired=True, insert_mean=160, insert_sd=40, err=0.004, low_qual_frac=0.02),
+    dict(seed=71, region_len=4000, str_every=200, cov_t=80, cov_n=80),             # STR-rich reference: long k sweeps, skipped windows
+    dict(seed=72, region_len=4000, str_every=500),
+    dict(seed=75, region_len=1500, err=0.01),                                      # heavy BFS: goes through the escalation pass
 ])
 def test_live_reference(kw, ctx):
     import run_ref
@@ -62,6 +68,22 @@ def test_live_reference(kw, ctx):
     res = ctx.process(b)
     assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
     assert res.records() == want
+
+
+@pytest.mark.parametrize("k", [31, 33, 63, 65, 101])
+def test_large_k(k):
+    """multi-word k-mers: k-mer sizes around the 32/64-base word boundaries and the reference's maximum"""
+    import run_ref
+    if not run_ref.available():
+        pytest.skip("oracle/_ref/ref_windows not built")
+    from lancet_b200.synth import make_batch
+    b = make_batch(seed=81, region_len=2500, read_len=150)
+    want, _ = run_ref.run(b, threads=8, min_k=k, max_k=k)
+    c = _ctx(min_k=k, max_k=k)
+    res = c.process(b)
+    assert (res.windows["status"] < 3).all()
+    assert res.records() == want
+    c.close()
 
 
 def test_edge_cases(ctx):
