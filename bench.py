@@ -185,7 +185,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))            # ncu capture of an earlier run of this kernel (per-window DRAM bytes x windows of this launch)
+                traffic = tj["dram_bytes_per_window"] * batch.n_windows
             except Exception:
                 pass
         out = {
