@@ -37,16 +37,12 @@ template <class Get, class Set>
 LB2_DEV uint32_t lb2_excl_scan(lb2_win &W, uint32_t n, Get get, Set set)
 {
 	const unsigned tid = lb2_tid(), nt = lb2_nthr(); uint32_t *sc = W.sh->scan;
-	const uint32_t chunk = (n + nt - 1) / nt, lo = tid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+	const uint32_t chunk = (n + nt - 1) / nt, lo = (tid * chunk < n) ? tid * chunk : n, hi = (lo + chunk < n) ? lo + chunk : n;
 	uint32_t sum = 0;
 	for (uint32_t i = lo; i < hi; ++i) { sum += get(i); }
-	sc[tid] = sum;
-	lb2_sync();
-	if (tid == 0) { uint32_t acc = 0; for (unsigned t = 0; t < nt; ++t) { uint32_t v = sc[t]; sc[t] = acc; acc += v; } sc[nt] = acc; }
-	lb2_sync();
-	uint32_t acc = sc[tid];
+	uint32_t total = 0;
+	uint32_t acc = lb2_block_excl(sc, sum, &total);
 	for (uint32_t i = lo; i < hi; ++i) { uint32_t v = get(i); set(i, acc); acc += v; }
-	uint32_t total = sc[nt];
 	lb2_sync();
 	return total;
 }

@@ -296,7 +296,7 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	if (ctx->escalate) {
 		// escalation pass: the largest table that still fits beside the staged reads, big arena / BFS queue, one CTA per SM
 		lb2_cfg &C2 = ctx->C2; C2 = C;
-		C2.table_slots = 8192; C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 150u << 10);
+		C2.table_slots = env_u32("LB2_TABLE_SLOTS2", 16384); C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 184u << 10);
 		while (C2.graph_bytes > C.graph_bytes && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.graph_bytes -= 4096; }
 		while (C2.table_slots > C.table_slots && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.table_slots >>= 1; }
 		C2.max_nodes = C2.table_slots - C2.table_slots / 4;

@@ -305,6 +305,47 @@ LB2_DEV uint32_t lb2_level_bkt(uint32_t n_before) {   // bucket count in force w
 	return 0;
 }
 
+// Iteration order of the reference's map after the build, computed by all lanes (no list is walked):
+// an insert into an empty bucket goes to the list head, an insert into a non-empty bucket goes to the front of that
+// bucket's run, and _M_rehash_aux re-places every element by the same two rules in old list order.  Hence after any
+// sequence of placements the list is: buckets by DEscending creation time, inside a bucket elements by DEscending
+// placement time.  Per level (bucket count B) the placement time of an element is its list position
+// before the rehash (old elements) or its dense id (elements inserted at this level), and
+//     new position = (number of elements in buckets created later) + (number of later elements in its own bucket).
+// tm/tm2/bk: u16[n] (tm = time, tm2 = new position / rank, bk = bucket); nx/S/cm: u16[n]; head: u32[B].
+// Returns the array holding the final list position of every dense node; *bk_out = bucket at the final bucket count,
+// *free_out = the other u16[n] array (free for the caller).
+LB2_DEVNI uint16_t *lb2_emulate_order(lb2_win &W, uint32_t n, uint16_t *tm, uint16_t *tm2, uint16_t *bk, uint16_t *nx, uint16_t *S, uint16_t *cm, uint32_t *head, uint16_t **free_out)
+{
+	lb2_ws &ws = W.ws; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	uint32_t done = 0;
+	while (done < n) {
+		const uint32_t B = lb2_level_bkt(done); const uint32_t end = B < n ? B : n;     // elements [done, end) arrive at this bucket count
+		for (uint32_t j = tid; j < end; j += nt) { bk[j] = (uint16_t)(ws.b_hash[j] % B); if (j >= done) { tm[j] = (uint16_t)j; } }
+		for (uint32_t b = tid; b < B; b += nt) { head[b] = LB2_NIL; }
+		lb2_sync();
+		for (uint32_t j = tid; j < end; j += nt) { nx[j] = (uint16_t)lb2x_exch32(&head[bk[j]], j); }
+		lb2_sync();
+		for (uint32_t j = tid; j < end; j += nt) {
+			const uint32_t tj = tm[j]; uint32_t cmin = tj, cnt = 0, rank = 0;
+			for (uint32_t y = head[bk[j]]; y != LB2_NIL; ) {
+				uint32_t ty = tm[y]; ++cnt; if (ty < cmin) { cmin = ty; } if (ty > tj) { ++rank; }
+				uint32_t nxt = nx[y]; y = (nxt == 0xFFFFu) ? LB2_NIL : nxt;
+			}
+			S[tj] = (uint16_t)((tj == cmin) ? cnt : 0u); cm[j] = (uint16_t)cmin; tm2[j] = (uint16_t)rank;
+		}
+		lb2_sync();
+		// S[t] := number of elements in buckets created after time t (exclusive suffix sum)
+		lb2_excl_scan(W, end, [&](uint32_t i) -> uint32_t { return S[end - 1 - i]; }, [&](uint32_t i, uint32_t v) { S[end - 1 - i] = (uint16_t)v; });
+		for (uint32_t j = tid; j < end; j += nt) { tm2[j] = (uint16_t)(S[cm[j]] + tm2[j]); }
+		lb2_sync();
+		uint16_t *t = tm; tm = tm2; tm2 = t;
+		done = end;
+	}
+	*free_out = tm2;
+	return tm;
+}
+
 LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
@@ -329,7 +370,7 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		else { for (int i = 0; i < K; ++i) { dst[i] = lb2_base(lb2_getbase(W.bits, g0 + i)); } }
 	}
 	lb2_sync();
-	// row-space layout first (its size decides where the all-node emulation arrays can live)
+	// row-space layout (filled after the emulation: its temporaries borrow the same shared memory)
 	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
 	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
 	size_t rows_bytes = 0;
@@ -344,87 +385,70 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 #undef LB2_GT
 		ws.chain = ws.stack; rows_bytes = (off + 15) & ~(size_t)15;
 	}
-	// all-node emulation arrays: over the packed reads (dead now) or, if those are too small, behind the row arrays
-	const size_t an_bytes = ((size_t)n * 2 * 3 + (size_t)Bfinal * 2 + 15) & ~(size_t)15;
+	// scratch of the graph stage in the (now dead) packed-read words: list index of every row, then the parallel
+	// compaction's words.  The emulation arrays: three u16[n] here, the rest over the graph region; when either does not
+	// fit, all of them live in the workspace slab instead.
 	const size_t bits_bytes = ((size_t)W.C->max_bp / 16 + 4) * 4;
-	uint16_t *a_next = nullptr;
-	if (an_bytes <= bits_bytes) { a_next = (uint16_t *)W.bits; }
-	else if (rows_bytes + an_bytes <= Gbytes) { a_next = (uint16_t *)(G + rows_bytes); }
-	if (Bfinal == 0 || n >= 0x7FF0u || NT > LB2_MAX_ROWS || rows_bytes > Gbytes || !a_next) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
-	uint16_t *a_bk = a_next + n, *a_row = a_bk + n, *a_bkt = a_row + n;
-	const uint16_t NIL16 = 0xFFFF, SENT16 = 0xFFFE;
-	for (uint32_t j = tid; j < n; j += nt) { uint32_t r = ws.b_row[j]; a_row[j] = (r == LB2_NIL) ? NIL16 : (uint16_t)r; }
-	if (tid == 0) { sh->lhead = NIL16; sh->lowq_live = 0; sh->bits_live = 0; }
-	uint32_t done = 0;
-	while (done < n) {
-		const uint32_t B = lb2_level_bkt(done); uint32_t end = B < n ? B : n;     // elements [done, end) arrive at this bucket count
-		for (uint32_t j = tid; j < end; j += nt) { a_bk[j] = (uint16_t)(ws.b_hash[j] % B); }
-		for (uint32_t b = tid; b < B; b += nt) { a_bkt[b] = NIL16; }
-		lb2_sync();
-		if (tid == 0) {
-			uint32_t head = sh->lhead;
-			// _M_rehash_aux over the current list
-			uint32_t p = head; head = NIL16; uint32_t bbegin = 0;
-			while (p != NIL16) {
-				uint32_t nx = a_next[p], b = a_bk[p];
-				if (a_bkt[b] == NIL16) { a_next[p] = (uint16_t)head; head = p; a_bkt[b] = SENT16; if (a_next[p] != NIL16) { a_bkt[bbegin] = (uint16_t)p; } bbegin = b; }
-				else { uint32_t before = a_bkt[b]; if (before == SENT16) { a_next[p] = (uint16_t)head; head = p; } else { a_next[p] = a_next[before]; a_next[before] = (uint16_t)p; } }
-				p = nx;
-			}
-			// _M_insert_bucket_begin for the new elements
-			for (uint32_t id = done; id < end; ++id) {
-				uint32_t b = a_bk[id];
-				if (a_bkt[b] != NIL16) { uint32_t before = a_bkt[b]; if (before == SENT16) { a_next[id] = (uint16_t)head; head = id; } else { a_next[id] = a_next[before]; a_next[before] = (uint16_t)id; } }
-				else { a_next[id] = (uint16_t)head; head = id; if (a_next[id] != NIL16) { a_bkt[a_bk[a_next[id]]] = (uint16_t)id; } a_bkt[b] = SENT16; }
-			}
-			sh->lhead = head;
-		}
-		done = end;
-		lb2_sync();
+	ws.d_pos = (uint16_t *)W.bits; ws.px = (uint32_t *)((uint8_t *)W.bits + (((size_t)NT * 2 + 15) & ~(size_t)15));
+	ws.px_words = (bits_bytes > (((size_t)NT * 2 + 15) & ~(size_t)15)) ? (uint32_t)((bits_bytes - (((size_t)NT * 2 + 15) & ~(size_t)15)) / 4) : 0u;
+	const size_t n6 = ((size_t)n * 6 + 15) & ~(size_t)15;
+	if (Bfinal == 0 || n >= 0x7FF0u || NT > LB2_MAX_ROWS || rows_bytes > Gbytes || (size_t)NT * 2 + 16 > bits_bytes || n > W.C->max_nodes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
+	uint16_t *tm, *tm2, *bk, *nx, *S, *cm; uint32_t *head;
+	if (n6 <= bits_bytes && n6 + (size_t)Bfinal * 4 <= Gbytes) {
+		tm = (uint16_t *)W.bits; tm2 = tm + n; bk = tm2 + n;
+		nx = (uint16_t *)G; S = nx + n; cm = S + n; head = (uint32_t *)(G + n6);
+	} else {
+		tm = (uint16_t *)ws.emu; tm2 = tm + n; bk = tm2 + n; nx = bk + n; S = nx + n; cm = S + n; head = (uint32_t *)((uint8_t *)ws.emu + (((size_t)n * 12 + 15) & ~(size_t)15));
 	}
+	if (tid == 0) { sh->lowq_live = 0; sh->bits_live = 0; }
+	uint16_t *ord = nullptr;
+	uint16_t *pos = lb2_emulate_order(W, n, tm, tm2, bk, nx, S, cm, head, &ord);
+	for (uint32_t j = tid; j < n; j += nt) { ord[pos[j]] = (uint16_t)j; }     // dense node at every list position
+	lb2_sync();
 	lb2_mark(W, LB2_PH_ORDER);
 	if (tid == 0) { sh->bkt_cap = bcap; sh->bkt_count = Bfinal; sh->next_resize = Bfinal; sh->elem_count = NR; sh->n_eov = 0; }
 	for (uint32_t r = tid; r < NT; r += nt) { ws.d_eov[r] = 0; ws.d_ne[r] = 0; }
 	lb2_sync();
 	for (uint32_t j = tid; j < n; j += nt) {
 		uint32_t r = ws.b_row[j]; if (r == LB2_NIL) { continue; }
-		ws.d_bk[r] = a_bk[j];
+		ws.d_bk[r] = bk[j];
 		uint32_t tot = 0;
 		for (int c = 0; c < 4; ++c) { uint32_t v = ws.b_cnt[j * 4 + c]; ws.d_cov[r * 4 + c] = (float)v; ws.d_cnt[r * 4 + c] = v; tot += v; }
 		ws.d_len[r] = (uint32_t)K; ws.d_stn[r] = 1; ws.d_stT[r] = ws.b_stT[j]; ws.d_comp[r] = 0;
 		ws.d_flags[r] = 0; ws.d_color[r] = 0;
 		ws.d_rep[r] = ws.b_rep[j]; ws.d_hash[r] = ws.b_hash[j]; ws.d_orig[r] = j;
 		ws.d_mincov[r] = (int32_t)tot; ws.d_mincovqv[r] = ws.b_mincovqv[j]; ws.d_str[r] = 8 + r * (uint32_t)K; ws.d_cd[r] = LB2_NIL;
-		int ne = ws.b_ne[j];
-		if (ne <= LB2_EINL) {
-			for (int e = 0; e < ne; ++e) {
-				lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e];
-				lb2_edge ed; ed.to = (uint16_t)ws.b_row[be.to]; ed.dir = (uint16_t)be.dir; ed.flag = 0; ed.pad = 0;
-				ws.d_edge[(size_t)r * LB2_EINL + e] = ed;
-			}
-			ws.d_ne[r] = (uint8_t)ne;
-		} else { ws.d_ne[r] = 0xFF; }      // more than the inline slots: lane 0 fills these below (pool allocation is serial)
+		const int ne = ws.b_ne[j];
+		lb2_edge *dst = ws.d_edge + (size_t)r * LB2_EINL;
+		if (ne > LB2_EINL) {          // more than the inline slots: a block of the pool
+			uint32_t blk = lb2_add32(&sh->n_eov, 1u);
+			if (blk >= LB2_EOV_BLOCKS) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); continue; }
+			ws.d_eov[r] = (uint8_t)(blk + 1); dst = ws.e_pool + (size_t)blk * LB2_ECAP;
+		}
+		for (int e = 0; e < ne; ++e) {
+			lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e];
+			lb2_edge ed; ed.to = (uint16_t)ws.b_row[be.to]; ed.dir = (uint16_t)be.dir; ed.flag = 0; ed.pad = 0;
+			dst[e] = ed;
+		}
+		ws.d_ne[r] = (uint8_t)ne;
 	}
 	for (uint32_t p = tid; p < LB2_MAX_REF; p += nt) { uint32_t j = ws.refnode[p]; if (j != LB2_NIL) { ws.refnode[p] = ws.b_row[j]; } }
 	for (uint32_t b = tid; b < bcap; b += nt) { lb2_bset(W, b, LB2_NIL); }
+	// the survivors in list order (erase keeps the relative order): rows at list index 0..NR-1
+	uint32_t *rowlist = ws.stack;
+	lb2_excl_scan(W, n, [&](uint32_t p) -> uint32_t { return (ws.b_row[ord[p]] != LB2_NIL) ? 1u : 0u; },
+	              [&](uint32_t p, uint32_t v) { uint32_t r = ws.b_row[ord[p]]; if (r != LB2_NIL) { rowlist[v] = r; } });
+	if (sh->n_eov > LB2_EOV_BLOCKS && tid == 0) { sh->n_eov = LB2_EOV_BLOCKS; }
 	lb2_sync();
-	if (tid == 0) {
-		for (uint32_t j = 0; j < n; ++j) {      // (rare) nodes with more than LB2_EINL edges
-			uint32_t r = a_row[j]; if (r == NIL16 || ws.d_ne[r] != 0xFF) { continue; }
-			ws.d_ne[r] = 0; int ne = ws.b_ne[j];
-			for (int e = 0; e < ne; ++e) { lb2_bedge be = ws.b_edge[(size_t)j * LB2_BECAP + e]; lb2_push_edge(W, r, ws.b_row[be.to], (int)be.dir, 0); }
-		}
-		// translate the list to row ids, dropping the dead; rebuild the bucket heads (before-begin pointers)
-		uint32_t prev = LB2_SENT; uint32_t head = LB2_NIL;
-		for (uint32_t p = sh->lhead; p != NIL16; p = a_next[p]) {
-			uint32_t r = a_row[p]; if (r == NIL16) { continue; }
-			if (prev == LB2_SENT) { head = r; } else { ws.d_lnext[prev] = r; }
-			uint32_t b = ws.d_bk[r]; if (lb2_bget(W, b) == LB2_NIL) { lb2_bset(W, b, prev); }
-			prev = r;
-		}
-		if (prev != LB2_SENT) { ws.d_lnext[prev] = LB2_NIL; }
-		sh->lhead = head;
+	for (uint32_t li = tid; li < NR; li += nt) {
+		const uint32_t r = rowlist[li], b = ws.d_bk[r];
+		ws.d_lnext[r] = (li + 1 < NR) ? rowlist[li + 1] : LB2_NIL;
+		if (li == 0) { lb2_bset(W, b, LB2_SENT); }
+		else { uint32_t pr = rowlist[li - 1]; if (ws.d_bk[pr] != b) { lb2_bset(W, b, pr); } }      // bucket -> node before its first node
 	}
+	if (tid == 0) { sh->lhead = NR ? rowlist[0] : LB2_NIL; }
+	lb2_sync();
+	for (uint32_t li = tid; li < NR; li += nt) { ws.d_pos[rowlist[li]] = (uint16_t)li; }     // (d_pos overlays the emulation arrays: they are dead now)
 	lb2_sync();
 	lb2_mark(W, LB2_PH_LOWCOV_CC);
 }
@@ -444,21 +468,42 @@ LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
 	lb2_clean_dead(W);
 }
 
+// Graph_t::markConnectedComponents (src/Graph.cc:2252-2336) by all lanes: the reference numbers a component when its
+// first node comes up in map iteration order and labels everything reachable from it; edges are reciprocal, so the
+// labels are the connected components numbered by their smallest list index.  Min-label hooking + pointer jumping
+// over list indices (P lives in ws.cpos, the numbering in ws.stack).  Returns the number of components.
 LB2_DEVNI int lb2_mark_components(lb2_win &W) {
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
-	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) { ws.d_comp[p] = 0; }
-	int comp = 0; uint32_t *Q = ws.stack;   // FIFO; every node is pushed once
-	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
-		if (ws.d_comp[p] != 0) { continue; }
-		++comp;
-		uint32_t qh = 0, qt = 0; Q[qt++] = p; ws.d_comp[p] = comp;
-		while (qh < qt) {   // labels depend only on connectivity and on which node opens the component
-			uint32_t cur = Q[qh++];
-			lb2_edge *e = lb2_edges(ws, cur); int ne = ws.d_ne[cur];
-			for (int i = 0; i < ne; ++i) { if (ws.d_comp[e[i].to] == 0) { ws.d_comp[e[i].to] = comp; Q[qt++] = e[i].to; } }
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t NR = sh->n_rows; uint32_t *P = ws.cpos; uint32_t *num = ws.stack;
+	for (uint32_t i = tid; i < NR; i += nt) { P[i] = i; }
+	lb2_sync();
+	for (uint32_t round = 0; round < 2 * LB2_MAX_ROWS; ++round) {
+		for (uint32_t r = tid; r < NR; r += nt) {
+			const uint32_t pi = P[ws.d_pos[r]];
+			const lb2_edge *e = lb2_edges(ws, r); const int ne = ws.d_ne[r];
+			for (int x = 0; x < ne; ++x) {
+				const uint32_t pj = P[ws.d_pos[e[x].to]];
+				if (pi < pj) { lb2_min32(&P[pj], pi); } else if (pj < pi) { lb2_min32(&P[pi], pj); }
+			}
 		}
+		if (tid == 0) { sh->flag_b = 0; }
+		lb2_sync();
+		for (uint32_t i = tid; i < NR; i += nt) { uint32_t p = lb2_ld32(&P[i]); while (true) { uint32_t q = lb2_ld32(&P[p]); if (q == p) { break; } p = q; } P[i] = p; }
+		lb2_sync();
+		for (uint32_t r = tid; r < NR; r += nt) {
+			const uint32_t pi = P[ws.d_pos[r]]; bool diff = false;
+			const lb2_edge *e = lb2_edges(ws, r); const int ne = ws.d_ne[r];
+			for (int x = 0; x < ne; ++x) { if (P[ws.d_pos[e[x].to]] != pi) { diff = true; } }
+			if (diff) { sh->flag_b = 1; }
+		}
+		lb2_sync();
+		if (!sh->flag_b) { break; }
+		lb2_sync();
 	}
-	return comp;
+	uint32_t ncomp = lb2_excl_scan(W, NR, [&](uint32_t i) -> uint32_t { return P[i] == i ? 1u : 0u; }, [&](uint32_t i, uint32_t v) { num[i] = v; });
+	for (uint32_t r = tid; r < NR; r += nt) { ws.d_comp[r] = (int16_t)(num[P[ws.d_pos[r]]] + 1u); }
+	lb2_sync();
+	return (int)ncomp;
 }
 
 // special node creation: key string "source<c>" / "sink<c>" hashed like any other map key

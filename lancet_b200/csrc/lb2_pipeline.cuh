@@ -22,7 +22,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	LB2_TAKE(d_mincov, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_mincovqv, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_str, uint32_t, LB2_MAX_ROWS); LB2_TAKE(d_cd, uint32_t, LB2_MAX_ROWS);
 	LB2_TAKE(deficit, uint16_t, c.deficit_bytes / 2);
 	LB2_TAKE(refnode, uint32_t, LB2_MAX_REF); LB2_TAKE(refcov, uint16_t, 2 * LB2_MAX_REF * 2);
-	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(queue, lb2_qent, c.queue_cap); LB2_TAKE(jobs, uint32_t, LB2_MAX_ROWS * 10); LB2_TAKE(pstart, uint32_t, LB2_MAX_PNODES + 1);
+	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(emu, uint32_t, (size_t)c.max_nodes * 3 + (size_t)c.max_nodes * 9 / 4 + 64); LB2_TAKE(queue, lb2_qent, c.queue_cap); LB2_TAKE(jobs, uint32_t, LB2_MAX_ROWS * 10); LB2_TAKE(pstart, uint32_t, LB2_MAX_PNODES + 1);
 	LB2_TAKE(pathseq, char, LB2_MAX_PATH + 16); LB2_TAKE(pcovN, lb2_cov, LB2_MAX_PATH + 16); LB2_TAKE(pcovT, lb2_cov, LB2_MAX_PATH + 16);
 	LB2_TAKE(pnodes, uint32_t, LB2_MAX_PNODES); LB2_TAKE(pdirs, uint8_t, LB2_MAX_PNODES); LB2_TAKE(peidx, uint8_t, LB2_MAX_PNODES);
 	LB2_TAKE(aln_ref, char, LB2_MAX_PATH + LB2_MAX_REF + 16); LB2_TAKE(aln_path, char, LB2_MAX_PATH + LB2_MAX_REF + 16);
@@ -93,9 +93,9 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			lb2_mark(W, LB2_PH_REFCOV);
 			lb2_order_and_pack(W);
 			if (sh->err) { break; }
-			if (tid == 0) {
-				sh->flag_c = 0;
-				sh->numcomp = lb2_mark_components(W);
+			{
+				int nc = lb2_mark_components(W);
+				if (tid == 0) { sh->flag_c = 0; sh->numcomp = nc; }
 				lb2_mark(W, LB2_PH_LOWCOV_CC);
 			}
 			lb2_sync();

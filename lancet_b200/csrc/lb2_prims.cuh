@@ -33,6 +33,10 @@ static inline int lb2_ctz64(uint64_t x) { return __builtin_ctzll(x); }
 static inline int lb2_clz32(uint32_t x) { return __builtin_clz(x); }
 static inline int lb2_ctz32(uint32_t x) { return __builtin_ctz(x); }
 static inline unsigned long long lb2_clock() { return 0; }
+// CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
+static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) { (void)sc; *total = v; return 0; }
+// atomics on an address that may be shared OR global (scratch that falls back to the workspace slab)
+static inline uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 #else
 #define LB2_DEV   __device__ __forceinline__
 #define LB2_DEVNI __device__ __noinline__
@@ -60,6 +64,22 @@ LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }
 LB2_DEV int lb2_ctz32(uint32_t x) { return __ffs((int)x) - 1; }
 LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
+// CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
+LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {
+	const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31u) >> 5;
+	uint32_t x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (unsigned)o) { x += y; } }
+	if (lane == 31u) { sc[wid] = x; }
+	__syncthreads();
+	uint32_t base = 0, tot = 0;
+	for (unsigned w = 0; w < nwarp; ++w) { uint32_t t = sc[w]; if (w < wid) { base += t; } tot += t; }
+	__syncthreads();
+	*total = tot;
+	return base + x - v;
+}
+// atomics on an address that may be shared OR global (scratch that falls back to the workspace slab)
+LB2_DEV uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 #endif
 
 #endif

@@ -54,6 +54,7 @@ struct lb2_ws {
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
 	// --- graph stage, row space.  hot (shared memory): ---
 	uint32_t *d_lnext; uint32_t *d_bk; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
+	uint16_t *d_pos; uint32_t *px; uint32_t px_words;   // (packed-read words, dead in the graph stage) list index of every row; scratch of the parallel compaction
 	lb2_edge *d_edge; lb2_edge *e_pool; float *d_cov; uint16_t *d_len; uint16_t *d_stn; uint16_t *d_stT; uint32_t *stack; uint32_t *chain; uint32_t *cpos;
 	// cold (global):
 	uint32_t *d_rep; uint64_t *d_hash; uint32_t *d_cnt; uint32_t *d_orig; int32_t *d_mincov; int32_t *d_mincovqv; uint32_t *d_str; uint32_t *d_cd;
@@ -61,6 +62,7 @@ struct lb2_ws {
 	uint32_t *refnode;            // [LB2_MAX_REF] node of the reference k-mer at each offset (dense id, then row id)
 	uint16_t *refcov;             // [2 samples][LB2_MAX_REF][2] fwd,rev
 	uint8_t  *arena;
+	uint32_t *emu;                // order-emulation arrays when they do not fit in shared memory
 	lb2_qent *queue; uint32_t *jobs; uint32_t *pstart;
 	// --- path processing ---
 	char *pathseq; lb2_cov *pcovN; lb2_cov *pcovT; uint32_t *pnodes; uint8_t *pdirs; uint8_t *peidx;
