@@ -23,6 +23,7 @@ struct lb2_win {
 	char     *ref_raw;   // smem: window reference, ASCII
 	uint8_t  *treg;      // smem region T: Mer->Node table during the build, graph-stage arrays afterwards
 	uint32_t *t_key; uint16_t *t_id;   // smem: table keys; slot -> dense node id (bit 15: needs first-seen edge order)
+	lb2_variant *ovar; char *ostr; uint32_t ovar_cap, ostr_cap; bool escal;   // this window's output slab (regular or large)
 };
 
 LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2);

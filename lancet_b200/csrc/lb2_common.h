@@ -65,6 +65,10 @@ struct lb2_dev_out {
 	char            *strings;   // [n_windows * str_bytes]
 	uint32_t        *str_used;  // [n_windows]
 	unsigned long long *prof;   // [24] cycles per pipeline phase summed over windows (lane 0), may be NULL
+	// large output slabs handed to windows of the escalation pass (a window that emits more records than its regular
+	// slab holds is one of them): big_slot[w] = index of the large slab window w used, or 0xFFFFFFFF
+	lb2_variant     *big_variants; char *big_strings; uint32_t *big_slot; uint32_t *big_count;
+	uint32_t         big_cap, big_max_var, big_str_bytes;
 };
 
 #endif

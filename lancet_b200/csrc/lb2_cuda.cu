@@ -30,7 +30,7 @@ lb2_window_kernel(const lb2_launch *Lp)
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ uint32_t s_next;
 	lb2_win W;
-	W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O;
+	W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O; W.escal = (Lp->win_list != nullptr);
 	lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws); W.ws0 = W.ws;
 	W.sh = (lb2_sh *)smem;
 	W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
@@ -94,10 +94,12 @@ __global__ void lb2_gather_kernel(const lb2_launch *Lp)
 	const uint32_t w = blockIdx.x; const uint32_t nv = Lp->O.info[w].n_variants;
 	if (!nv) { return; }
 	const uint32_t vo = Lp->var_off[w], so = Lp->str_off[w], sb = Lp->O.str_used[w];
+	const uint32_t big = Lp->O.big_slot[w];
+	const lb2_variant *vsrc = (big != 0xFFFFFFFFu) ? Lp->O.big_variants + (size_t)big * Lp->O.big_max_var : Lp->O.variants + (size_t)w * Lp->C.max_var;
 	for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
-		lb2_variant v = Lp->O.variants[(size_t)w * Lp->C.max_var + i]; v.str_off += so; Lp->cvars[vo + i] = v;
+		lb2_variant v = vsrc[i]; v.str_off += so; Lp->cvars[vo + i] = v;
 	}
-	const char *src = Lp->O.strings + (size_t)w * Lp->C.str_bytes;
+	const char *src = (big != 0xFFFFFFFFu) ? Lp->O.big_strings + (size_t)big * Lp->O.big_str_bytes : Lp->O.strings + (size_t)w * Lp->C.str_bytes;
 	for (uint32_t i = threadIdx.x; i < sb; i += blockDim.x) { Lp->cstr[so + i] = src[i]; }
 }
 
@@ -112,7 +114,8 @@ struct lb2_ctx {
 	// device buffers of the resident batch
 	struct Buf { void *p = nullptr; size_t cap = 0; };
 	Buf d_ref_off, d_ref_start, d_wr_off, d_wr_idx, d_base_off, d_flags, d_name_rank, d_ref_seq, d_seq, d_qual;
-	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws;
+	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws, d_big_vars, d_big_strs, d_big_slot;
+	uint32_t *d_big_count = nullptr; uint32_t big_cap = 256, big_max_var = 1024, big_str_bytes = 128u << 10;
 	uint32_t *d_counter = nullptr, *d_totals = nullptr; lb2_launch *d_launch = nullptr; unsigned long long *d_prof = nullptr;
 	lb2_launch L;
 	uint32_t n_windows = 0; bool resident = false, ran = false;
@@ -186,6 +189,8 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
+	ctx->big_cap = env_u32("LB2_BIG_SLABS", 256); ctx->big_max_var = env_u32("LB2_BIG_MAX_VAR", 1024); ctx->big_str_bytes = env_u32("LB2_BIG_STR_BYTES", 128u << 10);
+	if (cudaMalloc(&ctx->d_big_count, 4) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->threads = env_u32("LB2_THREADS", 256); if (ctx->threads < 32 || ctx->threads > 256 || (ctx->threads & 31)) { ctx->threads = 256; }
 	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
 		delete ctx; return LB2_ERR_CUDA;
@@ -200,10 +205,10 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	lb2_ctx::Buf *bufs[] = { &ctx->d_ref_off, &ctx->d_ref_start, &ctx->d_wr_off, &ctx->d_wr_idx, &ctx->d_base_off, &ctx->d_flags, &ctx->d_name_rank,
 		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used, &ctx->d_var_off, &ctx->d_str_off,
-		&ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws };
+		&ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot };
 	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
 	if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); } if (ctx->d_retry.p) { cudaFree(ctx->d_retry.p); }
-	cudaFree(ctx->d_counter2); cudaFree(ctx->d_retry_count); cudaFree(ctx->d_launch2);
+	cudaFree(ctx->d_big_count); cudaFree(ctx->d_counter2); cudaFree(ctx->d_retry_count); cudaFree(ctx->d_launch2);
 	cudaFree(ctx->d_counter); cudaFree(ctx->d_totals); cudaFree(ctx->d_launch);
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -275,8 +280,12 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	if ((rc = lb2_reserve(ctx, ctx->d_str_used, sizeof(uint32_t) * (size_t)W))) return rc;
 	if ((rc = lb2_reserve(ctx, ctx->d_var_off, sizeof(uint32_t) * (size_t)W))) return rc;
 	if ((rc = lb2_reserve(ctx, ctx->d_str_off, sizeof(uint32_t) * (size_t)W))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_cvars, sizeof(lb2_variant) * (size_t)W * C.max_var))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_cstr, (size_t)W * C.str_bytes))) return rc;
+	const uint32_t nbig = ctx->escalate ? std::min<uint32_t>(ctx->big_cap, std::max(W, 1u)) : 0u;
+	if ((rc = lb2_reserve(ctx, ctx->d_cvars, sizeof(lb2_variant) * ((size_t)W * C.max_var + (size_t)nbig * ctx->big_max_var)))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_cstr, (size_t)W * C.str_bytes + (size_t)nbig * ctx->big_str_bytes))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_big_vars, sizeof(lb2_variant) * (size_t)nbig * ctx->big_max_var + 64))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_big_strs, (size_t)nbig * ctx->big_str_bytes + 64))) return rc;
+	if ((rc = lb2_reserve(ctx, ctx->d_big_slot, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
 	lb2_launch &L = ctx->L;
 	L.P = ctx->P; L.C = C;
 	L.B.n_windows = W; L.B.ref_off = (const uint32_t *)ctx->d_ref_off.p; L.B.ref_start = (const int32_t *)ctx->d_ref_start.p;
@@ -286,6 +295,8 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	L.B.seq = (const char *)ctx->d_seq.p; L.B.qual = (const char *)ctx->d_qual.p;
 	L.O.info = (lb2_window_info *)ctx->d_info.p; L.O.variants = (lb2_variant *)ctx->d_vars.p; L.O.strings = (char *)ctx->d_strs.p;
 	L.O.str_used = (uint32_t *)ctx->d_str_used.p; L.O.prof = ctx->d_prof;
+	L.O.big_variants = (lb2_variant *)ctx->d_big_vars.p; L.O.big_strings = (char *)ctx->d_big_strs.p; L.O.big_slot = (uint32_t *)ctx->d_big_slot.p;
+	L.O.big_count = ctx->d_big_count; L.O.big_cap = nbig; L.O.big_max_var = ctx->big_max_var; L.O.big_str_bytes = ctx->big_str_bytes;
 	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
 	L.win_list = nullptr; L.n_list = nullptr;
 	if ((rc = lb2_reserve(ctx, ctx->d_retry, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
@@ -328,6 +339,8 @@ extern "C" int lb2_run(lb2_ctx *ctx)
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
 	const uint32_t W = ctx->n_windows;
 	LB2_CK(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
+	LB2_CK(cudaMemsetAsync(ctx->d_big_count, 0, 4, ctx->stream));
+	LB2_CK(cudaMemsetAsync(ctx->d_big_slot.p, 0xFF, sizeof(uint32_t) * (size_t)(W + 1), ctx->stream));
 	LB2_CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	if (W) {
 		lb2_window_kernel<<<ctx->C.n_slots, ctx->threads, ctx->C.smem_bytes, ctx->stream>>>(ctx->d_launch);

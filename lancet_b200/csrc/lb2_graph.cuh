@@ -770,6 +770,41 @@ LB2_DEVNI void lb2_materialize(lb2_win &W) {
 	}
 }
 
+// Graph_t::cleanDead by all lanes: every live node finds its next live node (unordered_map::erase keeps the relative
+// order of the survivors), then the bucket array is rebuilt from its invariant (bucket -> node before the bucket's
+// first node).  Dead nodes are only read, live nodes only written by their owner lane.
+LB2_DEVNI void lb2_clean_dead_par(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t NT = sh->n_rows + sh->n_spec;
+	if (tid == 0) { sh->n_dead = 0; }
+	lb2_sync();
+	uint32_t nd = 0;
+	for (uint32_t r = tid; r < NT; r += nt) {
+		const uint8_t f = ws.d_flags[r];
+		if (f & LB2_NF_GONE) { continue; }
+		if (f & LB2_NF_DEAD) { ++nd; continue; }
+		uint32_t x = ws.d_lnext[r];
+		while (x != LB2_NIL && (ws.d_flags[x] & LB2_NF_DEAD)) { x = ws.d_lnext[x]; }
+		ws.d_lnext[r] = x;
+	}
+	if (nd) { lb2_add32(&sh->n_dead, nd); }
+	if (tid == 0) { uint32_t x = sh->lhead; while (x != LB2_NIL && (ws.d_flags[x] & LB2_NF_DEAD)) { x = ws.d_lnext[x]; } sh->lhead = x; }
+	lb2_sync();
+	if (!sh->n_dead) { return; }
+	for (uint32_t b = tid; b < sh->bkt_count; b += nt) { lb2_bset(W, b, LB2_NIL); }
+	lb2_sync();
+	for (uint32_t r = tid; r < NT; r += nt) {
+		const uint8_t f = ws.d_flags[r];
+		if (f & LB2_NF_GONE) { continue; }
+		if (f & LB2_NF_DEAD) { ws.d_flags[r] = f | LB2_NF_GONE; continue; }
+		const uint32_t nb = ws.d_lnext[r];
+		if (nb != LB2_NIL && ws.d_bk[nb] != ws.d_bk[r]) { lb2_bset(W, ws.d_bk[nb], r); }
+	}
+	if (tid == 0) { if (sh->lhead != LB2_NIL) { lb2_bset(W, ws.d_bk[sh->lhead], LB2_SENT); } sh->elem_count -= sh->n_dead; }
+	lb2_sync();
+}
+
 // Graph_t::compress (all lanes)
 LB2_DEVNI void lb2_compress(lb2_win &W, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
@@ -783,10 +818,211 @@ LB2_DEVNI void lb2_compress(lb2_win &W, int compid) {
 	if (lb2_tid() == 0 && !sh->err) {
 		const lb2_job *jobs = (const lb2_job *)ws.jobs;
 		for (uint32_t q = 0; q < sh->n_jobs; ++q) { const lb2_job &jb = jobs[q]; ws.d_str[jb.node] = jb.so; ws.d_cd[jb.node] = jb.co; ws.d_len[jb.node] = jb.curlen; }
-		lb2_clean_dead(W);
 	}
+	lb2_sync();
+	if (!sh->err) { lb2_clean_dead_par(W); }
 	lb2_mark(W, LB2_PH_CCLEAN);
 	lb2_sync();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The FIRST compaction of a component (hundreds of single-k-mer nodes -> a handful of unitigs) by all lanes.
+// compressNode's stop conditions (src/Graph.cc:2486-2706; Node_t::getBuddy/isTandem src/Node.cc:235-266) only look
+// at the two nodes of a step, and absorbing a node never changes them for any other pair, so "x absorbs y through
+// its side o" is a static, symmetric relation (a link): x, y not special, not tandem, x has exactly one edge leaving
+// in orientation o (to y != x) and y exactly one edge leaving towards x.  The maximal chains of links are the
+// unitigs; a chain is swallowed whole by its first node in map iteration order (compressNode(F) then (R) run to the
+// chain's two ends).  So: successor of every oriented node (x,o), pointer jumping to the chain end (distance + end
+// state), seed = smallest list index of the chain, and every member's slot in the seed's absorb order
+// (F-side in order, then R-side).  The float coverage averages are still folded in that order, one lane per chain;
+// the edge surgery is evaluated from the untouched edge arrays into a side buffer (seed keeps its non-link edges, then
+// the F-end's, then the R-end's outward edges; every target is renamed to its chain's seed, orientation bits flipped
+// for reverse-complemented members) and written back after a barrier.  A closed ring of links (no chain end) makes
+// the function return false before anything is modified; the caller then runs the sequential sweep.
+// ---------------------------------------------------------------------------------------------------
+LB2_DEV uint32_t lb2_pc_succ(lb2_ws &ws, uint32_t r, int o) {       // oriented successor state or LB2_NIL
+	if (!ws.d_color[r]) { return LB2_NIL; }
+	const lb2_edge *e = lb2_edges(ws, r); const int ne = ws.d_ne[r]; int cnt = 0; lb2_edge pick; pick.to = 0; pick.dir = 0;
+	for (int i = 0; i < ne; ++i) { if ((int)(e[i].dir >> 1) == o) { ++cnt; pick = e[i]; } }
+	if (cnt != 1) { return LB2_NIL; }
+	const uint32_t v = pick.to; if (!ws.d_color[v]) { return LB2_NIL; }
+	const int ov = (int)(pick.dir & 1), back = 1 - ov;
+	const lb2_edge *f = lb2_edges(ws, v); const int nf = ws.d_ne[v]; int cb = 0;
+	for (int i = 0; i < nf; ++i) { if ((int)(f[i].dir >> 1) == back) { ++cb; } }
+	if (cb != 1) { return LB2_NIL; }
+	return 2u * v + (uint32_t)ov;
+}
+#define LB2_PI_MEMBER 0x20000u
+#define LB2_PI_SEED   0x40000u
+LB2_DEV lb2_edge lb2_pc_map(const uint32_t *INF, lb2_edge e) {       // rename the target to its chain's seed
+	const uint32_t iy = INF[e.to];
+	if (iy & LB2_PI_MEMBER) { e.to = (uint16_t)(iy & 0xFFFFu); e.dir = (uint16_t)(e.dir ^ ((iy >> 16) & 1u)); }
+	return e;
+}
+
+#ifdef LB2_HOSTSIM
+static unsigned long lb2_dbg_par[4];     // debug build only: [0] taken, [1] no scratch, [2] ring
+#define LB2_DBG(i) (++lb2_dbg_par[i])
+#else
+#define LB2_DBG(i) ((void)0)
+#endif
+LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t NT = sh->n_rows + sh->n_spec;
+	if ((size_t)NT * 4 + 8 > ws.px_words) { LB2_DBG(1); return false; }
+	uint32_t *J = ws.px, *SEED = J + 2 * NT, *INF = SEED + NT;
+	lb2_edge *etmp = ws.etmp; uint8_t *etn = (uint8_t *)(ws.etmp + (size_t)LB2_MAX_ROWS * LB2_ECAP);
+	lb2_job *jobs = (lb2_job *)ws.jobs;
+	// eligibility (d_color is idle between the cycle checks)
+	for (uint32_t r = tid; r < NT; r += nt) {
+		uint8_t ok = (ws.d_comp[r] == compid && !(ws.d_flags[r] & (LB2_NF_DEAD | LB2_NF_GONE | LB2_NF_SPECIAL))) ? 1 : 0;
+		if (ok) { const lb2_edge *e = lb2_edges(ws, r); const int ne = ws.d_ne[r]; for (int i = 0; i < ne; ++i) { if (e[i].to == r) { ok = 0; } } }
+		ws.d_color[r] = ok; SEED[r] = LB2_NIL; INF[r] = 0;
+	}
+	if (tid == 0) { sh->flag_b = 0; }
+	lb2_sync();
+	for (uint32_t s = tid; s < 2 * NT; s += nt) {
+		const uint32_t nx = lb2_pc_succ(ws, s >> 1, (int)(s & 1));
+		J[s] = (nx == LB2_NIL) ? (s << 16) : ((nx << 16) | 1u);
+	}
+	lb2_sync();
+	uint32_t rounds = 2; while ((1u << (rounds - 2)) < 2 * NT) { ++rounds; }
+	for (uint32_t it = 0; it < rounds; ++it) {
+		for (uint32_t s = tid; s < 2 * NT; s += nt) {
+			const uint32_t w = J[s], j = w >> 16;
+			if (j == s) { continue; }
+			const uint32_t w2 = lb2_lds(&J[j]), j2 = w2 >> 16;
+			if (j2 == j) { continue; }                      // j is a chain end
+			uint32_t d = (w & 0xFFFFu) + (w2 & 0xFFFFu); if (d > 0xFFFFu) { d = 0xFFFFu; }
+			J[s] = (j2 << 16) | d;
+		}
+		lb2_sync();
+	}
+	for (uint32_t s = tid; s < 2 * NT; s += nt) { const uint32_t j = J[s] >> 16; if ((J[j] >> 16) != j) { sh->flag_b = 1; } }   // never reached an end: ring
+	lb2_sync();
+	if (sh->flag_b) { lb2_sync(); LB2_DBG(2); return false; }
+	LB2_DBG(0);
+	// seed of every chain: smallest list index; key of a chain = smaller node id of its two end states
+	for (uint32_t r = tid; r < NT; r += nt) {
+		if (!ws.d_color[r]) { continue; }
+		const uint32_t a = J[2 * r] >> 17, b = J[2 * r + 1] >> 17;
+		lb2_min32(&SEED[a < b ? a : b], ((uint32_t)ws.d_pos[r] << 16) | r);
+	}
+	lb2_sync();
+	for (uint32_t r = tid; r < NT; r += nt) {
+		if (!ws.d_color[r]) { continue; }
+		const uint32_t a = J[2 * r] >> 17, b = J[2 * r + 1] >> 17;
+		const uint32_t sd = SEED[a < b ? a : b] & 0xFFFFu;
+		if (sd == r) { INF[r] = LB2_PI_SEED | r; }
+		else { const uint32_t ostar = ((J[2 * r] >> 16) == (J[2 * sd] >> 16)) ? 0u : 1u; INF[r] = LB2_PI_MEMBER | (ostar << 16) | sd; }
+	}
+	lb2_sync();
+	// jobs (seeds that absorb something) and their chain segments
+	const uint32_t tot = lb2_excl_scan(W, NT,
+		[&](uint32_t r) -> uint32_t { if (!(INF[r] & LB2_PI_SEED)) { return 0u; } uint32_t na = (J[2 * r] & 0xFFFFu) + (J[2 * r + 1] & 0xFFFFu); return na ? ((1u << 16) | na) : 0u; },
+		[&](uint32_t r, uint32_t v) { if (INF[r] & LB2_PI_SEED) { SEED[r] = v; } });
+	const uint32_t njobs = tot >> 16;
+	for (uint32_t r = tid; r < NT; r += nt) {
+		const uint32_t ir = INF[r];
+		if (ir & LB2_PI_SEED) {
+			const uint32_t nF = J[2 * r] & 0xFFFFu, nR = J[2 * r + 1] & 0xFFFFu;
+			if (nF + nR) { lb2_job jb; jb.node = r; jb.cbeg = SEED[r] & 0xFFFFu; jb.nF = nF; jb.nAll = nF + nR; jb.len0 = ws.d_len[r]; jb.curlen = 0; jb.so = 0; jb.co = 0; jb.leftlen = 0; jb.pad = 0; jobs[SEED[r] >> 16] = jb; }
+		} else if (ir & LB2_PI_MEMBER) {
+			const uint32_t sd = ir & 0xFFFFu, ostar = (ir >> 16) & 1u, cbeg = SEED[sd] & 0xFFFFu;
+			const uint32_t dFs = J[2 * sd] & 0xFFFFu, dRs = J[2 * sd + 1] & 0xFFFFu;
+			const uint32_t dx = J[2 * r + ostar] & 0xFFFFu;
+			uint32_t slot;
+			if (dx < dFs) { slot = cbeg + (dFs - dx - 1); }
+			else { const uint32_t dy = J[2 * r + (1u - ostar)] & 0xFFFFu; slot = cbeg + dFs + (dRs - dy - 1); }
+			ws.chain[slot] = r | (ostar << 31);
+		}
+	}
+	lb2_sync();
+	// fold the float coverages in the reference's absorb order (src/Graph.cc:2631-2636), one lane per chain
+	for (uint32_t q = tid; q < njobs; q += nt) {
+		lb2_job jb = jobs[q]; const uint32_t node = jb.node; const uint32_t *chain = ws.chain + jb.cbeg;
+		float c0 = ws.d_cov[node * 4 + 0], c1 = ws.d_cov[node * 4 + 1], c2 = ws.d_cov[node * 4 + 2], c3 = ws.d_cov[node * 4 + 3];
+		uint32_t stn = ws.d_stn[node], stt = ws.d_stT[node], curlen = jb.len0, leftlen = 0;
+		for (uint32_t c = 0; c < jb.nAll; ++c) {
+			const uint32_t b = chain[c] & 0x7FFFFFFFu;
+			const int amerlen = (int)curlen - K + 1, bmerlen = (int)ws.d_len[b] - K + 1;
+			c0 = ((c0 * amerlen) + (ws.d_cov[b * 4 + 0] * bmerlen)) / (amerlen + bmerlen);
+			c1 = ((c1 * amerlen) + (ws.d_cov[b * 4 + 1] * bmerlen)) / (amerlen + bmerlen);
+			c2 = ((c2 * amerlen) + (ws.d_cov[b * 4 + 2] * bmerlen)) / (amerlen + bmerlen);
+			c3 = ((c3 * amerlen) + (ws.d_cov[b * 4 + 3] * bmerlen)) / (amerlen + bmerlen);
+			curlen += (uint32_t)bmerlen; stn += ws.d_stn[b]; stt += ws.d_stT[b];
+			if (c >= jb.nF) { leftlen += (uint32_t)bmerlen; }
+		}
+		ws.d_cov[node * 4 + 0] = c0; ws.d_cov[node * 4 + 1] = c1; ws.d_cov[node * 4 + 2] = c2; ws.d_cov[node * 4 + 3] = c3;
+		ws.d_stn[node] = (uint16_t)stn; ws.d_stT[node] = (uint16_t)stt;
+		uint32_t pos = leftlen + jb.len0;
+		for (uint32_t c = 0; c < jb.nF; ++c) { ws.cpos[jb.cbeg + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
+		pos = leftlen;
+		for (uint32_t c = jb.nF; c < jb.nAll; ++c) { pos -= ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; ws.cpos[jb.cbeg + c] = pos; }
+		ws.d_mincov[node] = 10000000; ws.d_mincovqv[node] = 10000000;
+		jobs[q].curlen = curlen; jobs[q].leftlen = leftlen;
+	}
+	lb2_sync();
+	if (tid == 0) {
+		for (uint32_t q = 0; q < njobs && !sh->err; ++q) { jobs[q].so = lb2_arena_alloc(W, jobs[q].curlen); jobs[q].co = lb2_arena_alloc(W, jobs[q].curlen * 2 * (uint32_t)sizeof(lb2_cov)); }
+		sh->n_jobs = njobs;
+	}
+	// edge surgery, evaluated from the untouched edge arrays into the side buffer
+	for (uint32_t z = tid; z < NT; z += nt) {
+		if (ws.d_comp[z] != compid || (ws.d_flags[z] & (LB2_NF_DEAD | LB2_NF_GONE)) || (INF[z] & LB2_PI_MEMBER)) { continue; }
+		lb2_edge *out = etmp + (size_t)z * LB2_ECAP; int no = 0; bool ovf = false;
+		const bool seed = (INF[z] & LB2_PI_SEED) != 0;
+		const uint32_t nF = seed ? (J[2 * z] & 0xFFFFu) : 0u, nR = seed ? (J[2 * z + 1] & 0xFFFFu) : 0u;
+		const lb2_edge *e = lb2_edges(ws, z); const int ne = ws.d_ne[z];
+		for (int i = 0; i < ne; ++i) {
+			const int st = (int)(e[i].dir >> 1);
+			if ((st == 0 && nF) || (st == 1 && nR)) { continue; }        // the link edge of that side
+			if (no >= LB2_ECAP) { ovf = true; break; }
+			out[no++] = lb2_pc_map(INF, e[i]);
+		}
+		for (int side = 0; side < 2 && !ovf; ++side) {
+			const uint32_t cnt = side ? nR : nF; if (!cnt) { continue; }
+			const uint32_t cbeg = SEED[z] & 0xFFFFu;
+			const uint32_t ce = ws.chain[cbeg + (side ? nF + nR : nF) - 1], last = ce & 0x7FFFFFFFu, fl = ce >> 31;
+			const int ot = side ? (int)(1u - fl) : (int)fl;                // orientation in which the end node is traversed
+			const lb2_edge *f = lb2_edges(ws, last); const int nf = ws.d_ne[last];
+			for (int i = 0; i < nf; ++i) {
+				if ((int)(f[i].dir >> 1) != ot) { continue; }               // (the single edge of the other side leads back into the chain)
+				if (no >= LB2_ECAP) { ovf = true; break; }
+				lb2_edge x = f[i]; x.dir = (uint16_t)(x.dir ^ (fl << 1));
+				out[no++] = lb2_pc_map(INF, x);
+			}
+		}
+		if (ovf) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); no = 0; }
+		etn[z] = (uint8_t)no;
+	}
+	lb2_sync();
+	if (sh->err) { return true; }
+	for (uint32_t z = tid; z < NT; z += nt) {
+		if (ws.d_comp[z] != compid || (ws.d_flags[z] & (LB2_NF_DEAD | LB2_NF_GONE))) { continue; }
+		if (INF[z] & LB2_PI_MEMBER) { ws.d_flags[z] |= LB2_NF_DEAD; continue; }
+		const int no = etn[z];
+		if (no > LB2_EINL && !ws.d_eov[z]) {
+			uint32_t blk = lb2_add32(&sh->n_eov, 1u);
+			if (blk >= LB2_EOV_BLOCKS) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); continue; }
+			ws.d_eov[z] = (uint8_t)(blk + 1);
+		}
+		lb2_edge *dst = lb2_edges(ws, z); const lb2_edge *src = etmp + (size_t)z * LB2_ECAP;
+		for (int i = 0; i < no; ++i) { dst[i] = src[i]; }
+		ws.d_ne[z] = (uint8_t)no;
+	}
+	lb2_sync();
+	if (sh->err) { if (tid == 0 && sh->n_eov > LB2_EOV_BLOCKS) { sh->n_eov = LB2_EOV_BLOCKS; } lb2_sync(); return true; }
+	lb2_mark(W, LB2_PH_CSWEEP);
+	lb2_materialize(W);
+	lb2_sync();
+	lb2_mark(W, LB2_PH_CMAT);
+	for (uint32_t q = tid; q < njobs; q += nt) { const lb2_job &jb = jobs[q]; ws.d_str[jb.node] = jb.so; ws.d_cd[jb.node] = jb.co; ws.d_len[jb.node] = (uint16_t)jb.curlen; }
+	lb2_sync();
+	lb2_clean_dead_par(W);
+	lb2_mark(W, LB2_PH_CCLEAN);
+	return true;
 }
 
 LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {      // all lanes

@@ -22,7 +22,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	LB2_TAKE(d_mincov, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_mincovqv, int32_t, LB2_MAX_ROWS); LB2_TAKE(d_str, uint32_t, LB2_MAX_ROWS); LB2_TAKE(d_cd, uint32_t, LB2_MAX_ROWS);
 	LB2_TAKE(deficit, uint16_t, c.deficit_bytes / 2);
 	LB2_TAKE(refnode, uint32_t, LB2_MAX_REF); LB2_TAKE(refcov, uint16_t, 2 * LB2_MAX_REF * 2);
-	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(emu, uint32_t, (size_t)c.max_nodes * 3 + (size_t)c.max_nodes * 9 / 4 + 64); LB2_TAKE(queue, lb2_qent, c.queue_cap); LB2_TAKE(jobs, uint32_t, LB2_MAX_ROWS * 10); LB2_TAKE(pstart, uint32_t, LB2_MAX_PNODES + 1);
+	LB2_TAKE(arena, uint8_t, c.arena_bytes); LB2_TAKE(etmp, lb2_edge, (size_t)LB2_MAX_ROWS * LB2_ECAP + LB2_MAX_ROWS / 2 + 8); LB2_TAKE(emu, uint32_t, (size_t)c.max_nodes * 3 + (size_t)c.max_nodes * 9 / 4 + 64); LB2_TAKE(queue, lb2_qent, c.queue_cap); LB2_TAKE(jobs, uint32_t, LB2_MAX_ROWS * 10); LB2_TAKE(pstart, uint32_t, LB2_MAX_PNODES + 1);
 	LB2_TAKE(pathseq, char, LB2_MAX_PATH + 16); LB2_TAKE(pcovN, lb2_cov, LB2_MAX_PATH + 16); LB2_TAKE(pcovT, lb2_cov, LB2_MAX_PATH + 16);
 	LB2_TAKE(pnodes, uint32_t, LB2_MAX_PNODES); LB2_TAKE(pdirs, uint8_t, LB2_MAX_PNODES); LB2_TAKE(peidx, uint8_t, LB2_MAX_PNODES);
 	LB2_TAKE(aln_ref, char, LB2_MAX_PATH + LB2_MAX_REF + 16); LB2_TAKE(aln_path, char, LB2_MAX_PATH + LB2_MAX_REF + 16);
@@ -62,7 +62,15 @@ LB2_DEVNI void lb2_ref_coverage(lb2_win &W)
 LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 {
 	lb2_sh *sh = W.sh; const lb2_params *P = W.P; const unsigned tid = lb2_tid();
-	if (tid == 0) { for (int i = 0; i < 24; ++i) { sh->prof[i] = 0; } sh->t_last = lb2_clock(); }
+	if (tid == 0) {
+		for (int i = 0; i < 24; ++i) { sh->prof[i] = 0; } sh->t_last = lb2_clock();
+		uint32_t slot = LB2_NIL;
+		if (W.escal && W.O->big_count) { slot = lb2g_add32(W.O->big_count, 1u); if (slot >= W.O->big_cap) { slot = LB2_NIL; } W.O->big_slot[w] = slot; }
+		sh->big = slot;
+	}
+	lb2_sync();
+	if (sh->big != LB2_NIL) { W.ovar = W.O->big_variants + (size_t)sh->big * W.O->big_max_var; W.ostr = W.O->big_strings + (size_t)sh->big * W.O->big_str_bytes; W.ovar_cap = W.O->big_max_var; W.ostr_cap = W.O->big_str_bytes; }
+	else { W.ovar = W.O->variants + (size_t)w * W.C->max_var; W.ostr = W.O->strings + (size_t)w * W.C->str_bytes; W.ovar_cap = W.C->max_var; W.ostr_cap = W.C->str_bytes; }
 	lb2_stage_window(W, w);
 	lb2_mark(W, LB2_PH_STAGE);
 	if (sh->status == LB2_WIN_OK) {
@@ -104,14 +112,22 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			const int numcomp = sh->numcomp;
 			for (int c = 1; c <= numcomp; ++c) {
 				lb2_find_anchors(W, c);
-				if (tid == 0) {
-					lb2_mark_ref_ends(W, c);
-					sh->flag_c = (!sh->err && lb2_has_cycle(W)) ? 1u : 0u;
-					lb2_mark(W, LB2_PH_ANCHOR);
-				}
+				if (tid == 0) { lb2_mark_ref_ends(W, c); sh->flag_c = 0; lb2_mark(W, LB2_PH_ANCHOR); }
 				lb2_sync();
+				if (!sh->err) {
+					// the cycle check before the first compaction (src/Microassembler.cc:179) gives the same answer on the
+					// compacted graph (a chain of links is always traversed whole), where it costs a handful of nodes
+					const bool par = lb2_compress_par(W, c);
+					if (!par) {
+						if (tid == 0) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+						lb2_sync();
+						if (!sh->flag_c) { lb2_compress(W, c); }
+					} else {
+						if (tid == 0 && !sh->err) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+						lb2_sync();
+					}
+				}
 				if (!sh->flag_c && !sh->err) {
-					lb2_compress(W, c);
 					if (tid == 0 && !sh->err) { lb2_remove_lowcov(W, c); }      // removeLowCov(true,c): sweep, cleanDead, then compress
 					lb2_sync();
 					if (!sh->err) { lb2_compress(W, c); }

@@ -62,6 +62,7 @@ struct lb2_ws {
 	uint32_t *refnode;            // [LB2_MAX_REF] node of the reference k-mer at each offset (dense id, then row id)
 	uint16_t *refcov;             // [2 samples][LB2_MAX_REF][2] fwd,rev
 	uint8_t  *arena;
+	lb2_edge *etmp;               // side buffer of the parallel edge surgery [LB2_MAX_ROWS][LB2_ECAP] + a count per row
 	uint32_t *emu;                // order-emulation arrays when they do not fit in shared memory
 	lb2_qent *queue; uint32_t *jobs; uint32_t *pstart;
 	// --- path processing ---
@@ -93,7 +94,7 @@ struct lb2_sh {
 	// output
 	uint32_t n_var, str_used, n_k_tried, final_k, last_nodes;
 	int32_t  numcomp;
-	uint32_t stop_k;
+	uint32_t stop_k; uint32_t n_dead; uint32_t big;
 	unsigned long long prof[24]; unsigned long long t_last;
 	uint32_t scan[520];           // block-scan partials (<= 512 lanes)
 };

@@ -45,10 +45,10 @@ int main(int argc, char **argv)
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
 	B.base_off = base_off.data(); B.flags = flags.data(); B.name_rank = name_rank.data(); B.ref_seq = ref_seq.data(); B.seq = seq.data(); B.qual = qual.data();
 	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
-	lb2_dev_out O; O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
+	lb2_dev_out O; memset(&O, 0, sizeof O); O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);
 	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp, C.table_slots, C.graph_bytes) + 64, 0);
-	lb2_win Wn; Wn.P = &P; Wn.C = &C; Wn.B = &B; Wn.O = &O;
+	lb2_win Wn; Wn.P = &P; Wn.C = &C; Wn.B = &B; Wn.O = &O; Wn.escal = false;
 	lb2_ws_layout(C, slab.data(), &Wn.ws); Wn.ws0 = Wn.ws;
 	Wn.sh = (lb2_sh *)smem.data();
 	Wn.ref_raw = (char *)smem.data() + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
@@ -77,6 +77,7 @@ int main(int argc, char **argv)
 				x.rcn_fwd, x.rcn_rev, x.rct_fwd, x.rct_rev, x.acn_fwd, x.acn_rev, x.act_fwd, x.act_rev, x.prev_bp_ref, x.prev_bp_alt);
 		}
 	}
+	if (getenv("LB2_SIM_DBG")) { fprintf(stderr, "compress_par taken %lu, no scratch %lu, ring %lu\n", lb2_dbg_par[0], lb2_dbg_par[1], lb2_dbg_par[2]); }
 	if (fo != stdout) fclose(fo);
 	return 0;
 }

@@ -41,7 +41,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *b, lb2_result *res)
 	lb2_dev_out O; memset(&O, 0, sizeof O); O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);
 	std::vector<uint8_t> slab(wsb, 0); std::vector<uint8_t> smem(lb2_smem_bytes(C.max_bp, C.table_slots, C.graph_bytes) + 64, 0);
-	lb2_win Wn; Wn.P = &ctx->P; Wn.C = &C; Wn.B = &B; Wn.O = &O;
+	lb2_win Wn; Wn.P = &ctx->P; Wn.C = &C; Wn.B = &B; Wn.O = &O; Wn.escal = false;
 	lb2_ws_layout(C, slab.data(), &Wn.ws); Wn.ws0 = Wn.ws;
 	Wn.sh = (lb2_sh *)smem.data();
 	Wn.ref_raw = (char *)smem.data() + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
