@@ -48,6 +48,7 @@ struct lb2_cfg {
 	uint32_t graph_bytes;   // shared memory for the graph-stage arrays (quality-mask bytes included)
 	uint32_t n_slots;       // resident CTAs (workspace slabs)
 	uint32_t smem_bytes;    // dynamic shared memory per CTA
+	uint32_t debug_flags;   // bit 0: sequential first compaction (LB2_DEBUG_FLAGS, debugging aid)
 };
 
 // device view of one uploaded batch

@@ -870,7 +870,10 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const uint32_t NT = sh->n_rows + sh->n_spec;
-	if ((size_t)NT * 4 + 8 > ws.px_words) { LB2_DBG(1); return false; }
+#ifdef LB2_HOSTSIM
+	if (getenv("LB2_SIM_NOPAR")) { LB2_DBG(1); return false; }
+#endif
+	if ((size_t)NT * 4 + 8 > ws.px_words || (W.C->debug_flags & 1u)) { LB2_DBG(1); return false; }
 	uint32_t *J = ws.px, *SEED = J + 2 * NT, *INF = SEED + NT;
 	lb2_edge *etmp = ws.etmp; uint8_t *etn = (uint8_t *)(ws.etmp + (size_t)LB2_MAX_ROWS * LB2_ECAP);
 	lb2_job *jobs = (lb2_job *)ws.jobs;

@@ -346,11 +346,11 @@ LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
 			ACNF = 0; ACNR = 0;
 		}
 		if (ACNF > 0 || ACNR > 0 || ACTF > 0 || ACTR > 0) {
-			const lb2_dev_out *O = W.O; uint32_t w = sh->w;
-			if (sh->n_var >= W.C->max_var) { sh->err |= 1u << LB2_D_VARIANTS; return; }
+			uint32_t w = sh->w;
+			if (sh->n_var >= W.ovar_cap) { sh->err |= 1u << LB2_D_VARIANTS; return; }
 			uint32_t need = t.ref_len + t.qry_len;
-			char *spool = O->strings + (size_t)w * W.C->str_bytes;
-			if (sh->str_used + need + 64 > W.C->str_bytes) { sh->err |= 1u << LB2_D_STRINGS; return; }
+			char *spool = W.ostr;
+			if (sh->str_used + need + 64 > W.ostr_cap) { sh->err |= 1u << LB2_D_STRINGS; return; }
 			lb2_variant v;
 			v.window = w; v.pos = (int32_t)t.pos - 1; v.str_off = sh->str_used;
 			v.ref_len = (uint16_t)t.ref_len; v.alt_len = (uint16_t)t.qry_len;
@@ -366,7 +366,7 @@ LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
 			v.rcn_fwd = RCNF; v.rcn_rev = RCNR; v.rct_fwd = RCTF; v.rct_rev = RCTR;
 			v.acn_fwd = ACNF; v.acn_rev = ACNR; v.act_fwd = ACTF; v.act_rev = ACTR;
 			v.code = t.code; v.prev_bp_ref = t.prev_bp_ref; v.prev_bp_alt = t.prev_bp_alt; v.kmer = (uint8_t)K;
-			O->variants[(size_t)w * W.C->max_var + sh->n_var] = v;
+			W.ovar[sh->n_var] = v;
 			sh->n_var += 1;
 		}
 	}

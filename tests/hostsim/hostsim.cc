@@ -6,6 +6,7 @@
 #define LB2_HOSTSIM 1
 #include <cstdio>
 #include <cstdlib>
+#include <stdlib.h>
 #include <cstring>
 #include <string>
 #include <vector>
