@@ -189,13 +189,20 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 
 // ---------------------------------------------------------------------------------------------
 // Mer -> Node table in SHARED memory (region T), TS = cfg.table_slots slots, per slot:
-//   t_key  u32  0x80000000 | fingerprint10 << 21 | (g << 1 | ori): g = staged base index of one
-//               representative occurrence (matches are verified against the packed bases)
-//   t_id   u16  (after the sort) dense node id, bit 15 = "branching" (needs first-seen edge order)
-// and, in GLOBAL memory, fed by fire-and-forget reductions (nothing on the lane's critical path reads them back):
-//   g_occ  u32  0xFFFFFFFF - first occurrence (max)
-//   g_cnt  2xu32  tumour / normal occurrence counts, fwd in the low half, rev in the high half (add)
-//   g_em   u32  bits 0-7 edge types seen (start orientation*4 + appended base), bit 8 normal, bit 9 tumour-qualified (or)
+//   t_key  u32  0x80000000 | fingerprint10 << 21 | (g << 1 | ori): g = staged base index of the FIRST occurrence seen
+//               so far (kept minimal with a shared-memory min: reads are staged in the reference's processing
+//               order, so the smallest g is the occurrence that inserts the node into the reference's map);
+//               matches are verified against the packed bases
+//   t_id   u16  during the walk: bits 0-7 edge types seen (start orientation*4 + appended base), bit 8 normal,
+//               bit 9 tumour-qualified (tested with a plain load, set with a shared-memory or only when missing);
+//               after the compaction: dense node id, bit 15 = "branching" (needs first-seen edge order)
+// and, in GLOBAL memory:
+//   g_cnt  2xu32 per slot  tumour / normal occurrence counts, fwd in the low half, rev in the high half
+//               (fire-and-forget reductions: nothing on the lane's critical path reads them back)
+//   g_em   u32 per DENSE node  the slot's mask, saved before t_id is reused
+//   inst   u32 per occurrence  slot | orientation << 31 (| 0x40000000 suppressed by the mate replay), indexed
+//               ibase + offset * istride: transposed (offset-major) so that the lanes of a warp -- one read each, same
+//               offset -- store to consecutive words; read-major when the transposed array would not fit
 // ---------------------------------------------------------------------------------------------
 #define LB2_EM_NORMAL 0x100u
 #define LB2_EM_TUMOR  0x200u
@@ -222,7 +229,10 @@ template <int NWT = LB2_MAXW> LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, co
 		if ((cur & 0xFFE00000u) == fp) {
 			uint32_t r = cur & 0x1FFFFFu;
 			lb2_kmer o; lb2_extract<NWT>(W.bits, r >> 1, K, o);
-			if (lb2_equal<NWT>(o, (r & 1) ? nonc : canon, nw)) { return i; }
+			if (lb2_equal<NWT>(o, (r & 1) ? nonc : canon, nw)) {
+				if (insert && rep < r) { lb2_min32(&tk[i], fp | rep); }      // same k-mer => same fingerprint: the word orders by rep
+				return i;
+			}
 		}
 		i = (i + 1) & mask;
 	}
@@ -230,8 +240,14 @@ template <int NWT = LB2_MAXW> LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, co
 	return LB2_NIL;
 }
 
+// set mask bits of a slot (16-bit lanes of the words that later hold t_id)
+LB2_DEV void lb2_em_or(lb2_win &W, uint32_t slot, uint32_t bits) {
+	uint32_t *wp = (uint32_t *)W.t_id + (slot >> 1); const uint32_t sh = (slot & 1u) << 4;
+	if ((((lb2_ld32(wp)) >> sh) & bits) != bits) { lb2_or32(wp, bits << sh); }
+}
+
 // one work item: a whole read, or a 64-pair chunk of the reference "read"
-template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uint32_t o_end, uint32_t kbase,
+template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
                       bool isref, uint32_t cls, int K, int nw)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
@@ -252,24 +268,22 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 	uint32_t ori_u = fless ? 0u : 1u;
 	uint32_t su = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
-	lb2g_red_max(&ws.g_occ[su], 0xFFFFFFFFu - (kbase + o_begin));
-	ws.inst[kbase + o_begin] = su | (ori_u << 31);
+	ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
 	if (isref) { ws.refnode[o_begin] = su; }
 	else if (o_begin == 0) {
 		lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
-		if (normal) { lb2g_red_or(&ws.g_em[su], LB2_EM_NORMAL); }
+		if (normal) { lb2_em_or(W, su, LB2_EM_NORMAL); }
 	}
 	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
 		if ((g & 15) == 0) { wordbuf = lb2_lds(&W.bits[g >> 4]); }
 		int c = (wordbuf >> ((g & 15) << 1)) & 3;
-		int a = lb2_getbase(W.bits, g0 + o);                      // base that leaves the window
+		int a = (int)(f.w[0] & 3);                                 // base that leaves the window (first base of u)
 		lb2_roll_fwd<NWT>(f, K, c); lb2_roll_rc<NWT>(rc, K, c);
 		fless = lb2_less<NWT>(f, rc, nw);
 		uint32_t ori_v = fless ? 0u : 1u;
 		uint32_t sv = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, K, nw, true);
 		if (sv == LB2_NIL) { return; }
-		lb2g_red_max(&ws.g_occ[sv], 0xFFFFFFFFu - (kbase + o + 1));
-		ws.inst[kbase + o + 1] = sv | (ori_v << 31);
+		ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
 		uint32_t emu = 1u << (ori_u * 4 + (uint32_t)c);            // u leaves in orientation ori_u appending c
 		uint32_t emv = 1u << ((1u - ori_v) * 4 + (uint32_t)(3 - a)); // v leaves in the flipped orientation appending comp(a)
 		if (isref) { ws.refnode[o + 1] = sv; }
@@ -286,7 +300,7 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 				if (clean) { emu |= LB2_EM_TUMOR; emv |= LB2_EM_TUMOR; }
 			}
 		}
-		lb2g_red_or(&ws.g_em[su], emu); lb2g_red_or(&ws.g_em[sv], emv);
+		lb2_em_or(W, su, emu); lb2_em_or(W, sv, emv);
 		su = sv; ori_u = ori_v;
 	}
 }
@@ -360,7 +374,9 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	const uint32_t R = sh->R, L = sh->L, TS = C->table_slots;
 	if (!sh->bits_live) { lb2_stage_bits(W); }
 	if (!sh->lowq_live && sh->has_lowq) { lb2_stage_lowq(W); }
-	W.t_key = (uint32_t *)W.treg; W.t_id = (uint16_t *)(W.t_key + TS);
+	if (tid == 0) { sh->maxnk = 0; W.t_key = (uint32_t *)W.treg; W.t_id = (uint16_t *)(W.t_key + TS); }
+	lb2_sync();
+	{ uint32_t mx = 0; for (uint32_t r = tid; r < R; r += nt) { uint32_t n = ws.rd_len[r]; if (n > (uint32_t)K && n - K + 1 > mx) { mx = n - K + 1; } } if (mx) { lb2_max32(&sh->maxnk, mx); } }
 	uint32_t kcum = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { uint32_t n = ws.rd_len[r]; return (n > (uint32_t)K) ? (n - K + 1) : 0; },
 	                              [&](uint32_t r, uint32_t v) { ws.rd_kbase[r] = v; });
 	if (tid == 0) {
@@ -368,44 +384,64 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		ws.rd_kbase[R] = cum;
 		sh->n_used = 0; sh->err = 0; sh->n_spec = 0; sh->flag_a = 0;
 		sh->K = K; sh->nw = nw;
-		if (cum + L + 2 > C->max_inst) { sh->err |= 1u << LB2_D_READS; }
+		// occurrence array: offset-major (coalesced stores) when it fits, read-major otherwise
+		const uint32_t Rs = (R + 31u) & ~31u;
+		bool transposed = (uint64_t)sh->maxnk * Rs + L + 2 <= (uint64_t)C->max_inst;
+#ifdef LB2_HOSTSIM
+		if (getenv("LB2_SIM_COMPACT")) { transposed = false; }
+#endif
+		if (transposed) { sh->inst_stride = Rs; sh->inst_ref = sh->maxnk * Rs; }
+		else { sh->inst_stride = 0; sh->inst_ref = cum; if (cum + L + 2 > C->max_inst) { sh->err |= 1u << LB2_D_READS; } }
 	}
 	for (uint32_t i = tid; i < LB2_MAX_REF; i += nt) { ws.refnode[i] = LB2_NIL; }
 	for (uint32_t i = tid; i < TS; i += nt) { W.t_key[i] = 0; }
-	for (uint32_t i = tid; i < TS * 4; i += nt) { ws.g_occ[i] = 0; }      // g_occ, g_cnt, g_em are contiguous
+	for (uint32_t i = tid; i < TS / 2; i += nt) { ((uint32_t *)W.t_id)[i] = 0; }
+	for (uint32_t i = tid; i < TS * 2; i += nt) { ws.g_cnt[i] = 0; }
 	lb2_sync();
 	if (sh->err) { return; }
+	const uint32_t istr = sh->inst_stride ? sh->inst_stride : 1u;
 	const uint32_t nref_pairs = (L > (uint32_t)K) ? (L - K) : 0;
 	const uint32_t nchunks = (nref_pairs + 63) / 64;
 	for (uint32_t it = tid; it < R + nchunks; it += nt) {
 		if (it < R) {
 			uint32_t n = ws.rd_len[it];
 			if (n > (uint32_t)K) {
-				if (nw == 1) { lb2_walk<1>(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
-				else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
-				else { lb2_walk<LB2_MAXW>(W, ws.rd_start[it], n, 0, n - K, ws.rd_kbase[it], false, ws.rd_info[it] & 3u, K, nw); }
+				const uint32_t ib = sh->inst_stride ? it : ws.rd_kbase[it];
+				if (nw == 1) { lb2_walk<1>(W, ws.rd_start[it], n, 0, n - K, ib, istr, false, ws.rd_info[it] & 3u, K, nw); }
+				else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[it], n, 0, n - K, ib, istr, false, ws.rd_info[it] & 3u, K, nw); }
+				else { lb2_walk<LB2_MAXW>(W, ws.rd_start[it], n, 0, n - K, ib, istr, false, ws.rd_info[it] & 3u, K, nw); }
 			}
 		} else {
 			uint32_t c = it - R, ob = c * 64, oe = ob + 64; if (oe > nref_pairs) { oe = nref_pairs; }
-			if (nw == 1) { lb2_walk<1>(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw); }
-			else if (nw == 2) { lb2_walk<2>(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw); }
-			else { lb2_walk<LB2_MAXW>(W, sh->ref_g, L, ob, oe, ws.rd_kbase[R], true, 0, K, nw); }
+			if (nw == 1) { lb2_walk<1>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
+			else if (nw == 2) { lb2_walk<2>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
+			else { lb2_walk<LB2_MAXW>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
 		}
 	}
 	lb2_sync();
 	lb2_mark(W, LB2_PH_WALK);
 	if (sh->err) { return; }
-	// ---- compaction: order used slots by first occurrence = insertion order of the reference map
+	// ---- compaction: dense ids in order of first occurrence = insertion order of the reference map.  The first
+	//      occurrences are distinct staged base indices, so the rank of a node is the number of set bits below its
+	//      index in a bitmap over the staged bases (one popcount scan instead of a sort).
 	const uint32_t n = sh->n_used;
-	uint32_t n2 = 1; while (n2 < n) { n2 <<= 1; }
-	for (uint32_t j = tid; j < n2; j += nt) {
-		if (j < n) { uint32_t s = ws.used[j]; ws.sortk[j] = ((uint64_t)(0xFFFFFFFFu - ws.g_occ[s]) << 32) | s; }
-		else { ws.sortk[j] = ~0ull; }
+	{
+		uint32_t *bm = (uint32_t *)ws.sortk; const uint32_t nwords = (sh->total_bp >> 5) + 2; uint32_t *pref = bm + nwords;
+		for (uint32_t i = tid; i < nwords; i += nt) { bm[i] = 0; }
+		lb2_sync();
+		for (uint32_t j = tid; j < n; j += nt) { const uint32_t g = (W.t_key[ws.used[j]] & 0x1FFFFFu) >> 1; lb2g_red_or(&bm[g >> 5], 1u << (g & 31)); }
+		lb2_sync();
+		lb2_excl_scan(W, nwords, [&](uint32_t i) -> uint32_t { return (uint32_t)lb2_popc32(bm[i]); }, [&](uint32_t i, uint32_t v) { pref[i] = v; });
+		for (uint32_t j = tid; j < n; j += nt) {
+			const uint32_t s = ws.used[j]; const uint32_t g = (W.t_key[s] & 0x1FFFFFu) >> 1;
+			ws.b_row[pref[g >> 5] + (uint32_t)lb2_popc32(bm[g >> 5] & ((1u << (g & 31)) - 1u))] = s;      // b_row is free until lb2_order_and_pack
+		}
+		lb2_sync();
+		for (uint32_t j = tid; j < n; j += nt) { const uint32_t s = ws.b_row[j]; ws.used[j] = s; ws.g_em[j] = (((const uint32_t *)W.t_id)[s >> 1] >> ((s & 1u) << 4)) & 0xFFFFu; }   // used := dense id -> slot
+		lb2_sync();
+		for (uint32_t j = tid; j < n; j += nt) { W.t_id[ws.used[j]] = (uint16_t)j; }      // slot -> dense id (the mask bits were saved above)
+		lb2_sync();
 	}
-	lb2_sync();
-	lb2_sort64(ws.sortk, n2);
-	for (uint32_t j = tid; j < n; j += nt) { uint32_t s = (uint32_t)ws.sortk[j]; W.t_id[s] = (uint16_t)j; ws.used[j] = s; }   // slot -> dense id, used := dense id -> slot
-	lb2_sync();
 	for (uint32_t j = tid; j < n; j += nt) {
 		uint32_t s = ws.used[j];
 		uint32_t rep = W.t_key[s] & 0x1FFFFFu;
@@ -415,7 +451,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		uint32_t ct = ws.g_cnt[s * 2], cn = ws.g_cnt[s * 2 + 1];
 		uint32_t v[4] = { ct & 0xFFFFu, ct >> 16, cn & 0xFFFFu, cn >> 16 }, tot = 0;
 		for (int c = 0; c < 4; ++c) { ws.b_cnt[j * 4 + c] = v[c]; tot += v[c]; }
-		uint32_t em = ws.g_em[s];
+		uint32_t em = ws.g_em[j];
 		ws.b_stT[j] = ((em & (LB2_EM_NORMAL | LB2_EM_TUMOR)) == LB2_EM_TUMOR) ? 1u : 0u;   // cov_status 'T': tumour-qualified, never normal
 		ws.b_mincovqv[j] = (int32_t)tot;
 		ws.b_flags[j] = 0; ws.b_ne[j] = 0;
@@ -432,7 +468,11 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	if (sh->has_pairs) {
 		const uint32_t total = ws.rd_kbase[R];
 		uint32_t t2 = 1; while (t2 < total) { t2 <<= 1; }
-		for (uint32_t x = tid; x < t2; x += nt) { ws.sortk[x] = (x < total) ? (((uint64_t)W.t_id[ws.inst[x] & 0x3FFFFFFFu] << 32) | x) : ~0ull; }
+		for (uint32_t x = total + tid; x < t2; x += nt) { ws.sortk[x] = ~0ull; }
+		for (uint32_t r = tid; r < R; r += nt) {        // x = read-major occurrence number (the replay needs read order)
+			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
+			for (uint32_t o = 0; o < nk; ++o) { ws.sortk[kb + o] = ((uint64_t)W.t_id[ws.inst[ib + o * istr] & 0x3FFFFFFFu] << 32) | (kb + o); }
+		}
 		lb2_sync();
 		lb2_sort64(ws.sortk, t2);
 		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
@@ -464,7 +504,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					uint32_t cnt_other = (mate == 1) ? n2_ : n1;
 					bool ovl = false;
 					if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
-					if (ovl) { ws.inst[s_] |= 0x40000000u; ws.b_cnt[j * 4 + cls] -= 1; }
+					if (ovl) { ws.inst[(sh->inst_stride ? r : ws.rd_kbase[r]) + p * istr] |= 0x40000000u; ws.b_cnt[j * 4 + cls] -= 1; }
 					uint32_t last = ws.rd_len[r] - (uint32_t)K;
 					uint32_t pushes = (p == 0 || p == last) ? 1u : 2u;
 					for (uint32_t q = 0; q < pushes; ++q) { if (mate == 1) { L1[n1++] = name; } else { *(L2top - n2_) = name; ++n2_; } }
@@ -485,12 +525,12 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			lb2_sync();
 			for (uint32_t r = tid; r < R; r += nt) {
 				uint32_t len = ws.rd_len[r]; if (len <= (uint32_t)K) { continue; }
-				uint32_t g0 = ws.rd_start[r]; uint32_t cls = ws.rd_info[r] & 3u; uint32_t kb = ws.rd_kbase[r];
+				uint32_t g0 = ws.rd_start[r]; uint32_t cls = ws.rd_info[r] & 3u; uint32_t kb = sh->inst_stride ? r : ws.rd_kbase[r];
 				for (uint32_t q = 0; q < len; ++q) {
 					if (!lb2_getbit(W.lowq, g0 + q)) { continue; }
 					uint32_t p0 = (q + 1 > (uint32_t)K) ? (q + 1 - K) : 0, p1 = (q < len - K) ? q : (len - K);
 					for (uint32_t p = p0; p <= p1; ++p) {
-						uint32_t iw = ws.inst[kb + p];
+						uint32_t iw = ws.inst[kb + p * istr];
 						if (iw & 0x40000000u) { continue; }               // suppressed (overlapping mate)
 						uint32_t id = W.t_id[iw & 0x3FFFFFFFu];
 						uint32_t i = (iw >> 31) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
@@ -528,7 +568,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	// ---- edges of the survivors: every edge type (start orientation, appended base) names one neighbour
 	for (uint32_t j = tid; j < n; j += nt) {
 		if (ws.b_flags[j] & LB2_NF_DEAD) { continue; }
-		uint32_t s = ws.used[j]; uint32_t em = ws.g_em[s] & 0xFFu;
+		uint32_t em = ws.g_em[j] & 0xFFu;
 		lb2_kmer C0; lb2_rep_kmer(W, ws.b_rep[j], K, C0);
 		lb2_kmer C1; lb2_revcomp(C0, K, C1);
 		int ne = 0, nF = 0, nR = 0;
@@ -556,12 +596,12 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		for (uint32_t j = tid; j < n; j += nt) { if (ws.b_flags[j] & 0x20) { W.t_id[ws.used[j]] |= LB2_ID_BRANCH; } }
 		lb2_sync();
 		for (uint32_t it = tid; it < R + 1; it += nt) {
-			uint32_t g0, np, kb;
-			if (it < R) { uint32_t n_ = ws.rd_len[it]; if (n_ <= (uint32_t)K) { continue; } g0 = ws.rd_start[it]; np = n_ - K; kb = ws.rd_kbase[it]; }
-			else { g0 = sh->ref_g; np = nref_pairs; kb = ws.rd_kbase[R]; }
-			uint32_t iu = ws.inst[kb];
+			uint32_t g0, np, kb, ks, st;      // kb: occurrence number (first-seen stamps), ks/st: where the occurrences are stored
+			if (it < R) { uint32_t n_ = ws.rd_len[it]; if (n_ <= (uint32_t)K) { continue; } g0 = ws.rd_start[it]; np = n_ - K; kb = ws.rd_kbase[it]; ks = sh->inst_stride ? it : kb; st = istr; }
+			else { g0 = sh->ref_g; np = nref_pairs; kb = ws.rd_kbase[R]; ks = sh->inst_ref; st = 1u; }
+			uint32_t iu = ws.inst[ks];
 			for (uint32_t o = 0; o < np; ++o) {
-				uint32_t iv = ws.inst[kb + o + 1];
+				uint32_t iv = ws.inst[ks + (o + 1) * st];
 				uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
 				if (W.t_id[su] & LB2_ID_BRANCH) {
 					uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);

@@ -29,14 +29,21 @@ lb2_window_kernel(const lb2_launch *Lp)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ uint32_t s_next;
-	lb2_win W;
-	W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O; W.escal = (Lp->win_list != nullptr);
-	lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws); W.ws0 = W.ws;
-	W.sh = (lb2_sh *)smem;
-	W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
-	W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);
-	W.lowq = W.bits + (Lp->C.max_bp / 16 + 4);
-	W.treg = smem + ((lb2_smem_fixed(Lp->C.max_bp) + 15) & ~(size_t)15);
+	// the window descriptor (some 150 pointers, identical for every lane) lives in SHARED memory: as a kernel-local
+	// struct handed by reference to the pipeline's functions it sat in per-thread local memory, which with three 72 KB
+	// CTAs per SM has next to no L1 behind it -- every pointer fetch was an L2 round trip
+	__shared__ lb2_win sW;
+	lb2_win &W = sW;
+	if (threadIdx.x == 0) {
+		W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O; W.escal = (Lp->win_list != nullptr);
+		lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws); W.ws0 = W.ws;
+		W.sh = (lb2_sh *)smem;
+		W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
+		W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);
+		W.lowq = W.bits + (Lp->C.max_bp / 16 + 4);
+		W.treg = smem + ((lb2_smem_fixed(Lp->C.max_bp) + 15) & ~(size_t)15);
+	}
+	__syncthreads();
 	const uint32_t nwin = Lp->win_list ? *Lp->n_list : Lp->B.n_windows;
 	while (true) {
 		if (threadIdx.x == 0) { s_next = atomicAdd(Lp->counter, 1u); }

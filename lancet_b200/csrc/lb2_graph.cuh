@@ -376,21 +376,24 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 	size_t rows_bytes = 0;
 	{
 		size_t off = 0;
-#define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; ws.field = (type *)(G + off); off += sizeof(type) * (size_t)(count); } while (0)
+#define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; if (tid == 0) { ws.field = (type *)(G + off); } off += sizeof(type) * (size_t)(count); } while (0)
 		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint16_t, bcap);
 		LB2_GT(d_cov, float, NT * 4); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8);
 		LB2_GT(d_edge, lb2_edge, NT * LB2_EINL); LB2_GT(e_pool, lb2_edge, LB2_EOV_BLOCKS * LB2_ECAP);
 		LB2_GT(d_len, uint16_t, NT); LB2_GT(d_stn, uint16_t, NT); LB2_GT(d_stT, uint16_t, NT); LB2_GT(d_comp, int16_t, NT);
 		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT); LB2_GT(d_eov, uint8_t, NT);
 #undef LB2_GT
-		ws.chain = ws.stack; rows_bytes = (off + 15) & ~(size_t)15;
+		if (tid == 0) { ws.chain = ws.stack; } rows_bytes = (off + 15) & ~(size_t)15;
 	}
 	// scratch of the graph stage in the (now dead) packed-read words: list index of every row, then the parallel
 	// compaction's words.  The emulation arrays: three u16[n] here, the rest over the graph region; when either does not
 	// fit, all of them live in the workspace slab instead.
 	const size_t bits_bytes = ((size_t)W.C->max_bp / 16 + 4) * 4;
-	ws.d_pos = (uint16_t *)W.bits; ws.px = (uint32_t *)((uint8_t *)W.bits + (((size_t)NT * 2 + 15) & ~(size_t)15));
-	ws.px_words = (bits_bytes > (((size_t)NT * 2 + 15) & ~(size_t)15)) ? (uint32_t)((bits_bytes - (((size_t)NT * 2 + 15) & ~(size_t)15)) / 4) : 0u;
+	if (tid == 0) {
+		ws.d_pos = (uint16_t *)W.bits; ws.px = (uint32_t *)((uint8_t *)W.bits + (((size_t)NT * 2 + 15) & ~(size_t)15));
+		ws.px_words = (bits_bytes > (((size_t)NT * 2 + 15) & ~(size_t)15)) ? (uint32_t)((bits_bytes - (((size_t)NT * 2 + 15) & ~(size_t)15)) / 4) : 0u;
+	}
+	lb2_sync();
 	const size_t n6 = ((size_t)n * 6 + 15) & ~(size_t)15;
 	if (Bfinal == 0 || n >= 0x7FF0u || NT > LB2_MAX_ROWS || rows_bytes > Gbytes || (size_t)NT * 2 + 16 > bits_bytes || n > W.C->max_nodes) { if (tid == 0) { sh->err |= 1u << LB2_D_SMEM; } lb2_sync(); return; }
 	uint16_t *tm, *tm2, *bk, *nx, *S, *cm; uint32_t *head;

@@ -13,7 +13,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 #define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
 	const size_t MN = (size_t)c.max_nodes + 16, MR = (size_t)c.max_reads + 2;
 	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
-	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(g_occ, uint32_t, c.table_slots); LB2_TAKE(g_cnt, uint32_t, (size_t)c.table_slots * 2); LB2_TAKE(g_em, uint32_t, c.table_slots); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
+	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(g_cnt, uint32_t, (size_t)c.table_slots * 2); LB2_TAKE(g_em, uint32_t, c.table_slots); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
 	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR);
 	LB2_TAKE(b_rep, uint32_t, MN); LB2_TAKE(b_hash, uint64_t, MN); LB2_TAKE(b_cnt, uint32_t, MN * 4); LB2_TAKE(b_mincovqv, int32_t, MN);
@@ -67,10 +67,11 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		uint32_t slot = LB2_NIL;
 		if (W.escal && W.O->big_count) { slot = lb2g_add32(W.O->big_count, 1u); if (slot >= W.O->big_cap) { slot = LB2_NIL; } W.O->big_slot[w] = slot; }
 		sh->big = slot;
+		// (the descriptor is shared by the CTA: one lane writes it, everybody reads it after the barrier)
+		if (slot != LB2_NIL) { W.ovar = W.O->big_variants + (size_t)slot * W.O->big_max_var; W.ostr = W.O->big_strings + (size_t)slot * W.O->big_str_bytes; W.ovar_cap = W.O->big_max_var; W.ostr_cap = W.O->big_str_bytes; }
+		else { W.ovar = W.O->variants + (size_t)w * W.C->max_var; W.ostr = W.O->strings + (size_t)w * W.C->str_bytes; W.ovar_cap = W.C->max_var; W.ostr_cap = W.C->str_bytes; }
 	}
 	lb2_sync();
-	if (sh->big != LB2_NIL) { W.ovar = W.O->big_variants + (size_t)sh->big * W.O->big_max_var; W.ostr = W.O->big_strings + (size_t)sh->big * W.O->big_str_bytes; W.ovar_cap = W.O->big_max_var; W.ostr_cap = W.O->big_str_bytes; }
-	else { W.ovar = W.O->variants + (size_t)w * W.C->max_var; W.ostr = W.O->strings + (size_t)w * W.C->str_bytes; W.ovar_cap = W.C->max_var; W.ostr_cap = W.C->str_bytes; }
 	lb2_stage_window(W, w);
 	lb2_mark(W, LB2_PH_STAGE);
 	if (sh->status == LB2_WIN_OK) {
@@ -91,7 +92,9 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		for (int k = P->min_k; k <= P->max_k; k += 2) {
 			// isRepeat(rawseq,k) || isAlmostRepeat(rawseq,k,MAX_MISMATCH)  (src/Microassembler.cc:118-131)
 			if ((uint32_t)k <= sh->ref_emax || (uint32_t)k + 1 <= sh->ref_wmax) { continue; }
-			W.ws = W.ws0;                         // row-space pointers go back to their global homes
+			lb2_sync();
+			if (tid == 0) { W.ws = W.ws0; }       // row-space pointers go back to their global homes
+			lb2_sync();
 			lb2_build_graph(W, k);
 			if (tid == 0) { sh->n_k_tried += 1; sh->final_k = (uint32_t)k; }
 			lb2_sync();

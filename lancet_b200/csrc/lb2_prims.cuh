@@ -32,6 +32,7 @@ static inline uint32_t lb2_lds(const uint32_t *p) { return *p; }
 static inline int lb2_ctz64(uint64_t x) { return __builtin_ctzll(x); }
 static inline int lb2_clz32(uint32_t x) { return __builtin_clz(x); }
 static inline int lb2_ctz32(uint32_t x) { return __builtin_ctz(x); }
+static inline int lb2_popc32(uint32_t x) { return __builtin_popcount(x); }
 static inline unsigned long long lb2_clock() { return 0; }
 // CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
 static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) { (void)sc; *total = v; return 0; }
@@ -63,6 +64,7 @@ LB2_DEV uint32_t lb2g_min32(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }
 LB2_DEV int lb2_ctz32(uint32_t x) { return __ffs((int)x) - 1; }
+LB2_DEV int lb2_popc32(uint32_t x) { return __popc(x); }
 LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
 // CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
 LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {

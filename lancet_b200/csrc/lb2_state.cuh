@@ -47,7 +47,7 @@ struct lb2_trans {                // Transcript_t (reference src/Transcript.hh:3
 struct lb2_ws {
 	// --- build stage ---
 	uint32_t *used; uint64_t *sortk; uint32_t *inst; uint32_t *mates; uint32_t *bseq;
-	uint32_t *g_occ; uint32_t *g_cnt; uint32_t *g_em;   // per-slot accumulators of the build (fed by fire-and-forget reductions)
+	uint32_t *g_cnt; uint32_t *g_em;   // per-slot accumulators of the build (fed by fire-and-forget reductions)
 	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
 	lb2_bedge *b_edge; uint32_t *b_row;
 	// --- reads ---
@@ -95,6 +95,7 @@ struct lb2_sh {
 	uint32_t n_var, str_used, n_k_tried, final_k, last_nodes;
 	int32_t  numcomp;
 	uint32_t stop_k; uint32_t n_dead; uint32_t big;
+	uint32_t maxnk, inst_stride, inst_ref;     // occurrence array layout of this (window,k): see lb2_build.cuh
 	unsigned long long prof[24]; unsigned long long t_last;
 	uint32_t scan[520];           // block-scan partials (<= 512 lanes)
 };
