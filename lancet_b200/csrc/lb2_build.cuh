@@ -266,7 +266,7 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
 	bool fless = lb2_less<NWT>(f, rc, nw);
 	uint32_t ori_u = fless ? 0u : 1u;
-	uint32_t su = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, K, nw, true);
+	uint32_t su = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fless, f, rc), lb2_pick<NWT>(fless, rc, f), ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
 	ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
 	if (isref) { ws.refnode[o_begin] = su; }
@@ -281,7 +281,7 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 		lb2_roll_fwd<NWT>(f, K, c); lb2_roll_rc<NWT>(rc, K, c);
 		fless = lb2_less<NWT>(f, rc, nw);
 		uint32_t ori_v = fless ? 0u : 1u;
-		uint32_t sv = lb2_find_or_insert<NWT>(W, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, K, nw, true);
+		uint32_t sv = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fless, f, rc), lb2_pick<NWT>(fless, rc, f), ((g0 + o + 1) << 1) | ori_v, K, nw, true);
 		if (sv == LB2_NIL) { return; }
 		ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
 		uint32_t emu = 1u << (ori_u * 4 + (uint32_t)c);            // u leaves in orientation ori_u appending c
@@ -332,34 +332,64 @@ LB2_DEV uint64_t lb2_rev2(uint64_t x) {
 	x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
 	return (x >> 32) | (x << 32);
 }
-LB2_DEV void lb2_revcomp(const lb2_kmer &f, int K, lb2_kmer &rc) {
+template <int NWT = LB2_MAXW> LB2_DEV void lb2_revcomp(const lb2_kmer &f, int K, lb2_kmer &rc) {
 	const int nw = lb2_nw(K);
-	uint64_t t[LB2_MAXW];
+	uint64_t t[NWT];
 	// reversed words of the complement, as if the k-mer filled nw*32 bases; word order reversed within the nw words
+	// (all indexing is static after unrolling: the words stay in registers)
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
+	for (int j = 0; j < NWT; ++j) {
 		uint64_t v = 0;
 #pragma unroll
-		for (int s = 0; s < LB2_MAXW; ++s) { if (s == nw - 1 - j) { v = lb2_rev2(~f.w[s]); } }
+		for (int s = 0; s < NWT; ++s) { if (s == nw - 1 - j) { v = lb2_rev2(~f.w[s]); } }
 		t[j] = (j < nw) ? v : 0;
 	}
 	// the (nw*32 - K) pad bases now sit at the low end: shift right by 2*pad bits
 	const int sh = (nw * 32 - K) * 2;
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
-		uint64_t hi = (j + 1 < LB2_MAXW) ? t[(j + 1 < LB2_MAXW) ? j + 1 : j] : 0;
+	for (int j = 0; j < NWT; ++j) {
+		uint64_t hi = (j + 1 < NWT) ? t[(j + 1 < NWT) ? j + 1 : j] : 0;
 		rc.w[j] = sh ? ((t[j] >> sh) | (hi << (64 - sh))) : t[j];
 	}
-	lb2_mask_top(rc, K);
+	lb2_mask_top<NWT>(rc, K);
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) { if (j >= nw) { rc.w[j] = 0; } }
+	for (int j = 0; j < LB2_MAXW; ++j) { if (j >= nw || j >= NWT) { rc.w[j] = 0; } }
 }
 // canonical k-mer of a dense node (from its representative occurrence)
-LB2_DEV void lb2_rep_kmer(lb2_win &W, uint32_t rep, int K, lb2_kmer &km) {
-	lb2_extract(W.bits, rep >> 1, K, km);
-	if (rep & 1) { lb2_kmer t; lb2_revcomp(km, K, t); km = t; }
+template <int NWT = LB2_MAXW> LB2_DEV void lb2_rep_kmer(lb2_win &W, uint32_t rep, int K, lb2_kmer &km) {
+	lb2_extract<NWT>(W.bits, rep >> 1, K, km);
+#pragma unroll
+	for (int j = NWT; j < LB2_MAXW; ++j) { km.w[j] = 0; }
+	if (rep & 1) { lb2_kmer t; lb2_revcomp<NWT>(km, K, t); km = lb2_pick<NWT>(true, t, t); }
 }
-LB2_DEV void lb2_shift_append(lb2_kmer &k, int K, int c) { lb2_roll_fwd(k, K, c); }
+
+// edges of one surviving node: every edge type (start orientation, appended base) names one neighbour
+template <int NWT> LB2_DEV void lb2_node_edges(lb2_win &W, uint32_t j, int K, int nw)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	uint32_t em = ws.g_em[j] & 0xFFu;
+	lb2_kmer C0; lb2_rep_kmer<NWT>(W, ws.b_rep[j], K, C0);
+	lb2_kmer C1; lb2_revcomp<NWT>(C0, K, C1);
+	int ne = 0, nF = 0, nR = 0;
+	for (int t = 0; t < 8; ++t) {
+		if (!(em & (1u << t))) { continue; }
+		int o = t >> 2, b = t & 3;
+		lb2_kmer V = lb2_pick<NWT>(o != 0, C1, C0); lb2_roll_fwd<NWT>(V, K, b);
+		lb2_kmer Vr; lb2_revcomp<NWT>(V, K, Vr);
+		bool fl = lb2_less<NWT>(V, Vr, nw);
+		uint32_t ts = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fl, V, Vr), lb2_pick<NWT>(fl, Vr, V), 0, K, nw, false);
+		if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); break; }
+		uint32_t to = W.t_id[ts] & 0x7FFFu;
+		if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
+		lb2_bedge ed; ed.to = to; ed.dir = (uint32_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.type = (uint32_t)t;
+		ws.b_edge[(size_t)j * LB2_BECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
+	}
+	ws.b_ne[j] = (uint8_t)ne;
+	if (nF > 1 || nR > 1) {   // first-seen order matters only among edges leaving in the same orientation
+		ws.b_flags[j] |= 0x20; sh->flag_a = 1;      // slot's branch bit is set after the barrier (t_id is being read by other lanes)
+		for (int t = 0; t < 8; ++t) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
+	}
+}
 
 // ---------------------------------------------------------------------------------------------
 // build the graph for k-mer size K.  On return: dense nodes in insertion order (all nodes), the
@@ -446,8 +476,10 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		uint32_t s = ws.used[j];
 		uint32_t rep = W.t_key[s] & 0x1FFFFFu;
 		ws.b_rep[j] = rep;
-		lb2_kmer km; lb2_rep_kmer(W, rep, K, km);
-		ws.b_hash[j] = lb2_stdhash_kmer(km, K);
+		lb2_kmer km;
+		if (nw == 1) { lb2_rep_kmer<1>(W, rep, K, km); ws.b_hash[j] = lb2_stdhash_kmer<1>(km, K); }
+		else if (nw == 2) { lb2_rep_kmer<2>(W, rep, K, km); ws.b_hash[j] = lb2_stdhash_kmer<2>(km, K); }
+		else { lb2_rep_kmer<LB2_MAXW>(W, rep, K, km); ws.b_hash[j] = lb2_stdhash_kmer<LB2_MAXW>(km, K); }
 		uint32_t ct = ws.g_cnt[s * 2], cn = ws.g_cnt[s * 2 + 1];
 		uint32_t v[4] = { ct & 0xFFFFu, ct >> 16, cn & 0xFFFFu, cn >> 16 }, tot = 0;
 		for (int c = 0; c < 4; ++c) { ws.b_cnt[j * 4 + c] = v[c]; tot += v[c]; }
@@ -568,28 +600,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	// ---- edges of the survivors: every edge type (start orientation, appended base) names one neighbour
 	for (uint32_t j = tid; j < n; j += nt) {
 		if (ws.b_flags[j] & LB2_NF_DEAD) { continue; }
-		uint32_t em = ws.g_em[j] & 0xFFu;
-		lb2_kmer C0; lb2_rep_kmer(W, ws.b_rep[j], K, C0);
-		lb2_kmer C1; lb2_revcomp(C0, K, C1);
-		int ne = 0, nF = 0, nR = 0;
-		for (int t = 0; t < 8; ++t) {
-			if (!(em & (1u << t))) { continue; }
-			int o = t >> 2, b = t & 3;
-			lb2_kmer V = o ? C1 : C0; lb2_roll_fwd(V, K, b);
-			lb2_kmer Vr; lb2_revcomp(V, K, Vr);
-			bool fl = lb2_less(V, Vr, nw);
-			uint32_t ts = lb2_find_or_insert(W, fl ? V : Vr, fl ? Vr : V, 0, K, nw, false);
-			if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); break; }
-			uint32_t to = W.t_id[ts] & 0x7FFFu;
-			if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
-			lb2_bedge ed; ed.to = to; ed.dir = (uint32_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.type = (uint32_t)t;
-			ws.b_edge[(size_t)j * LB2_BECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
-		}
-		ws.b_ne[j] = (uint8_t)ne;
-		if (nF > 1 || nR > 1) {   // first-seen order matters only among edges leaving in the same orientation
-			ws.b_flags[j] |= 0x20; sh->flag_a = 1;      // slot's branch bit is set after the barrier (t_id is being read by other lanes)
-			for (int t = 0; t < 8; ++t) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
-		}
+		if (nw == 1) { lb2_node_edges<1>(W, j, K, nw); } else if (nw == 2) { lb2_node_edges<2>(W, j, K, nw); } else { lb2_node_edges<LB2_MAXW>(W, j, K, nw); }
 	}
 	lb2_sync();
 	if (sh->flag_a && !sh->err) {

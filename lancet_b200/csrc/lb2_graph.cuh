@@ -676,10 +676,8 @@ LB2_DEV uint32_t lb2_compress_dir(lb2_win &W, uint32_t node, int dir, uint32_t *
 		chain[nchain++] = buddy | (flip << 31);
 		const int amerlen = (int)curlen - K + 1, bmerlen = (int)LEN[buddy] - K + 1;
 		// same expression order as src/Graph.cc:2631-2636
-		c0 = ((c0 * amerlen) + (COV[buddy * 4 + 0] * bmerlen)) / (amerlen + bmerlen);
-		c1 = ((c1 * amerlen) + (COV[buddy * 4 + 1] * bmerlen)) / (amerlen + bmerlen);
-		c2 = ((c2 * amerlen) + (COV[buddy * 4 + 2] * bmerlen)) / (amerlen + bmerlen);
-		c3 = ((c3 * amerlen) + (COV[buddy * 4 + 3] * bmerlen)) / (amerlen + bmerlen);
+		c0 = lb2_wavg(c0, amerlen, COV[buddy * 4 + 0], bmerlen); c1 = lb2_wavg(c1, amerlen, COV[buddy * 4 + 1], bmerlen);
+		c2 = lb2_wavg(c2, amerlen, COV[buddy * 4 + 2], bmerlen); c3 = lb2_wavg(c3, amerlen, COV[buddy * 4 + 3], bmerlen);
 		curlen += (uint32_t)bmerlen; stn += STN[buddy]; stt += STT[buddy];
 		FL[buddy] |= LB2_NF_DEAD;
 		last = buddy; last_buid = buid; last_edir = edir;
@@ -953,10 +951,8 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 		for (uint32_t c = 0; c < jb.nAll; ++c) {
 			const uint32_t b = chain[c] & 0x7FFFFFFFu;
 			const int amerlen = (int)curlen - K + 1, bmerlen = (int)ws.d_len[b] - K + 1;
-			c0 = ((c0 * amerlen) + (ws.d_cov[b * 4 + 0] * bmerlen)) / (amerlen + bmerlen);
-			c1 = ((c1 * amerlen) + (ws.d_cov[b * 4 + 1] * bmerlen)) / (amerlen + bmerlen);
-			c2 = ((c2 * amerlen) + (ws.d_cov[b * 4 + 2] * bmerlen)) / (amerlen + bmerlen);
-			c3 = ((c3 * amerlen) + (ws.d_cov[b * 4 + 3] * bmerlen)) / (amerlen + bmerlen);
+			c0 = lb2_wavg(c0, amerlen, ws.d_cov[b * 4 + 0], bmerlen); c1 = lb2_wavg(c1, amerlen, ws.d_cov[b * 4 + 1], bmerlen);
+			c2 = lb2_wavg(c2, amerlen, ws.d_cov[b * 4 + 2], bmerlen); c3 = lb2_wavg(c3, amerlen, ws.d_cov[b * 4 + 3], bmerlen);
 			curlen += (uint32_t)bmerlen; stn += ws.d_stn[b]; stt += ws.d_stT[b];
 			if (c >= jb.nF) { leftlen += (uint32_t)bmerlen; }
 		}

@@ -49,6 +49,14 @@ template <int NWT = LB2_MAXW> LB2_DEV void lb2_extract(const uint32_t *bits, uin
 	lb2_mask_top<NWT>(out, K);
 }
 
+// word-wise select (a conditional on whole structs takes addresses and sends both k-mers to local memory)
+template <int NWT = LB2_MAXW> LB2_DEV lb2_kmer lb2_pick(bool first, const lb2_kmer &a, const lb2_kmer &b) {
+	lb2_kmer r;
+#pragma unroll
+	for (int j = 0; j < LB2_MAXW; ++j) { r.w[j] = (j < NWT) ? (first ? a.w[j] : b.w[j]) : 0ull; }
+	return r;
+}
+
 // (all indexing below is static after unrolling, so k-mers stay in registers)
 template <int NWT = LB2_MAXW> LB2_DEV void lb2_mask_top(lb2_kmer &k, int K) {
 	const int nw = lb2_nw(K), rem = (K & 31);
@@ -147,10 +155,10 @@ LB2_DEV uint64_t lb2_stdhash_bytes(const char *p, uint32_t len) {
 	return lb2_sh_final(s);
 }
 // hash of the ASCII spelling of a packed k-mer
-LB2_DEV uint64_t lb2_stdhash_kmer(const lb2_kmer &k, int K) {
+template <int NWT = LB2_MAXW> LB2_DEV uint64_t lb2_stdhash_kmer(const lb2_kmer &k, int K) {
 	lb2_stdhash s; lb2_sh_init(s, (uint32_t)K);
 #pragma unroll
-	for (int j = 0; j < LB2_MAXW; ++j) {
+	for (int j = 0; j < NWT; ++j) {
 		const uint64_t w = k.w[j];
 		for (int i = 0; i < 32 && j * 32 + i < K; ++i) { lb2_sh_byte(s, (unsigned char)lb2_base((int)((w >> (i << 1)) & 3))); }
 	}

@@ -266,6 +266,67 @@ LB2_DEV lb2_cov lb2_refcov_at(lb2_win &W, uint32_t pos, int sample) {   // Ref_t
 }
 LB2_DEV bool lb2_isACGT(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
+// ---------------------------------------------------------------------------------------------------
+// findTandems (src/util.cc:574-758) of the loaded path for EVERY query position at once, by all lanes.  The reference
+// walks i = 0..len-1 and, per unit length m, compares the block at i with the block at offsets[m][i % m] -- the last
+// position of that phase where the comparison failed ("flagged").  Between two flagged positions all blocks are equal,
+// so the block at i can just as well be compared with the block at i-m: every (i,m) is independent.  A flagged (i,m)
+// finds its run start by stepping back over unflagged positions, applies the reference's length / left-neighbour /
+// minimal-unit tests and becomes an event; the per-variant answer is a filter over the events in (i,m) order.
+// ---------------------------------------------------------------------------------------------------
+LB2_DEVNI void lb2_path_tandems(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const lb2_params *P = W.P; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t MAXU = (uint32_t)P->max_unit_len, slen = sh->plen;
+	uint8_t *JV = (uint8_t *)ws.px; char *sq = (char *)JV + (size_t)MAXU * slen;
+	const bool fits = MAXU >= 1 && MAXU <= 16 && slen > 0 && slen < 0xFFF0u && (size_t)MAXU * slen + slen + 32 <= (size_t)ws.px_words * 4;
+	if (tid == 0) { sh->n_tev = fits ? 0u : LB2_NIL; sh->tev_ovf = 0; }
+	if (!fits) { lb2_sync(); return; }
+	for (uint32_t i = tid; i < slen + 16; i += nt) { sq[i] = (i < slen) ? ws.pathseq[i] : (char)0; }
+	lb2_sync();
+	for (uint32_t idx = tid; idx < MAXU * slen; idx += nt) {
+		const uint32_t m = idx / slen + 1, i = idx % slen, ref = (i >= m) ? i - m : i;
+		uint32_t j = 0;
+		while (j < m && i + j < slen && sq[i + j] == sq[ref + j]) { ++j; }
+		JV[idx] = (uint8_t)(j | ((j != m || i + j + 1 == slen) ? 0x80u : 0u));
+	}
+	lb2_sync();
+	for (uint32_t idx = tid; idx < MAXU * slen; idx += nt) {
+		const uint32_t v = JV[idx]; if (!(v & 0x80u)) { continue; }
+		const uint32_t m = idx / slen + 1, i = idx % slen, j = v & 0x7Fu;
+		const uint8_t *row = JV + (size_t)(m - 1) * slen;
+		int q = (int)i - (int)m; while (q >= 0 && !(row[q] & 0x80u)) { q -= (int)m; }
+		const uint32_t offset = (q >= 0) ? (uint32_t)q : i % m, span = i - offset;
+		if (span / m < (uint32_t)P->min_report_units || span < (uint32_t)P->min_report_len) { continue; }
+		const char left = (offset >= 1) ? sq[offset - 1] : (char)0;
+		if (left == sq[offset + m - 1]) { continue; }
+		uint32_t ml = 1;
+		while (ml < m) {
+			const uint32_t units = (span + j) / ml; bool allmatch = true;
+			for (uint32_t index = 1; allmatch && index < units; ++index) {
+				for (uint32_t x = 0; x < ml; ++x) { if (sq[offset + x] != sq[offset + index * ml + x]) { allmatch = false; break; } }
+			}
+			if (!allmatch) { ++ml; } else { break; }
+		}
+		if (ml != m) { continue; }
+		const uint32_t slot = lb2_add32(&sh->n_tev, 1u);
+		if (slot < LB2_MAX_TEV) { lb2_tev e; e.i = (uint16_t)i; e.off = (uint16_t)offset; e.m = (uint8_t)m; e.j = (uint8_t)j; e.pad = 0; sh->tev[slot] = e; }
+		else { sh->tev_ovf = 1; }
+	}
+	lb2_sync();
+	if (tid == 0) {
+		if (sh->tev_ovf) { sh->n_tev = LB2_NIL; }
+		else {      // the reference meets the events in (i, m) order
+			for (uint32_t a = 1; a < sh->n_tev; ++a) {
+				lb2_tev x = sh->tev[a]; int b = (int)a - 1;
+				while (b >= 0 && (sh->tev[b].i > x.i || (sh->tev[b].i == x.i && sh->tev[b].m > x.m))) { sh->tev[b + 1] = sh->tev[b]; --b; }
+				sh->tev[b + 1] = x;
+			}
+		}
+	}
+	lb2_sync();
+}
+
 // column scan + stats + emission (lane 0).  aligned strings are in ws.aln_ref / ws.aln_path.
 LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
 {
@@ -359,7 +420,17 @@ LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
 			for (uint32_t k = 0; k < t.qry_len; ++k) { dst[t.ref_len + k] = poolQ[t.qry_off + k]; }
 			int LEN = 0; uint32_t ml = 0; bool movf = false;
 			const char *ps = ws.pathseq;
-			bool ans = lb2_find_tandems([&](uint32_t q) -> char { return ps[q]; }, plen, W.P, (int)t.start_pos, LEN, dst + need, ml, 64, movf);
+			bool ans = false;
+			if (sh->n_tev != LB2_NIL) {
+				const int pos = (int)t.start_pos, delta = W.P->dist_from_str;
+				for (uint32_t e = 0; e < sh->n_tev; ++e) {
+					const lb2_tev ev = sh->tev[e]; const int start = (int)ev.off, end = (int)ev.i + (int)ev.j;
+					if (pos >= start - delta && pos <= end + delta) {
+						ans = true; LEN = end - start;
+						for (uint32_t z = 0; z < ev.m; ++z) { if (ml < 64) { dst[need + ml++] = ps[ev.off + z]; } else { movf = true; } }
+					}
+				}
+			} else { ans = lb2_find_tandems([&](uint32_t q) -> char { return ps[q]; }, plen, W.P, (int)t.start_pos, LEN, dst + need, ml, 64, movf); }
 			if (movf) { sh->err |= 1u << LB2_D_MOTIF; return; }
 			v.motif_len = (uint16_t)(ans ? ml : 0); v.str_len = (uint16_t)(ans ? LEN : 0);
 			sh->str_used += need + v.motif_len;
@@ -397,6 +468,7 @@ LB2_DEVNI void lb2_process_path(lb2_win &W)
 		lb2_sync();
 	}
 	lb2_mark(W, LB2_PH_ALIGN);
+	lb2_path_tandems(W);
 	if (lb2_tid() == 0 && !sh->err) { lb2_scan_alignment(W); }
 	lb2_sync();
 	lb2_mark(W, LB2_PH_SCAN);

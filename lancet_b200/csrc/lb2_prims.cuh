@@ -33,6 +33,9 @@ static inline int lb2_ctz64(uint64_t x) { return __builtin_ctzll(x); }
 static inline int lb2_clz32(uint32_t x) { return __builtin_clz(x); }
 static inline int lb2_ctz32(uint32_t x) { return __builtin_ctz(x); }
 static inline int lb2_popc32(uint32_t x) { return __builtin_popcount(x); }
+// length-weighted coverage average of compressNode (src/Graph.cc:2631-2636): two products, a sum, a quotient, each rounded
+// (the reference is x86-64 without FMA; the device must not contract the sum of products)
+static inline float lb2_wavg(float a, int la, float b, int lb) { volatile float p = a * la; volatile float q = b * lb; volatile float sm = p + q; return sm / (la + lb); }
 static inline unsigned long long lb2_clock() { return 0; }
 // CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
 static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) { (void)sc; *total = v; return 0; }
@@ -65,6 +68,9 @@ LB2_DEV int lb2_ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
 LB2_DEV int lb2_clz32(uint32_t x) { return __clz((int)x); }
 LB2_DEV int lb2_ctz32(uint32_t x) { return __ffs((int)x) - 1; }
 LB2_DEV int lb2_popc32(uint32_t x) { return __popc(x); }
+// length-weighted coverage average of compressNode (src/Graph.cc:2631-2636): two products, a sum, a quotient, each rounded
+// (the reference is x86-64 without FMA; the device must not contract the sum of products)
+LB2_DEV float lb2_wavg(float a, int la, float b, int lb) { return __fdiv_rn(__fadd_rn(__fmul_rn(a, (float)la), __fmul_rn(b, (float)lb)), (float)(la + lb)); }
 LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
 // CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
 LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {

@@ -72,6 +72,10 @@ struct lb2_ws {
 
 struct lb2_sizes { size_t total; size_t off[64]; };
 
+// one qualifying tandem repeat of the current path (findTandems event: flagged position i, unit m, matched prefix j, run start off)
+struct lb2_tev { uint16_t i, off; uint8_t m, j; uint16_t pad; };
+#define LB2_MAX_TEV 48
+
 // shared (smem) scalars of one window
 struct lb2_sh {
 	// window
@@ -96,6 +100,7 @@ struct lb2_sh {
 	int32_t  numcomp;
 	uint32_t stop_k; uint32_t n_dead; uint32_t big;
 	uint32_t maxnk, inst_stride, inst_ref;     // occurrence array layout of this (window,k): see lb2_build.cuh
+	uint32_t n_tev, tev_ovf; lb2_tev tev[LB2_MAX_TEV];     // tandem repeats of the loaded path (n_tev = LB2_NIL: not computed, scan per variant)
 	unsigned long long prof[24]; unsigned long long t_last;
 	uint32_t scan[520];           // block-scan partials (<= 512 lanes)
 };
