@@ -52,22 +52,47 @@ LB2_DEV void lb2_fail(lb2_win &W, uint32_t status, uint32_t detail) {
 	if (lb2_cas32(&W.sh->status, LB2_WIN_OK, status) == LB2_WIN_OK) { W.sh->detail = detail; }
 }
 
+// ---- 16 read bases at a time (device: five aligned 32-bit loads per 16 bytes, SIMD-in-register classification) ----
+// 2-bit codes of four ASCII bases in the byte lanes of w -> 8 bits (A=0 C=1 G=2 T=3; other characters give garbage)
+LB2_DEV uint32_t lb2_codes4(uint32_t w) {
+	const uint32_t x = (w >> 1) & 0x03030303u, c = x ^ ((x >> 1) & 0x01010101u);
+	return (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
+}
+LB2_DEV uint32_t lb2_bytemask4(uint32_t m) { return (((m & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; }      // 0xFF/0x00 byte lanes -> 4 bits
+LB2_DEV uint32_t lb2_codes16(const char *s) {
+	uint32_t sw[4]; lb2_load16(s, sw);
+	return lb2_codes4(sw[0]) | (lb2_codes4(sw[1]) << 8) | (lb2_codes4(sw[2]) << 16) | (lb2_codes4(sw[3]) << 24);
+}
+LB2_DEV uint32_t lb2_low16(const char *q, uint32_t thr4) {       // bit i: quality byte i < threshold
+	uint32_t qw[4]; lb2_load16(q, qw);
+	return lb2_bytemask4(lb2_ltu4(qw[0], thr4)) | (lb2_bytemask4(lb2_ltu4(qw[1], thr4)) << 4) | (lb2_bytemask4(lb2_ltu4(qw[2], thr4)) << 8) | (lb2_bytemask4(lb2_ltu4(qw[3], thr4)) << 12);
+}
+LB2_DEV uint32_t lb2_nacgt16(const char *s) {                    // bit i: base i is not one of ACGT
+	uint32_t sw[4]; lb2_load16(s, sw); uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint32_t ok = lb2_eq4(sw[k], 0x41414141u) | lb2_eq4(sw[k], 0x43434343u) | lb2_eq4(sw[k], 0x47474747u) | lb2_eq4(sw[k], 0x54545454u);
+		r |= lb2_bytemask4(~ok) << (4 * k);
+	}
+	return r;
+}
+
 // 2-bit packed bases of the trimmed reads and of the window reference.  The packed bases' shared memory is lent to the
 // order emulation after every build (k-mer strings of the surviving nodes are copied out first), so the bases are
-// staged again before the build of a later k.
+// staged again before the build of a later k.  Eight lanes per read, one 16-base word each.
 LB2_DEVNI void lb2_stage_bits(lb2_win &W)
 {
 	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const uint32_t R = sh->R, L = sh->L; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
-	for (uint32_t r = tid; r < R; r += nt) {
-		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
+	for (uint32_t r = lb2_group(); r < R; r += lb2_ngroups()) {
+		const uint32_t n = ws.rd_len[r]; if (!n) { continue; }
 		const char *s = B->seq + B->base_off[widx[r]] + ws.rd_t5[r];
-		uint32_t g = ws.rd_start[r];
-		for (uint32_t b0 = 0; b0 < n; b0 += 16) {
-			uint32_t bw = 0, m = (n - b0 < 16) ? (n - b0) : 16;
-			for (uint32_t i = 0; i < m; ++i) { bw |= (uint32_t)lb2_code(s[b0 + i]) << (2 * i); }
-			W.bits[(g + b0) >> 4] = bw;
+		const uint32_t g = ws.rd_start[r];
+		for (uint32_t w = lb2_glane(); w * 16 < n; w += LB2_GS) {
+			uint32_t bw = lb2_codes16(s + w * 16); const uint32_t m = n - w * 16;
+			if (m < 16) { bw &= (1u << (2 * m)) - 1u; }
+			W.bits[(g >> 4) + w] = bw;
 		}
 	}
 	const uint32_t g = sh->ref_g;
@@ -87,19 +112,18 @@ LB2_DEVNI void lb2_stage_lowq(lb2_win &W)
 	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const uint32_t R = sh->R; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
-	const int qcall = W.P->min_qual_call;
+	const uint32_t qc = (uint32_t)W.P->min_qual_call & 0xFFu, qcall4 = qc * 0x01010101u;
 	for (uint32_t i = tid; i < (sh->total_bp >> 5) + 4; i += nt) { W.lowq[i] = 0; }
 	lb2_sync();
-	for (uint32_t r = tid; r < R; r += nt) {
-		uint32_t n = ws.rd_len[r]; if (!n) { continue; }
+	for (uint32_t r = lb2_group(); r < R; r += lb2_ngroups()) {
+		const uint32_t n = ws.rd_len[r]; if (!n) { continue; }
 		const char *q = B->qual + B->base_off[widx[r]] + ws.rd_t5[r];
-		uint32_t g = ws.rd_start[r], anylow = 0;      // reads start on 16-base boundaries: neighbours may share a mask word
-		for (uint32_t b0 = 0; b0 < n; b0 += 16) {
-			uint32_t lw = 0, m = (n - b0 < 16) ? (n - b0) : 16;
-			for (uint32_t i = 0; i < m; ++i) { if (q[b0 + i] < qcall) { lw |= 1u << i; } }
-			if (lw) { lb2_or32(&W.lowq[(g + b0) >> 5], lw << ((g + b0) & 31)); anylow = 1; }
+		const uint32_t g = ws.rd_start[r];      // reads start on 16-base boundaries: two words of a read share a mask word
+		for (uint32_t w = lb2_glane(); w * 16 < n; w += LB2_GS) {
+			uint32_t lw = lb2_low16(q + w * 16, qcall4); const uint32_t m = n - w * 16;
+			if (m < 16) { lw &= (1u << m) - 1u; }
+			if (lw) { lb2_or32(&W.lowq[(g + w * 16) >> 5], lw << ((g + w * 16) & 31)); sh->has_lowq = 1; }
 		}
-		if (anylow) { lb2_or32(&sh->has_lowq, 1u); }
 	}
 	if (tid == 0) { sh->lowq_live = 1; }
 	lb2_sync();
@@ -131,28 +155,47 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		if (lb2_code(c) < 0) { lb2_or32(&sh->flag_a, 1u); }
 	}
 	const uint32_t *widx = B->wr_idx + B->wr_off[w];
-	const int qtrim = W.P->min_qual_trim;
-	for (uint32_t r = tid; r < R; r += nt) {
-		uint32_t idx = widx[r];
-		uint64_t o0 = B->base_off[idx]; int len = (int)(B->base_off[idx + 1] - o0);
-		const char *s = B->seq + o0; const char *q = B->qual + o0;
-		uint8_t fl = B->flags[idx];
-		// Graph_t::trim (src/Graph.cc:355-384)
-		int t5 = 0, t3 = 0; bool junk = false;
-		while (t5 < len && (lb2_code(s[t5]) < 0 || q[t5] < qtrim)) { ++t5; }
-		if (t5 < len) {
-			while (t3 < len && (lb2_code(s[len - 1 - t3]) < 0 || q[len - 1 - t3] < qtrim)) { ++t3; }
-			for (int i = t5; i < len - t3; ++i) { if (lb2_code(s[i]) < 0) { junk = true; break; } }
-		} else { junk = true; }
-		int n = junk ? 0 : (len - t5 - t3);
-		if (n > 4095) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_READS); n = 0; }
-		ws.rd_len[r] = (uint32_t)n; ws.rd_t5[r] = (uint32_t)t5;
-		uint32_t cls = ((fl & LB2_READ_NORMAL) ? 2u : 0u) | ((fl & LB2_READ_REVERSE) ? 1u : 0u);
-		uint32_t mate = (fl >> LB2_READ_MATE_SHIFT) & 3u;
-		ws.rd_info[r] = cls | (mate << 2);
-		ws.rd_rank[r] = B->name_rank[idx];
-		if (!(fl & LB2_READ_UNMAPPED)) { lb2_or32(&sh->mapped, 1u); }
-		if (n) { lb2_add32(&sh->totalreadbp, (uint32_t)n); }
+	const uint32_t qt = (uint32_t)W.P->min_qual_trim & 0xFFu, qtrim4 = qt * 0x01010101u;
+	// Graph_t::trim (src/Graph.cc:355-384), eight lanes per read: a base is "good" when it is ACGT with quality >=
+	// MIN_QUAL_TRIM; trm5 = bases before the first good one, trm3 = bases after the last good one, junk = no good base
+	// or a non-ACGT base strictly between them.  (All lanes of a warp run the same number of rounds: the group
+	// reductions are warp shuffles.)
+	const uint32_t ng = lb2_ngroups(), grp = lb2_group(), gl = lb2_glane();
+	for (uint32_t r0 = 0; r0 < R; r0 += ng) {
+		const uint32_t r = r0 + grp; const bool act = r < R;
+		uint32_t idx = 0, len = 0; const char *s = nullptr, *q = nullptr;
+		if (act) { idx = widx[r]; const uint64_t o0 = B->base_off[idx]; len = (uint32_t)(B->base_off[idx + 1] - o0); s = B->seq + o0; q = B->qual + o0; }
+		const uint32_t nch = (len + 15u) >> 4;
+		uint32_t first = 0xFFFFFFFFu, last = 0, my_nac = 0, my_c = 0xFFFFFFFFu;      // last = index of the last good base + 1
+		for (uint32_t c = gl; c < nch; c += LB2_GS) {
+			const uint32_t m = len - c * 16, valid = (m < 16) ? ((1u << m) - 1u) : 0xFFFFu;
+			const uint32_t nac = lb2_nacgt16(s + c * 16) & valid, low = lb2_low16(q + c * 16, qtrim4) & valid;
+			const uint32_t good = valid & ~(nac | low);
+			if (good) { const uint32_t f = c * 16 + (uint32_t)lb2_ctz32(good), l = c * 16 + 32u - (uint32_t)lb2_clz32(good); if (f < first) { first = f; } if (l > last) { last = l; } }
+			my_nac = nac; my_c = c;
+		}
+		first = lb2_gmin(first); last = lb2_gmax(last);
+		uint32_t junk = (first == 0xFFFFFFFFu) ? 1u : 0u;
+		if (!junk) {      // a non-ACGT base inside (first, last-1)
+			for (uint32_t c = gl; c < nch; c += LB2_GS) {
+				const uint32_t m = len - c * 16, valid = (m < 16) ? ((1u << m) - 1u) : 0xFFFFu;
+				const uint32_t nac = (c == my_c) ? my_nac : (lb2_nacgt16(s + c * 16) & valid);      // (one chunk per lane: still in a register)
+				for (uint32_t x = nac; x; x &= x - 1) { const uint32_t p = c * 16 + (uint32_t)lb2_ctz32(x); if (p > first && p + 1 < last) { junk = 1; } }
+			}
+		}
+		junk = lb2_gor(junk);
+		if (act && gl == 0) {
+			const uint8_t fl = B->flags[idx];
+			int n = junk ? 0 : (int)(last - first); const uint32_t t5 = junk ? len : first;
+			if (n > 4095) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_READS); n = 0; }
+			ws.rd_len[r] = (uint32_t)n; ws.rd_t5[r] = t5;
+			uint32_t cls = ((fl & LB2_READ_NORMAL) ? 2u : 0u) | ((fl & LB2_READ_REVERSE) ? 1u : 0u);
+			uint32_t mate = (fl >> LB2_READ_MATE_SHIFT) & 3u;
+			ws.rd_info[r] = cls | (mate << 2);
+			ws.rd_rank[r] = B->name_rank[idx];
+			if (!(fl & LB2_READ_UNMAPPED)) { sh->mapped = 1; }
+			if (n) { lb2_add32(&sh->totalreadbp, (uint32_t)n); }
+		}
 	}
 	lb2_sync();
 	uint32_t cum_all = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { return (ws.rd_len[r] + 15u) & ~15u; }, [&](uint32_t r, uint32_t v) { ws.rd_start[r] = v; });
@@ -168,17 +211,24 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 	lb2_sync();
 	if (sh->status != LB2_WIN_OK) { return; }
 	{	// does any query name occur with both mate orders?  (otherwise hasOverlappingMate can never fire)
-		uint32_t r2 = 1; while (r2 < R) { r2 <<= 1; }
-		for (uint32_t r = tid; r < r2; r += nt) {
-			uint64_t k = ~0ull;
-			if (r < R) { uint32_t mate = (ws.rd_info[r] >> 2) & 3u; if (mate == 1 || mate == 2) { k = ((uint64_t)ws.rd_rank[r] << 2) | mate; } }
-			ws.sortk[r] = k;
-		}
+		// open-addressing set of name ranks in the (idle) table region, two mate-order bits per entry
+		uint32_t *hs = (uint32_t *)W.treg; const uint32_t TS = W.C->table_slots, hmask = TS - 1;
+		for (uint32_t i = tid; i < TS; i += nt) { hs[i] = 0xFFFFFFFFu; }
 		lb2_sync();
-		lb2_sort64(ws.sortk, r2);
-		for (uint32_t r = tid + 1; r < r2; r += nt) {
-			uint64_t a = ws.sortk[r - 1], b = ws.sortk[r];
-			if (b != ~0ull && (a >> 2) == (b >> 2) && (a & 3) != (b & 3)) { sh->has_pairs = 1; }
+		if (2 * R > TS) { if (tid == 0) { sh->has_pairs = 1; } }      // (would not fit: run the replay unconditionally, it is exact either way)
+		else {
+			for (uint32_t r = tid; r < R; r += nt) {
+				const uint32_t mate = (ws.rd_info[r] >> 2) & 3u; if (mate != 1 && mate != 2) { continue; }
+				const uint32_t rank = ws.rd_rank[r];
+				if (rank >= 0x3FFFFFFFu) { sh->has_pairs = 1; continue; }
+				uint32_t h = (rank * 2654435761u) & hmask;
+				for (uint32_t probes = 0; probes <= hmask; ++probes) {
+					uint32_t cur = lb2_ld32(&hs[h]);
+					if (cur == 0xFFFFFFFFu) { cur = lb2_cas32(&hs[h], 0xFFFFFFFFu, (rank << 2) | mate); if (cur == 0xFFFFFFFFu) { break; } }
+					if ((cur >> 2) == rank) { if ((cur & 3u) != mate) { sh->has_pairs = 1; } break; }
+					h = (h + 1) & hmask;
+				}
+			}
 		}
 		lb2_sync();
 	}

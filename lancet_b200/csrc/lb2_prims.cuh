@@ -41,6 +41,19 @@ static inline unsigned long long lb2_clock() { return 0; }
 static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) { (void)sc; *total = v; return 0; }
 // atomics on an address that may be shared OR global (scratch that falls back to the workspace slab)
 static inline uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
+// ---- sub-warp groups for the read staging (8 lanes per read on the device, 1 in the simulation) ----
+#define LB2_GS 1
+static inline unsigned lb2_glane() { return 0; }
+static inline unsigned lb2_group() { return 0; }
+static inline unsigned lb2_ngroups() { return 1; }
+static inline uint32_t lb2_gmin(uint32_t v) { return v; }
+static inline uint32_t lb2_gmax(uint32_t v) { return v; }
+static inline uint32_t lb2_gor(uint32_t v) { return v; }
+// 16 bytes from an arbitrarily aligned address (the device version reads whole aligned words around them)
+static inline void lb2_load16(const char *p, uint32_t o[4]) { memcpy(o, p, 16); }
+// per-byte compares: 0xFF in every byte lane where the predicate holds
+static inline uint32_t lb2_eq4(uint32_t w, uint32_t c4) { uint32_t r = 0; for (int b = 0; b < 4; ++b) { if (((w >> (8 * b)) & 0xFF) == ((c4 >> (8 * b)) & 0xFF)) { r |= 0xFFu << (8 * b); } } return r; }
+static inline uint32_t lb2_ltu4(uint32_t w, uint32_t c4) { uint32_t r = 0; for (int b = 0; b < 4; ++b) { if (((w >> (8 * b)) & 0xFF) < ((c4 >> (8 * b)) & 0xFF)) { r |= 0xFFu << (8 * b); } } return r; }
 #else
 #define LB2_DEV   __device__ __forceinline__
 #define LB2_DEVNI __device__ __noinline__
@@ -88,6 +101,22 @@ LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {
 }
 // atomics on an address that may be shared OR global (scratch that falls back to the workspace slab)
 LB2_DEV uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
+// ---- sub-warp groups for the read staging (8 lanes per read) ----
+#define LB2_GS 8
+LB2_DEV unsigned lb2_glane() { return threadIdx.x & 7u; }
+LB2_DEV unsigned lb2_group() { return threadIdx.x >> 3; }
+LB2_DEV unsigned lb2_ngroups() { return blockDim.x >> 3; }
+LB2_DEV uint32_t lb2_gmin(uint32_t v) { for (int o = 1; o < 8; o <<= 1) { uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = y < v ? y : v; } return v; }
+LB2_DEV uint32_t lb2_gmax(uint32_t v) { for (int o = 1; o < 8; o <<= 1) { uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = y > v ? y : v; } return v; }
+LB2_DEV uint32_t lb2_gor(uint32_t v) { for (int o = 1; o < 8; o <<= 1) { v |= __shfl_xor_sync(0xFFFFFFFFu, v, o); } return v; }
+// 16 bytes from an arbitrarily aligned address: five aligned words, funnel-shifted (reads up to 3 bytes before and 7 after)
+LB2_DEV void lb2_load16(const char *p, uint32_t o[4]) {
+	const uint32_t *a = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3); const uint32_t sh = (uint32_t)((uintptr_t)p & 3u) * 8u;
+	const uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = __ldg(a + 3), w4 = __ldg(a + 4);
+	o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+}
+LB2_DEV uint32_t lb2_eq4(uint32_t w, uint32_t c4) { return __vcmpeq4(w, c4); }
+LB2_DEV uint32_t lb2_ltu4(uint32_t w, uint32_t c4) { return __vcmpltu4(w, c4); }
 #endif
 
 #endif

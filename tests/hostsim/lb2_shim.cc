@@ -36,7 +36,8 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *b, lb2_result *res)
 	C.table_slots = 16384; C.max_nodes = 12000; C.max_reads = 8192; C.max_bp = (1 << 20) - 1024; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
 	C.queue_cap = 1 << 22; C.graph_bytes = 1 << 20; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = b->ref_off; B.ref_start = b->ref_start; B.wr_off = b->wr_off; B.wr_idx = b->wr_idx;
-	B.base_off = b->base_off; B.flags = b->flags; B.name_rank = b->name_rank; B.ref_seq = b->ref_seq; B.seq = b->seq; B.qual = b->qual;
+	B.base_off = b->base_off; B.flags = b->flags; B.name_rank = b->name_rank; B.ref_seq = b->ref_seq; std::vector<char> pseq(b->seq, b->seq + b->n_base_bytes), pqual(b->qual, b->qual + b->n_base_bytes); pseq.resize(pseq.size() + 64, 0); pqual.resize(pqual.size() + 64, 0);
+	B.seq = pseq.data(); B.qual = pqual.data();
 	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
 	lb2_dev_out O; memset(&O, 0, sizeof O); O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);
