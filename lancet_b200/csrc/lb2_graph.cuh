@@ -731,10 +731,11 @@ LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
 		uint32_t leftlen = 0;
 		for (uint32_t c = nF; c < nAll; ++c) { leftlen += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
 		jb.leftlen = leftlen;
-		uint32_t pos = leftlen + len0;
+		// (cpos is relative to the seed's left end: F entries start at leftlen + cpos, R entries at leftlen - cpos)
+		uint32_t pos = len0;
 		for (uint32_t c = 0; c < nF; ++c) { ws.cpos[cused + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
-		pos = leftlen;
-		for (uint32_t c = nF; c < nAll; ++c) { pos -= ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; ws.cpos[cused + c] = pos; }
+		pos = 0;
+		for (uint32_t c = nF; c < nAll; ++c) { pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; ws.cpos[cused + c] = pos; }
 		ws.d_mincov[p] = 10000000; ws.d_mincovqv[p] = 10000000;
 		jobs[njobs++] = jb; cused += nAll;
 	}
@@ -754,7 +755,8 @@ LB2_DEVNI void lb2_materialize(lb2_win &W) {
 			if (m == jb.nAll) { id = jb.node; flip = false; first = 0; count = jb.len0; dst = jb.leftlen; }
 			else {
 				uint32_t ce = ws.chain[jb.cbeg + m]; id = ce & 0x7FFFFFFFu; flip = (ce >> 31) != 0;
-				uint32_t bl = ws.d_len[id]; count = bl - K + 1; dst = ws.cpos[jb.cbeg + m];
+				uint32_t bl = ws.d_len[id]; count = bl - K + 1; const uint32_t rel = ws.cpos[jb.cbeg + m];
+				dst = (m < jb.nF) ? jb.leftlen + rel : jb.leftlen - rel;
 				first = (m < jb.nF) ? (uint32_t)K - 1 : 0;       // F: oriented[K-1..], R: frame[0..bl-K]
 			}
 			lb2_nview v; lb2_view(W, id, v);
@@ -943,27 +945,32 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 		}
 	}
 	lb2_sync();
-	// fold the float coverages in the reference's absorb order (src/Graph.cc:2631-2636), one lane per chain
-	for (uint32_t q = tid; q < njobs; q += nt) {
-		lb2_job jb = jobs[q]; const uint32_t node = jb.node; const uint32_t *chain = ws.chain + jb.cbeg;
-		float c0 = ws.d_cov[node * 4 + 0], c1 = ws.d_cov[node * 4 + 1], c2 = ws.d_cov[node * 4 + 2], c3 = ws.d_cov[node * 4 + 3];
-		uint32_t stn = ws.d_stn[node], stt = ws.d_stT[node], curlen = jb.len0, leftlen = 0;
-		for (uint32_t c = 0; c < jb.nAll; ++c) {
-			const uint32_t b = chain[c] & 0x7FFFFFFFu;
-			const int amerlen = (int)curlen - K + 1, bmerlen = (int)ws.d_len[b] - K + 1;
-			c0 = lb2_wavg(c0, amerlen, ws.d_cov[b * 4 + 0], bmerlen); c1 = lb2_wavg(c1, amerlen, ws.d_cov[b * 4 + 1], bmerlen);
-			c2 = lb2_wavg(c2, amerlen, ws.d_cov[b * 4 + 2], bmerlen); c3 = lb2_wavg(c3, amerlen, ws.d_cov[b * 4 + 3], bmerlen);
-			curlen += (uint32_t)bmerlen; stn += ws.d_stn[b]; stt += ws.d_stT[b];
-			if (c >= jb.nF) { leftlen += (uint32_t)bmerlen; }
+	// fold the float coverages in the reference's absorb order (src/Graph.cc:2631-2636): a serial recurrence per chain and
+	// channel (every step rounds), so one lane per (chain, channel); the integer bookkeeping rides along in every lane
+	for (uint32_t q = tid / LB2_FQ; q < njobs; q += nt / LB2_FQ) {
+		const lb2_job jb = jobs[q]; const uint32_t node = jb.node; const uint32_t *chain = ws.chain + jb.cbeg;
+		for (uint32_t ch = tid % LB2_FQ; ch < 4; ch += LB2_FQ) {
+			float cv = ws.d_cov[node * 4 + ch];
+			uint32_t stn = ws.d_stn[node], stt = ws.d_stT[node], curlen = jb.len0, leftlen = 0;
+			int amerlen = (int)jb.len0 - K + 1;
+			// one step ahead: the loads of the next entry do not depend on the recurrence
+			uint32_t b = jb.nAll ? (chain[0] & 0x7FFFFFFFu) : 0u;
+			int bmerlen = (int)ws.d_len[b] - K + 1; float bc = ws.d_cov[b * 4 + ch]; uint32_t bsn = ws.d_stn[b], bst = ws.d_stT[b];
+			for (uint32_t c = 0; c < jb.nAll; ++c) {
+				const int bm = bmerlen; const float bcv = bc; const uint32_t sn = bsn, st = bst;
+				if (c + 1 < jb.nAll) { b = chain[c + 1] & 0x7FFFFFFFu; bmerlen = (int)ws.d_len[b] - K + 1; bc = ws.d_cov[b * 4 + ch]; bsn = ws.d_stn[b]; bst = ws.d_stT[b]; }
+				cv = lb2_wavg(cv, amerlen, bcv, bm);
+				if (ch == 0) { ws.cpos[jb.cbeg + c] = (c < jb.nF) ? curlen : leftlen + (uint32_t)bm; }      // relative to the seed's left end, see lb2_materialize
+				amerlen += bm; curlen += (uint32_t)bm; stn += sn; stt += st;
+				if (c >= jb.nF) { leftlen += (uint32_t)bm; }
+			}
+			ws.d_cov[node * 4 + ch] = cv;
+			if (ch == 0) {
+				ws.d_stn[node] = (uint16_t)stn; ws.d_stT[node] = (uint16_t)stt;
+				ws.d_mincov[node] = 10000000; ws.d_mincovqv[node] = 10000000;
+				jobs[q].curlen = curlen; jobs[q].leftlen = leftlen;
+			}
 		}
-		ws.d_cov[node * 4 + 0] = c0; ws.d_cov[node * 4 + 1] = c1; ws.d_cov[node * 4 + 2] = c2; ws.d_cov[node * 4 + 3] = c3;
-		ws.d_stn[node] = (uint16_t)stn; ws.d_stT[node] = (uint16_t)stt;
-		uint32_t pos = leftlen + jb.len0;
-		for (uint32_t c = 0; c < jb.nF; ++c) { ws.cpos[jb.cbeg + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
-		pos = leftlen;
-		for (uint32_t c = jb.nF; c < jb.nAll; ++c) { pos -= ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; ws.cpos[jb.cbeg + c] = pos; }
-		ws.d_mincov[node] = 10000000; ws.d_mincovqv[node] = 10000000;
-		jobs[q].curlen = curlen; jobs[q].leftlen = leftlen;
 	}
 	lb2_sync();
 	if (tid == 0) {

@@ -32,9 +32,15 @@ LB2_DEV uint32_t lb2_mm16(const uint32_t *bits, uint32_t g0, uint32_t p, uint32_
 }
 
 // the sequence is ACGT only and 2-bit packed at base index g0 of `bits` (two readable words past the end).
-// One lane per diagonal walks only the MISMATCH positions q (ffs over 16 flags per XOR): with the previous
-// mismatches m1 > m2 > ... the zero run ending at q-1 has length q-m1-1 and the longest window ending at q-1
-// with <= max mismatches has length q - m_{max+1} - 1.
+// One lane per diagonal; inside a 16-position word the lane walks only the MISMATCH positions q (ffs over the 16
+// flags of one XOR): with the previous mismatches m1 > m2 > ... the zero run ending at q-1 has length q-m1-1 and the
+// longest window ending at q-1 with <= max mismatches has length q - m_{max+1} - 1.
+// Word filter: the results are only ever compared with k >= min_k (callers: lb2_pipeline.cuh), so runs and windows
+// shorter than 11 are irrelevant when min_k >= 11.  A run/window of 11+ positions contains two adjacent aligned
+// 4-position blocks holding <= max mismatches between them ("sparse pair"), and when it is evaluated at a mismatch q
+// inside word i that pair starts in word i-1 or i.  Words with no sparse pair in reach are skipped after a dozen
+// instructions (random sequence: ~98 % of them); a skipped word holds >= 2(max+1) mismatches, so the mismatch history
+// a later exact word needs is the top set bits of the word before it.  First and last word of a diagonal are exact.
 LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int len, int maxmm)
 {
 	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
@@ -42,16 +48,42 @@ LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int 
 	lb2_sync();
 	int emax = 0, wmax = 0;
 	if (maxmm > 3) { maxmm = 3; if (tid == 0) { sh->err |= 1u << LB2_D_KMAX; } }
-	for (int d = 1 + (int)tid; d < len; d += (int)nt) {
-		const int np = len - d;                 // positions p in [0, np)
-		int m1 = -1, m2 = -1, m3 = -1, m4 = -1; // previous mismatch positions (virtual mismatch at -1)
+	const bool filter = W.P->min_k >= 11 && maxmm >= 1;
+	const uint32_t bias = (0x80u - (uint32_t)(maxmm + 1)) * 0x010101u;
+	// diagonals dealt to the lanes boustrophedon (lengths fall with d): every lane gets about the same number of positions
+	const int ndiag = len - 1;
+	for (int r = 0; r * (int)nt < ndiag; ++r) {
+		const int j = r * (int)nt + ((r & 1) ? (int)(nt - 1 - tid) : (int)tid);
+		if (j >= ndiag) { continue; }
+		const int d = j + 1, np = len - d;                 // positions p in [0, np)
+		int m1 = -1, m2 = -1, m3 = -1, m4 = -1;             // previous mismatch positions (virtual mismatch at -1)
+		uint32_t prev_fw = 0, prev_c3 = 0; bool prev_sp = true, exact = true;
 		for (int p0 = 0; p0 < np; p0 += 16) {
 			uint32_t fw = lb2_mm16(bits, g0, (uint32_t)p0, (uint32_t)d);
+			const bool last = np - p0 <= 16;
 			if (np - p0 < 16) { fw &= (1u << (2 * (np - p0))) - 1u; }
+			if (filter) {
+				const uint32_t t = (fw & 0x11111111u) + ((fw >> 2) & 0x11111111u);
+				const uint32_t c = (t + (t >> 4)) & 0x0F0F0F0Fu;      // mismatches per 4-position block
+				const uint32_t s2 = c + (c >> 8);                     // blocks (0,1) (1,2) (2,3) in bytes 0..2
+				const bool sp = ((~(s2 + bias)) & 0x808080u) != 0;    // some pair inside the word is sparse
+				const bool cross = prev_c3 + (c & 0xFFu) <= (uint32_t)maxmm;
+				const bool slow = sp || cross || prev_sp || last;
+				prev_sp = sp; prev_c3 = c >> 24;
+				if (!slow) { prev_fw = fw; exact = false; continue; }
+				if (!exact) {      // history = the top set bits of the skipped word before this one
+					uint32_t x = prev_fw; const int pb = p0 - 16;
+					if (x) { int b = 31 - lb2_clz32(x); m1 = pb + (b >> 1); x &= ~(1u << b); }
+					if (x) { int b = 31 - lb2_clz32(x); m2 = pb + (b >> 1); x &= ~(1u << b); }
+					if (x) { int b = 31 - lb2_clz32(x); m3 = pb + (b >> 1); x &= ~(1u << b); }
+					if (x) { int b = 31 - lb2_clz32(x); m4 = pb + (b >> 1); }
+					exact = true;
+				}
+			}
 			while (fw) {
 				int b = lb2_ctz32(fw); fw &= fw - 1;
 				int q = p0 + (b >> 1);
-				int run = q - m1 - 1; if (q == np - 1) { /* position np-1 is outside the exact-repeat range anyway */ }
+				int run = q - m1 - 1;                       // (q == np-1 is outside the exact-repeat range, but then run ends at np-2 anyway)
 				if (run > emax) { emax = run; }
 				int far = (maxmm == 0) ? m1 : (maxmm == 1) ? m2 : (maxmm == 2) ? m3 : m4;
 				int win = q - far - 1; if (win > wmax) { wmax = win; }
@@ -190,36 +222,55 @@ LB2_DEV void lb2_flag_path(lb2_win &W, int flag) {
 // global_align_aff(S = trimmed reference, T = path): anti-diagonal wavefront over the CTA.
 // tb byte per cell: M.tb (0 '\\', 1 '<', 2 '^', 3 '*') | X.tb<<2 (0 '<', 1 '-', 2 other) | Y.tb<<4 (0 '^', 1 '|', 2 other)
 // ---------------------------------------------------------------------------------------------------
-LB2_DEVNI void lb2_align_fill(lb2_win &W)
+// (the traceback bytes are stored anti-diagonal-major, tb[(i+j) * (n+1) + i]: the lanes of a wavefront write consecutive bytes)
+template <class DT> LB2_DEV void lb2_align_fill_t(lb2_win &W, DT *dp, const char *T)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const int n = (int)sh->seq_len, m = (int)sh->plen;
-	const char *S = W.ref_raw + sh->seq_off; const char *T = ws.pathseq;
-	const int stride = LB2_MAX_REF + 2;
-	int32_t *Mb = ws.dp, *Xb = ws.dp + 3 * stride, *Yb = ws.dp + 5 * stride;
+	const char *S = W.ref_raw + sh->seq_off;
+	const int stride = n + 2;
+	DT *Mb = dp, *Xb = dp + 3 * stride, *Yb = dp + 5 * stride;
 	const size_t row = (size_t)n + 1;
 	for (int d = 0; d <= n + m; ++d) {
-		int32_t *M0 = Mb + (d % 3) * stride, *M1 = Mb + ((d + 2) % 3) * stride, *M2 = Mb + ((d + 1) % 3) * stride;
-		int32_t *X0 = Xb + (d & 1) * stride, *X1 = Xb + ((d + 1) & 1) * stride;
-		int32_t *Y0 = Yb + (d & 1) * stride, *Y1 = Yb + ((d + 1) & 1) * stride;
+		DT *M0 = Mb + (d % 3) * stride, *M1 = Mb + ((d + 2) % 3) * stride, *M2 = Mb + ((d + 1) % 3) * stride;
+		DT *X0 = Xb + (d & 1) * stride, *X1 = Xb + ((d + 1) & 1) * stride;
+		DT *Y0 = Yb + (d & 1) * stride, *Y1 = Yb + ((d + 1) & 1) * stride;
 		int lo = d - m; if (lo < 0) { lo = 0; } int hi = d < n ? d : n;
+		uint8_t *tbd = ws.tb + (size_t)d * row;
 		for (int i = lo + (int)tid; i <= hi; i += (int)nt) {
 			int j = d - i; uint8_t tb;
-			if (i == 0 && j == 0) { M0[0] = 0; X0[0] = -8; Y0[0] = -8; tb = 3 | (2 << 2) | (2 << 4); }
-			else if (i == 0) { M0[0] = -8 - j; X0[0] = -8 - j; Y0[0] = 0; tb = 2 | (2 << 2) | (2 << 4); }
-			else if (j == 0) { M0[i] = -8 - i; Y0[i] = -8 - i; X0[i] = 0; tb = 1 | (2 << 2) | (2 << 4); }
+			if (i == 0 && j == 0) { M0[0] = 0; X0[0] = (DT)-8; Y0[0] = (DT)-8; tb = 3 | (2 << 2) | (2 << 4); }
+			else if (i == 0) { M0[0] = (DT)(-8 - j); X0[0] = (DT)(-8 - j); Y0[0] = 0; tb = 2 | (2 << 2) | (2 << 4); }
+			else if (j == 0) { M0[i] = (DT)(-8 - i); Y0[i] = (DT)(-8 - i); X0[i] = 0; tb = 1 | (2 << 2) | (2 << 4); }
 			else {
-				int xe = X1[i - 1] - 1, xo = M1[i - 1] - 8; int x, xt; if (xe > xo) { x = xe; xt = 1; } else { x = xo; xt = 0; }
-				int ye = Y1[i] - 1, yo = M1[i] - 8; int y, yt; if (ye > yo) { y = ye; yt = 1; } else { y = yo; yt = 0; }
-				int z = M2[i - 1] + ((S[i - 1] == T[j - 1]) ? 2 : -4); int mt = 0;
+				int xe = (int)X1[i - 1] - 1, xo = (int)M1[i - 1] - 8; int x, xt; if (xe > xo) { x = xe; xt = 1; } else { x = xo; xt = 0; }
+				int ye = (int)Y1[i] - 1, yo = (int)M1[i] - 8; int y, yt; if (ye > yo) { y = ye; yt = 1; } else { y = yo; yt = 0; }
+				int z = (int)M2[i - 1] + ((S[i - 1] == T[j - 1]) ? 2 : -4); int mt = 0;
 				if (x > z) { z = x; mt = 1; }
 				if (y > z) { z = y; mt = 2; }
-				M0[i] = z; X0[i] = x; Y0[i] = y; tb = (uint8_t)(mt | (xt << 2) | (yt << 4));
+				M0[i] = (DT)z; X0[i] = (DT)x; Y0[i] = (DT)y; tb = (uint8_t)(mt | (xt << 2) | (yt << 4));
 			}
-			ws.tb[(size_t)j * row + i] = tb;
+			tbd[i] = tb;
 		}
 		lb2_sync();
 	}
+}
+LB2_DEVNI void lb2_align_fill(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const uint32_t n = sh->seq_len, m = sh->plen;
+	// the seven score rows as 16-bit values (|score| <= 8 + 4 * (n + m) < 2^15) and the path in the idle shared-memory scratch
+	const uint32_t dpw = (7u * (n + 2u) * 2u + 3u) / 4u, tw = (m + 4u) / 4u;
+	if (dpw <= ws.px_words) {
+		const char *T = ws.pathseq;
+		if (dpw + tw <= ws.px_words) {
+			char *Ts = (char *)(ws.px + dpw);
+			for (uint32_t i = tid; i < m; i += nt) { Ts[i] = ws.pathseq[i]; }
+			T = Ts;
+			lb2_sync();
+		}
+		lb2_align_fill_t<int16_t>(W, (int16_t *)ws.px, T);
+	} else { lb2_align_fill_t<int32_t>(W, ws.dp, ws.pathseq); }
 }
 
 LB2_DEVNI void lb2_align_trace(lb2_win &W)
@@ -229,7 +280,7 @@ LB2_DEVNI void lb2_align_trace(lb2_win &W)
 	const char *S = W.ref_raw + sh->seq_off; const char *T = ws.pathseq;
 	int i = n, j = m; bool forcex = false, forcey = false; uint32_t L = 0;
 	while (i > 0 || j > 0) {
-		uint8_t tb = ws.tb[(size_t)j * row + i]; int t = tb & 3, x = (tb >> 2) & 3, y = (tb >> 4) & 3;
+		uint8_t tb = ws.tb[(size_t)(i + j) * row + i]; int t = tb & 3, x = (tb >> 2) & 3, y = (tb >> 4) & 3;
 		char a, b;
 		if (t == 3) { break; }
 		else if (forcex) { if (i <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = S[i - 1]; b = '-'; if (x == 0) { forcex = false; } --i; }
@@ -327,22 +378,25 @@ LB2_DEVNI void lb2_path_tandems(lb2_win &W)
 	lb2_sync();
 }
 
-// column scan + stats + emission (lane 0).  aligned strings are in ws.aln_ref / ws.aln_path.
-LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
+// column scan + stats + emission.  aligned strings are in ws.aln_ref / ws.aln_path.  The reference walks every column;
+// only the columns that are not '=' do anything, so all lanes classify the columns, two prefix sums give every column's
+// reference / path position and the list of non-'=' columns, and lane 0 walks that list (lb2_scan_columns).
+LB2_DEV uint32_t lb2_col_class(char r, char p) { return r == '-' ? 1u : p == '-' ? 2u : (r != p) ? 3u : 0u; }   // 0 '=', 1 '^', 2 'v', 3 'x'
+LB2_DEVNI void lb2_scan_columns(lb2_win &W, const uint32_t *pre, const uint32_t *lst, uint32_t nne)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
-	const char *ra = ws.aln_ref, *pa = ws.aln_path; const uint32_t alen = sh->aln_len;
+	const char *ra = ws.aln_ref, *pa = ws.aln_path;
 	const uint32_t plen = sh->plen;
 	lb2_trans *tr = ws.trans; uint32_t ts = 0;
 	char *poolR = ws.tstr, *poolQ = ws.tstr + (LB2_MAX_PATH + LB2_MAX_REF + 8); uint32_t usedR = 0, usedQ = 0;
-	uint32_t pos_in_ref = 0, refpos = 0, pathpos = 0; char code = '?', prev_code = '?';
 	const uint32_t trim5 = sh->trim5;
-	for (uint32_t i = 0; i < alen; ++i) {
-		prev_code = code;
-		if (ra[i] == '-') { code = '^'; pos_in_ref = refpos; ++pathpos; }
-		else if (pa[i] == '-') { code = 'v'; pos_in_ref = refpos; ++refpos; }
-		else { code = (ra[i] != pa[i]) ? 'x' : '='; pos_in_ref = refpos; ++refpos; ++pathpos; }
-		if (code == '=') { continue; }   // (the spanner lookup of '=' columns has no side effect)
+	uint32_t prev_i = LB2_NIL;
+	for (uint32_t e = 0; e < nne; ++e) {
+		const uint32_t i = lst[e], cl = lb2_col_class(ra[i], pa[i]), pv = pre[i];
+		const char code = (cl == 1) ? '^' : (cl == 2) ? 'v' : 'x';
+		const uint32_t pos_in_ref = pv & 0xFFFFu, pathpos = (pv >> 16) + ((cl != 2) ? 1u : 0u);
+		const bool prev_noneq = (i == 0) || (prev_i != LB2_NIL && prev_i + 1 == i);      // prev_code != '='
+		prev_i = i;
 		uint32_t spanner = lb2_pathcontig(W, (int)pathpos);
 		if (spanner == LB2_NIL) { break; }
 		bool within_tumor = lb2_status_T(W, spanner);
@@ -355,7 +409,7 @@ LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
 		while (pr >= 0 && !lb2_isACGT(ra[pr])) { --pr; }
 		while (pq >= 0 && !lb2_isACGT(pa[pq])) { --pq; }
 		if (pr < 0 || pq < 0) { sh->err |= 1u << LB2_D_ALIGN; return; }
-		if (ts > 0 && prev_code != '=') {
+		if (ts > 0 && prev_noneq) {
 			lb2_trans &t = tr[ts - 1];
 			if (within_tumor) { t.isSomatic = 1; }
 			if (usedR >= LB2_MAX_PATH + LB2_MAX_REF || usedQ >= LB2_MAX_PATH + LB2_MAX_REF) { sh->err |= 1u << LB2_D_TRANS; return; }
@@ -443,24 +497,33 @@ LB2_DEVNI void lb2_scan_alignment(lb2_win &W)
 	}
 }
 
+LB2_DEVNI void lb2_scan_alignment(lb2_win &W)      // all lanes
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const char *ra = ws.aln_ref, *pa = ws.aln_path; const uint32_t alen = sh->aln_len;
+	uint32_t *pre = (uint32_t *)ws.sortk, *lst = pre + ((alen + 3u) & ~3u);      // (the build's sort keys are idle in the graph stage)
+	// reference position before the column (low half) | path position before the column (high half)
+	lb2_excl_scan(W, alen, [&](uint32_t i) -> uint32_t { const uint32_t c = lb2_col_class(ra[i], pa[i]); return ((c != 1u) ? 1u : 0u) | ((c != 2u) ? 0x10000u : 0u); },
+	              [&](uint32_t i, uint32_t v) { pre[i] = v; });
+	const uint32_t nne = lb2_excl_scan(W, alen, [&](uint32_t i) -> uint32_t { return lb2_col_class(ra[i], pa[i]) ? 1u : 0u; },
+	                                   [&](uint32_t i, uint32_t v) { if (lb2_col_class(ra[i], pa[i])) { lst[v] = i; } });
+	if (lb2_tid() == 0) { lb2_scan_columns(W, pre, lst, nne); }
+}
+
 // processPath for the path loaded in ws.pathseq (all lanes: the alignment is CTA-wide)
 LB2_DEVNI void lb2_process_path(lb2_win &W)
 {
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
-	if (lb2_tid() == 0) {
-		// HammingDistance cut-off (src/Graph.cc:818-826)
-		int hd = -1;
-		if (sh->seq_len == sh->plen) {
-			hd = 0; const char *S = W.ref_raw + sh->seq_off;
-			for (uint32_t i = 0; i < sh->plen; ++i) { if (S[i] != ws.pathseq[i]) { ++hd; } }
-		}
-		sh->need_align = (hd == -1 || hd > 5) ? 1u : 0u;
-		if (!sh->need_align) {
-			const char *S = W.ref_raw + sh->seq_off;
-			for (uint32_t i = 0; i < sh->plen; ++i) { ws.aln_ref[i] = S[i]; ws.aln_path[i] = ws.pathseq[i]; }
-			sh->aln_len = sh->plen;
-		}
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	// HammingDistance cut-off (src/Graph.cc:818-826): equal lengths and <= 5 mismatches => the identity alignment
+	const bool samelen = sh->seq_len == sh->plen;
+	if (tid == 0) { sh->flag_b = 0; }
+	lb2_sync();
+	if (samelen) {
+		const char *S = W.ref_raw + sh->seq_off; uint32_t hd = 0;
+		for (uint32_t i = tid; i < sh->plen; i += nt) { const char a = S[i], b = ws.pathseq[i]; ws.aln_ref[i] = a; ws.aln_path[i] = b; if (a != b) { ++hd; } }
+		if (hd) { lb2_add32(&sh->flag_b, hd); }
 	}
+	lb2_sync();
+	if (tid == 0) { sh->need_align = (!samelen || sh->flag_b > 5) ? 1u : 0u; if (!sh->need_align) { sh->aln_len = sh->plen; } }
 	lb2_sync();
 	if (sh->need_align) {
 		lb2_align_fill(W);
@@ -469,7 +532,7 @@ LB2_DEVNI void lb2_process_path(lb2_win &W)
 	}
 	lb2_mark(W, LB2_PH_ALIGN);
 	lb2_path_tandems(W);
-	if (lb2_tid() == 0 && !sh->err) { lb2_scan_alignment(W); }
+	if (!sh->err) { lb2_scan_alignment(W); }
 	lb2_sync();
 	lb2_mark(W, LB2_PH_SCAN);
 }

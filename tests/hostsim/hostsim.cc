@@ -28,6 +28,39 @@ int main(int argc, char **argv)
 		else if (a == "--count") count = atoi(argv[++i]); else if (a == "--dfs-limit") P.dfs_limit = atoi(argv[++i]);
 		else fn = argv[i];
 	}
+	if (fn && std::string(fn) == "scantest") {
+		// the word filter of lb2_diag_scan against the unfiltered scan (min_k < 11 switches the filter off): for every k >= 11
+		// both must answer isRepeat / isAlmostRepeat alike, i.e. max(emax,10) and max(wmax,11) agree
+		std::vector<uint8_t> smem(sizeof(lb2_sh) + 64, 0); lb2_win Wn; memset(&Wn, 0, sizeof Wn); Wn.sh = (lb2_sh *)smem.data(); Wn.P = &P;
+		unsigned long long rs = 88172645463325252ull; auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t)(rs >> 11); };
+		int bad = 0, ntest = 0, nrel = 0;
+		for (int t = 0; t < 6000; ++t) {
+			const int len = 20 + (int)(rnd() % 900); std::string q(len, 'A');
+			for (int i = 0; i < len; ++i) { q[i] = "ACGT"[rnd() & 3]; }
+			const int mode = t % 6;
+			if (mode >= 1) {      // planted repeats: copies with 0..4 substitutions, tandem units, at the string ends too
+				const int nplant = 1 + (int)(rnd() % 3);
+				for (int z = 0; z < nplant; ++z) {
+					const int rl = 8 + (int)(rnd() % 40); if (rl * 2 + 2 > len) { continue; }
+					int a = (int)(rnd() % (len - rl)), b = (int)(rnd() % (len - rl));
+					if (mode == 2) { a = 0; } if (mode == 3) { b = len - rl; } if (mode == 4) { b = a + 1 + (int)(rnd() % 6); if (b + rl > len) { continue; } }
+					for (int i = 0; i < rl; ++i) { q[b + i] = q[a + i]; }
+					const int nsub = (int)(rnd() % 5);
+					for (int i = 0; i < nsub; ++i) { q[b + (int)(rnd() % rl)] = "ACGT"[rnd() & 3]; }
+				}
+			}
+			std::vector<uint32_t> pk(len / 16 + 8, 0);
+			for (int i = 0; i < len; ++i) { pk[i >> 4] |= (uint32_t)lb2_code(q[i]) << (2 * (i & 15)); }
+			for (int mm = 1; mm <= 3; ++mm) {
+				P.min_k = 11; lb2_diag_scan(Wn, pk.data(), 0, len, mm); const uint32_t e1 = Wn.sh->scan_emax, w1 = Wn.sh->scan_wmax;
+				P.min_k = 5;  lb2_diag_scan(Wn, pk.data(), 0, len, mm); const uint32_t e0 = Wn.sh->scan_emax, w0 = Wn.sh->scan_wmax;
+				++ntest; if (e0 >= 11 || w0 >= 12) { ++nrel; }
+				if (std::max(e1, 10u) != std::max(e0, 10u) || std::max(w1, 11u) != std::max(w0, 11u)) { if (bad++ < 10) { fprintf(stderr, "MISMATCH t=%d len=%d mm=%d: filtered e=%u w=%u, exact e=%u w=%u\n", t, len, mm, e1, w1, e0, w0); } }
+			}
+		}
+		printf("scantest: %d scans (%d with a result >= the thresholds), %d mismatches\n", ntest, nrel, bad);
+		return bad ? 1 : 0;
+	}
 	FILE *f = fopen(fn, "rb"); if (!f) { perror(fn); return 2; }
 	char magic[4]; uint32_t ver, W, R, nwr; uint64_t nref, nbase;
 	if (fread(magic, 1, 4, f) != 4 || fread(&ver, 4, 1, f) != 1 || fread(&W, 4, 1, f) != 1 || fread(&R, 4, 1, f) != 1 || fread(&nwr, 4, 1, f) != 1 ||
