@@ -464,6 +464,9 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		ws.rd_kbase[R] = cum;
 		sh->n_used = 0; sh->err = 0; sh->n_spec = 0; sh->flag_a = 0;
 		sh->K = K; sh->nw = nw;
+		// up to four pieces per read, none shorter than 16 pairs (every piece re-derives its first k-mer)
+		{ const uint32_t mp = sh->maxnk > 1 ? sh->maxnk - 1 : 1u; uint32_t np_ = mp / 16u; if (np_ < 1) { np_ = 1; } if (np_ > 4) { np_ = 4; }
+		  sh->walk_np = np_; sh->walk_pl = (mp + np_ - 1) / np_; if (sh->walk_pl < 16) { sh->walk_pl = 16; } sh->walk_next = 0; }
 		// occurrence array: offset-major (coalesced stores) when it fits, read-major otherwise
 		const uint32_t Rs = (R + 31u) & ~31u;
 		bool transposed = (uint64_t)sh->maxnk * Rs + L + 2 <= (uint64_t)C->max_inst;
@@ -481,18 +484,29 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	if (sh->err) { return; }
 	const uint32_t istr = sh->inst_stride ? sh->inst_stride : 1u;
 	const uint32_t nref_pairs = (L > (uint32_t)K) ? (L - K) : 0;
-	const uint32_t nchunks = (nref_pairs + 63) / 64;
-	for (uint32_t it = tid; it < R + nchunks; it += nt) {
-		if (it < R) {
-			uint32_t n = ws.rd_len[it];
+	// work items: (piece of a read) and (piece of the reference), handed out to whole warps from a shared counter so that
+	// the warps finish together.  Item = piece * R + read: the lanes of a warp walk the same piece of consecutive reads
+	// (equal lengths, consecutive words of the offset-major occurrence array).
+	const uint32_t PL = sh->walk_pl, NP = sh->walk_np;
+	const uint32_t nchunks = (nref_pairs + PL - 1) / PL, nitems = NP * R + nchunks;
+	while (true) {
+		const uint32_t it = lb2_batch_next(&sh->walk_next);
+		if (it >= ((nitems + 31u) & ~31u)) { break; }
+		if (it >= nitems) { continue; }
+		if (it < NP * R) {
+			const uint32_t piece = it / R, r = it - piece * R;
+			const uint32_t n = ws.rd_len[r];
 			if (n > (uint32_t)K) {
-				const uint32_t ib = sh->inst_stride ? it : ws.rd_kbase[it];
-				if (nw == 1) { lb2_walk<1>(W, ws.rd_start[it], n, 0, n - K, ib, istr, false, ws.rd_info[it] & 3u, K, nw); }
-				else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[it], n, 0, n - K, ib, istr, false, ws.rd_info[it] & 3u, K, nw); }
-				else { lb2_walk<LB2_MAXW>(W, ws.rd_start[it], n, 0, n - K, ib, istr, false, ws.rd_info[it] & 3u, K, nw); }
+				const uint32_t np_ = n - K, ob = piece * PL; uint32_t oe = ob + PL; if (oe > np_) { oe = np_; }
+				if (ob < np_) {
+					const uint32_t ib = sh->inst_stride ? r : ws.rd_kbase[r];
+					if (nw == 1) { lb2_walk<1>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
+					else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
+					else { lb2_walk<LB2_MAXW>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
+				}
 			}
 		} else {
-			uint32_t c = it - R, ob = c * 64, oe = ob + 64; if (oe > nref_pairs) { oe = nref_pairs; }
+			uint32_t c = it - NP * R, ob = c * PL, oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
 			if (nw == 1) { lb2_walk<1>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
 			else if (nw == 2) { lb2_walk<2>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
 			else { lb2_walk<LB2_MAXW>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
@@ -655,24 +669,46 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	lb2_sync();
 	if (sh->flag_a && !sh->err) {
 		for (uint32_t j = tid; j < n; j += nt) { if (ws.b_flags[j] & 0x20) { W.t_id[ws.used[j]] |= LB2_ID_BRANCH; } }
+		if (tid == 0) { sh->walk_next = 0; }
 		lb2_sync();
-		for (uint32_t it = tid; it < R + 1; it += nt) {
-			uint32_t g0, np, kb, ks, st;      // kb: occurrence number (first-seen stamps), ks/st: where the occurrences are stored
-			if (it < R) { uint32_t n_ = ws.rd_len[it]; if (n_ <= (uint32_t)K) { continue; } g0 = ws.rd_start[it]; np = n_ - K; kb = ws.rd_kbase[it]; ks = sh->inst_stride ? it : kb; st = istr; }
-			else { g0 = sh->ref_g; np = nref_pairs; kb = ws.rd_kbase[R]; ks = sh->inst_ref; st = 1u; }
-			uint32_t iu = ws.inst[ks];
-			for (uint32_t o = 0; o < np; ++o) {
-				uint32_t iv = ws.inst[ks + (o + 1) * st];
-				uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
-				if (W.t_id[su] & LB2_ID_BRANCH) {
-					uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
-					lb2g_min32(&ws.bseq[(size_t)(W.t_id[su] & 0x7FFFu) * 8 + t], 2 * (kb + o));
+		// second pass over the occurrence array, same work items as the walk; the occurrence words are fetched eight at a
+		// time (the loads do not depend on each other, the lane would otherwise sit out one memory latency per k-mer)
+		while (true) {
+			const uint32_t it = lb2_batch_next(&sh->walk_next);
+			if (it >= ((nitems + 31u) & ~31u)) { break; }
+			if (it >= nitems) { continue; }
+			uint32_t g0, ob, oe, kb, ks, st;      // kb: occurrence number (first-seen stamps), ks/st: where the occurrences are stored
+			if (it < NP * R) {
+				const uint32_t piece = it / R, r = it - piece * R, n_ = ws.rd_len[r];
+				if (n_ <= (uint32_t)K) { continue; }
+				ob = piece * PL; oe = ob + PL; if (oe > n_ - K) { oe = n_ - K; }
+				if (ob >= n_ - K) { continue; }
+				g0 = ws.rd_start[r]; kb = ws.rd_kbase[r]; ks = sh->inst_stride ? r : kb; st = istr;
+			} else {
+				ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
+				g0 = sh->ref_g; kb = ws.rd_kbase[R]; ks = sh->inst_ref; st = 1u;
+			}
+			uint32_t iu = ws.inst[ks + ob * st];
+			for (uint32_t o8 = ob; o8 < oe; o8 += 8) {
+				uint32_t v[8];
+#pragma unroll
+				for (uint32_t q = 0; q < 8; ++q) { v[q] = (o8 + q < oe) ? ws.inst[ks + (o8 + q + 1) * st] : 0u; }
+#pragma unroll
+				for (uint32_t q = 0; q < 8; ++q) {
+					if (o8 + q >= oe) { continue; }
+					const uint32_t o = o8 + q, iv = v[q];
+					const uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
+					const uint32_t idu = W.t_id[su], idv = W.t_id[sv];
+					if (idu & LB2_ID_BRANCH) {
+						uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
+						lb2g_min32(&ws.bseq[(size_t)(idu & 0x7FFFu) * 8 + t], 2 * (kb + o));
+					}
+					if (idv & LB2_ID_BRANCH) {
+						uint32_t t = (1u - (iv >> 31)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
+						lb2g_min32(&ws.bseq[(size_t)(idv & 0x7FFFu) * 8 + t], 2 * (kb + o) + 1);
+					}
+					iu = iv;
 				}
-				if (W.t_id[sv] & LB2_ID_BRANCH) {
-					uint32_t t = (1u - (iv >> 31)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
-					lb2g_min32(&ws.bseq[(size_t)(W.t_id[sv] & 0x7FFFu) * 8 + t], 2 * (kb + o) + 1);
-				}
-				iu = iv;
 			}
 		}
 		lb2_sync();

@@ -750,7 +750,10 @@ LB2_DEVNI void lb2_materialize(lb2_win &W) {
 		lb2_job jb = jobs[q];
 		char *S = (char *)ws.arena + jb.so; lb2_cov *CT = (lb2_cov *)(ws.arena + jb.co); lb2_cov *CN = CT + jb.curlen;
 		int mn = 10000000, mnq = 10000000;
-		for (uint32_t m = tid; m <= jb.nAll; m += nt) {
+		// many short members (first compaction: single k-mer nodes): one lane per member; a few long ones (later
+		// compactions merge unitigs): the members in turn, lanes across the bases
+		const bool by_member = jb.nAll + 1 >= 64;
+		for (uint32_t m = by_member ? tid : 0u; m <= jb.nAll; m += by_member ? nt : 1u) {
 			uint32_t id, first, count, dst; bool flip;
 			if (m == jb.nAll) { id = jb.node; flip = false; first = 0; count = jb.len0; dst = jb.leftlen; }
 			else {
@@ -760,7 +763,7 @@ LB2_DEVNI void lb2_materialize(lb2_win &W) {
 				first = (m < jb.nF) ? (uint32_t)K - 1 : 0;       // F: oriented[K-1..], R: frame[0..bl-K]
 			}
 			lb2_nview v; lb2_view(W, id, v);
-			for (uint32_t i = 0; i < count; ++i) {
+			for (uint32_t i = by_member ? 0u : tid; i < count; i += by_member ? 1u : nt) {
 				uint32_t o = first + i, src = flip ? (v.len - 1 - o) : o;
 				char ch = lb2_vchar(W, v, src); S[dst + i] = flip ? lb2_comp(ch) : ch;
 				lb2_cov ct = lb2_vcov(W, v, src, 0), cn = lb2_vcov(W, v, src, 1);
@@ -782,6 +785,22 @@ LB2_DEVNI void lb2_clean_dead_par(lb2_win &W)
 	const uint32_t NT = sh->n_rows + sh->n_spec;
 	if (tid == 0) { sh->n_dead = 0; }
 	lb2_sync();
+	// runs of dead nodes are shortcut first (pointer jumping on the dead nodes' own links, in place: a dead node's link is
+	// never followed again once the node is erased; a stale read is still a valid, shorter shortcut)
+	while (true) {
+		if (tid == 0) { sh->flag_d = 0; }
+		lb2_sync();
+		bool ch = false;
+		for (uint32_t r = tid; r < NT; r += nt) {
+			if ((ws.d_flags[r] & (LB2_NF_DEAD | LB2_NF_GONE)) != LB2_NF_DEAD) { continue; }
+			const uint32_t x = ws.d_lnext[r];
+			if (x != LB2_NIL && (ws.d_flags[x] & LB2_NF_DEAD)) { ws.d_lnext[r] = ws.d_lnext[x]; ch = true; }
+		}
+		if (ch) { sh->flag_d = 1; }
+		lb2_sync();
+		if (!sh->flag_d) { break; }
+		lb2_sync();
+	}
 	uint32_t nd = 0;
 	for (uint32_t r = tid; r < NT; r += nt) {
 		const uint8_t f = ws.d_flags[r];
@@ -947,28 +966,36 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 	lb2_sync();
 	// fold the float coverages in the reference's absorb order (src/Graph.cc:2631-2636): a serial recurrence per chain and
 	// channel (every step rounds), so one lane per (chain, channel); the integer bookkeeping rides along in every lane
-	for (uint32_t q = tid / LB2_FQ; q < njobs; q += nt / LB2_FQ) {
-		const lb2_job jb = jobs[q]; const uint32_t node = jb.node; const uint32_t *chain = ws.chain + jb.cbeg;
-		for (uint32_t ch = tid % LB2_FQ; ch < 4; ch += LB2_FQ) {
-			float cv = ws.d_cov[node * 4 + ch];
-			uint32_t stn = ws.d_stn[node], stt = ws.d_stT[node], curlen = jb.len0, leftlen = 0;
-			int amerlen = (int)jb.len0 - K + 1;
-			// one step ahead: the loads of the next entry do not depend on the recurrence
-			uint32_t b = jb.nAll ? (chain[0] & 0x7FFFFFFFu) : 0u;
-			int bmerlen = (int)ws.d_len[b] - K + 1; float bc = ws.d_cov[b * 4 + ch]; uint32_t bsn = ws.d_stn[b], bst = ws.d_stT[b];
-			for (uint32_t c = 0; c < jb.nAll; ++c) {
-				const int bm = bmerlen; const float bcv = bc; const uint32_t sn = bsn, st = bst;
-				if (c + 1 < jb.nAll) { b = chain[c + 1] & 0x7FFFFFFFu; bmerlen = (int)ws.d_len[b] - K + 1; bc = ws.d_cov[b * 4 + ch]; bsn = ws.d_stn[b]; bst = ws.d_stT[b]; }
-				cv = lb2_wavg(cv, amerlen, bcv, bm);
-				if (ch == 0) { ws.cpos[jb.cbeg + c] = (c < jb.nF) ? curlen : leftlen + (uint32_t)bm; }      // relative to the seed's left end, see lb2_materialize
-				amerlen += bm; curlen += (uint32_t)bm; stn += sn; stt += st;
-				if (c >= jb.nF) { leftlen += (uint32_t)bm; }
-			}
-			ws.d_cov[node * 4 + ch] = cv;
-			if (ch == 0) {
-				ws.d_stn[node] = (uint16_t)stn; ws.d_stT[node] = (uint16_t)stt;
-				ws.d_mincov[node] = 10000000; ws.d_mincovqv[node] = 10000000;
-				jobs[q].curlen = curlen; jobs[q].leftlen = leftlen;
+	{
+		// (array bases in registers: the descriptor lives in shared memory and would be re-read after every store)
+		const uint16_t *const LEN = ws.d_len, *const STN = ws.d_stn, *const STT = ws.d_stT; const float *const COV = ws.d_cov;
+		uint32_t *const CPOS = ws.cpos; const int K1 = K - 1;
+		for (uint32_t q = tid / LB2_FQ; q < njobs; q += nt / LB2_FQ) {
+			const lb2_job jb = jobs[q]; const uint32_t node = jb.node, nAll = jb.nAll, nF = jb.nF; const uint32_t *const chain = ws.chain + jb.cbeg;
+			for (uint32_t ch = tid % LB2_FQ; ch < 4; ch += LB2_FQ) {
+				float cv = COV[node * 4 + ch];
+				uint32_t stn = STN[node], stt = STT[node], curlen = jb.len0, leftlen = 0;
+				int amerlen = (int)jb.len0 - K1;
+				// software pipeline: the entry of step c was loaded during step c-1, the node id of step c+1 during step c-1
+				uint32_t b1 = nAll ? (chain[0] & 0x7FFFFFFFu) : 0u;
+				uint32_t len_c = LEN[b1], sn_c = STN[b1], st_c = STT[b1]; float cov_c = COV[b1 * 4 + ch];
+				b1 = (nAll > 1) ? (chain[1] & 0x7FFFFFFFu) : 0u;
+				for (uint32_t c = 0; c < nAll; ++c) {
+					const uint32_t len_n = LEN[b1], sn_n = STN[b1], st_n = STT[b1]; const float cov_n = COV[b1 * 4 + ch];      // step c+1 (a harmless re-read at the end)
+					const uint32_t b2 = (c + 2 < nAll) ? (chain[c + 2] & 0x7FFFFFFFu) : 0u;
+					const int bm = (int)len_c - K1;
+					cv = lb2_wavg(cv, amerlen, cov_c, bm);
+					CPOS[jb.cbeg + c] = (c < nF) ? curlen : leftlen + (uint32_t)bm;      // relative to the seed's left end, see lb2_materialize (same value from every channel's lane)
+					amerlen += bm; curlen += (uint32_t)bm; stn += sn_c; stt += st_c;
+					if (c >= nF) { leftlen += (uint32_t)bm; }
+					len_c = len_n; sn_c = sn_n; st_c = st_n; cov_c = cov_n; b1 = b2;
+				}
+				ws.d_cov[node * 4 + ch] = cv;
+				if (ch == 0) {
+					ws.d_stn[node] = (uint16_t)stn; ws.d_stT[node] = (uint16_t)stt;
+					ws.d_mincov[node] = 10000000; ws.d_mincovqv[node] = 10000000;
+					jobs[q].curlen = curlen; jobs[q].leftlen = leftlen;
+				}
 			}
 		}
 	}

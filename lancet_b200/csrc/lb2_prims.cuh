@@ -43,6 +43,8 @@ static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total)
 static inline uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 // ---- sub-warp groups for the read staging (8 lanes per read on the device, 1 in the simulation) ----
 #define LB2_GS 1
+// work items handed out to whole warps: every lane of the warp calls this together and gets its own item index
+static inline uint32_t lb2_batch_next(uint32_t *ctr) { return (*ctr)++; }
 #define LB2_FQ 1      /* lanes per chain in the coverage fold of the parallel compaction (one per channel on the device) */
 static inline unsigned lb2_glane() { return 0; }
 static inline unsigned lb2_group() { return 0; }
@@ -104,6 +106,13 @@ LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {
 LB2_DEV uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 // ---- sub-warp groups for the read staging (8 lanes per read) ----
 #define LB2_GS 8
+// work items handed out to whole warps (32 consecutive items per fetch): every lane of the warp calls this together
+LB2_DEV uint32_t lb2_batch_next(uint32_t *ctr) {
+	uint32_t base = 0;
+	__syncwarp();
+	if ((threadIdx.x & 31u) == 0) { base = lb2_add32(ctr, 32u); }
+	return __shfl_sync(0xFFFFFFFFu, base, 0) + (threadIdx.x & 31u);
+}
 #define LB2_FQ 4      /* lanes per chain in the coverage fold of the parallel compaction: one per channel */
 LB2_DEV unsigned lb2_glane() { return threadIdx.x & 7u; }
 LB2_DEV unsigned lb2_group() { return threadIdx.x >> 3; }

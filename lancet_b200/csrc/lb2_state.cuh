@@ -85,7 +85,7 @@ struct lb2_sh {
 	int32_t  K, nw;
 	uint32_t n_used, n_nodes, n_rows, n_spec, n_jobs, n_eov, err;
 	uint32_t totalreadbp;
-	uint32_t flag_a, flag_b, flag_c; uint32_t scan_emax, scan_wmax, ref_emax, ref_wmax;
+	uint32_t flag_a, flag_b, flag_c, flag_d; uint32_t scan_emax, scan_wmax, ref_emax, ref_wmax;
 	// reference trimming state (Ref_t::seq/trim5/trim3, persists across k: SURVEY B4)
 	uint32_t seq_off, seq_len; uint32_t trim5, trim3;
 	// order emulation
@@ -100,6 +100,7 @@ struct lb2_sh {
 	int32_t  numcomp;
 	uint32_t stop_k; uint32_t n_dead; uint32_t big;
 	uint32_t maxnk, inst_stride, inst_ref;     // occurrence array layout of this (window,k): see lb2_build.cuh
+	uint32_t walk_next, walk_pl, walk_np;      // k-mer walk: work-item counter, pairs per piece, pieces per read
 	uint32_t n_tev, tev_ovf; lb2_tev tev[LB2_MAX_TEV];     // tandem repeats of the loaded path (n_tev = LB2_NIL: not computed, scan per variant)
 	unsigned long long prof[24]; unsigned long long t_last;
 	uint32_t scan[520];           // block-scan partials (<= 512 lanes)
