@@ -258,8 +258,45 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 #define LB2_EM_TUMOR  0x200u
 #define LB2_ID_BRANCH 0x8000u
 
+// one-word k-mers (K <= 32; KT = uint32_t when K <= 16): table and packed bases through precomputed shared addresses
+template <class KT> LB2_DEV uint32_t lb2_foi_small(lb2_win &W, lb2_sp tk, lb2_sp bits, uint32_t mask, KT canon, KT nonc, uint32_t rep, KT kmask, bool insert)
+{
+	const uint32_t h = lb2_hash1((uint32_t)canon, sizeof(KT) > 4 ? (uint32_t)((uint64_t)canon >> 32) : 0u);
+	uint32_t i = h & mask;
+	const uint32_t fp = 0x80000000u | ((h >> 22) << 21);
+	for (uint32_t probes = 0; probes <= mask; ++probes) {
+		const lb2_sp at = lb2_sp_at(tk, i);
+		uint32_t cur = lb2s_ldv(at);
+		if (cur == 0) {
+			if (!insert) { return LB2_NIL; }
+			const uint32_t prev = lb2s_cas(at, 0u, fp | rep);
+			if (prev == 0) {
+				uint32_t u = lb2_add32(&W.sh->n_used, 1u);
+				if (u < W.C->max_nodes && u < (mask + 1) - ((mask + 1) >> 2)) { W.ws.used[u] = i; } else { lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL); }
+				return i;
+			}
+			cur = prev;
+		}
+		if ((cur & 0xFFE00000u) == fp) {
+			const uint32_t r = cur & 0x1FFFFFu;
+			const KT o = lb2_extract_small<KT>(bits, r >> 1) & kmask;
+			if (o == ((r & 1u) ? nonc : canon)) {
+				if (insert && rep < r) { lb2s_min(at, fp | rep); }      // same k-mer => same fingerprint: the word orders by rep
+				return i;
+			}
+		}
+		i = (i + 1) & mask;
+	}
+	lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL);
+	return LB2_NIL;
+}
+
 template <int NWT = LB2_MAXW> LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2_kmer &nonc, uint32_t rep, int K, int nw, bool insert)
 {
+	if (NWT == 1) {      // (the same hash and fingerprint as the one-word walk)
+		const uint64_t kmask = (~0ull) >> (64 - 2 * K);
+		return lb2_foi_small<uint64_t>(W, lb2_sp_of(W.t_key), lb2_sp_of(W.bits), W.C->table_slots - 1, canon.w[0], nonc.w[0], rep, kmask, insert);
+	}
 	uint32_t *tk = W.t_key; const uint32_t mask = W.C->table_slots - 1;
 	uint64_t h = lb2_table_hash<NWT>(canon, nw);
 	uint32_t i = (uint32_t)h & mask;
@@ -353,6 +390,74 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 		lb2_em_or(W, su, emu); lb2_em_or(W, sv, emv);
 		su = sv; ori_u = ori_v;
 	}
+}
+
+// the same work item for one-word k-mers: little-endian f / rc for the table, big-endian copies so that the reference's
+// string comparison mer < rc is one integer compare; one mask update per k-mer (the bits a k-mer receives as the v of one
+// pair and as the u of the next are merged)
+template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
+                      bool isref, uint32_t cls, int K)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	const lb2_sp tk = lb2_sp_of(W.t_key), tidw = lb2_sp_of(W.t_id), bits = lb2_sp_of(W.bits);
+	const uint32_t mask = W.C->table_slots - 1;
+	const int topsh = 2 * (K - 1); const KT kmask = (KT)(~(KT)0) >> (sizeof(KT) * 8 - 2 * K);
+	KT f = 0, rc = 0, fB = 0, rcB = 0;
+	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
+	for (int i = 0; i < K; ++i, ++g) {          // first K bases
+		if ((g & 15) == 0 || i == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
+		const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
+		f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
+		fB = ((fB << 2) | (KT)c) & kmask; rcB = (rcB >> 2) | ((KT)(3u - c) << topsh);
+	}
+	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
+	const bool track_q = tumor && sh->has_lowq;
+	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u, csel = cls >> 1;
+	int lowcnt = 0;    // low-quality bases in [o, o+K-1]; the pair window adds base o+K
+	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
+	bool fless = fB < rcB;
+	uint32_t ori_u = fless ? 0u : 1u;
+	uint32_t su = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, kmask, true);
+	if (su == LB2_NIL) { return; }
+	ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
+	uint32_t pend = 0;      // mask bits owed to su
+	if (isref) { ws.refnode[o_begin] = su; }
+	else if (o_begin == 0) {
+		lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
+		if (normal) { pend = LB2_EM_NORMAL; }
+	}
+	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
+		if ((g & 15) == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
+		const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
+		const uint32_t a = (uint32_t)f & 3u;                           // base that leaves the window (first base of u)
+		f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
+		fB = ((fB << 2) | (KT)c) & kmask; rcB = (rcB >> 2) | ((KT)(3u - c) << topsh);
+		fless = fB < rcB;
+		const uint32_t ori_v = fless ? 0u : 1u;
+		const uint32_t sv = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, kmask, true);
+		if (sv == LB2_NIL) { return; }
+		ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
+		uint32_t emu = 1u << (ori_u * 4 + c);                         // u leaves in orientation ori_u appending c
+		uint32_t emv = 1u << ((1u - ori_v) * 4 + (3u - a));           // v leaves in the flipped orientation appending comp(a)
+		if (isref) { ws.refnode[o + 1] = sv; }
+		else {
+			lb2g_red_add(&ws.g_cnt[sv * 2 + csel], cadd);
+			if (normal) { emv |= LB2_EM_NORMAL; }
+			if (tumor) {
+				bool clean = true;
+				if (track_q) {
+					int wl = lowcnt + lb2_getbit(W.lowq, g);          // window [o, o+K]
+					clean = (wl == 0);
+					lowcnt = wl - lb2_getbit(W.lowq, g0 + o);         // slide to [o+1, o+K]
+				}
+				if (clean) { emu |= LB2_EM_TUMOR; emv |= LB2_EM_TUMOR; }
+			}
+		}
+		pend |= emu;
+		{ const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
+		pend = emv; su = sv; ori_u = ori_v;
+	}
+	if (pend) { const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
 }
 
 // bitonic sort of a[0..n2) ascending, n2 a power of two
@@ -500,14 +605,16 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				const uint32_t np_ = n - K, ob = piece * PL; uint32_t oe = ob + PL; if (oe > np_) { oe = np_; }
 				if (ob < np_) {
 					const uint32_t ib = sh->inst_stride ? r : ws.rd_kbase[r];
-					if (nw == 1) { lb2_walk<1>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
+					if (K <= 16) { lb2_walk_small<uint32_t>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K); }
+					else if (nw == 1) { lb2_walk_small<uint64_t>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K); }
 					else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
 					else { lb2_walk<LB2_MAXW>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
 				}
 			}
 		} else {
 			uint32_t c = it - NP * R, ob = c * PL, oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
-			if (nw == 1) { lb2_walk<1>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
+			if (K <= 16) { lb2_walk_small<uint32_t>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K); }
+			else if (nw == 1) { lb2_walk_small<uint64_t>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K); }
 			else if (nw == 2) { lb2_walk<2>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
 			else { lb2_walk<LB2_MAXW>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
 		}

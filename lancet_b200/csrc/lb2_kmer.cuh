@@ -122,6 +122,22 @@ template <int NWT = LB2_MAXW> LB2_DEV uint64_t lb2_table_hash(const lb2_kmer &k,
 	return ((uint64_t)g << 32) | h;
 }
 
+// table hash of a one-word k-mer (K <= 32): slot from the low bits, fingerprint from the top ten
+LB2_DEV uint32_t lb2_hash1(uint32_t lo, uint32_t hi) {
+	uint32_t h = lo * 0xCC9E2D51u + hi * 0x1B873593u;
+	h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
+	return h;
+}
+// K <= 16 (KT = uint32_t) / K <= 32 (KT = uint64_t) bases starting at base g of the packed array, not yet masked to 2K bits
+template <class KT> LB2_DEV KT lb2_extract_small(lb2_sp bits, uint32_t g) {
+	const uint32_t bp = g << 1, wi = bp >> 5, sh = bp & 31u;
+	const uint32_t w0 = lb2s_ld(lb2_sp_at(bits, wi)), w1 = lb2s_ld(lb2_sp_at(bits, wi + 1));
+	const uint32_t lo = lb2_fsr(w0, w1, sh);
+	if (sizeof(KT) == 4) { return (KT)lo; }
+	const uint32_t w2 = lb2s_ld(lb2_sp_at(bits, wi + 2));
+	return (KT)(((uint64_t)lb2_fsr(w1, w2, sh) << 32) | lo);
+}
+
 // ---- libstdc++ std::hash<std::string> == _Hash_bytes(p, len, 0xc70f6907) (64-bit murmur2 variant)
 // (libstdc++-v3/libsupc++/hash_bytes.cc).  Semantically significant: it
 // fixes the iteration order of the reference's unordered_map<string,Node_t*> (src/Graph.hh:68).

@@ -43,6 +43,17 @@ static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total)
 static inline uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 // ---- sub-warp groups for the read staging (8 lanes per read on the device, 1 in the simulation) ----
 #define LB2_GS 1
+// ---- shared-memory words addressed by a precomputed base (device: 32-bit shared-window address, no generic->shared
+// ---- conversion per access; simulation: a plain pointer) ----
+typedef uint32_t *lb2_sp;
+static inline lb2_sp lb2_sp_of(const void *p) { return (uint32_t *)p; }
+static inline lb2_sp lb2_sp_at(lb2_sp b, uint32_t i) { return b + i; }
+static inline uint32_t lb2s_ldv(lb2_sp a) { return *a; }
+static inline uint32_t lb2s_ld(lb2_sp a) { return *a; }
+static inline uint32_t lb2s_cas(lb2_sp a, uint32_t cmp, uint32_t val) { uint32_t o = *a; if (o == cmp) *a = val; return o; }
+static inline void lb2s_min(lb2_sp a, uint32_t v) { if (v < *a) *a = v; }
+static inline void lb2s_or(lb2_sp a, uint32_t v) { *a |= v; }
+static inline uint32_t lb2_fsr(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31u; return sh ? ((lo >> sh) | (hi << (32u - sh))) : lo; }
 // work items handed out to whole warps: every lane of the warp calls this together and gets its own item index
 static inline uint32_t lb2_batch_next(uint32_t *ctr) { return (*ctr)++; }
 #define LB2_FQ 1      /* lanes per chain in the coverage fold of the parallel compaction (one per channel on the device) */
@@ -106,6 +117,16 @@ LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {
 LB2_DEV uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 // ---- sub-warp groups for the read staging (8 lanes per read) ----
 #define LB2_GS 8
+// ---- shared-memory words addressed by a precomputed 32-bit shared-window address (no generic->shared conversion per access) ----
+typedef uint32_t lb2_sp;
+LB2_DEV lb2_sp lb2_sp_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LB2_DEV lb2_sp lb2_sp_at(lb2_sp b, uint32_t i) { return b + 4u * i; }
+LB2_DEV uint32_t lb2s_ldv(lb2_sp a) { uint32_t o; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(o) : "r"(a) : "memory"); return o; }
+LB2_DEV uint32_t lb2s_ld(lb2_sp a) { uint32_t o; asm("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(a)); return o; }
+LB2_DEV uint32_t lb2s_cas(lb2_sp a, uint32_t cmp, uint32_t val) { uint32_t o; asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(o) : "r"(a), "r"(cmp), "r"(val) : "memory"); return o; }
+LB2_DEV void lb2s_min(lb2_sp a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+LB2_DEV void lb2s_or(lb2_sp a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+LB2_DEV uint32_t lb2_fsr(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 // work items handed out to whole warps (32 consecutive items per fetch): every lane of the warp calls this together
 LB2_DEV uint32_t lb2_batch_next(uint32_t *ctr) {
 	uint32_t base = 0;

@@ -3,7 +3,7 @@
 diff the Variant_t tuples.  Lets control-flow changes to lancet_b200/csrc/*.cuh be checked in the GPU-less
 container before they go to the B200 (the GPU parity tests in tests/ remain the gate).
 
-usage: python tools/sim_parity.py [quick|full]
+usage: python tools/sim_parity.py [quick|full] [min_k,min_k,...]
 """
 import os
 import subprocess
@@ -57,20 +57,23 @@ def main():
     build()
     cases = FULL if (len(sys.argv) > 1 and sys.argv[1] == "full") else QUICK
     bad = 0
-    for kw in cases:
+    ks = [11]
+    if len(sys.argv) > 2:
+        ks = [int(x) for x in sys.argv[2].split(",")]        # extra argument: comma-separated --min-k values (exercises the wider k-mer paths)
+    for mink, kw in [(k, c) for k in ks for c in cases]:
         b = make_batch(**kw)
         with tempfile.TemporaryDirectory() as td:
             p = os.path.join(td, "b.lb2b"); b.save(p)
             t0 = time.time()
-            want, _ = run_ref.run(path=p, threads=8)
+            want, _ = run_ref.run(path=p, threads=8, min_k=mink)
             t1 = time.time()
             out = os.path.join(td, "sim.tsv")
-            r = subprocess.run([SIM, p, "--out", out], capture_output=True, text=True)
+            r = subprocess.run([SIM, p, "--out", out, "--min-k", str(mink)], capture_output=True, text=True)
             t2 = time.time()
             got = run_ref.parse_tsv(open(out).read()) if r.returncode == 0 else None
         ok = got == want
         bad += 0 if ok else 1
-        print(f"{'OK ' if ok else 'BAD'} {kw} windows={b.n_windows} records={len(want)} ref={t1 - t0:.1f}s sim={t2 - t1:.1f}s"
+        print(f"{'OK ' if ok else 'BAD'} k>={mink} {kw} windows={b.n_windows} records={len(want)} ref={t1 - t0:.1f}s sim={t2 - t1:.1f}s"
               + ("" if not r.stderr.strip() else "  [" + r.stderr.strip().splitlines()[0] + (" ..." if len(r.stderr.strip().splitlines()) > 1 else "") + "]"))
         if not ok and got is not None:
             sw, sg = set(want), set(got)
