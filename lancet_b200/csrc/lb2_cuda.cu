@@ -12,12 +12,15 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <thread>
+#include <chrono>
 
 #include "lb2_pipeline.cuh"
 
 struct lb2_launch {
 	lb2_params P; lb2_cfg C; lb2_dev_batch B; lb2_dev_out O;
 	uint8_t *ws_base; size_t ws_stride; uint32_t *counter;
+	const uint32_t *avail;      // streamed lb2_process: windows [0, *avail) have their reads in HBM (NULL: the batch is resident)
 	const uint32_t *win_list; const uint32_t *n_list;   // escalation pass: indices of the windows to redo (NULL = all windows)
 	uint32_t *retry_list; uint32_t *retry_count;
 	// compaction outputs
@@ -46,7 +49,14 @@ lb2_window_kernel(const lb2_launch *Lp)
 	__syncthreads();
 	const uint32_t nwin = Lp->win_list ? *Lp->n_list : Lp->B.n_windows;
 	while (true) {
-		if (threadIdx.x == 0) { s_next = atomicAdd(Lp->counter, 1u); }
+		if (threadIdx.x == 0) {
+			const uint32_t nx = atomicAdd(Lp->counter, 1u);
+			if (Lp->avail && nx < nwin) {      // the read pool is still arriving on the copy stream: wait for this window's watermark
+				while (*(volatile const uint32_t *)Lp->avail <= nx) { __nanosleep(200); }
+				__threadfence_system();
+			}
+			s_next = nx;
+		}
 		__syncthreads();
 		uint32_t w = s_next;
 		__syncthreads();
@@ -113,8 +123,12 @@ __global__ void lb2_gather_kernel(const lb2_launch *Lp)
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#define LB2_MAX_MARKS 1024
 struct lb2_ctx {
 	int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
+	cudaStream_t copy_stream = nullptr; uint32_t *d_avail = nullptr;      // streamed lb2_process
+	cudaEvent_t ev_avail = nullptr; uint32_t *h_marks = nullptr;          // (pinned) per chunk: windows ready
+	std::vector<uint32_t> h_need;                                         // per window: leading pool reads the windows up to it use
 	lb2_params P; lb2_cfg C;
 	int sm_count; uint32_t threads = 256;
 	std::string err;
@@ -185,6 +199,8 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (prop.major < 10) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
+	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&ctx->d_avail, 4) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->ev_avail, cudaEventDisableTiming) != cudaSuccess || cudaHostAlloc((void **)&ctx->h_marks, sizeof(uint32_t) * LB2_MAX_MARKS, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
 	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096); C.max_nodes = C.table_slots - C.table_slots / 4;
@@ -218,12 +234,17 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 	cudaFree(ctx->d_big_count); cudaFree(ctx->d_counter2); cudaFree(ctx->d_retry_count); cudaFree(ctx->d_launch2);
 	cudaFree(ctx->d_counter); cudaFree(ctx->d_totals); cudaFree(ctx->d_launch);
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
+	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); } cudaFree(ctx->d_avail);
+	if (ctx->ev_avail) { cudaEventDestroy(ctx->ev_avail); } if (ctx->h_marks) { cudaFreeHost(ctx->h_marks); }
 	delete ctx;
 }
 
 extern "C" uint64_t lb2_kernel_launches(const lb2_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
+// streamed = false: the whole batch is copied and the call returns when it is resident (lb2_upload).
+// streamed = true (lb2_process): everything except the read pool's bases/qualities is enqueued; h_need[w] = number of
+// leading pool reads the windows [0, w] use, so that the pool can follow in chunks while the kernel already runs.
+static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
 {
 	if (!ctx || !b) { return LB2_ERR_ARG; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
@@ -231,15 +252,33 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	const uint32_t W = b->n_windows, R = b->n_reads;
 	// staging bound: every read rounded up to 32 bases + reference + padding (untrimmed lengths)
 	uint32_t max_bp = 0, max_reads = 0;
-	for (uint32_t w = 0; w < W; ++w) {
-		uint64_t bp = 0;
-		for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
-			uint32_t r = b->wr_idx[x]; if (r >= R) { return LB2_ERR_ARG; }
-			bp += ((b->base_off[r + 1] - b->base_off[r]) + 15) & ~15ull;
-		}
-		bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; bp += 128;
-		if (bp > max_bp) { max_bp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
-		max_reads = std::max(max_reads, b->wr_off[w + 1] - b->wr_off[w]);
+	if (streamed) { ctx->h_need.resize(W); }
+	{
+		// one pass over the windows' read lists (millions of entries for a 1 Mb region): split over a few host threads
+		const unsigned hw = std::thread::hardware_concurrency();
+		const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(hw, 8u), env_u32("LB2_HOST_THREADS", 8)) : 1u;
+		std::vector<uint32_t> t_bp(T, 0), t_rd(T, 0); std::vector<int> t_bad(T, 0);
+		auto work = [&](unsigned t) {
+			const uint32_t w0 = (uint32_t)((uint64_t)W * t / T), w1 = (uint32_t)((uint64_t)W * (t + 1) / T);
+			uint32_t mbp = 0, mrd = 0;
+			for (uint32_t w = w0; w < w1; ++w) {
+				uint64_t bp = 0; uint32_t top = 0;
+				for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
+					const uint32_t r = b->wr_idx[x]; if (r >= R) { t_bad[t] = 1; return; }
+					bp += ((b->base_off[r + 1] - b->base_off[r]) + 15) & ~15ull;
+					if (r >= top) { top = r + 1; }
+				}
+				if (streamed) { ctx->h_need[w] = top; }
+				bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; bp += 128;
+				if (bp > mbp) { mbp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
+				mrd = std::max(mrd, b->wr_off[w + 1] - b->wr_off[w]);
+			}
+			t_bp[t] = mbp; t_rd[t] = mrd;
+		};
+		if (T == 1) { work(0); }
+		else { std::vector<std::thread> th; for (unsigned t = 0; t < T; ++t) { th.emplace_back(work, t); } for (auto &x : th) { x.join(); } }
+		for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); }
+		if (streamed) { uint32_t need = 0; for (uint32_t w = 0; w < W; ++w) { need = std::max(need, ctx->h_need[w]); ctx->h_need[w] = need; } }      // leading pool reads the windows [0, w] use
 	}
 	max_bp = (max_bp + 1023) & ~1023u; if (max_bp < 32768) { max_bp = 32768; }
 	const uint32_t smem_cap = 220u << 10;
@@ -268,16 +307,19 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	uint64_t h2d = 0;
 #define LB2_UP(buf, ptr, bytes) do { int rc_ = lb2_reserve(ctx, ctx->buf, (bytes)); if (rc_) return rc_; \
 		LB2_CK(cudaMemcpyAsync(ctx->buf.p, (ptr), (bytes), cudaMemcpyHostToDevice, ctx->stream)); h2d += (bytes); } while (0)
+	// streamed: only the three per-window offset tables go ahead of the kernels, everything else follows in chunks (lb2_process)
+#define LB2_UPS(buf, ptr, bytes) do { if (!streamed) { LB2_UP(buf, ptr, bytes); } else { int rc2_ = lb2_reserve(ctx, ctx->buf, (bytes)); if (rc2_) return rc2_; h2d += (bytes); } } while (0)
 	LB2_UP(d_ref_off, b->ref_off, sizeof(uint32_t) * (size_t)(W + 1));
 	LB2_UP(d_ref_start, b->ref_start, sizeof(int32_t) * (size_t)W);
 	LB2_UP(d_wr_off, b->wr_off, sizeof(uint32_t) * (size_t)(W + 1));
-	LB2_UP(d_wr_idx, b->wr_idx, sizeof(uint32_t) * (size_t)b->n_wr);
-	LB2_UP(d_base_off, b->base_off, sizeof(uint64_t) * (size_t)(R + 1));
-	LB2_UP(d_flags, b->flags, (size_t)R);
-	LB2_UP(d_name_rank, b->name_rank, sizeof(uint32_t) * (size_t)R);
-	LB2_UP(d_ref_seq, b->ref_seq, (size_t)b->n_ref_bytes);
-	LB2_UP(d_seq, b->seq, (size_t)b->n_base_bytes);
-	LB2_UP(d_qual, b->qual, (size_t)b->n_base_bytes);
+	LB2_UPS(d_wr_idx, b->wr_idx, sizeof(uint32_t) * (size_t)b->n_wr);
+	LB2_UPS(d_base_off, b->base_off, sizeof(uint64_t) * (size_t)(R + 1));
+	LB2_UPS(d_flags, b->flags, (size_t)R);
+	LB2_UPS(d_name_rank, b->name_rank, sizeof(uint32_t) * (size_t)R);
+	LB2_UPS(d_ref_seq, b->ref_seq, (size_t)b->n_ref_bytes);
+	LB2_UPS(d_seq, b->seq, (size_t)b->n_base_bytes);
+	LB2_UPS(d_qual, b->qual, (size_t)b->n_base_bytes);
+#undef LB2_UPS
 #undef LB2_UP
 	ctx->h2d_bytes = h2d;
 	int rc;
@@ -305,7 +347,7 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 	L.O.big_variants = (lb2_variant *)ctx->d_big_vars.p; L.O.big_strings = (char *)ctx->d_big_strs.p; L.O.big_slot = (uint32_t *)ctx->d_big_slot.p;
 	L.O.big_count = ctx->d_big_count; L.O.big_cap = nbig; L.O.big_max_var = ctx->big_max_var; L.O.big_str_bytes = ctx->big_str_bytes;
 	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
-	L.win_list = nullptr; L.n_list = nullptr;
+	L.win_list = nullptr; L.n_list = nullptr; L.avail = streamed ? ctx->d_avail : nullptr;
 	if ((rc = lb2_reserve(ctx, ctx->d_retry, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
 	L.retry_list = (uint32_t *)ctx->d_retry.p; L.retry_count = ctx->d_retry_count;
 	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_totals;
@@ -328,16 +370,18 @@ extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 			LB2_CK(cudaMalloc(&ctx->d_ws2.p, stride2 * C2.n_slots)); ctx->d_ws2.cap = stride2 * C2.n_slots;
 			ctx->ws2_stride = stride2; ctx->ws2_slots = C2.n_slots;
 		}
-		lb2_launch &L2 = ctx->L2; L2 = L; L2.C = C2;
+		lb2_launch &L2 = ctx->L2; L2 = L; L2.C = C2; L2.avail = nullptr;      // (the first pass ends after the last pool chunk has arrived)
 		L2.ws_base = (uint8_t *)ctx->d_ws2.p; L2.ws_stride = stride2; L2.counter = ctx->d_counter2;
 		L2.win_list = (const uint32_t *)ctx->d_retry.p; L2.n_list = ctx->d_retry_count;
 		LB2_CK(cudaMemcpyAsync(ctx->d_launch2, &L2, sizeof L2, cudaMemcpyHostToDevice, ctx->stream));
 		LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(C.smem_bytes, C2.smem_bytes)));
 	}
-	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	if (!streamed) { LB2_CK(cudaStreamSynchronize(ctx->stream)); }
 	ctx->n_windows = W; ctx->resident = true;
 	return LB2_OK;
 }
+
+extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b) { return lb2_upload_impl(ctx, b, false); }
 
 extern "C" int lb2_run(lb2_ctx *ctx)
 {
@@ -391,10 +435,77 @@ extern "C" int lb2_download(lb2_ctx *ctx, lb2_result *res)
 	return LB2_OK;
 }
 
+// Host buffers in, host buffers out.  The window tables go first, the kernels are enqueued behind them, and the read
+// pool (bases + qualities, ~85 % of the bytes) follows on a second stream in chunks; after every chunk a watermark in
+// device memory tells the running kernel how many windows have all their reads in HBM.  Chunk boundaries are 128-byte
+// aligned and a window only counts as ready once 128 bytes past its last read have arrived, so no cache line (and no
+// 16-byte over-read of the staging loads) is ever touched before it is complete.
 extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *result)
 {
-	int rc = lb2_upload(ctx, batch); if (rc) { return rc; }
+	if (!ctx || !batch || !result) { return LB2_ERR_ARG; }
+	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
+	{	// copies from pageable memory do not overlap a running kernel (a kernel waiting for them would wait forever):
+		// the pool is only streamed from page-locked buffers, otherwise the batch is made resident first
+		bool pinned = batch->n_base_bytes > 0 && batch->n_windows > 0 && env_u32("LB2_STREAM", 1) != 0;
+		const void *arrs[] = { batch->seq, batch->qual, batch->base_off, batch->flags, batch->name_rank, batch->wr_idx, batch->ref_seq };
+		const uint64_t sizes[] = { batch->n_base_bytes, batch->n_base_bytes, 1, batch->n_reads, batch->n_reads, batch->n_wr, batch->n_ref_bytes };
+		for (int i = 0; i < 7 && pinned; ++i) {
+			if (!sizes[i]) { continue; }
+			cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, arrs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost) { pinned = false; }
+		}
+		cudaGetLastError();
+		if (!pinned) {
+			int rc0 = lb2_upload_impl(ctx, batch, false); if (rc0) { return rc0; }
+			rc0 = lb2_run(ctx); if (rc0) { return rc0; }
+			return lb2_download(ctx, result);
+		}
+	}
+	const bool timing = env_u32("LB2_TIMING", 0) != 0; const auto t0 = std::chrono::steady_clock::now();
+	// the watermark starts at 0 before the kernel may look at it (same stream as the updates that follow)
+	LB2_CK(cudaMemsetAsync(ctx->d_avail, 0, 4, ctx->copy_stream));
+	LB2_CK(cudaEventRecord(ctx->ev_avail, ctx->copy_stream));
+	LB2_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_avail, 0));
+	int rc = lb2_upload_impl(ctx, batch, true); if (rc) { return rc; }
+	const uint32_t W = ctx->n_windows; const uint64_t nb = batch->n_base_bytes;
+	const auto t1 = std::chrono::steady_clock::now();
 	rc = lb2_run(ctx); if (rc) { return rc; }
+	// chunks of consecutive windows: everything the windows [wa, wb) read -- their reference bases, their read lists, and
+	// the leading part of the pool they use (per-read tables, bases, qualities) -- then the watermark wb.  Every array's
+	// upload boundary is a multiple of 128 bytes, at least 128 bytes past the last byte the ready windows touch.
+	const uint32_t R = batch->n_reads; const uint64_t n_wr = batch->n_wr, n_ref = batch->n_ref_bytes;
+	const uint64_t chunk_max = std::max<uint64_t>((uint64_t)env_u32("LB2_STREAM_CHUNK", 8u << 20), 1u << 16);
+	uint64_t chunk = std::min<uint64_t>(chunk_max, 1u << 20);      // short chunks first: the kernel starts on the first one
+	uint64_t up_by = 0, up_rd = 0, up_bo = 0, up_wr = 0, up_ref = 0; uint32_t wa = 0; size_t c = 0;
+	auto up128 = [](uint64_t x, uint64_t unit, uint64_t cap) { const uint64_t per = 128 / unit; x = (x + per - 1) / per * per; return x > cap ? cap : x; };
+#define LB2_PIECE(buf, ptr, esz, from, to) do { if ((to) > (from)) { LB2_CK(cudaMemcpyAsync((char *)ctx->buf.p + (size_t)(from) * (esz), (const char *)(ptr) + (size_t)(from) * (esz), \
+		(size_t)((to) - (from)) * (esz), cudaMemcpyHostToDevice, ctx->copy_stream)); } } while (0)
+	while (wa < W) {
+		uint32_t wb = wa + 1;
+		if (c + 2 >= LB2_MAX_MARKS) { wb = W; }
+		else { const uint64_t lim = up_by + chunk; while (wb < W && batch->base_off[ctx->h_need[wb]] <= lim) { ++wb; } }
+		const uint64_t rd_t = ctx->h_need[wb - 1];
+		const uint64_t to_by = up128(batch->base_off[rd_t] + 128, 1, nb), to_rd = up128(rd_t + 1, 1, R), to_bo = up128(rd_t + 2, 8, (uint64_t)R + 1);
+		const uint64_t to_wr = up128((uint64_t)batch->wr_off[wb] + 32, 4, n_wr), to_ref = up128((uint64_t)batch->ref_off[wb] + 128, 1, n_ref);
+		LB2_PIECE(d_ref_seq, batch->ref_seq, 1, up_ref, to_ref); if (to_ref > up_ref) { up_ref = to_ref; }
+		LB2_PIECE(d_wr_idx, batch->wr_idx, 4, up_wr, to_wr); if (to_wr > up_wr) { up_wr = to_wr; }
+		LB2_PIECE(d_base_off, batch->base_off, 8, up_bo, to_bo); if (to_bo > up_bo) { up_bo = to_bo; }
+		LB2_PIECE(d_flags, batch->flags, 1, up_rd, to_rd);
+		LB2_PIECE(d_name_rank, batch->name_rank, 4, up_rd, to_rd); if (to_rd > up_rd) { up_rd = to_rd; }
+		LB2_PIECE(d_seq, batch->seq, 1, up_by, to_by);
+		LB2_PIECE(d_qual, batch->qual, 1, up_by, to_by); if (to_by > up_by) { up_by = to_by; }
+		ctx->h_marks[c] = wb;
+		LB2_CK(cudaMemcpyAsync(ctx->d_avail, &ctx->h_marks[c], 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+		++c; wa = wb; chunk = std::min<uint64_t>(chunk_max, chunk * 2);
+	}
+#undef LB2_PIECE
+	const auto t2 = std::chrono::steady_clock::now();
+	LB2_CK(cudaStreamSynchronize(ctx->copy_stream));      // the caller's buffers are free again when the call returns
+	if (timing) {
+		const auto t3 = std::chrono::steady_clock::now(); rc = lb2_download(ctx, result); const auto t4 = std::chrono::steady_clock::now();
+		auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a).count(); };
+		fprintf(stderr, "lb2_process: tables+config %.2f ms, enqueue %.2f ms, pool copies done +%.2f ms, kernels+download +%.2f ms, total %.2f ms (kernels alone %.2f ms)\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t0, t4), (double)result->kernel_ms);
+		return rc;
+	}
 	return lb2_download(ctx, result);
 }
 

@@ -14,7 +14,7 @@ CLI = os.path.join(ROOT, "lancet_b200", "lancet_b200_cli")
 REFCLI = os.path.join(ROOT, "oracle", "_ref", "lancet")
 
 
-def _run(binp, d, args, timeout=900):
+def _run(binp, d, args, timeout=240):
     from lancet_b200.simbam import normalise_vcf
     r = subprocess.run([binp, "--tumor", d["tumor"], "--normal", d["normal"], "--ref", d["ref"]] + args, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]

@@ -130,3 +130,38 @@ def test_properties_large(ctx):
     assert sorted(subp, key=lambda r: r[0]) == want
     # planted variants are recovered: every planted SNV position appears in some record
     assert len(rec1) > 50
+
+
+def _pinned(b):
+    """the batch with its arrays in page-locked host memory (what a caller that wants the copy overlap provides)"""
+    import copy
+    import torch
+    b = copy.copy(b); b._pins = []
+    for name in ("ref_off", "ref_start", "chr_id", "wr_off", "wr_idx", "base_off", "flags", "name_rank", "ref_seq", "seq", "qual"):
+        a = getattr(b, name)
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        v = t.numpy()[:a.nbytes].view(a.dtype); v[...] = a
+        setattr(b, name, v); b._pins.append(t)
+    return b
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_streamed_equals_resident(ctx, monkeypatch):
+    """From page-locked buffers lb2_process streams the read pool in chunks behind the running kernel (windows wait
+    for a watermark); lb2_upload + lb2_run + lb2_download work on a resident batch, and so does lb2_process from
+    pageable memory.  Same records every way, also with tiny chunks (many watermark updates) and with a permuted
+    window order (windows that need late reads come first)."""
+    from lancet_b200.synth import make_batch
+    b = make_batch(seed=52, region_len=30000, var_every=700)
+    ctx.upload(b); ctx.run(); ctx.wait(); res0 = ctx.download(); rec0 = res0.records()
+    assert len(rec0) > 20
+    assert ctx.process(b).records() == rec0                    # pageable: resident path
+    bp = _pinned(b)
+    for chunk in ("65536", "1048576", str(1 << 30)):
+        monkeypatch.setenv("LB2_STREAM_CHUNK", chunk)
+        assert ctx.process(bp).records() == rec0
+    monkeypatch.setenv("LB2_STREAM_CHUNK", "65536")
+    perm = np.random.default_rng(1).permutation(b.n_windows)
+    bq = b.subset(perm)
+    ctx.upload(bq); ctx.run(); ctx.wait(); recp = ctx.download().records()
+    assert ctx.process(_pinned(bq)).records() == recp
