@@ -77,57 +77,51 @@ LB2_DEV uint32_t lb2_nacgt16(const char *s) {                    // bit i: base 
 	return r;
 }
 
-// 2-bit packed bases of the trimmed reads and of the window reference.  The packed bases' shared memory is lent to the
-// order emulation after every build (k-mer strings of the surviving nodes are copied out first), so the bases are
-// staged again before the build of a later k.  Eight lanes per read, one 16-base word each.
-LB2_DEVNI void lb2_stage_bits(lb2_win &W)
+// 2-bit packed bases of the trimmed reads and of the window reference, and the low-quality mask (quality <
+// MIN_QUAL_CALL) of the staged bases.  Both shared-memory areas are lent to the graph stage after every build (k-mer
+// strings of the surviving nodes are copied out first), so they are staged again before the build of a later k.
+// Eight lanes per read, one 16-base word each; the read's length / pool offset / staged position for the NEXT round are
+// fetched while the current round's bases are on their way.
+LB2_DEVNI void lb2_stage_pack(lb2_win &W, bool do_bits, bool do_lowq)
 {
 	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
 	const unsigned tid = lb2_tid(), nt = lb2_nthr();
-	const uint32_t R = sh->R, L = sh->L; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
-	for (uint32_t r = lb2_group(); r < R; r += lb2_ngroups()) {
-		const uint32_t n = ws.rd_len[r]; if (!n) { continue; }
-		const char *s = B->seq + B->base_off[widx[r]] + ws.rd_t5[r];
-		const uint32_t g = ws.rd_start[r];
-		for (uint32_t w = lb2_glane(); w * 16 < n; w += LB2_GS) {
-			uint32_t bw = lb2_codes16(s + w * 16); const uint32_t m = n - w * 16;
-			if (m < 16) { bw &= (1u << (2 * m)) - 1u; }
-			W.bits[(g >> 4) + w] = bw;
-		}
-	}
-	const uint32_t g = sh->ref_g;
-	for (uint32_t b0 = tid * 16; b0 < ((L + 15u) & ~15u) + 64; b0 += nt * 16) {
-		uint32_t bw = 0;
-		for (uint32_t i = 0; i < 16 && b0 + i < L; ++i) { bw |= (uint32_t)(lb2_code(W.ref_raw[b0 + i]) & 3) << (2 * i); }
-		W.bits[(g + b0) >> 4] = bw;
-	}
-	if (tid == 0) { sh->bits_live = 1; }
-	lb2_sync();
-}
-
-// low-quality mask (quality < MIN_QUAL_CALL) of the staged bases.  The mask's shared memory is lent to the
-// graph stage after every build, so it is staged again before the build of a later k.
-LB2_DEVNI void lb2_stage_lowq(lb2_win &W)
-{
-	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
-	const unsigned tid = lb2_tid(), nt = lb2_nthr();
-	const uint32_t R = sh->R; const uint32_t *widx = B->wr_idx + B->wr_off[sh->w];
+	const uint32_t R = sh->R, L = sh->L;
 	const uint32_t qc = (uint32_t)W.P->min_qual_call & 0xFFu, qcall4 = qc * 0x01010101u;
-	for (uint32_t i = tid; i < (sh->total_bp >> 5) + 4; i += nt) { W.lowq[i] = 0; }
-	lb2_sync();
-	for (uint32_t r = lb2_group(); r < R; r += lb2_ngroups()) {
-		const uint32_t n = ws.rd_len[r]; if (!n) { continue; }
-		const char *q = B->qual + B->base_off[widx[r]] + ws.rd_t5[r];
-		const uint32_t g = ws.rd_start[r];      // reads start on 16-base boundaries: two words of a read share a mask word
-		for (uint32_t w = lb2_glane(); w * 16 < n; w += LB2_GS) {
-			uint32_t lw = lb2_low16(q + w * 16, qcall4); const uint32_t m = n - w * 16;
-			if (m < 16) { lw &= (1u << m) - 1u; }
-			if (lw) { lb2_or32(&W.lowq[(g + w * 16) >> 5], lw << ((g + w * 16) & 31)); sh->has_lowq = 1; }
+	if (do_lowq) { for (uint32_t i = tid; i < (sh->total_bp >> 5) + 4; i += nt) { W.lowq[i] = 0; } lb2_sync(); }
+	const uint32_t ng = lb2_ngroups(), gl = lb2_glane();
+	uint32_t r = lb2_group();
+	uint32_t n_n = 0, g_n = 0; uint64_t src_n = 0;
+	if (r < R) { n_n = ws.rd_len[r]; g_n = ws.rd_start[r]; src_n = ws.rd_src[r]; }
+	for (; r < R; r += ng) {
+		const uint32_t n = n_n, g = g_n; const uint64_t src = src_n;
+		if (r + ng < R) { n_n = ws.rd_len[r + ng]; g_n = ws.rd_start[r + ng]; src_n = ws.rd_src[r + ng]; }
+		if (!n) { continue; }
+		for (uint32_t w = gl; w * 16 < n; w += LB2_GS) {
+			const uint32_t m = n - w * 16;
+			uint32_t bw = 0, lw = 0;
+			if (do_bits) { bw = lb2_codes16(B->seq + src + w * 16); }
+			if (do_lowq) { lw = lb2_low16(B->qual + src + w * 16, qcall4); }
+			if (do_bits) { if (m < 16) { bw &= (1u << (2 * m)) - 1u; } W.bits[(g >> 4) + w] = bw; }
+			if (do_lowq) {      // reads start on 16-base boundaries: two words of a read share a mask word
+				if (m < 16) { lw &= (1u << m) - 1u; }
+				if (lw) { lb2_or32(&W.lowq[(g + w * 16) >> 5], lw << ((g + w * 16) & 31)); sh->has_lowq = 1; }
+			}
 		}
 	}
-	if (tid == 0) { sh->lowq_live = 1; }
+	if (do_bits) {
+		const uint32_t g = sh->ref_g;
+		for (uint32_t b0 = tid * 16; b0 < ((L + 15u) & ~15u) + 64; b0 += nt * 16) {
+			uint32_t bw = 0;
+			for (uint32_t i = 0; i < 16 && b0 + i < L; ++i) { bw |= (uint32_t)(lb2_code(W.ref_raw[b0 + i]) & 3) << (2 * i); }
+			W.bits[(g + b0) >> 4] = bw;
+		}
+	}
+	if (tid == 0) { if (do_bits) { sh->bits_live = 1; } if (do_lowq) { sh->lowq_live = 1; } }
 	lb2_sync();
 }
+LB2_DEV void lb2_stage_bits(lb2_win &W) { lb2_stage_pack(W, true, false); }
+LB2_DEV void lb2_stage_lowq(lb2_win &W) { lb2_stage_pack(W, false, true); }
 
 // ---------------------------------------------------------------------------------------------
 // stage the window: trim every read, pack bases/low-quality mask into shared memory
@@ -161,10 +155,17 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 	// or a non-ACGT base strictly between them.  (All lanes of a warp run the same number of rounds: the group
 	// reductions are warp shuffles.)
 	const uint32_t ng = lb2_ngroups(), grp = lb2_group(), gl = lb2_glane();
+	// (the read index of round i+2 and the pool offsets of round i+1 are fetched during round i: the chain
+	// read list -> offset table -> bases would otherwise cost three memory latencies per round)
+	uint32_t idx_n = (grp < R) ? widx[grp] : 0u, idx_nn = (grp + ng < R) ? widx[grp + ng] : 0u;
+	uint64_t o0_n = 0, o1_n = 0; if (grp < R) { o0_n = B->base_off[idx_n]; o1_n = B->base_off[idx_n + 1]; }
 	for (uint32_t r0 = 0; r0 < R; r0 += ng) {
 		const uint32_t r = r0 + grp; const bool act = r < R;
-		uint32_t idx = 0, len = 0; const char *s = nullptr, *q = nullptr;
-		if (act) { idx = widx[r]; const uint64_t o0 = B->base_off[idx]; len = (uint32_t)(B->base_off[idx + 1] - o0); s = B->seq + o0; q = B->qual + o0; }
+		const uint32_t idx = idx_n; const uint64_t o0 = o0_n; const uint32_t len = act ? (uint32_t)(o1_n - o0_n) : 0u;
+		const char *s = B->seq + o0, *q = B->qual + o0;
+		idx_n = idx_nn; if (r + ng < R) { o0_n = B->base_off[idx_n]; o1_n = B->base_off[idx_n + 1]; }
+		idx_nn = (r + 2 * ng < R) ? widx[r + 2 * ng] : 0u;
+		uint32_t fl_v = 0, rk_v = 0; if (act && gl == 0) { fl_v = B->flags[idx]; rk_v = B->name_rank[idx]; }      // (used at the end of the round)
 		const uint32_t nch = (len + 15u) >> 4;
 		uint32_t first = 0xFFFFFFFFu, last = 0, my_nac = 0, my_c = 0xFFFFFFFFu;      // last = index of the last good base + 1
 		for (uint32_t c = gl; c < nch; c += LB2_GS) {
@@ -185,14 +186,14 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		}
 		junk = lb2_gor(junk);
 		if (act && gl == 0) {
-			const uint8_t fl = B->flags[idx];
+			const uint8_t fl = (uint8_t)fl_v;
 			int n = junk ? 0 : (int)(last - first); const uint32_t t5 = junk ? len : first;
 			if (n > 4095) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_READS); n = 0; }
-			ws.rd_len[r] = (uint32_t)n; ws.rd_t5[r] = t5;
+			ws.rd_len[r] = (uint32_t)n; ws.rd_t5[r] = t5; ws.rd_src[r] = o0 + t5;
 			uint32_t cls = ((fl & LB2_READ_NORMAL) ? 2u : 0u) | ((fl & LB2_READ_REVERSE) ? 1u : 0u);
 			uint32_t mate = (fl >> LB2_READ_MATE_SHIFT) & 3u;
 			ws.rd_info[r] = cls | (mate << 2);
-			ws.rd_rank[r] = B->name_rank[idx];
+			ws.rd_rank[r] = rk_v;
 			if (!(fl & LB2_READ_UNMAPPED)) { sh->mapped = 1; }
 			if (n) { lb2_add32(&sh->totalreadbp, (uint32_t)n); }
 		}
@@ -232,9 +233,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		}
 		lb2_sync();
 	}
-	lb2_stage_bits(W);
-	lb2_stage_lowq(W);
-	lb2_sync();
+	lb2_stage_pack(W, true, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,31 +263,33 @@ template <class KT> LB2_DEV uint32_t lb2_foi_small(lb2_win &W, lb2_sp tk, lb2_sp
 	const uint32_t h = lb2_hash1((uint32_t)canon, sizeof(KT) > 4 ? (uint32_t)((uint64_t)canon >> 32) : 0u);
 	uint32_t i = h & mask;
 	const uint32_t fp = 0x80000000u | ((h >> 22) << 21);
+	// one exit (the loop's end): the lanes of a warp leave the probe sequence at different times and meet again right
+	// behind it, instead of each carrying its own copy of the caller's continuation
+	uint32_t res = LB2_NIL; bool full = true;
 	for (uint32_t probes = 0; probes <= mask; ++probes) {
 		const lb2_sp at = lb2_sp_at(tk, i);
 		uint32_t cur = lb2s_ldv(at);
 		if (cur == 0) {
-			if (!insert) { return LB2_NIL; }
-			const uint32_t prev = lb2s_cas(at, 0u, fp | rep);
-			if (prev == 0) {
+			if (!insert) { full = false; break; }
+			cur = lb2s_cas(at, 0u, fp | rep);
+			if (cur == 0) {      // this lane created the slot
 				uint32_t u = lb2_add32(&W.sh->n_used, 1u);
 				if (u < W.C->max_nodes && u < (mask + 1) - ((mask + 1) >> 2)) { W.ws.used[u] = i; } else { lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL); }
-				return i;
+				res = i; full = false; break;
 			}
-			cur = prev;
 		}
 		if ((cur & 0xFFE00000u) == fp) {
 			const uint32_t r = cur & 0x1FFFFFu;
 			const KT o = lb2_extract_small<KT>(bits, r >> 1) & kmask;
 			if (o == ((r & 1u) ? nonc : canon)) {
 				if (insert && rep < r) { lb2s_min(at, fp | rep); }      // same k-mer => same fingerprint: the word orders by rep
-				return i;
+				res = i; full = false; break;
 			}
 		}
 		i = (i + 1) & mask;
 	}
-	lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL);
-	return LB2_NIL;
+	if (full) { lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL); }
+	return res;
 }
 
 template <int NWT = LB2_MAXW> LB2_DEV uint32_t lb2_find_or_insert(lb2_win &W, const lb2_kmer &canon, const lb2_kmer &nonc, uint32_t rep, int K, int nw, bool insert)
@@ -394,8 +395,9 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 
 // the same work item for one-word k-mers: little-endian f / rc for the table, big-endian copies so that the reference's
 // string comparison mer < rc is one integer compare; one mask update per k-mer (the bits a k-mer receives as the v of one
-// pair and as the u of the next are merged)
-template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, uint32_t g0, uint32_t n, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
+// pair and as the u of the next are merged).  Warp-converged: EVERY lane of the warp calls it (active = false: no item),
+// the pair loop runs to the warp's longest piece with the lanes re-joined at the top of every round.
+template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_t g0, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
                       bool isref, uint32_t cls, int K)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
@@ -404,29 +406,37 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, uint32_t g0, uint32_
 	const int topsh = 2 * (K - 1); const KT kmask = (KT)(~(KT)0) >> (sizeof(KT) * 8 - 2 * K);
 	KT f = 0, rc = 0, fB = 0, rcB = 0;
 	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
-	for (int i = 0; i < K; ++i, ++g) {          // first K bases
-		if ((g & 15) == 0 || i == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
-		const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
-		f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
-		fB = ((fB << 2) | (KT)c) & kmask; rcB = (rcB >> 2) | ((KT)(3u - c) << topsh);
+	if (active) {
+		for (int i = 0; i < K; ++i, ++g) {          // first K bases
+			if ((g & 15) == 0 || i == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
+			const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
+			f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
+			fB = ((fB << 2) | (KT)c) & kmask; rcB = (rcB >> 2) | ((KT)(3u - c) << topsh);
+		}
 	}
 	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
-	const bool track_q = tumor && sh->has_lowq;
+	const bool track_q = active && tumor && sh->has_lowq;
 	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u, csel = cls >> 1;
 	int lowcnt = 0;    // low-quality bases in [o, o+K-1]; the pair window adds base o+K
 	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
 	bool fless = fB < rcB;
-	uint32_t ori_u = fless ? 0u : 1u;
-	uint32_t su = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, kmask, true);
-	if (su == LB2_NIL) { return; }
-	ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
-	uint32_t pend = 0;      // mask bits owed to su
-	if (isref) { ws.refnode[o_begin] = su; }
-	else if (o_begin == 0) {
-		lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
-		if (normal) { pend = LB2_EM_NORMAL; }
+	uint32_t ori_u = fless ? 0u : 1u, su = LB2_NIL, pend = 0;      // pend: mask bits owed to su
+	if (active) {
+		su = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, kmask, true);
+		if (su != LB2_NIL) {
+			ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
+			if (isref) { ws.refnode[o_begin] = su; }
+			else if (o_begin == 0) {
+				lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
+				if (normal) { pend = LB2_EM_NORMAL; }
+			}
+		}
 	}
-	for (uint32_t o = o_begin; o < o_end; ++o, ++g) {
+	const uint32_t nsteps = (active && su != LB2_NIL) ? (o_end - o_begin) : 0u, maxsteps = lb2_warp_max(nsteps);
+	uint32_t o = o_begin;
+	for (uint32_t st = 0; st < maxsteps; ++st) {
+		lb2_warp_sync();
+		if (st >= nsteps || su == LB2_NIL) { continue; }
 		if ((g & 15) == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
 		const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
 		const uint32_t a = (uint32_t)f & 3u;                           // base that leaves the window (first base of u)
@@ -435,29 +445,31 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, uint32_t g0, uint32_
 		fless = fB < rcB;
 		const uint32_t ori_v = fless ? 0u : 1u;
 		const uint32_t sv = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, kmask, true);
-		if (sv == LB2_NIL) { return; }
-		ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
 		uint32_t emu = 1u << (ori_u * 4 + c);                         // u leaves in orientation ori_u appending c
 		uint32_t emv = 1u << ((1u - ori_v) * 4 + (3u - a));           // v leaves in the flipped orientation appending comp(a)
-		if (isref) { ws.refnode[o + 1] = sv; }
-		else {
-			lb2g_red_add(&ws.g_cnt[sv * 2 + csel], cadd);
-			if (normal) { emv |= LB2_EM_NORMAL; }
-			if (tumor) {
-				bool clean = true;
-				if (track_q) {
-					int wl = lowcnt + lb2_getbit(W.lowq, g);          // window [o, o+K]
-					clean = (wl == 0);
-					lowcnt = wl - lb2_getbit(W.lowq, g0 + o);         // slide to [o+1, o+K]
+		if (sv != LB2_NIL) {
+			ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
+			if (isref) { ws.refnode[o + 1] = sv; }
+			else {
+				lb2g_red_add(&ws.g_cnt[sv * 2 + csel], cadd);
+				if (normal) { emv |= LB2_EM_NORMAL; }
+				if (tumor) {
+					bool clean = true;
+					if (track_q) {
+						int wl = lowcnt + lb2_getbit(W.lowq, g);          // window [o, o+K]
+						clean = (wl == 0);
+						lowcnt = wl - lb2_getbit(W.lowq, g0 + o);         // slide to [o+1, o+K]
+					}
+					if (clean) { emu |= LB2_EM_TUMOR; emv |= LB2_EM_TUMOR; }
 				}
-				if (clean) { emu |= LB2_EM_TUMOR; emv |= LB2_EM_TUMOR; }
 			}
-		}
-		pend |= emu;
-		{ const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
-		pend = emv; su = sv; ori_u = ori_v;
+			pend |= emu;
+			{ const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
+			pend = emv;
+		} else { pend = 0; }      // (table full: the window is redone by the escalation pass)
+		su = sv; ori_u = ori_v; ++o; ++g;
 	}
-	if (pend) { const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
+	if (pend && su != LB2_NIL) { const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
 }
 
 // bitonic sort of a[0..n2) ascending, n2 a power of two
@@ -518,31 +530,40 @@ template <int NWT = LB2_MAXW> LB2_DEV void lb2_rep_kmer(lb2_win &W, uint32_t rep
 	if (rep & 1) { lb2_kmer t; lb2_revcomp<NWT>(km, K, t); km = lb2_pick<NWT>(true, t, t); }
 }
 
-// edges of one surviving node: every edge type (start orientation, appended base) names one neighbour
-template <int NWT> LB2_DEV void lb2_node_edges(lb2_win &W, uint32_t j, int K, int nw)
+// edges of one surviving node: every edge type (start orientation, appended base) names one neighbour.  A group of
+// LB2_GS lanes per node, one edge type each (all lanes of a warp call this together; act = false: no node)
+template <int NWT> LB2_DEV void lb2_node_edges(lb2_win &W, bool act, uint32_t j, int K, int nw)
 {
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
-	uint32_t em = ws.g_em[j] & 0xFFu;
-	lb2_kmer C0; lb2_rep_kmer<NWT>(W, ws.b_rep[j], K, C0);
-	lb2_kmer C1; lb2_revcomp<NWT>(C0, K, C1);
-	int ne = 0, nF = 0, nR = 0;
-	for (int t = 0; t < 8; ++t) {
-		if (!(em & (1u << t))) { continue; }
-		int o = t >> 2, b = t & 3;
-		lb2_kmer V = lb2_pick<NWT>(o != 0, C1, C0); lb2_roll_fwd<NWT>(V, K, b);
-		lb2_kmer Vr; lb2_revcomp<NWT>(V, K, Vr);
-		bool fl = lb2_less<NWT>(V, Vr, nw);
-		uint32_t ts = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fl, V, Vr), lb2_pick<NWT>(fl, Vr, V), 0, K, nw, false);
-		if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); break; }
-		uint32_t to = W.t_id[ts] & 0x7FFFu;
-		if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
-		lb2_bedge ed; ed.to = to; ed.dir = (uint32_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.type = (uint32_t)t;
-		ws.b_edge[(size_t)j * LB2_BECAP + ne] = ed; ++ne; if (o) { ++nR; } else { ++nF; }
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const uint32_t gl = lb2_glane();
+	uint32_t livemask = 0; lb2_bedge edl[8 / LB2_GS];
+	if (act) {
+		const uint32_t em = ws.g_em[j] & 0xFFu;
+		lb2_kmer C0; lb2_rep_kmer<NWT>(W, ws.b_rep[j], K, C0);
+		lb2_kmer C1; lb2_revcomp<NWT>(C0, K, C1);
+		for (uint32_t t = gl; t < 8; t += LB2_GS) {
+			if (!(em & (1u << t))) { continue; }
+			const int o = (int)(t >> 2), b = (int)(t & 3);
+			lb2_kmer V = lb2_pick<NWT>(o != 0, C1, C0); lb2_roll_fwd<NWT>(V, K, b);
+			lb2_kmer Vr; lb2_revcomp<NWT>(V, K, Vr);
+			bool fl = lb2_less<NWT>(V, Vr, nw);
+			uint32_t ts = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fl, V, Vr), lb2_pick<NWT>(fl, Vr, V), 0, K, nw, false);
+			if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); continue; }
+			uint32_t to = W.t_id[ts] & 0x7FFFu;
+			if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
+			lb2_bedge ed; ed.to = to; ed.dir = (uint32_t)(o * 2 + (fl ? 0 : 1)); ed.flag = 0; ed.type = t;
+			edl[t / LB2_GS] = ed; livemask |= 1u << t;
+		}
 	}
-	ws.b_ne[j] = (uint8_t)ne;
+	livemask = lb2_gor(livemask);      // the node's live edge types; edges are stored in type order
+	if (!act) { return; }
+	for (uint32_t t = gl; t < 8; t += LB2_GS) {
+		if (livemask & (1u << t)) { ws.b_edge[(size_t)j * LB2_BECAP + (uint32_t)lb2_popc32(livemask & ((1u << t) - 1u))] = edl[t / LB2_GS]; }
+	}
+	const int nF = lb2_popc32(livemask & 0x0Fu), nR = lb2_popc32(livemask & 0xF0u);
+	if (gl == 0) { ws.b_ne[j] = (uint8_t)(nF + nR); }
 	if (nF > 1 || nR > 1) {   // first-seen order matters only among edges leaving in the same orientation
-		ws.b_flags[j] |= 0x20; sh->flag_a = 1;      // slot's branch bit is set after the barrier (t_id is being read by other lanes)
-		for (int t = 0; t < 8; ++t) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
+		if (gl == 0) { ws.b_flags[j] |= 0x20; sh->flag_a = 1; }      // slot's branch bit is set after the barrier (t_id is being read by other lanes)
+		for (uint32_t t = gl; t < 8; t += LB2_GS) { ws.bseq[(size_t)j * 8 + t] = 0xFFFFFFFFu; }
 	}
 }
 
@@ -597,26 +618,24 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	while (true) {
 		const uint32_t it = lb2_batch_next(&sh->walk_next);
 		if (it >= ((nitems + 31u) & ~31u)) { break; }
-		if (it >= nitems) { continue; }
+		// this lane's item (none: active = false; the one-word walks are called by all lanes of the warp together)
+		bool active = false, isref = false; uint32_t g0 = 0, n = 0, ob = 0, oe = 0, ib = 0, st = 1, cls = 0;
 		if (it < NP * R) {
 			const uint32_t piece = it / R, r = it - piece * R;
-			const uint32_t n = ws.rd_len[r];
+			n = ws.rd_len[r];
 			if (n > (uint32_t)K) {
-				const uint32_t np_ = n - K, ob = piece * PL; uint32_t oe = ob + PL; if (oe > np_) { oe = np_; }
-				if (ob < np_) {
-					const uint32_t ib = sh->inst_stride ? r : ws.rd_kbase[r];
-					if (K <= 16) { lb2_walk_small<uint32_t>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K); }
-					else if (nw == 1) { lb2_walk_small<uint64_t>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K); }
-					else if (nw == 2) { lb2_walk<2>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
-					else { lb2_walk<LB2_MAXW>(W, ws.rd_start[r], n, ob, oe, ib, istr, false, ws.rd_info[r] & 3u, K, nw); }
-				}
+				const uint32_t np_ = n - K; ob = piece * PL; oe = ob + PL; if (oe > np_) { oe = np_; }
+				if (ob < np_) { active = true; g0 = ws.rd_start[r]; ib = sh->inst_stride ? r : ws.rd_kbase[r]; st = istr; cls = ws.rd_info[r] & 3u; }
 			}
-		} else {
-			uint32_t c = it - NP * R, ob = c * PL, oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
-			if (K <= 16) { lb2_walk_small<uint32_t>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K); }
-			else if (nw == 1) { lb2_walk_small<uint64_t>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K); }
-			else if (nw == 2) { lb2_walk<2>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
-			else { lb2_walk<LB2_MAXW>(W, sh->ref_g, L, ob, oe, sh->inst_ref, 1u, true, 0, K, nw); }
+		} else if (it < nitems) {
+			ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
+			active = true; isref = true; g0 = sh->ref_g; n = L; ib = sh->inst_ref; st = 1u;
+		}
+		if (K <= 16) { lb2_walk_small<uint32_t>(W, active, g0, ob, oe, ib, st, isref, cls, K); }
+		else if (nw == 1) { lb2_walk_small<uint64_t>(W, active, g0, ob, oe, ib, st, isref, cls, K); }
+		else if (active) {
+			if (nw == 2) { lb2_walk<2>(W, g0, n, ob, oe, ib, st, isref, cls, K, nw); }
+			else { lb2_walk<LB2_MAXW>(W, g0, n, ob, oe, ib, st, isref, cls, K, nw); }
 		}
 	}
 	lb2_sync();
@@ -769,9 +788,15 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	}
 	lb2_sync();
 	// ---- edges of the survivors: every edge type (start orientation, appended base) names one neighbour
-	for (uint32_t j = tid; j < n; j += nt) {
-		if (ws.b_flags[j] & LB2_NF_DEAD) { continue; }
-		if (nw == 1) { lb2_node_edges<1>(W, j, K, nw); } else if (nw == 2) { lb2_node_edges<2>(W, j, K, nw); } else { lb2_node_edges<LB2_MAXW>(W, j, K, nw); }
+	{
+		uint32_t *slist = (uint32_t *)ws.sortk;      // the survivors (the sort keys are idle by now)
+		const uint32_t nlive = lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return (ws.b_flags[j] & LB2_NF_DEAD) ? 0u : 1u; },
+		                                     [&](uint32_t j, uint32_t v) { if (!(ws.b_flags[j] & LB2_NF_DEAD)) { slist[v] = j; } });
+		const uint32_t ng = lb2_ngroups(), grp = lb2_group();
+		for (uint32_t j0 = 0; j0 < nlive; j0 += ng) {
+			const bool act = j0 + grp < nlive; const uint32_t j = act ? slist[j0 + grp] : 0u;
+			if (nw == 1) { lb2_node_edges<1>(W, act, j, K, nw); } else if (nw == 2) { lb2_node_edges<2>(W, act, j, K, nw); } else { lb2_node_edges<LB2_MAXW>(W, act, j, K, nw); }
+		}
 	}
 	lb2_sync();
 	if (sh->flag_a && !sh->err) {

@@ -731,11 +731,10 @@ LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
 		uint32_t leftlen = 0;
 		for (uint32_t c = nF; c < nAll; ++c) { leftlen += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
 		jb.leftlen = leftlen;
-		// (cpos is relative to the seed's left end: F entries start at leftlen + cpos, R entries at leftlen - cpos)
-		uint32_t pos = len0;
-		for (uint32_t c = 0; c < nF; ++c) { ws.cpos[cused + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
-		pos = 0;
-		for (uint32_t c = nF; c < nAll; ++c) { pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; ws.cpos[cused + c] = pos; }
+		// (cpos: k-mers absorbed before the entry, in chain order -- F entries then R entries; lb2_materialize turns that
+		// into positions: F entry at leftlen + len0 + cpos, R entry ending at leftlen - (cpos - cpos[first R entry]))
+		uint32_t pos = 0;
+		for (uint32_t c = 0; c < nAll; ++c) { ws.cpos[cused + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
 		ws.d_mincov[p] = 10000000; ws.d_mincovqv[p] = 10000000;
 		jobs[njobs++] = jb; cused += nAll;
 	}
@@ -758,8 +757,8 @@ LB2_DEVNI void lb2_materialize(lb2_win &W) {
 			if (m == jb.nAll) { id = jb.node; flip = false; first = 0; count = jb.len0; dst = jb.leftlen; }
 			else {
 				uint32_t ce = ws.chain[jb.cbeg + m]; id = ce & 0x7FFFFFFFu; flip = (ce >> 31) != 0;
-				uint32_t bl = ws.d_len[id]; count = bl - K + 1; const uint32_t rel = ws.cpos[jb.cbeg + m];
-				dst = (m < jb.nF) ? jb.leftlen + rel : jb.leftlen - rel;
+				uint32_t bl = ws.d_len[id]; count = bl - K + 1; const uint32_t pre = ws.cpos[jb.cbeg + m] - ws.cpos[jb.cbeg];
+				dst = (m < jb.nF) ? jb.leftlen + jb.len0 + pre : jb.leftlen - (pre - (ws.cpos[jb.cbeg + jb.nF] - ws.cpos[jb.cbeg]) + count);
 				first = (m < jb.nF) ? (uint32_t)K - 1 : 0;       // F: oriented[K-1..], R: frame[0..bl-K]
 			}
 			lb2_nview v; lb2_view(W, id, v);
@@ -895,8 +894,8 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 #ifdef LB2_HOSTSIM
 	if (getenv("LB2_SIM_NOPAR")) { LB2_DBG(1); return false; }
 #endif
-	if ((size_t)NT * 4 + 8 > ws.px_words || (W.C->debug_flags & 1u)) { LB2_DBG(1); return false; }
-	uint32_t *J = ws.px, *SEED = J + 2 * NT, *INF = SEED + NT;
+	if ((size_t)NT * 5 + 16 > ws.px_words || (W.C->debug_flags & 1u)) { LB2_DBG(1); return false; }
+	uint32_t *J = ws.px, *SEED = J + 2 * NT, *INF = SEED + NT; float *RCP = (float *)(INF + NT);
 	lb2_edge *etmp = ws.etmp; uint8_t *etn = (uint8_t *)(ws.etmp + (size_t)LB2_MAX_ROWS * LB2_ECAP);
 	lb2_job *jobs = (lb2_job *)ws.jobs;
 	// eligibility (d_color is idle between the cycle checks)
@@ -966,40 +965,57 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 	lb2_sync();
 	// fold the float coverages in the reference's absorb order (src/Graph.cc:2631-2636): a serial recurrence per chain and
 	// channel (every step rounds), so one lane per (chain, channel); the integer bookkeeping rides along in every lane
+	// cpos[slot] = k-mers absorbed before the slot (prefix over ALL chain slots; a job's own prefix is the difference to
+	// its first slot), one more entry for the total; RCP[slot] = correctly rounded reciprocal of the slot's divisor
+	const uint32_t totc = tot & 0xFFFFu;
 	{
+		const uint32_t K1 = (uint32_t)K - 1u;
+		const uint32_t tk_ = lb2_excl_scan(W, totc, [&](uint32_t x) -> uint32_t { return (uint32_t)ws.d_len[ws.chain[x] & 0x7FFFFFFFu] - K1; }, [&](uint32_t x, uint32_t v) { ws.cpos[x] = v; });
+		if (tid == 0) { ws.cpos[totc] = tk_; }
+		lb2_sync();
+		for (uint32_t x = tid; x < totc; x += nt) {
+			const uint32_t b = ws.chain[x] & 0x7FFFFFFFu, sd = INF[b] & 0xFFFFu, cbeg = SEED[sd] & 0xFFFFu;
+			RCP[x] = lb2_rcp_int((uint32_t)ws.d_len[sd] - K1 + (ws.cpos[x + 1] - ws.cpos[cbeg]));
+			lb2g_red_add(&jobs[SEED[sd] >> 16].pad, (uint32_t)ws.d_stn[b] | ((uint32_t)ws.d_stT[b] << 16));      // status counts of the absorbed nodes (sums < 2^16)
+		}
+		lb2_sync();
+	}
+	lb2_mark(W, LB2_PH_CP_LINK);
+	{
+		// fold the float coverages in the reference's absorb order (src/Graph.cc:2631-2636): a serial recurrence per chain
+		// and channel (every step rounds), so one lane per (chain, channel).  Only product, sum and the division's three
+		// fused corrections depend on the running value; everything else of a step is loaded / converted one step ahead.
 		// (array bases in registers: the descriptor lives in shared memory and would be re-read after every store)
-		const uint16_t *const LEN = ws.d_len, *const STN = ws.d_stn, *const STT = ws.d_stT; const float *const COV = ws.d_cov;
-		uint32_t *const CPOS = ws.cpos; const int K1 = K - 1;
+		const uint16_t *const LEN = ws.d_len; const float *const COV = ws.d_cov;
+		const uint32_t *const CPOS = ws.cpos; const int K1 = K - 1;
 		for (uint32_t q = tid / LB2_FQ; q < njobs; q += nt / LB2_FQ) {
 			const lb2_job jb = jobs[q]; const uint32_t node = jb.node, nAll = jb.nAll, nF = jb.nF; const uint32_t *const chain = ws.chain + jb.cbeg;
+			const uint32_t *const P = CPOS + jb.cbeg; const float *const RC = RCP + jb.cbeg;
 			for (uint32_t ch = tid % LB2_FQ; ch < 4; ch += LB2_FQ) {
 				float cv = COV[node * 4 + ch];
-				uint32_t stn = STN[node], stt = STT[node], curlen = jb.len0, leftlen = 0;
-				int amerlen = (int)jb.len0 - K1;
-				// software pipeline: the entry of step c was loaded during step c-1, the node id of step c+1 during step c-1
+				int am = (int)jb.len0 - K1;
 				uint32_t b1 = nAll ? (chain[0] & 0x7FFFFFFFu) : 0u;
-				uint32_t len_c = LEN[b1], sn_c = STN[b1], st_c = STT[b1]; float cov_c = COV[b1 * 4 + ch];
+				uint32_t len_c = LEN[b1]; float cov_c = COV[b1 * 4 + ch], r_c = RC[0];
 				b1 = (nAll > 1) ? (chain[1] & 0x7FFFFFFFu) : 0u;
 				for (uint32_t c = 0; c < nAll; ++c) {
-					const uint32_t len_n = LEN[b1], sn_n = STN[b1], st_n = STT[b1]; const float cov_n = COV[b1 * 4 + ch];      // step c+1 (a harmless re-read at the end)
+					const uint32_t len_n = LEN[b1]; const float cov_n = COV[b1 * 4 + ch], r_n = RC[(c + 1 < nAll) ? c + 1 : c];
 					const uint32_t b2 = (c + 2 < nAll) ? (chain[c + 2] & 0x7FFFFFFFu) : 0u;
 					const int bm = (int)len_c - K1;
-					cv = lb2_wavg(cv, amerlen, cov_c, bm);
-					CPOS[jb.cbeg + c] = (c < nF) ? curlen : leftlen + (uint32_t)bm;      // relative to the seed's left end, see lb2_materialize (same value from every channel's lane)
-					amerlen += bm; curlen += (uint32_t)bm; stn += sn_c; stt += st_c;
-					if (c >= nF) { leftlen += (uint32_t)bm; }
-					len_c = len_n; sn_c = sn_n; st_c = st_n; cov_c = cov_n; b1 = b2;
+					cv = lb2_wavg_rcp(cv, am, cov_c, bm, r_c);
+					am += bm;
+					len_c = len_n; cov_c = cov_n; r_c = r_n; b1 = b2;
 				}
 				ws.d_cov[node * 4 + ch] = cv;
 				if (ch == 0) {
-					ws.d_stn[node] = (uint16_t)stn; ws.d_stT[node] = (uint16_t)stt;
+					ws.d_stn[node] = (uint16_t)(ws.d_stn[node] + (jb.pad & 0xFFFFu)); ws.d_stT[node] = (uint16_t)(ws.d_stT[node] + (jb.pad >> 16));
 					ws.d_mincov[node] = 10000000; ws.d_mincovqv[node] = 10000000;
-					jobs[q].curlen = curlen; jobs[q].leftlen = leftlen;
+					jobs[q].curlen = jb.len0 + (P[nAll] - P[0]); jobs[q].leftlen = P[nAll] - P[nF];
 				}
 			}
 		}
 	}
 	lb2_sync();
+	lb2_mark(W, LB2_PH_CP_FOLD);
 	if (tid == 0) {
 		for (uint32_t q = 0; q < njobs && !sh->err; ++q) { jobs[q].so = lb2_arena_alloc(W, jobs[q].curlen); jobs[q].co = lb2_arena_alloc(W, jobs[q].curlen * 2 * (uint32_t)sizeof(lb2_cov)); }
 		sh->n_jobs = njobs;

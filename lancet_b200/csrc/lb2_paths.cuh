@@ -32,54 +32,74 @@ LB2_DEV uint32_t lb2_mm16(const uint32_t *bits, uint32_t g0, uint32_t p, uint32_
 }
 
 // the sequence is ACGT only and 2-bit packed at base index g0 of `bits` (two readable words past the end).
-// One lane per diagonal; inside a 16-position word the lane walks only the MISMATCH positions q (ffs over the 16
-// flags of one XOR): with the previous mismatches m1 > m2 > ... the zero run ending at q-1 has length q-m1-1 and the
-// longest window ending at q-1 with <= max mismatches has length q - m_{max+1} - 1.
+// Exact rule per diagonal (lane-serial): walking the MISMATCH positions q (ffs over the 16 flags of one XOR) with the
+// previous mismatches m1 > m2 > ..., the zero run ending at q-1 has length q-m1-1 and the longest window ending at q-1
+// with <= max mismatches has length q - m_{max+1} - 1.
 // Word filter: the results are only ever compared with k >= min_k (callers: lb2_pipeline.cuh), so runs and windows
 // shorter than 11 are irrelevant when min_k >= 11.  A run/window of 11+ positions contains two adjacent aligned
 // 4-position blocks holding <= max mismatches between them ("sparse pair"), and when it is evaluated at a mismatch q
-// inside word i that pair starts in word i-1 or i.  Words with no sparse pair in reach are skipped after a dozen
-// instructions (random sequence: ~98 % of them); a skipped word holds >= 2(max+1) mismatches, so the mismatch history
-// a later exact word needs is the top set bits of the word before it.  First and last word of a diagonal are exact.
+// inside word i that pair starts in word i-1 or i.  So a word needs the exact rule only if it or its predecessor holds a
+// sparse pair or one straddles their boundary (random sequence: ~2-3 % of the words).
+// Pass 1 (one lane per diagonal, dealt boustrophedon because the lengths fall with d) only classifies the words -- a
+// dozen instructions each -- and queues the START of every maximal stretch of exact-rule words.  Pass 2 (one lane per
+// queued stretch) applies the exact rule along its stretch.  The word before a stretch was skipped, hence holds
+// >= 2(max+1) mismatches: the mismatch history the stretch starts from is the top set bits of that word.
+struct lb2_wflags { uint32_t fw; bool sp; uint32_t c0, c3; };
+LB2_DEV lb2_wflags lb2_scan_word(const uint32_t *bits, uint32_t g0, int p0, int d, int np, uint32_t bias) {
+	lb2_wflags r; r.fw = lb2_mm16(bits, g0, (uint32_t)p0, (uint32_t)d);
+	if (np - p0 < 16) { r.fw &= (1u << (2 * (np - p0))) - 1u; }
+	const uint32_t t = (r.fw & 0x11111111u) + ((r.fw >> 2) & 0x11111111u);
+	const uint32_t c = (t + (t >> 4)) & 0x0F0F0F0Fu;      // mismatches per 4-position block
+	const uint32_t s2 = c + (c >> 8);                     // blocks (0,1) (1,2) (2,3) in bytes 0..2
+	r.sp = ((~(s2 + bias)) & 0x808080u) != 0;             // some pair inside the word is sparse
+	r.c0 = c & 0xFFu; r.c3 = c >> 24;
+	return r;
+}
 LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int len, int maxmm)
 {
 	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
-	if (tid == 0) { sh->scan_emax = 0; sh->scan_wmax = 0; }
+	uint32_t *tasks = (uint32_t *)W.ws0.sortk;      // (the build's sort keys: idle whenever a scan runs)
+	if (tid == 0) { sh->scan_emax = 0; sh->scan_wmax = 0; sh->walk_next = 0; }
 	lb2_sync();
-	int emax = 0, wmax = 0;
 	if (maxmm > 3) { maxmm = 3; if (tid == 0) { sh->err |= 1u << LB2_D_KMAX; } }
 	const bool filter = W.P->min_k >= 11 && maxmm >= 1;
 	const uint32_t bias = (0x80u - (uint32_t)(maxmm + 1)) * 0x010101u;
-	// diagonals dealt to the lanes boustrophedon (lengths fall with d): every lane gets about the same number of positions
 	const int ndiag = len - 1;
+	// ---- pass 1: classify, queue the stretches
 	for (int r = 0; r * (int)nt < ndiag; ++r) {
 		const int j = r * (int)nt + ((r & 1) ? (int)(nt - 1 - tid) : (int)tid);
 		if (j >= ndiag) { continue; }
 		const int d = j + 1, np = len - d;                 // positions p in [0, np)
-		int m1 = -1, m2 = -1, m3 = -1, m4 = -1;             // previous mismatch positions (virtual mismatch at -1)
-		uint32_t prev_fw = 0, prev_c3 = 0; bool prev_sp = true, exact = true;
+		if (!filter) { tasks[lb2_add32(&sh->walk_next, 1u)] = (uint32_t)d << 12; continue; }
+		uint32_t prev_c3 = 4; bool prev_sp = false, prev_slow = false;
 		for (int p0 = 0; p0 < np; p0 += 16) {
-			uint32_t fw = lb2_mm16(bits, g0, (uint32_t)p0, (uint32_t)d);
-			const bool last = np - p0 <= 16;
-			if (np - p0 < 16) { fw &= (1u << (2 * (np - p0))) - 1u; }
-			if (filter) {
-				const uint32_t t = (fw & 0x11111111u) + ((fw >> 2) & 0x11111111u);
-				const uint32_t c = (t + (t >> 4)) & 0x0F0F0F0Fu;      // mismatches per 4-position block
-				const uint32_t s2 = c + (c >> 8);                     // blocks (0,1) (1,2) (2,3) in bytes 0..2
-				const bool sp = ((~(s2 + bias)) & 0x808080u) != 0;    // some pair inside the word is sparse
-				const bool cross = prev_c3 + (c & 0xFFu) <= (uint32_t)maxmm;
-				const bool slow = sp || cross || prev_sp || last;
-				prev_sp = sp; prev_c3 = c >> 24;
-				if (!slow) { prev_fw = fw; exact = false; continue; }
-				if (!exact) {      // history = the top set bits of the skipped word before this one
-					uint32_t x = prev_fw; const int pb = p0 - 16;
-					if (x) { int b = 31 - lb2_clz32(x); m1 = pb + (b >> 1); x &= ~(1u << b); }
-					if (x) { int b = 31 - lb2_clz32(x); m2 = pb + (b >> 1); x &= ~(1u << b); }
-					if (x) { int b = 31 - lb2_clz32(x); m3 = pb + (b >> 1); x &= ~(1u << b); }
-					if (x) { int b = 31 - lb2_clz32(x); m4 = pb + (b >> 1); }
-					exact = true;
-				}
-			}
+			const lb2_wflags wf = lb2_scan_word(bits, g0, p0, d, np, bias);
+			const bool slow = wf.sp || prev_sp || (prev_c3 + wf.c0 <= (uint32_t)maxmm);
+			if (slow && !prev_slow) { tasks[lb2_add32(&sh->walk_next, 1u)] = ((uint32_t)d << 12) | (uint32_t)(p0 >> 4); }
+			prev_sp = wf.sp; prev_c3 = wf.c3; prev_slow = slow;
+		}
+	}
+	lb2_sync();
+	// ---- pass 2: the exact rule along every queued stretch
+	const uint32_t ntask = sh->walk_next; int emax = 0, wmax = 0;
+	for (uint32_t t = tid; t < ntask; t += nt) {
+		const uint32_t tk = tasks[t]; const int d = (int)(tk >> 12), np = len - d; int p0 = (int)(tk & 0xFFFu) << 4;
+		int m1 = -1, m2 = -1, m3 = -1, m4 = -1;             // previous mismatch positions (virtual mismatch at -1)
+		uint32_t prev_c3 = 4; bool prev_sp = false;
+		if (p0 > 0) {      // history and block count of the skipped word before the stretch
+			const lb2_wflags pw = lb2_scan_word(bits, g0, p0 - 16, d, np, bias);
+			uint32_t x = pw.fw; const int pb = p0 - 16; prev_c3 = pw.c3;
+			if (x) { int b = 31 - lb2_clz32(x); m1 = pb + (b >> 1); x &= ~(1u << b); }
+			if (x) { int b = 31 - lb2_clz32(x); m2 = pb + (b >> 1); x &= ~(1u << b); }
+			if (x) { int b = 31 - lb2_clz32(x); m3 = pb + (b >> 1); x &= ~(1u << b); }
+			if (x) { int b = 31 - lb2_clz32(x); m4 = pb + (b >> 1); }
+		}
+		bool at_end = false;
+		for (; p0 < np; p0 += 16) {
+			const lb2_wflags wf = lb2_scan_word(bits, g0, p0, d, np, bias);
+			if (filter && !(wf.sp || prev_sp || (prev_c3 + wf.c0 <= (uint32_t)maxmm))) { break; }      // the stretch ends here
+			prev_sp = wf.sp; prev_c3 = wf.c3;
+			uint32_t fw = wf.fw;
 			while (fw) {
 				int b = lb2_ctz32(fw); fw &= fw - 1;
 				int q = p0 + (b >> 1);
@@ -89,10 +109,12 @@ LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int 
 				int win = q - far - 1; if (win > wmax) { wmax = win; }
 				m4 = m3; m3 = m2; m2 = m1; m1 = q;
 			}
+			at_end = p0 + 16 >= np;
 		}
-		// end of the diagonal: exact runs may use positions <= np-2, near-repeat windows positions <= np-1
-		{ int run = (np - 1) - m1 - 1; if (run > emax) { emax = run; } }
-		{ int far = (maxmm == 0) ? m1 : (maxmm == 1) ? m2 : (maxmm == 2) ? m3 : m4; int win = np - far - 1; if (win > wmax) { wmax = win; } }
+		if (at_end) {      // end of the diagonal: exact runs may use positions <= np-2, near-repeat windows positions <= np-1
+			{ int run = (np - 1) - m1 - 1; if (run > emax) { emax = run; } }
+			{ int far = (maxmm == 0) ? m1 : (maxmm == 1) ? m2 : (maxmm == 2) ? m3 : m4; int win = np - far - 1; if (win > wmax) { wmax = win; } }
+		}
 	}
 	if (emax > 0) { lb2_max32(&sh->scan_emax, (uint32_t)emax); }
 	if (wmax > 0) { lb2_max32(&sh->scan_wmax, (uint32_t)wmax); }
@@ -273,28 +295,47 @@ LB2_DEVNI void lb2_align_fill(lb2_win &W)
 	} else { lb2_align_fill_t<int32_t>(W, ws.dp, ws.pathseq); }
 }
 
+// traceback by the first warp.  Every step reads one traceback byte whose address depends on the previous step -- a
+// chain of dependent global loads -- but alignments are mostly runs of plain diagonal moves: lane l looks at the cell l
+// steps down the diagonal, a ballot gives the length of the leading run of diagonal moves, and the lanes emit those
+// columns together.  Anything else (gaps, the forcex / forcey continuation states) takes one step by the scalar rule.
 LB2_DEVNI void lb2_align_trace(lb2_win &W)
 {
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned lane = lb2_tid();
+	if (lane >= LB2_WARP) { return; }
 	const int n = (int)sh->seq_len, m = (int)sh->plen; const size_t row = (size_t)n + 1;
 	const char *S = W.ref_raw + sh->seq_off; const char *T = ws.pathseq;
-	int i = n, j = m; bool forcex = false, forcey = false; uint32_t L = 0;
+	int i = n, j = m; bool forcex = false, forcey = false; uint32_t L = 0; bool bad = false;      // (identical in every lane)
 	while (i > 0 || j > 0) {
+		if (!forcex && !forcey) {
+			const int ii = i - (int)lane, jj = j - (int)lane; bool diag = false;
+			if (ii > 0 && jj > 0) { diag = (ws.tb[(size_t)(ii + jj) * row + ii] & 3) == 0; }
+			const uint32_t bal = lb2_ballot(diag);
+			const int nrun = (bal == 0xFFFFFFFFu) ? 32 : lb2_ctz32(~bal);
+			if (nrun > 0) {
+				if ((int)lane < nrun) { ws.aln_ref[L + lane] = S[ii - 1]; ws.aln_path[L + lane] = T[jj - 1]; }
+				L += (uint32_t)nrun; i -= nrun; j -= nrun;
+				continue;
+			}
+		}
 		uint8_t tb = ws.tb[(size_t)(i + j) * row + i]; int t = tb & 3, x = (tb >> 2) & 3, y = (tb >> 4) & 3;
 		char a, b;
 		if (t == 3) { break; }
-		else if (forcex) { if (i <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = S[i - 1]; b = '-'; if (x == 0) { forcex = false; } --i; }
-		else if (t == 1) { if (i <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = S[i - 1]; b = '-'; if (x == 1) { forcex = true; } --i; }
-		else if (forcey) { if (j <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = '-'; b = T[j - 1]; if (y == 0) { forcey = false; } --j; }
-		else if (t == 2) { if (j <= 0) { sh->err |= 1u << LB2_D_ALIGN; return; } a = '-'; b = T[j - 1]; if (y == 1) { forcey = true; } --j; }
+		else if (forcex) { if (i <= 0) { bad = true; break; } a = S[i - 1]; b = '-'; if (x == 0) { forcex = false; } --i; }
+		else if (t == 1) { if (i <= 0) { bad = true; break; } a = S[i - 1]; b = '-'; if (x == 1) { forcex = true; } --i; }
+		else if (forcey) { if (j <= 0) { bad = true; break; } a = '-'; b = T[j - 1]; if (y == 0) { forcey = false; } --j; }
+		else if (t == 2) { if (j <= 0) { bad = true; break; } a = '-'; b = T[j - 1]; if (y == 1) { forcey = true; } --j; }
 		else { a = S[i - 1]; b = T[j - 1]; --i; --j; }
-		ws.aln_ref[L] = a; ws.aln_path[L] = b; ++L;
+		if (lane == 0) { ws.aln_ref[L] = a; ws.aln_path[L] = b; }
+		++L;
 	}
-	for (uint32_t k = 0; k < L / 2; ++k) {
+	if (bad) { if (lane == 0) { sh->err |= 1u << LB2_D_ALIGN; } return; }
+	lb2_warp_sync();
+	for (uint32_t k = lane; k < L / 2; k += LB2_WARP) {
 		char c = ws.aln_ref[k]; ws.aln_ref[k] = ws.aln_ref[L - 1 - k]; ws.aln_ref[L - 1 - k] = c;
 		c = ws.aln_path[k]; ws.aln_path[k] = ws.aln_path[L - 1 - k]; ws.aln_path[L - 1 - k] = c;
 	}
-	sh->aln_len = L;
+	if (lane == 0) { sh->aln_len = L; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -527,7 +568,7 @@ LB2_DEVNI void lb2_process_path(lb2_win &W)
 	lb2_sync();
 	if (sh->need_align) {
 		lb2_align_fill(W);
-		if (lb2_tid() == 0) { lb2_align_trace(W); }
+		lb2_align_trace(W);
 		lb2_sync();
 	}
 	lb2_mark(W, LB2_PH_ALIGN);

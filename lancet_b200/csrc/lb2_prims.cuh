@@ -36,6 +36,11 @@ static inline int lb2_popc32(uint32_t x) { return __builtin_popcount(x); }
 // length-weighted coverage average of compressNode (src/Graph.cc:2631-2636): two products, a sum, a quotient, each rounded
 // (the reference is x86-64 without FMA; the device must not contract the sum of products)
 static inline float lb2_wavg(float a, int la, float b, int lb) { volatile float p = a * la; volatile float q = b * lb; volatile float sm = p + q; return sm / (la + lb); }
+// the same average for a serial fold, with the reciprocal of the (integer) divisor supplied by the caller
+static inline float lb2_rcp_int(uint32_t n) { return 1.0f / (float)n; }
+static inline float lb2_wavg_rcp(float a, int la, float b, int lb, float r) { (void)r; return lb2_wavg(a, la, b, lb); }
+// (simulation of the device's division, for tests/hostsim's divtest)
+static inline float lb2_div_nr2(float s, float n, float r) { float q0 = s * r; float e0 = fmaf(-n, q0, s); float q1 = fmaf(e0, r, q0); float e1 = fmaf(-n, q1, s); return fmaf(e1, r, q1); }
 static inline unsigned long long lb2_clock() { return 0; }
 // CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
 static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) { (void)sc; *total = v; return 0; }
@@ -56,6 +61,10 @@ static inline void lb2s_or(lb2_sp a, uint32_t v) { *a |= v; }
 static inline uint32_t lb2_fsr(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31u; return sh ? ((lo >> sh) | (hi << (32u - sh))) : lo; }
 // work items handed out to whole warps: every lane of the warp calls this together and gets its own item index
 static inline uint32_t lb2_batch_next(uint32_t *ctr) { return (*ctr)++; }
+#define LB2_WARP 1     /* lanes that run warp-cooperative code (one in the simulation) */
+static inline uint32_t lb2_ballot(bool p) { return p ? 1u : 0u; }
+static inline void lb2_warp_sync() {}
+static inline uint32_t lb2_warp_max(uint32_t v) { return v; }
 #define LB2_FQ 1      /* lanes per chain in the coverage fold of the parallel compaction (one per channel on the device) */
 static inline unsigned lb2_glane() { return 0; }
 static inline unsigned lb2_group() { return 0; }
@@ -98,6 +107,18 @@ LB2_DEV int lb2_popc32(uint32_t x) { return __popc(x); }
 // length-weighted coverage average of compressNode (src/Graph.cc:2631-2636): two products, a sum, a quotient, each rounded
 // (the reference is x86-64 without FMA; the device must not contract the sum of products)
 LB2_DEV float lb2_wavg(float a, int la, float b, int lb) { return __fdiv_rn(__fadd_rn(__fmul_rn(a, (float)la), __fmul_rn(b, (float)lb)), (float)(la + lb)); }
+// the same average for a serial fold: the correctly rounded reciprocal r = RN(1/(la+lb)) of the (integer-valued) divisor
+// comes from the caller (computed in parallel beforehand), and the division is q0 = s*r followed by two fused residual
+// corrections.  With r = RN(1/n) and q1 faithful, the last correction returns RN(s/n) (Markstein); tests/hostsim
+// "divtest" checks the sequence against IEEE division.  s is a finite non-negative normal (coverage x length sums),
+// n an integer < 2^16.  Only product, sum and the corrections depend on a.
+LB2_DEV float lb2_rcp_int(uint32_t n) { return __frcp_rn((float)n); }
+LB2_DEV float lb2_wavg_rcp(float a, int la, float b, int lb, float r) {
+	const float n = (float)(la + lb), q = __fmul_rn(b, (float)lb);
+	const float s = __fadd_rn(__fmul_rn(a, (float)la), q);
+	const float q0 = __fmul_rn(s, r), e0 = __fmaf_rn(-n, q0, s), q1 = __fmaf_rn(e0, r, q0), e1 = __fmaf_rn(-n, q1, s);
+	return __fmaf_rn(e1, r, q1);
+}
 LB2_DEV unsigned long long lb2_clock() { return (unsigned long long)clock64(); }
 // CTA-wide exclusive prefix sum of one value per lane (sc: >= 34 words of shared scratch); every lane must call it
 LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {
@@ -134,6 +155,10 @@ LB2_DEV uint32_t lb2_batch_next(uint32_t *ctr) {
 	if ((threadIdx.x & 31u) == 0) { base = lb2_add32(ctr, 32u); }
 	return __shfl_sync(0xFFFFFFFFu, base, 0) + (threadIdx.x & 31u);
 }
+#define LB2_WARP 32
+LB2_DEV uint32_t lb2_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+LB2_DEV void lb2_warp_sync() { __syncwarp(); }
+LB2_DEV uint32_t lb2_warp_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 #define LB2_FQ 4      /* lanes per chain in the coverage fold of the parallel compaction: one per channel */
 LB2_DEV unsigned lb2_glane() { return threadIdx.x & 7u; }
 LB2_DEV unsigned lb2_group() { return threadIdx.x >> 3; }

@@ -51,7 +51,7 @@ struct lb2_ws {
 	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
 	lb2_bedge *b_edge; uint32_t *b_row;
 	// --- reads ---
-	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase;
+	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase; uint64_t *rd_src;      // rd_src: pool offset of the first kept base
 	// --- graph stage, row space.  hot (shared memory): ---
 	uint32_t *d_lnext; uint32_t *d_bk; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
 	uint16_t *d_pos; uint32_t *px; uint32_t px_words;   // (packed-read words, dead in the graph stage) list index of every row; scratch of the parallel compaction
@@ -109,7 +109,7 @@ struct lb2_sh {
 // phase ids for the optional cycle profile (lb2_dev_out::prof)
 enum { LB2_PH_STAGE = 0, LB2_PH_PRESCAN, LB2_PH_REFSCAN, LB2_PH_WALK, LB2_PH_COMPACT, LB2_PH_MATES, LB2_PH_LOWQ, LB2_PH_CLEAR,
        LB2_PH_REFCOV, LB2_PH_ORDER, LB2_PH_LOWCOV_CC, LB2_PH_COMP_SEQ, LB2_PH_BFS, LB2_PH_PATHSCAN, LB2_PH_ALIGN, LB2_PH_SCAN, LB2_PH_OTHER,
-       LB2_PH_ANCHOR, LB2_PH_CSWEEP, LB2_PH_CMAT, LB2_PH_CCLEAN, LB2_PH_N };
+       LB2_PH_ANCHOR, LB2_PH_CSWEEP, LB2_PH_CMAT, LB2_PH_CCLEAN, LB2_PH_CP_LINK, LB2_PH_CP_FOLD, LB2_PH_N };
 
 #ifdef __CUDACC__
 #define LB2_HD __host__ __device__ inline

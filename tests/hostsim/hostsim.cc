@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <stdlib.h>
 #include <cstring>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -28,10 +29,33 @@ int main(int argc, char **argv)
 		else if (a == "--count") count = atoi(argv[++i]); else if (a == "--dfs-limit") P.dfs_limit = atoi(argv[++i]);
 		else fn = argv[i];
 	}
+	if (fn && std::string(fn) == "divtest") {
+		// the division of the device's coverage fold (s*r and two fused residual corrections, r = RN(1/n)) against IEEE s/n
+		unsigned long long rs = 88172645463325252ull; auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return rs; };
+		unsigned long long bad = 0, total = 0; const int per = getenv("LB2_DIVTEST_PER") ? atoi(getenv("LB2_DIVTEST_PER")) : 4000;
+		for (int n = 1; n <= 8192; ++n) {
+			const float fnn = (float)n, r = 1.0f / fnn;
+			for (int it = 0; it < per; ++it) {
+				float s; const unsigned long long x = rnd();
+				switch (it & 3) {
+					case 0: { uint32_t b = (uint32_t)(x >> 20) & 0x7FFFFFFFu; b = (b % (0x4D000000u - 0x30000000u)) + 0x30000000u; memcpy(&s, &b, 4); break; }
+					case 1: { s = (float)(x % 200000000ull) / 16.0f; break; }
+					case 2: { float t; uint32_t b = 0x3F800000u + (uint32_t)(x & 0x7FFFFFu) + (((uint32_t)(x >> 40) % 20) << 23); memcpy(&t, &b, 4); s = t * fnn; uint32_t sb; memcpy(&sb, &s, 4); sb += (int)((x >> 60) & 7) - 3; memcpy(&s, &sb, 4); break; }
+					default: { s = (float)((x >> 8) % 70000) * (float)(1 + (x & 1023)) + (float)((x >> 30) % 70000); break; }
+				}
+				if (!(s >= 0.0f) || std::isinf(s)) { continue; }
+				volatile float want = s / fnn; const float got = lb2_div_nr2(s, fnn, r); const float w2 = want;
+				++total; if (memcmp(&w2, &got, 4) != 0) { if (bad++ < 10) { fprintf(stderr, "MISMATCH s=%a n=%d want=%a got=%a\n", s, n, w2, got); } }
+			}
+		}
+		printf("divtest: %llu cases, %llu mismatches\n", total, bad);
+		return bad ? 1 : 0;
+	}
 	if (fn && std::string(fn) == "scantest") {
 		// the word filter of lb2_diag_scan against the unfiltered scan (min_k < 11 switches the filter off): for every k >= 11
 		// both must answer isRepeat / isAlmostRepeat alike, i.e. max(emax,10) and max(wmax,11) agree
 		std::vector<uint8_t> smem(sizeof(lb2_sh) + 64, 0); lb2_win Wn; memset(&Wn, 0, sizeof Wn); Wn.sh = (lb2_sh *)smem.data(); Wn.P = &P;
+		std::vector<uint64_t> taskbuf(1 << 16); Wn.ws0.sortk = taskbuf.data(); Wn.ws.sortk = taskbuf.data();
 		unsigned long long rs = 88172645463325252ull; auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t)(rs >> 11); };
 		int bad = 0, ntest = 0, nrel = 0;
 		for (int t = 0; t < 6000; ++t) {
