@@ -21,6 +21,7 @@ struct lb2_launch {
 	lb2_params P; lb2_cfg C; lb2_dev_batch B; lb2_dev_out O;
 	uint8_t *ws_base; size_t ws_stride; uint32_t *counter;
 	const uint32_t *avail;      // streamed lb2_process: windows [0, *avail) have their reads in HBM (NULL: the batch is resident)
+	uint32_t *stalled;          // set when a window fetch gave up waiting for the watermark (the host then redoes the batch resident)
 	const uint32_t *win_list; const uint32_t *n_list;   // escalation pass: indices of the windows to redo (NULL = all windows)
 	uint32_t *retry_list; uint32_t *retry_count;
 	// compaction outputs
@@ -51,11 +52,19 @@ lb2_window_kernel(const lb2_launch *Lp)
 	while (true) {
 		if (threadIdx.x == 0) {
 			const uint32_t nx = atomicAdd(Lp->counter, 1u);
+			uint32_t nx2 = nx;
 			if (Lp->avail && nx < nwin) {      // the read pool is still arriving on the copy stream: wait for this window's watermark
-				while (*(volatile const uint32_t *)Lp->avail <= nx) { __nanosleep(200); }
+				// (never forever: if something serialises the copy stream behind this kernel -- a profiler, a debugger --
+				// the fetch gives up after two seconds and the host redoes the batch the resident way)
+				unsigned long long t0 = 0, t1 = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+				while (*(volatile const uint32_t *)Lp->avail <= nx) {
+					__nanosleep(200);
+					asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+					if (t1 - t0 > 2000000000ull || *(volatile uint32_t *)Lp->stalled) { *(volatile uint32_t *)Lp->stalled = 1u; nx2 = nwin; break; }
+				}
 				__threadfence_system();
 			}
-			s_next = nx;
+			s_next = nx2;
 		}
 		__syncthreads();
 		uint32_t w = s_next;
@@ -126,7 +135,7 @@ __global__ void lb2_gather_kernel(const lb2_launch *Lp)
 #define LB2_MAX_MARKS 1024
 struct lb2_ctx {
 	int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
-	cudaStream_t copy_stream = nullptr; uint32_t *d_avail = nullptr;      // streamed lb2_process
+	cudaStream_t copy_stream = nullptr; uint32_t *d_avail = nullptr, *d_stalled = nullptr;      // streamed lb2_process
 	cudaEvent_t ev_avail = nullptr; uint32_t *h_marks = nullptr;          // (pinned) per chunk: windows ready
 	std::vector<uint32_t> h_need;                                         // per window: leading pool reads the windows up to it use
 	lb2_params P; lb2_cfg C;
@@ -199,7 +208,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	if (prop.major < 10) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
-	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&ctx->d_avail, 4) != cudaSuccess ||
+	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&ctx->d_avail, 4) != cudaSuccess || cudaMalloc(&ctx->d_stalled, 4) != cudaSuccess || cudaMemset(ctx->d_stalled, 0, 4) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->ev_avail, cudaEventDisableTiming) != cudaSuccess || cudaHostAlloc((void **)&ctx->h_marks, sizeof(uint32_t) * LB2_MAX_MARKS, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
@@ -234,7 +243,7 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 	cudaFree(ctx->d_big_count); cudaFree(ctx->d_counter2); cudaFree(ctx->d_retry_count); cudaFree(ctx->d_launch2);
 	cudaFree(ctx->d_counter); cudaFree(ctx->d_totals); cudaFree(ctx->d_launch);
 	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
-	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); } cudaFree(ctx->d_avail);
+	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); } cudaFree(ctx->d_avail); cudaFree(ctx->d_stalled);
 	if (ctx->ev_avail) { cudaEventDestroy(ctx->ev_avail); } if (ctx->h_marks) { cudaFreeHost(ctx->h_marks); }
 	delete ctx;
 }
@@ -347,7 +356,7 @@ static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
 	L.O.big_variants = (lb2_variant *)ctx->d_big_vars.p; L.O.big_strings = (char *)ctx->d_big_strs.p; L.O.big_slot = (uint32_t *)ctx->d_big_slot.p;
 	L.O.big_count = ctx->d_big_count; L.O.big_cap = nbig; L.O.big_max_var = ctx->big_max_var; L.O.big_str_bytes = ctx->big_str_bytes;
 	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
-	L.win_list = nullptr; L.n_list = nullptr; L.avail = streamed ? ctx->d_avail : nullptr;
+	L.win_list = nullptr; L.n_list = nullptr; L.avail = streamed ? ctx->d_avail : nullptr; L.stalled = ctx->d_stalled;
 	if ((rc = lb2_reserve(ctx, ctx->d_retry, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
 	L.retry_list = (uint32_t *)ctx->d_retry.p; L.retry_count = ctx->d_retry_count;
 	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_totals;
@@ -447,6 +456,8 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	{	// copies from pageable memory do not overlap a running kernel (a kernel waiting for them would wait forever):
 		// the pool is only streamed from page-locked buffers, otherwise the batch is made resident first
 		bool pinned = batch->n_base_bytes > 0 && batch->n_windows > 0 && env_u32("LB2_STREAM", 1) != 0;
+		// tools that make kernel launches synchronous would park the kernel in front of the copies it waits for
+		if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSYS_PROFILING_SESSION_ID") || env_u32("CUDA_LAUNCH_BLOCKING", 0)) { pinned = false; }
 		const void *arrs[] = { batch->seq, batch->qual, batch->base_off, batch->flags, batch->name_rank, batch->wr_idx, batch->ref_seq };
 		const uint64_t sizes[] = { batch->n_base_bytes, batch->n_base_bytes, 1, batch->n_reads, batch->n_reads, batch->n_wr, batch->n_ref_bytes };
 		for (int i = 0; i < 7 && pinned; ++i) {
@@ -463,6 +474,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	const bool timing = env_u32("LB2_TIMING", 0) != 0; const auto t0 = std::chrono::steady_clock::now();
 	// the watermark starts at 0 before the kernel may look at it (same stream as the updates that follow)
 	LB2_CK(cudaMemsetAsync(ctx->d_avail, 0, 4, ctx->copy_stream));
+	LB2_CK(cudaMemsetAsync(ctx->d_stalled, 0, 4, ctx->copy_stream));
 	LB2_CK(cudaEventRecord(ctx->ev_avail, ctx->copy_stream));
 	LB2_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_avail, 0));
 	int rc = lb2_upload_impl(ctx, batch, true); if (rc) { return rc; }
@@ -500,6 +512,16 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 #undef LB2_PIECE
 	const auto t2 = std::chrono::steady_clock::now();
 	LB2_CK(cudaStreamSynchronize(ctx->copy_stream));      // the caller's buffers are free again when the call returns
+	{	// safety net: a window fetch that gave up on the watermark => the whole batch again, resident (it is by now)
+		uint32_t stalled = 0;
+		LB2_CK(cudaStreamSynchronize(ctx->stream));
+		LB2_CK(cudaMemcpy(&stalled, ctx->d_stalled, 4, cudaMemcpyDeviceToHost));
+		if (stalled) {
+			ctx->L.avail = nullptr;
+			LB2_CK(cudaMemcpyAsync(ctx->d_launch, &ctx->L, sizeof ctx->L, cudaMemcpyHostToDevice, ctx->stream));
+			rc = lb2_run(ctx); if (rc) { return rc; }
+		}
+	}
 	if (timing) {
 		const auto t3 = std::chrono::steady_clock::now(); rc = lb2_download(ctx, result); const auto t4 = std::chrono::steady_clock::now();
 		auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a).count(); };
