@@ -249,7 +249,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 //   g_cnt  2xu32 per slot  tumour / normal occurrence counts, fwd in the low half, rev in the high half
 //               (fire-and-forget reductions: nothing on the lane's critical path reads them back)
 //   g_em   u32 per DENSE node  the slot's mask, saved before t_id is reused
-//   inst   u32 per occurrence  slot | orientation << 31 (| 0x40000000 suppressed by the mate replay), indexed
+//   inst   u16 per occurrence  slot (14 bits) | orientation << 15 (| 0x4000 suppressed by the mate replay), indexed
 //               ibase + offset * istride: transposed (offset-major) so that the lanes of a warp -- one read each, same
 //               offset -- store to consecutive words; read-major when the transposed array would not fit
 // ---------------------------------------------------------------------------------------------
@@ -356,7 +356,7 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 	uint32_t ori_u = fless ? 0u : 1u;
 	uint32_t su = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fless, f, rc), lb2_pick<NWT>(fless, rc, f), ((g0 + o_begin) << 1) | ori_u, K, nw, true);
 	if (su == LB2_NIL) { return; }
-	ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
+	ws.inst[ibase + o_begin * istride] = (uint16_t)(su | (ori_u << 15));
 	if (isref) { ws.refnode[o_begin] = su; }
 	else if (o_begin == 0) {
 		lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
@@ -371,7 +371,7 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 		uint32_t ori_v = fless ? 0u : 1u;
 		uint32_t sv = lb2_find_or_insert<NWT>(W, lb2_pick<NWT>(fless, f, rc), lb2_pick<NWT>(fless, rc, f), ((g0 + o + 1) << 1) | ori_v, K, nw, true);
 		if (sv == LB2_NIL) { return; }
-		ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
+		ws.inst[ibase + (o + 1) * istride] = (uint16_t)(sv | (ori_v << 15));
 		uint32_t emu = 1u << (ori_u * 4 + (uint32_t)c);            // u leaves in orientation ori_u appending c
 		uint32_t emv = 1u << ((1u - ori_v) * 4 + (uint32_t)(3 - a)); // v leaves in the flipped orientation appending comp(a)
 		if (isref) { ws.refnode[o + 1] = sv; }
@@ -403,6 +403,8 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	const lb2_sp tk = lb2_sp_of(W.t_key), tidw = lb2_sp_of(W.t_id), bits = lb2_sp_of(W.bits);
 	const uint32_t mask = W.C->table_slots - 1;
+	// (array bases in registers: the descriptor lives in shared memory and would be re-read behind every store)
+	uint16_t *inst_p = ws.inst + ibase + (size_t)o_begin * istride; uint32_t *const GC = ws.g_cnt + (cls >> 1); uint32_t *const RN = ws.refnode;
 	const int topsh = 2 * (K - 1); const KT kmask = (KT)(~(KT)0) >> (sizeof(KT) * 8 - 2 * K);
 	KT f = 0, rc = 0, fB = 0, rcB = 0;
 	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
@@ -416,7 +418,7 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	}
 	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
 	const bool track_q = active && tumor && sh->has_lowq;
-	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u, csel = cls >> 1;
+	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u;
 	int lowcnt = 0;    // low-quality bases in [o, o+K-1]; the pair window adds base o+K
 	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
 	bool fless = fB < rcB;
@@ -424,10 +426,10 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	if (active) {
 		su = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, kmask, true);
 		if (su != LB2_NIL) {
-			ws.inst[ibase + o_begin * istride] = su | (ori_u << 31);
-			if (isref) { ws.refnode[o_begin] = su; }
+			*inst_p = (uint16_t)(su | (ori_u << 15));
+			if (isref) { RN[o_begin] = su; }
 			else if (o_begin == 0) {
-				lb2g_red_add(&ws.g_cnt[su * 2 + csel], cadd);
+				lb2g_red_add(&GC[su * 2], cadd);
 				if (normal) { pend = LB2_EM_NORMAL; }
 			}
 		}
@@ -448,10 +450,10 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 		uint32_t emu = 1u << (ori_u * 4 + c);                         // u leaves in orientation ori_u appending c
 		uint32_t emv = 1u << ((1u - ori_v) * 4 + (3u - a));           // v leaves in the flipped orientation appending comp(a)
 		if (sv != LB2_NIL) {
-			ws.inst[ibase + (o + 1) * istride] = sv | (ori_v << 31);
-			if (isref) { ws.refnode[o + 1] = sv; }
+			inst_p += istride; *inst_p = (uint16_t)(sv | (ori_v << 15));
+			if (isref) { RN[o + 1] = sv; }
 			else {
-				lb2g_red_add(&ws.g_cnt[sv * 2 + csel], cadd);
+				lb2g_red_add(&GC[sv * 2], cadd);
 				if (normal) { emv |= LB2_EM_NORMAL; }
 				if (tumor) {
 					bool clean = true;
@@ -693,7 +695,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		for (uint32_t x = total + tid; x < t2; x += nt) { ws.sortk[x] = ~0ull; }
 		for (uint32_t r = tid; r < R; r += nt) {        // x = read-major occurrence number (the replay needs read order)
 			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
-			for (uint32_t o = 0; o < nk; ++o) { ws.sortk[kb + o] = ((uint64_t)W.t_id[ws.inst[ib + o * istr] & 0x3FFFFFFFu] << 32) | (kb + o); }
+			for (uint32_t o = 0; o < nk; ++o) { ws.sortk[kb + o] = ((uint64_t)W.t_id[ws.inst[ib + o * istr] & 0x3FFFu] << 32) | (kb + o); }
 		}
 		lb2_sync();
 		lb2_sort64(ws.sortk, t2);
@@ -726,7 +728,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					uint32_t cnt_other = (mate == 1) ? n2_ : n1;
 					bool ovl = false;
 					if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
-					if (ovl) { ws.inst[(sh->inst_stride ? r : ws.rd_kbase[r]) + p * istr] |= 0x40000000u; ws.b_cnt[j * 4 + cls] -= 1; }
+					if (ovl) { ws.inst[(sh->inst_stride ? r : ws.rd_kbase[r]) + p * istr] |= 0x4000u; ws.b_cnt[j * 4 + cls] -= 1; }
 					uint32_t last = ws.rd_len[r] - (uint32_t)K;
 					uint32_t pushes = (p == 0 || p == last) ? 1u : 2u;
 					for (uint32_t q = 0; q < pushes; ++q) { if (mate == 1) { L1[n1++] = name; } else { *(L2top - n2_) = name; ++n2_; } }
@@ -753,9 +755,9 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 					uint32_t p0 = (q + 1 > (uint32_t)K) ? (q + 1 - K) : 0, p1 = (q < len - K) ? q : (len - K);
 					for (uint32_t p = p0; p <= p1; ++p) {
 						uint32_t iw = ws.inst[kb + p * istr];
-						if (iw & 0x40000000u) { continue; }               // suppressed (overlapping mate)
-						uint32_t id = W.t_id[iw & 0x3FFFFFFFu];
-						uint32_t i = (iw >> 31) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
+						if (iw & 0x4000u) { continue; }                   // suppressed (overlapping mate)
+						uint32_t id = W.t_id[iw & 0x3FFFu];
+						uint32_t i = (iw >> 15) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
 						lb2g_add32(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
 					}
 				}
@@ -829,14 +831,14 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				for (uint32_t q = 0; q < 8; ++q) {
 					if (o8 + q >= oe) { continue; }
 					const uint32_t o = o8 + q, iv = v[q];
-					const uint32_t su = iu & 0x3FFFFFFFu, sv = iv & 0x3FFFFFFFu;
+					const uint32_t su = iu & 0x3FFFu, sv = iv & 0x3FFFu;
 					const uint32_t idu = W.t_id[su], idv = W.t_id[sv];
 					if (idu & LB2_ID_BRANCH) {
-						uint32_t t = (iu >> 31) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
+						uint32_t t = ((iu >> 15) & 1u) * 4 + (uint32_t)lb2_getbase(W.bits, g0 + o + K);
 						lb2g_min32(&ws.bseq[(size_t)(idu & 0x7FFFu) * 8 + t], 2 * (kb + o));
 					}
 					if (idv & LB2_ID_BRANCH) {
-						uint32_t t = (1u - (iv >> 31)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
+						uint32_t t = (1u - ((iv >> 15) & 1u)) * 4 + (uint32_t)(3 - lb2_getbase(W.bits, g0 + o));
 						lb2g_min32(&ws.bseq[(size_t)(idv & 0x7FFFu) * 8 + t], 2 * (kb + o) + 1);
 					}
 					iu = iv;

@@ -293,7 +293,7 @@ static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
 	const uint32_t smem_cap = 220u << 10;
 	if (max_bp > (1u << 20) - 1024) { max_bp = (1u << 20) - 1024; }   // representative base index has 20 bits in the table key
 	lb2_cfg &C = ctx->C;
-	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096);
+	C.table_slots = std::min<uint32_t>(env_u32("LB2_TABLE_SLOTS", 4096), 16384u);      // (occurrence words hold 14-bit slot numbers)
 	while (C.table_slots > 1024 && lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes) > smem_cap) { C.table_slots >>= 1; }
 	while (lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
 	C.max_nodes = C.table_slots - C.table_slots / 4;
@@ -365,7 +365,7 @@ static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
 	if (ctx->escalate) {
 		// escalation pass: the largest table that still fits beside the staged reads, big arena / BFS queue, one CTA per SM
 		lb2_cfg &C2 = ctx->C2; C2 = C;
-		C2.table_slots = env_u32("LB2_TABLE_SLOTS2", 16384); C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 184u << 10);
+		C2.table_slots = std::min<uint32_t>(env_u32("LB2_TABLE_SLOTS2", 16384), 16384u); C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 184u << 10);
 		while (C2.graph_bytes > C.graph_bytes && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.graph_bytes -= 4096; }
 		while (C2.table_slots > C.table_slots && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.table_slots >>= 1; }
 		C2.max_nodes = C2.table_slots - C2.table_slots / 4;

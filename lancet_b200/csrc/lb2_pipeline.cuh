@@ -13,7 +13,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 #define LB2_TAKE(field, type, count) do { off = (off + 15) & ~(size_t)15; if (ws) { ws->field = (type *)(base + off); } off += sizeof(type) * (size_t)(count); } while (0)
 	const size_t MN = (size_t)c.max_nodes + 16, MR = (size_t)c.max_reads + 2;
 	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
-	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(g_cnt, uint32_t, (size_t)c.table_slots * 2); LB2_TAKE(g_em, uint32_t, c.table_slots); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint32_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
+	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(g_cnt, uint32_t, (size_t)c.table_slots * 2); LB2_TAKE(g_em, uint32_t, c.table_slots); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint16_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
 	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR); LB2_TAKE(rd_src, uint64_t, MR);
 	LB2_TAKE(b_rep, uint32_t, MN); LB2_TAKE(b_hash, uint64_t, MN); LB2_TAKE(b_cnt, uint32_t, MN * 4); LB2_TAKE(b_mincovqv, int32_t, MN);

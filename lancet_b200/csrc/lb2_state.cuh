@@ -46,7 +46,7 @@ struct lb2_trans {                // Transcript_t (reference src/Transcript.hh:3
 // graph-stage arrays, into the CTA's shared memory (assigned per (window,k) by lb2_order_and_pack)
 struct lb2_ws {
 	// --- build stage ---
-	uint32_t *used; uint64_t *sortk; uint32_t *inst; uint32_t *mates; uint32_t *bseq;
+	uint32_t *used; uint64_t *sortk; uint16_t *inst; uint32_t *mates; uint32_t *bseq;
 	uint32_t *g_cnt; uint32_t *g_em;   // per-slot accumulators of the build (fed by fire-and-forget reductions)
 	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
 	lb2_bedge *b_edge; uint32_t *b_row;
