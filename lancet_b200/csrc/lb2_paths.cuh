@@ -139,15 +139,19 @@ LB2_DEVNI void lb2_pack_path(lb2_win &W, uint32_t *dst)
 LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
-	lb2_qent *Q = ws.queue; const uint32_t cap = W.C->queue_cap;
+	const uint32_t cap = W.C->queue_cap;
+	// the head of the queue lives in the idle shared-memory scratch (most searches never leave it), the rest in the slab
+	lb2_qent *const Qs = (lb2_qent *)ws.px, *const Qg = ws.queue; const uint32_t qs = (uint32_t)(((size_t)ws.px_words * 4) / sizeof(lb2_qent));
+	if (lb2_tid() == 0) { W.sh->q_smem = qs; }
+#define Q_AT(i) ((i) < qs ? Qs[(i)] : Qg[(i)])
 	const int reflen = (int)sh->seq_len;
 	uint32_t qh = 0, qt = 0; int visit = 0; uint32_t best = LB2_NIL; int bestscore = 0;
 	lb2_qent root; root.parent = LB2_NIL; root.node = sh->source; root.len = K; root.score = 0; root.eidx = 0; root.dirflag = 2;   // dir F, flag 1
-	Q[qt++] = root;
+	Q_AT(qt) = root; ++qt;
 	while (qh < qt) {
 		++visit;
 		if (W.P->dfs_limit && visit > W.P->dfs_limit) { break; }
-		uint32_t idx = qh++; lb2_qent e = Q[idx];
+		uint32_t idx = qh++; lb2_qent e = Q_AT(idx);
 		uint32_t cur = e.node; int pdir = e.dirflag & 1; int pflag = (e.dirflag >> 1) & 1;
 		if (cur == sh->sink && pflag == 0) {
 			if (best == LB2_NIL || (int)e.score > bestscore) { best = idx; bestscore = e.score; }
@@ -163,22 +167,26 @@ LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 				int nflag = pflag * (int)ed[i].flag;
 				c.score = (uint16_t)(e.score + (ed[i].flag == 0 ? 1 : 0));
 				c.dirflag = (uint8_t)(lb2_dir_dest(ed[i].dir) | (nflag << 1));
-				Q[qt++] = c;
+				Q_AT(qt) = c; ++qt;
 			}
 		}
 	}
 	return best;
+#undef Q_AT
 }
 
 // materialise the chosen path: node list, string, per-base tumour/normal coverage
 LB2_DEVNI void lb2_load_path(lb2_win &W, uint32_t best)
 {
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; lb2_qent *Q = ws.queue;
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	lb2_qent *const Qs = (lb2_qent *)ws.px, *const Qg = ws.queue; const uint32_t qs = sh->q_smem;
+#define Q_AT(i) ((i) < qs ? Qs[(i)] : Qg[(i)])
 	uint32_t n = 0;
-	for (uint32_t x = best; x != LB2_NIL; x = Q[x].parent) { ++n; }
+	for (uint32_t x = best; x != LB2_NIL; x = Q_AT(x).parent) { ++n; }
 	if (n > LB2_MAX_PNODES) { sh->err |= 1u << LB2_D_PATH; return; }
 	uint32_t k = n;
-	for (uint32_t x = best; x != LB2_NIL; x = Q[x].parent) { --k; ws.pnodes[k] = Q[x].node; ws.peidx[k] = Q[x].eidx; }
+	for (uint32_t x = best; x != LB2_NIL; x = Q_AT(x).parent) { --k; const lb2_qent e = Q_AT(x); ws.pnodes[k] = e.node; ws.peidx[k] = e.eidx; }
+#undef Q_AT
 	sh->pn = n;
 	for (uint32_t i = 1; i < n; ++i) { ws.pdirs[i - 1] = lb2_edges(ws, ws.pnodes[i - 1])[ws.peidx[i]].dir; }
 	// Path_t::str / covDistr: where every node's contribution starts (lane 0); the copy itself is lb2_copy_path
@@ -245,34 +253,41 @@ LB2_DEV void lb2_flag_path(lb2_win &W, int flag) {
 // tb byte per cell: M.tb (0 '\\', 1 '<', 2 '^', 3 '*') | X.tb<<2 (0 '<', 1 '-', 2 other) | Y.tb<<4 (0 '^', 1 '|', 2 other)
 // ---------------------------------------------------------------------------------------------------
 // (the traceback bytes are stored anti-diagonal-major, tb[(i+j) * (n+1) + i]: the lanes of a wavefront write consecutive bytes)
-template <class DT> LB2_DEV void lb2_align_fill_t(lb2_win &W, DT *dp, const char *T)
+// One cell record {M, X, Y} per row index and anti-diagonal, three rotating anti-diagonals: a cell reads the records
+// [i-1] and [i] of the previous anti-diagonal and [i-1] of the one before with one load each.  The matrix borders are
+// written by two designated lanes, the loop body is interior cells only.
+struct lb2_cell16 { int16_t m, x, y, pad; };
+struct lb2_cell32 { int32_t m, x, y, pad; };
+template <class CT> LB2_DEV void lb2_align_fill_t(lb2_win &W, CT *dp, const char *T)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const int n = (int)sh->seq_len, m = (int)sh->plen;
 	const char *S = W.ref_raw + sh->seq_off;
 	const int stride = n + 2;
-	DT *Mb = dp, *Xb = dp + 3 * stride, *Yb = dp + 5 * stride;
 	const size_t row = (size_t)n + 1;
 	for (int d = 0; d <= n + m; ++d) {
-		DT *M0 = Mb + (d % 3) * stride, *M1 = Mb + ((d + 2) % 3) * stride, *M2 = Mb + ((d + 1) % 3) * stride;
-		DT *X0 = Xb + (d & 1) * stride, *X1 = Xb + ((d + 1) & 1) * stride;
-		DT *Y0 = Yb + (d & 1) * stride, *Y1 = Yb + ((d + 1) & 1) * stride;
-		int lo = d - m; if (lo < 0) { lo = 0; } int hi = d < n ? d : n;
+		CT *C0 = dp + (d % 3) * stride; const CT *C1 = dp + ((d + 2) % 3) * stride, *C2 = dp + ((d + 1) % 3) * stride;
 		uint8_t *tbd = ws.tb + (size_t)d * row;
+		if (tid == 0 && d <= m) {          // cell (0, d)
+			CT c; c.pad = 0;
+			if (d == 0) { c.m = 0; c.x = -8; c.y = -8; tbd[0] = 3 | (2 << 2) | (2 << 4); }
+			else { c.m = (decltype(c.m))(-8 - d); c.x = c.m; c.y = 0; tbd[0] = 2 | (2 << 2) | (2 << 4); }
+			C0[0] = c;
+		}
+		if (tid == (nt > 1 ? 1u : 0u) && d >= 1 && d <= n) {      // cell (d, 0)
+			CT c; c.pad = 0; c.m = (decltype(c.m))(-8 - d); c.y = c.m; c.x = 0; C0[d] = c; tbd[d] = 1 | (2 << 2) | (2 << 4);
+		}
+		int lo = d - m; if (lo < 1) { lo = 1; } const int hi = (d - 1 < n) ? d - 1 : n;      // interior cells: 1 <= i <= n, 1 <= j = d - i <= m
 		for (int i = lo + (int)tid; i <= hi; i += (int)nt) {
-			int j = d - i; uint8_t tb;
-			if (i == 0 && j == 0) { M0[0] = 0; X0[0] = (DT)-8; Y0[0] = (DT)-8; tb = 3 | (2 << 2) | (2 << 4); }
-			else if (i == 0) { M0[0] = (DT)(-8 - j); X0[0] = (DT)(-8 - j); Y0[0] = 0; tb = 2 | (2 << 2) | (2 << 4); }
-			else if (j == 0) { M0[i] = (DT)(-8 - i); Y0[i] = (DT)(-8 - i); X0[i] = 0; tb = 1 | (2 << 2) | (2 << 4); }
-			else {
-				int xe = (int)X1[i - 1] - 1, xo = (int)M1[i - 1] - 8; int x, xt; if (xe > xo) { x = xe; xt = 1; } else { x = xo; xt = 0; }
-				int ye = (int)Y1[i] - 1, yo = (int)M1[i] - 8; int y, yt; if (ye > yo) { y = ye; yt = 1; } else { y = yo; yt = 0; }
-				int z = (int)M2[i - 1] + ((S[i - 1] == T[j - 1]) ? 2 : -4); int mt = 0;
-				if (x > z) { z = x; mt = 1; }
-				if (y > z) { z = y; mt = 2; }
-				M0[i] = (DT)z; X0[i] = (DT)x; Y0[i] = (DT)y; tb = (uint8_t)(mt | (xt << 2) | (yt << 4));
-			}
-			tbd[i] = tb;
+			const int j = d - i;
+			const CT up = C1[i - 1], lf = C1[i], dg = C2[i - 1];      // (i-1, j), (i, j-1), (i-1, j-1)
+			int xe = (int)up.x - 1, xo = (int)up.m - 8; int x, xt; if (xe > xo) { x = xe; xt = 1; } else { x = xo; xt = 0; }
+			int ye = (int)lf.y - 1, yo = (int)lf.m - 8; int y, yt; if (ye > yo) { y = ye; yt = 1; } else { y = yo; yt = 0; }
+			int z = (int)dg.m + ((S[i - 1] == T[j - 1]) ? 2 : -4); int mt = 0;
+			if (x > z) { z = x; mt = 1; }
+			if (y > z) { z = y; mt = 2; }
+			CT c; c.m = (decltype(c.m))z; c.x = (decltype(c.m))x; c.y = (decltype(c.m))y; c.pad = 0; C0[i] = c;
+			tbd[i] = (uint8_t)(mt | (xt << 2) | (yt << 4));
 		}
 		lb2_sync();
 	}
@@ -281,8 +296,8 @@ LB2_DEVNI void lb2_align_fill(lb2_win &W)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const uint32_t n = sh->seq_len, m = sh->plen;
-	// the seven score rows as 16-bit values (|score| <= 8 + 4 * (n + m) < 2^15) and the path in the idle shared-memory scratch
-	const uint32_t dpw = (7u * (n + 2u) * 2u + 3u) / 4u, tw = (m + 4u) / 4u;
+	// three anti-diagonals of 16-bit cell records (|score| <= 8 + 4 * (n + m) < 2^15) and the path in the idle shared-memory scratch
+	const uint32_t dpw = 3u * (n + 2u) * 2u, tw = (m + 4u) / 4u;
 	if (dpw <= ws.px_words) {
 		const char *T = ws.pathseq;
 		if (dpw + tw <= ws.px_words) {
@@ -291,8 +306,8 @@ LB2_DEVNI void lb2_align_fill(lb2_win &W)
 			T = Ts;
 			lb2_sync();
 		}
-		lb2_align_fill_t<int16_t>(W, (int16_t *)ws.px, T);
-	} else { lb2_align_fill_t<int32_t>(W, ws.dp, ws.pathseq); }
+		lb2_align_fill_t<lb2_cell16>(W, (lb2_cell16 *)ws.px, T);
+	} else { lb2_align_fill_t<lb2_cell32>(W, (lb2_cell32 *)ws.dp, ws.pathseq); }
 }
 
 // traceback by the first warp.  Every step reads one traceback byte whose address depends on the previous step -- a

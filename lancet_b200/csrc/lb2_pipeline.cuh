@@ -26,7 +26,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	LB2_TAKE(pathseq, char, LB2_MAX_PATH + 16); LB2_TAKE(pcovN, lb2_cov, LB2_MAX_PATH + 16); LB2_TAKE(pcovT, lb2_cov, LB2_MAX_PATH + 16);
 	LB2_TAKE(pnodes, uint32_t, LB2_MAX_PNODES); LB2_TAKE(pdirs, uint8_t, LB2_MAX_PNODES); LB2_TAKE(peidx, uint8_t, LB2_MAX_PNODES);
 	LB2_TAKE(aln_ref, char, LB2_MAX_PATH + LB2_MAX_REF + 16); LB2_TAKE(aln_path, char, LB2_MAX_PATH + LB2_MAX_REF + 16);
-	LB2_TAKE(dp, int32_t, 7 * (LB2_MAX_REF + 2)); LB2_TAKE(tb, uint8_t, (size_t)(LB2_MAX_REF + 1) * (LB2_MAX_PATH + LB2_MAX_REF + 2));      /* anti-diagonal-major */
+	LB2_TAKE(dp, int32_t, 12 * (LB2_MAX_REF + 2)); LB2_TAKE(tb, uint8_t, (size_t)(LB2_MAX_REF + 1) * (LB2_MAX_PATH + LB2_MAX_REF + 2));      /* anti-diagonal-major */
 	LB2_TAKE(trans, lb2_trans, LB2_MAX_TRANS); LB2_TAKE(tstr, char, 2 * (LB2_MAX_PATH + LB2_MAX_REF + 8));
 #undef LB2_TAKE
 	return (off + 255) & ~(size_t)255;
