@@ -155,7 +155,7 @@ class Context:
 
     PHASES = ("stage", "prescan_maxk", "ref_repeat_scan", "kmer_walk", "compact_sort", "mate_replay", "lowq_deficits",
               "table_clear", "ref_coverage", "order_emulation", "lowcov_components", "component_sequential", "bfs_loadpath",
-              "path_repeat_scan", "align", "column_scan_emit", "other", "anchors_cycle1", "compress_sweep", "compress_layout", "compress_cleandead", "compact_links", "compact_fold")
+              "path_repeat_scan", "align", "column_scan_emit", "other", "anchors_cycle1", "compress_sweep", "compress_layout", "compress_cleandead", "compact_links", "compact_fold", "bfs_lane0")
 
     def phase_cycles(self, reset: bool = True) -> dict:
         """lane-0 cycles per pipeline phase, summed over windows since the last reset (debugging aid)."""

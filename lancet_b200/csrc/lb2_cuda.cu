@@ -37,9 +37,12 @@ lb2_window_kernel(const lb2_launch *Lp)
 	// struct handed by reference to the pipeline's functions it sat in per-thread local memory, which with three 72 KB
 	// CTAs per SM has next to no L1 behind it -- every pointer fetch was an L2 round trip
 	__shared__ lb2_win sW;
+	// ... and so do the parameter blocks it points to (read inside lane-0 loops: a global load each time otherwise)
+	__shared__ lb2_params sP; __shared__ lb2_cfg sC; __shared__ lb2_dev_batch sB; __shared__ lb2_dev_out sO;
 	lb2_win &W = sW;
 	if (threadIdx.x == 0) {
-		W.P = &Lp->P; W.C = &Lp->C; W.B = &Lp->B; W.O = &Lp->O; W.escal = (Lp->win_list != nullptr);
+		sP = Lp->P; sC = Lp->C; sB = Lp->B; sO = Lp->O;
+		W.P = &sP; W.C = &sC; W.B = &sB; W.O = &sO; W.escal = (Lp->win_list != nullptr);
 		lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws); W.ws0 = W.ws;
 		W.sh = (lb2_sh *)smem;
 		W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
@@ -457,7 +460,8 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 		// the pool is only streamed from page-locked buffers, otherwise the batch is made resident first
 		bool pinned = batch->n_base_bytes > 0 && batch->n_windows > 0 && env_u32("LB2_STREAM", 1) != 0;
 		// tools that make kernel launches synchronous would park the kernel in front of the copies it waits for
-		if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSYS_PROFILING_SESSION_ID") || env_u32("CUDA_LAUNCH_BLOCKING", 0)) { pinned = false; }
+		if ((getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSYS_PROFILING_SESSION_ID") || env_u32("CUDA_LAUNCH_BLOCKING", 0)) &&
+		    !env_u32("LB2_STREAM_FORCE", 0)) { pinned = false; }      // (LB2_STREAM_FORCE: test hook for the time-out path below)
 		const void *arrs[] = { batch->seq, batch->qual, batch->base_off, batch->flags, batch->name_rank, batch->wr_idx, batch->ref_seq };
 		const uint64_t sizes[] = { batch->n_base_bytes, batch->n_base_bytes, 1, batch->n_reads, batch->n_reads, batch->n_wr, batch->n_ref_bytes };
 		for (int i = 0; i < 7 && pinned; ++i) {

@@ -384,6 +384,13 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT); LB2_GT(d_eov, uint8_t, NT);
 #undef LB2_GT
 		if (tid == 0) { ws.chain = ws.stack; } rows_bytes = (off + 15) & ~(size_t)15;
+		// the node list of the current path (lane-0 code walks it over and over) moves in as well when there is room
+		const size_t pbytes = sizeof(uint32_t) * (2 * (size_t)LB2_MAX_PNODES + 1) + 2 * (size_t)LB2_MAX_PNODES + 16;
+		if (rows_bytes <= Gbytes && rows_bytes + pbytes <= Gbytes && tid == 0) {
+			uint8_t *q = G + rows_bytes;
+			ws.pnodes = (uint32_t *)q; q += sizeof(uint32_t) * LB2_MAX_PNODES; ws.pstart = (uint32_t *)q; q += sizeof(uint32_t) * (LB2_MAX_PNODES + 1);
+			ws.pdirs = q; q += LB2_MAX_PNODES; ws.peidx = q;
+		}
 	}
 	// scratch of the graph stage in the (now dead) packed-read words: list index of every row, then the parallel
 	// compaction's words.  The emulation arrays: three u16[n] here, the rest over the graph region; when either does not
@@ -613,21 +620,23 @@ LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {   // lane 0, after lb
 
 // hasCycle / hasCycleRec with an explicit stack; frame = node << 16 | incoming orientation << 15 | next edge index
 LB2_DEV bool lb2_cycle_from(lb2_win &W, uint32_t start, int ori) {
-	lb2_ws &ws = W.ws; uint32_t *st = ws.stack; uint32_t sp = 0; bool ans = false;
+	lb2_ws &ws = W.ws; uint32_t *const st = ws.stack; uint32_t sp = 0; bool ans = false;
 	const uint32_t cap = W.sh->n_rows + LB2_MAX_SPECIAL;
-	ws.d_color[start] = 2; st[sp++] = (start << 16) | ((uint32_t)ori << 15);
+	// (array bases in registers: the descriptor lives in shared memory and would be re-read behind every store)
+	uint8_t *const COL = ws.d_color; const uint8_t *const NE = ws.d_ne, *const FL = ws.d_flags, *const EOV = ws.d_eov; const lb2_edge *const ED = ws.d_edge, *const EP = ws.e_pool;
+	COL[start] = 2; st[sp++] = (start << 16) | ((uint32_t)ori << 15);
 	while (sp) {
 		uint32_t v = st[sp - 1]; uint32_t node = v >> 16; int o = (int)((v >> 15) & 1); int i = (int)(v & 0x7FFF);
-		if (ans || i >= (int)ws.d_ne[node]) { ws.d_color[node] = 3; --sp; continue; }
+		if (ans || i >= (int)NE[node]) { COL[node] = 3; --sp; continue; }
 		st[sp - 1] = v + 1;
-		lb2_edge ed = lb2_edges(ws, node)[i];
+		const uint32_t ov = EOV[node]; const lb2_edge ed = (ov ? (EP + (size_t)(ov - 1) * LB2_ECAP) : (ED + (size_t)node * LB2_EINL))[i];
 		if (!lb2_is_dir(ed.dir, o)) { continue; }
 		uint32_t other = ed.to;
-		if (lb2_special(W, other)) { continue; }
-		if (ws.d_color[other] == 2) { ans = true; continue; }
-		if (ws.d_color[other] == 1) {
+		if (FL[other] & LB2_NF_SPECIAL) { continue; }
+		if (COL[other] == 2) { ans = true; continue; }
+		if (COL[other] == 1) {
 			if (sp + 1 > cap) { W.sh->err |= 1u << LB2_D_STACK; return true; }
-			ws.d_color[other] = 2; st[sp++] = (other << 16) | ((uint32_t)lb2_dir_dest(ed.dir) << 15);
+			COL[other] = 2; st[sp++] = (other << 16) | ((uint32_t)lb2_dir_dest(ed.dir) << 15);
 		}
 	}
 	return ans;

@@ -148,25 +148,29 @@ LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 	uint32_t qh = 0, qt = 0; int visit = 0; uint32_t best = LB2_NIL; int bestscore = 0;
 	lb2_qent root; root.parent = LB2_NIL; root.node = sh->source; root.len = K; root.score = 0; root.eidx = 0; root.dirflag = 2;   // dir F, flag 1
 	Q_AT(qt) = root; ++qt;
+	// (array bases and scalars in registers: the descriptor lives in shared memory and would be re-read behind every store)
+	const uint8_t *const NE = ws.d_ne, *const FL = ws.d_flags, *const EOV = ws.d_eov; const lb2_edge *const ED = ws.d_edge, *const EP = ws.e_pool;
+	const uint16_t *const LEN = ws.d_len; const uint32_t sink = sh->sink; const int dfs_limit = W.P->dfs_limit, maxlen = reflen + W.P->max_indel_len;
 	while (qh < qt) {
 		++visit;
-		if (W.P->dfs_limit && visit > W.P->dfs_limit) { break; }
+		if (dfs_limit && visit > dfs_limit) { break; }
 		uint32_t idx = qh++; lb2_qent e = Q_AT(idx);
 		uint32_t cur = e.node; int pdir = e.dirflag & 1; int pflag = (e.dirflag >> 1) & 1;
-		if (cur == sh->sink && pflag == 0) {
+		if (cur == sink && pflag == 0) {
 			if (best == LB2_NIL || (int)e.score > bestscore) { best = idx; bestscore = e.score; }
-		} else if (e.len > reflen + W.P->max_indel_len) {
+		} else if (e.len > maxlen) {
 		} else {
-			lb2_edge *ed = lb2_edges(ws, cur); int ne = ws.d_ne[cur];
+			const uint32_t ov = EOV[cur]; const lb2_edge *ed = ov ? (EP + (size_t)(ov - 1) * LB2_ECAP) : (ED + (size_t)cur * LB2_EINL); const int ne = NE[cur];
 			for (int i = 0; i < ne; ++i) {
-				if (!lb2_is_dir(ed[i].dir, pdir)) { continue; }
-				uint32_t other = ed[i].to;
+				const lb2_edge ei = ed[i];
+				if (!lb2_is_dir(ei.dir, pdir)) { continue; }
+				uint32_t other = ei.to;
 				if (qt >= cap) { sh->err |= 1u << LB2_D_QUEUE; return LB2_NIL; }
 				lb2_qent c; c.parent = idx; c.node = other; c.eidx = (uint8_t)i;
-				c.len = e.len + (int)lb2_strlen(W, other) - K + 1;
-				int nflag = pflag * (int)ed[i].flag;
-				c.score = (uint16_t)(e.score + (ed[i].flag == 0 ? 1 : 0));
-				c.dirflag = (uint8_t)(lb2_dir_dest(ed[i].dir) | (nflag << 1));
+				c.len = e.len + (int)((FL[other] & LB2_NF_SPECIAL) ? 0u : (uint32_t)LEN[other]) - K + 1;
+				int nflag = pflag * (int)ei.flag;
+				c.score = (uint16_t)(e.score + (ei.flag == 0 ? 1 : 0));
+				c.dirflag = (uint8_t)(lb2_dir_dest(ei.dir) | (nflag << 1));
 				Q_AT(qt) = c; ++qt;
 			}
 		}

@@ -151,6 +151,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
 						if (sh->path_found) { lb2_load_path(W, best); }
+						lb2_mark(W, LB2_PH_BFS_SEQ);
 					}
 					lb2_sync();
 					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
@@ -179,6 +180,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 						uint32_t best = lb2_bfs(W);
 						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
 						if (sh->path_found) { lb2_load_path(W, best); }
+						lb2_mark(W, LB2_PH_BFS_SEQ);
 					}
 					lb2_sync();
 					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }

@@ -109,7 +109,7 @@ struct lb2_sh {
 // phase ids for the optional cycle profile (lb2_dev_out::prof)
 enum { LB2_PH_STAGE = 0, LB2_PH_PRESCAN, LB2_PH_REFSCAN, LB2_PH_WALK, LB2_PH_COMPACT, LB2_PH_MATES, LB2_PH_LOWQ, LB2_PH_CLEAR,
        LB2_PH_REFCOV, LB2_PH_ORDER, LB2_PH_LOWCOV_CC, LB2_PH_COMP_SEQ, LB2_PH_BFS, LB2_PH_PATHSCAN, LB2_PH_ALIGN, LB2_PH_SCAN, LB2_PH_OTHER,
-       LB2_PH_ANCHOR, LB2_PH_CSWEEP, LB2_PH_CMAT, LB2_PH_CCLEAN, LB2_PH_CP_LINK, LB2_PH_CP_FOLD, LB2_PH_N };
+       LB2_PH_ANCHOR, LB2_PH_CSWEEP, LB2_PH_CMAT, LB2_PH_CCLEAN, LB2_PH_CP_LINK, LB2_PH_CP_FOLD, LB2_PH_BFS_SEQ, LB2_PH_N };
 
 #ifdef __CUDACC__
 #define LB2_HD __host__ __device__ inline

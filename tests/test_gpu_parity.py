@@ -165,3 +165,33 @@ def test_streamed_equals_resident(ctx, monkeypatch):
     bq = b.subset(perm)
     ctx.upload(bq); ctx.run(); ctx.wait(); recp = ctx.download().records()
     assert ctx.process(_pinned(bq)).records() == recp
+
+
+_STALL_SCRIPT = r"""
+import sys, os, json
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from lancet_b200.api import Context
+from lancet_b200.synth import make_batch
+from test_gpu_parity import _pinned
+b = make_batch(seed=53, region_len=8000, var_every=600)
+c = Context(device=0)
+c.upload(b); c.run(); c.wait(); want = c.download().records()
+got = c.process(_pinned(b)).records()
+print(json.dumps({"same": got == want, "n": len(want)}))
+"""
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_stream_timeout_safety_net():
+    """With launches made synchronous (CUDA_LAUNCH_BLOCKING=1) the streamed kernel would wait for copies that the host
+    has not issued yet.  Normally lb2_process detects that and stays resident; with the detection switched off the
+    window fetch must give up after its time-out and the host must redo the batch -- same records, no hang."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", LB2_STREAM_FORCE="1")
+    r = subprocess.run([sys.executable, "-c", _STALL_SCRIPT, root], capture_output=True, text=True, timeout=200, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["same"] and out["n"] > 5
