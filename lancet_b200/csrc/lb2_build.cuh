@@ -263,12 +263,14 @@ template <class KT> LB2_DEV uint32_t lb2_foi_small(lb2_win &W, lb2_sp tk, lb2_sp
 	const uint32_t h = lb2_hash1((uint32_t)canon, sizeof(KT) > 4 ? (uint32_t)((uint64_t)canon >> 32) : 0u);
 	uint32_t i = h & mask;
 	const uint32_t fp = 0x80000000u | ((h >> 22) << 21);
-	// one exit (the loop's end): the lanes of a warp leave the probe sequence at different times and meet again right
-	// behind it, instead of each carrying its own copy of the caller's continuation
-	uint32_t res = LB2_NIL; bool full = true;
-	for (uint32_t probes = 0; probes <= mask; ++probes) {
-		const lb2_sp at = lb2_sp_at(tk, i);
-		uint32_t cur = lb2s_ldv(at);
+	// One exit (the outer loop's end): the lanes of a warp leave the probe sequence at different times and meet again
+	// right behind it.  The inner loop only skips slots of other fingerprints -- three instructions per slot, which is
+	// what the lanes that are already done wait for; bases are fetched and compared once a fingerprint matches.
+	uint32_t res = LB2_NIL, probes = 0; bool full = true;
+	while (true) {
+		lb2_sp at = lb2_sp_at(tk, i); uint32_t cur = lb2s_ldv(at);
+		while (cur != 0 && (cur & 0xFFE00000u) != fp && probes <= mask) { i = (i + 1) & mask; ++probes; at = lb2_sp_at(tk, i); cur = lb2s_ldv(at); }
+		if (probes > mask) { break; }
 		if (cur == 0) {
 			if (!insert) { full = false; break; }
 			cur = lb2s_cas(at, 0u, fp | rep);
@@ -286,7 +288,7 @@ template <class KT> LB2_DEV uint32_t lb2_foi_small(lb2_win &W, lb2_sp tk, lb2_sp
 				res = i; full = false; break;
 			}
 		}
-		i = (i + 1) & mask;
+		i = (i + 1) & mask; ++probes;
 	}
 	if (full) { lb2_or32(&W.sh->err, 1u << LB2_D_HASH_FULL); }
 	return res;

@@ -195,3 +195,54 @@ def test_stream_timeout_safety_net():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["same"] and out["n"] > 5
+
+
+@pytest.mark.parametrize("mink,maxk", [(7, 9), (9, 15), (15, 17)])
+def test_small_k(mink, maxk):
+    """k below 11 switches the repeat scan's word filter off (every word takes the exact rule); k <= 16 is the
+    32-bit k-mer walk, 17 the first 64-bit one."""
+    import run_ref
+    if not run_ref.available():
+        pytest.skip("oracle/_ref/ref_windows not built")
+    from lancet_b200.synth import make_batch
+    b = make_batch(seed=91, region_len=2500, var_every=300)
+    want, _ = run_ref.run(b, threads=8, min_k=mink, max_k=maxk)
+    c = _ctx(min_k=mink, max_k=maxk)
+    res = c.process(b)
+    assert (res.windows["status"] < 3).all()
+    assert res.records() == want
+    c.close()
+
+
+def test_long_reads_and_ragged_trims(ctx):
+    """250 bp reads (two rounds of 16-base chunks per 8-lane group), N bases and low-quality runs at both ends and
+    inside reads (Graph_t::trim: 5'/3' trims, junk reads), reads shorter than k after trimming."""
+    import run_ref
+    if not run_ref.available():
+        pytest.skip("oracle/_ref/ref_windows not built")
+    from lancet_b200.synth import make_batch
+    from lancet_b200.batch import Batch
+    b = make_batch(seed=92, region_len=3000, read_len=250, cov_t=50, cov_n=50, var_every=400)
+    rng = np.random.default_rng(5)
+    seq = b.seq.copy(); qual = b.qual.copy()
+    for r in range(b.n_reads):
+        o0, o1 = int(b.base_off[r]), int(b.base_off[r + 1]); n = o1 - o0
+        u = rng.random()
+        if u < 0.15:      # low-quality 5' and 3' tails of random length
+            a, z = int(rng.integers(0, 40)), int(rng.integers(0, 40))
+            qual[o0:o0 + a] = 33 + 5; qual[o1 - z:o1] = 33 + 5 if z else qual[o1 - z:o1]
+        elif u < 0.22:    # N at the ends (trimmed) ...
+            seq[o0:o0 + int(rng.integers(1, 5))] = ord("N"); seq[o1 - int(rng.integers(1, 5)):o1] = ord("N")
+        elif u < 0.26:    # ... or in the middle (junk read)
+            seq[o0 + n // 2] = ord("N")
+        elif u < 0.29:    # almost everything low quality: shorter than k after the trim
+            qual[o0:o1 - 8] = 33 + 3
+        elif u < 0.31:    # nothing left
+            qual[o0:o1] = 33 + 2
+    b2 = Batch(ref_off=b.ref_off, ref_start=b.ref_start, chr_id=b.chr_id, wr_off=b.wr_off, wr_idx=b.wr_idx,
+               base_off=b.base_off, flags=b.flags, name_rank=b.name_rank, ref_seq=b.ref_seq, seq=seq, qual=qual)
+    want, _ = run_ref.run(b2, threads=8)
+    res = ctx.process(b2)
+    assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
+    assert res.records() == want
+    assert len(want) > 5
