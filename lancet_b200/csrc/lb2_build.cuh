@@ -395,8 +395,9 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 	}
 }
 
-// the same work item for one-word k-mers: little-endian f / rc for the table, big-endian copies so that the reference's
-// string comparison mer < rc is one integer compare; one mask update per k-mer (the bits a k-mer receives as the v of one
+// the same work item for one-word k-mers.  With base i at bits [2i, 2i+1], the reverse complement's integer is
+// (4^K - 1) minus the base-0-first ("big-endian") integer of the k-mer, so the reference's string comparison
+// mer < rc is the integer comparison rc > f of the two little-endian words the walk rolls anyway; one mask update per k-mer (the bits a k-mer receives as the v of one
 // pair and as the u of the next are merged).  Warp-converged: EVERY lane of the warp calls it (active = false: no item),
 // the pair loop runs to the warp's longest piece with the lanes re-joined at the top of every round.
 template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_t g0, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
@@ -408,14 +409,13 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	// (array bases in registers: the descriptor lives in shared memory and would be re-read behind every store)
 	uint16_t *inst_p = ws.inst + ibase + (size_t)o_begin * istride; uint32_t *const GC = ws.g_cnt + (cls >> 1); uint32_t *const RN = ws.refnode;
 	const int topsh = 2 * (K - 1); const KT kmask = (KT)(~(KT)0) >> (sizeof(KT) * 8 - 2 * K);
-	KT f = 0, rc = 0, fB = 0, rcB = 0;
+	KT f = 0, rc = 0;
 	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
 	if (active) {
 		for (int i = 0; i < K; ++i, ++g) {          // first K bases
 			if ((g & 15) == 0 || i == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
 			const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
 			f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
-			fB = ((fB << 2) | (KT)c) & kmask; rcB = (rcB >> 2) | ((KT)(3u - c) << topsh);
 		}
 	}
 	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
@@ -423,7 +423,7 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	const uint32_t cadd = (cls & 1) ? 0x10000u : 1u;
 	int lowcnt = 0;    // low-quality bases in [o, o+K-1]; the pair window adds base o+K
 	if (track_q) { for (int i = 0; i < K; ++i) { lowcnt += lb2_getbit(W.lowq, g0 + o_begin + i); } }
-	bool fless = fB < rcB;
+	bool fless = rc > f;
 	uint32_t ori_u = fless ? 0u : 1u, su = LB2_NIL, pend = 0;      // pend: mask bits owed to su
 	if (active) {
 		su = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o_begin) << 1) | ori_u, kmask, true);
@@ -445,8 +445,7 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 		const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
 		const uint32_t a = (uint32_t)f & 3u;                           // base that leaves the window (first base of u)
 		f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
-		fB = ((fB << 2) | (KT)c) & kmask; rcB = (rcB >> 2) | ((KT)(3u - c) << topsh);
-		fless = fB < rcB;
+		fless = rc > f;
 		const uint32_t ori_v = fless ? 0u : 1u;
 		const uint32_t sv = lb2_foi_small<KT>(W, tk, bits, mask, fless ? f : rc, fless ? rc : f, ((g0 + o + 1) << 1) | ori_v, kmask, true);
 		uint32_t emu = 1u << (ori_u * 4 + c);                         // u leaves in orientation ori_u appending c
@@ -497,12 +496,16 @@ LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2)
 
 // reverse complement: complement, reverse the 2-bit groups of the 256-bit integer, shift down to 2K bits
 LB2_DEV uint64_t lb2_rev2(uint64_t x) {
+#ifndef LB2_HOSTSIM
+	{ const uint64_t y = __brevll(x); return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1); }      // bit reversal, then the two bits of every base back in order
+#endif
 	x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
 	x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
 	x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
 	x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
 	return (x >> 32) | (x << 32);
 }
+LB2_DEV uint64_t lb2_revcomp1(uint64_t f, int K) { return lb2_rev2(~f) >> (64 - 2 * K); }      // one-word k-mer (K <= 32)
 template <int NWT = LB2_MAXW> LB2_DEV void lb2_revcomp(const lb2_kmer &f, int K, lb2_kmer &rc) {
 	const int nw = lb2_nw(K);
 	uint64_t t[NWT];
@@ -540,7 +543,26 @@ template <int NWT> LB2_DEV void lb2_node_edges(lb2_win &W, bool act, uint32_t j,
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const uint32_t gl = lb2_glane();
 	uint32_t livemask = 0; lb2_bedge edl[8 / LB2_GS];
-	if (act) {
+	if (act && NWT == 1) {      // one-word k-mers as plain 64-bit integers (mer < rc  <=>  rc > mer as integers, see lb2_walk_small)
+		const uint32_t em = ws.g_em[j] & 0xFFu, rep = ws.b_rep[j];
+		const uint64_t kmask = (~0ull) >> (64 - 2 * K); const int topsh = 2 * (K - 1);
+		const lb2_sp tk = lb2_sp_of(W.t_key), bits = lb2_sp_of(W.bits); const uint32_t mask = W.C->table_slots - 1;
+		uint64_t c0 = lb2_extract_small<uint64_t>(bits, rep >> 1) & kmask;
+		if (rep & 1u) { c0 = lb2_revcomp1(c0, K); }
+		const uint64_t c1 = lb2_revcomp1(c0, K);
+		for (uint32_t t = gl; t < 8; t += LB2_GS) {
+			if (!(em & (1u << t))) { continue; }
+			const uint32_t o = t >> 2, b = t & 3u;
+			const uint64_t V = ((o ? c1 : c0) >> 2) | ((uint64_t)b << topsh), Vr = lb2_revcomp1(V, K);
+			const bool fl = Vr > V;
+			const uint32_t ts = lb2_foi_small<uint64_t>(W, tk, bits, mask, fl ? V : Vr, fl ? Vr : V, 0, kmask, false);
+			if (ts == LB2_NIL) { lb2_or32(&sh->err, 1u << LB2_D_EDGES); continue; }
+			const uint32_t to = W.t_id[ts] & 0x7FFFu;
+			if (ws.b_flags[to] & LB2_NF_DEAD) { continue; }
+			lb2_bedge ed; ed.to = to; ed.dir = o * 2 + (fl ? 0u : 1u); ed.flag = 0; ed.type = t;
+			edl[t / LB2_GS] = ed; livemask |= 1u << t;
+		}
+	} else if (act) {
 		const uint32_t em = ws.g_em[j] & 0xFFu;
 		lb2_kmer C0; lb2_rep_kmer<NWT>(W, ws.b_rep[j], K, C0);
 		lb2_kmer C1; lb2_revcomp<NWT>(C0, K, C1);
