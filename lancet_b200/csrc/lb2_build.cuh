@@ -267,8 +267,10 @@ template <class KT> LB2_DEV uint32_t lb2_foi_small(lb2_win &W, lb2_sp tk, lb2_sp
 	// right behind it.  The inner loop only skips slots of other fingerprints -- three instructions per slot, which is
 	// what the lanes that are already done wait for; bases are fetched and compared once a fingerprint matches.
 	uint32_t res = LB2_NIL, probes = 0; bool full = true;
+#pragma unroll 1
 	while (true) {
 		lb2_sp at = lb2_sp_at(tk, i); uint32_t cur = lb2s_ldv(at);
+#pragma unroll 1
 		while (cur != 0 && (cur & 0xFFE00000u) != fp && probes <= mask) { i = (i + 1) & mask; ++probes; at = lb2_sp_at(tk, i); cur = lb2s_ldv(at); }
 		if (probes > mask) { break; }
 		if (cur == 0) {
@@ -395,13 +397,14 @@ template <int NWT> LB2_DEV void lb2_walk(lb2_win &W, uint32_t g0, uint32_t n, ui
 	}
 }
 
+LB2_DEV uint64_t lb2_revcomp1(uint64_t f, int K);
 // the same work item for one-word k-mers.  With base i at bits [2i, 2i+1], the reverse complement's integer is
 // (4^K - 1) minus the base-0-first ("big-endian") integer of the k-mer, so the reference's string comparison
 // mer < rc is the integer comparison rc > f of the two little-endian words the walk rolls anyway; one mask update per k-mer (the bits a k-mer receives as the v of one
 // pair and as the u of the next are merged).  Warp-converged: EVERY lane of the warp calls it (active = false: no item),
 // the pair loop runs to the warp's longest piece with the lanes re-joined at the top of every round.
-template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_t g0, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
-                      bool isref, uint32_t cls, int K)
+template <class KT, bool isref> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_t g0, uint32_t o_begin, uint32_t o_end, uint32_t ibase, uint32_t istride,
+                      uint32_t cls, int K)
 {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	const lb2_sp tk = lb2_sp_of(W.t_key), tidw = lb2_sp_of(W.t_id), bits = lb2_sp_of(W.bits);
@@ -411,12 +414,11 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	const int topsh = 2 * (K - 1); const KT kmask = (KT)(~(KT)0) >> (sizeof(KT) * 8 - 2 * K);
 	KT f = 0, rc = 0;
 	uint32_t wordbuf = 0; uint32_t g = g0 + o_begin;
-	if (active) {
-		for (int i = 0; i < K; ++i, ++g) {          // first K bases
-			if ((g & 15) == 0 || i == 0) { wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4)); }
-			const uint32_t c = (wordbuf >> ((g & 15) << 1)) & 3u;
-			f = (f >> 2) | ((KT)c << topsh); rc = ((rc << 2) | (KT)(3u - c)) & kmask;
-		}
+	if (active) {      // the piece's first k-mer straight from the packed bases
+		f = lb2_extract_small<KT>(bits, g) & kmask;
+		rc = (KT)lb2_revcomp1((uint64_t)f, K);
+		g += (uint32_t)K;
+		wordbuf = lb2s_ld(lb2_sp_at(bits, g >> 4));
 	}
 	const bool tumor = !isref && cls < 2, normal = !isref && cls >= 2;
 	const bool track_q = active && tumor && sh->has_lowq;
@@ -438,6 +440,7 @@ template <class KT> LB2_DEV void lb2_walk_small(lb2_win &W, bool active, uint32_
 	}
 	const uint32_t nsteps = (active && su != LB2_NIL) ? (o_end - o_begin) : 0u, maxsteps = lb2_warp_max(nsteps);
 	uint32_t o = o_begin;
+#pragma unroll 1
 	for (uint32_t st = 0; st < maxsteps; ++st) {
 		lb2_warp_sync();
 		if (st >= nsteps || su == LB2_NIL) { continue; }
@@ -657,9 +660,14 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
 			active = true; isref = true; g0 = sh->ref_g; n = L; ib = sh->inst_ref; st = 1u;
 		}
-		if (K <= 16) { lb2_walk_small<uint32_t>(W, active, g0, ob, oe, ib, st, isref, cls, K); }
-		else if (nw == 1) { lb2_walk_small<uint64_t>(W, active, g0, ob, oe, ib, st, isref, cls, K); }
-		else if (active) {
+		const bool hasreads = (it & ~31u) < NP * R, hasref = (it | 31u) >= NP * R;      // (the same for all lanes of the warp)
+		if (K <= 16) {
+			if (hasreads) { lb2_walk_small<uint32_t, false>(W, active && !isref, g0, ob, oe, ib, st, cls, K); }
+			if (hasref) { lb2_walk_small<uint32_t, true>(W, active && isref, g0, ob, oe, ib, st, cls, K); }
+		} else if (nw == 1) {
+			if (hasreads) { lb2_walk_small<uint64_t, false>(W, active && !isref, g0, ob, oe, ib, st, cls, K); }
+			if (hasref) { lb2_walk_small<uint64_t, true>(W, active && isref, g0, ob, oe, ib, st, cls, K); }
+		} else if (active) {
 			if (nw == 2) { lb2_walk<2>(W, g0, n, ob, oe, ib, st, isref, cls, K, nw); }
 			else { lb2_walk<LB2_MAXW>(W, g0, n, ob, oe, ib, st, isref, cls, K, nw); }
 		}
