@@ -468,14 +468,16 @@ LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
 	double thr = W.P->min_cov_ratio * avgcov;
+	uint32_t removed = 0;
 	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
 		if (ws.d_comp[p] != compid) { continue; }
 		if (lb2_special(W, p)) { continue; }
 		int mq = ws.d_mincovqv[p];
 		float tt = ws.d_cov[p * 4 + 0] + ws.d_cov[p * 4 + 1], tn = ws.d_cov[p * 4 + 2] + ws.d_cov[p * 4 + 3];
-		if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { lb2_remove_node(W, p); }
+		if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { lb2_remove_node(W, p); ++removed; }
 	}
-	lb2_clean_dead(W);
+	sh->flag_b = removed;      // (nothing removed: the graph is still fully compacted and the compaction that follows is a no-op)
+	if (removed) { lb2_clean_dead(W); }
 }
 
 // Graph_t::markConnectedComponents (src/Graph.cc:2252-2336) by all lanes: the reference numbers a component when its
@@ -754,33 +756,55 @@ LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
 LB2_DEVNI void lb2_materialize(lb2_win &W) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const lb2_job *jobs = (const lb2_job *)ws.jobs;
-	for (uint32_t q = 0; q < sh->n_jobs; ++q) {
-		lb2_job jb = jobs[q];
+	const uint32_t njobs = sh->n_jobs;
+	if (!njobs) { return; }
+	// one member's contribution: `count` bases from position `first` of node `id` (reverse-complemented when flip) to
+	// position dst of its job's unitig; lanes `l0, l0 + lstep, ...` of the member take part
+	auto put = [&](const lb2_job &jb, uint32_t m, uint32_t l0, uint32_t lstep, int &mn, int &mnq) {
 		char *S = (char *)ws.arena + jb.so; lb2_cov *CT = (lb2_cov *)(ws.arena + jb.co); lb2_cov *CN = CT + jb.curlen;
-		int mn = 10000000, mnq = 10000000;
-		// many short members (first compaction: single k-mer nodes): one lane per member; a few long ones (later
-		// compactions merge unitigs): the members in turn, lanes across the bases
-		const bool by_member = jb.nAll + 1 >= 64;
-		for (uint32_t m = by_member ? tid : 0u; m <= jb.nAll; m += by_member ? nt : 1u) {
-			uint32_t id, first, count, dst; bool flip;
-			if (m == jb.nAll) { id = jb.node; flip = false; first = 0; count = jb.len0; dst = jb.leftlen; }
-			else {
-				uint32_t ce = ws.chain[jb.cbeg + m]; id = ce & 0x7FFFFFFFu; flip = (ce >> 31) != 0;
-				uint32_t bl = ws.d_len[id]; count = bl - K + 1; const uint32_t pre = ws.cpos[jb.cbeg + m] - ws.cpos[jb.cbeg];
-				dst = (m < jb.nF) ? jb.leftlen + jb.len0 + pre : jb.leftlen - (pre - (ws.cpos[jb.cbeg + jb.nF] - ws.cpos[jb.cbeg]) + count);
-				first = (m < jb.nF) ? (uint32_t)K - 1 : 0;       // F: oriented[K-1..], R: frame[0..bl-K]
-			}
-			lb2_nview v; lb2_view(W, id, v);
-			for (uint32_t i = by_member ? 0u : tid; i < count; i += by_member ? 1u : nt) {
-				uint32_t o = first + i, src = flip ? (v.len - 1 - o) : o;
-				char ch = lb2_vchar(W, v, src); S[dst + i] = flip ? lb2_comp(ch) : ch;
-				lb2_cov ct = lb2_vcov(W, v, src, 0), cn = lb2_vcov(W, v, src, 1);
-				CT[dst + i] = ct; CN[dst + i] = cn;
-				int t = ct.fwd + ct.rev + cn.fwd + cn.rev, qq = ct.mqf + ct.mqr + cn.mqf + cn.mqr;
-				if (t < mn) { mn = t; } if (qq < mnq) { mnq = qq; }
-			}
+		uint32_t id, first, count, dst; bool flip;
+		if (m == jb.nAll) { id = jb.node; flip = false; first = 0; count = jb.len0; dst = jb.leftlen; }
+		else {
+			uint32_t ce = ws.chain[jb.cbeg + m]; id = ce & 0x7FFFFFFFu; flip = (ce >> 31) != 0;
+			uint32_t bl = ws.d_len[id]; count = bl - K + 1; const uint32_t pre = ws.cpos[jb.cbeg + m] - ws.cpos[jb.cbeg];
+			dst = (m < jb.nF) ? jb.leftlen + jb.len0 + pre : jb.leftlen - (pre - (ws.cpos[jb.cbeg + jb.nF] - ws.cpos[jb.cbeg]) + count);
+			first = (m < jb.nF) ? (uint32_t)K - 1 : 0;       // F: oriented[K-1..], R: frame[0..bl-K]
 		}
-		if (mn != 10000000) { lb2g_min32((uint32_t *)&ws.d_mincov[jb.node], (uint32_t)mn); lb2g_min32((uint32_t *)&ws.d_mincovqv[jb.node], (uint32_t)mnq); }
+		lb2_nview v; lb2_view(W, id, v);
+		for (uint32_t i = l0; i < count; i += lstep) {
+			uint32_t o = first + i, src = flip ? (v.len - 1 - o) : o;
+			char ch = lb2_vchar(W, v, src); S[dst + i] = flip ? lb2_comp(ch) : ch;
+			lb2_cov ct = lb2_vcov(W, v, src, 0), cn = lb2_vcov(W, v, src, 1);
+			CT[dst + i] = ct; CN[dst + i] = cn;
+			int t = ct.fwd + ct.rev + cn.fwd + cn.rev, qq = ct.mqf + ct.mqr + cn.mqf + cn.mqr;
+			if (t < mn) { mn = t; } if (qq < mnq) { mnq = qq; }
+		}
+	};
+	const uint32_t totc = jobs[njobs - 1].cbeg + jobs[njobs - 1].nAll;      // chain slots of all jobs (jobs are in slot order)
+	if (totc + njobs >= 64) {
+		// many members (first compaction: hundreds of single k-mer nodes in a dozen unitigs): one lane per member over ALL
+		// jobs at once; the member's job is found by bisection on the jobs' first slots
+		for (uint32_t it = tid; it < totc + njobs; it += nt) {
+			uint32_t q, m;
+			if (it < totc) {
+				uint32_t lo = 0, hi = njobs;
+				while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (jobs[mid].cbeg <= it) { lo = mid; } else { hi = mid; } }
+				q = lo; m = it - jobs[q].cbeg;
+			} else { q = it - totc; m = jobs[q].nAll; }
+			const lb2_job jb = jobs[q];
+			if (m > jb.nAll) { continue; }      // (a seed without absorbed nodes owns no slots: cannot be hit, kept as a guard)
+			int mn = 10000000, mnq = 10000000;
+			put(jb, m, 0u, 1u, mn, mnq);
+			if (mn != 10000000) { lb2g_min32((uint32_t *)&ws.d_mincov[jb.node], (uint32_t)mn); lb2g_min32((uint32_t *)&ws.d_mincovqv[jb.node], (uint32_t)mnq); }
+		}
+	} else {
+		// a few long members (later compactions merge unitigs): job by job, member by member, lanes across the bases
+		for (uint32_t q = 0; q < njobs; ++q) {
+			const lb2_job jb = jobs[q];
+			int mn = 10000000, mnq = 10000000;
+			for (uint32_t m = 0; m <= jb.nAll; ++m) { put(jb, m, tid, nt, mn, mnq); }
+			if (mn != 10000000) { lb2g_min32((uint32_t *)&ws.d_mincov[jb.node], (uint32_t)mn); lb2g_min32((uint32_t *)&ws.d_mincovqv[jb.node], (uint32_t)mnq); }
+		}
 	}
 }
 

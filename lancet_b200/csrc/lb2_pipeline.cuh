@@ -133,7 +133,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				if (!sh->flag_c && !sh->err) {
 					if (tid == 0 && !sh->err) { lb2_remove_lowcov(W, c); }      // removeLowCov(true,c): sweep, cleanDead, then compress
 					lb2_sync();
-					if (!sh->err) { lb2_compress(W, c); }
+					if (!sh->err && sh->flag_b) { lb2_compress(W, c); }          // (compaction is idempotent: skipped when the sweep removed nothing)
 					if (!sh->err) { lb2_remove_tips(W, c); }
 					if (!sh->err) { lb2_remove_short_links(W, c); }
 					if (tid == 0 && !sh->err) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
