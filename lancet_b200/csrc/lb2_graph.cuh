@@ -476,7 +476,7 @@ LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
 		float tt = ws.d_cov[p * 4 + 0] + ws.d_cov[p * 4 + 1], tn = ws.d_cov[p * 4 + 2] + ws.d_cov[p * 4 + 3];
 		if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { lb2_remove_node(W, p); ++removed; }
 	}
-	sh->flag_b = removed;      // (nothing removed: the graph is still fully compacted and the compaction that follows is a no-op)
+	sh->flag_b = removed; sh->n_changed = removed;      // (nothing removed: the graph is still fully compacted and the compaction that follows is a no-op)
 	if (removed) { lb2_clean_dead(W); }
 }
 
@@ -1120,7 +1120,7 @@ LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {      // all lanes
 				int deg = ws.d_ne[p]; int len = (int)lb2_strlen(W, p) - K + 1;
 				if (deg <= 1 && len < W.P->max_tip_len) { lb2_remove_node(W, p); ++tips; }
 			}
-			sh->flag_b = (uint32_t)tips;
+			sh->flag_b = (uint32_t)tips; sh->n_changed += (uint32_t)tips;
 		}
 		lb2_sync();
 		if (!sh->flag_b || sh->err) { break; }
@@ -1145,7 +1145,7 @@ LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {   // all lanes
 				if (LEN == 0) { lb2_remove_node(W, p); ++links; }
 			}
 		}
-		sh->flag_b = (uint32_t)links;
+		sh->flag_b = (uint32_t)links; sh->n_changed += (uint32_t)links;
 	}
 	lb2_sync();
 	if (sh->flag_b && !sh->err) { lb2_compress(W, compid); }

@@ -585,6 +585,10 @@ LB2_DEVNI void lb2_process_path(lb2_win &W)
 	lb2_sync();
 	if (tid == 0) { sh->need_align = (!samelen || sh->flag_b > 5) ? 1u : 0u; if (!sh->need_align) { sh->aln_len = sh->plen; } }
 	lb2_sync();
+	if (samelen && sh->flag_b == 0) {      // the path IS the reference: every column is '=', no transcript, nothing to emit
+		lb2_mark(W, LB2_PH_ALIGN);
+		return;
+	}
 	if (sh->need_align) {
 		lb2_align_fill(W);
 		lb2_align_trace(W);

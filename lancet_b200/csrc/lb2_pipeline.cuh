@@ -136,7 +136,8 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 					if (!sh->err && sh->flag_b) { lb2_compress(W, c); }          // (compaction is idempotent: skipped when the sweep removed nothing)
 					if (!sh->err) { lb2_remove_tips(W, c); }
 					if (!sh->err) { lb2_remove_short_links(W, c); }
-					if (tid == 0 && !sh->err) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+					// (the graph the first check called acyclic is only checked again if one of the three sweeps changed it)
+					if (tid == 0 && !sh->err && sh->n_changed) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
 				}
 				lb2_mark(W, LB2_PH_COMP_SEQ);
 				lb2_sync();
@@ -173,19 +174,25 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				}
 				lb2_sync();
 				if (rpt) { retry = true; break; }
-				// ---- eka: repeat { best path; processPath; flag its edges }
+				// ---- eka: repeat { best path; processPath; flag its edges }.  The enumeration is the one the loop above just did
+				// (same graph, flags cleared): if that found exactly one path, the path is still loaded and copied and there is
+				// nothing to search for, neither now nor after it has been flagged
+				const bool single = (nflag == 1);
 				for (uint32_t round = 0; ; ++round) {
 					if (round > 8 * LB2_MAX_ROWS) { if (tid == 0) { sh->err |= 1u << LB2_D_STACK; } lb2_sync(); break; }
-					if (tid == 0) {
-						uint32_t best = lb2_bfs(W);
-						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
-						if (sh->path_found) { lb2_load_path(W, best); }
-						lb2_mark(W, LB2_PH_BFS_SEQ);
+					if (single) { if (round == 1) { break; } }
+					else {
+						if (tid == 0) {
+							uint32_t best = lb2_bfs(W);
+							sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
+							if (sh->path_found) { lb2_load_path(W, best); }
+							lb2_mark(W, LB2_PH_BFS_SEQ);
+						}
+						lb2_sync();
+						if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
+						lb2_copy_path(W);
+						lb2_mark(W, LB2_PH_BFS);
 					}
-					lb2_sync();
-					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
-					lb2_copy_path(W);
-					lb2_mark(W, LB2_PH_BFS);
 					lb2_process_path(W);
 					if (sh->err) { break; }
 					if (tid == 0) { lb2_flag_path(W, 1); }

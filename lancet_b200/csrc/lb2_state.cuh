@@ -98,7 +98,7 @@ struct lb2_sh {
 	// output
 	uint32_t n_var, str_used, n_k_tried, final_k, last_nodes;
 	int32_t  numcomp;
-	uint32_t stop_k; uint32_t n_dead; uint32_t big;
+	uint32_t stop_k; uint32_t n_dead; uint32_t big; uint32_t n_changed;      // n_changed: nodes removed by the sweeps since the first compaction
 	uint32_t maxnk, inst_stride, inst_ref;     // occurrence array layout of this (window,k): see lb2_build.cuh
 	uint32_t walk_next, walk_pl, walk_np;      // k-mer walk: work-item counter, pairs per piece, pieces per read
 	uint32_t n_tev, tev_ovf; lb2_tev tev[LB2_MAX_TEV];     // tandem repeats of the loaded path (n_tev = LB2_NIL: not computed, scan per variant)
