@@ -569,6 +569,22 @@ LB2_DEVNI void lb2_scan_alignment(lb2_win &W)      // all lanes
 	if (lb2_tid() == 0) { lb2_scan_columns(W, pre, lst, nne); }
 }
 
+// does the loaded path spell exactly the trimmed reference?  (all lanes)
+LB2_DEVNI bool lb2_path_is_ref(lb2_win &W)
+{
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	if (sh->seq_len != sh->plen) { return false; }
+	if (tid == 0) { sh->flag_b = 0; }
+	lb2_sync();
+	const char *S = W.ref_raw + sh->seq_off; bool diff = false;
+	for (uint32_t i = tid; i < sh->plen; i += nt) { if (S[i] != ws.pathseq[i]) { diff = true; } }
+	if (diff) { sh->flag_b = 1; }
+	lb2_sync();
+	const bool same = sh->flag_b == 0;
+	lb2_sync();      // (flag_b is reused right away)
+	return same;
+}
+
 // processPath for the path loaded in ws.pathseq (all lanes: the alignment is CTA-wide)
 LB2_DEVNI void lb2_process_path(lb2_win &W)
 {

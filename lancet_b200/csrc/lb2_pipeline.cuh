@@ -158,10 +158,15 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
 					lb2_copy_path(W);
 					lb2_mark(W, LB2_PH_BFS);
-					lb2_pack_path(W, W.ws.cpos);               // cpos is idle outside lb2_compress
-					lb2_diag_scan(W, W.ws.cpos, 0, (int)sh->plen, P->max_mismatch);
-					lb2_mark(W, LB2_PH_PATHSCAN);
-					if ((uint32_t)k + 1 <= sh->scan_wmax) { rpt = true; break; }
+					// A path that spells the (trimmed) reference is a substring of the window reference: every window of every
+					// diagonal inside it exists in the window's own scan, whose wmax this k has already passed (k + 1 >
+					// ref_wmax, or the k loop would have skipped this k) -- no need to scan it again
+					if (!lb2_path_is_ref(W)) {
+						lb2_pack_path(W, W.ws.cpos);               // cpos is idle outside lb2_compress
+						lb2_diag_scan(W, W.ws.cpos, 0, (int)sh->plen, P->max_mismatch);
+						lb2_mark(W, LB2_PH_PATHSCAN);
+						if ((uint32_t)k + 1 <= sh->scan_wmax) { rpt = true; break; }
+					}
 					if (tid == 0) { lb2_flag_path(W, 1); }
 					++nflag;
 					lb2_sync();
