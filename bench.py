@@ -123,6 +123,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the lancet_b200 hot path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from lancet_b200.api import Context
 
