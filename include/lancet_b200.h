@@ -145,8 +145,15 @@ void lb2_destroy(lb2_ctx *ctx);
 const char *lb2_strerror(const lb2_ctx *ctx, int code);
 
 /* End-to-end call (the drop-in for "addAlignment* ; processGraph" over many windows):
- * host batch in -> H2D -> kernels -> D2H -> host result out. */
+ * host batch in -> H2D -> kernels -> D2H -> host result out.  When the batch arrays are page-locked
+ * (lb2_alloc_pinned below, cudaHostAlloc, cudaHostRegister) the copy runs behind the kernels: windows are
+ * assembled as soon as their reads have arrived.  Pageable arrays give the same result, copy first. */
 int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *result);
+
+/* page-locked host memory for batch arrays, for callers that do not link the CUDA runtime themselves
+ * (NULL when there is no device or no memory) */
+void *lb2_alloc_pinned(size_t bytes);
+void  lb2_free_pinned(void *p);
 
 /* Split-phase variant for callers that keep batches resident in HBM (and for bench.py):
  * upload copies the batch to the device, run executes the pipeline on the resident batch

@@ -550,6 +550,9 @@ extern "C" uint32_t lb2_smem_per_cta(const lb2_ctx *ctx) { return ctx ? ctx->C.s
 extern "C" int lb2_wait(lb2_ctx *ctx) { if (!ctx) return LB2_ERR_ARG; LB2_CK(cudaStreamSynchronize(ctx->stream)); return LB2_OK; }
 extern "C" float lb2_last_kernel_ms(lb2_ctx *ctx) { if (!ctx) return 0; float ms = 0; cudaEventSynchronize(ctx->ev1); cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); return ms; }
 
+extern "C" void *lb2_alloc_pinned(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+extern "C" void lb2_free_pinned(void *p) { if (p) { cudaFreeHost(p); } }
+
 extern "C" int lb2_rank_names(const char *const *names, uint32_t n, uint32_t *rank_out)
 {
 	if (!names || !rank_out) { return LB2_ERR_ARG; }
