@@ -88,7 +88,8 @@ __global__ void lb2_collect_kernel(const lb2_launch *Lp)
 		if (wi.status == LB2_WIN_OVERFLOW) {
 			uint32_t d = wi.detail;
 			if (d == LB2_D_HASH_FULL || d == LB2_D_NODES || d == LB2_D_ARENA || d == LB2_D_QUEUE || d == LB2_D_SMEM || d == LB2_D_BUCKETS ||
-			    d == LB2_D_STACK || d == LB2_D_EDGES || d == LB2_D_SPECIAL || d == LB2_D_READS) {
+			    d == LB2_D_STACK || d == LB2_D_EDGES || d == LB2_D_SPECIAL || d == LB2_D_READS ||
+			    d == LB2_D_VARIANTS || d == LB2_D_STRINGS) {      // (escalated windows emit into the large output slabs)
 				Lp->retry_list[atomicAdd(Lp->retry_count, 1u)] = w;
 			}
 		}

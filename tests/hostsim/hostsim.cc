@@ -100,6 +100,7 @@ int main(int argc, char **argv)
 	if (getenv("LB2_SIM_TS")) { C.table_slots = atoi(getenv("LB2_SIM_TS")); C.max_nodes = C.table_slots - C.table_slots / 4; }
 	if (getenv("LB2_SIM_BP")) { C.max_bp = atoi(getenv("LB2_SIM_BP")); }
 	if (getenv("LB2_SIM_GB")) { C.graph_bytes = atoi(getenv("LB2_SIM_GB")); }
+	if (getenv("LB2_SIM_MAXVAR")) { C.max_var = atoi(getenv("LB2_SIM_MAXVAR")); C.str_bytes = 128u << 10; }
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
 	B.base_off = base_off.data(); B.flags = flags.data(); B.name_rank = name_rank.data(); B.ref_seq = ref_seq.data(); seq.resize(seq.size() + 64, 0); qual.resize(qual.size() + 64, 0);      /* the staging reads 16 bytes at a time (the device buffers have the same slack) */
 	B.seq = seq.data(); B.qual = qual.data();

@@ -246,3 +246,22 @@ def test_long_reads_and_ragged_trims(ctx):
     assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
     assert res.records() == want
     assert len(want) > 5
+
+
+def test_many_records_per_window(ctx):
+    """windows with more records than a first-pass output slab holds (32) are redone by the escalation pass, which emits
+    into the large slabs: dense variants + 0.8 % errors at 100x give up to ~130 records in one window"""
+    import run_ref
+    if not run_ref.available():
+        pytest.skip("oracle/_ref/ref_windows not built")
+    from collections import Counter
+    from lancet_b200.api import Context, Params
+    from lancet_b200.synth import make_batch
+    b = make_batch(seed=1002, region_len=1200, cov_t=100, cov_n=60, read_len=76, err=0.008, var_every=80)
+    want, _ = run_ref.run(b, threads=8, min_k=17)
+    assert max(Counter(r[0] for r in want).values()) > 64
+    c = Context(Params.default(min_k=17), device=0)
+    res = c.process(b)
+    assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
+    assert res.records() == want
+    c.close()
