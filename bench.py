@@ -101,7 +101,7 @@ def reference_arm(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/int32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "dtype": "u8/int32", "data": "synthetic", "config": {"workload": WORKLOAD}, "sample": sample,
         "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

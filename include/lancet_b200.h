@@ -165,6 +165,22 @@ int lb2_download(lb2_ctx *ctx, lb2_result *result);
 /* number of kernels launched by this context so far */
 uint64_t lb2_kernel_launches(const lb2_ctx *ctx);
 
+/* ---- measurement / diagnostics (used by bench.py and tools/; not needed by an integrator) --------------------
+ * The reference has no counterpart: its only timing output is the per-thread "elapsed time" line of
+ * src/Microassembler.cc:865. */
+int      lb2_wait(lb2_ctx *ctx);                        /* block until the kernels of the last lb2_run have finished      */
+float    lb2_last_kernel_ms(lb2_ctx *ctx);              /* device time of the last lb2_run (CUDA events on its stream)     */
+float    lb2_last_kernel_ms_of(lb2_ctx *ctx, int which);/* ... of one kernel: 0 pack (pool pre-pack), 1 window pipeline,
+                                                           2 escalation pass, 3 result compaction                       */
+uint64_t lb2_last_h2d_bytes(const lb2_ctx *ctx);        /* bytes copied host->device by the last upload / process          */
+uint64_t lb2_last_d2h_bytes(const lb2_ctx *ctx);        /* bytes copied device->host by the last download / process        */
+uint32_t lb2_resident_ctas(const lb2_ctx *ctx);         /* persistent CTAs of the window kernel for the last batch         */
+uint32_t lb2_smem_per_cta(const lb2_ctx *ctx);          /* dynamic shared memory per CTA of the window kernel              */
+/* cycles per pipeline phase summed over windows (all zero unless the library was built with -DLB2_PROFILE) */
+int      lb2_phase_cycles(lb2_ctx *ctx, unsigned long long *out24, int reset);
+/* build identity of the kernels: bench.py refuses profile-derived numbers recorded for another version */
+const char *lb2_kernel_version(void);
+
 /* helper: order-preserving ranks for n NUL-terminated query names (host side, std::sort) */
 int lb2_rank_names(const char *const *names, uint32_t n, uint32_t *rank_out);
 

@@ -10,7 +10,6 @@
 #define LB2_ECAP         12         // half-edges per node (8 possible k-mer neighbours + specials)
 #define LB2_MAX_REF      1024       // max window reference length
 #define LB2_MAX_PATH     2304       // max assembled path length (reflen + MAX_INDEL_LEN + slack)
-#define LB2_MAX_SPECIAL  32         // source/sink nodes per (window,k)
 #define LB2_MAX_TRANS    64         // transcripts per path
 #define LB2_MAX_PNODES   512        // nodes per path
 
@@ -49,6 +48,7 @@ struct lb2_cfg {
 	uint32_t n_slots;       // resident CTAs (workspace slabs)
 	uint32_t smem_bytes;    // dynamic shared memory per CTA
 	uint32_t debug_flags;   // bit 0: sequential first compaction (LB2_DEBUG_FLAGS, debugging aid)
+	uint32_t max_special;   // source/sink nodes per (window,k): two per anchored component
 };
 
 // device view of one uploaded batch

@@ -221,7 +221,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 18);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
-	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
+	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 128); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
@@ -375,7 +375,7 @@ static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
 		C2.max_nodes = C2.table_slots - C2.table_slots / 4;
 		C2.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes);
 		C2.arena_bytes = env_u32("LB2_ARENA_BYTES2", 8u << 20); C2.deficit_bytes = env_u32("LB2_DEFICIT_BYTES2", 16u << 20);
-		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 22); C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20);
+		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 22); C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20); C2.max_special = env_u32("LB2_MAX_SPECIAL2", 2048);
 		C2.n_slots = (uint32_t)std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 64));
 		size_t stride2 = lb2_ws_layout(C2, nullptr, nullptr);
 		if (stride2 != ctx->ws2_stride || C2.n_slots > ctx->ws2_slots) {

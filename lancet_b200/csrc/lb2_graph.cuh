@@ -236,53 +236,53 @@ LB2_DEV int lb2_get_buddy(lb2_win &W, uint32_t id, int ori) {   // Node_t::getBu
 	return r;
 }
 
-// ---- findTandems (src/util.cc:574-758); seq given through an accessor; returns ans, LEN, motif appended ----
+// ---- findTandems (src/util.cc:574-758) for ONE query position, scalar, no scratch memory.  Same event formulation as
+//      the CTA-wide lb2_path_tandems (lb2_paths.cuh): for a unit length m the reference compares the unit at i with the
+//      unit at the last position of the same phase where that comparison failed -- and every unit in between equals
+//      both, so the unit one period back (i - m) serves as well.  A position whose comparison fails (or that reaches the
+//      end of the string) closes a run of period m; the run's first unit is found by stepping back over positions whose
+//      comparison succeeded.  Runs that are long enough, are not preceded by a further copy of the unit's last base and
+//      have no shorter period are the reference's candidate repeats, met in (i, m) order; those within `delta` of `pos`
+//      set LEN (the last one wins) and append their unit to the motif.
 template <class GetC>
 LB2_DEV bool lb2_find_tandems(GetC getc, uint32_t slen, const lb2_params *P, int pos, int &len, char *motif, uint32_t &mlen, uint32_t mcap, bool &movf)
 {
-	bool ans = false;
-	const uint32_t MAXU = (uint32_t)P->max_unit_len;
-	int offsets[17][17];
-	for (uint32_t m = 1; m <= MAXU && m <= 16; ++m) { for (uint32_t ph = 0; ph < m; ++ph) { offsets[m][ph] = (int)ph; } }
+	const uint32_t maxu = (uint32_t)P->max_unit_len < 16u ? (uint32_t)P->max_unit_len : 16u;
 	const int delta = P->dist_from_str;
+	// bases of the unit at i that agree with the unit one period back (the first unit of a phase is compared with itself)
+	auto agree = [&](uint32_t i, uint32_t m) -> uint32_t {
+		const uint32_t back = (i >= m) ? i - m : i; uint32_t j = 0;
+		while (j < m && i + j < slen && getc(i + j) == getc(back + j)) { ++j; }
+		return j;
+	};
+	auto closes = [&](uint32_t i, uint32_t m, uint32_t j) -> bool { return j != m || i + j + 1 == slen; };
+	bool found = false;
 	for (uint32_t i = 0; i < slen; ++i) {
-		for (uint32_t merlen = 1; merlen <= MAXU && merlen <= 16; ++merlen) {
-			int phase = (int)(i % merlen);
-			int offset = offsets[merlen][phase];
-			uint32_t j = 0;
-			while (j < merlen && i + j < slen && getc(i + j) == getc((uint32_t)offset + j)) { ++j; }
-			if (j != merlen || (i + j + 1 == slen)) {
-				// seq[offset-1] at offset 0 reads the byte before the buffer: 0 in practice
-				char left = (offset >= 1) ? getc((uint32_t)offset - 1) : (char)0;
-				if (left != getc((uint32_t)offset + merlen - 1)) {
-					if (((i - (uint32_t)offset) / merlen >= (uint32_t)P->min_report_units) && (i - (uint32_t)offset >= (uint32_t)P->min_report_len)) {
-						uint32_t ml = 1;
-						while (ml < merlen) {
-							uint32_t units = (i - (uint32_t)offset + j) / ml;
-							int allmatch = 1;
-							for (uint32_t index = 1; allmatch && index < units; ++index) {
-								for (uint32_t m = 0; m < ml; ++m) {
-									if (getc((uint32_t)offset + m) != getc((uint32_t)offset + index * ml + m)) { allmatch = 0; break; }
-								}
-							}
-							if (!allmatch) { ++ml; } else { break; }
-						}
-						if (ml == merlen) {
-							int start = offset, end = (int)(i + j), LL = (int)(i + j) - offset;
-							if (pos >= start - delta && pos <= end + delta) {
-								ans = true; len = LL;
-								for (uint32_t z = 0; z < merlen; ++z) {
-									if (mlen < mcap) { motif[mlen++] = getc((uint32_t)offset + z); } else { movf = true; }
-								}
-							}
-						}
-					}
-				}
-				offsets[merlen][phase] = (int)i;
+		for (uint32_t m = 1; m <= maxu; ++m) {
+			const uint32_t j = agree(i, m);
+			if (!closes(i, m, j)) { continue; }
+			int q = (int)i - (int)m;
+			while (q >= 0 && !closes((uint32_t)q, m, agree((uint32_t)q, m))) { q -= (int)m; }
+			const uint32_t first = (q >= 0) ? (uint32_t)q : i % m, span = i - first;
+			if (span / m < (uint32_t)P->min_report_units || span < (uint32_t)P->min_report_len) { continue; }
+			// seq[first-1] at first == 0 reads the byte before the buffer: 0 in practice
+			const char before = first ? getc(first - 1) : (char)0;
+			if (before == getc(first + m - 1)) { continue; }
+			// a shorter period d < m that tiles the whole run (whole units of length d only) disqualifies the unit
+			bool shorter = false;
+			for (uint32_t d = 1; d < m && !shorter; ++d) {
+				const uint32_t copies = (span + j) / d; bool tiles = true;
+				for (uint32_t c = 1; tiles && c < copies; ++c) { for (uint32_t x = 0; x < d; ++x) { if (getc(first + x) != getc(first + c * d + x)) { tiles = false; break; } } }
+				shorter = tiles;
 			}
+			if (shorter) { continue; }
+			const int lo = (int)first, hi = (int)(i + j);
+			if (pos < lo - delta || pos > hi + delta) { continue; }
+			found = true; len = hi - lo;
+			for (uint32_t z = 0; z < m; ++z) { if (mlen < mcap) { motif[mlen++] = getc(first + z); } else { movf = true; } }
 		}
 	}
-	return ans;
+	return found;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -371,10 +371,14 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 	}
 	lb2_sync();
 	// row-space layout (filled after the emulation: its temporaries borrow the same shared memory)
-	const uint32_t NR = sh->n_rows, NT = NR + LB2_MAX_SPECIAL;
-	uint32_t bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
+	// rows = survivors + room for the source/sink nodes of the anchored components: as many as the configuration allows
+	// (cfg.max_special) and the shared-memory graph region holds next to the survivors, never fewer than 32
+	const uint32_t NR = sh->n_rows; const size_t bits_bytes = ((size_t)W.C->max_bp / 16 + 4) * 4;
+	uint32_t spec_cap = W.C->max_special < 32u ? 32u : W.C->max_special, NT = 0, bcap = 0;
 	size_t rows_bytes = 0;
-	{
+	while (true) {
+		NT = NR + spec_cap;
+		bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
 		size_t off = 0;
 #define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; if (tid == 0) { ws.field = (type *)(G + off); } off += sizeof(type) * (size_t)(count); } while (0)
 		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint16_t, bcap);
@@ -384,18 +388,22 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		LB2_GT(d_ne, uint8_t, NT); LB2_GT(d_flags, uint8_t, NT); LB2_GT(d_color, uint8_t, NT); LB2_GT(d_eov, uint8_t, NT);
 #undef LB2_GT
 		if (tid == 0) { ws.chain = ws.stack; } rows_bytes = (off + 15) & ~(size_t)15;
-		// the node list of the current path (lane-0 code walks it over and over) moves in as well when there is room
-		const size_t pbytes = sizeof(uint32_t) * (2 * (size_t)LB2_MAX_PNODES + 1) + 2 * (size_t)LB2_MAX_PNODES + 16;
-		if (rows_bytes <= Gbytes && rows_bytes + pbytes <= Gbytes && tid == 0) {
-			uint8_t *q = G + rows_bytes;
-			ws.pnodes = (uint32_t *)q; q += sizeof(uint32_t) * LB2_MAX_PNODES; ws.pstart = (uint32_t *)q; q += sizeof(uint32_t) * (LB2_MAX_PNODES + 1);
-			ws.pdirs = q; q += LB2_MAX_PNODES; ws.peidx = q;
+		if (spec_cap <= 32u || (NT <= LB2_MAX_ROWS && rows_bytes <= Gbytes && (size_t)NT * 2 + 16 <= bits_bytes)) {
+			if (tid == 0) { sh->spec_cap = spec_cap; }
+			// the node list of the current path (lane-0 code walks it over and over) moves in as well when there is room
+			const size_t pbytes = sizeof(uint32_t) * (2 * (size_t)LB2_MAX_PNODES + 1) + 2 * (size_t)LB2_MAX_PNODES + 16;
+			if (rows_bytes <= Gbytes && rows_bytes + pbytes <= Gbytes && tid == 0) {
+				uint8_t *q = G + rows_bytes;
+				ws.pnodes = (uint32_t *)q; q += sizeof(uint32_t) * LB2_MAX_PNODES; ws.pstart = (uint32_t *)q; q += sizeof(uint32_t) * (LB2_MAX_PNODES + 1);
+				ws.pdirs = q; q += LB2_MAX_PNODES; ws.peidx = q;
+			}
+			break;
 		}
+		spec_cap >>= 1;
 	}
 	// scratch of the graph stage in the (now dead) packed-read words: list index of every row, then the parallel
 	// compaction's words.  The emulation arrays: three u16[n] here, the rest over the graph region; when either does not
 	// fit, all of them live in the workspace slab instead.
-	const size_t bits_bytes = ((size_t)W.C->max_bp / 16 + 4) * 4;
 	if (tid == 0) {
 		ws.d_pos = (uint16_t *)W.bits; ws.px = (uint32_t *)((uint8_t *)W.bits + (((size_t)NT * 2 + 15) & ~(size_t)15));
 		ws.px_words = (bits_bytes > (((size_t)NT * 2 + 15) & ~(size_t)15)) ? (uint32_t)((bits_bytes - (((size_t)NT * 2 + 15) & ~(size_t)15)) / 4) : 0u;
@@ -521,7 +529,7 @@ LB2_DEVNI int lb2_mark_components(lb2_win &W) {
 // special node creation: key string "source<c>" / "sink<c>" hashed like any other map key
 LB2_DEV uint32_t lb2_new_special(lb2_win &W, bool source, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
-	if (sh->n_spec >= LB2_MAX_SPECIAL) { sh->err |= 1u << LB2_D_SPECIAL; return LB2_NIL; }
+	if (sh->n_spec >= sh->spec_cap) { sh->err |= 1u << LB2_D_SPECIAL; return LB2_NIL; }
 	uint32_t id = sh->n_rows + sh->n_spec++;
 	char buf[24]; int n = 0;
 	const char *pre = source ? "source" : "sink";
@@ -623,7 +631,7 @@ LB2_DEVNI void lb2_mark_ref_ends(lb2_win &W, int compid) {   // lane 0, after lb
 // hasCycle / hasCycleRec with an explicit stack; frame = node << 16 | incoming orientation << 15 | next edge index
 LB2_DEV bool lb2_cycle_from(lb2_win &W, uint32_t start, int ori) {
 	lb2_ws &ws = W.ws; uint32_t *const st = ws.stack; uint32_t sp = 0; bool ans = false;
-	const uint32_t cap = W.sh->n_rows + LB2_MAX_SPECIAL;
+	const uint32_t cap = W.sh->n_rows + W.sh->spec_cap;
 	// (array bases in registers: the descriptor lives in shared memory and would be re-read behind every store)
 	uint8_t *const COL = ws.d_color; const uint8_t *const NE = ws.d_ne, *const FL = ws.d_flags, *const EOV = ws.d_eov; const lb2_edge *const ED = ws.d_edge, *const EP = ws.e_pool;
 	COL[start] = 2; st[sp++] = (start << 16) | ((uint32_t)ori << 15);
@@ -722,7 +730,7 @@ struct lb2_job { uint32_t node, cbeg, nF, nAll, len0, curlen, so, co, leftlen, p
 
 LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
-	uint32_t cused = 0, njobs = 0; const uint32_t ccap = sh->n_rows + LB2_MAX_SPECIAL;
+	uint32_t cused = 0, njobs = 0; const uint32_t ccap = sh->n_rows + sh->spec_cap;
 	lb2_job *jobs = (lb2_job *)ws.jobs;
 	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
 		if (ws.d_comp[p] != compid) { continue; }

@@ -117,6 +117,10 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				lb2_find_anchors(W, c);
 				if (tid == 0) { lb2_mark_ref_ends(W, c); sh->flag_c = 0; lb2_mark(W, LB2_PH_ANCHOR); }
 				lb2_sync();
+				// A component without anchors is invisible from here on: both cycle checks, the path-repeat scan and the path
+				// enumeration return at once without a source (src/Graph.cc:602, :689, :2422), and the sweeps in between only
+				// touch this component's own nodes, which nothing looks at again -- so it is not compacted or swept at all
+				if (!sh->err && (sh->source == LB2_NIL || sh->sink == LB2_NIL)) { continue; }
 				if (!sh->err) {
 					// the cycle check before the first compaction (src/Microassembler.cc:179) gives the same answer on the
 					// compacted graph (a chain of links is always traversed whole), where it costs a handful of nodes

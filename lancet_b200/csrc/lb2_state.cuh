@@ -91,7 +91,7 @@ struct lb2_sh {
 	// order emulation
 	uint32_t bkt_count, bkt_cap, elem_count, next_resize, lhead;
 	// anchors
-	uint32_t source, sink, anc_src, anc_snk, anc_amb;
+	uint32_t source, sink, anc_src, anc_snk, anc_amb, spec_cap;
 	uint32_t arena_used, tstr_used;
 	// path
 	uint32_t plen, pn, need_align, n_trans, path_found, aln_len, q_smem;

@@ -51,6 +51,16 @@ int main(int argc, char **argv)
 		printf("divtest: %llu cases, %llu mismatches\n", total, bad);
 		return bad ? 1 : 0;
 	}
+	if (fn && std::string(fn) == "tandemtest") {
+		// lb2_find_tandems on "T <pos> <seq>" lines of stdin, same output format as oracle/kat_reference.cc
+		char op[8]; int pos; static char buf[1 << 16];
+		while (scanf("%7s %d %65535s", op, &pos, buf) == 3) {
+			const std::string q(buf); int len = 0; char motif[256]; uint32_t ml = 0; bool ov = false;
+			const bool ans = lb2_find_tandems([&](uint32_t i) -> char { return q[i]; }, (uint32_t)q.size(), &P, pos, len, motif, ml, 255, ov);
+			printf("%d %d %s\n", ans ? 1 : 0, len, ml ? std::string(motif, ml).c_str() : ".");
+		}
+		return 0;
+	}
 	if (fn && std::string(fn) == "scantest") {
 		// the word filter of lb2_diag_scan against the unfiltered scan (min_k < 11 switches the filter off): for every k >= 11
 		// both must answer isRepeat / isAlmostRepeat alike, i.e. max(emax,10) and max(wmax,11) agree
@@ -96,7 +106,7 @@ int main(int argc, char **argv)
 
 	lb2_cfg C; memset(&C, 0, sizeof C);
 	C.table_slots = 16384; C.max_nodes = 12000; C.max_reads = 8192; C.max_bp = (1 << 20) - 1024; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
-	C.queue_cap = 1 << 22; C.graph_bytes = 1 << 20; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
+	C.queue_cap = 1 << 22; C.graph_bytes = 1 << 20; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1; C.max_special = 2048;
 	if (getenv("LB2_SIM_TS")) { C.table_slots = atoi(getenv("LB2_SIM_TS")); C.max_nodes = C.table_slots - C.table_slots / 4; }
 	if (getenv("LB2_SIM_BP")) { C.max_bp = atoi(getenv("LB2_SIM_BP")); }
 	if (getenv("LB2_SIM_GB")) { C.graph_bytes = atoi(getenv("LB2_SIM_GB")); }

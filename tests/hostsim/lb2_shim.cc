@@ -34,7 +34,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *b, lb2_result *res)
 	const uint32_t W = b->n_windows;
 	lb2_cfg C; memset(&C, 0, sizeof C);
 	C.table_slots = 16384; C.max_nodes = 12000; C.max_reads = 8192; C.max_bp = (1 << 20) - 1024; C.arena_bytes = 1 << 21; C.deficit_bytes = 1 << 23;
-	C.queue_cap = 1 << 22; C.graph_bytes = 1 << 20; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1;
+	C.queue_cap = 1 << 22; C.graph_bytes = 1 << 20; C.max_inst = 1 << 20; C.max_var = 64; C.str_bytes = 8192; C.bucket_cap = 10273; C.max_k = 127; C.n_slots = 1; C.max_special = 2048;
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = b->ref_off; B.ref_start = b->ref_start; B.wr_off = b->wr_off; B.wr_idx = b->wr_idx;
 	B.base_off = b->base_off; B.flags = b->flags; B.name_rank = b->name_rank; B.ref_seq = b->ref_seq; std::vector<char> pseq(b->seq, b->seq + b->n_base_bytes), pqual(b->qual, b->qual + b->n_base_bytes); pseq.resize(pseq.size() + 64, 0); pqual.resize(pqual.size() + 64, 0);
 	B.seq = pseq.data(); B.qual = pqual.data();

@@ -22,6 +22,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
 
 
+def test_every_exported_symbol_is_declared():
+    """the other direction: nothing is exported from the library that the header does not declare"""
+    import subprocess
+    so = os.path.join(ROOT, "lancet_b200", "_lb2.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split()[-1].startswith("lb2_") and " T " in ln})
+    declared = set(_declared())
+    assert exported, "no lb2_* symbols exported?"
+    missing = [n for n in exported if n not in declared]
+    assert not missing, f"exported but not declared in include/lancet_b200.h: {missing}"
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

@@ -27,7 +27,7 @@ def test_cli_golden(name):
     d = os.path.join(GOLD, name)
     args = [a.replace("@DIR@", d) for a in json.load(open(os.path.join(d, "args.json")))["args"]]
     got, err = _run(CLI, {"tumor": os.path.join(d, "tumor.bam"), "normal": os.path.join(d, "normal.bam"), "ref": os.path.join(d, "ref.fa")}, args)
-    assert "not assembled on the device" not in err
+    assert "not assembled" not in err
     assert got == open(os.path.join(d, "expected.vcf")).read().rstrip("\n")
 
 
@@ -53,6 +53,6 @@ def test_cli_live_reference(name, tmp_path):
     d = simbam.write_dataset(str(tmp_path / name), **kw)
     want, _ = _run(REFCLI, d, args)
     got, err = _run(CLI, d, args)
-    assert "not assembled on the device" not in err
+    assert "not assembled" not in err
     assert got == want
     assert sum(1 for l in want.splitlines() if not l.startswith("#")) > 5

@@ -30,3 +30,21 @@ def test_fold_division_equals_ieee(sim):
     r = subprocess.run([sim, "divtest"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 mismatches" in r.stdout
+
+
+def test_scalar_find_tandems_matches_reference_goldens(sim):
+    """the device's scalar findTandems (run-event formulation, lb2_graph.cuh) against the outputs of the reference's own
+    findTandems (tests/golden/kat_reference.json, generated from /root/reference by tests/golden/make_kat.py)"""
+    import json
+    cases = [c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "kat_reference.json"))) if c["in"][0] == "T"]
+    assert len(cases) >= 40
+    inp = "".join(f"T {c['in'][1]} {c['in'][2]}\n" for c in cases)
+    r = subprocess.run([sim, "tandemtest"], input=inp, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = r.stdout.splitlines()
+    assert len(got) == len(cases)
+    for c, g in zip(cases, got):
+        ans, ln, motif = g.split()
+        assert ans == c["out"][0], c
+        if ans == "1":
+            assert ln == c["out"][1] and motif == c["out"][2], (c, g)
