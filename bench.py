@@ -151,10 +151,12 @@ def main():
     launches0 = ctx.kernel_launches
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    dev_ms = 0.0
+    dev_ms = 0.0; part_ms = {"pack": 0.0, "windows": 0.0, "escalation": 0.0, "compaction": 0.0}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.run(); ctx.wait(); dev_ms += ctx.last_kernel_ms       # CUDA events on the launching stream
+        for k in part_ms:
+            part_ms[k] += ctx.last_kernel_ms_of(k)
     barrier()
     wall = time.perf_counter() - t0
     launches = ctx.kernel_launches - launches0
@@ -180,16 +182,23 @@ def main():
 
     if rank == 0:
         peak, how = peak_hbm()
+        from lancet_b200.api import KERNEL_VERSION
         alg_bytes = batch.algorithmic_bytes(n_var)                  # this rank's launch (B_win summed)
-        achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+        win_ms = part_ms["windows"] / args.steps                    # lb2_window_kernel alone (first pass), CUDA events on its stream
+        achieved = alg_bytes / (win_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                tj = json.load(open(tp))            # ncu capture of an earlier run of this kernel (per-window DRAM bytes x windows of this launch)
-                traffic = tj["dram_bytes_per_window"] * batch.n_windows
+                tj = json.load(open(tp))            # ncu capture of this kernel version (per-window DRAM bytes x windows of this launch)
+                if tj.get("kernel_version") == KERNEL_VERSION:      # a capture of another kernel version says nothing about this one
+                    traffic = tj["dram_bytes_per_window"] * batch.n_windows
             except Exception:
                 pass
+        # the pre-pack pass is the one HBM-shaped kernel of the path: 2 bytes in per base, 3/8 byte + 12 bytes per read out
+        nbases = int(batch.seq.nbytes)
+        pack_bytes = 2 * nbases + int(((batch.base_off[1:] - batch.base_off[:-1] + 15) // 16).sum()) * 6 + 12 * batch.n_reads + 8 * batch.n_reads
+        pack_ms = part_ms["pack"] / args.steps
         out = {
             "metric": METRIC, "value": total_windows / (ms_step * 1e-3), "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -202,7 +211,12 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "kernel": "lb2_window_kernel"},
+                         "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes, "kernel": "lb2_window_kernel", "kernel_ms": win_ms,
+                         "kernel_version": KERNEL_VERSION},
+            "roofline_pack": {"bound": "hbm", "kernel": "lb2_pack_kernel (+count, scan)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9 if pack_ms > 0 else None,
+                              "peak": peak, "unit": "GB/s", "frac": (pack_bytes / (pack_ms * 1e-3) / 1e9 / peak) if pack_ms > 0 else None,
+                              "algorithmic_bytes_per_launch": pack_bytes, "kernel_ms": pack_ms},
+            "step_ms": {k: v / args.steps for k, v in part_ms.items()},
         }
         if world == 1 and os.environ.get("LB2_SKIP_CPU_BASELINE") is None:
             import run_ref

@@ -15,7 +15,8 @@ import numpy as np
 
 from .batch import Batch, LB2Batch
 
-_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lb2.so")
+# LB2_SO selects another build of the same library (tools/phase_profile.py: the -DLB2_PROFILE variant _lb2_prof.so)
+_SO = os.environ.get("LB2_SO") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lb2.so")
 if not os.path.exists(_SO):
     raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(there is no CPU fallback for the lancet_b200 hot path)")
@@ -75,6 +76,10 @@ for _n in ("lb2_resident_ctas", "lb2_smem_per_cta"):
 _lib.lb2_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 _lib.lb2_last_kernel_ms.argtypes = [ctypes.c_void_p]
 _lib.lb2_last_kernel_ms.restype = ctypes.c_float
+_lib.lb2_last_kernel_ms_of.argtypes = [ctypes.c_void_p, ctypes.c_int]
+_lib.lb2_last_kernel_ms_of.restype = ctypes.c_float
+_lib.lb2_kernel_version.restype = ctypes.c_char_p
+KERNEL_VERSION = _lib.lb2_kernel_version().decode()
 
 
 class Result:
@@ -152,6 +157,10 @@ class Context:
     resident_ctas = property(lambda self: int(_lib.lb2_resident_ctas(self._h)))
     smem_per_cta = property(lambda self: int(_lib.lb2_smem_per_cta(self._h)))
     last_kernel_ms = property(lambda self: float(_lib.lb2_last_kernel_ms(self._h)))
+
+    def last_kernel_ms_of(self, which: str) -> float:
+        """device time of one stage of the last run(): 'pack' (pool pre-pack), 'windows' (first pass), 'escalation', 'compaction'"""
+        return float(_lib.lb2_last_kernel_ms_of(self._h, ("pack", "windows", "escalation", "compaction").index(which)))
 
     PHASES = ("stage", "prescan_maxk", "ref_repeat_scan", "kmer_walk", "compact_sort", "mate_replay", "lowq_deficits",
               "table_clear", "ref_coverage", "order_emulation", "lowcov_components", "component_sequential", "bfs_loadpath",

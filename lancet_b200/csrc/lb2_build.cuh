@@ -28,10 +28,15 @@ struct lb2_win {
 
 LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2);
 
-// attribute the cycles since the previous mark to phase ph (lane 0 only)
+// attribute the cycles since the previous mark to phase ph (lane 0 only).  Instrumentation: compiled in only with
+// -DLB2_PROFILE (tools/phase_profile.py builds that variant as lancet_b200/_lb2_prof.so); the product library has none of it
+#ifdef LB2_PROFILE
 LB2_DEV void lb2_mark(lb2_win &W, int ph) {
 	if (lb2_tid() == 0) { unsigned long long t = lb2_clock(); W.sh->prof[ph] += t - W.sh->t_last; W.sh->t_last = t; }
 }
+#else
+LB2_DEV void lb2_mark(lb2_win &, int) {}
+#endif
 
 // CTA-wide exclusive prefix sum: set(i, sum_{j<i} get(j)); returns the total.  Each lane owns a contiguous chunk.
 template <class Get, class Set>
@@ -52,64 +57,47 @@ LB2_DEV void lb2_fail(lb2_win &W, uint32_t status, uint32_t detail) {
 	if (lb2_cas32(&W.sh->status, LB2_WIN_OK, status) == LB2_WIN_OK) { W.sh->detail = detail; }
 }
 
-// ---- 16 read bases at a time (device: five aligned 32-bit loads per 16 bytes, SIMD-in-register classification) ----
-// 2-bit codes of four ASCII bases in the byte lanes of w -> 8 bits (A=0 C=1 G=2 T=3; other characters give garbage)
-LB2_DEV uint32_t lb2_codes4(uint32_t w) {
-	const uint32_t x = (w >> 1) & 0x03030303u, c = x ^ ((x >> 1) & 0x01010101u);
-	return (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
-}
-LB2_DEV uint32_t lb2_bytemask4(uint32_t m) { return (((m & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; }      // 0xFF/0x00 byte lanes -> 4 bits
-LB2_DEV uint32_t lb2_codes16(const char *s) {
-	uint32_t sw[4]; lb2_load16(s, sw);
-	return lb2_codes4(sw[0]) | (lb2_codes4(sw[1]) << 8) | (lb2_codes4(sw[2]) << 16) | (lb2_codes4(sw[3]) << 24);
-}
-LB2_DEV uint32_t lb2_low16(const char *q, uint32_t thr4) {       // bit i: quality byte i < threshold
-	uint32_t qw[4]; lb2_load16(q, qw);
-	return lb2_bytemask4(lb2_ltu4(qw[0], thr4)) | (lb2_bytemask4(lb2_ltu4(qw[1], thr4)) << 4) | (lb2_bytemask4(lb2_ltu4(qw[2], thr4)) << 8) | (lb2_bytemask4(lb2_ltu4(qw[3], thr4)) << 12);
-}
-LB2_DEV uint32_t lb2_nacgt16(const char *s) {                    // bit i: base i is not one of ACGT
-	uint32_t sw[4]; lb2_load16(s, sw); uint32_t r = 0;
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const uint32_t ok = lb2_eq4(sw[k], 0x41414141u) | lb2_eq4(sw[k], 0x43434343u) | lb2_eq4(sw[k], 0x47474747u) | lb2_eq4(sw[k], 0x54545454u);
-		r |= lb2_bytemask4(~ok) << (4 * k);
-	}
-	return r;
-}
-
-// 2-bit packed bases of the trimmed reads and of the window reference, and the low-quality mask (quality <
-// MIN_QUAL_CALL) of the staged bases.  Both shared-memory areas are lent to the graph stage after every build (k-mer
-// strings of the surviving nodes are copied out first), so they are staged again before the build of a later k.
-// Eight lanes per read, one 16-base word each; the read's length / pool offset / staged position for the NEXT round are
-// fetched while the current round's bases are on their way.
+// ---------------------------------------------------------------------------------------------
+// Staging.  The window's reads come out of the packed pool (lb2_pack.cuh) as whole 16-base words: a read lands in shared
+// memory UNtrimmed, its first kept base at staged index g = 16 * word + trm5.  Pool reads that follow each other in the
+// window's list (the usual case: a window's tumour reads are one run of the coordinate-sorted pool, its normal reads
+// another) keep their pool layout, so a run moves with one bulk-async copy (cp.async.bulk, completion on an mbarrier).
+// Bulk copies want 16-byte alignment on both sides; the quality mask has 2 bytes per word, hence a run is placed so that
+// its shared-memory word index equals its pool word index modulo 8, with up to 7 pad words before and after it (the
+// copy moves whole 8-word blocks, the pad words receive whatever surrounds the run in the pool and are never looked at).
+// Both shared-memory areas are lent to the graph stage after every build, so they are staged again (copies only) before
+// the build of a later k.
+// ---------------------------------------------------------------------------------------------
 LB2_DEVNI void lb2_stage_pack(lb2_win &W, bool do_bits, bool do_lowq)
 {
 	lb2_sh *sh = W.sh; const lb2_dev_batch *B = W.B; lb2_ws &ws = W.ws;
-	const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	const unsigned tid = lb2_tid(), nt = lb2_nthr(), lane = lb2_lane();
 	const uint32_t R = sh->R, L = sh->L;
-	const uint32_t qc = (uint32_t)W.P->min_qual_call & 0xFFu, qcall4 = qc * 0x01010101u;
-	if (do_lowq) { for (uint32_t i = tid; i < (sh->total_bp >> 5) + 4; i += nt) { W.lowq[i] = 0; } lb2_sync(); }
-	const uint32_t ng = lb2_ngroups(), gl = lb2_glane();
-	uint32_t r = lb2_group();
-	uint32_t n_n = 0, g_n = 0; uint64_t src_n = 0;
-	if (r < R) { n_n = ws.rd_len[r]; g_n = ws.rd_start[r]; src_n = ws.rd_src[r]; }
-	for (; r < R; r += ng) {
-		const uint32_t n = n_n, g = g_n; const uint64_t src = src_n;
-		if (r + ng < R) { n_n = ws.rd_len[r + ng]; g_n = ws.rd_start[r + ng]; src_n = ws.rd_src[r + ng]; }
-		if (!n) { continue; }
-		for (uint32_t w = gl; w * 16 < n; w += LB2_GS) {
-			const uint32_t m = n - w * 16;
-			uint32_t bw = 0, lw = 0;
-			if (do_bits) { bw = lb2_codes16(B->seq + src + w * 16); }
-			if (do_lowq) { lw = lb2_low16(B->qual + src + w * 16, qcall4); }
-			if (do_bits) { if (m < 16) { bw &= (1u << (2 * m)) - 1u; } W.bits[(g >> 4) + w] = bw; }
-			if (do_lowq) {      // reads start on 16-base boundaries: two words of a read share a mask word
-				if (m < 16) { lw &= (1u << m) - 1u; }
-				if (lw) { lb2_or32(&W.lowq[(g + w * 16) >> 5], lw << ((g + w * 16) & 31)); sh->has_lowq = 1; }
+	lb2_sync();                  // every ordinary access to the two areas is over ...
+	lb2_async_fence();           // ... and ordered before this lane's bulk copies
+	const uint32_t *const pbits = B->pk_bits; const uint16_t *const plowq = B->pk_lowq; uint16_t *const lowq16 = (uint16_t *)W.lowq;
+	// pieces: maximal stretches of reads that are consecutive in the pool AND in shared memory, cut at groups of LB2_WARP reads;
+	// the first lane of a piece issues its copies
+	for (uint32_t base = (tid / LB2_WARP) * LB2_WARP; base < R; base += (nt / LB2_WARP) * LB2_WARP) {
+		const uint32_t i = base + lane; const bool valid = i < R;
+		uint32_t gw = 0, nw = 0, sw = 0;
+		if (valid) { const uint64_t v = ws.rd_src[i]; gw = (uint32_t)v; nw = (uint32_t)(v >> 32); sw = (ws.rd_start[i] - ws.rd_t5[i]) >> 4; }
+		const uint32_t pg = lb2_shfl_up1(gw + nw), ps = lb2_shfl_up1(sw + nw);
+		const bool head = valid && (lane == 0 || pg != gw || ps != sw);
+		const uint32_t heads = lb2_ballot(head), above = (lane + 1 < LB2_WARP) ? (heads >> (lane + 1)) : 0u;
+		uint32_t tail = above ? lane + (uint32_t)lb2_ctz32(above) : LB2_WARP - 1u;      // last lane of the piece that starts here
+		if (base + tail >= R) { tail = R - 1u - base; }
+		const uint32_t gend = lb2_shfl(gw + nw, tail);
+		if (head) {
+			const uint32_t g0 = gw & ~7u, g1 = (gend + 7u) & ~7u, s0 = sw - (gw & 7u);
+			if (g1 > g0) {
+				if (do_bits) { lb2_bulk_g2s(W.bits + s0, pbits + g0, (g1 - g0) * 4u, &sh->mbar); }
+				if (do_lowq) { lb2_bulk_g2s(lowq16 + s0, plowq + g0, (g1 - g0) * 2u, &sh->mbar); }
 			}
 		}
 	}
-	if (do_bits) {
+	lb2_mbar_arrive(&sh->mbar);
+	if (do_bits) {      // the window reference, packed from its ASCII copy
 		const uint32_t g = sh->ref_g;
 		for (uint32_t b0 = tid * 16; b0 < ((L + 15u) & ~15u) + 64; b0 += nt * 16) {
 			uint32_t bw = 0;
@@ -117,14 +105,17 @@ LB2_DEVNI void lb2_stage_pack(lb2_win &W, bool do_bits, bool do_lowq)
 			W.bits[(g + b0) >> 4] = bw;
 		}
 	}
-	if (tid == 0) { if (do_bits) { sh->bits_live = 1; } if (do_lowq) { sh->lowq_live = 1; } }
+	if (do_lowq) { for (uint32_t i = (sh->ref_g >> 5) + tid; i < (sh->total_bp >> 5) + 4; i += nt) { W.lowq[i] = 0; } }      // (the reference "read" has quality 'K' everywhere)
+	lb2_mbar_wait(&sh->mbar, sh->mbar_phase);
+	lb2_sync();
+	if (tid == 0) { sh->mbar_phase ^= 1u; if (do_bits) { sh->bits_live = 1; } if (do_lowq) { sh->lowq_live = 1; } }
 	lb2_sync();
 }
 LB2_DEV void lb2_stage_bits(lb2_win &W) { lb2_stage_pack(W, true, false); }
 LB2_DEV void lb2_stage_lowq(lb2_win &W) { lb2_stage_pack(W, false, true); }
 
 // ---------------------------------------------------------------------------------------------
-// stage the window: trim every read, pack bases/low-quality mask into shared memory
+// stage the window: per-read records from the packed pool, shared-memory layout, bulk copies
 // ---------------------------------------------------------------------------------------------
 LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 {
@@ -135,8 +126,9 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		sh->L = B->ref_off[w + 1] - B->ref_off[w];
 		sh->R = B->wr_off[w + 1] - B->wr_off[w];
 		sh->ref_start = B->ref_start[w];
-		sh->has_lowq = 0; sh->has_pairs = 0; sh->mapped = 0; sh->flag_a = 0; sh->totalreadbp = 0;
+		sh->has_lowq = 0; sh->has_pairs = 0; sh->mapped = 0; sh->flag_a = 0; sh->flag_b = 0; sh->totalreadbp = 0;
 		sh->n_var = 0; sh->str_used = 0; sh->n_k_tried = 0; sh->final_k = 0; sh->last_nodes = 0;
+		sh->err = 0;      // (a window whose every k is skipped never reaches lb2_build_graph, which resets it per k)
 		if (sh->L > LB2_MAX_REF) { sh->status = LB2_WIN_OVERFLOW; sh->detail = LB2_D_REFLEN; }
 		else if (sh->R + 1 > W.C->max_reads) { sh->status = LB2_WIN_OVERFLOW; sh->detail = LB2_D_READS; }
 	}
@@ -149,64 +141,34 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		if (lb2_code(c) < 0) { lb2_or32(&sh->flag_a, 1u); }
 	}
 	const uint32_t *widx = B->wr_idx + B->wr_off[w];
-	const uint32_t qt = (uint32_t)W.P->min_qual_trim & 0xFFu, qtrim4 = qt * 0x01010101u;
-	// Graph_t::trim (src/Graph.cc:355-384), eight lanes per read: a base is "good" when it is ACGT with quality >=
-	// MIN_QUAL_TRIM; trm5 = bases before the first good one, trm3 = bases after the last good one, junk = no good base
-	// or a non-ACGT base strictly between them.  (All lanes of a warp run the same number of rounds: the group
-	// reductions are warp shuffles.)
-	const uint32_t ng = lb2_ngroups(), grp = lb2_group(), gl = lb2_glane();
-	// (the read index of round i+2 and the pool offsets of round i+1 are fetched during round i: the chain
-	// read list -> offset table -> bases would otherwise cost three memory latencies per round)
-	uint32_t idx_n = (grp < R) ? widx[grp] : 0u, idx_nn = (grp + ng < R) ? widx[grp + ng] : 0u;
-	uint64_t o0_n = 0, o1_n = 0; if (grp < R) { o0_n = B->base_off[idx_n]; o1_n = B->base_off[idx_n + 1]; }
-	for (uint32_t r0 = 0; r0 < R; r0 += ng) {
-		const uint32_t r = r0 + grp; const bool act = r < R;
-		const uint32_t idx = idx_n; const uint64_t o0 = o0_n; const uint32_t len = act ? (uint32_t)(o1_n - o0_n) : 0u;
-		const char *s = B->seq + o0, *q = B->qual + o0;
-		idx_n = idx_nn; if (r + ng < R) { o0_n = B->base_off[idx_n]; o1_n = B->base_off[idx_n + 1]; }
-		idx_nn = (r + 2 * ng < R) ? widx[r + 2 * ng] : 0u;
-		uint32_t fl_v = 0, rk_v = 0; if (act && gl == 0) { fl_v = B->flags[idx]; rk_v = B->name_rank[idx]; }      // (used at the end of the round)
-		const uint32_t nch = (len + 15u) >> 4;
-		uint32_t first = 0xFFFFFFFFu, last = 0, my_nac = 0, my_c = 0xFFFFFFFFu;      // last = index of the last good base + 1
-		for (uint32_t c = gl; c < nch; c += LB2_GS) {
-			const uint32_t m = len - c * 16, valid = (m < 16) ? ((1u << m) - 1u) : 0xFFFFu;
-			const uint32_t nac = lb2_nacgt16(s + c * 16) & valid, low = lb2_low16(q + c * 16, qtrim4) & valid;
-			const uint32_t good = valid & ~(nac | low);
-			if (good) { const uint32_t f = c * 16 + (uint32_t)lb2_ctz32(good), l = c * 16 + 32u - (uint32_t)lb2_clz32(good); if (f < first) { first = f; } if (l > last) { last = l; } }
-			my_nac = nac; my_c = c;
+	const lb2_pkread *const PK = B->pk; const uint32_t *const NR_ = B->name_rank;
+	{	// per-read records; words each read adds to the layout (its own, plus the pad words where a run of pool-consecutive reads starts / ends)
+		uint32_t bp = 0, fl = 0;
+		for (uint32_t i = tid; i < R; i += nt) {
+			const uint32_t idx = widx[i]; const lb2_pkread rec = PK[idx];
+			const bool first = (i == 0) || (widx[i - 1] + 1u != idx), last = (i + 1 == R) || (widx[i + 1] != idx + 1u);
+			const uint32_t lead = first ? (rec.woff & 7u) : 0u, trail = last ? ((0u - (rec.woff + rec.nw)) & 7u) : 0u;
+			ws.rd_len[i] = rec.n; ws.rd_t5[i] = rec.t5; ws.rd_info[i] = rec.info & 15u; ws.rd_rank[i] = NR_[idx];
+			ws.rd_src[i] = (uint64_t)rec.woff | ((uint64_t)rec.nw << 32);
+			ws.rd_kbase[i] = ((uint32_t)rec.nw + lead + trail) | (lead << 28);      // (scratch until the build of the first k)
+			bp += rec.n;
+			fl |= (rec.info & LB2_PK_UNMAPPED) ? 0u : 1u; fl |= (rec.info & LB2_PK_TOOLONG) ? 2u : 0u; fl |= rec.lowq ? 4u : 0u;
 		}
-		first = lb2_gmin(first); last = lb2_gmax(last);
-		uint32_t junk = (first == 0xFFFFFFFFu) ? 1u : 0u;
-		if (!junk) {      // a non-ACGT base inside (first, last-1)
-			for (uint32_t c = gl; c < nch; c += LB2_GS) {
-				const uint32_t m = len - c * 16, valid = (m < 16) ? ((1u << m) - 1u) : 0xFFFFu;
-				const uint32_t nac = (c == my_c) ? my_nac : (lb2_nacgt16(s + c * 16) & valid);      // (one chunk per lane: still in a register)
-				for (uint32_t x = nac; x; x &= x - 1) { const uint32_t p = c * 16 + (uint32_t)lb2_ctz32(x); if (p > first && p + 1 < last) { junk = 1; } }
-			}
-		}
-		junk = lb2_gor(junk);
-		if (act && gl == 0) {
-			const uint8_t fl = (uint8_t)fl_v;
-			int n = junk ? 0 : (int)(last - first); const uint32_t t5 = junk ? len : first;
-			if (n > 4095) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_READS); n = 0; }
-			ws.rd_len[r] = (uint32_t)n; ws.rd_t5[r] = t5; ws.rd_src[r] = o0 + t5;
-			uint32_t cls = ((fl & LB2_READ_NORMAL) ? 2u : 0u) | ((fl & LB2_READ_REVERSE) ? 1u : 0u);
-			uint32_t mate = (fl >> LB2_READ_MATE_SHIFT) & 3u;
-			ws.rd_info[r] = cls | (mate << 2);
-			ws.rd_rank[r] = rk_v;
-			if (!(fl & LB2_READ_UNMAPPED)) { sh->mapped = 1; }
-			if (n) { lb2_add32(&sh->totalreadbp, (uint32_t)n); }
-		}
+		if (bp) { lb2_add32(&sh->totalreadbp, bp); }
+		if (fl) { lb2_or32(&sh->flag_b, fl); }
 	}
 	lb2_sync();
-	uint32_t cum_all = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { return (ws.rd_len[r] + 15u) & ~15u; }, [&](uint32_t r, uint32_t v) { ws.rd_start[r] = v; });
+	const uint32_t words = lb2_excl_scan(W, R, [&](uint32_t r) -> uint32_t { return ws.rd_kbase[r] & 0x0FFFFFFFu; },
+	                                     [&](uint32_t r, uint32_t v) { ws.rd_start[r] = 16u * (v + (ws.rd_kbase[r] >> 28)) + ws.rd_t5[r]; });
 	if (tid == 0) {
-		uint32_t cum = cum_all;
+		uint32_t cum = 16u * words;      // (a multiple of 8 words: every run is padded to whole 8-word blocks)
 		ws.rd_start[R] = cum; sh->ref_g = cum; cum += (L + 31u) & ~31u;
 		sh->total_bp = cum;
+		const uint32_t fl = sh->flag_b; sh->mapped = fl & 1u; sh->has_lowq = (fl & 4u) ? 1u : 0u; sh->flag_b = 0;
 		if (cum + 64 > W.C->max_bp) { lb2_fail(W, LB2_WIN_OVERFLOW, LB2_D_SMEM); }
+		if (fl & 2u) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_READS); }
 		if (sh->flag_a) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_NREF); }
-		if (!sh->mapped) { lb2_fail(W, LB2_WIN_NO_READS, 0); }
+		if (!(fl & 1u)) { lb2_fail(W, LB2_WIN_NO_READS, 0); }
 		sh->seq_off = 0; sh->seq_len = L; sh->trim5 = 0; sh->trim3 = 0;
 	}
 	lb2_sync();
@@ -233,7 +195,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		}
 		lb2_sync();
 	}
-	lb2_stage_pack(W, true, true);
+	lb2_stage_pack(W, true, sh->has_lowq != 0);
 }
 
 // ---------------------------------------------------------------------------------------------

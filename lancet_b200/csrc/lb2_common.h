@@ -51,12 +51,29 @@ struct lb2_cfg {
 	uint32_t max_special;   // source/sink nodes per (window,k): two per anchored component
 };
 
+// one pooled read after the pre-pack pass (lb2_pack.cuh): where its 2-bit words start in the packed pool, the result of
+// Graph_t::trim (reference src/Graph.cc:355-384), the read flags the pipeline looks at
+struct lb2_pkread {
+	uint32_t woff;   // first 16-base word of the read in pk_bits / pk_lowq
+	uint16_t t5;     // trm5: bases before the first kept base (the whole length for a junk read)
+	uint16_t n;      // kept bases (0: junk read)
+	uint16_t nw;     // 16-base words of the untrimmed read
+	uint8_t  info;   // bits 0-1 class (sample*2 + strand), bits 2-3 mate order, LB2_PK_*
+	uint8_t  lowq;   // some kept base has quality < MIN_QUAL_CALL
+};
+#define LB2_PK_UNMAPPED 0x10u
+#define LB2_PK_TOOLONG  0x20u   /* more than 4095 kept bases: not handled by the device path */
+
 // device view of one uploaded batch
 struct lb2_dev_batch {
 	uint32_t n_windows;
 	const uint32_t *ref_off; const int32_t *ref_start; const uint32_t *wr_off; const uint32_t *wr_idx;
 	const uint64_t *base_off; const uint8_t *flags; const uint32_t *name_rank;
-	const char *ref_seq; const char *seq; const char *qual;
+	const char *ref_seq; const char *seq; const char *qual;      // seq / qual / base_off / flags: read by the pre-pack pass only
+	// the packed pool (written by the pre-pack pass, read by the window pipeline)
+	const lb2_pkread *pk;      // [n_reads]
+	const uint32_t *pk_bits;   // 2-bit bases, 16 per word, every read on a word boundary
+	const uint16_t *pk_lowq;   // one bit per base (quality < MIN_QUAL_CALL), 16 per entry, same indexing as pk_bits
 };
 
 // per-window device output slab header (variants + strings follow at fixed strides)

@@ -1,8 +1,9 @@
 // lb2_cuda.cu -- the sm_100a kernels and the extern "C" boundary declared in include/lancet_b200.h.
 //
-// One persistent CTA per resident slot; each CTA pulls window indices from a global counter and runs
-// the whole micro-assembly of that window (lb2_process_window) out of its own workspace slab, with the
-// window's reads staged 2-bit-packed in shared memory.  No CPU fallback exists in this file: every
+// lb2_pack_*_kernel: the read pool is classified once (trim, 2-bit bases, quality mask; lb2_pack.cuh) -- a streaming pass.
+// lb2_window_kernel: one persistent CTA per resident slot; each CTA pulls window indices from a global counter and runs
+// the whole micro-assembly of that window (lb2_process_window) out of its own workspace slab, with the window's reads
+// staged from the packed pool into shared memory by bulk-async copies.  No CPU fallback exists in this file: every
 // entry point fails with LB2_ERR_CUDA when there is no usable device.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -17,19 +18,20 @@
 
 #include "lb2_pipeline.cuh"
 
+#define LB2_KERNEL_VERSION "r02-v1"
+
 struct lb2_launch {
 	lb2_params P; lb2_cfg C; lb2_dev_batch B; lb2_dev_out O;
 	uint8_t *ws_base; size_t ws_stride; uint32_t *counter;
-	const uint32_t *avail;      // streamed lb2_process: windows [0, *avail) have their reads in HBM (NULL: the batch is resident)
-	uint32_t *stalled;          // set when a window fetch gave up waiting for the watermark (the host then redoes the batch resident)
-	const uint32_t *win_list; const uint32_t *n_list;   // escalation pass: indices of the windows to redo (NULL = all windows)
+	uint32_t w_begin, w_end;      // first pass: the windows of this launch (one launch per upload segment)
+	const uint32_t *win_list; const uint32_t *n_list;   // escalation pass: indices of the windows to redo (NULL = [w_begin, w_end))
 	uint32_t *retry_list; uint32_t *retry_count;
 	// compaction outputs
 	uint32_t *var_off; uint32_t *str_off; uint32_t *totals; lb2_variant *cvars; char *cstr;
 };
 
 __global__ void __launch_bounds__(256, 3)
-lb2_window_kernel(const lb2_launch *Lp)
+lb2_window_kernel(const __grid_constant__ lb2_launch L)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ uint32_t s_next;
@@ -37,143 +39,172 @@ lb2_window_kernel(const lb2_launch *Lp)
 	// struct handed by reference to the pipeline's functions it sat in per-thread local memory, which with three 72 KB
 	// CTAs per SM has next to no L1 behind it -- every pointer fetch was an L2 round trip
 	__shared__ lb2_win sW;
-	// ... and so do the parameter blocks it points to (read inside lane-0 loops: a global load each time otherwise)
+	// ... and so do the parameter blocks it points to (read inside lane-0 loops)
 	__shared__ lb2_params sP; __shared__ lb2_cfg sC; __shared__ lb2_dev_batch sB; __shared__ lb2_dev_out sO;
 	lb2_win &W = sW;
 	if (threadIdx.x == 0) {
-		sP = Lp->P; sC = Lp->C; sB = Lp->B; sO = Lp->O;
-		W.P = &sP; W.C = &sC; W.B = &sB; W.O = &sO; W.escal = (Lp->win_list != nullptr);
-		lb2_ws_layout(Lp->C, Lp->ws_base + (size_t)blockIdx.x * Lp->ws_stride, &W.ws); W.ws0 = W.ws;
+		sP = L.P; sC = L.C; sB = L.B; sO = L.O;
+		W.P = &sP; W.C = &sC; W.B = &sB; W.O = &sO; W.escal = (L.win_list != nullptr);
+		lb2_ws_layout(L.C, L.ws_base + (size_t)blockIdx.x * L.ws_stride, &W.ws); W.ws0 = W.ws;
 		W.sh = (lb2_sh *)smem;
 		W.ref_raw = (char *)smem + ((sizeof(lb2_sh) + 15) & ~(size_t)15);
 		W.bits = (uint32_t *)(W.ref_raw + LB2_MAX_REF);
-		W.lowq = W.bits + (Lp->C.max_bp / 16 + 4);
-		W.treg = smem + ((lb2_smem_fixed(Lp->C.max_bp) + 15) & ~(size_t)15);
+		W.lowq = W.bits + (L.C.max_bp / 16 + 4);
+		W.treg = smem + ((lb2_smem_fixed(L.C.max_bp) + 15) & ~(size_t)15);
+		lb2_mbar_init(&W.sh->mbar, blockDim.x); W.sh->mbar_phase = 0;
 	}
 	__syncthreads();
-	const uint32_t nwin = Lp->win_list ? *Lp->n_list : Lp->B.n_windows;
+	const uint32_t nwin = L.win_list ? *L.n_list : (L.w_end - L.w_begin);
 	while (true) {
-		if (threadIdx.x == 0) {
-			const uint32_t nx = atomicAdd(Lp->counter, 1u);
-			uint32_t nx2 = nx;
-			if (Lp->avail && nx < nwin) {      // the read pool is still arriving on the copy stream: wait for this window's watermark
-				// (never forever: if something serialises the copy stream behind this kernel -- a profiler, a debugger --
-				// the fetch gives up after two seconds and the host redoes the batch the resident way)
-				unsigned long long t0 = 0, t1 = 0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-				while (*(volatile const uint32_t *)Lp->avail <= nx) {
-					__nanosleep(200);
-					asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-					if (t1 - t0 > 2000000000ull || *(volatile uint32_t *)Lp->stalled) { *(volatile uint32_t *)Lp->stalled = 1u; nx2 = nwin; break; }
-				}
-				__threadfence_system();
-			}
-			s_next = nx2;
-		}
+		if (threadIdx.x == 0) { s_next = atomicAdd(L.counter, 1u); }
 		__syncthreads();
 		uint32_t w = s_next;
 		__syncthreads();
 		if (w >= nwin) { break; }
-		if (Lp->win_list) { w = Lp->win_list[w]; }
+		w = L.win_list ? L.win_list[w] : L.w_begin + w;
 		lb2_process_window(W, w);
 	}
 }
 
-// windows that ran out of a per-CTA capacity in the first pass are redone by the escalation pass
-// (same kernel, larger table / arena / BFS queue, one CTA per SM)
-__global__ void lb2_collect_kernel(const lb2_launch *Lp)
+// ---- the pre-pack pass over pool reads [r0, r1): word counts per block of LB2_PACK_BLOCK reads, their exclusive scan
+// ---- (continuing from *carry, the words of the reads packed before), then the pass itself
+#define LB2_PACK_BLOCK 1024
+__global__ void __launch_bounds__(256) lb2_pack_count_kernel(const uint64_t *base_off, uint32_t r0, uint32_t r1, uint32_t *blk)
 {
-	const uint32_t n = Lp->B.n_windows;
+	__shared__ uint32_t sc[40];
+	const uint32_t r = r0 + blockIdx.x * LB2_PACK_BLOCK + threadIdx.x * 4u; uint32_t sum = 0;
+	for (uint32_t q = 0; q < 4; ++q) { if (r + q < r1) { sum += lb2_pack_nwords(base_off[r + q + 1] - base_off[r + q]); } }
+	uint32_t total = 0; lb2_block_excl(sc, sum, &total);
+	if (threadIdx.x == 0) { blk[blockIdx.x] = total; }
+}
+__global__ void __launch_bounds__(1024) lb2_pack_scan_kernel(uint32_t *blk, uint32_t nblk, uint32_t *carry)
+{
+	__shared__ uint32_t sc[40]; __shared__ uint32_t s_base;
+	if (threadIdx.x == 0) { s_base = *carry; }
+	__syncthreads();
+	for (uint32_t i0 = 0; i0 < nblk; i0 += blockDim.x) {
+		const uint32_t i = i0 + threadIdx.x, v = i < nblk ? blk[i] : 0u; uint32_t tot = 0;
+		const uint32_t ex = lb2_block_excl(sc, v, &tot);
+		if (i < nblk) { blk[i] = s_base + ex; }
+		__syncthreads();
+		if (threadIdx.x == 0) { s_base += tot; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { *carry = s_base; }
+}
+__global__ void __launch_bounds__(256) lb2_pack_kernel(const lb2_dev_batch B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4,
+                                                      uint32_t r0, uint32_t r1, const uint32_t *blk)
+{
+	__shared__ uint32_t sc[40]; __shared__ uint32_t s_w[LB2_PACK_BLOCK];
+	const uint32_t rb = r0 + blockIdx.x * LB2_PACK_BLOCK, t = threadIdx.x; uint32_t cnt[4], sum = 0;
+	for (uint32_t q = 0; q < 4; ++q) { const uint32_t r = rb + t * 4u + q; cnt[q] = (r < r1) ? lb2_pack_nwords(B.base_off[r + 1] - B.base_off[r]) : 0u; sum += cnt[q]; }
+	uint32_t total = 0, ex = lb2_block_excl(sc, sum, &total) + blk[blockIdx.x];
+	for (uint32_t q = 0; q < 4; ++q) { s_w[t * 4u + q] = ex; ex += cnt[q]; }
+	__syncthreads();
+	// a group of LB2_GS lanes per read, neighbouring groups on neighbouring reads (every lane of a warp runs every round)
+	for (uint32_t j = lb2_group(); j < LB2_PACK_BLOCK; j += lb2_ngroups()) {
+		const uint32_t r = rb + j;
+		lb2_pack_read(B, pk, pk_bits, pk_lowq, qtrim4, qcall4, r < r1, r, s_w[j]);
+	}
+}
+
+// windows that ran out of a per-CTA capacity in the first pass are redone by the escalation pass
+// (same kernel, larger table / arena / BFS queue / staging area, one CTA per SM)
+__global__ void lb2_collect_kernel(const __grid_constant__ lb2_launch L)
+{
+	const uint32_t n = L.B.n_windows;
 	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
-		lb2_window_info wi = Lp->O.info[w];
+		lb2_window_info wi = L.O.info[w];
 		if (wi.status == LB2_WIN_OVERFLOW) {
 			uint32_t d = wi.detail;
 			if (d == LB2_D_HASH_FULL || d == LB2_D_NODES || d == LB2_D_ARENA || d == LB2_D_QUEUE || d == LB2_D_SMEM || d == LB2_D_BUCKETS ||
 			    d == LB2_D_STACK || d == LB2_D_EDGES || d == LB2_D_SPECIAL || d == LB2_D_READS ||
 			    d == LB2_D_VARIANTS || d == LB2_D_STRINGS) {      // (escalated windows emit into the large output slabs)
-				Lp->retry_list[atomicAdd(Lp->retry_count, 1u)] = w;
+				L.retry_list[atomicAdd(L.retry_count, 1u)] = w;
 			}
 		}
 	}
 }
 
 // exclusive scans of per-window variant counts and string bytes (one block)
-__global__ void lb2_scan_kernel(const lb2_launch *Lp)
+__global__ void lb2_scan_kernel(const __grid_constant__ lb2_launch L)
 {
 	__shared__ uint32_t pv[1024], ps[1024];
-	const uint32_t n = Lp->B.n_windows, t = threadIdx.x, nt = blockDim.x;
-	const uint32_t chunk = (n + nt - 1) / nt, lo = t * chunk, hi = min(n, lo + chunk);
+	const uint32_t n = L.B.n_windows, t = threadIdx.x, nt = blockDim.x;
+	const uint32_t chunk = (n + nt - 1) / nt, lo = min(n, t * chunk), hi = min(n, lo + chunk);
 	uint32_t sv = 0, ss = 0;
-	for (uint32_t w = lo; w < hi; ++w) { sv += Lp->O.info[w].n_variants; ss += (Lp->O.info[w].n_variants ? Lp->O.str_used[w] : 0); }
+	for (uint32_t w = lo; w < hi; ++w) { sv += L.O.info[w].n_variants; ss += (L.O.info[w].n_variants ? L.O.str_used[w] : 0); }
 	pv[t] = sv; ps[t] = ss; __syncthreads();
 	if (t == 0) {
 		uint32_t av = 0, as = 0;
 		for (uint32_t i = 0; i < nt; ++i) { uint32_t v = pv[i], s = ps[i]; pv[i] = av; ps[i] = as; av += v; as += s; }
-		Lp->totals[0] = av; Lp->totals[1] = as;
+		L.totals[0] = av; L.totals[1] = as;
 	}
 	__syncthreads();
 	uint32_t av = pv[t], as = ps[t];
 	for (uint32_t w = lo; w < hi; ++w) {
-		Lp->var_off[w] = av; Lp->str_off[w] = as;
-		uint32_t nv = Lp->O.info[w].n_variants; av += nv; as += (nv ? Lp->O.str_used[w] : 0);
+		L.var_off[w] = av; L.str_off[w] = as;
+		uint32_t nv = L.O.info[w].n_variants; av += nv; as += (nv ? L.O.str_used[w] : 0);
 	}
 }
 
 // gather the per-window slabs into dense arrays (one block per window)
-__global__ void lb2_gather_kernel(const lb2_launch *Lp)
+__global__ void lb2_gather_kernel(const __grid_constant__ lb2_launch L)
 {
-	const uint32_t w = blockIdx.x; const uint32_t nv = Lp->O.info[w].n_variants;
+	const uint32_t w = blockIdx.x; const uint32_t nv = L.O.info[w].n_variants;
 	if (!nv) { return; }
-	const uint32_t vo = Lp->var_off[w], so = Lp->str_off[w], sb = Lp->O.str_used[w];
-	const uint32_t big = Lp->O.big_slot[w];
-	const lb2_variant *vsrc = (big != 0xFFFFFFFFu) ? Lp->O.big_variants + (size_t)big * Lp->O.big_max_var : Lp->O.variants + (size_t)w * Lp->C.max_var;
+	const uint32_t vo = L.var_off[w], so = L.str_off[w], sb = L.O.str_used[w];
+	const uint32_t big = L.O.big_slot[w];
+	const lb2_variant *vsrc = (big != 0xFFFFFFFFu) ? L.O.big_variants + (size_t)big * L.O.big_max_var : L.O.variants + (size_t)w * L.C.max_var;
 	for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
-		lb2_variant v = vsrc[i]; v.str_off += so; Lp->cvars[vo + i] = v;
+		lb2_variant v = vsrc[i]; v.str_off += so; L.cvars[vo + i] = v;
 	}
-	const char *src = (big != 0xFFFFFFFFu) ? Lp->O.big_strings + (size_t)big * Lp->O.big_str_bytes : Lp->O.strings + (size_t)w * Lp->C.str_bytes;
-	for (uint32_t i = threadIdx.x; i < sb; i += blockDim.x) { Lp->cstr[so + i] = src[i]; }
+	const char *src = (big != 0xFFFFFFFFu) ? L.O.big_strings + (size_t)big * L.O.big_str_bytes : L.O.strings + (size_t)w * L.C.str_bytes;
+	for (uint32_t i = threadIdx.x; i < sb; i += blockDim.x) { L.cstr[so + i] = src[i]; }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-#define LB2_MAX_MARKS 1024
+#define LB2_MAX_SEG 16
+struct lb2_seg { uint32_t w0, w1, r0, r1; };      // windows [w0, w1) need pool reads [0, r1); reads [r0, r1) are uploaded with this segment
 struct lb2_ctx {
-	int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
-	cudaStream_t copy_stream = nullptr; uint32_t *d_avail = nullptr, *d_stalled = nullptr;      // streamed lb2_process
-	cudaEvent_t ev_avail = nullptr; uint32_t *h_marks = nullptr;          // (pinned) per chunk: windows ready
-	std::vector<uint32_t> h_need;                                         // per window: leading pool reads the windows up to it use
+	int device = 0; int sm_count = 0; uint32_t threads = 256; size_t smem_optin = 0;
+	cudaStream_t stream = nullptr, copy_stream = nullptr, wstream[2] = { nullptr, nullptr };
+	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };      // run: start, packed, first pass, escalation, compaction
+	cudaEvent_t ev_ready = nullptr, ev_seg[LB2_MAX_SEG] = {}, ev_w[2] = { nullptr, nullptr };
 	lb2_params P; lb2_cfg C;
-	int sm_count; uint32_t threads = 256;
 	std::string err;
-	// device buffers of the resident batch
 	struct Buf { void *p = nullptr; size_t cap = 0; };
+	// device buffers of the batch: the caller's arrays, the packed pool, the outputs
 	Buf d_ref_off, d_ref_start, d_wr_off, d_wr_idx, d_base_off, d_flags, d_name_rank, d_ref_seq, d_seq, d_qual;
-	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws, d_big_vars, d_big_strs, d_big_slot;
-	uint32_t *d_big_count = nullptr; uint32_t big_cap = 256, big_max_var = 1024, big_str_bytes = 128u << 10;
-	uint32_t *d_counter = nullptr, *d_totals = nullptr; lb2_launch *d_launch = nullptr; unsigned long long *d_prof = nullptr;
-	lb2_launch L;
-	uint32_t n_windows = 0; bool resident = false, ran = false;
-	size_t ws_stride = 0; uint32_t ws_slots = 0;
-	// escalation pass
-	lb2_cfg C2; lb2_launch L2; lb2_launch *d_launch2 = nullptr; Buf d_ws2, d_retry; uint32_t *d_counter2 = nullptr, *d_retry_count = nullptr;
-	size_t ws2_stride = 0; uint32_t ws2_slots = 0; bool escalate = true;
+	Buf d_pk, d_pk_bits, d_pk_lowq, d_blk;
+	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws, d_big_vars, d_big_strs, d_big_slot, d_ws2, d_retry;
+	uint32_t *d_counters = nullptr;      // [LB2_MAX_SEG] window counters of the first-pass launches, [LB2_MAX_SEG] escalation, +1 retry count, +2 big count, +3 pack carry, +4.. totals
+	unsigned long long *d_prof = nullptr;
+	uint32_t big_cap = 256, big_max_var = 1024, big_str_bytes = 128u << 10;
+	lb2_launch L, L2;
+	uint32_t n_windows = 0, n_reads = 0; bool resident = false, ran = false, escalate = true;
+	size_t ws_stride = 0; uint32_t ws_slots = 0, ws_sets = 0; size_t ws2_stride = 0; uint32_t ws2_slots = 0;
+	lb2_cfg C2;
+	std::vector<uint32_t> h_need;        // per window: leading pool reads the windows up to it use
 	uint64_t launches = 0;
 	float kernel_ms = 0;
 	// host result
 	std::vector<lb2_window_info> h_info; std::vector<lb2_variant> h_vars; std::vector<char> h_str;
 	uint64_t h2d_bytes = 0, d2h_bytes = 0;
 };
+enum { LB2_CTR_RETRY = 2 * LB2_MAX_SEG, LB2_CTR_BIG, LB2_CTR_CARRY, LB2_CTR_TOTALS, LB2_CTR_N = LB2_CTR_TOTALS + 2 };
 
 #define LB2_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return LB2_ERR_CUDA; } } while (0)
 
-static int lb2_reserve(lb2_ctx *ctx, lb2_ctx::Buf &b, size_t bytes, bool zero = false)
+static int lb2_reserve(lb2_ctx *ctx, lb2_ctx::Buf &b, size_t bytes)
 {
 	if (bytes <= b.cap && b.p) { return LB2_OK; }
 	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 	size_t cap = bytes + bytes / 4 + 256;
 	LB2_CK(cudaMalloc(&b.p, cap));
 	b.cap = cap;
-	if (zero) { LB2_CK(cudaMemsetAsync(b.p, 0, cap, ctx->stream)); }
 	return LB2_OK;
 }
 
@@ -196,25 +227,45 @@ extern "C" const char *lb2_strerror(const lb2_ctx *ctx, int code)
 	}
 	return "unknown error";
 }
+extern "C" const char *lb2_kernel_version(void) { return LB2_KERNEL_VERSION; }
 
 static uint32_t env_u32(const char *name, uint32_t dflt) { const char *s = getenv(name); return s ? (uint32_t)strtoul(s, nullptr, 10) : dflt; }
+
+extern "C" void lb2_destroy(lb2_ctx *ctx)
+{
+	if (!ctx) { return; }
+	cudaSetDevice(ctx->device);
+	lb2_ctx::Buf *bufs[] = { &ctx->d_ref_off, &ctx->d_ref_start, &ctx->d_wr_off, &ctx->d_wr_idx, &ctx->d_base_off, &ctx->d_flags, &ctx->d_name_rank,
+		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_pk, &ctx->d_pk_bits, &ctx->d_pk_lowq, &ctx->d_blk, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used,
+		&ctx->d_var_off, &ctx->d_str_off, &ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot, &ctx->d_ws2, &ctx->d_retry };
+	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
+	if (ctx->d_counters) { cudaFree(ctx->d_counters); } if (ctx->d_prof) { cudaFree(ctx->d_prof); }
+	for (auto &e : ctx->ev) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_seg) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_w) { if (e) { cudaEventDestroy(e); } }
+	if (ctx->ev_ready) { cudaEventDestroy(ctx->ev_ready); }
+	if (ctx->stream) { cudaStreamDestroy(ctx->stream); } if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); }
+	for (auto &st : ctx->wstream) { if (st) { cudaStreamDestroy(st); } }
+	cudaGetLastError();
+	delete ctx;
+}
 
 extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 {
 	if (!out || !params) { return LB2_ERR_ARG; }
 	*out = nullptr;
 	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { return LB2_ERR_CUDA; }
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return LB2_ERR_CUDA; }
 	lb2_ctx *ctx = new lb2_ctx();
 	ctx->device = device; ctx->P = *params;
+	auto fail = [&]() { lb2_destroy(ctx); return LB2_ERR_CUDA; };      // (frees whatever the half-built context holds)
 	cudaDeviceProp prop;
-	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
-	if (prop.major < 10) { delete ctx; return LB2_ERR_CUDA; }
-	ctx->sm_count = prop.multiProcessorCount;
-	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
-	if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&ctx->d_avail, 4) != cudaSuccess || cudaMalloc(&ctx->d_stalled, 4) != cudaSuccess || cudaMemset(ctx->d_stalled, 0, 4) != cudaSuccess ||
-	    cudaEventCreateWithFlags(&ctx->ev_avail, cudaEventDisableTiming) != cudaSuccess || cudaHostAlloc((void **)&ctx->h_marks, sizeof(uint32_t) * LB2_MAX_MARKS, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
-	cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { return fail(); }
+	ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	cudaStream_t *streams[] = { &ctx->stream, &ctx->copy_stream, &ctx->wstream[0], &ctx->wstream[1] };
+	for (auto st : streams) { if (cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess) { return fail(); } }
+	for (auto &e : ctx->ev) { if (cudaEventCreate(&e) != cudaSuccess) { return fail(); } }
+	for (auto &e : ctx->ev_seg) { if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return fail(); } }
+	for (auto &e : ctx->ev_w) { if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return fail(); } }
+	if (cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess) { return fail(); }
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
 	C.table_slots = env_u32("LB2_TABLE_SLOTS", 4096); C.max_nodes = C.table_slots - C.table_slots / 4;
 	C.max_reads = 4096; C.max_bp = 0;
@@ -222,66 +273,48 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 18);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
 	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 128); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
-	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
-	if (cudaMalloc(&ctx->d_counter2, 4) != cudaSuccess || cudaMalloc(&ctx->d_retry_count, 4) != cudaSuccess || cudaMalloc(&ctx->d_launch2, sizeof(lb2_launch)) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
+	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { return fail(); }
+	if (cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess || cudaMemset(ctx->d_counters, 0, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess) { return fail(); }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
 	ctx->big_cap = env_u32("LB2_BIG_SLABS", 256); ctx->big_max_var = env_u32("LB2_BIG_MAX_VAR", 1024); ctx->big_str_bytes = env_u32("LB2_BIG_STR_BYTES", 128u << 10);
-	if (cudaMalloc(&ctx->d_big_count, 4) != cudaSuccess) { delete ctx; return LB2_ERR_CUDA; }
 	ctx->threads = env_u32("LB2_THREADS", 256); if (ctx->threads < 32 || ctx->threads > 256 || (ctx->threads & 31)) { ctx->threads = 256; }
-	if (cudaMalloc(&ctx->d_counter, 4) != cudaSuccess || cudaMalloc(&ctx->d_totals, 8) != cudaSuccess || cudaMalloc(&ctx->d_launch, sizeof(lb2_launch)) != cudaSuccess) {
-		delete ctx; return LB2_ERR_CUDA;
-	}
 	*out = ctx;
 	return LB2_OK;
 }
 
-extern "C" void lb2_destroy(lb2_ctx *ctx)
-{
-	if (!ctx) { return; }
-	cudaSetDevice(ctx->device);
-	lb2_ctx::Buf *bufs[] = { &ctx->d_ref_off, &ctx->d_ref_start, &ctx->d_wr_off, &ctx->d_wr_idx, &ctx->d_base_off, &ctx->d_flags, &ctx->d_name_rank,
-		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used, &ctx->d_var_off, &ctx->d_str_off,
-		&ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot };
-	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
-	if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); } if (ctx->d_retry.p) { cudaFree(ctx->d_retry.p); }
-	cudaFree(ctx->d_big_count); cudaFree(ctx->d_counter2); cudaFree(ctx->d_retry_count); cudaFree(ctx->d_launch2);
-	cudaFree(ctx->d_counter); cudaFree(ctx->d_totals); cudaFree(ctx->d_launch);
-	cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
-	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); } cudaFree(ctx->d_avail); cudaFree(ctx->d_stalled);
-	if (ctx->ev_avail) { cudaEventDestroy(ctx->ev_avail); } if (ctx->h_marks) { cudaFreeHost(ctx->h_marks); }
-	delete ctx;
-}
-
 extern "C" uint64_t lb2_kernel_launches(const lb2_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-// streamed = false: the whole batch is copied and the call returns when it is resident (lb2_upload).
-// streamed = true (lb2_process): everything except the read pool's bases/qualities is enqueued; h_need[w] = number of
-// leading pool reads the windows [0, w] use, so that the pool can follow in chunks while the kernel already runs.
-static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
+// ---- planning: one pass over the windows' read lists (millions of entries for a 1 Mb region, split over a few host threads):
+// staging need per window (whole 16-base words of the untrimmed reads, up to 14 pad words per run of pool-consecutive reads,
+// the reference), reads per window, and how far into the pool the windows up to each window reach.  Then the launch
+// configuration, the device buffers and the launch descriptors.
+static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 {
 	if (!ctx || !b) { return LB2_ERR_ARG; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
 	ctx->resident = false; ctx->ran = false;
 	const uint32_t W = b->n_windows, R = b->n_reads;
-	// staging bound: every read rounded up to 32 bases + reference + padding (untrimmed lengths)
+	if ((W && (!b->ref_off || !b->ref_start || !b->wr_off)) || (R && (!b->base_off || !b->flags || !b->name_rank)) || (b->n_wr && !b->wr_idx)) { return LB2_ERR_ARG; }
 	uint32_t max_bp = 0, max_reads = 0;
-	if (streamed) { ctx->h_need.resize(W); }
+	ctx->h_need.resize(W);
 	{
-		// one pass over the windows' read lists (millions of entries for a 1 Mb region): split over a few host threads
 		const unsigned hw = std::thread::hardware_concurrency();
-		const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(hw, 8u), env_u32("LB2_HOST_THREADS", 8)) : 1u;
+		const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(hw, 8u), std::max(1u, env_u32("LB2_HOST_THREADS", 8))) : 1u;
 		std::vector<uint32_t> t_bp(T, 0), t_rd(T, 0); std::vector<int> t_bad(T, 0);
 		auto work = [&](unsigned t) {
 			const uint32_t w0 = (uint32_t)((uint64_t)W * t / T), w1 = (uint32_t)((uint64_t)W * (t + 1) / T);
 			uint32_t mbp = 0, mrd = 0;
 			for (uint32_t w = w0; w < w1; ++w) {
-				uint64_t bp = 0; uint32_t top = 0;
+				uint64_t bp = 0; uint32_t top = 0, prev = 0xFFFFFFFEu;
+				if (b->wr_off[w + 1] < b->wr_off[w] || b->wr_off[w + 1] > b->n_wr || b->ref_off[w + 1] < b->ref_off[w]) { t_bad[t] = 1; return; }
 				for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
 					const uint32_t r = b->wr_idx[x]; if (r >= R) { t_bad[t] = 1; return; }
-					bp += ((b->base_off[r + 1] - b->base_off[r]) + 15) & ~15ull;
+					bp += (uint64_t)lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]) * 16u;
+					if (r != prev + 1u) { bp += 14u * 16u; }
+					prev = r;
 					if (r >= top) { top = r + 1; }
 				}
-				if (streamed) { ctx->h_need[w] = top; }
+				ctx->h_need[w] = top;
 				bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; bp += 128;
 				if (bp > mbp) { mbp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
 				mrd = std::max(mrd, b->wr_off[w + 1] - b->wr_off[w]);
@@ -291,135 +324,180 @@ static int lb2_upload_impl(lb2_ctx *ctx, const lb2_batch *b, bool streamed)
 		if (T == 1) { work(0); }
 		else { std::vector<std::thread> th; for (unsigned t = 0; t < T; ++t) { th.emplace_back(work, t); } for (auto &x : th) { x.join(); } }
 		for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); }
-		if (streamed) { uint32_t need = 0; for (uint32_t w = 0; w < W; ++w) { need = std::max(need, ctx->h_need[w]); ctx->h_need[w] = need; } }      // leading pool reads the windows [0, w] use
+		uint32_t need = 0; for (uint32_t w = 0; w < W; ++w) { need = std::max(need, ctx->h_need[w]); ctx->h_need[w] = need; }
 	}
-	max_bp = (max_bp + 1023) & ~1023u; if (max_bp < 32768) { max_bp = 32768; }
-	const uint32_t smem_cap = 220u << 10;
-	if (max_bp > (1u << 20) - 1024) { max_bp = (1u << 20) - 1024; }   // representative base index has 20 bits in the table key
+	const uint32_t need_bp = std::min<uint32_t>((max_bp + 1023) & ~1023u, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
+	const uint32_t smem_cap = (uint32_t)std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : (227u << 10), 227u << 10) - 2048u;      // (static shared memory of the kernel comes on top)
 	lb2_cfg &C = ctx->C;
 	C.table_slots = std::min<uint32_t>(env_u32("LB2_TABLE_SLOTS", 4096), 16384u);      // (occurrence words hold 14-bit slot numbers)
-	while (C.table_slots > 1024 && lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes) > smem_cap) { C.table_slots >>= 1; }
-	while (lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes) > smem_cap) { max_bp -= 1024; }   // windows beyond this report LB2_WIN_OVERFLOW
+	// First pass: sized for the windows that still let LB2_MIN_CTAS_PER_SM CTAs share an SM; a window that needs more staging
+	// area than that goes to the escalation pass, which has the whole SM to itself (one outlier must not cost every window
+	// of the batch its occupancy)
+	uint32_t bp1 = std::max(need_bp, 32768u);
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+	{
+		const uint32_t want_occ = std::max(1u, env_u32("LB2_MIN_CTAS_PER_SM", 3));
+		while (bp1 > 32768u) {
+			int occ = 0; const size_t sm = lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes);
+			if (sm <= smem_cap && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, (int)ctx->threads, sm) == cudaSuccess && (uint32_t)occ >= want_occ) { break; }
+			bp1 -= 1024;
+		}
+		cudaGetLastError();
+	}
+	while (C.table_slots > 1024 && lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes) > smem_cap) { C.table_slots >>= 1; }
 	C.max_nodes = C.table_slots - C.table_slots / 4;
-	C.max_bp = max_bp; C.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C.table_slots, C.graph_bytes); C.max_reads = std::max(max_reads + 2, 64u);
-	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smem_bytes));
+	C.max_bp = bp1; C.smem_bytes = (uint32_t)lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes); C.max_reads = std::max(max_reads + 2, 64u);
 	int occ = 0;
 	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, (int)ctx->threads, C.smem_bytes));
 	if (occ < 1) { ctx->err = "kernel does not fit on an SM"; return LB2_ERR_CUDA; }
-	uint32_t max_occ = env_u32("LB2_MAX_CTAS_PER_SM", 16);
-	C.n_slots = (uint32_t)ctx->sm_count * std::min<uint32_t>((uint32_t)occ, max_occ);
-	if (C.n_slots > std::max(W, 1u)) { C.n_slots = std::max(W, 1u); }
-	size_t stride = lb2_ws_layout(C, nullptr, nullptr);
-	if (stride != ctx->ws_stride || C.n_slots > ctx->ws_slots) {
+	C.n_slots = (uint32_t)ctx->sm_count * std::min<uint32_t>((uint32_t)occ, env_u32("LB2_MAX_CTAS_PER_SM", 16));
+	const size_t stride = lb2_ws_layout(C, nullptr, nullptr); const uint32_t sets = two_sets ? 2u : 1u;
+	if (stride != ctx->ws_stride || C.n_slots > ctx->ws_slots || sets > ctx->ws_sets) {
 		if (ctx->d_ws.p) { cudaFree(ctx->d_ws.p); ctx->d_ws.p = nullptr; ctx->d_ws.cap = 0; }
-		size_t bytes = stride * C.n_slots;
+		const size_t bytes = stride * C.n_slots * sets;
 		LB2_CK(cudaMalloc(&ctx->d_ws.p, bytes)); ctx->d_ws.cap = bytes;
-		LB2_CK(cudaMemsetAsync(ctx->d_ws.p, 0, bytes, ctx->stream));   // the hash table must start all-zero
-		ctx->ws_stride = stride; ctx->ws_slots = C.n_slots;
+		ctx->ws_stride = stride; ctx->ws_slots = C.n_slots; ctx->ws_sets = sets;
 	}
-	uint64_t h2d = 0;
-#define LB2_UP(buf, ptr, bytes) do { int rc_ = lb2_reserve(ctx, ctx->buf, (bytes)); if (rc_) return rc_; \
-		LB2_CK(cudaMemcpyAsync(ctx->buf.p, (ptr), (bytes), cudaMemcpyHostToDevice, ctx->stream)); h2d += (bytes); } while (0)
-	// streamed: only the three per-window offset tables go ahead of the kernels, everything else follows in chunks (lb2_process)
-#define LB2_UPS(buf, ptr, bytes) do { if (!streamed) { LB2_UP(buf, ptr, bytes); } else { int rc2_ = lb2_reserve(ctx, ctx->buf, (bytes)); if (rc2_) return rc2_; h2d += (bytes); } } while (0)
-	LB2_UP(d_ref_off, b->ref_off, sizeof(uint32_t) * (size_t)(W + 1));
-	LB2_UP(d_ref_start, b->ref_start, sizeof(int32_t) * (size_t)W);
-	LB2_UP(d_wr_off, b->wr_off, sizeof(uint32_t) * (size_t)(W + 1));
-	LB2_UPS(d_wr_idx, b->wr_idx, sizeof(uint32_t) * (size_t)b->n_wr);
-	LB2_UPS(d_base_off, b->base_off, sizeof(uint64_t) * (size_t)(R + 1));
-	LB2_UPS(d_flags, b->flags, (size_t)R);
-	LB2_UPS(d_name_rank, b->name_rank, sizeof(uint32_t) * (size_t)R);
-	LB2_UPS(d_ref_seq, b->ref_seq, (size_t)b->n_ref_bytes);
-	LB2_UPS(d_seq, b->seq, (size_t)b->n_base_bytes);
-	LB2_UPS(d_qual, b->qual, (size_t)b->n_base_bytes);
-#undef LB2_UPS
-#undef LB2_UP
-	ctx->h2d_bytes = h2d;
 	int rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_info, sizeof(lb2_window_info) * (size_t)W))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_vars, sizeof(lb2_variant) * (size_t)W * C.max_var))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_strs, (size_t)W * C.str_bytes))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_str_used, sizeof(uint32_t) * (size_t)W))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_var_off, sizeof(uint32_t) * (size_t)W))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_str_off, sizeof(uint32_t) * (size_t)W))) return rc;
+#define LB2_RS(buf, bytes) do { if ((rc = lb2_reserve(ctx, ctx->buf, (bytes)))) { return rc; } } while (0)
+	LB2_RS(d_ref_off, sizeof(uint32_t) * (size_t)(W + 1)); LB2_RS(d_ref_start, sizeof(int32_t) * (size_t)W + 4); LB2_RS(d_wr_off, sizeof(uint32_t) * (size_t)(W + 1));
+	LB2_RS(d_wr_idx, sizeof(uint32_t) * (size_t)b->n_wr + 4); LB2_RS(d_base_off, sizeof(uint64_t) * (size_t)(R + 1)); LB2_RS(d_flags, (size_t)R + 4);
+	LB2_RS(d_name_rank, sizeof(uint32_t) * (size_t)R + 4); LB2_RS(d_ref_seq, (size_t)b->n_ref_bytes + 4); LB2_RS(d_seq, (size_t)b->n_base_bytes + 64); LB2_RS(d_qual, (size_t)b->n_base_bytes + 64);
+	const size_t pk_words = (size_t)(b->n_base_bytes / 16) + R + 64;
+	LB2_RS(d_pk, sizeof(lb2_pkread) * ((size_t)R + 1)); LB2_RS(d_pk_bits, 4 * pk_words); LB2_RS(d_pk_lowq, 2 * pk_words); LB2_RS(d_blk, sizeof(uint32_t) * ((size_t)R / LB2_PACK_BLOCK + 2 + LB2_MAX_SEG));
+	LB2_RS(d_info, sizeof(lb2_window_info) * (size_t)W + 16); LB2_RS(d_vars, sizeof(lb2_variant) * (size_t)W * C.max_var + 64); LB2_RS(d_strs, (size_t)W * C.str_bytes + 64);
+	LB2_RS(d_str_used, sizeof(uint32_t) * (size_t)W + 4); LB2_RS(d_var_off, sizeof(uint32_t) * (size_t)W + 4); LB2_RS(d_str_off, sizeof(uint32_t) * (size_t)W + 4);
 	const uint32_t nbig = ctx->escalate ? std::min<uint32_t>(ctx->big_cap, std::max(W, 1u)) : 0u;
-	if ((rc = lb2_reserve(ctx, ctx->d_cvars, sizeof(lb2_variant) * ((size_t)W * C.max_var + (size_t)nbig * ctx->big_max_var)))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_cstr, (size_t)W * C.str_bytes + (size_t)nbig * ctx->big_str_bytes))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_big_vars, sizeof(lb2_variant) * (size_t)nbig * ctx->big_max_var + 64))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_big_strs, (size_t)nbig * ctx->big_str_bytes + 64))) return rc;
-	if ((rc = lb2_reserve(ctx, ctx->d_big_slot, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
-	lb2_launch &L = ctx->L;
+	LB2_RS(d_cvars, sizeof(lb2_variant) * ((size_t)W * C.max_var + (size_t)nbig * ctx->big_max_var) + 64); LB2_RS(d_cstr, (size_t)W * C.str_bytes + (size_t)nbig * ctx->big_str_bytes + 64);
+	LB2_RS(d_big_vars, sizeof(lb2_variant) * (size_t)nbig * ctx->big_max_var + 64); LB2_RS(d_big_strs, (size_t)nbig * ctx->big_str_bytes + 64);
+	LB2_RS(d_big_slot, sizeof(uint32_t) * (size_t)(W + 1)); LB2_RS(d_retry, sizeof(uint32_t) * (size_t)(W + 1));
+#undef LB2_RS
+	lb2_launch &L = ctx->L; memset(&L, 0, sizeof L);
 	L.P = ctx->P; L.C = C;
 	L.B.n_windows = W; L.B.ref_off = (const uint32_t *)ctx->d_ref_off.p; L.B.ref_start = (const int32_t *)ctx->d_ref_start.p;
 	L.B.wr_off = (const uint32_t *)ctx->d_wr_off.p; L.B.wr_idx = (const uint32_t *)ctx->d_wr_idx.p;
 	L.B.base_off = (const uint64_t *)ctx->d_base_off.p; L.B.flags = (const uint8_t *)ctx->d_flags.p;
 	L.B.name_rank = (const uint32_t *)ctx->d_name_rank.p; L.B.ref_seq = (const char *)ctx->d_ref_seq.p;
 	L.B.seq = (const char *)ctx->d_seq.p; L.B.qual = (const char *)ctx->d_qual.p;
+	L.B.pk = (const lb2_pkread *)ctx->d_pk.p; L.B.pk_bits = (const uint32_t *)ctx->d_pk_bits.p; L.B.pk_lowq = (const uint16_t *)ctx->d_pk_lowq.p;
 	L.O.info = (lb2_window_info *)ctx->d_info.p; L.O.variants = (lb2_variant *)ctx->d_vars.p; L.O.strings = (char *)ctx->d_strs.p;
 	L.O.str_used = (uint32_t *)ctx->d_str_used.p; L.O.prof = ctx->d_prof;
 	L.O.big_variants = (lb2_variant *)ctx->d_big_vars.p; L.O.big_strings = (char *)ctx->d_big_strs.p; L.O.big_slot = (uint32_t *)ctx->d_big_slot.p;
-	L.O.big_count = ctx->d_big_count; L.O.big_cap = nbig; L.O.big_max_var = ctx->big_max_var; L.O.big_str_bytes = ctx->big_str_bytes;
-	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counter;
-	L.win_list = nullptr; L.n_list = nullptr; L.avail = streamed ? ctx->d_avail : nullptr; L.stalled = ctx->d_stalled;
-	if ((rc = lb2_reserve(ctx, ctx->d_retry, sizeof(uint32_t) * (size_t)(W + 1)))) return rc;
-	L.retry_list = (uint32_t *)ctx->d_retry.p; L.retry_count = ctx->d_retry_count;
-	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_totals;
+	L.O.big_count = ctx->d_counters + LB2_CTR_BIG; L.O.big_cap = nbig; L.O.big_max_var = ctx->big_max_var; L.O.big_str_bytes = ctx->big_str_bytes;
+	L.ws_base = (uint8_t *)ctx->d_ws.p; L.ws_stride = ctx->ws_stride; L.counter = ctx->d_counters;
+	L.w_begin = 0; L.w_end = W; L.win_list = nullptr; L.n_list = nullptr;
+	L.retry_list = (uint32_t *)ctx->d_retry.p; L.retry_count = ctx->d_counters + LB2_CTR_RETRY;
+	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_counters + LB2_CTR_TOTALS;
 	L.cvars = (lb2_variant *)ctx->d_cvars.p; L.cstr = (char *)ctx->d_cstr.p;
-	LB2_CK(cudaMemcpyAsync(ctx->d_launch, &L, sizeof L, cudaMemcpyHostToDevice, ctx->stream));
 	if (ctx->escalate) {
-		// escalation pass: the largest table that still fits beside the staged reads, big arena / BFS queue, one CTA per SM
+		// escalation pass: one CTA per SM, the largest staging area / table / graph region that fit, big arena / BFS queue
 		lb2_cfg &C2 = ctx->C2; C2 = C;
 		C2.table_slots = std::min<uint32_t>(env_u32("LB2_TABLE_SLOTS2", 16384), 16384u); C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 184u << 10);
-		while (C2.graph_bytes > C.graph_bytes && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.graph_bytes -= 4096; }
-		while (C2.table_slots > C.table_slots && lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.table_slots >>= 1; }
+		C2.max_bp = std::max(need_bp, bp1);
+		while (C2.graph_bytes > C.graph_bytes && lb2_smem_bytes(C2.max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.graph_bytes -= 4096; }
+		while (C2.table_slots > C.table_slots && lb2_smem_bytes(C2.max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.table_slots >>= 1; }
+		while (C2.max_bp > bp1 && lb2_smem_bytes(C2.max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.max_bp -= 1024; }      // windows beyond this report LB2_WIN_OVERFLOW
 		C2.max_nodes = C2.table_slots - C2.table_slots / 4;
-		C2.smem_bytes = (uint32_t)lb2_smem_bytes(max_bp, C2.table_slots, C2.graph_bytes);
+		C2.smem_bytes = (uint32_t)lb2_smem_bytes(C2.max_bp, C2.table_slots, C2.graph_bytes);
 		C2.arena_bytes = env_u32("LB2_ARENA_BYTES2", 8u << 20); C2.deficit_bytes = env_u32("LB2_DEFICIT_BYTES2", 16u << 20);
 		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 22); C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20); C2.max_special = env_u32("LB2_MAX_SPECIAL2", 2048);
-		C2.n_slots = (uint32_t)std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 64));
-		size_t stride2 = lb2_ws_layout(C2, nullptr, nullptr);
+		C2.n_slots = std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 1024));
+		const size_t stride2 = lb2_ws_layout(C2, nullptr, nullptr);
 		if (stride2 != ctx->ws2_stride || C2.n_slots > ctx->ws2_slots) {
 			if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); ctx->d_ws2.p = nullptr; }
 			LB2_CK(cudaMalloc(&ctx->d_ws2.p, stride2 * C2.n_slots)); ctx->d_ws2.cap = stride2 * C2.n_slots;
 			ctx->ws2_stride = stride2; ctx->ws2_slots = C2.n_slots;
 		}
-		lb2_launch &L2 = ctx->L2; L2 = L; L2.C = C2; L2.avail = nullptr;      // (the first pass ends after the last pool chunk has arrived)
-		L2.ws_base = (uint8_t *)ctx->d_ws2.p; L2.ws_stride = stride2; L2.counter = ctx->d_counter2;
-		L2.win_list = (const uint32_t *)ctx->d_retry.p; L2.n_list = ctx->d_retry_count;
-		LB2_CK(cudaMemcpyAsync(ctx->d_launch2, &L2, sizeof L2, cudaMemcpyHostToDevice, ctx->stream));
-		LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(C.smem_bytes, C2.smem_bytes)));
+		lb2_launch &L2 = ctx->L2; L2 = L; L2.C = C2;
+		L2.ws_base = (uint8_t *)ctx->d_ws2.p; L2.ws_stride = stride2; L2.counter = ctx->d_counters + LB2_MAX_SEG;
+		L2.win_list = (const uint32_t *)ctx->d_retry.p; L2.n_list = ctx->d_counters + LB2_CTR_RETRY;
 	}
-	if (!streamed) { LB2_CK(cudaStreamSynchronize(ctx->stream)); }
-	ctx->n_windows = W; ctx->resident = true;
+	ctx->n_windows = W; ctx->n_reads = R;
 	return LB2_OK;
 }
 
-extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b) { return lb2_upload_impl(ctx, b, false); }
+// enqueue the pre-pack pass over pool reads [r0, r1) on stream st
+static int lb2_enqueue_pack(lb2_ctx *ctx, uint32_t r0, uint32_t r1, cudaStream_t st)
+{
+	if (r1 <= r0) { return LB2_OK; }
+	const uint32_t nblk = (r1 - r0 + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK; uint32_t *blk = (uint32_t *)ctx->d_blk.p;
+	const uint32_t qt = (uint32_t)ctx->P.min_qual_trim & 0xFFu, qc = (uint32_t)ctx->P.min_qual_call & 0xFFu;
+	lb2_pack_count_kernel<<<nblk, 256, 0, st>>>(ctx->L.B.base_off, r0, r1, blk);
+	lb2_pack_scan_kernel<<<1, 1024, 0, st>>>(blk, nblk, ctx->d_counters + LB2_CTR_CARRY);
+	lb2_pack_kernel<<<nblk, 256, 0, st>>>(ctx->L.B, (lb2_pkread *)ctx->d_pk.p, (uint32_t *)ctx->d_pk_bits.p, (uint16_t *)ctx->d_pk_lowq.p, qt * 0x01010101u, qc * 0x01010101u, r0, r1, blk);
+	ctx->launches += 3;
+	LB2_CK(cudaGetLastError());
+	return LB2_OK;
+}
 
+// enqueue one first-pass launch over windows [w0, w1) on stream st, out of workspace set `set`, counted on counter `ci`
+static int lb2_enqueue_windows(lb2_ctx *ctx, uint32_t w0, uint32_t w1, uint32_t set, uint32_t ci, cudaStream_t st)
+{
+	if (w1 <= w0) { return LB2_OK; }
+	lb2_launch L = ctx->L; L.w_begin = w0; L.w_end = w1; L.counter = ctx->d_counters + ci;
+	L.ws_base = (uint8_t *)ctx->d_ws.p + (size_t)set * ctx->ws_stride * ctx->C.n_slots;
+	const uint32_t grid = std::min<uint32_t>(ctx->C.n_slots, w1 - w0);
+	lb2_window_kernel<<<grid, ctx->threads, ctx->C.smem_bytes, st>>>(L);
+	ctx->launches += 1;
+	LB2_CK(cudaGetLastError());
+	return LB2_OK;
+}
+
+// collect the windows the first pass could not hold, redo them, compact the record slabs (stream st)
+static int lb2_enqueue_finish(lb2_ctx *ctx, cudaStream_t st, cudaEvent_t after_escalation)
+{
+	const uint32_t W = ctx->n_windows;
+	if (ctx->escalate) {
+		lb2_collect_kernel<<<64, 256, 0, st>>>(ctx->L);
+		lb2_window_kernel<<<ctx->C2.n_slots, ctx->threads, ctx->C2.smem_bytes, st>>>(ctx->L2);
+		ctx->launches += 2;
+	}
+	if (after_escalation) { LB2_CK(cudaEventRecord(after_escalation, st)); }
+	lb2_scan_kernel<<<1, 1024, 0, st>>>(ctx->L);
+	lb2_gather_kernel<<<W, 64, 0, st>>>(ctx->L);
+	ctx->launches += 2;
+	LB2_CK(cudaGetLastError());
+	return LB2_OK;
+}
+
+static int lb2_enqueue_reset(lb2_ctx *ctx, cudaStream_t st)
+{
+	LB2_CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * LB2_CTR_N, st));
+	LB2_CK(cudaMemsetAsync(ctx->d_big_slot.p, 0xFF, sizeof(uint32_t) * (size_t)(ctx->n_windows + 1), st));
+	return LB2_OK;
+}
+
+extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
+{
+	int rc = lb2_prepare(ctx, b, false); if (rc) { return rc; }
+	const uint32_t W = b->n_windows, R = b->n_reads; uint64_t h2d = 0;
+#define LB2_UP(buf, ptr, bytes) do { if (bytes) { LB2_CK(cudaMemcpyAsync(ctx->buf.p, (ptr), (bytes), cudaMemcpyHostToDevice, ctx->stream)); h2d += (bytes); } } while (0)
+	LB2_UP(d_ref_off, b->ref_off, sizeof(uint32_t) * (size_t)(W + 1)); LB2_UP(d_ref_start, b->ref_start, sizeof(int32_t) * (size_t)W); LB2_UP(d_wr_off, b->wr_off, sizeof(uint32_t) * (size_t)(W + 1));
+	LB2_UP(d_wr_idx, b->wr_idx, sizeof(uint32_t) * (size_t)b->n_wr); LB2_UP(d_base_off, b->base_off, sizeof(uint64_t) * (size_t)(R + 1)); LB2_UP(d_flags, b->flags, (size_t)R);
+	LB2_UP(d_name_rank, b->name_rank, sizeof(uint32_t) * (size_t)R); LB2_UP(d_ref_seq, b->ref_seq, (size_t)b->n_ref_bytes); LB2_UP(d_seq, b->seq, (size_t)b->n_base_bytes); LB2_UP(d_qual, b->qual, (size_t)b->n_base_bytes);
+#undef LB2_UP
+	ctx->h2d_bytes = h2d;
+	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	ctx->resident = true;
+	return LB2_OK;
+}
+
+// the hot path over a resident batch: pre-pack pass, window pipeline, escalation pass, record compaction
 extern "C" int lb2_run(lb2_ctx *ctx)
 {
 	if (!ctx) { return LB2_ERR_ARG; }
 	if (!ctx->resident) { return LB2_ERR_STATE; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
-	const uint32_t W = ctx->n_windows;
-	LB2_CK(cudaMemsetAsync(ctx->d_counter, 0, 4, ctx->stream));
-	LB2_CK(cudaMemsetAsync(ctx->d_big_count, 0, 4, ctx->stream));
-	LB2_CK(cudaMemsetAsync(ctx->d_big_slot.p, 0xFF, sizeof(uint32_t) * (size_t)(W + 1), ctx->stream));
-	LB2_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-	if (W) {
-		lb2_window_kernel<<<ctx->C.n_slots, ctx->threads, ctx->C.smem_bytes, ctx->stream>>>(ctx->d_launch);
-		if (ctx->escalate) {
-			LB2_CK(cudaMemsetAsync(ctx->d_counter2, 0, 4, ctx->stream)); LB2_CK(cudaMemsetAsync(ctx->d_retry_count, 0, 4, ctx->stream));
-			lb2_collect_kernel<<<64, 256, 0, ctx->stream>>>(ctx->d_launch);
-			lb2_window_kernel<<<ctx->C2.n_slots, ctx->threads, ctx->C2.smem_bytes, ctx->stream>>>(ctx->d_launch2);
-			ctx->launches += 2;
-		}
-		lb2_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_launch);
-		lb2_gather_kernel<<<W, 64, 0, ctx->stream>>>(ctx->d_launch);
-		ctx->launches += 3;
-	}
-	LB2_CK(cudaEventRecord(ctx->ev1, ctx->stream));
-	LB2_CK(cudaGetLastError());
+	const uint32_t W = ctx->n_windows; int rc;
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? ctx->C2.smem_bytes : 0u)));
+	if ((rc = lb2_enqueue_reset(ctx, ctx->stream))) { return rc; }
+	LB2_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+	if (W) { if ((rc = lb2_enqueue_pack(ctx, 0, ctx->n_reads, ctx->stream))) { return rc; } }
+	LB2_CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+	if (W) { if ((rc = lb2_enqueue_windows(ctx, 0, W, 0, 0, ctx->stream))) { return rc; } }
+	LB2_CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+	if (W) { if ((rc = lb2_enqueue_finish(ctx, ctx->stream, ctx->ev[3]))) { return rc; } } else { LB2_CK(cudaEventRecord(ctx->ev[3], ctx->stream)); }
+	LB2_CK(cudaEventRecord(ctx->ev[4], ctx->stream));
 	ctx->ran = true;
 	return LB2_OK;
 }
@@ -433,7 +511,7 @@ extern "C" int lb2_download(lb2_ctx *ctx, lb2_result *res)
 	uint32_t totals[2] = { 0, 0 };
 	ctx->h_info.resize(W);
 	if (W) {
-		LB2_CK(cudaMemcpyAsync(totals, ctx->d_totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		LB2_CK(cudaMemcpyAsync(totals, ctx->d_counters + LB2_CTR_TOTALS, 8, cudaMemcpyDeviceToHost, ctx->stream));
 		LB2_CK(cudaMemcpyAsync(ctx->h_info.data(), ctx->d_info.p, sizeof(lb2_window_info) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	LB2_CK(cudaStreamSynchronize(ctx->stream));
@@ -441,28 +519,26 @@ extern "C" int lb2_download(lb2_ctx *ctx, lb2_result *res)
 	if (totals[0]) { LB2_CK(cudaMemcpyAsync(ctx->h_vars.data(), ctx->d_cvars.p, sizeof(lb2_variant) * (size_t)totals[0], cudaMemcpyDeviceToHost, ctx->stream)); }
 	if (totals[1]) { LB2_CK(cudaMemcpyAsync(ctx->h_str.data(), ctx->d_cstr.p, totals[1], cudaMemcpyDeviceToHost, ctx->stream)); }
 	LB2_CK(cudaStreamSynchronize(ctx->stream));
-	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->kernel_ms = ms;
+	float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->kernel_ms = ms;
 	ctx->d2h_bytes = 8 + sizeof(lb2_window_info) * (size_t)W + sizeof(lb2_variant) * (size_t)totals[0] + totals[1];
 	res->n_windows = W; res->n_variants = totals[0]; res->windows = ctx->h_info.data(); res->variants = ctx->h_vars.data();
 	res->strings = ctx->h_str.data(); res->n_string_bytes = totals[1]; res->kernel_ms = ms;
 	return LB2_OK;
 }
 
-// Host buffers in, host buffers out.  The window tables go first, the kernels are enqueued behind them, and the read
-// pool (bases + qualities, ~85 % of the bytes) follows on a second stream in chunks; after every chunk a watermark in
-// device memory tells the running kernel how many windows have all their reads in HBM.  Chunk boundaries are 128-byte
-// aligned and a window only counts as ready once 128 bytes past its last read have arrived, so no cache line (and no
-// 16-byte over-read of the staging loads) is ever touched before it is complete.
+// Host buffers in, host buffers out.  The batch is cut into a few segments of consecutive windows (short ones first);
+// per segment the copy stream uploads what its windows read that is not on the device yet -- their reference bases,
+// their read lists, the next stretch of the pool -- and runs the pre-pack pass over those reads; the segment's windows
+// are then assembled by their own launch on one of two compute streams, while the copy stream is already busy with
+// the next segment.  Plain stream/event ordering: no kernel ever waits for a copy that was issued after it.
+// From pageable memory the copies do not overlap anything, so the batch is one segment.
 extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *result)
 {
 	if (!ctx || !batch || !result) { return LB2_ERR_ARG; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
-	{	// copies from pageable memory do not overlap a running kernel (a kernel waiting for them would wait forever):
-		// the pool is only streamed from page-locked buffers, otherwise the batch is made resident first
-		bool pinned = batch->n_base_bytes > 0 && batch->n_windows > 0 && env_u32("LB2_STREAM", 1) != 0;
-		// tools that make kernel launches synchronous would park the kernel in front of the copies it waits for
-		if ((getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSYS_PROFILING_SESSION_ID") || env_u32("CUDA_LAUNCH_BLOCKING", 0)) &&
-		    !env_u32("LB2_STREAM_FORCE", 0)) { pinned = false; }      // (LB2_STREAM_FORCE: test hook for the time-out path below)
+	const bool timing = env_u32("LB2_TIMING", 0) != 0; const auto t0 = std::chrono::steady_clock::now();
+	bool pinned = batch->n_base_bytes > 0 && batch->n_windows > 0 && env_u32("LB2_STREAM", 1) != 0;
+	{
 		const void *arrs[] = { batch->seq, batch->qual, batch->base_off, batch->flags, batch->name_rank, batch->wr_idx, batch->ref_seq };
 		const uint64_t sizes[] = { batch->n_base_bytes, batch->n_base_bytes, 1, batch->n_reads, batch->n_reads, batch->n_wr, batch->n_ref_bytes };
 		for (int i = 0; i < 7 && pinned; ++i) {
@@ -470,73 +546,74 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 			cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, arrs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost) { pinned = false; }
 		}
 		cudaGetLastError();
-		if (!pinned) {
-			int rc0 = lb2_upload_impl(ctx, batch, false); if (rc0) { return rc0; }
-			rc0 = lb2_run(ctx); if (rc0) { return rc0; }
-			return lb2_download(ctx, result);
+	}
+	int rc = lb2_prepare(ctx, batch, pinned); if (rc) { return rc; }
+	const uint32_t W = ctx->n_windows, R = ctx->n_reads;
+	// segments: the first one small (the kernels start after it), then doubling; cut at window boundaries by pool bytes
+	std::vector<lb2_seg> segs;
+	{
+		const uint64_t nb = batch->n_base_bytes;
+		const uint64_t first = std::max<uint64_t>(env_u32("LB2_SEG_FIRST", 12u << 20), 1u << 16), min_w = std::max(1u, env_u32("LB2_SEG_MIN_WINDOWS", 768));
+		uint64_t lim = first, chunk = first; uint32_t wa = 0, ra = 0;
+		while (wa < W) {
+			uint32_t wb = W;
+			if (pinned && segs.size() + 1 < LB2_MAX_SEG && nb > 2 * first) {
+				wb = wa + 1;
+				while (wb < W && (batch->base_off[ctx->h_need[wb]] <= lim || wb - wa < min_w)) { ++wb; }
+				if (W - wb < min_w) { wb = W; }
+			}
+			lb2_seg sg; sg.w0 = wa; sg.w1 = wb; sg.r0 = ra; sg.r1 = (wb == W) ? R : std::max(ra, ctx->h_need[wb - 1]);
+			segs.push_back(sg); wa = wb; ra = sg.r1; chunk *= 2; lim = batch->base_off[ra] + chunk;
 		}
 	}
-	const bool timing = env_u32("LB2_TIMING", 0) != 0; const auto t0 = std::chrono::steady_clock::now();
-	// the watermark starts at 0 before the kernel may look at it (same stream as the updates that follow)
-	LB2_CK(cudaMemsetAsync(ctx->d_avail, 0, 4, ctx->copy_stream));
-	LB2_CK(cudaMemsetAsync(ctx->d_stalled, 0, 4, ctx->copy_stream));
-	LB2_CK(cudaEventRecord(ctx->ev_avail, ctx->copy_stream));
-	LB2_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_avail, 0));
-	int rc = lb2_upload_impl(ctx, batch, true); if (rc) { return rc; }
-	const uint32_t W = ctx->n_windows; const uint64_t nb = batch->n_base_bytes;
 	const auto t1 = std::chrono::steady_clock::now();
-	rc = lb2_run(ctx); if (rc) { return rc; }
-	// chunks of consecutive windows: everything the windows [wa, wb) read -- their reference bases, their read lists, and
-	// the leading part of the pool they use (per-read tables, bases, qualities) -- then the watermark wb.  Every array's
-	// upload boundary is a multiple of 128 bytes, at least 128 bytes past the last byte the ready windows touch.
-	const uint32_t R = batch->n_reads; const uint64_t n_wr = batch->n_wr, n_ref = batch->n_ref_bytes;
-	const uint64_t chunk_max = std::max<uint64_t>((uint64_t)env_u32("LB2_STREAM_CHUNK", 8u << 20), 1u << 16);
-	uint64_t chunk = std::min<uint64_t>(chunk_max, 1u << 20);      // short chunks first: the kernel starts on the first one
-	uint64_t up_by = 0, up_rd = 0, up_bo = 0, up_wr = 0, up_ref = 0; uint32_t wa = 0; size_t c = 0;
-	auto up128 = [](uint64_t x, uint64_t unit, uint64_t cap) { const uint64_t per = 128 / unit; x = (x + per - 1) / per * per; return x > cap ? cap : x; };
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? ctx->C2.smem_bytes : 0u)));
+	if ((rc = lb2_enqueue_reset(ctx, ctx->stream))) { return rc; }
+	LB2_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+	LB2_CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+	LB2_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));      // (the pack carry is one of the counters just reset)
+	LB2_CK(cudaStreamWaitEvent(ctx->wstream[0], ctx->ev_ready, 0)); LB2_CK(cudaStreamWaitEvent(ctx->wstream[1], ctx->ev_ready, 0));
+	uint64_t h2d = 0;
 #define LB2_PIECE(buf, ptr, esz, from, to) do { if ((to) > (from)) { LB2_CK(cudaMemcpyAsync((char *)ctx->buf.p + (size_t)(from) * (esz), (const char *)(ptr) + (size_t)(from) * (esz), \
-		(size_t)((to) - (from)) * (esz), cudaMemcpyHostToDevice, ctx->copy_stream)); } } while (0)
-	while (wa < W) {
-		uint32_t wb = wa + 1;
-		if (c + 2 >= LB2_MAX_MARKS) { wb = W; }
-		else { const uint64_t lim = up_by + chunk; while (wb < W && batch->base_off[ctx->h_need[wb]] <= lim) { ++wb; } }
-		const uint64_t rd_t = ctx->h_need[wb - 1];
-		const uint64_t to_by = up128(batch->base_off[rd_t] + 128, 1, nb), to_rd = up128(rd_t + 1, 1, R), to_bo = up128(rd_t + 2, 8, (uint64_t)R + 1);
-		const uint64_t to_wr = up128((uint64_t)batch->wr_off[wb] + 32, 4, n_wr), to_ref = up128((uint64_t)batch->ref_off[wb] + 128, 1, n_ref);
-		LB2_PIECE(d_ref_seq, batch->ref_seq, 1, up_ref, to_ref); if (to_ref > up_ref) { up_ref = to_ref; }
-		LB2_PIECE(d_wr_idx, batch->wr_idx, 4, up_wr, to_wr); if (to_wr > up_wr) { up_wr = to_wr; }
-		LB2_PIECE(d_base_off, batch->base_off, 8, up_bo, to_bo); if (to_bo > up_bo) { up_bo = to_bo; }
-		LB2_PIECE(d_flags, batch->flags, 1, up_rd, to_rd);
-		LB2_PIECE(d_name_rank, batch->name_rank, 4, up_rd, to_rd); if (to_rd > up_rd) { up_rd = to_rd; }
-		LB2_PIECE(d_seq, batch->seq, 1, up_by, to_by);
-		LB2_PIECE(d_qual, batch->qual, 1, up_by, to_by); if (to_by > up_by) { up_by = to_by; }
-		ctx->h_marks[c] = wb;
-		LB2_CK(cudaMemcpyAsync(ctx->d_avail, &ctx->h_marks[c], 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-		++c; wa = wb; chunk = std::min<uint64_t>(chunk_max, chunk * 2);
+		(size_t)((to) - (from)) * (esz), cudaMemcpyHostToDevice, ctx->copy_stream)); h2d += (uint64_t)((to) - (from)) * (esz); } } while (0)
+	LB2_PIECE(d_ref_off, batch->ref_off, 4, (size_t)0, (size_t)W + 1); LB2_PIECE(d_ref_start, batch->ref_start, 4, (size_t)0, (size_t)W); LB2_PIECE(d_wr_off, batch->wr_off, 4, (size_t)0, (size_t)W + 1);
+	for (size_t s = 0; s < segs.size(); ++s) {
+		const lb2_seg &sg = segs[s];
+		LB2_PIECE(d_ref_seq, batch->ref_seq, 1, (size_t)batch->ref_off[sg.w0], (size_t)batch->ref_off[sg.w1]);
+		LB2_PIECE(d_wr_idx, batch->wr_idx, 4, (size_t)batch->wr_off[sg.w0], (size_t)batch->wr_off[sg.w1]);
+		if (sg.r1 > sg.r0) {
+			LB2_PIECE(d_base_off, batch->base_off, 8, (size_t)sg.r0, (size_t)sg.r1 + 1);
+			LB2_PIECE(d_flags, batch->flags, 1, (size_t)sg.r0, (size_t)sg.r1); LB2_PIECE(d_name_rank, batch->name_rank, 4, (size_t)sg.r0, (size_t)sg.r1);
+			LB2_PIECE(d_seq, batch->seq, 1, (size_t)batch->base_off[sg.r0], (size_t)batch->base_off[sg.r1]);
+			LB2_PIECE(d_qual, batch->qual, 1, (size_t)batch->base_off[sg.r0], (size_t)batch->base_off[sg.r1]);
+			if ((rc = lb2_enqueue_pack(ctx, sg.r0, sg.r1, ctx->copy_stream))) { return rc; }
+		}
+		LB2_CK(cudaEventRecord(ctx->ev_seg[s], ctx->copy_stream));
+		cudaStream_t ws = ctx->wstream[s & 1];
+		LB2_CK(cudaStreamWaitEvent(ws, ctx->ev_seg[s], 0));
+		if ((rc = lb2_enqueue_windows(ctx, sg.w0, sg.w1, pinned ? (uint32_t)(s & 1) : 0u, (uint32_t)s, ws))) { return rc; }
 	}
 #undef LB2_PIECE
+	ctx->h2d_bytes = h2d;
+	for (int i = 0; i < 2; ++i) { LB2_CK(cudaEventRecord(ctx->ev_w[i], ctx->wstream[i])); LB2_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_w[i], 0)); }
+	LB2_CK(cudaEventRecord(ctx->ev[1], ctx->stream)); LB2_CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+	if (W) { if ((rc = lb2_enqueue_finish(ctx, ctx->stream, ctx->ev[3]))) { return rc; } } else { LB2_CK(cudaEventRecord(ctx->ev[3], ctx->stream)); }
+	LB2_CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+	ctx->ran = true; ctx->resident = true;
 	const auto t2 = std::chrono::steady_clock::now();
 	LB2_CK(cudaStreamSynchronize(ctx->copy_stream));      // the caller's buffers are free again when the call returns
-	{	// safety net: a window fetch that gave up on the watermark => the whole batch again, resident (it is by now)
-		uint32_t stalled = 0;
-		LB2_CK(cudaStreamSynchronize(ctx->stream));
-		LB2_CK(cudaMemcpy(&stalled, ctx->d_stalled, 4, cudaMemcpyDeviceToHost));
-		if (stalled) {
-			ctx->L.avail = nullptr;
-			LB2_CK(cudaMemcpyAsync(ctx->d_launch, &ctx->L, sizeof ctx->L, cudaMemcpyHostToDevice, ctx->stream));
-			rc = lb2_run(ctx); if (rc) { return rc; }
-		}
-	}
+	const auto t3 = std::chrono::steady_clock::now();
+	rc = lb2_download(ctx, result);
 	if (timing) {
-		const auto t3 = std::chrono::steady_clock::now(); rc = lb2_download(ctx, result); const auto t4 = std::chrono::steady_clock::now();
+		const auto t4 = std::chrono::steady_clock::now();
 		auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a).count(); };
-		fprintf(stderr, "lb2_process: tables+config %.2f ms, enqueue %.2f ms, pool copies done +%.2f ms, kernels+download +%.2f ms, total %.2f ms (kernels alone %.2f ms)\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t0, t4), (double)result->kernel_ms);
-		return rc;
+		fprintf(stderr, "lb2_process: %zu segment(s)%s, plan %.2f ms, enqueue %.2f ms, copies done +%.2f ms, kernels+download +%.2f ms, total %.2f ms (device span %.2f ms)\n",
+		        segs.size(), pinned ? "" : " (pageable)", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t0, t4), (double)result->kernel_ms);
 	}
-	return lb2_download(ctx, result);
+	return rc;
 }
 
-// debugging aid: cycles per pipeline phase (lane 0 of every CTA), summed since the context was created
+// cycles per pipeline phase (lane 0 of every CTA), summed since the context was created: zero unless built with -DLB2_PROFILE
 extern "C" int lb2_phase_cycles(lb2_ctx *ctx, unsigned long long *out24, int reset)
 {
 	if (!ctx || !out24) { return LB2_ERR_ARG; }
@@ -549,7 +626,14 @@ extern "C" uint64_t lb2_last_d2h_bytes(const lb2_ctx *ctx) { return ctx ? ctx->d
 extern "C" uint32_t lb2_resident_ctas(const lb2_ctx *ctx) { return ctx ? ctx->C.n_slots : 0; }
 extern "C" uint32_t lb2_smem_per_cta(const lb2_ctx *ctx) { return ctx ? ctx->C.smem_bytes : 0; }
 extern "C" int lb2_wait(lb2_ctx *ctx) { if (!ctx) return LB2_ERR_ARG; LB2_CK(cudaStreamSynchronize(ctx->stream)); return LB2_OK; }
-extern "C" float lb2_last_kernel_ms(lb2_ctx *ctx) { if (!ctx) return 0; float ms = 0; cudaEventSynchronize(ctx->ev1); cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); return ms; }
+extern "C" float lb2_last_kernel_ms(lb2_ctx *ctx) { if (!ctx || !ctx->ran) return 0; float ms = 0; cudaEventSynchronize(ctx->ev[4]); cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); return ms; }
+extern "C" float lb2_last_kernel_ms_of(lb2_ctx *ctx, int which)
+{
+	if (!ctx || !ctx->ran || which < 0 || which > 3) { return 0; }
+	float ms = 0; cudaEventSynchronize(ctx->ev[4]);
+	if (cudaEventElapsedTime(&ms, ctx->ev[which], ctx->ev[which + 1]) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return ms;
+}
 
 extern "C" void *lb2_alloc_pinned(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 extern "C" void lb2_free_pinned(void *p) { if (p) { cudaFreeHost(p); } }

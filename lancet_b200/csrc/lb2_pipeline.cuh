@@ -63,7 +63,9 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 {
 	lb2_sh *sh = W.sh; const lb2_params *P = W.P; const unsigned tid = lb2_tid();
 	if (tid == 0) {
+#ifdef LB2_PROFILE
 		for (int i = 0; i < 24; ++i) { sh->prof[i] = 0; } sh->t_last = lb2_clock();
+#endif
 		uint32_t slot = LB2_NIL;
 		if (W.escal && W.O->big_count) { slot = lb2g_add32(W.O->big_count, 1u); if (slot >= W.O->big_cap) { slot = LB2_NIL; } W.O->big_slot[w] = slot; }
 		sh->big = slot;
@@ -75,7 +77,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 	lb2_stage_window(W, w);
 	lb2_mark(W, LB2_PH_STAGE);
 	if (sh->status == LB2_WIN_OK) {
-		if (P->max_unit_len > 16 || P->max_k > (int32_t)W.C->max_k) { if (tid == 0) { sh->status = LB2_WIN_UNSUPPORTED; sh->detail = LB2_D_KMAX; } lb2_sync(); }
+		if (P->max_unit_len > 16 || P->max_k > (int32_t)W.C->max_k || P->max_mismatch > 3) { if (tid == 0) { sh->status = LB2_WIN_UNSUPPORTED; sh->detail = LB2_D_KMAX; } lb2_sync(); }
 	}
 	if (sh->status == LB2_WIN_OK) {
 		// one pass over the window reference answers isRepeat / isAlmostRepeat for every k
@@ -219,7 +221,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		wi.n_variants = (sh->status == LB2_WIN_OK) ? sh->n_var : 0; wi.n_nodes = sh->last_nodes; wi.detail = sh->detail;
 		W.O->info[w] = wi; W.O->str_used[w] = sh->str_used;
 		lb2_mark(W, LB2_PH_OTHER);
-#ifndef LB2_HOSTSIM
+#if defined(LB2_PROFILE) && !defined(LB2_HOSTSIM)
 		if (W.O->prof) { for (int i = 0; i < LB2_PH_N; ++i) { if (sh->prof[i]) { atomicAdd(&W.O->prof[i], sh->prof[i]); } } }
 #endif
 	}

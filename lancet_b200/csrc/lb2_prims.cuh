@@ -65,6 +65,9 @@ static inline uint32_t lb2_batch_next(uint32_t *ctr) { return (*ctr)++; }
 static inline uint32_t lb2_ballot(bool p) { return p ? 1u : 0u; }
 static inline void lb2_warp_sync() {}
 static inline uint32_t lb2_warp_max(uint32_t v) { return v; }
+static inline unsigned lb2_lane() { return 0; }
+static inline uint32_t lb2_shfl(uint32_t v, uint32_t) { return v; }
+static inline uint32_t lb2_shfl_up1(uint32_t v) { return v; }
 #define LB2_FQ 1      /* lanes per chain in the coverage fold of the parallel compaction (one per channel on the device) */
 static inline unsigned lb2_glane() { return 0; }
 static inline unsigned lb2_group() { return 0; }
@@ -74,6 +77,13 @@ static inline uint32_t lb2_gmax(uint32_t v) { return v; }
 static inline uint32_t lb2_gor(uint32_t v) { return v; }
 // 16 bytes from an arbitrarily aligned address (the device version reads whole aligned words around them)
 static inline void lb2_load16(const char *p, uint32_t o[4]) { memcpy(o, p, 16); }
+// ---- bulk-async staging (device: cp.async.bulk global -> shared, completion counted on an mbarrier; simulation: memcpy) ----
+typedef uint64_t lb2_mbar;
+static inline void lb2_mbar_init(lb2_mbar *, uint32_t) {}
+static inline void lb2_async_fence() {}
+static inline void lb2_bulk_g2s(void *dst, const void *src, uint32_t bytes, lb2_mbar *) { memcpy(dst, src, bytes); }
+static inline void lb2_mbar_arrive(lb2_mbar *) {}
+static inline void lb2_mbar_wait(lb2_mbar *, uint32_t) {}
 // per-byte compares: 0xFF in every byte lane where the predicate holds
 static inline uint32_t lb2_eq4(uint32_t w, uint32_t c4) { uint32_t r = 0; for (int b = 0; b < 4; ++b) { if (((w >> (8 * b)) & 0xFF) == ((c4 >> (8 * b)) & 0xFF)) { r |= 0xFFu << (8 * b); } } return r; }
 static inline uint32_t lb2_ltu4(uint32_t w, uint32_t c4) { uint32_t r = 0; for (int b = 0; b < 4; ++b) { if (((w >> (8 * b)) & 0xFF) < ((c4 >> (8 * b)) & 0xFF)) { r |= 0xFFu << (8 * b); } } return r; }
@@ -159,6 +169,9 @@ LB2_DEV uint32_t lb2_batch_next(uint32_t *ctr) {
 LB2_DEV uint32_t lb2_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 LB2_DEV void lb2_warp_sync() { __syncwarp(); }
 LB2_DEV uint32_t lb2_warp_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+LB2_DEV unsigned lb2_lane() { return threadIdx.x & 31u; }
+LB2_DEV uint32_t lb2_shfl(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, (int)src); }
+LB2_DEV uint32_t lb2_shfl_up1(uint32_t v) { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
 #define LB2_FQ 4      /* lanes per chain in the coverage fold of the parallel compaction: one per channel */
 LB2_DEV unsigned lb2_glane() { return threadIdx.x & 7u; }
 LB2_DEV unsigned lb2_group() { return threadIdx.x >> 3; }
@@ -171,6 +184,31 @@ LB2_DEV void lb2_load16(const char *p, uint32_t o[4]) {
 	const uint32_t *a = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3); const uint32_t sh = (uint32_t)((uintptr_t)p & 3u) * 8u;
 	const uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = __ldg(a + 3), w4 = __ldg(a + 4);
 	o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+}
+// ---- bulk-async staging: 1-D cp.async.bulk (the TMA engine's untiled copy) from global to this CTA's shared memory, 16-byte
+// aligned on both sides, size a multiple of 16.  Completion is counted in bytes on an mbarrier: every lane announces the
+// bytes of its own copies (expect_tx, no arrival), issues them, and arrives once when it has issued all of them; the phase
+// completes when all lanes have arrived and every announced byte has landed.  Data written by a bulk copy is visible to
+// ordinary loads of the lanes that observed the phase flip.
+typedef uint64_t lb2_mbar;
+LB2_DEV void lb2_mbar_init(lb2_mbar *b, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(lb2_saddr(b)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this lane's earlier ordinary shared-memory accesses before its later bulk copies (generic -> async proxy)
+LB2_DEV void lb2_async_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+LB2_DEV void lb2_bulk_g2s(void *dst, const void *src, uint32_t bytes, lb2_mbar *b) {
+	const uint32_t ba = lb2_saddr(b);
+	asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(ba), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(lb2_saddr(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(ba) : "memory");
+}
+LB2_DEV void lb2_mbar_arrive(lb2_mbar *b) { asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(lb2_saddr(b)) : "memory"); }
+LB2_DEV void lb2_mbar_wait(lb2_mbar *b, uint32_t parity) {
+	const uint32_t ba = lb2_saddr(b); uint32_t done = 0;
+	while (!done) {
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(ba), "r"(parity) : "memory");
+	}
 }
 LB2_DEV uint32_t lb2_eq4(uint32_t w, uint32_t c4) { return __vcmpeq4(w, c4); }
 LB2_DEV uint32_t lb2_ltu4(uint32_t w, uint32_t c4) { return __vcmpltu4(w, c4); }

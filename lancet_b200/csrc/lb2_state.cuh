@@ -3,6 +3,7 @@
 #define LB2_STATE_CUH
 
 #include "lb2_common.h"
+#include "lb2_pack.cuh"
 #include "lb2_kmer.cuh"
 
 #define LB2_NIL 0xFFFFFFFFu
@@ -51,7 +52,7 @@ struct lb2_ws {
 	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
 	lb2_bedge *b_edge; uint32_t *b_row;
 	// --- reads ---
-	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase; uint64_t *rd_src;      // rd_src: pool offset of the first kept base
+	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase; uint64_t *rd_src;      // rd_src: first word in the packed pool | words << 32
 	// --- graph stage, row space.  hot (shared memory): ---
 	uint32_t *d_lnext; uint32_t *d_bk; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
 	uint16_t *d_pos; uint32_t *px; uint32_t px_words;   // (packed-read words, dead in the graph stage) list index of every row; scratch of the parallel compaction
@@ -78,6 +79,7 @@ struct lb2_tev { uint16_t i, off; uint8_t m, j; uint16_t pad; };
 
 // shared (smem) scalars of one window
 struct lb2_sh {
+	lb2_mbar mbar; uint32_t mbar_phase, pad0;      // completion barrier of the bulk-async staging copies (first: 8-byte aligned)
 	// window
 	uint32_t w, R, L, total_bp, ref_g, has_lowq, lowq_live, bits_live, has_pairs, mapped, status, detail;
 	int32_t  ref_start;

@@ -13,6 +13,7 @@
 #include <vector>
 #include <algorithm>
 #include "../../lancet_b200/csrc/lb2_pipeline.cuh"
+#include "sim_pack.h"
 
 template <class T> static void rd(FILE *f, std::vector<T> &v, size_t n) { v.resize(n); if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 
@@ -110,10 +111,15 @@ int main(int argc, char **argv)
 	if (getenv("LB2_SIM_TS")) { C.table_slots = atoi(getenv("LB2_SIM_TS")); C.max_nodes = C.table_slots - C.table_slots / 4; }
 	if (getenv("LB2_SIM_BP")) { C.max_bp = atoi(getenv("LB2_SIM_BP")); }
 	if (getenv("LB2_SIM_GB")) { C.graph_bytes = atoi(getenv("LB2_SIM_GB")); }
+	if (getenv("LB2_SIM_QUEUE")) { C.queue_cap = atoi(getenv("LB2_SIM_QUEUE")); }
+	if (getenv("LB2_SIM_SPECIAL")) { C.max_special = atoi(getenv("LB2_SIM_SPECIAL")); }
+	if (getenv("LB2_SIM_ARENA")) { C.arena_bytes = atoi(getenv("LB2_SIM_ARENA")); }
+	if (getenv("LB2_SIM_INST")) { C.max_inst = atoi(getenv("LB2_SIM_INST")); }
 	if (getenv("LB2_SIM_MAXVAR")) { C.max_var = atoi(getenv("LB2_SIM_MAXVAR")); C.str_bytes = 128u << 10; }
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = ref_off.data(); B.ref_start = ref_start.data(); B.wr_off = wr_off.data(); B.wr_idx = wr_idx.data();
 	B.base_off = base_off.data(); B.flags = flags.data(); B.name_rank = name_rank.data(); B.ref_seq = ref_seq.data(); seq.resize(seq.size() + 64, 0); qual.resize(qual.size() + 64, 0);      /* the staging reads 16 bytes at a time (the device buffers have the same slack) */
 	B.seq = seq.data(); B.qual = qual.data();
+	SimPack sp; sim_pack(B, R, P, sp);
 	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
 	lb2_dev_out O; memset(&O, 0, sizeof O); O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);

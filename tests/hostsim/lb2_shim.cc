@@ -10,6 +10,7 @@
 #include <numeric>
 #include <algorithm>
 #include "../../lancet_b200/csrc/lb2_pipeline.cuh"
+#include "sim_pack.h"
 
 struct lb2_ctx { lb2_params P; std::vector<lb2_window_info> info; std::vector<lb2_variant> vars; std::vector<char> strs; };
 
@@ -38,6 +39,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *b, lb2_result *res)
 	lb2_dev_batch B; B.n_windows = W; B.ref_off = b->ref_off; B.ref_start = b->ref_start; B.wr_off = b->wr_off; B.wr_idx = b->wr_idx;
 	B.base_off = b->base_off; B.flags = b->flags; B.name_rank = b->name_rank; B.ref_seq = b->ref_seq; std::vector<char> pseq(b->seq, b->seq + b->n_base_bytes), pqual(b->qual, b->qual + b->n_base_bytes); pseq.resize(pseq.size() + 64, 0); pqual.resize(pqual.size() + 64, 0);
 	B.seq = pseq.data(); B.qual = pqual.data();
+	SimPack sp; sim_pack(B, b->n_reads, ctx->P, sp);
 	std::vector<lb2_window_info> info(W); std::vector<lb2_variant> vars((size_t)W * C.max_var); std::vector<char> strs((size_t)W * C.str_bytes); std::vector<uint32_t> sused(W);
 	lb2_dev_out O; memset(&O, 0, sizeof O); O.info = info.data(); O.variants = vars.data(); O.strings = strs.data(); O.str_used = sused.data();
 	size_t wsb = lb2_ws_layout(C, NULL, NULL);

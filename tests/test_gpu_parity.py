@@ -146,55 +146,33 @@ def _pinned(b):
 
 
 @pytest.mark.timeout(240, method="thread")
-def test_streamed_equals_resident(ctx, monkeypatch):
-    """From page-locked buffers lb2_process streams the read pool in chunks behind the running kernel (windows wait
-    for a watermark); lb2_upload + lb2_run + lb2_download work on a resident batch, and so does lb2_process from
-    pageable memory.  Same records every way, also with tiny chunks (many watermark updates) and with a permuted
-    window order (windows that need late reads come first)."""
+def test_segmented_equals_resident(ctx, monkeypatch):
+    """From page-locked buffers lb2_process uploads the batch in segments of consecutive windows and assembles a segment
+    while the next one is on its way (one launch per segment, two compute streams); lb2_upload + lb2_run +
+    lb2_download work on a resident batch, and so does lb2_process from pageable memory (one segment).  Same records
+    every way, also with many tiny segments and with a permuted window order (windows that need late reads come first)."""
     from lancet_b200.synth import make_batch
     b = make_batch(seed=52, region_len=30000, var_every=700)
     ctx.upload(b); ctx.run(); ctx.wait(); res0 = ctx.download(); rec0 = res0.records()
     assert len(rec0) > 20
-    assert ctx.process(b).records() == rec0                    # pageable: resident path
+    assert ctx.process(b).records() == rec0                    # pageable: one segment
     bp = _pinned(b)
-    for chunk in ("65536", "1048576", str(1 << 30)):
-        monkeypatch.setenv("LB2_STREAM_CHUNK", chunk)
+    for first, minw in (("65536", "8"), ("262144", "40"), ("1048576", "64"), (str(1 << 30), "768")):
+        monkeypatch.setenv("LB2_SEG_FIRST", first); monkeypatch.setenv("LB2_SEG_MIN_WINDOWS", minw)
         assert ctx.process(bp).records() == rec0
-    monkeypatch.setenv("LB2_STREAM_CHUNK", "65536")
+    monkeypatch.setenv("LB2_SEG_FIRST", "65536"); monkeypatch.setenv("LB2_SEG_MIN_WINDOWS", "16")
     perm = np.random.default_rng(1).permutation(b.n_windows)
     bq = b.subset(perm)
     ctx.upload(bq); ctx.run(); ctx.wait(); recp = ctx.download().records()
     assert ctx.process(_pinned(bq)).records() == recp
-
-
-_STALL_SCRIPT = r"""
-import sys, os, json
-sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
-from lancet_b200.api import Context
-from lancet_b200.synth import make_batch
-from test_gpu_parity import _pinned
-b = make_batch(seed=53, region_len=8000, var_every=600)
-c = Context(device=0)
-c.upload(b); c.run(); c.wait(); want = c.download().records()
-got = c.process(_pinned(b)).records()
-print(json.dumps({"same": got == want, "n": len(want)}))
-"""
-
-
-@pytest.mark.timeout(240, method="thread")
-def test_stream_timeout_safety_net():
-    """With launches made synchronous (CUDA_LAUNCH_BLOCKING=1) the streamed kernel would wait for copies that the host
-    has not issued yet.  Normally lb2_process detects that and stays resident; with the detection switched off the
-    window fetch must give up after its time-out and the host must redo the batch -- same records, no hang."""
-    import json
-    import subprocess
-    import sys
-    root = os.path.dirname(HERE)
-    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", LB2_STREAM_FORCE="1")
-    r = subprocess.run([sys.executable, "-c", _STALL_SCRIPT, root], capture_output=True, text=True, timeout=200, env=env)
-    assert r.returncode == 0, r.stderr[-2000:]
-    out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["same"] and out["n"] > 5
+    # a second context on the same device with another shared-memory configuration must not disturb the first one
+    from lancet_b200.api import Context
+    c2 = Context(device=0)
+    small = make_batch(seed=53, region_len=2000)
+    r_small = c2.process(small).records()
+    ctx.upload(b); ctx.run(); ctx.wait(); assert ctx.download().records() == rec0
+    assert c2.process(small).records() == r_small
+    c2.close()
 
 
 @pytest.mark.parametrize("mink,maxk", [(7, 9), (9, 15), (15, 17)])

@@ -23,5 +23,7 @@ for kw in cases:
         for r in [r for r in want if r[0] == w and r not in got][:3]: print("    want", r)
         for r in [r for r in got if r[0] == w and r not in want][:3]: print("    got ", r)
     st = res.windows["status"]
+    for w in [int(x) for x in (st >= 3).nonzero()[0][:12]]:
+        print("  not assembled: window", w, {k: int(res.windows[k][w]) for k in ("status", "final_k", "n_k_tried", "n_variants", "n_nodes", "detail")})
     print("  status counts", {int(s): int((st == s).sum()) for s in set(st.tolist())})
     c.close()

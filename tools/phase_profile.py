@@ -1,12 +1,16 @@
 """Per-phase cycle shares of the window pipeline (lane-0 clock64 marks), for a synthetic region."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as _g
+os.environ["LB2_SO"] = _g.build_profile()      # the instrumented build (the product library has no counters)
 from lancet_b200.api import Context
 from lancet_b200.synth import make_batch
 
 region = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 kw = json.loads(sys.argv[2]) if len(sys.argv) > 2 else {}
-b = make_batch(seed=1000, region_len=region, region_start=1_000_001, var_every=5000, **kw)
+kw = {**dict(seed=1000, region_start=1_000_001, var_every=5000), **kw}
+b = make_batch(region_len=region, **kw)
 ctx = Context()
 ctx.upload(b); ctx.run(); ctx.wait(); ctx.phase_cycles(reset=True)
 t0 = time.perf_counter(); ctx.run(); ctx.wait(); dt = time.perf_counter() - t0
