@@ -26,8 +26,6 @@ struct lb2_win {
 	lb2_variant *ovar; char *ostr; uint32_t ovar_cap, ostr_cap; bool escal;   // this window's output slab (regular or large)
 };
 
-LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2);
-
 // attribute the cycles since the previous mark to phase ph (lane 0 only).  Instrumentation: compiled in only with
 // -DLB2_PROFILE (tools/phase_profile.py builds that variant as lancet_b200/_lb2_prof.so); the product library has none of it
 #ifdef LB2_PROFILE
@@ -126,7 +124,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		sh->L = B->ref_off[w + 1] - B->ref_off[w];
 		sh->R = B->wr_off[w + 1] - B->wr_off[w];
 		sh->ref_start = B->ref_start[w];
-		sh->has_lowq = 0; sh->has_pairs = 0; sh->mapped = 0; sh->flag_a = 0; sh->flag_b = 0; sh->totalreadbp = 0;
+		sh->has_lowq = 0; sh->has_pairs = 0; sh->mapped = 0; sh->flag_a = 0; sh->flag_b = 0; sh->totalreadbp = 0; sh->ref_hasN = 0;
 		sh->n_var = 0; sh->str_used = 0; sh->n_k_tried = 0; sh->final_k = 0; sh->last_nodes = 0;
 		sh->err = 0;      // (a window whose every k is skipped never reaches lb2_build_graph, which resets it per k)
 		if (sh->L > LB2_MAX_REF) { sh->status = LB2_WIN_OVERFLOW; sh->detail = LB2_D_REFLEN; }
@@ -136,9 +134,11 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 	if (sh->status != LB2_WIN_OK) { return; }
 	const uint32_t L = sh->L, R = sh->R;
 	const char *ref = B->ref_seq + B->ref_off[w];
+	for (uint32_t i = tid; i < LB2_MAX_REF / 32 + 2; i += nt) { sh->refn[i] = 0; }
+	lb2_sync();
 	for (uint32_t i = tid; i < L; i += nt) {
 		char c = ref[i]; W.ref_raw[i] = c;
-		if (lb2_code(c) < 0) { lb2_or32(&sh->flag_a, 1u); }
+		if (lb2_code(c) < 0) { if (c == 'N') { lb2_or32(&sh->refn[i >> 5], 1u << (i & 31)); sh->ref_hasN = 1; } else { lb2_or32(&sh->flag_a, 1u); } }
 	}
 	const uint32_t *widx = B->wr_idx + B->wr_off[w];
 	const lb2_pkread *const PK = B->pk; const uint32_t *const NR_ = B->name_rank;
@@ -167,7 +167,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 		const uint32_t fl = sh->flag_b; sh->mapped = fl & 1u; sh->has_lowq = (fl & 4u) ? 1u : 0u; sh->flag_b = 0;
 		if (cum + 64 > W.C->max_bp) { lb2_fail(W, LB2_WIN_OVERFLOW, LB2_D_SMEM); }
 		if (fl & 2u) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_READS); }
-		if (sh->flag_a) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_NREF); }
+		if (sh->flag_a) { lb2_fail(W, LB2_WIN_UNSUPPORTED, LB2_D_NREF); }      // a reference character that is neither ACGT nor N (callers map IUPAC codes to N)
 		if (!(fl & 1u)) { lb2_fail(W, LB2_WIN_NO_READS, 0); }
 		sh->seq_off = 0; sh->seq_len = L; sh->trim5 = 0; sh->trim3 = 0;
 	}
@@ -440,25 +440,6 @@ template <class KT, bool isref> LB2_DEV void lb2_walk_small(lb2_win &W, bool act
 	if (pend && su != LB2_NIL) { const lb2_sp wp = lb2_sp_at(tidw, su >> 1); const uint32_t s4 = (su & 1u) << 4; if (((lb2s_ldv(wp) >> s4) & pend) != pend) { lb2s_or(wp, pend << s4); } }
 }
 
-// bitonic sort of a[0..n2) ascending, n2 a power of two
-LB2_DEVNI void lb2_sort64(uint64_t *a, uint32_t n2)
-{
-	const unsigned tid = lb2_tid(), nt = lb2_nthr();
-	for (uint32_t k = 2; k <= n2; k <<= 1) {
-		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t i = tid; i < n2; i += nt) {
-				uint32_t l = i ^ j;
-				if (l > i) {
-					uint64_t x = a[i], y = a[l];
-					bool up = ((i & k) == 0);
-					if ((x > y) == up) { a[i] = y; a[l] = x; }
-				}
-			}
-			lb2_sync();
-		}
-	}
-}
-
 // reverse complement: complement, reverse the 2-bit groups of the 256-bit integer, shift down to 2K bits
 LB2_DEV uint64_t lb2_rev2(uint64_t x) {
 #ifndef LB2_HOSTSIM
@@ -593,6 +574,17 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		if (transposed) { sh->inst_stride = Rs; sh->inst_ref = sh->maxnk * Rs; }
 		else { sh->inst_stride = 0; sh->inst_ref = cum; if (cum + L + 2 > C->max_inst) { sh->err |= 1u << LB2_D_READS; } }
 	}
+	if (tid == 0 && sh->ref_hasN) {
+		// the reference walk stops at N: its work items are pieces (<= walk_pl pairs, ob | oe << 16) of the N-free stretches
+		// that hold at least one k-mer; k-mers with an N get no table slot (they become dead map entries further down)
+		uint32_t ni = 0, a = 0; const uint32_t PL_ = sh->walk_pl;
+		for (uint32_t i = 0; i <= L; ++i) {
+			if (i < L && !((sh->refn[i >> 5] >> (i & 31)) & 1u)) { continue; }
+			if (i - a >= (uint32_t)K) { uint32_t ob = a; const uint32_t lastk = i - (uint32_t)K; while (true) { uint32_t oe = ob + PL_; if (oe > lastk) { oe = lastk; } ws.jobs[ni++] = ob | (oe << 16); if (oe == lastk) { break; } ob = oe; } }
+			a = i + 1;
+		}
+		sh->n_refitems = ni;
+	}
 	for (uint32_t i = tid; i < LB2_MAX_REF; i += nt) { ws.refnode[i] = LB2_NIL; }
 	for (uint32_t i = tid; i < TS; i += nt) { W.t_key[i] = 0; }
 	for (uint32_t i = tid; i < TS / 2; i += nt) { ((uint32_t *)W.t_id)[i] = 0; }
@@ -605,7 +597,8 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	// the warps finish together.  Item = piece * R + read: the lanes of a warp walk the same piece of consecutive reads
 	// (equal lengths, consecutive words of the offset-major occurrence array).
 	const uint32_t PL = sh->walk_pl, NP = sh->walk_np;
-	const uint32_t nchunks = (nref_pairs + PL - 1) / PL, nitems = NP * R + nchunks;
+	const bool refN = sh->ref_hasN != 0;
+	const uint32_t nchunks = refN ? sh->n_refitems : (nref_pairs + PL - 1) / PL, nitems = NP * R + nchunks;
 	while (true) {
 		const uint32_t it = lb2_batch_next(&sh->walk_next);
 		if (it >= ((nitems + 31u) & ~31u)) { break; }
@@ -619,7 +612,8 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				if (ob < np_) { active = true; g0 = ws.rd_start[r]; ib = sh->inst_stride ? r : ws.rd_kbase[r]; st = istr; cls = ws.rd_info[r] & 3u; }
 			}
 		} else if (it < nitems) {
-			ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
+			if (refN) { const uint32_t v = ws.jobs[it - NP * R]; ob = v & 0xFFFFu; oe = v >> 16; }
+			else { ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; } }
 			active = true; isref = true; g0 = sh->ref_g; n = L; ib = sh->inst_ref; st = 1u;
 		}
 		const bool hasreads = (it & ~31u) < NP * R, hasref = (it | 31u) >= NP * R;      // (the same for all lanes of the warp)
@@ -640,26 +634,78 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	// ---- compaction: dense ids in order of first occurrence = insertion order of the reference map.  The first
 	//      occurrences are distinct staged base indices, so the rank of a node is the number of set bits below its
 	//      index in a bitmap over the staged bases (one popcount scan instead of a sort).
-	const uint32_t n = sh->n_used;
+	// ---- reference k-mers that contain an N.  The reference is loaded as an untrimmed read (src/Graph.cc:534-540; isNseq
+	//      never fires, src/util.cc:259-273), so each distinct one is an entry of the reference's map: never covered by a
+	//      read, removed by the first low-coverage sweep, but present while the map grows -- it shifts the iteration order
+	//      of everything else.  Here: canonical form on the ASCII window (rrc('N') = 'N', 'G' < 'N' < 'T'), std::hash of
+	//      it, first occurrence of every distinct one; they join the dense nodes below as dead nodes without a table slot.
+	uint64_t *const nkh = (uint64_t *)ws.mates; uint8_t *const nkf = (uint8_t *)(nkh + LB2_MAX_REF);      // (the mate lists are idle until the replay)
+	if (tid == 0) { sh->n_nk = 0; }
+	if (refN) {
+		const char *const RR = W.ref_raw;
+		auto canon_at = [&](uint32_t o, uint32_t ori, uint32_t i) -> char { return ori ? lb2_comp(RR[o + (uint32_t)K - 1u - i]) : RR[o + i]; };
+		for (uint32_t o = tid; o + (uint32_t)K <= L; o += nt) {
+			bool hasn = false; for (uint32_t i = o; i < o + (uint32_t)K && !hasn; ++i) { hasn = ((sh->refn[i >> 5] >> (i & 31)) & 1u) != 0; }
+			uint8_t f = 0;
+			if (hasn) {
+				uint32_t ori = 1;      // CanonicalMer_t::set: F iff mer < rc2(mer) as strings (a palindrome is R)
+				for (int i = 0; i < K; ++i) { const char a = RR[o + i], b = lb2_comp(RR[o + K - 1 - i]); if (a != b) { ori = ((unsigned char)a < (unsigned char)b) ? 0u : 1u; break; } }
+				lb2_stdhash hs; lb2_sh_init(hs, (uint32_t)K);
+				for (int i = 0; i < K; ++i) { lb2_sh_byte(hs, (unsigned char)canon_at(o, ori, (uint32_t)i)); }
+				nkh[o] = lb2_sh_final(hs); f = (uint8_t)(1u | (ori << 1));
+			}
+			nkf[o] = f;
+		}
+		lb2_sync();
+		uint32_t mine = 0;
+		for (uint32_t o = tid; o + (uint32_t)K <= L; o += nt) {
+			const uint8_t f = nkf[o]; if (!(f & 1u)) { continue; }
+			bool first = true;
+			for (uint32_t p_ = 0; p_ < o && first; ++p_) {
+				const uint8_t fp_ = nkf[p_]; if (!(fp_ & 1u) || nkh[p_] != nkh[o]) { continue; }
+				bool same = true; for (int i = 0; i < K && same; ++i) { same = canon_at(o, (f >> 1) & 1u, (uint32_t)i) == canon_at(p_, (fp_ >> 1) & 1u, (uint32_t)i); }
+				if (same) { first = false; }
+			}
+			if (first) { nkf[o] = (uint8_t)(f | 4u); ++mine; }      // (bit 2 is only read after the barrier below)
+		}
+		if (mine) { lb2_add32(&sh->n_nk, mine); }
+		lb2_sync();
+		if (tid == 0 && (sh->n_used + sh->n_nk > C->max_nodes || sh->n_used + sh->n_nk >= 0x7FF0u)) { sh->err |= 1u << LB2_D_HASH_FULL; }
+		lb2_sync();
+		if (sh->err) { return; }
+	}
+	const uint32_t n_slots_used = sh->n_used, n = n_slots_used + sh->n_nk;
 	{
 		uint32_t *bm = (uint32_t *)ws.sortk; const uint32_t nwords = (sh->total_bp >> 5) + 2; uint32_t *pref = bm + nwords;
 		for (uint32_t i = tid; i < nwords; i += nt) { bm[i] = 0; }
 		lb2_sync();
-		for (uint32_t j = tid; j < n; j += nt) { const uint32_t g = (W.t_key[ws.used[j]] & 0x1FFFFFu) >> 1; lb2g_red_or(&bm[g >> 5], 1u << (g & 31)); }
+		for (uint32_t j = tid; j < n_slots_used; j += nt) { const uint32_t g = (W.t_key[ws.used[j]] & 0x1FFFFFu) >> 1; lb2g_red_or(&bm[g >> 5], 1u << (g & 31)); }
+		if (refN) { for (uint32_t o = tid; o + (uint32_t)K <= L; o += nt) { if (nkf[o] & 4u) { const uint32_t g = sh->ref_g + o; lb2g_red_or(&bm[g >> 5], 1u << (g & 31)); } } }
 		lb2_sync();
 		lb2_excl_scan(W, nwords, [&](uint32_t i) -> uint32_t { return (uint32_t)lb2_popc32(bm[i]); }, [&](uint32_t i, uint32_t v) { pref[i] = v; });
-		for (uint32_t j = tid; j < n; j += nt) {
+		for (uint32_t j = tid; j < n_slots_used; j += nt) {
 			const uint32_t s = ws.used[j]; const uint32_t g = (W.t_key[s] & 0x1FFFFFu) >> 1;
 			ws.b_row[pref[g >> 5] + (uint32_t)lb2_popc32(bm[g >> 5] & ((1u << (g & 31)) - 1u))] = s;      // b_row is free until lb2_order_and_pack
 		}
+		if (refN) {      // an N k-mer has no slot: its entry is 0x80000000 | reference offset
+			for (uint32_t o = tid; o + (uint32_t)K <= L; o += nt) {
+				if (nkf[o] & 4u) { const uint32_t g = sh->ref_g + o; ws.b_row[pref[g >> 5] + (uint32_t)lb2_popc32(bm[g >> 5] & ((1u << (g & 31)) - 1u))] = 0x80000000u | o; }
+			}
+		}
 		lb2_sync();
-		for (uint32_t j = tid; j < n; j += nt) { const uint32_t s = ws.b_row[j]; ws.used[j] = s; ws.g_em[j] = (((const uint32_t *)W.t_id)[s >> 1] >> ((s & 1u) << 4)) & 0xFFFFu; }   // used := dense id -> slot
+		for (uint32_t j = tid; j < n; j += nt) { const uint32_t s = ws.b_row[j]; ws.used[j] = s; ws.g_em[j] = (s & 0x80000000u) ? 0u : ((((const uint32_t *)W.t_id)[s >> 1] >> ((s & 1u) << 4)) & 0xFFFFu); }   // used := dense id -> slot
 		lb2_sync();
-		for (uint32_t j = tid; j < n; j += nt) { W.t_id[ws.used[j]] = (uint16_t)j; }      // slot -> dense id (the mask bits were saved above)
+		for (uint32_t j = tid; j < n; j += nt) { const uint32_t s = ws.used[j]; if (!(s & 0x80000000u)) { W.t_id[s] = (uint16_t)j; } }      // slot -> dense id (the mask bits were saved above)
 		lb2_sync();
 	}
 	for (uint32_t j = tid; j < n; j += nt) {
 		uint32_t s = ws.used[j];
+		if (s & 0x80000000u) {      // N k-mer: no coverage, no edges (dies in the first low-coverage sweep below)
+			ws.b_rep[j] = 0; ws.b_hash[j] = nkh[s & 0xFFFFu];
+			for (int c = 0; c < 4; ++c) { ws.b_cnt[j * 4 + c] = 0; }
+			ws.b_stT[j] = 0; ws.b_mincovqv[j] = 0; ws.b_flags[j] = 0; ws.b_ne[j] = 0;
+			continue;
+		}
 		uint32_t rep = W.t_key[s] & 0x1FFFFFu;
 		ws.b_rep[j] = rep;
 		lb2_kmer km;
@@ -684,19 +730,46 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	//      order (unsorted) at that time.  Queries of one read only look at lists fed by reads of
 	//      the other mate order, so per node it suffices to replay its occurrences in read order.
 	if (sh->has_pairs) {
+		// The occurrences of every node in read order: a counting sort by node.  Every warp owns a contiguous stretch of
+		// reads (about the same number of occurrences each), counts its occurrences per node, the per-(warp, node) counts
+		// are turned into first positions (node's start + the counts of the warps before), and the warp then walks its
+		// reads again, 32 consecutive occurrences at a time, handing out positions in order (lanes holding the same node
+		// rank themselves by lane number: __match_any).  occ[pos] = read-major occurrence number.
 		const uint32_t total = ws.rd_kbase[R];
-		uint32_t t2 = 1; while (t2 < total) { t2 <<= 1; }
-		for (uint32_t x = total + tid; x < t2; x += nt) { ws.sortk[x] = ~0ull; }
-		for (uint32_t r = tid; r < R; r += nt) {        // x = read-major occurrence number (the replay needs read order)
-			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
-			for (uint32_t o = 0; o < nk; ++o) { ws.sortk[kb + o] = ((uint64_t)W.t_id[ws.inst[ib + o * istr] & 0x3FFFu] << 32) | (kb + o); }
+		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
+		uint32_t *occ = (uint32_t *)ws.sortk, *wcnt = ws.bseq;      // (bseq: 8 words per node, idle until the edges are built)
+		const uint32_t NW = nt / LB2_WARP, wid = tid / LB2_WARP, lane = lb2_lane();
+		lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return ws.b_cnt[j * 4] + ws.b_cnt[j * 4 + 1] + ws.b_cnt[j * 4 + 2] + ws.b_cnt[j * 4 + 3]; },
+		              [&](uint32_t j, uint32_t v) { nstart[j] = v; });
+		if (NW > 8) { if (tid == 0) { sh->err |= 1u << LB2_D_READS; } }
+		for (uint32_t i = tid; i < NW * n && NW <= 8; i += nt) { wcnt[i] = 0; }
+		// this warp's reads: [ra, rb) with rd_kbase[ra] the first read start >= total * wid / NW
+		uint32_t ra, rb;
+		{
+			auto first_read = [&](uint32_t x) -> uint32_t { uint32_t lo = 0, hi = R; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ws.rd_kbase[mid] < x) { lo = mid + 1; } else { hi = mid; } } return lo; };
+			ra = first_read((uint32_t)((uint64_t)total * wid / NW)); rb = (wid + 1 == NW) ? R : first_read((uint32_t)((uint64_t)total * (wid + 1) / NW));
 		}
 		lb2_sync();
-		lb2_sort64(ws.sortk, t2);
-		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
-		for (uint32_t x = tid; x < total; x += nt) {
-			uint32_t nd = (uint32_t)(ws.sortk[x] >> 32);
-			if (x == 0 || (uint32_t)(ws.sortk[x - 1] >> 32) != nd) { nstart[nd] = x; }
+		if (sh->err) { return; }
+		for (uint32_t r = ra; r < rb; ++r) {
+			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
+			for (uint32_t o = lane; o < nk; o += LB2_WARP) { lb2g_red_add(&wcnt[wid * n + W.t_id[ws.inst[ib + o * istr] & 0x3FFFu]], 1u); }
+		}
+		lb2_sync();
+		for (uint32_t j = tid; j < n; j += nt) { uint32_t run = nstart[j]; for (uint32_t w = 0; w < NW; ++w) { const uint32_t c = wcnt[w * n + j]; wcnt[w * n + j] = run; run += c; } }
+		lb2_sync();
+		for (uint32_t r = ra; r < rb; ++r) {
+			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
+			for (uint32_t o0 = 0; o0 < nk; o0 += LB2_WARP) {
+				const uint32_t o = o0 + lane; const bool act = o < nk;
+				const uint32_t j = act ? (uint32_t)W.t_id[ws.inst[ib + o * istr] & 0x3FFFu] : 0xFFFFFFFFu;
+				const uint32_t same = lb2_match_any(j), leader = (uint32_t)lb2_ctz32(same), below = same & ((1u << lane) - 1u);
+				uint32_t pos = 0;
+				if (act && lane == leader) { pos = wcnt[wid * n + j]; wcnt[wid * n + j] = pos + (uint32_t)lb2_popc32(same); }
+				pos = lb2_shfl(pos, leader);
+				if (act) { occ[pos + (uint32_t)lb2_popc32(below)] = kb + o; }
+				lb2_warp_sync();
+			}
 		}
 		lb2_sync();
 		for (uint32_t j = tid; j < n; j += nt) {
@@ -706,7 +779,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			uint32_t *L1 = ws.mates + 2 * (size_t)b0; uint32_t *L2top = ws.mates + 2 * (size_t)b0 + 2 * (size_t)tot - 1;   // list 2 grows downwards
 			uint32_t n1 = 0, n2_ = 0;
 			for (uint32_t x = b0; x < b0 + tot; ++x) {
-				uint32_t s_ = (uint32_t)ws.sortk[x];
+				uint32_t s_ = occ[x];
 				uint32_t lo = 0, hi = R;                       // read of occurrence s_: last r with kbase[r] <= s_
 				while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (ws.rd_kbase[mid] <= s_) { lo = mid; } else { hi = mid; } }
 				uint32_t r = lo, p = s_ - ws.rd_kbase[r];
@@ -813,7 +886,8 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				if (ob >= n_ - K) { continue; }
 				g0 = ws.rd_start[r]; kb = ws.rd_kbase[r]; ks = sh->inst_stride ? r : kb; st = istr;
 			} else {
-				ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; }
+				if (refN) { const uint32_t v = ws.jobs[it - NP * R]; ob = v & 0xFFFFu; oe = v >> 16; }
+				else { ob = (it - NP * R) * PL; oe = ob + PL; if (oe > nref_pairs) { oe = nref_pairs; } }
 				g0 = sh->ref_g; kb = ws.rd_kbase[R]; ks = sh->inst_ref; st = 1u;
 			}
 			uint32_t iu = ws.inst[ks + ob * st];

@@ -400,7 +400,7 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 		C2.max_nodes = C2.table_slots - C2.table_slots / 4;
 		C2.smem_bytes = (uint32_t)lb2_smem_bytes(C2.max_bp, C2.table_slots, C2.graph_bytes);
 		C2.arena_bytes = env_u32("LB2_ARENA_BYTES2", 8u << 20); C2.deficit_bytes = env_u32("LB2_DEFICIT_BYTES2", 16u << 20);
-		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 22); C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20); C2.max_special = env_u32("LB2_MAX_SPECIAL2", 2048);
+		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 23);      /* DFS_LIMIT visits x a few children each */ C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20); C2.max_special = env_u32("LB2_MAX_SPECIAL2", 2048);
 		C2.n_slots = std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 1024));
 		const size_t stride2 = lb2_ws_layout(C2, nullptr, nullptr);
 		if (stride2 != ctx->ws2_stride || C2.n_slots > ctx->ws2_slots) {

@@ -45,8 +45,18 @@ LB2_DEV uint32_t lb2_mm16(const uint32_t *bits, uint32_t g0, uint32_t p, uint32_
 // queued stretch) applies the exact rule along its stretch.  The word before a stretch was skipped, hence holds
 // >= 2(max+1) mismatches: the mismatch history the stretch starts from is the top set bits of that word.
 struct lb2_wflags { uint32_t fw; bool sp; uint32_t c0, c3; };
-LB2_DEV lb2_wflags lb2_scan_word(const uint32_t *bits, uint32_t g0, int p0, int d, int np, uint32_t bias) {
+// 16 bits of a one-bit-per-position mask starting at position p, spread to the even bits of a word
+LB2_DEV uint32_t lb2_nbits16(const uint32_t *nm, uint32_t p) {
+	const uint32_t lo = nm[p >> 5], hi = nm[(p >> 5) + 1], sh = p & 31u;
+	uint32_t x = (sh ? ((lo >> sh) | (hi << (32u - sh))) : lo) & 0xFFFFu;
+	x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+	return x;
+}
+// nm (may be NULL): positions holding an 'N' (the window reference only).  'N' equals 'N' and differs from every base,
+// whatever 2-bit code the packed copy holds in its place.
+LB2_DEV lb2_wflags lb2_scan_word(const uint32_t *bits, uint32_t g0, int p0, int d, int np, uint32_t bias, const uint32_t *nm) {
 	lb2_wflags r; r.fw = lb2_mm16(bits, g0, (uint32_t)p0, (uint32_t)d);
+	if (nm) { const uint32_t na = lb2_nbits16(nm, (uint32_t)p0), nb = lb2_nbits16(nm, (uint32_t)(p0 + d)); r.fw = (r.fw & ~(na & nb)) | (na ^ nb); }
 	if (np - p0 < 16) { r.fw &= (1u << (2 * (np - p0))) - 1u; }
 	const uint32_t t = (r.fw & 0x11111111u) + ((r.fw >> 2) & 0x11111111u);
 	const uint32_t c = (t + (t >> 4)) & 0x0F0F0F0Fu;      // mismatches per 4-position block
@@ -55,7 +65,7 @@ LB2_DEV lb2_wflags lb2_scan_word(const uint32_t *bits, uint32_t g0, int p0, int 
 	r.c0 = c & 0xFFu; r.c3 = c >> 24;
 	return r;
 }
-LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int len, int maxmm)
+LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int len, int maxmm, const uint32_t *nm = nullptr)
 {
 	lb2_sh *sh = W.sh; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	uint32_t *tasks = (uint32_t *)W.ws0.sortk;      // (the build's sort keys: idle whenever a scan runs)
@@ -73,7 +83,7 @@ LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int 
 		if (!filter) { tasks[lb2_add32(&sh->walk_next, 1u)] = (uint32_t)d << 12; continue; }
 		uint32_t prev_c3 = 4; bool prev_sp = false, prev_slow = false;
 		for (int p0 = 0; p0 < np; p0 += 16) {
-			const lb2_wflags wf = lb2_scan_word(bits, g0, p0, d, np, bias);
+			const lb2_wflags wf = lb2_scan_word(bits, g0, p0, d, np, bias, nm);
 			const bool slow = wf.sp || prev_sp || (prev_c3 + wf.c0 <= (uint32_t)maxmm);
 			if (slow && !prev_slow) { tasks[lb2_add32(&sh->walk_next, 1u)] = ((uint32_t)d << 12) | (uint32_t)(p0 >> 4); }
 			prev_sp = wf.sp; prev_c3 = wf.c3; prev_slow = slow;
@@ -87,7 +97,7 @@ LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int 
 		int m1 = -1, m2 = -1, m3 = -1, m4 = -1;             // previous mismatch positions (virtual mismatch at -1)
 		uint32_t prev_c3 = 4; bool prev_sp = false;
 		if (p0 > 0) {      // history and block count of the skipped word before the stretch
-			const lb2_wflags pw = lb2_scan_word(bits, g0, p0 - 16, d, np, bias);
+			const lb2_wflags pw = lb2_scan_word(bits, g0, p0 - 16, d, np, bias, nm);
 			uint32_t x = pw.fw; const int pb = p0 - 16; prev_c3 = pw.c3;
 			if (x) { int b = 31 - lb2_clz32(x); m1 = pb + (b >> 1); x &= ~(1u << b); }
 			if (x) { int b = 31 - lb2_clz32(x); m2 = pb + (b >> 1); x &= ~(1u << b); }
@@ -96,7 +106,7 @@ LB2_DEVNI void lb2_diag_scan(lb2_win &W, const uint32_t *bits, uint32_t g0, int 
 		}
 		bool at_end = false;
 		for (; p0 < np; p0 += 16) {
-			const lb2_wflags wf = lb2_scan_word(bits, g0, p0, d, np, bias);
+			const lb2_wflags wf = lb2_scan_word(bits, g0, p0, d, np, bias, nm);
 			if (filter && !(wf.sp || prev_sp || (prev_c3 + wf.c0 <= (uint32_t)maxmm))) { break; }      // the stretch ends here
 			prev_sp = wf.sp; prev_c3 = wf.c3;
 			uint32_t fw = wf.fw;
@@ -134,49 +144,73 @@ LB2_DEVNI void lb2_pack_path(lb2_win &W, uint32_t *dst)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// bfs: best = first complete path (dequeue order) with the most not-yet-flagged edges
+// bfs (src/Graph.cc:1299-1425): best = first complete path (dequeue order) with the most not-yet-flagged edges.
+// By all lanes: the FIFO queue is expanded a CTA-width of entries at a time.  Lane i takes the i-th unvisited entry,
+// counts the children it will push, an exclusive scan over the lanes places every entry's children behind those of the
+// entries before it -- the order the reference's one-at-a-time loop pushes them in -- and the visit limit (DFS_LIMIT:
+// the reference stops at its (limit+1)-th dequeue) becomes "entries with index >= limit are never expanded".  Every lane
+// keeps the first best candidate among its own (increasing) indices; the winner is the highest score, lowest index.
+// Returns the queue index of the best complete path or LB2_NIL, the same value in every lane.
 // ---------------------------------------------------------------------------------------------------
 LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 {
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	const uint32_t cap = W.C->queue_cap;
 	// the head of the queue lives in the idle shared-memory scratch (most searches never leave it), the rest in the slab
 	lb2_qent *const Qs = (lb2_qent *)ws.px, *const Qg = ws.queue; const uint32_t qs = (uint32_t)(((size_t)ws.px_words * 4) / sizeof(lb2_qent));
-	if (lb2_tid() == 0) { W.sh->q_smem = qs; }
 #define Q_AT(i) ((i) < qs ? Qs[(i)] : Qg[(i)])
 	const int reflen = (int)sh->seq_len;
-	uint32_t qh = 0, qt = 0; int visit = 0; uint32_t best = LB2_NIL; int bestscore = 0;
-	lb2_qent root; root.parent = LB2_NIL; root.node = sh->source; root.len = K; root.score = 0; root.eidx = 0; root.dirflag = 2;   // dir F, flag 1
-	Q_AT(qt) = root; ++qt;
-	// (array bases and scalars in registers: the descriptor lives in shared memory and would be re-read behind every store)
 	const uint8_t *const NE = ws.d_ne, *const FL = ws.d_flags, *const EOV = ws.d_eov; const lb2_edge *const ED = ws.d_edge, *const EP = ws.e_pool;
-	const uint16_t *const LEN = ws.d_len; const uint32_t sink = sh->sink; const int dfs_limit = W.P->dfs_limit, maxlen = reflen + W.P->max_indel_len;
-	while (qh < qt) {
-		++visit;
-		if (dfs_limit && visit > dfs_limit) { break; }
-		uint32_t idx = qh++; lb2_qent e = Q_AT(idx);
-		uint32_t cur = e.node; int pdir = e.dirflag & 1; int pflag = (e.dirflag >> 1) & 1;
-		if (cur == sink && pflag == 0) {
-			if (best == LB2_NIL || (int)e.score > bestscore) { best = idx; bestscore = e.score; }
-		} else if (e.len > maxlen) {
-		} else {
-			const uint32_t ov = EOV[cur]; const lb2_edge *ed = ov ? (EP + (size_t)(ov - 1) * LB2_ECAP) : (ED + (size_t)cur * LB2_EINL); const int ne = NE[cur];
+	const uint16_t *const LEN = ws.d_len; const uint32_t sink = sh->sink; const int maxlen = reflen + W.P->max_indel_len;
+	const uint32_t limit = W.P->dfs_limit ? (uint32_t)W.P->dfs_limit : 0xFFFFFFFFu;
+	if (tid == 0) {
+		sh->q_smem = qs; sh->bfs_score = 0; sh->bfs_best = LB2_NIL;
+		lb2_qent root; root.parent = LB2_NIL; root.node = sh->source; root.len = K; root.score = 0; root.eidx = 0; root.dirflag = 2;   // dir F, flag 1
+		Q_AT(0) = root;
+	}
+	lb2_sync();
+	uint32_t qh = 0, qt = 1, my_best = LB2_NIL; int my_score = -1;      // (qh, qt: the same in every lane)
+	while (qh < qt && qh < limit) {
+		const uint32_t end = qt < limit ? qt : limit, idx = qh + tid;
+		lb2_qent e; e.parent = 0; e.node = 0; e.len = 0; e.score = 0; e.eidx = 0; e.dirflag = 0;
+		const lb2_edge *ed = nullptr; int ne = 0, pdir = 0, pflag = 0; uint32_t nchild = 0;
+		if (idx < end) {
+			e = Q_AT(idx); const uint32_t cur = e.node; pdir = e.dirflag & 1; pflag = (e.dirflag >> 1) & 1;
+			if (cur == sink && pflag == 0) { if ((int)e.score > my_score) { my_best = idx; my_score = (int)e.score; } }
+			else if (e.len > maxlen) { }
+			else {
+				const uint32_t ov = EOV[cur]; ed = ov ? (EP + (size_t)(ov - 1) * LB2_ECAP) : (ED + (size_t)cur * LB2_EINL); ne = NE[cur];
+				for (int i = 0; i < ne; ++i) { if (lb2_is_dir(ed[i].dir, pdir)) { ++nchild; } }
+			}
+		}
+		uint32_t total = 0; const uint32_t off = lb2_block_excl(sh->scan, nchild, &total);
+		if (total > cap - qt) { if (tid == 0) { sh->err |= 1u << LB2_D_QUEUE; } lb2_sync(); return LB2_NIL; }
+		if (nchild) {
+			uint32_t o = qt + off;
 			for (int i = 0; i < ne; ++i) {
 				const lb2_edge ei = ed[i];
 				if (!lb2_is_dir(ei.dir, pdir)) { continue; }
-				uint32_t other = ei.to;
-				if (qt >= cap) { sh->err |= 1u << LB2_D_QUEUE; return LB2_NIL; }
+				const uint32_t other = ei.to;
 				lb2_qent c; c.parent = idx; c.node = other; c.eidx = (uint8_t)i;
 				c.len = e.len + (int)((FL[other] & LB2_NF_SPECIAL) ? 0u : (uint32_t)LEN[other]) - K + 1;
-				int nflag = pflag * (int)ei.flag;
+				const int nflag = pflag * (int)ei.flag;
 				c.score = (uint16_t)(e.score + (ei.flag == 0 ? 1 : 0));
 				c.dirflag = (uint8_t)(lb2_dir_dest(ei.dir) | (nflag << 1));
-				Q_AT(qt) = c; ++qt;
+				Q_AT(o) = c; ++o;
 			}
 		}
+		lb2_sync();
+		qh = (end - qh > nt) ? qh + nt : end; qt += total;
 	}
-	return best;
 #undef Q_AT
+	const uint32_t key = (my_best == LB2_NIL) ? 0u : (uint32_t)my_score + 1u;
+	if (key) { lb2_max32(&sh->bfs_score, key); }
+	lb2_sync();
+	if (key && key == sh->bfs_score) { lb2_min32(&sh->bfs_best, my_best); }
+	lb2_sync();
+	const uint32_t best = sh->bfs_best;
+	lb2_sync();
+	return best;
 }
 
 // materialise the chosen path: node list, string, per-base tumour/normal coverage

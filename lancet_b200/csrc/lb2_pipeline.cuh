@@ -81,7 +81,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 	}
 	if (sh->status == LB2_WIN_OK) {
 		// one pass over the window reference answers isRepeat / isAlmostRepeat for every k
-		lb2_diag_scan(W, W.bits, sh->ref_g, (int)sh->L, P->max_mismatch);
+		lb2_diag_scan(W, W.bits, sh->ref_g, (int)sh->L, P->max_mismatch, sh->ref_hasN ? sh->refn : nullptr);
 		if (tid == 0) {
 			sh->ref_emax = sh->scan_emax; sh->ref_wmax = sh->scan_wmax;
 			// window pre-skip: isRepeat(rawseq, maxK)  (src/Microassembler.cc:800)
@@ -154,11 +154,13 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				bool rpt = false; uint32_t nflag = 0;
 				while (true) {
 					if (nflag > 8 * LB2_MAX_ROWS) { if (tid == 0) { sh->err |= 1u << LB2_D_STACK; } lb2_sync(); break; }   // every round flags >= 1 new edge
-					if (tid == 0) {
-						uint32_t best = lb2_bfs(W);
-						sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
-						if (sh->path_found) { lb2_load_path(W, best); }
-						lb2_mark(W, LB2_PH_BFS_SEQ);
+					{
+						const uint32_t best = lb2_bfs(W);
+						if (tid == 0) {
+							sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
+							if (sh->path_found) { lb2_load_path(W, best); }
+							lb2_mark(W, LB2_PH_BFS_SEQ);
+						}
 					}
 					lb2_sync();
 					if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }
@@ -193,11 +195,13 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 					if (round > 8 * LB2_MAX_ROWS) { if (tid == 0) { sh->err |= 1u << LB2_D_STACK; } lb2_sync(); break; }
 					if (single) { if (round == 1) { break; } }
 					else {
-						if (tid == 0) {
-							uint32_t best = lb2_bfs(W);
-							sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
-							if (sh->path_found) { lb2_load_path(W, best); }
-							lb2_mark(W, LB2_PH_BFS_SEQ);
+						{
+							const uint32_t best = lb2_bfs(W);
+							if (tid == 0) {
+								sh->path_found = (best != LB2_NIL && !sh->err) ? 1u : 0u;
+								if (sh->path_found) { lb2_load_path(W, best); }
+								lb2_mark(W, LB2_PH_BFS_SEQ);
+							}
 						}
 						lb2_sync();
 						if (sh->err || !sh->path_found) { lb2_mark(W, LB2_PH_BFS); break; }

@@ -66,6 +66,7 @@ static inline uint32_t lb2_ballot(bool p) { return p ? 1u : 0u; }
 static inline void lb2_warp_sync() {}
 static inline uint32_t lb2_warp_max(uint32_t v) { return v; }
 static inline unsigned lb2_lane() { return 0; }
+static inline uint32_t lb2_match_any(uint32_t) { return 1u; }      // lanes of the warp holding the same value
 static inline uint32_t lb2_shfl(uint32_t v, uint32_t) { return v; }
 static inline uint32_t lb2_shfl_up1(uint32_t v) { return v; }
 #define LB2_FQ 1      /* lanes per chain in the coverage fold of the parallel compaction (one per channel on the device) */
@@ -170,6 +171,7 @@ LB2_DEV uint32_t lb2_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 LB2_DEV void lb2_warp_sync() { __syncwarp(); }
 LB2_DEV uint32_t lb2_warp_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 LB2_DEV unsigned lb2_lane() { return threadIdx.x & 31u; }
+LB2_DEV uint32_t lb2_match_any(uint32_t v) { return __match_any_sync(0xFFFFFFFFu, v); }      // lanes of the warp holding the same value
 LB2_DEV uint32_t lb2_shfl(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, (int)src); }
 LB2_DEV uint32_t lb2_shfl_up1(uint32_t v) { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
 #define LB2_FQ 4      /* lanes per chain in the coverage fold of the parallel compaction: one per channel */

@@ -96,13 +96,17 @@ struct lb2_sh {
 	uint32_t source, sink, anc_src, anc_snk, anc_amb, spec_cap;
 	uint32_t arena_used, tstr_used;
 	// path
-	uint32_t plen, pn, need_align, n_trans, path_found, aln_len, q_smem;
+	uint32_t plen, pn, need_align, n_trans, path_found, aln_len, q_smem, bfs_score, bfs_best;
 	// output
 	uint32_t n_var, str_used, n_k_tried, final_k, last_nodes;
 	int32_t  numcomp;
 	uint32_t stop_k; uint32_t n_dead; uint32_t big; uint32_t n_changed;      // n_changed: nodes removed by the sweeps since the first compaction
 	uint32_t maxnk, inst_stride, inst_ref;     // occurrence array layout of this (window,k): see lb2_build.cuh
 	uint32_t walk_next, walk_pl, walk_np;      // k-mer walk: work-item counter, pairs per piece, pieces per read
+	// non-ACGT ('N') bases of the window reference: one bit per base (two readable words past the end), the N-free work
+	// items of the reference walk, the map entries its N-containing k-mers become (src/Graph.cc:534-540: the reference is
+	// loaded untrimmed)
+	uint32_t ref_hasN, n_refitems, n_nk; uint32_t refn[LB2_MAX_REF / 32 + 2];
 	uint32_t n_tev, tev_ovf; lb2_tev tev[LB2_MAX_TEV];     // tandem repeats of the loaded path (n_tev = LB2_NIL: not computed, scan per variant)
 	unsigned long long prof[24]; unsigned long long t_last;
 	uint32_t scan[520];           // block-scan partials (<= 512 lanes)

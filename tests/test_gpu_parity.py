@@ -243,3 +243,45 @@ def test_many_records_per_window(ctx):
     assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
     assert res.records() == want
     c.close()
+
+
+def _with_n_runs(b, seed):
+    """window references with runs of N, N at both ends, periodic N (many distinct N k-mers, short N-free stretches), all N"""
+    from lancet_b200.batch import Batch
+    rng = np.random.default_rng(seed); ref = b.ref_seq.copy()
+    for w in range(b.n_windows):
+        o0, o1 = int(b.ref_off[w]), int(b.ref_off[w + 1]); L = o1 - o0
+        u = rng.random()
+        if u < 0.3:
+            a = int(rng.integers(0, L - 40)); ref[o0 + a:o0 + a + int(rng.integers(2, 40))] = ord("N")
+        elif u < 0.5:
+            ref[o0:o0 + int(rng.integers(1, 20))] = ord("N"); ref[o1 - int(rng.integers(1, 20)):o1] = ord("N")
+        elif u < 0.6:
+            ref[o0 + int(rng.integers(0, 15)):o1:int(rng.integers(12, 30))] = ord("N")
+        elif u < 0.65:
+            ref[o0:o1] = ord("N")
+    return Batch(ref_off=b.ref_off, ref_start=b.ref_start, chr_id=b.chr_id, wr_off=b.wr_off, wr_idx=b.wr_idx, base_off=b.base_off,
+                 flags=b.flags, name_rank=b.name_rank, ref_seq=ref, seq=b.seq, qual=b.qual)
+
+
+@pytest.mark.parametrize("case,mink", [("single", 11), ("dense", 11), ("runs", 11), ("runs", 31), ("runs_err", 11), ("runs_str", 63)])
+def test_reference_with_n(case, mink):
+    """A window reference with non-ACGT bases: the reference loads it untrimmed (src/Graph.cc:534-540), its N-containing
+    k-mers become map entries that die in the first low-coverage sweep but shift the iteration order of everything else,
+    'N' columns come out as SNV records.  Assembled on the device like any other window."""
+    import run_ref
+    if not run_ref.available():
+        pytest.skip("oracle/_ref/ref_windows not built")
+    from lancet_b200.synth import make_batch
+    b = {"single": lambda: make_batch(seed=201, region_len=4000, n_in_ref=12),
+         "dense": lambda: make_batch(seed=202, region_len=4000, n_in_ref=40, var_every=300),
+         "runs": lambda: _with_n_runs(make_batch(seed=203, region_len=5000, var_every=300), 1),
+         "runs_err": lambda: _with_n_runs(make_batch(seed=204, region_len=4000, err=0.004), 2),
+         "runs_str": lambda: _with_n_runs(make_batch(seed=205, region_len=4000, str_every=300), 3)}[case]()
+    want, _ = run_ref.run(b, threads=8, min_k=mink)
+    c = _ctx(min_k=mink)
+    res = c.process(b)
+    assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
+    assert res.records() == want
+    assert any("N" in r[4] for r in want) or case == "runs_str"
+    c.close()
