@@ -11,8 +11,11 @@ tumour/normal, 100 bp reads, default k-sweep 11..101) -> ~10 000 windows of 600 
   --impl reference : the reference's own CPU implementation (oracle/_ref/ref_windows = unmodified
                      nygenome/lancet sources behind the same window-batch boundary), all host threads
 
-N > 1: one process per GPU (torchrun), windows are independent => no data-path collective; every rank
-assembles its own 1 Mb region (weak scaling); timing = max over ranks.
+N > 1: one process per GPU (torchrun), ONE workload of N Mb (N regions of 1 Mb laid end to end) sharded by contiguous
+window ranges: rank r assembles the windows of Mb r (weak scaling: fixed work per GPU).  Windows are independent, so
+there is no collective on the per-window path; the one exchange is the gather of the variant records on rank 0 over
+NCCL (C ABI lb2_comm_gather: ncclAllGather of counts, ncclSend/ncclRecv of the payloads), timed inside `e2e`.
+Timing = max over ranks.
 """
 import argparse
 import json
@@ -76,6 +79,43 @@ def peak_hbm():
     return 6650.0, "fallback"
 
 
+def bam_vcf_leg(cores: int, device: int):
+    """BAM -> VCF wall time of the two command lines on the same synthetic BAM pair: the unmodified reference
+    CLI (oracle/_ref/lancet --num-threads <cores>) and lancet_b200_cli (BAI region fetch, multi-threaded inflate/decode,
+    batches through lb2_process), second of two runs each (warm page cache), VCFs compared byte for byte."""
+    import shutil
+    import tempfile
+    from lancet_b200 import simbam
+    refcli = os.path.join(ROOT, "oracle", "_ref", "lancet"); cli = os.path.join(ROOT, "lancet_b200", "lancet_b200_cli")
+    if not (os.path.exists(refcli) and os.path.exists(cli) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "test_view"))):
+        return {"unavailable": "needs oracle/_ref/{lancet,test_view} and lancet_b200/lancet_b200_cli"}
+    region = int(os.environ.get("LB2_BAM_REGION", 100_000))
+    td = tempfile.mkdtemp(prefix="lb2_bamvcf_")
+    try:
+        d = simbam.write_dataset(td, seed=500, chroms=(("chr22", region),), var_every=700, som_every=1500)
+        base = ["--tumor", d["tumor"], "--normal", d["normal"], "--ref", d["ref"], "--reg", f"chr22:1-{region}", "--num-threads", str(cores)]
+
+        def run(cmd):
+            best, out = None, None
+            for _ in range(2):
+                t0 = time.perf_counter(); r = subprocess.run(cmd, capture_output=True, text=True, timeout=900); dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return None, r.stderr[-400:]
+                best, out = dt, r.stdout
+            return best, out
+        t_ref, v_ref = run([refcli] + base)
+        t_our, v_our = run([cli] + base + ["--gpu", str(device)])
+        if t_ref is None or t_our is None:
+            return {"error": (v_ref if t_ref is None else v_our)}
+        same = simbam.normalise_vcf(v_ref) == simbam.normalise_vcf(v_our)
+        nwin = len(range(0, region, 100))
+        return {"region_bp": region, "windows": nwin, "records": sum(1 for l in v_ref.splitlines() if not l.startswith("#")),
+                "reference_s": t_ref, "reference_threads": cores, "ours_s": t_our, "speedup": t_ref / t_our, "vcf_identical": same,
+                "windows_per_s_reference": nwin / t_ref, "windows_per_s_ours": nwin / t_our}
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
 def reference_arm(args, rank):
     """CPU reference: unmodified lancet sources (oracle/_ref/ref_windows), all host threads, bounded sample."""
     if rank != 0:
@@ -135,6 +175,10 @@ def main():
         v = t.numpy()[:a.nbytes].view(a.dtype); v[...] = a
         setattr(batch, name, v); batch.__dict__.setdefault("_pins", []).append(t)
     ctx = Context(device=local)
+    if world > 1:
+        from lancet_b200.shard import init_comm
+        init_comm(ctx, device=torch.device("cuda", local))
+    win_offset = rank * batch.n_windows      # this rank's share of the one N Mb workload (every Mb tiles into the same number of windows)
 
     def barrier():
         if world > 1:
@@ -162,12 +206,18 @@ def main():
     launches = ctx.kernel_launches - launches0
     ms_step = dev_ms / args.steps
     # ---- end-to-end leg: host buffers -> H2D -> kernels -> D2H, through lb2_process ---------------
+    gathered = 0
     for _ in range(1):
-        ctx.process(batch)
+        r = ctx.process(batch)
+        if world > 1:
+            ctx.comm_gather(r.variants, r.strings, window_offset=win_offset)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = ctx.process(batch)
+        if world > 1:      # the exchange step of the sharded path: every rank's records to rank 0
+            gv, gs, _st = ctx.comm_gather(r.variants, r.strings, window_offset=win_offset)
+            gathered = len(gv) if gv is not None else 0
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     h2d, d2h = ctx.last_h2d_bytes, ctx.last_d2h_bytes
@@ -205,7 +255,9 @@ def main():
             "dtype": "u8/int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "windows_per_gpu": batch.n_windows, "reads_per_gpu": batch.n_reads,
                        "windows_ok": n_ok_all, "windows_failed": n_fail_all, "variant_records": n_var_all,
-                       "l2": f"inputs ({(batch.seq.nbytes * 2) >> 20} MiB per step) larger than L2", "parallelism": f"window-sharded x{world}, no collective",
+                       "l2": f"inputs ({(batch.seq.nbytes * 2) >> 20} MiB per step) larger than L2",
+                       "parallelism": (f"one {world} Mb workload window-sharded x{world} (rank r = Mb r); no collective per window; records gathered on rank 0 by NCCL "
+                                       f"(ncclAllGather counts + ncclSend/ncclRecv payloads) inside e2e: {gathered} records per step") if world > 1 else "1 GPU",
                        "resident_ctas": ctx.resident_ctas, "smem_per_cta": ctx.smem_per_cta, "wall_ms_per_step": wall_ms},
             "e2e": {"value": total_windows / (e2e_ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
@@ -230,6 +282,11 @@ def main():
                                        "sample": f"first {count} of {batch.n_windows} windows, {cores} threads, {t['best_s']:.1f} s"}
             else:
                 out["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref not built"}
+            if os.environ.get("LB2_SKIP_BAM_VCF") is None:
+                try:
+                    out["e2e_bam_vcf"] = bam_vcf_leg(cores, local)
+                except Exception as e:      # the headline line must not depend on this leg
+                    out["e2e_bam_vcf"] = {"error": repr(e)[:300]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -181,6 +181,20 @@ int      lb2_phase_cycles(lb2_ctx *ctx, unsigned long long *out24, int reset);
 /* build identity of the kernels: bench.py refuses profile-derived numbers recorded for another version */
 const char *lb2_kernel_version(void);
 
+/* ---- several GPUs: one process per GPU, windows are independent, the only exchange is the gather of the variant records on
+ * one rank (reference: the per-thread VariantDB_t are merged serially in thread order, src/Lancet.cc:943-959).  NCCL:
+ * counts by ncclAllGather, payloads by ncclSend/ncclRecv to `root`.
+ *   lb2_comm_unique_id : rank 0 creates the id and hands it to the other ranks by any means (a file, MPI, ...)
+ *   lb2_comm_init      : every rank, after lb2_create, with the same id
+ *   lb2_comm_gather    : every rank passes its own records (window = caller's global window index, str_off into strs) and
+ *                        n_stats <= 8 counters; on root `merged` holds all ranks' records in rank order (string offsets
+ *                        rebased; memory owned by the context) and stats[] the sums over ranks; other ranks get n_variants = 0 */
+#define LB2_COMM_ID_BYTES 128
+int lb2_comm_unique_id(char id_out[LB2_COMM_ID_BYTES]);
+int lb2_comm_init(lb2_ctx *ctx, const char id[LB2_COMM_ID_BYTES], int rank, int world);
+int lb2_comm_gather(lb2_ctx *ctx, const lb2_variant *vars, uint32_t n_vars, const char *strs, uint64_t n_str_bytes,
+                    uint64_t *stats, int n_stats, int root, lb2_result *merged);
+
 /* helper: order-preserving ranks for n NUL-terminated query names (host side, std::sort) */
 int lb2_rank_names(const char *const *names, uint32_t n, uint32_t *rank_out);
 

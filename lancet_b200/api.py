@@ -82,6 +82,22 @@ _lib.lb2_kernel_version.restype = ctypes.c_char_p
 KERNEL_VERSION = _lib.lb2_kernel_version().decode()
 
 
+_lib.lb2_comm_unique_id.argtypes = [ctypes.c_char_p]
+_lib.lb2_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+_lib.lb2_comm_gather.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64,
+                                 ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Result)]
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """NCCL id for Context.comm_init (created on one rank, handed to the others by any means)"""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    rc = _lib.lb2_comm_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"lb2_comm_unique_id failed ({rc}): no GPU or no NCCL")
+    return buf.raw
+
+
 class Result:
     """Host copy of an lb2_result."""
 
@@ -150,6 +166,24 @@ class Context:
         r = _Result()
         self._ck(_lib.lb2_download(self._h, ctypes.byref(r)))
         return Result(r)
+
+    # ---- several GPUs, one process each: the record gather on one rank over NCCL (include/lancet_b200.h) ----
+    def comm_init(self, comm_id: bytes, rank: int, world: int) -> None:
+        self._ck(_lib.lb2_comm_init(self._h, comm_id, rank, world))
+        self.rank, self.world = rank, world
+
+    def comm_gather(self, variants: np.ndarray, strings: bytes, window_offset: int = 0, stats=(), root: int = 0):
+        """every rank passes its records (local window indices + window_offset = global); on `root` returns
+        (variants, strings, summed stats) of all ranks in rank order, elsewhere (None, None, None)"""
+        v = np.ascontiguousarray(variants.copy()); v["window"] += window_offset
+        st = (ctypes.c_uint64 * max(len(stats), 1))(*[int(x) for x in stats])
+        r = _Result()
+        self._ck(_lib.lb2_comm_gather(self._h, v.ctypes.data if len(v) else None, len(v), strings, len(strings), st, len(stats), root, ctypes.byref(r)))
+        if self.rank != root:
+            return None, None, None
+        gv = np.ctypeslib.as_array(ctypes.cast(r.variants, ctypes.POINTER(ctypes.c_uint8)), (r.n_variants * 40,)).view(VARIANT_DTYPE).copy() if r.n_variants else np.zeros(0, VARIANT_DTYPE)
+        gs = ctypes.string_at(r.strings, r.n_string_bytes) if r.n_string_bytes else b""
+        return gv, gs, [int(st[i]) for i in range(len(stats))]
 
     kernel_launches = property(lambda self: int(_lib.lb2_kernel_launches(self._h)))
     last_h2d_bytes = property(lambda self: int(_lib.lb2_last_h2d_bytes(self._h)))

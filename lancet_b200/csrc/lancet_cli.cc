@@ -12,6 +12,12 @@
 // the replay order of VariantDB_t::addVar, reference src/Lancet.cc:305-310,943-959), except for the
 // ##fileDate / ##cmdline header lines.
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -27,6 +33,11 @@
 #include <string>
 #include <vector>
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <climits>
+#include <sys/types.h>
+#include <sys/wait.h>
 
 #include "../../include/lancet_b200.h"
 
@@ -47,7 +58,7 @@ struct Opts {
 	int max_indel_len = 500, max_mismatch = 2, max_unit_len = 4, min_report_units = 3, min_report_len = 7, dist_from_str = 1;
 	double cov_ratio = 0.01;
 	bool primary_only = false, xa_filter = false, active_regions = true, verbose = false;
-	int gpu = 0;
+	int gpu = 0, gpus = 1, rank = -1, world = 1, batch_windows = 16384, io_threads = 0; string nccl_id_file;
 	Filters f;
 };
 
@@ -223,7 +234,10 @@ static void print_header(const Opts &o, const string &sn, const string &st)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// BAM decode (BGZF blocks inflated with zlib; records kept only for the reference sequences asked for)
+// BAM access (the reference uses bamtools' SetRegion per window, src/Microassembler.cc:802-834; here: BGZF + BAI read
+// directly).  A region fetch looks the first block up in the BAI linear index, reads compressed blocks from there,
+// inflates them on several threads, cuts the stream into records and decodes those on several threads, and stops at
+// the first record that starts at or beyond the region's end.  Without an index the file is scanned from its first record.
 // ------------------------------------------------------------------------------------------------------------
 struct Aln {
 	int32_t pos = 0, end = 0; uint16_t flag = 0; uint8_t mapq = 0; int32_t l_seq = 0;
@@ -231,102 +245,214 @@ struct Aln {
 	vector<uint32_t> cigar;                // BAM encoding: len << 4 | op
 	float as = -1, xs = -1; bool has_md = false;
 };
-struct Bam {
-	vector<string> ref_names; vector<int32_t> ref_lens; string sample = "NA"; bool first_has_md = true;
-	std::map<int, vector<Aln>> by_ref;
-};
 
-static bool inflate_bgzf(const string &path, vector<uint8_t> &out)
+template <class F> static void parallel_for(size_t n, unsigned threads, F f)
 {
-	FILE *f = fopen(path.c_str(), "rb"); if (!f) { return false; }
-	vector<uint8_t> in; uint8_t buf[1 << 16]; size_t n;
-	while ((n = fread(buf, 1, sizeof buf, f)) > 0) { in.insert(in.end(), buf, buf + n); }
-	fclose(f);
-	size_t p = 0;
-	while (p + 18 <= in.size()) {
-		if (in[p] != 31 || in[p + 1] != 139) { return false; }
-		uint16_t xlen = in[p + 10] | (in[p + 11] << 8); uint32_t bsize = 0; size_t x = p + 12, xe = x + xlen;
-		while (x + 4 <= xe) { uint16_t sl = in[x + 2] | (in[x + 3] << 8); if (in[x] == 'B' && in[x + 1] == 'C') { bsize = (in[x + 4] | (in[x + 5] << 8)) + 1u; } x += 4 + sl; }
-		if (!bsize || p + bsize > in.size()) { return false; }
-		size_t cdata = p + 12 + xlen, clen = bsize - xlen - 19;
-		uint32_t isize = in[p + bsize - 4] | (in[p + bsize - 3] << 8) | (in[p + bsize - 2] << 16) | ((uint32_t)in[p + bsize - 1] << 24);
-		size_t o0 = out.size(); out.resize(o0 + isize);
-		if (isize) {
-			z_stream zs; memset(&zs, 0, sizeof zs);
-			if (inflateInit2(&zs, -15) != Z_OK) { return false; }
-			zs.next_in = in.data() + cdata; zs.avail_in = (uInt)clen; zs.next_out = out.data() + o0; zs.avail_out = isize;
-			int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
-			if (rc != Z_STREAM_END) { return false; }
-		}
-		p += bsize;
-	}
-	return true;
+	if (threads <= 1 || n < 2) { for (size_t i = 0; i < n; ++i) { f(i); } return; }
+	std::atomic<size_t> next(0); vector<std::thread> th; const unsigned T = (unsigned)std::min<size_t>(threads, n);
+	for (unsigned t = 0; t < T; ++t) { th.emplace_back([&]() { while (true) { size_t i = next.fetch_add(1); if (i >= n) { break; } f(i); } }); }
+	for (auto &x : th) { x.join(); }
 }
 
-static bool read_bam(const string &path, Bam &b, const std::map<string, bool> &want_refs)
+static void decode_record(const uint8_t *r, int32_t bs, Aln &a)
 {
-	vector<uint8_t> d;
-	if (!inflate_bgzf(path, d)) { return false; }
-	auto i32 = [&](size_t o) { int32_t v; memcpy(&v, d.data() + o, 4); return v; };
-	if (d.size() < 12 || memcmp(d.data(), "BAM\1", 4)) { return false; }
-	size_t p = 4; int32_t l_text = i32(p); p += 4; string text((const char *)d.data() + p, l_text); p += l_text;
-	{	// first @RG line with an SM: field (reference retriveSampleName, src/Microassembler.cc:52-67)
-		std::istringstream is(text); string line;
-		while (std::getline(is, line)) {
-			if (line.compare(0, 3, "@RG") == 0) {
-				size_t q = line.find("\tSM:");
-				if (q != string::npos) { size_t e = line.find('\t', q + 1); b.sample = line.substr(q + 4, e == string::npos ? string::npos : e - q - 4); }
-				break;
-			}
-		}
-	}
-	int32_t n_ref = i32(p); p += 4;
-	for (int r = 0; r < n_ref; ++r) { int32_t l = i32(p); p += 4; b.ref_names.push_back(string((const char *)d.data() + p, l - 1)); p += l; b.ref_lens.push_back(i32(p)); p += 4; }
-	bool first = true;
 	static const char *NT = "=ACMGRSVTWYHKDBN";
-	while (p + 4 <= d.size()) {
-		int32_t bs = i32(p); p += 4; size_t r0 = p; p += bs; if (p > d.size()) { break; }
-		int32_t refID = i32(r0), pos = i32(r0 + 4); uint8_t l_name = d[r0 + 8], mapq = d[r0 + 9];
-		uint16_t n_cig = d[r0 + 12] | (d[r0 + 13] << 8), flag = d[r0 + 14] | (d[r0 + 15] << 8); int32_t l_seq = i32(r0 + 16);
-		size_t q = r0 + 32; const char *name = (const char *)d.data() + q; q += l_name;
-		size_t cig = q; q += 4 * (size_t)n_cig; size_t sq = q; q += (l_seq + 1) / 2; size_t ql = q; q += l_seq; size_t tags = q, tend = r0 + bs;
-		bool has_md = false; string md, xt, xa; float as = -1, xs = -1;
-		size_t t = tags;
-		while (t + 3 <= tend) {
-			char t0 = d[t], t1 = d[t + 1], ty = d[t + 2]; t += 3; double num = 0; bool isnum = false; string sv;
-			switch (ty) {
-				case 'A': {      // bamtools GetTag<std::string> does strlen() on the value: a char tag runs on into the next tag's bytes up to a NUL
-					size_t e = t; while (e < tend && d[e]) { ++e; } sv = string((const char *)d.data() + t, e - t); t += 1; break; }
-				case 'c': num = (int8_t)d[t]; isnum = true; t += 1; break; case 'C': num = d[t]; isnum = true; t += 1; break;
-				case 's': { int16_t v; memcpy(&v, d.data() + t, 2); num = v; isnum = true; t += 2; break; }
-				case 'S': { uint16_t v; memcpy(&v, d.data() + t, 2); num = v; isnum = true; t += 2; break; }
-				case 'i': { int32_t v; memcpy(&v, d.data() + t, 4); num = v; isnum = true; t += 4; break; }
-				case 'I': { uint32_t v; memcpy(&v, d.data() + t, 4); num = v; isnum = true; t += 4; break; }
-				case 'f': { float v; memcpy(&v, d.data() + t, 4); num = v; isnum = true; t += 4; break; }
-				case 'Z': case 'H': { size_t e = t; while (e < tend && d[e]) { ++e; } sv = string((const char *)d.data() + t, e - t); t = e + 1; break; }
-				case 'B': { char st = d[t]; int32_t cnt; memcpy(&cnt, d.data() + t + 1, 4); int es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; t += 5 + (size_t)es * cnt; break; }
-				default: t = tend; break;
-			}
-			if (t0 == 'M' && t1 == 'D') { has_md = true; md = sv; }
-			else if (t0 == 'A' && t1 == 'S' && isnum) { as = (float)num; } else if (t0 == 'X' && t1 == 'S' && isnum) { xs = (float)num; }
-			else if (t0 == 'X' && t1 == 'T') { xt = sv; } else if (t0 == 'X' && t1 == 'A') { xa = sv; }
+	auto i32 = [&](size_t o) { int32_t v; memcpy(&v, r + o, 4); return v; };
+	const int32_t pos = i32(4); const uint8_t l_name = r[8], mapq = r[9];
+	const uint16_t n_cig = r[12] | (r[13] << 8), flag = r[14] | (r[15] << 8); const int32_t l_seq = i32(16);
+	size_t q = 32; const char *name = (const char *)r + q; q += l_name;
+	const size_t cig = q; q += 4 * (size_t)n_cig; const size_t sq = q; q += (l_seq + 1) / 2; const size_t ql = q; q += l_seq; size_t t = q; const size_t tend = (size_t)bs;
+	a.pos = pos; a.flag = flag; a.mapq = mapq; a.l_seq = l_seq; a.name = name;
+	while (t + 3 <= tend) {
+		char t0 = r[t], t1 = r[t + 1], ty = r[t + 2]; t += 3; double num = 0; bool isnum = false; string sv;
+		switch (ty) {
+			case 'A': {      // bamtools GetTag<std::string> does strlen() on the value: a char tag runs on into the next tag's bytes up to a NUL
+				size_t e = t; while (e < tend && r[e]) { ++e; } sv = string((const char *)r + t, e - t); t += 1; break; }
+			case 'c': num = (int8_t)r[t]; isnum = true; t += 1; break; case 'C': num = r[t]; isnum = true; t += 1; break;
+			case 's': { int16_t v; memcpy(&v, r + t, 2); num = v; isnum = true; t += 2; break; }
+			case 'S': { uint16_t v; memcpy(&v, r + t, 2); num = v; isnum = true; t += 2; break; }
+			case 'i': { int32_t v; memcpy(&v, r + t, 4); num = v; isnum = true; t += 4; break; }
+			case 'I': { uint32_t v; memcpy(&v, r + t, 4); num = v; isnum = true; t += 4; break; }
+			case 'f': { float v; memcpy(&v, r + t, 4); num = v; isnum = true; t += 4; break; }
+			case 'Z': case 'H': { size_t e = t; while (e < tend && r[e]) { ++e; } sv = string((const char *)r + t, e - t); t = e + 1; break; }
+			case 'B': { char st = r[t]; int32_t cnt; memcpy(&cnt, r + t + 1, 4); int es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; t += 5 + (size_t)es * cnt; break; }
+			default: t = tend; break;
 		}
-		if (first) { b.first_has_md = has_md; first = false; }
-		if (refID < 0 || refID >= n_ref || !want_refs.count(b.ref_names[refID])) { continue; }
-		Aln a; a.pos = pos; a.flag = flag; a.mapq = mapq; a.l_seq = l_seq; a.name = name; a.has_md = has_md; a.md = md; a.xt = xt; a.xa = xa; a.as = as; a.xs = xs;
-		a.cigar.resize(n_cig); int32_t end = pos;
-		for (int c = 0; c < n_cig; ++c) {
-			uint32_t v; memcpy(&v, d.data() + cig + 4 * c, 4); a.cigar[c] = v; int op = v & 15;
-			if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) { end += (int32_t)(v >> 4); }      // M D N = X (BamAlignment::GetEndPosition)
-		}
-		a.end = end;
-		a.seq.resize(l_seq); a.qual.resize(l_seq);
-		for (int i = 0; i < l_seq; ++i) { uint8_t by = d[sq + i / 2]; a.seq[i] = NT[(i & 1) ? (by & 15) : (by >> 4)]; a.qual[i] = (char)(d[ql + i] + 33); }
-		if (l_seq && d[ql] == 0xFF) { a.qual.clear(); }
-		b.by_ref[refID].push_back(std::move(a));
+		if (t0 == 'M' && t1 == 'D') { a.has_md = true; a.md = sv; }
+		else if (t0 == 'A' && t1 == 'S' && isnum) { a.as = (float)num; } else if (t0 == 'X' && t1 == 'S' && isnum) { a.xs = (float)num; }
+		else if (t0 == 'X' && t1 == 'T') { a.xt = sv; } else if (t0 == 'X' && t1 == 'A') { a.xa = sv; }
 	}
-	return true;
+	a.cigar.resize(n_cig); int32_t end = pos;
+	for (int c = 0; c < n_cig; ++c) {
+		uint32_t v; memcpy(&v, r + cig + 4 * c, 4); a.cigar[c] = v; int op = v & 15;
+		if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) { end += (int32_t)(v >> 4); }      // M D N = X (BamAlignment::GetEndPosition)
+	}
+	a.end = end;
+	a.seq.resize(l_seq); a.qual.resize(l_seq);
+	for (int i = 0; i < l_seq; ++i) { uint8_t by = r[sq + i / 2]; a.seq[i] = NT[(i & 1) ? (by & 15) : (by >> 4)]; a.qual[i] = (char)(r[ql + i] + 33); }
+	if (l_seq && r[ql] == 0xFF) { a.qual.clear(); }
 }
+
+struct BamFile {
+	string path; FILE *f = nullptr; uint64_t file_size = 0;
+	vector<string> ref_names; vector<int32_t> ref_lens; string sample = "NA"; bool first_has_md = true;
+	uint64_t first_voff = 0;                       // virtual offset of the first alignment record
+	bool has_index = false; vector<vector<uint64_t>> linear; vector<uint64_t> ref_first;      // BAI: linear index and smallest chunk start per reference
+	unsigned threads = 1;
+	~BamFile() { if (f) { fclose(f); } }
+
+	// compressed blocks [coff, ...) up to ~want bytes: (file offset, block size, inflated size) of every complete block read
+	struct Blk { uint64_t coff; uint32_t bsize, isize; size_t in_off, out_off; };
+	bool read_blocks(uint64_t coff, size_t want, vector<uint8_t> &in, vector<Blk> &blks, bool &eof) {
+		blks.clear(); eof = false;
+		if (coff >= file_size) { eof = true; return true; }
+		const size_t n = (size_t)std::min<uint64_t>(want + (1u << 16), file_size - coff);
+		in.resize(n);
+		if (fseeko(f, (off_t)coff, SEEK_SET) != 0 || fread(in.data(), 1, n, f) != n) { return false; }
+		size_t p = 0, out = 0;
+		while (p + 18 <= n) {
+			if (in[p] != 31 || in[p + 1] != 139) { return false; }
+			const uint16_t xlen = in[p + 10] | (in[p + 11] << 8); uint32_t bsize = 0; size_t x = p + 12, xe = x + xlen;
+			if (xe > n) { break; }
+			while (x + 4 <= xe) { uint16_t sl = in[x + 2] | (in[x + 3] << 8); if (in[x] == 'B' && in[x + 1] == 'C') { bsize = (in[x + 4] | (in[x + 5] << 8)) + 1u; } x += 4 + sl; }
+			if (!bsize) { return false; }
+			if (p + bsize > n) { break; }
+			Blk b; b.coff = coff + p; b.bsize = bsize; b.in_off = p; b.out_off = out;
+			b.isize = in[p + bsize - 4] | (in[p + bsize - 3] << 8) | (in[p + bsize - 2] << 16) | ((uint32_t)in[p + bsize - 1] << 24);
+			blks.push_back(b); out += b.isize; p += bsize;
+		}
+		if (coff + p >= file_size) { eof = true; }
+		return !blks.empty() || eof;
+	}
+	bool inflate_blocks(const vector<uint8_t> &in, const vector<Blk> &blks, vector<uint8_t> &out, size_t keep) {
+		const size_t total = blks.empty() ? 0 : blks.back().out_off + blks.back().isize;
+		out.resize(keep + total);
+		std::atomic<int> bad(0);
+		parallel_for(blks.size(), threads, [&](size_t i) {
+			const Blk &b = blks[i]; if (!b.isize) { return; }
+			const uint16_t xlen = in[b.in_off + 10] | (in[b.in_off + 11] << 8);
+			z_stream zs; memset(&zs, 0, sizeof zs);
+			if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+			zs.next_in = (Bytef *)in.data() + b.in_off + 12 + xlen; zs.avail_in = (uInt)(b.bsize - xlen - 19); zs.next_out = out.data() + keep + b.out_off; zs.avail_out = b.isize;
+			const int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
+			if (rc != Z_STREAM_END) { bad = 1; }
+		});
+		return !bad;
+	}
+
+	bool open(const string &p, unsigned nthreads) {
+		path = p; threads = std::max(1u, nthreads);
+		f = fopen(p.c_str(), "rb"); if (!f) { return false; }
+		fseeko(f, 0, SEEK_END); file_size = (uint64_t)ftello(f);
+		// header: text, reference dictionary; then the first record (MD tag check, reference src/Lancet.cc:817-825)
+		vector<uint8_t> in, d; vector<Blk> blks; bool eof = false; uint64_t coff = 0; vector<uint64_t> blk_coff, blk_end;      // inflated end offset of every block read
+		auto more = [&]() -> bool {
+			if (eof) { return false; }
+			if (!read_blocks(coff, 1u << 20, in, blks, eof) || blks.empty()) { return false; }
+			const size_t keep = d.size();
+			if (!inflate_blocks(in, blks, d, keep)) { return false; }
+			for (auto &b : blks) { blk_coff.push_back(b.coff); blk_end.push_back(keep + b.out_off + b.isize); }
+			coff = blks.back().coff + blks.back().bsize;
+			return true;
+		};
+		auto need = [&](size_t upto) -> bool { while (d.size() < upto) { if (!more()) { return false; } } return true; };
+		auto i32 = [&](size_t o) { int32_t v; memcpy(&v, d.data() + o, 4); return v; };
+		if (!need(12) || memcmp(d.data(), "BAM\1", 4)) { return false; }
+		size_t q = 4; const int32_t l_text = i32(q); q += 4; if (!need(q + l_text + 4)) { return false; }
+		const string text((const char *)d.data() + q, l_text); q += l_text;
+		{	// first @RG line with an SM: field (reference retriveSampleName, src/Microassembler.cc:52-67)
+			std::istringstream is(text); string line;
+			while (std::getline(is, line)) {
+				if (line.compare(0, 3, "@RG") == 0) {
+					size_t x = line.find("\tSM:");
+					if (x != string::npos) { size_t e = line.find('\t', x + 1); sample = line.substr(x + 4, e == string::npos ? string::npos : e - x - 4); }
+					break;
+				}
+			}
+		}
+		const int32_t n_ref = i32(q); q += 4;
+		for (int r = 0; r < n_ref; ++r) {
+			if (!need(q + 4)) { return false; } const int32_t l = i32(q); q += 4;
+			if (!need(q + l + 4)) { return false; }
+			ref_names.push_back(string((const char *)d.data() + q, l - 1)); q += l; ref_lens.push_back(i32(q)); q += 4;
+		}
+		// virtual offset of the first record = (start of the block holding inflated offset q, offset inside it)
+		{
+			if (!need(q + 1) && d.size() < q) { return false; }
+			size_t bi = 0; while (bi < blk_end.size() && blk_end[bi] <= q) { ++bi; }
+			if (bi < blk_end.size()) { const size_t bstart = bi ? blk_end[bi - 1] : 0; first_voff = (blk_coff[bi] << 16) | (uint64_t)(q - bstart); }
+			else { first_voff = coff << 16; }
+		}
+		if (need(q + 4)) { const int32_t bs = i32(q); if (bs >= 32 && need(q + 4 + bs)) { Aln a; decode_record(d.data() + q + 4, bs, a); first_has_md = a.has_md; } }
+		load_index();
+		return true;
+	}
+
+	void load_index() {
+		string cand[2] = { path + ".bai", path.size() > 4 ? path.substr(0, path.size() - 4) + ".bai" : string() };
+		for (auto &ip : cand) {
+			if (ip.empty()) { continue; }
+			FILE *g = fopen(ip.c_str(), "rb"); if (!g) { continue; }
+			vector<uint8_t> b; uint8_t buf[1 << 16]; size_t n; while ((n = fread(buf, 1, sizeof buf, g)) > 0) { b.insert(b.end(), buf, buf + n); } fclose(g);
+			size_t q = 0; auto u32 = [&]() { uint32_t v = 0; if (q + 4 <= b.size()) { memcpy(&v, b.data() + q, 4); } q += 4; return v; };
+			auto u64 = [&]() { uint64_t v = 0; if (q + 8 <= b.size()) { memcpy(&v, b.data() + q, 8); } q += 8; return v; };
+			if (b.size() < 8 || memcmp(b.data(), "BAI\1", 4)) { continue; }
+			q = 4; const uint32_t n_ref = u32(); linear.assign(n_ref, {}); ref_first.assign(n_ref, ~0ull);
+			for (uint32_t r = 0; r < n_ref && q <= b.size(); ++r) {
+				const uint32_t n_bin = u32();
+				for (uint32_t i = 0; i < n_bin; ++i) {
+					const uint32_t bin = u32(), n_chunk = u32();
+					for (uint32_t c = 0; c < n_chunk; ++c) { const uint64_t cb = u64(); u64(); if (bin != 37450 && cb < ref_first[r]) { ref_first[r] = cb; } }      // (bin 37450: metadata pseudo-bin)
+				}
+				const uint32_t n_intv = u32(); linear[r].resize(n_intv);
+				for (uint32_t i = 0; i < n_intv; ++i) { linear[r][i] = u64(); }
+			}
+			has_index = q <= b.size();
+			if (has_index) { return; }
+			linear.clear(); ref_first.clear();
+		}
+	}
+
+	// all records of reference refID whose position lies in [beg, end), in file order
+	bool fetch(int refID, int beg, int end, vector<Aln> &out) {
+		out.clear();
+		if (refID < 0 || refID >= (int)ref_names.size() || end <= beg) { return true; }
+		uint64_t voff = first_voff;
+		if (has_index && refID < (int)linear.size()) {
+			if (ref_first[refID] == ~0ull) { return true; }            // no alignment on this reference
+			voff = ref_first[refID];
+			const vector<uint64_t> &li = linear[refID];
+			if (!li.empty()) { size_t i = std::min<size_t>((size_t)std::max(beg, 0) >> 14, li.size() - 1); while (i > 0 && li[i] == 0) { --i; } if (li[i] > voff) { voff = li[i]; } }
+		}
+		vector<uint8_t> in, d; vector<Blk> blks; bool eof = false; uint64_t coff = voff >> 16; size_t skip = (size_t)(voff & 0xFFFF);
+		vector<uint8_t> carry;
+		bool done = false; size_t want = 4u << 20;
+		while (!done) {
+			if (!read_blocks(coff, want, in, blks, eof)) { return false; }
+			if (blks.empty()) { break; }
+			d = carry; const size_t keep = d.size();
+			if (!inflate_blocks(in, blks, d, keep)) { return false; }
+			coff = blks.back().coff + blks.back().bsize;
+			// cut into records (sequential: every record names its own size), remember the ones of this region
+			size_t q = skip; skip = 0; vector<std::pair<size_t, int32_t>> recs;
+			while (q + 4 <= d.size()) {
+				int32_t bs; memcpy(&bs, d.data() + q, 4);
+				if (bs < 32) { return false; }
+				if (q + 4 + (size_t)bs > d.size()) { break; }
+				int32_t rid, pos; memcpy(&rid, d.data() + q + 4, 4); memcpy(&pos, d.data() + q + 8, 4);
+				if (rid < 0 || rid > refID || (rid == refID && pos >= end)) { done = true; break; }      // (coordinate-sorted: unplaced reads come last)
+				if (rid == refID && pos >= beg) { recs.push_back(std::make_pair(q + 4, bs)); }
+				q += 4 + (size_t)bs;
+			}
+			const size_t o0 = out.size(); out.resize(o0 + recs.size());
+			parallel_for((recs.size() + 255) / 256, threads, [&](size_t c) { for (size_t i = c * 256; i < std::min(recs.size(), (c + 1) * 256); ++i) { decode_record(d.data() + recs[i].first, recs[i].second, out[o0 + i]); } });
+			carry.assign(d.begin() + (done ? d.size() : q), d.end());
+			if (eof) { break; }
+			want = std::min<size_t>(want * 2, 64u << 20);
+		}
+		return true;
+	}
+};
 
 // ------------------------------------------------------------------------------------------------------------
 // FASTA fetch (reference uses htslib faidx; src/Lancet.cc:245-263): 1-based inclusive region, upper-cased, IUPAC -> N
@@ -355,7 +481,7 @@ static bool fasta_fetch(const string &path, const string &chr, int start1, int e
 // ------------------------------------------------------------------------------------------------------------
 struct Window { string chr, hdr, raw; int refstart, refend; int thread; };
 
-static int load_refs(const Opts &o, const Bam &bam, const string &region, vector<Window> &wins, int thread, int &num_windows)
+static int load_refs(const Opts &o, const BamFile &bam, const string &region, vector<Window> &wins, int thread, int &num_windows)
 {
 	string CHR, START, END;
 	size_t x = region.find_first_of(':');
@@ -449,7 +575,8 @@ int main(int argc, char **argv)
 		{"max-alt-count-normal", 1, 0, 'm'}, {"min-vaf-tumor", 1, 0, 'e'}, {"max-vaf-normal", 1, 0, 'i'}, {"min-coverage-tumor", 1, 0, 'o'},
 		{"max-coverage-tumor", 1, 0, 'y'}, {"min-coverage-normal", 1, 0, 'z'}, {"max-coverage-normal", 1, 0, 'j'}, {"linked-reads", 0, 0, 'J'},
 		{"primary-alignment-only", 0, 0, 'I'}, {"XA-tag-filter", 0, 0, 'O'}, {"active-region-off", 0, 0, 'W'}, {"kmer-recovery-on", 0, 0, 'R'},
-		{"verbose", 0, 0, 'v'}, {"more-verbose", 0, 0, 'V'}, {"print-graph", 0, 0, 'A'}, {"print-config-file", 0, 0, 'G'}, {"gpu", 1, 0, 1000}, {"self-test", 0, 0, 1001}, {0, 0, 0, 0} };
+		{"verbose", 0, 0, 'v'}, {"more-verbose", 0, 0, 'V'}, {"print-graph", 0, 0, 'A'}, {"print-config-file", 0, 0, 'G'}, {"gpu", 1, 0, 1000}, {"self-test", 0, 0, 1001},
+		{"gpus", 1, 0, 1002}, {"batch-windows", 1, 0, 1003}, {"io-threads", 1, 0, 1004}, {"rank", 1, 0, 1005}, {"world", 1, 0, 1006}, {"nccl-id-file", 1, 0, 1007}, {0, 0, 0, 0} };
 	int ch, oi = 0;
 	while ((ch = getopt_long(argc, argv, "u:n:r:g:k:K:l:f:t:c:C:d:x:GARhSIWJOL:T:P:M:vVF:q:b:B:Q:p:s:E:a:m:e:i:o:y:z:w:j:X:U:N:Y:D:Z:", lo, &oi)) != -1) {
 		switch (ch) {
@@ -467,6 +594,8 @@ int main(int argc, char **argv)
 			case 'z': o.f.minCovNormal = atoi(optarg); break; case 'j': o.f.maxCovNormal = atoi(optarg); break;
 			case 'I': o.primary_only = true; break; case 'O': o.xa_filter = true; break; case 'W': o.active_regions = false; break;
 			case 'v': case 'V': o.verbose = true; break; case 'G': break; case 1000: o.gpu = atoi(optarg); break;
+			case 1002: o.gpus = atoi(optarg); break; case 1003: o.batch_windows = atoi(optarg); break; case 1004: o.io_threads = atoi(optarg); break;
+			case 1005: o.rank = atoi(optarg); break; case 1006: o.world = atoi(optarg); break; case 1007: o.nccl_id_file = optarg; break;
 			case 1001: {      // known-answer hooks for tests/test_cli_host.py (hash, Fisher point probability, number formatting)
 				std::cout << "sha256(abc)=" << sha256_hex("abc") << "\nsha256()=" << sha256_hex("") << "\nsha256(chr22:1234:S:1:A:T x3)=" << sha256_hex("chr22:1234:S:1:A:Tchr22:1234:S:1:A:Tchr22:1234:S:1:A:T") << "\n";
 				int tabs[6][4] = { {10, 12, 0, 7}, {30, 28, 0, 0}, {3, 1, 1, 3}, {100, 90, 2, 25}, {0, 0, 5, 5}, {1000, 800, 0, 300} };
@@ -501,12 +630,41 @@ int main(int argc, char **argv)
 	n_bed_regions = regions.size();
 	if (!o.reg.empty()) { regions.push_back(o.reg); want[o.reg.substr(0, o.reg.find_first_of(':'))] = true; }
 
-	Bam T, N;
-	if (!read_bam(o.tumor, T, want)) { std::cerr << "Could not open tumor BAM file." << std::endl; return -1; }
-	if (!read_bam(o.normal, N, want)) { std::cerr << "Could not open normal BAM file." << std::endl; return -1; }
+	if (o.gpus < 1) { o.gpus = 1; } if (o.batch_windows < 1) { o.batch_windows = 1; } if (o.batch_windows > 65536) { o.batch_windows = 65536; }
+	if (o.io_threads <= 0) { o.io_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, o.rank >= 0 ? o.world : o.gpus))); }
+	// ---- several GPUs: one process per GPU.  The launcher (no --rank) writes an NCCL id, starts ranks 1..N-1 as copies of
+	// itself and continues as rank 0; every rank assembles a contiguous range of the windows on its own GPU, the records are
+	// gathered on rank 0 over NCCL (lb2_comm_gather), rank 0 replays them into the variant store and writes the VCF
+	vector<pid_t> children;
+	if (o.gpus > 1 && o.rank < 0) {
+		char id[LB2_COMM_ID_BYTES];
+		if (lb2_comm_unique_id(id) != LB2_OK) { std::cerr << "ERROR: cannot create the NCCL id (no GPU / no NCCL)" << std::endl; return 2; }
+		o.nccl_id_file = "/tmp/lancet_b200_nccl_" + itos((int)getpid()) + ".id";
+		{ std::ofstream idf(o.nccl_id_file, std::ios::binary); idf.write(id, sizeof id); }
+		o.world = o.gpus; o.rank = 0;
+		for (int r = 1; r < o.world; ++r) {
+			pid_t pid = fork();
+			if (pid == 0) {
+				vector<string> av(argv, argv + argc); av.push_back("--rank"); av.push_back(itos(r)); av.push_back("--world"); av.push_back(itos(o.world)); av.push_back("--nccl-id-file"); av.push_back(o.nccl_id_file);
+				vector<char *> cav; for (auto &x : av) { cav.push_back((char *)x.c_str()); } cav.push_back(nullptr);
+				int devnull = open("/dev/null", O_WRONLY); if (devnull >= 0) { dup2(devnull, 1); }      // only rank 0 writes the VCF
+				execv("/proc/self/exe", cav.data()); _exit(127);
+			}
+			if (pid < 0) { std::cerr << "ERROR: fork failed" << std::endl; return 2; }
+			children.push_back(pid);
+		}
+	}
+	if (o.rank < 0) { o.rank = 0; o.world = 1; }
+	const bool lead = o.rank == 0;
+
+	BamFile T, N;
+	if (!T.open(o.tumor, (unsigned)o.io_threads)) { std::cerr << "Could not open tumor BAM file." << std::endl; return -1; }
+	if (!N.open(o.normal, (unsigned)o.io_threads)) { std::cerr << "Could not open normal BAM file." << std::endl; return -1; }
 	if (!(T.first_has_md || N.first_has_md) && o.active_regions) {
-		std::cerr << "\n--------WARNING--------\nThe MD tag is required to select the active regions, but is missing from the alignments in the BAM(s) file(s).\n"
-		          << "To avoid unpredictable behavior, the active region module has been automatically turned off (--active-region-off)\n-----------------------\n" << std::endl;
+		if (lead) {
+			std::cerr << "\n--------WARNING--------\nThe MD tag is required to select the active regions, but is missing from the alignments in the BAM(s) file(s).\n"
+			          << "To avoid unpredictable behavior, the active region module has been automatically turned off (--active-region-off)\n-----------------------\n" << std::endl;
+		}
 		o.active_regions = false;
 	}
 	vector<Window> wins; int num_windows = 0, t = 0;
@@ -516,101 +674,173 @@ int main(int argc, char **argv)
 		for (auto &w : wins) { auto key = std::make_pair(w.thread, w.hdr); if (!seen.count(key)) { seen[key] = true; uniq.push_back(w); } }
 		wins.swap(uniq);
 	}
-	std::cerr << num_windows << " total windows to process" << std::endl;
+	if (lead) { std::cerr << num_windows << " total windows to process" << std::endl; }
 
-	// ---- read selection per window -> batch arrays ------------------------------------------------------------
-	vector<uint32_t> ref_off{0}, wr_off{0}, wr_idx, chr_id; vector<int32_t> ref_start; vector<uint64_t> base_off{0}; vector<uint8_t> flags;
-	vector<const char *> names; string ref_seq, seq, qual; int tot_skip = 0;
-	vector<uint32_t> win_of_batch;      // batch window -> index in wins
-	auto ref_id = [](const Bam &b, const string &chr) { for (size_t i = 0; i < b.ref_names.size(); ++i) { if (b.ref_names[i] == chr) { return (int)i; } } return -1; };
-	static const vector<Aln> none;
-	const int qcall = o.min_qv_call + o.qv_range; (void)qcall;
-	for (size_t wi = 0; wi < wins.size(); ++wi) {
-		const Window &w = wins[wi];
-		if (w.raw.empty()) { continue; }
-		int rt = ref_id(T, w.chr), rn = ref_id(N, w.chr);
-		const vector<Aln> &AT = (rt >= 0 && T.by_ref.count(rt)) ? T.by_ref[rt] : none, &AN = (rn >= 0 && N.by_ref.count(rn)) ? N.by_ref[rn] : none;
-		const int left = w.refstart, right = w.refend;      // 1-based numbers used as a 0-based half-open BAM region (reference quirk B9)
-		auto range = [&](const vector<Aln> &A, size_t &lo, size_t &hi) {
-			lo = std::lower_bound(A.begin(), A.end(), left, [](const Aln &a, int v) { return a.pos < v; }) - A.begin();
-			hi = std::lower_bound(A.begin(), A.end(), right, [](const Aln &a, int v) { return a.pos < v; }) - A.begin();
-		};
-		size_t tl, th, nl, nh; range(AT, tl, th); range(AN, nl, nh);
-		bool activeT = true, activeN = true;
-		if (o.active_regions) { activeT = is_active(AT, tl, th, left, right, false, o); activeN = is_active(AN, nl, nh, left, right, true, o); }
-		if (!(activeT || activeN)) { ++tot_skip; continue; }
-		size_t wr0 = wr_idx.size(); bool skip = false;
-		for (int sample = 0; sample < 2 && !skip; ++sample) {
-			const vector<Aln> &A = sample ? AN : AT; size_t lo_ = sample ? nl : tl, hi_ = sample ? nh : th;
-			const int MQ = sample ? 0 : o.min_map_qual; const int MIN_DELTA = sample ? -1 : 5;       // MAX_DELTA_AS_XS is 5 whatever -Z says
-			long totalbp = 0;
-			for (size_t i = lo_; i < hi_; ++i) {
-				const Aln &al = A[i];
-				if ((double)totalbp / (double)w.raw.length() > o.max_avg_cov) { skip = true; break; }
-				if (al.pos < left || al.end > right) { continue; }
-				if (o.primary_only && (al.flag & 0x100)) { continue; }
-				if (!(al.mapq >= MQ && !(al.flag & 0x400))) { continue; }
-				float delta = std::fabs(al.as - al.xs);
-				if (delta <= MIN_DELTA && al.as != -1 && al.xs != -1) { continue; }
-				if (al.xt == "R" && !sample) { continue; }
-				if (!al.xa.empty() && !sample && o.xa_filter) { continue; }
-				int mate = (al.flag & 0x40) ? 1 : 0; if (al.flag & 0x80) { mate = 2; }
-				uint8_t fl = (sample ? LB2_READ_NORMAL : 0) | ((al.flag & 0x10) ? LB2_READ_REVERSE : 0) | (uint8_t)(mate << LB2_READ_MATE_SHIFT) | ((al.flag & 0x4) ? LB2_READ_UNMAPPED : 0);
-				wr_idx.push_back((uint32_t)flags.size()); flags.push_back(fl); names.push_back(al.name.c_str());
-				seq += al.seq; qual += al.qual.empty() ? string(al.seq.size(), (char)(0xFF + 33)) : al.qual; base_off.push_back(seq.size());
-				totalbp += (long)al.seq.length();
-			}
-		}
-		if (skip) {      // "Too much coverage": the window is dropped (reads staged for it are simply not referenced)
-			std::cerr << "WARNING: Skip region " << w.chr << ":" << w.refstart << "-" << w.refend << ". Too much coverage (>" << o.max_avg_cov << "x)." << std::endl;
-			wr_idx.resize(wr0); ++tot_skip; continue;
-		}
-		ref_seq += w.raw; ref_off.push_back((uint32_t)ref_seq.size()); ref_start.push_back(w.refstart); chr_id.push_back(0); wr_off.push_back((uint32_t)wr_idx.size());
-		win_of_batch.push_back((uint32_t)wi);
-	}
-	std::cerr << "Total # of skipped windows: " << tot_skip << std::endl;
-
-	// ---- micro-assembly on the GPU ----------------------------------------------------------------------------
+	// ---- the GPU side ---------------------------------------------------------------------------------------------
 	lb2_params p; lb2_default_params(&p);
 	p.min_k = o.minK; p.max_k = o.maxK; p.min_qual_trim = o.min_qv_trim + o.qv_range; p.min_qual_call = o.min_qv_call + o.qv_range; p.cov_threshold = o.cov_thr;
 	p.low_cov_threshold = o.low_cov; p.max_tip_len = o.tip_len; p.dfs_limit = o.dfs_limit; p.max_indel_len = o.max_indel_len; p.max_mismatch = o.max_mismatch;
 	p.max_unit_len = o.max_unit_len; p.min_report_units = o.min_report_units; p.min_report_len = o.min_report_len; p.dist_from_str = o.dist_from_str; p.min_cov_ratio = o.cov_ratio;
 	lb2_ctx *ctx = nullptr;
-	int rc = lb2_create(&ctx, &p, o.gpu);
+	int rc = lb2_create(&ctx, &p, o.gpu + o.rank);
 	if (rc != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
-	vector<uint32_t> rank(names.size());
-	lb2_rank_names(names.data(), (uint32_t)names.size(), rank.data());
-	lb2_batch b; memset(&b, 0, sizeof b);
-	b.n_windows = (uint32_t)ref_start.size(); b.n_reads = (uint32_t)flags.size(); b.n_wr = (uint32_t)wr_idx.size(); b.n_ref_bytes = ref_seq.size(); b.n_base_bytes = seq.size();
-	b.ref_off = ref_off.data(); b.ref_start = ref_start.data(); b.chr_id = chr_id.data(); b.wr_off = wr_off.data(); b.wr_idx = wr_idx.data(); b.base_off = base_off.data();
-	b.flags = flags.data(); b.name_rank = rank.data(); b.ref_seq = ref_seq.data(); b.seq = seq.data(); b.qual = qual.data();
-	lb2_result res; memset(&res, 0, sizeof res);
-	if (b.n_windows) {
-		rc = lb2_process(ctx, &b, &res);
-		if (rc != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
+	if (o.world > 1) {
+		char id[LB2_COMM_ID_BYTES]; std::ifstream idf(o.nccl_id_file, std::ios::binary);
+		if (!idf.read(id, sizeof id) || (rc = lb2_comm_init(ctx, id, o.rank, o.world)) != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": NCCL set-up failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
 	}
-	{	// a window the device could not assemble would be missing from the VCF without a trace: that is an error, not a warning
-		uint32_t n_failed = 0;
-		for (uint32_t w = 0; w < res.n_windows; ++w) {
-			if (res.windows[w].status >= LB2_WIN_OVERFLOW) {
-				++n_failed;
-				std::cerr << "ERROR: window " << wins[win_of_batch[w]].hdr << " not assembled on the device (status " << (int)res.windows[w].status << ", detail " << res.windows[w].detail << ")" << std::endl;
+
+	// ---- this rank's windows, in batches: fetch the reads of the batch's span once per sample (BAI), select per window ----
+	const size_t wlo = wins.size() * (size_t)o.rank / (size_t)o.world, whi = wins.size() * (size_t)(o.rank + 1) / (size_t)o.world;
+	struct Pinned {      // a growable page-locked array (the copies to the GPU then overlap the assembly, include/lancet_b200.h)
+		void *p = nullptr; size_t cap = 0;
+		void *need(size_t bytes, size_t keep = 0) { if (bytes > cap) { size_t nc = std::max(bytes + bytes / 2, (size_t)4096); void *q = lb2_alloc_pinned(nc); if (!q) { std::cerr << "ERROR: out of page-locked memory" << std::endl; exit(2); } if (keep) { memcpy(q, p, keep); } if (p) { lb2_free_pinned(p); } p = q; cap = nc; } return p; }
+		~Pinned() { if (p) { lb2_free_pinned(p); } }
+	};
+	struct HostBatch {
+		Pinned ref_off, ref_start, chr_id, wr_off, wr_idx, base_off, flags, name_rank, ref_seq, seq, qual;
+		vector<uint32_t> win_of_batch; uint32_t n_windows = 0, n_reads = 0; uint64_t n_wr = 0, n_ref = 0, n_base = 0; int skipped = 0; bool last = false;
+	};
+	auto ref_id = [](const BamFile &b, const string &chr) { for (size_t i = 0; i < b.ref_names.size(); ++i) { if (b.ref_names[i] == chr) { return (int)i; } } return -1; };
+	auto usable = [&](const Aln &al, int sample) -> bool {      // the filters of extractReads that do not depend on the window (src/Microassembler.cc:505-616)
+		const int MQ = sample ? 0 : o.min_map_qual; const int MIN_DELTA = sample ? -1 : 5;       // MAX_DELTA_AS_XS is 5 whatever -Z says
+		if (o.primary_only && (al.flag & 0x100)) { return false; }
+		if (!(al.mapq >= MQ && !(al.flag & 0x400))) { return false; }
+		const float delta = std::fabs(al.as - al.xs);
+		if (delta <= MIN_DELTA && al.as != -1 && al.xs != -1) { return false; }
+		if (al.xt == "R" && !sample) { return false; }
+		if (!al.xa.empty() && !sample && o.xa_filter) { return false; }
+		return true;
+	};
+	auto build_batch = [&](size_t a, size_t b, HostBatch &hb) {
+		hb.win_of_batch.clear(); hb.skipped = 0;
+		int left_all = INT32_MAX, right_all = 0; for (size_t wi = a; wi < b; ++wi) { left_all = std::min(left_all, wins[wi].refstart); right_all = std::max(right_all, wins[wi].refend); }
+		const string &chr = wins[a].chr;
+		vector<Aln> A[2];
+		if (!T.fetch(ref_id(T, chr), left_all, right_all, A[0]) || !N.fetch(ref_id(N, chr), left_all, right_all, A[1])) { std::cerr << "ERROR: cannot read the BAM files (truncated or corrupt?)" << std::endl; exit(2); }
+		// the pool: every usable alignment of the span once, tumour first
+		vector<int64_t> pool_of[2]; uint32_t n_reads = 0; uint64_t n_base = 0;
+		for (int s_ = 0; s_ < 2; ++s_) { pool_of[s_].assign(A[s_].size(), -1); for (size_t i = 0; i < A[s_].size(); ++i) { if (usable(A[s_][i], s_)) { pool_of[s_][i] = n_reads++; n_base += A[s_][i].seq.size(); } } }
+		uint64_t *base_off = (uint64_t *)hb.base_off.need(8 * ((size_t)n_reads + 1)); uint8_t *flags = (uint8_t *)hb.flags.need(n_reads + 1); uint32_t *rank = (uint32_t *)hb.name_rank.need(4 * ((size_t)n_reads + 1));
+		char *seq = (char *)hb.seq.need(n_base + 64), *qual = (char *)hb.qual.need(n_base + 64);
+		vector<const char *> names(n_reads); uint64_t bo = 0; base_off[0] = 0;
+		for (int s_ = 0; s_ < 2; ++s_) {
+			for (size_t i = 0; i < A[s_].size(); ++i) {
+				const int64_t r = pool_of[s_][i]; if (r < 0) { continue; }
+				const Aln &al = A[s_][i];
+				int mate = (al.flag & 0x40) ? 1 : 0; if (al.flag & 0x80) { mate = 2; }
+				flags[r] = (uint8_t)((s_ ? LB2_READ_NORMAL : 0) | ((al.flag & 0x10) ? LB2_READ_REVERSE : 0) | (uint8_t)(mate << LB2_READ_MATE_SHIFT) | ((al.flag & 0x4) ? LB2_READ_UNMAPPED : 0));
+				names[r] = al.name.c_str();
+				memcpy(seq + bo, al.seq.data(), al.seq.size());
+				if (al.qual.empty()) { memset(qual + bo, (char)(0xFF + 33), al.seq.size()); } else { memcpy(qual + bo, al.qual.data(), al.seq.size()); }
+				bo += al.seq.size(); base_off[r + 1] = bo;
 			}
 		}
-		if (n_failed) { std::cerr << "ERROR: " << n_failed << " window(s) not assembled; no VCF written" << std::endl; lb2_destroy(ctx); return 3; }
+		lb2_rank_names(names.data(), n_reads, rank);
+		uint32_t *ref_off = (uint32_t *)hb.ref_off.need(4 * (b - a + 1)), *wr_off = (uint32_t *)hb.wr_off.need(4 * (b - a + 1)), *chr_id = (uint32_t *)hb.chr_id.need(4 * (b - a + 1));
+		int32_t *ref_start = (int32_t *)hb.ref_start.need(4 * (b - a + 1));
+		uint32_t nw = 0; uint64_t n_wr = 0, n_ref = 0; ref_off[0] = 0; wr_off[0] = 0;
+		for (size_t wi = a; wi < b; ++wi) {
+			const Window &w = wins[wi];
+			if (w.raw.empty()) { continue; }
+			const int left = w.refstart, right = w.refend;      // 1-based numbers used as a 0-based half-open BAM region (reference quirk B9)
+			size_t lo[2], hi[2];
+			for (int s_ = 0; s_ < 2; ++s_) {
+				lo[s_] = std::lower_bound(A[s_].begin(), A[s_].end(), left, [](const Aln &x, int v) { return x.pos < v; }) - A[s_].begin();
+				hi[s_] = std::lower_bound(A[s_].begin(), A[s_].end(), right, [](const Aln &x, int v) { return x.pos < v; }) - A[s_].begin();
+			}
+			bool activeT = true, activeN = true;
+			if (o.active_regions) { activeT = is_active(A[0], lo[0], hi[0], left, right, false, o); activeN = is_active(A[1], lo[1], hi[1], left, right, true, o); }
+			if (!(activeT || activeN)) { ++hb.skipped; continue; }
+			const uint64_t wr0 = n_wr; bool skip = false;
+			uint32_t *wr_idx = (uint32_t *)hb.wr_idx.need(4 * (n_wr + (hi[0] - lo[0]) + (hi[1] - lo[1]) + 1), 4 * n_wr);
+			for (int s_ = 0; s_ < 2 && !skip; ++s_) {
+				long totalbp = 0;
+				for (size_t i = lo[s_]; i < hi[s_]; ++i) {
+					const Aln &al = A[s_][i];
+					if ((double)totalbp / (double)w.raw.length() > o.max_avg_cov) { skip = true; break; }
+					if (al.pos < left || al.end > right) { continue; }
+					if (pool_of[s_][i] < 0) { continue; }
+					wr_idx[n_wr++] = (uint32_t)pool_of[s_][i];
+					totalbp += (long)al.seq.length();
+				}
+			}
+			if (skip) {      // "Too much coverage": the window is dropped
+				std::cerr << "WARNING: Skip region " << w.chr << ":" << w.refstart << "-" << w.refend << ". Too much coverage (>" << o.max_avg_cov << "x)." << std::endl;
+				n_wr = wr0; ++hb.skipped; continue;
+			}
+			if (n_wr > 0xFFFFFFF0ull || n_ref + w.raw.size() > 0xFFFFFFF0ull) { std::cerr << "ERROR: batch too large for 32-bit offsets (lower --batch-windows)" << std::endl; exit(2); }
+			char *rs = (char *)hb.ref_seq.need(n_ref + w.raw.size() + 64, n_ref); memcpy(rs + n_ref, w.raw.data(), w.raw.size()); n_ref += w.raw.size();
+			ref_start[nw] = w.refstart; chr_id[nw] = 0; ++nw; ref_off[nw] = (uint32_t)n_ref; wr_off[nw] = (uint32_t)n_wr;
+			hb.win_of_batch.push_back((uint32_t)wi);
+		}
+		hb.wr_idx.need(4 * (n_wr + 1), 4 * n_wr); hb.ref_seq.need(n_ref + 64, n_ref);
+		hb.n_windows = nw; hb.n_reads = n_reads; hb.n_wr = n_wr; hb.n_ref = n_ref; hb.n_base = n_base;
+	};
+	// batches of consecutive windows on one chromosome; a producer thread reads and selects for batch i+1 while the GPU assembles batch i
+	vector<std::pair<size_t, size_t>> spans;
+	for (size_t a = wlo; a < whi; ) { size_t b = a; while (b < whi && b - a < (size_t)o.batch_windows && wins[b].chr == wins[a].chr) { ++b; } spans.push_back(std::make_pair(a, b)); a = b; }
+	HostBatch slots[2]; std::mutex mu; std::condition_variable cv; int filled[2] = { 0, 0 };      // 0 free, 1 ready
+	std::thread producer([&]() {
+		for (size_t i = 0; i < spans.size(); ++i) {
+			HostBatch &hb = slots[i & 1];
+			{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[i & 1] == 0; }); }
+			build_batch(spans[i].first, spans[i].second, hb);
+			{ std::lock_guard<std::mutex> lk(mu); filled[i & 1] = 1; } cv.notify_all();
+		}
+	});
+	vector<lb2_variant> vars; string strs; int tot_skip = 0; uint32_t n_failed = 0;      // this rank's records: window = index into wins, str_off into strs
+	for (size_t i = 0; i < spans.size(); ++i) {
+		HostBatch &hb = slots[i & 1];
+		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[i & 1] == 1; }); }
+		tot_skip += hb.skipped;
+		if (hb.n_windows) {
+			lb2_batch b; memset(&b, 0, sizeof b);
+			b.n_windows = hb.n_windows; b.n_reads = hb.n_reads; b.n_wr = (uint32_t)hb.n_wr; b.n_ref_bytes = hb.n_ref; b.n_base_bytes = hb.n_base;
+			b.ref_off = (const uint32_t *)hb.ref_off.p; b.ref_start = (const int32_t *)hb.ref_start.p; b.chr_id = (const uint32_t *)hb.chr_id.p; b.wr_off = (const uint32_t *)hb.wr_off.p;
+			b.wr_idx = (const uint32_t *)hb.wr_idx.p; b.base_off = (const uint64_t *)hb.base_off.p; b.flags = (const uint8_t *)hb.flags.p; b.name_rank = (const uint32_t *)hb.name_rank.p;
+			b.ref_seq = (const char *)hb.ref_seq.p; b.seq = (const char *)hb.seq.p; b.qual = (const char *)hb.qual.p;
+			lb2_result res; memset(&res, 0, sizeof res);
+			rc = lb2_process(ctx, &b, &res);
+			if (rc != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc) << std::endl; _exit(2); }
+			for (uint32_t w = 0; w < res.n_windows; ++w) {      // a window the device could not assemble would be missing from the VCF without a trace: an error, not a warning
+				if (res.windows[w].status >= LB2_WIN_OVERFLOW) {
+					++n_failed;
+					std::cerr << "ERROR: window " << wins[hb.win_of_batch[w]].hdr << " not assembled on the device (status " << (int)res.windows[w].status << ", detail " << res.windows[w].detail << ")" << std::endl;
+				}
+			}
+			const size_t s0 = strs.size(); strs.append(res.strings, res.n_string_bytes);
+			for (uint32_t k = 0; k < res.n_variants; ++k) { lb2_variant v = res.variants[k]; v.window = hb.win_of_batch[v.window]; v.str_off += (uint32_t)s0; vars.push_back(v); }
+		}
+		{ std::lock_guard<std::mutex> lk(mu); filled[i & 1] = 0; } cv.notify_all();
 	}
+	producer.join();
+
+	// ---- gather on rank 0 (several GPUs) ------------------------------------------------------------------------------
+	const lb2_variant *all_v = vars.data(); const char *all_s = strs.data(); uint32_t all_n = (uint32_t)vars.size();
+	if (o.world > 1) {
+		uint64_t stats[2] = { (uint64_t)tot_skip, (uint64_t)n_failed }; lb2_result merged; memset(&merged, 0, sizeof merged);
+		rc = lb2_comm_gather(ctx, vars.data(), (uint32_t)vars.size(), strs.data(), (uint64_t)strs.size(), stats, 2, 0, &merged);
+		if (rc != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": record gather failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
+		if (!lead) { lb2_destroy(ctx); return n_failed ? 3 : 0; }
+		all_v = merged.variants; all_s = merged.strings; all_n = merged.n_variants; tot_skip = (int)stats[0]; n_failed = (uint32_t)stats[1];
+	}
+	std::cerr << "Total # of skipped windows: " << tot_skip << std::endl;
+	int child_bad = 0;
+	for (pid_t c : children) { int st = 0; waitpid(c, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { ++child_bad; } }
+	if (!o.nccl_id_file.empty() && !children.empty()) { unlink(o.nccl_id_file.c_str()); }
+	if (n_failed || child_bad) { std::cerr << "ERROR: " << n_failed << " window(s) not assembled" << (child_bad ? ", a rank failed" : "") << "; no VCF written" << std::endl; lb2_destroy(ctx); return 3; }
 
 	// ---- replay addVar in the reference's order: thread, then lexicographic window header, then emission ----------------
 	vector<vector<uint32_t>> per_window(wins.size());
-	for (uint32_t i = 0; i < res.n_variants; ++i) { per_window[win_of_batch[res.variants[i].window]].push_back(i); }
+	for (uint32_t i = 0; i < all_n; ++i) { per_window[all_v[i].window].push_back(i); }
 	vector<VariantDB> tdb(o.num_threads);
 	for (int th = 0; th < o.num_threads; ++th) {
 		vector<uint32_t> mine; for (size_t wi = 0; wi < wins.size(); ++wi) { if (wins[wi].thread == th) { mine.push_back((uint32_t)wi); } }
 		std::sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t c) { return wins[a].hdr < wins[c].hdr; });      // std::map<string,Ref_t*> order
 		for (uint32_t wi : mine) {
 			for (uint32_t i : per_window[wi]) {
-				const lb2_variant &v = res.variants[i]; const char *s = res.strings + v.str_off;
-				string ref(s, v.ref_len), alt(s + v.ref_len, v.alt_len), motif(s + v.ref_len + v.alt_len, v.motif_len);
+				const lb2_variant &v = all_v[i]; const char *s_ = all_s + v.str_off;
+				string ref(s_, v.ref_len), alt(s_ + v.ref_len, v.alt_len), motif(s_ + v.ref_len + v.alt_len, v.motif_len);
 				string str = v.str_len ? itos(v.str_len) + motif : string();
 				tdb[th].add(Variant(wins[wi].chr, v.pos, ref, alt, v, str));
 			}

@@ -560,7 +560,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	if (tid == 0) {
 		uint32_t cum = kcum;
 		ws.rd_kbase[R] = cum;
-		sh->n_used = 0; sh->err = 0; sh->n_spec = 0; sh->flag_a = 0;
+		sh->n_used = 0; sh->err = 0; sh->n_spec = 0; sh->flag_a = 0; sh->n_nk = 0; sh->n_refitems = 0;
 		sh->K = K; sh->nw = nw;
 		// up to four pieces per read, none shorter than 16 pairs (every piece re-derives its first k-mer)
 		{ const uint32_t mp = sh->maxnk > 1 ? sh->maxnk - 1 : 1u; uint32_t np_ = mp / 16u; if (np_ < 1) { np_ = 1; } if (np_ > 4) { np_ = 4; }
@@ -640,7 +640,6 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	//      of everything else.  Here: canonical form on the ASCII window (rrc('N') = 'N', 'G' < 'N' < 'T'), std::hash of
 	//      it, first occurrence of every distinct one; they join the dense nodes below as dead nodes without a table slot.
 	uint64_t *const nkh = (uint64_t *)ws.mates; uint8_t *const nkf = (uint8_t *)(nkh + LB2_MAX_REF);      // (the mate lists are idle until the replay)
-	if (tid == 0) { sh->n_nk = 0; }
 	if (refN) {
 		const char *const RR = W.ref_raw;
 		auto canon_at = [&](uint32_t o, uint32_t ori, uint32_t i) -> char { return ori ? lb2_comp(RR[o + (uint32_t)K - 1u - i]) : RR[o + i]; };

@@ -6,6 +6,7 @@
 // staged from the packed pool into shared memory by bulk-async copies.  No CPU fallback exists in this file: every
 // entry point fails with LB2_ERR_CUDA when there is no usable device.
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,40 +67,22 @@ lb2_window_kernel(const __grid_constant__ lb2_launch L)
 	}
 }
 
-// ---- the pre-pack pass over pool reads [r0, r1): word counts per block of LB2_PACK_BLOCK reads, their exclusive scan
-// ---- (continuing from *carry, the words of the reads packed before), then the pass itself
+// ---- the pre-pack pass over pool reads [r0, r1), r0 a multiple of LB2_PACK_BLOCK: one block per LB2_PACK_BLOCK reads;
+// blk[b] = packed words of all pool reads before the block's first read (prefix sums made by the host while it plans
+// the batch).  128 threads and 32 registers on purpose: one such block fits into what three resident window CTAs leave
+// of an SM (4096 registers, 6.9 KB shared memory), so the pass over the next upload segment runs beside the window
+// kernel of the current one instead of waiting for its CTAs to drain.
 #define LB2_PACK_BLOCK 1024
-__global__ void __launch_bounds__(256) lb2_pack_count_kernel(const uint64_t *base_off, uint32_t r0, uint32_t r1, uint32_t *blk)
-{
-	__shared__ uint32_t sc[40];
-	const uint32_t r = r0 + blockIdx.x * LB2_PACK_BLOCK + threadIdx.x * 4u; uint32_t sum = 0;
-	for (uint32_t q = 0; q < 4; ++q) { if (r + q < r1) { sum += lb2_pack_nwords(base_off[r + q + 1] - base_off[r + q]); } }
-	uint32_t total = 0; lb2_block_excl(sc, sum, &total);
-	if (threadIdx.x == 0) { blk[blockIdx.x] = total; }
-}
-__global__ void __launch_bounds__(1024) lb2_pack_scan_kernel(uint32_t *blk, uint32_t nblk, uint32_t *carry)
-{
-	__shared__ uint32_t sc[40]; __shared__ uint32_t s_base;
-	if (threadIdx.x == 0) { s_base = *carry; }
-	__syncthreads();
-	for (uint32_t i0 = 0; i0 < nblk; i0 += blockDim.x) {
-		const uint32_t i = i0 + threadIdx.x, v = i < nblk ? blk[i] : 0u; uint32_t tot = 0;
-		const uint32_t ex = lb2_block_excl(sc, v, &tot);
-		if (i < nblk) { blk[i] = s_base + ex; }
-		__syncthreads();
-		if (threadIdx.x == 0) { s_base += tot; }
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) { *carry = s_base; }
-}
-__global__ void __launch_bounds__(256) lb2_pack_kernel(const lb2_dev_batch B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4,
-                                                      uint32_t r0, uint32_t r1, const uint32_t *blk)
+#define LB2_PACK_THREADS 128
+__global__ void __launch_bounds__(LB2_PACK_THREADS, 16) lb2_pack_kernel(const lb2_dev_batch B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4,
+                                                                        uint32_t r0, uint32_t r1, const uint32_t *blk)
 {
 	__shared__ uint32_t sc[40]; __shared__ uint32_t s_w[LB2_PACK_BLOCK];
-	const uint32_t rb = r0 + blockIdx.x * LB2_PACK_BLOCK, t = threadIdx.x; uint32_t cnt[4], sum = 0;
-	for (uint32_t q = 0; q < 4; ++q) { const uint32_t r = rb + t * 4u + q; cnt[q] = (r < r1) ? lb2_pack_nwords(B.base_off[r + 1] - B.base_off[r]) : 0u; sum += cnt[q]; }
+	constexpr uint32_t PER = LB2_PACK_BLOCK / LB2_PACK_THREADS;
+	const uint32_t rb = r0 + blockIdx.x * LB2_PACK_BLOCK, t = threadIdx.x; uint32_t sum = 0;
+	for (uint32_t q = 0; q < PER; ++q) { const uint32_t r = rb + t * PER + q; const uint32_t c = (r < r1) ? lb2_pack_nwords(B.base_off[r + 1] - B.base_off[r]) : 0u; s_w[t * PER + q] = c; sum += c; }
 	uint32_t total = 0, ex = lb2_block_excl(sc, sum, &total) + blk[blockIdx.x];
-	for (uint32_t q = 0; q < 4; ++q) { s_w[t * 4u + q] = ex; ex += cnt[q]; }
+	for (uint32_t q = 0; q < PER; ++q) { const uint32_t c = s_w[t * PER + q]; s_w[t * PER + q] = ex; ex += c; }
 	__syncthreads();
 	// a group of LB2_GS lanes per read, neighbouring groups on neighbouring reads (every lane of a warp runs every round)
 	for (uint32_t j = lb2_group(); j < LB2_PACK_BLOCK; j += lb2_ngroups()) {
@@ -188,11 +171,15 @@ struct lb2_ctx {
 	size_t ws_stride = 0; uint32_t ws_slots = 0, ws_sets = 0; size_t ws2_stride = 0; uint32_t ws2_slots = 0;
 	lb2_cfg C2;
 	std::vector<uint32_t> h_need;        // per window: leading pool reads the windows up to it use
+	uint32_t *h_blk = nullptr; size_t h_blk_cap = 0;      // (page-locked) packed words before every block of LB2_PACK_BLOCK pool reads
 	uint64_t launches = 0;
 	float kernel_ms = 0;
 	// host result
 	std::vector<lb2_window_info> h_info; std::vector<lb2_variant> h_vars; std::vector<char> h_str;
 	uint64_t h2d_bytes = 0, d2h_bytes = 0;
+	// record gather across ranks (one process per GPU)
+	ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1; Buf d_comm_send, d_comm_recv, d_comm_cnt;
+	std::vector<lb2_variant> g_vars; std::vector<char> g_str;
 };
 enum { LB2_CTR_RETRY = 2 * LB2_MAX_SEG, LB2_CTR_BIG, LB2_CTR_CARRY, LB2_CTR_TOTALS, LB2_CTR_N = LB2_CTR_TOTALS + 2 };
 
@@ -231,6 +218,7 @@ extern "C" const char *lb2_kernel_version(void) { return LB2_KERNEL_VERSION; }
 
 static uint32_t env_u32(const char *name, uint32_t dflt) { const char *s = getenv(name); return s ? (uint32_t)strtoul(s, nullptr, 10) : dflt; }
 
+static void lb2_comm_release(ncclComm_t c);
 extern "C" void lb2_destroy(lb2_ctx *ctx)
 {
 	if (!ctx) { return; }
@@ -239,7 +227,9 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_pk, &ctx->d_pk_bits, &ctx->d_pk_lowq, &ctx->d_blk, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used,
 		&ctx->d_var_off, &ctx->d_str_off, &ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot, &ctx->d_ws2, &ctx->d_retry };
 	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
-	if (ctx->d_counters) { cudaFree(ctx->d_counters); } if (ctx->d_prof) { cudaFree(ctx->d_prof); }
+	if (ctx->comm) { lb2_comm_release(ctx->comm); }
+	{ lb2_ctx::Buf *cb[] = { &ctx->d_comm_send, &ctx->d_comm_recv, &ctx->d_comm_cnt }; for (auto b : cb) { if (b->p) { cudaFree(b->p); } } }
+	if (ctx->d_counters) { cudaFree(ctx->d_counters); } if (ctx->d_prof) { cudaFree(ctx->d_prof); } if (ctx->h_blk) { cudaFreeHost(ctx->h_blk); }
 	for (auto &e : ctx->ev) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_seg) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_w) { if (e) { cudaEventDestroy(e); } }
 	if (ctx->ev_ready) { cudaEventDestroy(ctx->ev_ready); }
 	if (ctx->stream) { cudaStreamDestroy(ctx->stream); } if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); }
@@ -293,6 +283,7 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	if (!ctx || !b) { return LB2_ERR_ARG; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
 	ctx->resident = false; ctx->ran = false;
+	cudaStreamSynchronize(ctx->stream);      // (work of an earlier batch may still read the buffers re-planned below)
 	const uint32_t W = b->n_windows, R = b->n_reads;
 	if ((W && (!b->ref_off || !b->ref_start || !b->wr_off)) || (R && (!b->base_off || !b->flags || !b->name_rank)) || (b->n_wr && !b->wr_idx)) { return LB2_ERR_ARG; }
 	uint32_t max_bp = 0, max_reads = 0;
@@ -325,6 +316,14 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 		else { std::vector<std::thread> th; for (unsigned t = 0; t < T; ++t) { th.emplace_back(work, t); } for (auto &x : th) { x.join(); } }
 		for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); }
 		uint32_t need = 0; for (uint32_t w = 0; w < W; ++w) { need = std::max(need, ctx->h_need[w]); ctx->h_need[w] = need; }
+	}
+	{	// packed words before every block of LB2_PACK_BLOCK reads (the pre-pack kernel's blocks start from these)
+		const size_t nblk = (size_t)R / LB2_PACK_BLOCK + 2;
+		if (nblk > ctx->h_blk_cap) { if (ctx->h_blk) { cudaFreeHost(ctx->h_blk); ctx->h_blk = nullptr; } LB2_CK(cudaHostAlloc((void **)&ctx->h_blk, sizeof(uint32_t) * (nblk + nblk / 2), cudaHostAllocDefault)); ctx->h_blk_cap = nblk + nblk / 2; }
+		uint64_t words = 0;
+		for (uint32_t r = 0; r < R; ++r) { if ((r % LB2_PACK_BLOCK) == 0) { ctx->h_blk[r / LB2_PACK_BLOCK] = (uint32_t)words; } words += lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]); }
+		ctx->h_blk[(size_t)(R + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK] = (uint32_t)words;
+		if (words > 0xFFFFFF00ull) { ctx->err = "read pool too large for 32-bit word offsets: split the batch"; return LB2_ERR_ARG; }
 	}
 	const uint32_t need_bp = std::min<uint32_t>((max_bp + 1023) & ~1023u, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
 	const uint32_t smem_cap = (uint32_t)std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : (227u << 10), 227u << 10) - 2048u;      // (static shared memory of the kernel comes on top)
@@ -364,7 +363,7 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	LB2_RS(d_wr_idx, sizeof(uint32_t) * (size_t)b->n_wr + 4); LB2_RS(d_base_off, sizeof(uint64_t) * (size_t)(R + 1)); LB2_RS(d_flags, (size_t)R + 4);
 	LB2_RS(d_name_rank, sizeof(uint32_t) * (size_t)R + 4); LB2_RS(d_ref_seq, (size_t)b->n_ref_bytes + 4); LB2_RS(d_seq, (size_t)b->n_base_bytes + 64); LB2_RS(d_qual, (size_t)b->n_base_bytes + 64);
 	const size_t pk_words = (size_t)(b->n_base_bytes / 16) + R + 64;
-	LB2_RS(d_pk, sizeof(lb2_pkread) * ((size_t)R + 1)); LB2_RS(d_pk_bits, 4 * pk_words); LB2_RS(d_pk_lowq, 2 * pk_words); LB2_RS(d_blk, sizeof(uint32_t) * ((size_t)R / LB2_PACK_BLOCK + 2 + LB2_MAX_SEG));
+	LB2_RS(d_pk, sizeof(lb2_pkread) * ((size_t)R + 1)); LB2_RS(d_pk_bits, 4 * pk_words); LB2_RS(d_pk_lowq, 2 * pk_words); LB2_RS(d_blk, sizeof(uint32_t) * ((size_t)R / LB2_PACK_BLOCK + 4));
 	LB2_RS(d_info, sizeof(lb2_window_info) * (size_t)W + 16); LB2_RS(d_vars, sizeof(lb2_variant) * (size_t)W * C.max_var + 64); LB2_RS(d_strs, (size_t)W * C.str_bytes + 64);
 	LB2_RS(d_str_used, sizeof(uint32_t) * (size_t)W + 4); LB2_RS(d_var_off, sizeof(uint32_t) * (size_t)W + 4); LB2_RS(d_str_off, sizeof(uint32_t) * (size_t)W + 4);
 	const uint32_t nbig = ctx->escalate ? std::min<uint32_t>(ctx->big_cap, std::max(W, 1u)) : 0u;
@@ -420,12 +419,12 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 static int lb2_enqueue_pack(lb2_ctx *ctx, uint32_t r0, uint32_t r1, cudaStream_t st)
 {
 	if (r1 <= r0) { return LB2_OK; }
-	const uint32_t nblk = (r1 - r0 + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK; uint32_t *blk = (uint32_t *)ctx->d_blk.p;
+	if (r0 % LB2_PACK_BLOCK) { return LB2_ERR_ARG; }
+	const uint32_t nblk = (r1 - r0 + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK, b0 = r0 / LB2_PACK_BLOCK; uint32_t *blk = (uint32_t *)ctx->d_blk.p;
 	const uint32_t qt = (uint32_t)ctx->P.min_qual_trim & 0xFFu, qc = (uint32_t)ctx->P.min_qual_call & 0xFFu;
-	lb2_pack_count_kernel<<<nblk, 256, 0, st>>>(ctx->L.B.base_off, r0, r1, blk);
-	lb2_pack_scan_kernel<<<1, 1024, 0, st>>>(blk, nblk, ctx->d_counters + LB2_CTR_CARRY);
-	lb2_pack_kernel<<<nblk, 256, 0, st>>>(ctx->L.B, (lb2_pkread *)ctx->d_pk.p, (uint32_t *)ctx->d_pk_bits.p, (uint16_t *)ctx->d_pk_lowq.p, qt * 0x01010101u, qc * 0x01010101u, r0, r1, blk);
-	ctx->launches += 3;
+	LB2_CK(cudaMemcpyAsync(blk + b0, ctx->h_blk + b0, sizeof(uint32_t) * nblk, cudaMemcpyHostToDevice, st));
+	lb2_pack_kernel<<<nblk, LB2_PACK_THREADS, 0, st>>>(ctx->L.B, (lb2_pkread *)ctx->d_pk.p, (uint32_t *)ctx->d_pk_bits.p, (uint16_t *)ctx->d_pk_lowq.p, qt * 0x01010101u, qc * 0x01010101u, r0, r1, blk + b0);
+	ctx->launches += 1;
 	LB2_CK(cudaGetLastError());
 	return LB2_OK;
 }
@@ -562,7 +561,8 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 				while (wb < W && (batch->base_off[ctx->h_need[wb]] <= lim || wb - wa < min_w)) { ++wb; }
 				if (W - wb < min_w) { wb = W; }
 			}
-			lb2_seg sg; sg.w0 = wa; sg.w1 = wb; sg.r0 = ra; sg.r1 = (wb == W) ? R : std::max(ra, ctx->h_need[wb - 1]);
+			lb2_seg sg; sg.w0 = wa; sg.w1 = wb; sg.r0 = ra;
+			sg.r1 = (wb == W) ? R : std::min<uint32_t>(R, (std::max(ra, ctx->h_need[wb - 1]) + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK * LB2_PACK_BLOCK);      // (whole pack blocks)
 			segs.push_back(sg); wa = wb; ra = sg.r1; chunk *= 2; lim = batch->base_off[ra] + chunk;
 		}
 	}
@@ -645,5 +645,108 @@ extern "C" int lb2_rank_names(const char *const *names, uint32_t n, uint32_t *ra
 	std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return strcmp(names[a], names[b]) < 0; });
 	uint32_t r = 0;
 	for (uint32_t i = 0; i < n; ++i) { if (i && strcmp(names[idx[i]], names[idx[i - 1]]) != 0) { ++r; } rank_out[idx[i]] = r; }
+	return LB2_OK;
+}
+
+// ---- record gather over NCCL (declared in include/lancet_b200.h) --------------------------------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2 on first use, the already loaded one if the process has one): a
+// process that also loads PyTorch must end up with ONE libnccl, and PyTorch ships its own.
+#include <dlfcn.h>
+namespace {
+struct lb2_nccl_api {
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr; ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr; const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr; ncclResult_t (*GroupEnd)() = nullptr;
+	bool ok = false;
+	lb2_nccl_api() {
+		void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+		if (!h) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); }
+		if (!h) { h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL); }
+		if (!h) { return; }
+#define LB2_SYM(f) do { *(void **)(&f) = dlsym(h, "nccl" #f); if (!f) { return; } } while (0)
+		LB2_SYM(GetUniqueId); LB2_SYM(CommInitRank); LB2_SYM(CommDestroy); LB2_SYM(GetErrorString); LB2_SYM(AllGather); LB2_SYM(Send); LB2_SYM(Recv); LB2_SYM(GroupStart); LB2_SYM(GroupEnd);
+#undef LB2_SYM
+		ok = true;
+	}
+};
+lb2_nccl_api &lb2_nccl() { static lb2_nccl_api api; return api; }
+}
+static void lb2_comm_release(ncclComm_t c) { if (lb2_nccl().ok) { lb2_nccl().CommDestroy(c); } }
+#define ncclGetUniqueId lb2_nccl().GetUniqueId
+#define ncclCommInitRank lb2_nccl().CommInitRank
+#define ncclGetErrorString lb2_nccl().GetErrorString
+#define ncclAllGather lb2_nccl().AllGather
+#define ncclSend lb2_nccl().Send
+#define ncclRecv lb2_nccl().Recv
+#define ncclGroupStart lb2_nccl().GroupStart
+#define ncclGroupEnd lb2_nccl().GroupEnd
+#define LB2_NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { ctx->err = std::string(#call) + ": " + ncclGetErrorString(r_); return LB2_ERR_CUDA; } } while (0)
+extern "C" int lb2_comm_unique_id(char *id_out)
+{
+	static_assert(sizeof(ncclUniqueId) <= LB2_COMM_ID_BYTES, "NCCL id does not fit");
+	if (!id_out) { return LB2_ERR_ARG; }
+	if (!lb2_nccl().ok) { return LB2_ERR_CUDA; }
+	ncclUniqueId id; if (ncclGetUniqueId(&id) != ncclSuccess) { return LB2_ERR_CUDA; }
+	memset(id_out, 0, LB2_COMM_ID_BYTES); memcpy(id_out, &id, sizeof id);
+	return LB2_OK;
+}
+extern "C" int lb2_comm_init(lb2_ctx *ctx, const char *id_in, int rank, int world)
+{
+	if (!ctx || !id_in || world < 1 || rank < 0 || rank >= world) { return LB2_ERR_ARG; }
+	if (!lb2_nccl().ok) { ctx->err = "libnccl.so.2 not found"; return LB2_ERR_CUDA; }
+	LB2_CK(cudaSetDevice(ctx->device));
+	if (ctx->comm) { lb2_nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+	ncclUniqueId id; memcpy(&id, id_in, sizeof id);
+	LB2_NC(ncclCommInitRank(&ctx->comm, world, id, rank));
+	ctx->comm_rank = rank; ctx->comm_world = world;
+	return LB2_OK;
+}
+extern "C" int lb2_comm_gather(lb2_ctx *ctx, const lb2_variant *vars, uint32_t n_vars, const char *strs, uint64_t n_str, uint64_t *stats, int n_stats, int root, lb2_result *merged)
+{
+	if (!ctx || !merged || n_stats < 0 || n_stats > 8 || (n_vars && !vars) || (n_str && !strs) || (n_stats && !stats)) { return LB2_ERR_ARG; }
+	if (!ctx->comm) { return LB2_ERR_STATE; }
+	LB2_CK(cudaSetDevice(ctx->device));
+	const int W = ctx->comm_world, me = ctx->comm_rank, M = 2 + n_stats; int rc;
+	if (root < 0 || root >= W) { return LB2_ERR_ARG; }
+	// counts of every rank: [records, string bytes, stats...]
+	if ((rc = lb2_reserve(ctx, ctx->d_comm_cnt, sizeof(uint64_t) * (size_t)M * W))) { return rc; }
+	std::vector<uint64_t> cnt((size_t)M * W, 0); uint64_t *mine = cnt.data() + (size_t)M * me;
+	mine[0] = n_vars; mine[1] = n_str; for (int i = 0; i < n_stats; ++i) { mine[2 + i] = stats[i]; }
+	uint64_t *d_cnt = (uint64_t *)ctx->d_comm_cnt.p;
+	LB2_CK(cudaMemcpyAsync(d_cnt + (size_t)M * me, mine, sizeof(uint64_t) * M, cudaMemcpyHostToDevice, ctx->stream));
+	LB2_NC(ncclAllGather(d_cnt + (size_t)M * me, d_cnt, (size_t)M, ncclUint64, ctx->comm, ctx->stream));
+	LB2_CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(uint64_t) * (size_t)M * W, cudaMemcpyDeviceToHost, ctx->stream));
+	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	// payloads: [records | strings] of every rank to root
+	auto bytes_of = [&](int r) -> size_t { return (size_t)cnt[(size_t)M * r] * sizeof(lb2_variant) + (((size_t)cnt[(size_t)M * r + 1] + 15) & ~(size_t)15); };
+	const size_t my_bytes = bytes_of(me);
+	if ((rc = lb2_reserve(ctx, ctx->d_comm_send, my_bytes + 16))) { return rc; }
+	if (n_vars) { LB2_CK(cudaMemcpyAsync(ctx->d_comm_send.p, vars, sizeof(lb2_variant) * (size_t)n_vars, cudaMemcpyHostToDevice, ctx->stream)); }
+	if (n_str) { LB2_CK(cudaMemcpyAsync((char *)ctx->d_comm_send.p + sizeof(lb2_variant) * (size_t)n_vars, strs, n_str, cudaMemcpyHostToDevice, ctx->stream)); }
+	std::vector<size_t> off(W + 1, 0); for (int r = 0; r < W; ++r) { off[r + 1] = off[r] + bytes_of(r); }
+	if (me == root) { if ((rc = lb2_reserve(ctx, ctx->d_comm_recv, off[W] + 16))) { return rc; } }
+	LB2_NC(ncclGroupStart());
+	if (me == root) {
+		for (int r = 0; r < W; ++r) { if (r != root && bytes_of(r)) { LB2_NC(ncclRecv((char *)ctx->d_comm_recv.p + off[r], bytes_of(r), ncclUint8, r, ctx->comm, ctx->stream)); } }
+	} else if (my_bytes) { LB2_NC(ncclSend(ctx->d_comm_send.p, my_bytes, ncclUint8, root, ctx->comm, ctx->stream)); }
+	LB2_NC(ncclGroupEnd());
+	memset(merged, 0, sizeof *merged);
+	if (me != root) { LB2_CK(cudaStreamSynchronize(ctx->stream)); return LB2_OK; }
+	if (my_bytes) { LB2_CK(cudaMemcpyAsync((char *)ctx->d_comm_recv.p + off[root], ctx->d_comm_send.p, my_bytes, cudaMemcpyDeviceToDevice, ctx->stream)); }
+	std::vector<char> raw(off[W]);
+	if (off[W]) { LB2_CK(cudaMemcpyAsync(raw.data(), ctx->d_comm_recv.p, off[W], cudaMemcpyDeviceToHost, ctx->stream)); }
+	LB2_CK(cudaStreamSynchronize(ctx->stream));
+	ctx->g_vars.clear(); ctx->g_str.clear();
+	for (int r = 0; r < W; ++r) {
+		const size_t nv = (size_t)cnt[(size_t)M * r], ns = (size_t)cnt[(size_t)M * r + 1]; const size_t sbase = ctx->g_str.size();
+		const lb2_variant *v = (const lb2_variant *)(raw.data() + off[r]);
+		for (size_t i = 0; i < nv; ++i) { lb2_variant x = v[i]; x.str_off += (uint32_t)sbase; ctx->g_vars.push_back(x); }
+		ctx->g_str.insert(ctx->g_str.end(), raw.data() + off[r] + nv * sizeof(lb2_variant), raw.data() + off[r] + nv * sizeof(lb2_variant) + ns);
+	}
+	for (int i = 0; i < n_stats; ++i) { uint64_t t = 0; for (int r = 0; r < W; ++r) { t += cnt[(size_t)M * r + 2 + i]; } stats[i] = t; }
+	merged->n_variants = (uint32_t)ctx->g_vars.size(); merged->variants = ctx->g_vars.data(); merged->strings = ctx->g_str.data(); merged->n_string_bytes = ctx->g_str.size();
 	return LB2_OK;
 }

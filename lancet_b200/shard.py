@@ -1,6 +1,9 @@
 """Multi-GPU plumbing of the window-sharded path: windows are independent, so each rank owns a
-contiguous range of the global window index and the only exchange is the final gather of variant records to rank 0
-(counts first, then padded payloads; works on NCCL and on gloo).  No collective sits on the per-window path."""
+contiguous range of the global window index and the only exchange is the final gather of variant records to rank 0.
+On GPUs that gather is the C ABI's lb2_comm_gather (NCCL: ncclAllGather of counts, ncclSend/ncclRecv of the payloads;
+`init_comm` hands the NCCL id round through torch.distributed); `gather_records` is the same exchange on a
+torch.distributed group (gloo on CPU: the host logic of tests/test_shard_gloo.py).  No collective sits on the
+per-window path."""
 from __future__ import annotations
 
 import numpy as np
@@ -48,3 +51,12 @@ def gather_records(variants: np.ndarray, strings: bytes, window_offset: int, dev
         a["str_off"] += soff
         vs.append(a); ss.append(h[mv:mv + ns].tobytes()); soff += ns
     return np.concatenate(vs) if vs else variants[:0], b"".join(ss)
+
+
+def init_comm(ctx, device=None):
+    """bind the context's NCCL communicator to the torch.distributed world (rank 0 creates the id, everybody gets it)"""
+    from .api import comm_unique_id
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, device=device)
+    ctx.comm_init(box[0], rank, world)

@@ -65,3 +65,10 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *b, lb2_result *res)
 	res->strings = ctx->strs.data(); res->n_string_bytes = ctx->strs.size(); res->kernel_ms = 0;
 	return LB2_OK;
 }
+
+// page-locked memory and the multi-rank gather have no meaning in the one-thread simulation
+extern "C" void *lb2_alloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 1); }
+extern "C" void lb2_free_pinned(void *p) { free(p); }
+extern "C" int lb2_comm_unique_id(char *) { return LB2_ERR_CUDA; }
+extern "C" int lb2_comm_init(lb2_ctx *, const char *, int, int) { return LB2_ERR_CUDA; }
+extern "C" int lb2_comm_gather(lb2_ctx *, const lb2_variant *, uint32_t, const char *, uint64_t, uint64_t *, int, int, lb2_result *) { return LB2_ERR_CUDA; }

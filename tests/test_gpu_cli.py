@@ -41,7 +41,12 @@ LIVE = {
                                                           "--min-alt-count-tumor", "4", "--min-base-qual", "20", "--min-map-qual", "20"]),
     "err1": (dict(seed=109, chroms=(("chr22", 6000),), err=0.01), ["--reg", "chr22:1-6000", "--num-threads", "2"]),
     "odd": (dict(seed=111, chroms=(("chr22", 6000),), odd_frac=0.5), ["--reg", "chr22", "--num-threads", "2"]),
+    # a run of N in the reference: the windows over it are assembled on the device like any other (no "unsupported" exit)
+    "nref": (dict(seed=112, chroms=(("chr22", 6000),), n_in_ref=True), ["--reg", "chr22:1-6000", "--num-threads", "2"]),
+    # many small batches (one lb2_process call each, the reads of a batch's span fetched through the BAI), two chromosomes
+    "batches": (dict(seed=113, chroms=(("chr21", 5000), ("chr22", 9000))), ["--reg", "chr22:1-9000", "--num-threads", "3"]),
 }
+OURS_ONLY = {"batches": ["--batch-windows", "11", "--io-threads", "3"]}      # options the reference does not have
 
 
 @pytest.mark.parametrize("name", sorted(LIVE))
@@ -52,7 +57,33 @@ def test_cli_live_reference(name, tmp_path):
     kw, args = LIVE[name]
     d = simbam.write_dataset(str(tmp_path / name), **kw)
     want, _ = _run(REFCLI, d, args)
-    got, err = _run(CLI, d, args)
+    got, err = _run(CLI, d, args + OURS_ONLY.get(name, []))
     assert "not assembled" not in err
     assert got == want
     assert sum(1 for l in want.splitlines() if not l.startswith("#")) > 5
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("ngpu", [2, 4])
+def test_cli_multi_gpu(ngpu, tmp_path):
+    """--gpus N: one process per GPU, each assembles a contiguous range of the windows, the records are gathered on rank 0
+    over NCCL and replayed in the reference's order -- the VCF is the one the reference writes for the same --num-threads."""
+    if _gpu_count() < ngpu:
+        pytest.skip(f"needs {ngpu} GPUs")
+    if not (os.path.exists(REFCLI) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "test_view"))):
+        pytest.skip("compiled reference not present")
+    from lancet_b200 import simbam
+    d = simbam.write_dataset(str(tmp_path / "mg"), seed=131, chroms=(("chr22", 30000),), var_every=400, som_every=900)
+    args = ["--reg", "chr22:1-30000", "--num-threads", "4"]
+    want, _ = _run(REFCLI, d, args, timeout=600)
+    got, err = _run(CLI, d, args + ["--gpus", str(ngpu), "--batch-windows", "64"], timeout=600)
+    assert "not assembled" not in err
+    assert got == want
+    assert sum(1 for l in want.splitlines() if not l.startswith("#")) > 50
