@@ -821,7 +821,7 @@ int main(int argc, char **argv)
 		uint64_t stats[2] = { (uint64_t)tot_skip, (uint64_t)n_failed }; lb2_result merged; memset(&merged, 0, sizeof merged);
 		rc = lb2_comm_gather(ctx, vars.data(), (uint32_t)vars.size(), strs.data(), (uint64_t)strs.size(), stats, 2, 0, &merged);
 		if (rc != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": record gather failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
-		if (!lead) { lb2_destroy(ctx); return n_failed ? 3 : 0; }
+		if (!lead) { fflush(nullptr); _exit(n_failed ? 3 : 0); }      // (no communicator teardown here: rank 0 is still busy and tears its side down alone)
 		all_v = merged.variants; all_s = merged.strings; all_n = merged.n_variants; tot_skip = (int)stats[0]; n_failed = (uint32_t)stats[1];
 	}
 	std::cerr << "Total # of skipped windows: " << tot_skip << std::endl;

@@ -175,20 +175,46 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 	if (sh->status != LB2_WIN_OK) { return; }
 	{	// does any query name occur with both mate orders?  (otherwise hasOverlappingMate can never fire)
 		// open-addressing set of name ranks in the (idle) table region, two mate-order bits per entry
-		uint32_t *hs = (uint32_t *)W.treg; const uint32_t TS = W.C->table_slots, hmask = TS - 1;
+		// ... and which read is whose mate: rd_mate[r] = the window's other read of the same name (LB2_NIL: none).  A name that
+		// occurs more than twice, or twice with the same mate order, makes the window "complex" (has_pairs = 2: the replay
+		// then takes no shortcut)
+		uint32_t *hs = (uint32_t *)W.treg; const uint32_t TS = W.C->table_slots, hmask = TS - 1; uint16_t *hi = (uint16_t *)(hs + TS);
 		for (uint32_t i = tid; i < TS; i += nt) { hs[i] = 0xFFFFFFFFu; }
+		for (uint32_t r = tid; r < R; r += nt) { ws.rd_mate[r] = LB2_NIL; }
 		lb2_sync();
-		if (2 * R > TS) { if (tid == 0) { sh->has_pairs = 1; } }      // (would not fit: run the replay unconditionally, it is exact either way)
+		if (2 * R > TS || R > 0xFFF0u) { if (tid == 0) { lb2_max32(&sh->has_pairs, 2u); } }      // (would not fit: run the full replay unconditionally, it is exact either way)
 		else {
-			for (uint32_t r = tid; r < R; r += nt) {
+			for (uint32_t r = tid; r < R; r += nt) {      // first read of every name claims a slot
 				const uint32_t mate = (ws.rd_info[r] >> 2) & 3u; if (mate != 1 && mate != 2) { continue; }
 				const uint32_t rank = ws.rd_rank[r];
-				if (rank >= 0x3FFFFFFFu) { sh->has_pairs = 1; continue; }
+				if (rank >= 0x3FFFFFFFu) { lb2_max32(&sh->has_pairs, 2u); continue; }
 				uint32_t h = (rank * 2654435761u) & hmask;
 				for (uint32_t probes = 0; probes <= hmask; ++probes) {
 					uint32_t cur = lb2_ld32(&hs[h]);
-					if (cur == 0xFFFFFFFFu) { cur = lb2_cas32(&hs[h], 0xFFFFFFFFu, (rank << 2) | mate); if (cur == 0xFFFFFFFFu) { break; } }
-					if ((cur >> 2) == rank) { if ((cur & 3u) != mate) { sh->has_pairs = 1; } break; }
+					if (cur == 0xFFFFFFFFu) { cur = lb2_cas32(&hs[h], 0xFFFFFFFFu, (rank << 2) | mate); if (cur == 0xFFFFFFFFu) { hi[h] = (uint16_t)r; break; } }
+					if ((cur >> 2) == rank) { break; }
+					h = (h + 1) & hmask;
+				}
+			}
+			lb2_sync();
+			for (uint32_t r = tid; r < R; r += nt) {      // every other read of the name meets the first one
+				const uint32_t mate = (ws.rd_info[r] >> 2) & 3u; if (mate != 1 && mate != 2) { continue; }
+				const uint32_t rank = ws.rd_rank[r]; if (rank >= 0x3FFFFFFFu) { continue; }
+				uint32_t h = (rank * 2654435761u) & hmask;
+				for (uint32_t probes = 0; probes <= hmask; ++probes) {
+					const uint32_t cur = lb2_ld32(&hs[h]);
+					if (cur == 0xFFFFFFFFu) { break; }
+					if ((cur >> 2) == rank) {
+						const uint32_t r0 = hi[h];
+						if (r0 != r) {
+							if ((cur & 3u) == mate) { lb2_max32(&sh->has_pairs, 2u); }
+							else {
+								if (lb2x_cas32(&ws.rd_mate[r0], LB2_NIL, r) != LB2_NIL) { lb2_max32(&sh->has_pairs, 2u); }      // a third read of that name
+								ws.rd_mate[r] = r0; lb2_max32(&sh->has_pairs, 1u);
+							}
+						}
+						break;
+					}
 					h = (h + 1) & hmask;
 				}
 			}
@@ -215,6 +241,7 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 //               ibase + offset * istride: transposed (offset-major) so that the lanes of a warp -- one read each, same
 //               offset -- store to consecutive words; read-major when the transposed array would not fit
 // ---------------------------------------------------------------------------------------------
+#define LB2_SEEN_WORDS 64         /* reads per window (x32) the mate replay can take its shortcut for */
 #define LB2_EM_NORMAL 0x100u
 #define LB2_EM_TUMOR  0x200u
 #define LB2_ID_BRANCH 0x8000u
@@ -733,7 +760,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		// reads (about the same number of occurrences each), counts its occurrences per node, the per-(warp, node) counts
 		// are turned into first positions (node's start + the counts of the warps before), and the warp then walks its
 		// reads again, 32 consecutive occurrences at a time, handing out positions in order (lanes holding the same node
-		// rank themselves by lane number: __match_any).  occ[pos] = read-major occurrence number.
+		// rank themselves by lane number: __match_any).  occ[pos] = read << 12 | offset.
 		const uint32_t total = ws.rd_kbase[R];
 		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
 		uint32_t *occ = (uint32_t *)ws.sortk, *wcnt = ws.bseq;      // (bseq: 8 words per node, idle until the edges are built)
@@ -766,7 +793,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 				uint32_t pos = 0;
 				if (act && lane == leader) { pos = wcnt[wid * n + j]; wcnt[wid * n + j] = pos + (uint32_t)lb2_popc32(same); }
 				pos = lb2_shfl(pos, leader);
-				if (act) { occ[pos + (uint32_t)lb2_popc32(below)] = kb + o; }
+				if (act) { occ[pos + (uint32_t)lb2_popc32(below)] = (r << 12) | o; }      // (read, offset of the occurrence: offsets < 4096)
 				lb2_warp_sync();
 			}
 		}
@@ -775,13 +802,23 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 			uint32_t tot = 0; for (int c = 0; c < 4; ++c) { tot += ws.b_cnt[j * 4 + c]; }
 			if (!tot) { continue; }
 			uint32_t b0 = nstart[j];
+			if (sh->has_pairs == 1 && R <= 32u * LB2_SEEN_WORDS) {
+				// A name can only be found in the other mate order's list if the read's mate (rd_mate) has had an occurrence
+				// in this node before -- binary_search on the unsorted list may miss a name that is there, it never finds one
+				// that is not.  No such occurrence => nothing of this node is suppressed, and the lists need not be built.
+				uint32_t seen[LB2_SEEN_WORDS]; const uint32_t nwd = (R + 31u) >> 5; bool hit = false;
+				for (uint32_t i = 0; i < nwd; ++i) { seen[i] = 0; }
+				for (uint32_t x = b0; x < b0 + tot && !hit; ++x) {
+					const uint32_t r = occ[x] >> 12, q = ws.rd_mate[r];
+					if (q != LB2_NIL && ((seen[q >> 5] >> (q & 31u)) & 1u)) { hit = true; }
+					seen[r >> 5] |= 1u << (r & 31u);
+				}
+				if (!hit) { continue; }
+			}
 			uint32_t *L1 = ws.mates + 2 * (size_t)b0; uint32_t *L2top = ws.mates + 2 * (size_t)b0 + 2 * (size_t)tot - 1;   // list 2 grows downwards
 			uint32_t n1 = 0, n2_ = 0;
 			for (uint32_t x = b0; x < b0 + tot; ++x) {
-				uint32_t s_ = occ[x];
-				uint32_t lo = 0, hi = R;                       // read of occurrence s_: last r with kbase[r] <= s_
-				while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (ws.rd_kbase[mid] <= s_) { lo = mid; } else { hi = mid; } }
-				uint32_t r = lo, p = s_ - ws.rd_kbase[r];
+				const uint32_t s_ = occ[x], r = s_ >> 12, p = s_ & 0xFFFu;
 				uint32_t info = ws.rd_info[r], mate = (info >> 2) & 3u, cls = info & 3u, name = ws.rd_rank[r];
 				if (mate == 1 || mate == 2) {
 					// std::binary_search(first,last,val) = lower_bound + !(val < *it)   (libstdc++ stl_algo.h)

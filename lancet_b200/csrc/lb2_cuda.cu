@@ -72,7 +72,7 @@ lb2_window_kernel(const __grid_constant__ lb2_launch L)
 // the batch).  128 threads and 32 registers on purpose: one such block fits into what three resident window CTAs leave
 // of an SM (4096 registers, 6.9 KB shared memory), so the pass over the next upload segment runs beside the window
 // kernel of the current one instead of waiting for its CTAs to drain.
-#define LB2_PACK_BLOCK 1024
+#define LB2_PACK_BLOCK 512
 #define LB2_PACK_THREADS 128
 __global__ void __launch_bounds__(LB2_PACK_THREADS, 16) lb2_pack_kernel(const lb2_dev_batch B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4,
                                                                         uint32_t r0, uint32_t r1, const uint32_t *blk)
@@ -162,14 +162,14 @@ struct lb2_ctx {
 	// device buffers of the batch: the caller's arrays, the packed pool, the outputs
 	Buf d_ref_off, d_ref_start, d_wr_off, d_wr_idx, d_base_off, d_flags, d_name_rank, d_ref_seq, d_seq, d_qual;
 	Buf d_pk, d_pk_bits, d_pk_lowq, d_blk;
-	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws, d_big_vars, d_big_strs, d_big_slot, d_ws2, d_retry;
+	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws, d_big_vars, d_big_strs, d_big_slot, d_ws2, d_wsm, d_retry;
 	uint32_t *d_counters = nullptr;      // [LB2_MAX_SEG] window counters of the first-pass launches, [LB2_MAX_SEG] escalation, +1 retry count, +2 big count, +3 pack carry, +4.. totals
 	unsigned long long *d_prof = nullptr;
 	uint32_t big_cap = 256, big_max_var = 1024, big_str_bytes = 128u << 10;
-	lb2_launch L, L2;
+	lb2_launch L, L2, Lm;
 	uint32_t n_windows = 0, n_reads = 0; bool resident = false, ran = false, escalate = true;
 	size_t ws_stride = 0; uint32_t ws_slots = 0, ws_sets = 0; size_t ws2_stride = 0; uint32_t ws2_slots = 0;
-	lb2_cfg C2;
+	lb2_cfg C2, Cm; size_t wsm_stride = 0; uint32_t wsm_slots = 0; bool mid = true;      // Cm: the middle pass (two CTAs per SM)
 	std::vector<uint32_t> h_need;        // per window: leading pool reads the windows up to it use
 	uint32_t *h_blk = nullptr; size_t h_blk_cap = 0;      // (page-locked) packed words before every block of LB2_PACK_BLOCK pool reads
 	uint64_t launches = 0;
@@ -225,7 +225,7 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	lb2_ctx::Buf *bufs[] = { &ctx->d_ref_off, &ctx->d_ref_start, &ctx->d_wr_off, &ctx->d_wr_idx, &ctx->d_base_off, &ctx->d_flags, &ctx->d_name_rank,
 		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_pk, &ctx->d_pk_bits, &ctx->d_pk_lowq, &ctx->d_blk, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used,
-		&ctx->d_var_off, &ctx->d_str_off, &ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot, &ctx->d_ws2, &ctx->d_retry };
+		&ctx->d_var_off, &ctx->d_str_off, &ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot, &ctx->d_ws2, &ctx->d_wsm, &ctx->d_retry };
 	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
 	if (ctx->comm) { lb2_comm_release(ctx->comm); }
 	{ lb2_ctx::Buf *cb[] = { &ctx->d_comm_send, &ctx->d_comm_recv, &ctx->d_comm_cnt }; for (auto b : cb) { if (b->p) { cudaFree(b->p); } } }
@@ -265,7 +265,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 128); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { return fail(); }
 	if (cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess || cudaMemset(ctx->d_counters, 0, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess) { return fail(); }
-	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0;
+	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0; ctx->mid = env_u32("LB2_MID", 1) != 0;
 	ctx->big_cap = env_u32("LB2_BIG_SLABS", 256); ctx->big_max_var = env_u32("LB2_BIG_MAX_VAR", 1024); ctx->big_str_bytes = env_u32("LB2_BIG_STR_BYTES", 128u << 10);
 	ctx->threads = env_u32("LB2_THREADS", 256); if (ctx->threads < 32 || ctx->threads > 256 || (ctx->threads & 31)) { ctx->threads = 256; }
 	*out = ctx;
@@ -290,7 +290,9 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	ctx->h_need.resize(W);
 	{
 		const unsigned hw = std::thread::hardware_concurrency();
-		const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(hw, 8u), std::max(1u, env_u32("LB2_HOST_THREADS", 8))) : 1u;
+		// (several ranks on one host share its cores: each takes its part)
+		const unsigned share = std::max(1u, hw / (unsigned)std::max(1, ctx->comm_world));
+		const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(share, 16u), std::max(1u, env_u32("LB2_HOST_THREADS", 16))) : 1u;
 		std::vector<uint32_t> t_bp(T, 0), t_rd(T, 0); std::vector<int> t_bad(T, 0);
 		auto work = [&](unsigned t) {
 			const uint32_t w0 = (uint32_t)((uint64_t)W * t / T), w1 = (uint32_t)((uint64_t)W * (t + 1) / T);
@@ -320,9 +322,20 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	{	// packed words before every block of LB2_PACK_BLOCK reads (the pre-pack kernel's blocks start from these)
 		const size_t nblk = (size_t)R / LB2_PACK_BLOCK + 2;
 		if (nblk > ctx->h_blk_cap) { if (ctx->h_blk) { cudaFreeHost(ctx->h_blk); ctx->h_blk = nullptr; } LB2_CK(cudaHostAlloc((void **)&ctx->h_blk, sizeof(uint32_t) * (nblk + nblk / 2), cudaHostAllocDefault)); ctx->h_blk_cap = nblk + nblk / 2; }
+		const size_t nb_ = ((size_t)R + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK;
+		auto block_words = [&](size_t blk0, size_t blk1) {      // h_blk[blk] := words of the block's own reads
+			for (size_t k = blk0; k < blk1; ++k) {
+				const uint32_t ra_ = (uint32_t)(k * LB2_PACK_BLOCK), rb_ = (uint32_t)std::min<size_t>(R, (k + 1) * LB2_PACK_BLOCK); uint32_t wsum = 0;
+				for (uint32_t r = ra_; r < rb_; ++r) { wsum += lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]); }
+				ctx->h_blk[k] = wsum;
+			}
+		};
+		const unsigned hw2 = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, ctx->comm_world)); const unsigned T2 = (nb_ >= 64 && hw2 > 1) ? std::min<unsigned>(std::min<unsigned>(hw2, 16u), std::max(1u, env_u32("LB2_HOST_THREADS", 16))) : 1u;
+		if (T2 == 1) { block_words(0, nb_); }
+		else { std::vector<std::thread> th; for (unsigned t = 0; t < T2; ++t) { th.emplace_back(block_words, nb_ * t / T2, nb_ * (t + 1) / T2); } for (auto &x : th) { x.join(); } }
 		uint64_t words = 0;
-		for (uint32_t r = 0; r < R; ++r) { if ((r % LB2_PACK_BLOCK) == 0) { ctx->h_blk[r / LB2_PACK_BLOCK] = (uint32_t)words; } words += lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]); }
-		ctx->h_blk[(size_t)(R + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK] = (uint32_t)words;
+		for (size_t k = 0; k < nb_; ++k) { const uint32_t c = ctx->h_blk[k]; ctx->h_blk[k] = (uint32_t)words; words += c; }
+		ctx->h_blk[nb_] = (uint32_t)words;
 		if (words > 0xFFFFFF00ull) { ctx->err = "read pool too large for 32-bit word offsets: split the batch"; return LB2_ERR_ARG; }
 	}
 	const uint32_t need_bp = std::min<uint32_t>((max_bp + 1023) & ~1023u, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
@@ -401,15 +414,32 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 		C2.arena_bytes = env_u32("LB2_ARENA_BYTES2", 8u << 20); C2.deficit_bytes = env_u32("LB2_DEFICIT_BYTES2", 16u << 20);
 		C2.queue_cap = env_u32("LB2_QUEUE_CAP2", 1u << 23);      /* DFS_LIMIT visits x a few children each */ C2.max_inst = env_u32("LB2_MAX_INST2", 1u << 20); C2.max_special = env_u32("LB2_MAX_SPECIAL2", 2048);
 		C2.n_slots = std::min<uint32_t>((uint32_t)ctx->sm_count, env_u32("LB2_SLOTS2", 1024));
+		// (the workspaces of the escalation passes -- gigabytes -- are allocated when a batch first needs them: lb2_enqueue_finish)
 		const size_t stride2 = lb2_ws_layout(C2, nullptr, nullptr);
-		if (stride2 != ctx->ws2_stride || C2.n_slots > ctx->ws2_slots) {
-			if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); ctx->d_ws2.p = nullptr; }
-			LB2_CK(cudaMalloc(&ctx->d_ws2.p, stride2 * C2.n_slots)); ctx->d_ws2.cap = stride2 * C2.n_slots;
-			ctx->ws2_stride = stride2; ctx->ws2_slots = C2.n_slots;
-		}
+		if (stride2 != ctx->ws2_stride || C2.n_slots > ctx->ws2_slots) { if (ctx->d_ws2.p) { cudaFree(ctx->d_ws2.p); ctx->d_ws2.p = nullptr; ctx->d_ws2.cap = 0; } ctx->ws2_stride = stride2; ctx->ws2_slots = C2.n_slots; }
 		lb2_launch &L2 = ctx->L2; L2 = L; L2.C = C2;
-		L2.ws_base = (uint8_t *)ctx->d_ws2.p; L2.ws_stride = stride2; L2.counter = ctx->d_counters + LB2_MAX_SEG;
+		L2.ws_base = nullptr; L2.ws_stride = stride2; L2.counter = ctx->d_counters + LB2_MAX_SEG;
 		L2.win_list = (const uint32_t *)ctx->d_retry.p; L2.n_list = ctx->d_counters + LB2_CTR_RETRY;
+		if (ctx->mid) {
+			// middle pass: windows with a few thousand k-mers (sequencing errors, low-complexity sequence) outgrow the first
+			// pass's table but do not need a whole SM -- twice the table, a larger graph region, two CTAs per SM
+			lb2_cfg &Cm = ctx->Cm; Cm = C;
+			Cm.table_slots = std::min<uint32_t>(2 * C.table_slots, 16384u); Cm.graph_bytes = env_u32("LB2_GRAPH_BYTES_MID", 80u << 10); Cm.max_bp = bp1;
+			while (Cm.graph_bytes > C.graph_bytes) {
+				int occ_m = 0; const size_t sm = lb2_smem_bytes(Cm.max_bp, Cm.table_slots, Cm.graph_bytes);
+				if (sm <= smem_cap && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, lb2_window_kernel, (int)ctx->threads, sm) == cudaSuccess && occ_m >= 2) { break; }
+				Cm.graph_bytes -= 4096;
+			}
+			cudaGetLastError();
+			Cm.max_nodes = Cm.table_slots - Cm.table_slots / 4; Cm.smem_bytes = (uint32_t)lb2_smem_bytes(Cm.max_bp, Cm.table_slots, Cm.graph_bytes);
+			Cm.arena_bytes = 2u << 20; Cm.deficit_bytes = 4u << 20; Cm.queue_cap = 1u << 20; Cm.max_inst = 1u << 19; Cm.max_special = 512;
+			int occ_m = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, lb2_window_kernel, (int)ctx->threads, Cm.smem_bytes); cudaGetLastError();
+			Cm.n_slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(1, std::min(occ_m, 2));
+			const size_t stridem = lb2_ws_layout(Cm, nullptr, nullptr);
+			if (stridem != ctx->wsm_stride || Cm.n_slots > ctx->wsm_slots) { if (ctx->d_wsm.p) { cudaFree(ctx->d_wsm.p); ctx->d_wsm.p = nullptr; ctx->d_wsm.cap = 0; } ctx->wsm_stride = stridem; ctx->wsm_slots = Cm.n_slots; }
+			lb2_launch &Lm = ctx->Lm; Lm = L2; Lm.C = Cm;
+			Lm.ws_base = nullptr; Lm.ws_stride = stridem; Lm.counter = ctx->d_counters + LB2_MAX_SEG + 1;
+		}
 	}
 	ctx->n_windows = W; ctx->n_reads = R;
 	return LB2_OK;
@@ -447,9 +477,30 @@ static int lb2_enqueue_finish(lb2_ctx *ctx, cudaStream_t st, cudaEvent_t after_e
 {
 	const uint32_t W = ctx->n_windows;
 	if (ctx->escalate) {
-		lb2_collect_kernel<<<64, 256, 0, st>>>(ctx->L);
-		lb2_window_kernel<<<ctx->C2.n_slots, ctx->threads, ctx->C2.smem_bytes, st>>>(ctx->L2);
-		ctx->launches += 2;
+		// how many windows the pass before could not hold (one 4-byte read-back per pass: the escalation workspaces are only
+		// allocated, and the passes only launched, for batches that need them)
+		auto pending = [&](uint32_t *n) -> int {
+			lb2_collect_kernel<<<64, 256, 0, st>>>(ctx->L); ctx->launches += 1;
+			LB2_CK(cudaMemcpyAsync(n, ctx->d_counters + LB2_CTR_RETRY, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+			LB2_CK(cudaStreamSynchronize(st));
+			return LB2_OK;
+		};
+		auto ensure = [&](lb2_ctx::Buf &buf, size_t stride, uint32_t slots, lb2_launch &Lx) -> int {
+			if (!buf.p) { LB2_CK(cudaMalloc(&buf.p, stride * slots)); buf.cap = stride * slots; }
+			Lx.ws_base = (uint8_t *)buf.p;
+			return LB2_OK;
+		};
+		uint32_t n_retry = 0; int rc = pending(&n_retry); if (rc) { return rc; }
+		if (n_retry && ctx->mid) {      // middle pass first; what it cannot hold either is collected again for the last pass
+			if ((rc = ensure(ctx->d_wsm, ctx->wsm_stride, ctx->wsm_slots, ctx->Lm))) { return rc; }
+			lb2_window_kernel<<<std::min(ctx->Cm.n_slots, n_retry), ctx->threads, ctx->Cm.smem_bytes, st>>>(ctx->Lm); ctx->launches += 1;
+			LB2_CK(cudaMemsetAsync(ctx->d_counters + LB2_CTR_RETRY, 0, sizeof(uint32_t), st));
+			if ((rc = pending(&n_retry))) { return rc; }
+		}
+		if (n_retry) {
+			if ((rc = ensure(ctx->d_ws2, ctx->ws2_stride, ctx->ws2_slots, ctx->L2))) { return rc; }
+			lb2_window_kernel<<<std::min(ctx->C2.n_slots, n_retry), ctx->threads, ctx->C2.smem_bytes, st>>>(ctx->L2); ctx->launches += 1;
+		}
 	}
 	if (after_escalation) { LB2_CK(cudaEventRecord(after_escalation, st)); }
 	lb2_scan_kernel<<<1, 1024, 0, st>>>(ctx->L);
@@ -488,7 +539,7 @@ extern "C" int lb2_run(lb2_ctx *ctx)
 	if (!ctx->resident) { return LB2_ERR_STATE; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
 	const uint32_t W = ctx->n_windows; int rc;
-	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? ctx->C2.smem_bytes : 0u)));
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? std::max(ctx->C2.smem_bytes, ctx->mid ? ctx->Cm.smem_bytes : 0u) : 0u)));
 	if ((rc = lb2_enqueue_reset(ctx, ctx->stream))) { return rc; }
 	LB2_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 	if (W) { if ((rc = lb2_enqueue_pack(ctx, 0, ctx->n_reads, ctx->stream))) { return rc; } }
@@ -552,7 +603,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	std::vector<lb2_seg> segs;
 	{
 		const uint64_t nb = batch->n_base_bytes;
-		const uint64_t first = std::max<uint64_t>(env_u32("LB2_SEG_FIRST", 12u << 20), 1u << 16), min_w = std::max(1u, env_u32("LB2_SEG_MIN_WINDOWS", 768));
+		const uint64_t first = std::max<uint64_t>(env_u32("LB2_SEG_FIRST", 4u << 20), 1u << 16), min_w = std::max(1u, env_u32("LB2_SEG_MIN_WINDOWS", 512));
 		uint64_t lim = first, chunk = first; uint32_t wa = 0, ra = 0;
 		while (wa < W) {
 			uint32_t wb = W;
@@ -567,7 +618,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 		}
 	}
 	const auto t1 = std::chrono::steady_clock::now();
-	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? ctx->C2.smem_bytes : 0u)));
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? std::max(ctx->C2.smem_bytes, ctx->mid ? ctx->Cm.smem_bytes : 0u) : 0u)));
 	if ((rc = lb2_enqueue_reset(ctx, ctx->stream))) { return rc; }
 	LB2_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 	LB2_CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
@@ -655,7 +706,7 @@ extern "C" int lb2_rank_names(const char *const *names, uint32_t n, uint32_t *ra
 namespace {
 struct lb2_nccl_api {
 	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr; ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr; const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr; ncclResult_t (*CommAbort)(ncclComm_t) = nullptr; const char *(*GetErrorString)(ncclResult_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -667,14 +718,14 @@ struct lb2_nccl_api {
 		if (!h) { h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL); }
 		if (!h) { return; }
 #define LB2_SYM(f) do { *(void **)(&f) = dlsym(h, "nccl" #f); if (!f) { return; } } while (0)
-		LB2_SYM(GetUniqueId); LB2_SYM(CommInitRank); LB2_SYM(CommDestroy); LB2_SYM(GetErrorString); LB2_SYM(AllGather); LB2_SYM(Send); LB2_SYM(Recv); LB2_SYM(GroupStart); LB2_SYM(GroupEnd);
+		LB2_SYM(GetUniqueId); LB2_SYM(CommInitRank); LB2_SYM(CommDestroy); LB2_SYM(CommAbort); LB2_SYM(GetErrorString); LB2_SYM(AllGather); LB2_SYM(Send); LB2_SYM(Recv); LB2_SYM(GroupStart); LB2_SYM(GroupEnd);
 #undef LB2_SYM
 		ok = true;
 	}
 };
 lb2_nccl_api &lb2_nccl() { static lb2_nccl_api api; return api; }
 }
-static void lb2_comm_release(ncclComm_t c) { if (lb2_nccl().ok) { lb2_nccl().CommDestroy(c); } }
+static void lb2_comm_release(ncclComm_t c) { if (lb2_nccl().ok) { lb2_nccl().CommAbort(c); } }      // (no rendezvous: the other ranks may be gone already)
 #define ncclGetUniqueId lb2_nccl().GetUniqueId
 #define ncclCommInitRank lb2_nccl().CommInitRank
 #define ncclGetErrorString lb2_nccl().GetErrorString
@@ -698,7 +749,7 @@ extern "C" int lb2_comm_init(lb2_ctx *ctx, const char *id_in, int rank, int worl
 	if (!ctx || !id_in || world < 1 || rank < 0 || rank >= world) { return LB2_ERR_ARG; }
 	if (!lb2_nccl().ok) { ctx->err = "libnccl.so.2 not found"; return LB2_ERR_CUDA; }
 	LB2_CK(cudaSetDevice(ctx->device));
-	if (ctx->comm) { lb2_nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+	if (ctx->comm) { lb2_nccl().CommAbort(ctx->comm); ctx->comm = nullptr; }
 	ncclUniqueId id; memcpy(&id, id_in, sizeof id);
 	LB2_NC(ncclCommInitRank(&ctx->comm, world, id, rank));
 	ctx->comm_rank = rank; ctx->comm_world = world;

@@ -15,7 +15,7 @@ LB2_HD size_t lb2_ws_layout(const lb2_cfg &c, uint8_t *base, lb2_ws *ws)
 	size_t n2 = 1; while (n2 < c.max_nodes || n2 < c.max_inst || n2 < MR) { n2 <<= 1; }
 	LB2_TAKE(used, uint32_t, c.max_nodes); LB2_TAKE(bseq, uint32_t, MN * 8); LB2_TAKE(g_cnt, uint32_t, (size_t)c.table_slots * 2); LB2_TAKE(g_em, uint32_t, c.table_slots); LB2_TAKE(sortk, uint64_t, n2); LB2_TAKE(inst, uint16_t, c.max_inst + 16); LB2_TAKE(mates, uint32_t, 2 * (size_t)c.max_inst + 16);
 	LB2_TAKE(rd_start, uint32_t, MR); LB2_TAKE(rd_len, uint32_t, MR); LB2_TAKE(rd_t5, uint32_t, MR);
-	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR); LB2_TAKE(rd_src, uint64_t, MR);
+	LB2_TAKE(rd_info, uint32_t, MR); LB2_TAKE(rd_rank, uint32_t, MR); LB2_TAKE(rd_kbase, uint32_t, MR); LB2_TAKE(rd_mate, uint32_t, MR); LB2_TAKE(rd_src, uint64_t, MR);
 	LB2_TAKE(b_rep, uint32_t, MN); LB2_TAKE(b_hash, uint64_t, MN); LB2_TAKE(b_cnt, uint32_t, MN * 4); LB2_TAKE(b_mincovqv, int32_t, MN);
 	LB2_TAKE(b_flags, uint8_t, MN); LB2_TAKE(b_stT, uint8_t, MN); LB2_TAKE(b_ne, uint8_t, MN); LB2_TAKE(b_edge, lb2_bedge, MN * LB2_BECAP); LB2_TAKE(b_row, uint32_t, MN);
 	LB2_TAKE(d_rep, uint32_t, LB2_MAX_ROWS); LB2_TAKE(d_hash, uint64_t, LB2_MAX_ROWS); LB2_TAKE(d_cnt, uint32_t, LB2_MAX_ROWS * 4); LB2_TAKE(d_orig, uint32_t, LB2_MAX_ROWS);
@@ -67,7 +67,10 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 		for (int i = 0; i < 24; ++i) { sh->prof[i] = 0; } sh->t_last = lb2_clock();
 #endif
 		uint32_t slot = LB2_NIL;
-		if (W.escal && W.O->big_count) { slot = lb2g_add32(W.O->big_count, 1u); if (slot >= W.O->big_cap) { slot = LB2_NIL; } W.O->big_slot[w] = slot; }
+		if (W.escal && W.O->big_count) {      // (a window redone twice keeps the large slab it was given the first time)
+			slot = W.O->big_slot[w];
+			if (slot == LB2_NIL) { slot = lb2g_add32(W.O->big_count, 1u); if (slot >= W.O->big_cap) { slot = LB2_NIL; } W.O->big_slot[w] = slot; }
+		}
 		sh->big = slot;
 		// (the descriptor is shared by the CTA: one lane writes it, everybody reads it after the barrier)
 		if (slot != LB2_NIL) { W.ovar = W.O->big_variants + (size_t)slot * W.O->big_max_var; W.ostr = W.O->big_strings + (size_t)slot * W.O->big_str_bytes; W.ovar_cap = W.O->big_max_var; W.ostr_cap = W.O->big_str_bytes; }

@@ -46,6 +46,7 @@ static inline unsigned long long lb2_clock() { return 0; }
 static inline uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) { (void)sc; *total = v; return 0; }
 // atomics on an address that may be shared OR global (scratch that falls back to the workspace slab)
 static inline uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
+static inline uint32_t lb2x_cas32(uint32_t *p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) { *p = v; } return o; }
 // ---- sub-warp groups for the read staging (8 lanes per read on the device, 1 in the simulation) ----
 #define LB2_GS 1
 // ---- shared-memory words addressed by a precomputed base (device: 32-bit shared-window address, no generic->shared
@@ -147,6 +148,7 @@ LB2_DEV uint32_t lb2_block_excl(uint32_t *sc, uint32_t v, uint32_t *total) {
 }
 // atomics on an address that may be shared OR global (scratch that falls back to the workspace slab)
 LB2_DEV uint32_t lb2x_exch32(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
+LB2_DEV uint32_t lb2x_cas32(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
 // ---- sub-warp groups for the read staging (8 lanes per read) ----
 #define LB2_GS 8
 // ---- shared-memory words addressed by a precomputed 32-bit shared-window address (no generic->shared conversion per access) ----

@@ -52,7 +52,7 @@ struct lb2_ws {
 	uint32_t *b_rep; uint64_t *b_hash; uint32_t *b_cnt; int32_t *b_mincovqv; uint8_t *b_flags; uint8_t *b_stT; uint8_t *b_ne;
 	lb2_bedge *b_edge; uint32_t *b_row;
 	// --- reads ---
-	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase; uint64_t *rd_src;      // rd_src: first word in the packed pool | words << 32
+	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase; uint32_t *rd_mate; uint64_t *rd_src;      // rd_src: first word in the packed pool | words << 32
 	// --- graph stage, row space.  hot (shared memory): ---
 	uint32_t *d_lnext; uint32_t *d_bk; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
 	uint16_t *d_pos; uint32_t *px; uint32_t px_words;   // (packed-read words, dead in the graph stage) list index of every row; scratch of the parallel compaction
@@ -109,7 +109,7 @@ struct lb2_sh {
 	uint32_t ref_hasN, n_refitems, n_nk; uint32_t refn[LB2_MAX_REF / 32 + 2];
 	uint32_t n_tev, tev_ovf; lb2_tev tev[LB2_MAX_TEV];     // tandem repeats of the loaded path (n_tev = LB2_NIL: not computed, scan per variant)
 	unsigned long long prof[24]; unsigned long long t_last;
-	uint32_t scan[520];           // block-scan partials (<= 512 lanes)
+	uint32_t scan[40];            // block-scan partials (one per warp, lb2_block_excl)
 };
 
 // phase ids for the optional cycle profile (lb2_dev_out::prof)

@@ -82,8 +82,8 @@ def test_cli_multi_gpu(ngpu, tmp_path):
     from lancet_b200 import simbam
     d = simbam.write_dataset(str(tmp_path / "mg"), seed=131, chroms=(("chr22", 30000),), var_every=400, som_every=900)
     args = ["--reg", "chr22:1-30000", "--num-threads", "4"]
-    want, _ = _run(REFCLI, d, args, timeout=600)
-    got, err = _run(CLI, d, args + ["--gpus", str(ngpu), "--batch-windows", "64"], timeout=600)
+    want, _ = _run(REFCLI, d, args, timeout=300)
+    got, err = _run(CLI, d, args + ["--gpus", str(ngpu), "--batch-windows", "64"], timeout=150)
     assert "not assembled" not in err
     assert got == want
     assert sum(1 for l in want.splitlines() if not l.startswith("#")) > 50

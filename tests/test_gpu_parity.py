@@ -285,3 +285,33 @@ def test_reference_with_n(case, mink):
     assert res.records() == want
     assert any("N" in r[4] for r in want) or case == "runs_str"
     c.close()
+
+
+def _concat(b1, b2):
+    """two batches as one (pools and windows appended)"""
+    from lancet_b200.batch import Batch
+    return Batch(ref_off=np.concatenate([b1.ref_off, b2.ref_off[1:] + b1.ref_off[-1]]), ref_start=np.concatenate([b1.ref_start, b2.ref_start]),
+                 chr_id=np.concatenate([b1.chr_id, b2.chr_id]), wr_off=np.concatenate([b1.wr_off, b2.wr_off[1:] + b1.wr_off[-1]]),
+                 wr_idx=np.concatenate([b1.wr_idx, b2.wr_idx + b1.n_reads]), base_off=np.concatenate([b1.base_off, b2.base_off[1:] + b1.base_off[-1]]),
+                 flags=np.concatenate([b1.flags, b2.flags]), name_rank=np.concatenate([b1.name_rank, b2.name_rank + (int(b1.name_rank.max()) + 1 if b1.n_reads else 0)]),
+                 ref_seq=np.concatenate([b1.ref_seq, b2.ref_seq]), seq=np.concatenate([b1.seq, b2.seq]), qual=np.concatenate([b1.qual, b2.qual]))
+
+
+def test_deep_windows_do_not_set_the_launch_configuration():
+    """A few deep windows (160x + 160x) in a batch of ordinary ones: the first pass stays sized for the ordinary
+    windows (three CTAs per SM), the deep ones go through the escalation pass with its own, larger staging area --
+    and every window comes out identical to the reference."""
+    import run_ref
+    if not run_ref.available():
+        pytest.skip("oracle/_ref/ref_windows not built")
+    from lancet_b200.synth import make_batch
+    normal = make_batch(seed=301, region_len=12000, var_every=600)
+    deep = make_batch(seed=302, region_len=900, cov_t=160, cov_n=160, var_every=300)
+    b = _concat(normal, deep)
+    want, _ = run_ref.run(b, threads=8)
+    c = _ctx()
+    res = c.process(b)
+    assert (res.windows["status"] < 3).all(), res.windows[res.windows["status"] >= 3]
+    assert res.records() == want
+    assert c.resident_ctas >= 3 * 148 or c.resident_ctas >= b.n_windows       # the deep windows did not cost the batch its occupancy
+    c.close()

@@ -33,13 +33,14 @@ def main():
         for _ in range(3):
             ctx.run(); ctx.wait(); ms.append(ctx.last_kernel_ms)
         res = ctx.download()
+        step_ms = {k: ctx.last_kernel_ms_of(k) for k in ("pack", "windows", "escalation", "compaction")}
         t0 = time.perf_counter(); r2 = ctx.process(b); e2e = time.perf_counter() - t0
         st = res.windows["status"]
         out = {"config": name, "desc": c["desc"], "windows": b.n_windows, "reads": b.n_reads, "gen_s": round(t_gen, 1), "kernel_ms": min(ms),
                "windows_per_s": b.n_windows / (min(ms) * 1e-3), "e2e_pageable_windows_per_s": b.n_windows / e2e,
                "assembled": int((st == 0).sum()), "skipped_repeat": int((st == 1).sum()), "no_reads": int((st == 2).sum()), "not_assembled": int((st >= 3).sum()),
                "k_tried_mean": float(res.windows["n_k_tried"].mean()), "records": len(res.variants),
-               "step_ms": {k: ctx.last_kernel_ms_of(k) for k in ("pack", "windows", "escalation", "compaction")}}
+               "step_ms": step_ms}
         if run_ref.available():
             rng = np.random.default_rng(1); pick = np.sort(rng.choice(b.n_windows, min(400, b.n_windows), replace=False))
             sub = b.subset(pick)
