@@ -77,17 +77,22 @@ lb2_window_kernel(const __grid_constant__ lb2_launch L)
 __global__ void __launch_bounds__(LB2_PACK_THREADS, 16) lb2_pack_kernel(const lb2_dev_batch B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4,
                                                                         uint32_t r0, uint32_t r1, const uint32_t *blk)
 {
-	__shared__ uint32_t sc[40]; __shared__ uint32_t s_w[LB2_PACK_BLOCK];
+	__shared__ uint32_t sc[40]; __shared__ uint32_t s_w[LB2_PACK_BLOCK]; __shared__ uint32_t s_o[LB2_PACK_BLOCK + 1]; __shared__ uint8_t s_f[LB2_PACK_BLOCK];      // (offsets relative to the block's first read: 4.7 KB in all, see above)
 	constexpr uint32_t PER = LB2_PACK_BLOCK / LB2_PACK_THREADS;
-	const uint32_t rb = r0 + blockIdx.x * LB2_PACK_BLOCK, t = threadIdx.x; uint32_t sum = 0;
-	for (uint32_t q = 0; q < PER; ++q) { const uint32_t r = rb + t * PER + q; const uint32_t c = (r < r1) ? lb2_pack_nwords(B.base_off[r + 1] - B.base_off[r]) : 0u; s_w[t * PER + q] = c; sum += c; }
+	const uint32_t rb = r0 + blockIdx.x * LB2_PACK_BLOCK, t = threadIdx.x;
+	// the block's pool offsets and flag bytes first (coalesced), so that the per-read work below starts with the base loads
+	const uint64_t o_first = B.base_off[rb];
+	for (uint32_t j = t; j <= LB2_PACK_BLOCK; j += LB2_PACK_THREADS) { const uint32_t r = rb + j; s_o[j] = (uint32_t)(B.base_off[r <= r1 ? r : r1] - o_first); if (j < LB2_PACK_BLOCK) { s_f[j] = (r < r1) ? B.flags[r] : (uint8_t)0; } }
+	__syncthreads();
+	uint32_t sum = 0;
+	for (uint32_t q = 0; q < PER; ++q) { const uint32_t j = t * PER + q; const uint32_t c = (rb + j < r1) ? lb2_pack_nwords(s_o[j + 1] - s_o[j]) : 0u; s_w[j] = c; sum += c; }
 	uint32_t total = 0, ex = lb2_block_excl(sc, sum, &total) + blk[blockIdx.x];
 	for (uint32_t q = 0; q < PER; ++q) { const uint32_t c = s_w[t * PER + q]; s_w[t * PER + q] = ex; ex += c; }
 	__syncthreads();
 	// a group of LB2_GS lanes per read, neighbouring groups on neighbouring reads (every lane of a warp runs every round)
 	for (uint32_t j = lb2_group(); j < LB2_PACK_BLOCK; j += lb2_ngroups()) {
 		const uint32_t r = rb + j;
-		lb2_pack_read(B, pk, pk_bits, pk_lowq, qtrim4, qcall4, r < r1, r, s_w[j]);
+		lb2_pack_read(B, pk, pk_bits, pk_lowq, qtrim4, qcall4, r < r1, r, s_w[j], o_first + s_o[j], (uint64_t)(s_o[j + 1] - s_o[j]), s_f[j]);
 	}
 }
 
@@ -262,7 +267,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 18);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
-	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 128); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
+	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 64); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { return fail(); }
 	if (cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess || cudaMemset(ctx->d_counters, 0, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess) { return fail(); }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0; ctx->mid = env_u32("LB2_MID", 1) != 0;
@@ -345,7 +350,9 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	// First pass: sized for the windows that still let LB2_MIN_CTAS_PER_SM CTAs share an SM; a window that needs more staging
 	// area than that goes to the escalation pass, which has the whole SM to itself (one outlier must not cost every window
 	// of the batch its occupancy)
-	uint32_t bp1 = std::max(need_bp, 32768u);
+	// (never less than 72 K bases: the staging area doubles as the scratch of the graph stage -- parallel first compaction,
+	// alignment rows, BFS queue head -- and those want ~18 KB whatever the depth of the windows)
+	uint32_t bp1 = std::max(need_bp, env_u32("LB2_MIN_BP", 73728u));
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
 	{
 		const uint32_t want_occ = std::max(1u, env_u32("LB2_MIN_CTAS_PER_SM", 3));
@@ -625,6 +632,8 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	LB2_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));      // (the pack carry is one of the counters just reset)
 	LB2_CK(cudaStreamWaitEvent(ctx->wstream[0], ctx->ev_ready, 0)); LB2_CK(cudaStreamWaitEvent(ctx->wstream[1], ctx->ev_ready, 0));
 	uint64_t h2d = 0;
+	// (LB2_TIMING=1: a device time line of the segments -- copy + pre-pack done, window launch begin / end)
+	std::vector<cudaEvent_t> tl; if (timing) { tl.resize(3 * segs.size()); for (auto &e : tl) { cudaEventCreate(&e); } }
 #define LB2_PIECE(buf, ptr, esz, from, to) do { if ((to) > (from)) { LB2_CK(cudaMemcpyAsync((char *)ctx->buf.p + (size_t)(from) * (esz), (const char *)(ptr) + (size_t)(from) * (esz), \
 		(size_t)((to) - (from)) * (esz), cudaMemcpyHostToDevice, ctx->copy_stream)); h2d += (uint64_t)((to) - (from)) * (esz); } } while (0)
 	LB2_PIECE(d_ref_off, batch->ref_off, 4, (size_t)0, (size_t)W + 1); LB2_PIECE(d_ref_start, batch->ref_start, 4, (size_t)0, (size_t)W); LB2_PIECE(d_wr_off, batch->wr_off, 4, (size_t)0, (size_t)W + 1);
@@ -640,9 +649,12 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 			if ((rc = lb2_enqueue_pack(ctx, sg.r0, sg.r1, ctx->copy_stream))) { return rc; }
 		}
 		LB2_CK(cudaEventRecord(ctx->ev_seg[s], ctx->copy_stream));
+		if (timing) { cudaEventRecord(tl[3 * s], ctx->copy_stream); }
 		cudaStream_t ws = ctx->wstream[s & 1];
 		LB2_CK(cudaStreamWaitEvent(ws, ctx->ev_seg[s], 0));
+		if (timing) { cudaEventRecord(tl[3 * s + 1], ws); }
 		if ((rc = lb2_enqueue_windows(ctx, sg.w0, sg.w1, pinned ? (uint32_t)(s & 1) : 0u, (uint32_t)s, ws))) { return rc; }
+		if (timing) { cudaEventRecord(tl[3 * s + 2], ws); }
 	}
 #undef LB2_PIECE
 	ctx->h2d_bytes = h2d;
@@ -658,6 +670,11 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	if (timing) {
 		const auto t4 = std::chrono::steady_clock::now();
 		auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a).count(); };
+		for (size_t s_ = 0; s_ < segs.size() && !tl.empty(); ++s_) {
+			float a = 0, b_ = 0, c = 0; cudaEventElapsedTime(&a, ctx->ev[0], tl[3 * s_]); cudaEventElapsedTime(&b_, ctx->ev[0], tl[3 * s_ + 1]); cudaEventElapsedTime(&c, ctx->ev[0], tl[3 * s_ + 2]);
+			fprintf(stderr, "  segment %zu: windows [%u, %u) reads [%u, %u): copied+packed at %.2f ms, windows %.2f .. %.2f ms\n", s_, segs[s_].w0, segs[s_].w1, segs[s_].r0, segs[s_].r1, a, b_, c);
+		}
+		for (auto &e : tl) { cudaEventDestroy(e); }
 		fprintf(stderr, "lb2_process: %zu segment(s)%s, plan %.2f ms, enqueue %.2f ms, copies done +%.2f ms, kernels+download +%.2f ms, total %.2f ms (device span %.2f ms)\n",
 		        segs.size(), pinned ? "" : " (pageable)", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t0, t4), (double)result->kernel_ms);
 	}

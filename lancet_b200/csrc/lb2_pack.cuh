@@ -43,11 +43,13 @@ static inline uint32_t lb2_pack_nwords(uint64_t len) { if (len > 0xFFFF0u) { len
 
 // One read by a group of LB2_GS lanes (all lanes of a warp call this together; act = false: the group has no read).
 // woff: the read's first word in the packed pool.
-LB2_DEV void lb2_pack_read(const lb2_dev_batch &B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4, bool act, uint32_t r, uint32_t woff)
+// o0 / len64 / fl: the read's pool offset, length and flag byte (the caller has them at hand: no dependent loads here).
+LB2_DEV void lb2_pack_read(const lb2_dev_batch &B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4, bool act, uint32_t r, uint32_t woff,
+                           uint64_t o0, uint64_t len64, uint8_t fl)
 {
 	const uint32_t gl = lb2_glane();
-	uint64_t o0 = 0; uint32_t len = 0;
-	if (act) { o0 = B.base_off[r]; const uint64_t l64 = B.base_off[r + 1] - o0; len = l64 > 0xFFFF0u ? 0xFFFF0u : (uint32_t)l64; }
+	uint32_t len = 0;
+	if (act) { len = len64 > 0xFFFF0u ? 0xFFFF0u : (uint32_t)len64; } else { o0 = 0; }
 	const char *s = B.seq + o0, *q = B.qual + o0;
 	const uint32_t nch = (len + 15u) >> 4;
 	uint32_t first = 0xFFFFFFFFu, last = 0, my_nac = 0, my_lowc = 0, my_c = 0xFFFFFFFFu;      // last = index of the last good base + 1
@@ -76,7 +78,6 @@ LB2_DEV void lb2_pack_read(const lb2_dev_batch &B, lb2_pkread *pk, uint32_t *pk_
 	}
 	junk = lb2_gor(junk); lowq = lb2_gor(lowq);
 	if (act && gl == 0) {
-		const uint8_t fl = B.flags[r];
 		uint32_t n = junk ? 0u : last - first; const uint32_t t5 = junk ? len : first;
 		uint32_t info = ((fl & LB2_READ_NORMAL) ? 2u : 0u) | ((fl & LB2_READ_REVERSE) ? 1u : 0u) | (((fl >> LB2_READ_MATE_SHIFT) & 3u) << 2);
 		if (fl & LB2_READ_UNMAPPED) { info |= LB2_PK_UNMAPPED; }

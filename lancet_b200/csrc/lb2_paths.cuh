@@ -169,12 +169,13 @@ LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 		Q_AT(0) = root;
 	}
 	lb2_sync();
-	uint32_t qh = 0, qt = 1, my_best = LB2_NIL; int my_score = -1;      // (qh, qt: the same in every lane)
-	while (qh < qt && qh < limit) {
-		const uint32_t end = qt < limit ? qt : limit, idx = qh + tid;
+	uint32_t qh = 0, qt = 1, my_best = LB2_NIL; int my_score = -1;      // (qh, qt: the same in every lane that takes part)
+	// one round: the next `width` unvisited entries, one per lane; returns the children pushed (LB2_NIL: queue overflow)
+	auto expand = [&](uint32_t lane_, uint32_t width, bool whole_cta) -> uint32_t {
+		const uint32_t end = qt < limit ? qt : limit, idx = qh + lane_;
 		lb2_qent e; e.parent = 0; e.node = 0; e.len = 0; e.score = 0; e.eidx = 0; e.dirflag = 0;
 		const lb2_edge *ed = nullptr; int ne = 0, pdir = 0, pflag = 0; uint32_t nchild = 0;
-		if (idx < end) {
+		if (idx < end && lane_ < width) {
 			e = Q_AT(idx); const uint32_t cur = e.node; pdir = e.dirflag & 1; pflag = (e.dirflag >> 1) & 1;
 			if (cur == sink && pflag == 0) { if ((int)e.score > my_score) { my_best = idx; my_score = (int)e.score; } }
 			else if (e.len > maxlen) { }
@@ -183,8 +184,8 @@ LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 				for (int i = 0; i < ne; ++i) { if (lb2_is_dir(ed[i].dir, pdir)) { ++nchild; } }
 			}
 		}
-		uint32_t total = 0; const uint32_t off = lb2_block_excl(sh->scan, nchild, &total);
-		if (total > cap - qt) { if (tid == 0) { sh->err |= 1u << LB2_D_QUEUE; } lb2_sync(); return LB2_NIL; }
+		uint32_t total = 0; const uint32_t off = whole_cta ? lb2_block_excl(sh->scan, nchild, &total) : lb2_warp_excl(nchild, &total);
+		if (total > cap - qt) { return LB2_NIL; }
 		if (nchild) {
 			uint32_t o = qt + off;
 			for (int i = 0; i < ne; ++i) {
@@ -199,8 +200,25 @@ LB2_DEVNI uint32_t lb2_bfs(lb2_win &W)
 				Q_AT(o) = c; ++o;
 			}
 		}
+		qh = (end - qh > width) ? qh + width : end; qt += total;
+		return total;
+	};
+	// small searches (nearly all of them) never leave the first warp: a warp-width of entries per round, warp barriers only;
+	// a frontier that keeps growing is handed to the whole CTA
+	bool overflow = false;
+	if (tid < LB2_WARP) {
+		while (qh < qt && qh < limit && qt - qh <= 8u * LB2_WARP) {
+			if (expand(tid, LB2_WARP, false) == LB2_NIL) { overflow = true; break; }
+			lb2_warp_sync();
+		}
+		if (tid == 0) { sh->bfs_qh = qh; sh->bfs_qt = overflow ? LB2_NIL : qt; }
+	}
+	lb2_sync();
+	qh = sh->bfs_qh; qt = sh->bfs_qt;
+	if (qt == LB2_NIL) { if (tid == 0) { sh->err |= 1u << LB2_D_QUEUE; } lb2_sync(); return LB2_NIL; }
+	while (qh < qt && qh < limit) {
+		if (expand(tid, nt, true) == LB2_NIL) { if (tid == 0) { sh->err |= 1u << LB2_D_QUEUE; } lb2_sync(); return LB2_NIL; }
 		lb2_sync();
-		qh = (end - qh > nt) ? qh + nt : end; qt += total;
 	}
 #undef Q_AT
 	const uint32_t key = (my_best == LB2_NIL) ? 0u : (uint32_t)my_score + 1u;

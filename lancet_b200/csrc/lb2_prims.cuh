@@ -68,6 +68,7 @@ static inline void lb2_warp_sync() {}
 static inline uint32_t lb2_warp_max(uint32_t v) { return v; }
 static inline unsigned lb2_lane() { return 0; }
 static inline uint32_t lb2_match_any(uint32_t) { return 1u; }      // lanes of the warp holding the same value
+static inline uint32_t lb2_warp_excl(uint32_t v, uint32_t *total) { *total = v; return 0; }      // warp-wide exclusive prefix sum
 static inline uint32_t lb2_shfl(uint32_t v, uint32_t) { return v; }
 static inline uint32_t lb2_shfl_up1(uint32_t v) { return v; }
 #define LB2_FQ 1      /* lanes per chain in the coverage fold of the parallel compaction (one per channel on the device) */
@@ -174,6 +175,13 @@ LB2_DEV void lb2_warp_sync() { __syncwarp(); }
 LB2_DEV uint32_t lb2_warp_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 LB2_DEV unsigned lb2_lane() { return threadIdx.x & 31u; }
 LB2_DEV uint32_t lb2_match_any(uint32_t v) { return __match_any_sync(0xFFFFFFFFu, v); }      // lanes of the warp holding the same value
+LB2_DEV uint32_t lb2_warp_excl(uint32_t v, uint32_t *total) {      // warp-wide exclusive prefix sum (all 32 lanes call it)
+	uint32_t x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((threadIdx.x & 31u) >= (unsigned)o) { x += y; } }
+	*total = __shfl_sync(0xFFFFFFFFu, x, 31);
+	return x - v;
+}
 LB2_DEV uint32_t lb2_shfl(uint32_t v, uint32_t src) { return __shfl_sync(0xFFFFFFFFu, v, (int)src); }
 LB2_DEV uint32_t lb2_shfl_up1(uint32_t v) { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
 #define LB2_FQ 4      /* lanes per chain in the coverage fold of the parallel compaction: one per channel */

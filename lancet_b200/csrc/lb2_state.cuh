@@ -96,7 +96,7 @@ struct lb2_sh {
 	uint32_t source, sink, anc_src, anc_snk, anc_amb, spec_cap;
 	uint32_t arena_used, tstr_used;
 	// path
-	uint32_t plen, pn, need_align, n_trans, path_found, aln_len, q_smem, bfs_score, bfs_best;
+	uint32_t plen, pn, need_align, n_trans, path_found, aln_len, q_smem, bfs_score, bfs_best, bfs_qh, bfs_qt;
 	// output
 	uint32_t n_var, str_used, n_k_tried, final_k, last_nodes;
 	int32_t  numcomp;

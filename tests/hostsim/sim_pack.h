@@ -11,7 +11,7 @@ static void sim_pack(lb2_dev_batch &B, uint32_t R, const lb2_params &P, SimPack 
 	const uint32_t qt = ((uint32_t)P.min_qual_trim & 0xFFu) * 0x01010101u, qc = ((uint32_t)P.min_qual_call & 0xFFu) * 0x01010101u;
 	uint32_t woff = 0;
 	for (uint32_t r = 0; r < R; ++r) {
-		lb2_pack_read(B, sp.pk.data(), sp.bits.data(), sp.lowq.data(), qt, qc, true, r, woff);
+		lb2_pack_read(B, sp.pk.data(), sp.bits.data(), sp.lowq.data(), qt, qc, true, r, woff, B.base_off[r], B.base_off[r + 1] - B.base_off[r], B.flags[r]);
 		woff += lb2_pack_nwords(B.base_off[r + 1] - B.base_off[r]);
 	}
 	B.pk = sp.pk.data(); B.pk_bits = sp.bits.data(); B.pk_lowq = sp.lowq.data();
