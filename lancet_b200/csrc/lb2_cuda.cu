@@ -67,15 +67,17 @@ lb2_window_kernel(const __grid_constant__ lb2_launch L)
 	}
 }
 
-// ---- the pre-pack pass over pool reads [r0, r1), r0 a multiple of LB2_PACK_BLOCK: one block per LB2_PACK_BLOCK reads;
-// blk[b] = packed words of all pool reads before the block's first read (prefix sums made by the host while it plans
-// the batch).  128 threads and 32 registers on purpose: one such block fits into what three resident window CTAs leave
+// ---- the pre-pack pass over pool reads [r0, r1), r0 a multiple of LB2_PACK_BLOCK: one block per LB2_PACK_BLOCK reads.
+// A block's reads start at packed word floor(pool offset of its first read / 16) + index of that read: an upper bound of
+// the words all earlier reads take (a read of len bases takes ceil(len/16) <= len/16 + 1 words), so blocks never overlap
+// and every block finds its place from the pool offsets alone -- stretches of the pool can be packed in any order.
+// 128 threads and 32 registers on purpose: one such block fits into what three resident window CTAs leave
 // of an SM (4096 registers, 6.9 KB shared memory), so the pass over the next upload segment runs beside the window
 // kernel of the current one instead of waiting for its CTAs to drain.
 #define LB2_PACK_BLOCK 512
 #define LB2_PACK_THREADS 128
 __global__ void __launch_bounds__(LB2_PACK_THREADS, 16) lb2_pack_kernel(const lb2_dev_batch B, lb2_pkread *pk, uint32_t *pk_bits, uint16_t *pk_lowq, uint32_t qtrim4, uint32_t qcall4,
-                                                                        uint32_t r0, uint32_t r1, const uint32_t *blk)
+                                                                        uint32_t r0, uint32_t r1)
 {
 	__shared__ uint32_t sc[40]; __shared__ uint32_t s_w[LB2_PACK_BLOCK]; __shared__ uint32_t s_o[LB2_PACK_BLOCK + 1]; __shared__ uint8_t s_f[LB2_PACK_BLOCK];      // (offsets relative to the block's first read: 4.7 KB in all, see above)
 	constexpr uint32_t PER = LB2_PACK_BLOCK / LB2_PACK_THREADS;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(LB2_PACK_THREADS, 16) lb2_pack_kernel(const lb
 	__syncthreads();
 	uint32_t sum = 0;
 	for (uint32_t q = 0; q < PER; ++q) { const uint32_t j = t * PER + q; const uint32_t c = (rb + j < r1) ? lb2_pack_nwords(s_o[j + 1] - s_o[j]) : 0u; s_w[j] = c; sum += c; }
-	uint32_t total = 0, ex = lb2_block_excl(sc, sum, &total) + blk[blockIdx.x];
+	uint32_t total = 0, ex = lb2_block_excl(sc, sum, &total) + (uint32_t)(o_first >> 4) + rb;
 	for (uint32_t q = 0; q < PER; ++q) { const uint32_t c = s_w[t * PER + q]; s_w[t * PER + q] = ex; ex += c; }
 	__syncthreads();
 	// a group of LB2_GS lanes per read, neighbouring groups on neighbouring reads (every lane of a warp runs every round)
@@ -155,18 +157,19 @@ __global__ void lb2_gather_kernel(const __grid_constant__ lb2_launch L)
 // host side
 // ------------------------------------------------------------------------------------------------
 #define LB2_MAX_SEG 16
-struct lb2_seg { uint32_t w0, w1, r0, r1; };      // windows [w0, w1) need pool reads [0, r1); reads [r0, r1) are uploaded with this segment
+// an upload segment: windows [w0, w1) and the stretches of the pool (whole pack blocks) that they use and that are not on the device yet
+struct lb2_seg { uint32_t w0, w1, nr; uint32_t r0[4], r1[4]; };
 struct lb2_ctx {
 	int device = 0; int sm_count = 0; uint32_t threads = 256; size_t smem_optin = 0;
-	cudaStream_t stream = nullptr, copy_stream = nullptr, wstream[2] = { nullptr, nullptr };
+	cudaStream_t stream = nullptr, copy_stream = nullptr, pack_stream = nullptr, wstream[2] = { nullptr, nullptr };
 	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };      // run: start, packed, first pass, escalation, compaction
-	cudaEvent_t ev_ready = nullptr, ev_seg[LB2_MAX_SEG] = {}, ev_w[2] = { nullptr, nullptr };
+	cudaEvent_t ev_ready = nullptr, ev_seg[LB2_MAX_SEG] = {}, ev_cp[LB2_MAX_SEG] = {}, ev_w[2] = { nullptr, nullptr };
 	lb2_params P; lb2_cfg C;
 	std::string err;
 	struct Buf { void *p = nullptr; size_t cap = 0; };
 	// device buffers of the batch: the caller's arrays, the packed pool, the outputs
 	Buf d_ref_off, d_ref_start, d_wr_off, d_wr_idx, d_base_off, d_flags, d_name_rank, d_ref_seq, d_seq, d_qual;
-	Buf d_pk, d_pk_bits, d_pk_lowq, d_blk;
+	Buf d_pk, d_pk_bits, d_pk_lowq;
 	Buf d_info, d_vars, d_strs, d_str_used, d_var_off, d_str_off, d_cvars, d_cstr, d_ws, d_big_vars, d_big_strs, d_big_slot, d_ws2, d_wsm, d_retry;
 	uint32_t *d_counters = nullptr;      // [LB2_MAX_SEG] window counters of the first-pass launches, [LB2_MAX_SEG] escalation, +1 retry count, +2 big count, +3 pack carry, +4.. totals
 	unsigned long long *d_prof = nullptr;
@@ -175,8 +178,10 @@ struct lb2_ctx {
 	uint32_t n_windows = 0, n_reads = 0; bool resident = false, ran = false, escalate = true;
 	size_t ws_stride = 0; uint32_t ws_slots = 0, ws_sets = 0; size_t ws2_stride = 0; uint32_t ws2_slots = 0;
 	lb2_cfg C2, Cm; size_t wsm_stride = 0; uint32_t wsm_slots = 0; bool mid = true;      // Cm: the middle pass (two CTAs per SM)
-	std::vector<uint32_t> h_need;        // per window: leading pool reads the windows up to it use
-	uint32_t *h_blk = nullptr; size_t h_blk_cap = 0;      // (page-locked) packed words before every block of LB2_PACK_BLOCK pool reads
+	// per window: the one or two stretches of the pool its reads lie in, [a0,a1) [b0,b1) (a window's list is tumour reads then
+	// normal reads, each ascending: two stretches far apart in a pool that holds all tumour reads before all normal ones)
+	std::vector<uint32_t> h_rng;
+	uint32_t plan_need_bp = 0, plan_max_reads = 0, smem_cap = 0, bp1_cached = 0, bp1_slots = 0;      // results of the window plan; cached first-pass staging size
 	uint64_t launches = 0;
 	float kernel_ms = 0;
 	// host result
@@ -229,15 +234,15 @@ extern "C" void lb2_destroy(lb2_ctx *ctx)
 	if (!ctx) { return; }
 	cudaSetDevice(ctx->device);
 	lb2_ctx::Buf *bufs[] = { &ctx->d_ref_off, &ctx->d_ref_start, &ctx->d_wr_off, &ctx->d_wr_idx, &ctx->d_base_off, &ctx->d_flags, &ctx->d_name_rank,
-		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_pk, &ctx->d_pk_bits, &ctx->d_pk_lowq, &ctx->d_blk, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used,
+		&ctx->d_ref_seq, &ctx->d_seq, &ctx->d_qual, &ctx->d_pk, &ctx->d_pk_bits, &ctx->d_pk_lowq, &ctx->d_info, &ctx->d_vars, &ctx->d_strs, &ctx->d_str_used,
 		&ctx->d_var_off, &ctx->d_str_off, &ctx->d_cvars, &ctx->d_cstr, &ctx->d_ws, &ctx->d_big_vars, &ctx->d_big_strs, &ctx->d_big_slot, &ctx->d_ws2, &ctx->d_wsm, &ctx->d_retry };
 	for (auto b : bufs) { if (b->p) { cudaFree(b->p); } }
 	if (ctx->comm) { lb2_comm_release(ctx->comm); }
 	{ lb2_ctx::Buf *cb[] = { &ctx->d_comm_send, &ctx->d_comm_recv, &ctx->d_comm_cnt }; for (auto b : cb) { if (b->p) { cudaFree(b->p); } } }
-	if (ctx->d_counters) { cudaFree(ctx->d_counters); } if (ctx->d_prof) { cudaFree(ctx->d_prof); } if (ctx->h_blk) { cudaFreeHost(ctx->h_blk); }
-	for (auto &e : ctx->ev) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_seg) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_w) { if (e) { cudaEventDestroy(e); } }
+	if (ctx->d_counters) { cudaFree(ctx->d_counters); } if (ctx->d_prof) { cudaFree(ctx->d_prof); }
+	for (auto &e : ctx->ev) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_seg) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_cp) { if (e) { cudaEventDestroy(e); } } for (auto &e : ctx->ev_w) { if (e) { cudaEventDestroy(e); } }
 	if (ctx->ev_ready) { cudaEventDestroy(ctx->ev_ready); }
-	if (ctx->stream) { cudaStreamDestroy(ctx->stream); } if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); }
+	if (ctx->stream) { cudaStreamDestroy(ctx->stream); } if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); } if (ctx->pack_stream) { cudaStreamDestroy(ctx->pack_stream); }
 	for (auto &st : ctx->wstream) { if (st) { cudaStreamDestroy(st); } }
 	cudaGetLastError();
 	delete ctx;
@@ -255,10 +260,11 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	cudaDeviceProp prop;
 	if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { return fail(); }
 	ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin;
-	cudaStream_t *streams[] = { &ctx->stream, &ctx->copy_stream, &ctx->wstream[0], &ctx->wstream[1] };
+	cudaStream_t *streams[] = { &ctx->stream, &ctx->copy_stream, &ctx->pack_stream, &ctx->wstream[0], &ctx->wstream[1] };
 	for (auto st : streams) { if (cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess) { return fail(); } }
 	for (auto &e : ctx->ev) { if (cudaEventCreate(&e) != cudaSuccess) { return fail(); } }
 	for (auto &e : ctx->ev_seg) { if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return fail(); } }
+	for (auto &e : ctx->ev_cp) { if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return fail(); } }
 	for (auto &e : ctx->ev_w) { if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return fail(); } }
 	if (cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess) { return fail(); }
 	lb2_cfg &C = ctx->C; memset(&C, 0, sizeof C);
@@ -267,7 +273,7 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 	C.arena_bytes = env_u32("LB2_ARENA_BYTES", 512u << 10); C.deficit_bytes = env_u32("LB2_DEFICIT_BYTES", 1u << 20);
 	C.max_inst = env_u32("LB2_MAX_INST", 1u << 18);
 	C.queue_cap = env_u32("LB2_QUEUE_CAP", 1u << 16); C.max_var = env_u32("LB2_MAX_VAR", 32); C.str_bytes = env_u32("LB2_STR_BYTES", 4096);
-	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 64); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
+	C.debug_flags = env_u32("LB2_DEBUG_FLAGS", 0); C.max_special = env_u32("LB2_MAX_SPECIAL", 128); C.bucket_cap = 10273; C.max_k = 127; C.graph_bytes = env_u32("LB2_GRAPH_BYTES", 48u << 10);
 	if (cudaMalloc(&ctx->d_prof, 24 * 8) != cudaSuccess || cudaMemset(ctx->d_prof, 0, 24 * 8) != cudaSuccess) { return fail(); }
 	if (cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess || cudaMemset(ctx->d_counters, 0, sizeof(uint32_t) * LB2_CTR_N) != cudaSuccess) { return fail(); }
 	ctx->escalate = env_u32("LB2_ESCALATE", 1) != 0; ctx->mid = env_u32("LB2_MID", 1) != 0;
@@ -279,11 +285,66 @@ extern "C" int lb2_create(lb2_ctx **out, const lb2_params *params, int device)
 
 extern "C" uint64_t lb2_kernel_launches(const lb2_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-// ---- planning: one pass over the windows' read lists (millions of entries for a 1 Mb region, split over a few host threads):
-// staging need per window (whole 16-base words of the untrimmed reads, up to 14 pad words per run of pool-consecutive reads,
-// the reference), reads per window, and how far into the pool the windows up to each window reach.  Then the launch
-// configuration, the device buffers and the launch descriptors.
-static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
+// ---- planning.  lb2_prepare_static: launch configuration of the first pass, device buffers, launch descriptor -- from the
+// batch header alone.  lb2_plan_windows: one pass over the windows' read lists (millions of entries for a 1 Mb region,
+// split over host threads): the one or two stretches of the pool every window's reads lie in, the deepest window's staging
+// need and read count (sizes of the escalation passes).  lb2_prepare_escalation: the configurations of the middle and the
+// last pass.  lb2_process runs the window pass beside the upload of its first segment.
+struct lb2_win_plan { uint32_t rng[4]; uint64_t bp; uint32_t nreads; bool bad; };
+static inline lb2_win_plan lb2_plan_one(const lb2_batch *b, uint32_t w)
+{
+	lb2_win_plan p; p.bad = false; p.bp = 0; p.nreads = 0; p.rng[0] = p.rng[1] = p.rng[2] = p.rng[3] = 0;
+	const uint32_t R = b->n_reads;
+	uint32_t top = 0, low = 0xFFFFFFFFu, prev = 0xFFFFFFFEu, gap = 0, gap_lo = 0, gap_hi = 0; bool ascending = true;
+	if (b->wr_off[w + 1] < b->wr_off[w] || b->wr_off[w + 1] > b->n_wr || b->ref_off[w + 1] < b->ref_off[w]) { p.bad = true; return p; }
+	for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
+		const uint32_t r = b->wr_idx[x]; if (r >= R) { p.bad = true; return p; }
+		p.bp += (uint64_t)lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]) * 16u;
+		if (r != prev + 1u) { p.bp += 14u * 16u; }
+		if (prev != 0xFFFFFFFEu) { if (r < prev) { ascending = false; } else if (r - prev > gap) { gap = r - prev; gap_lo = prev + 1; gap_hi = r; } }
+		prev = r;
+		if (r >= top) { top = r + 1; } if (r < low) { low = r; }
+	}
+	// one stretch [low, top), or two around the largest jump of an ascending list when that jump is worth it (a window's list is
+	// tumour reads then normal reads, each ascending: two stretches far apart in a pool that holds all tumour reads first)
+	if (top) {
+		if (ascending && gap > 8u * LB2_PACK_BLOCK) { p.rng[0] = low; p.rng[1] = gap_lo; p.rng[2] = gap_hi; p.rng[3] = top; }
+		else { p.rng[0] = low; p.rng[1] = top; }
+	}
+	p.bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; p.bp += 128;
+	p.nreads = b->wr_off[w + 1] - b->wr_off[w];
+	return p;
+}
+
+static int lb2_plan_windows(lb2_ctx *ctx, const lb2_batch *b)
+{
+	const uint32_t W = b->n_windows;
+	uint32_t max_bp = 0, max_reads = 0;
+	const unsigned hw = std::thread::hardware_concurrency();
+	const unsigned share = std::max(1u, hw / (unsigned)std::max(1, ctx->comm_world));      // (several ranks on one host share its cores)
+	const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(share, 16u), std::max(1u, env_u32("LB2_HOST_THREADS", 16))) : 1u;
+	std::vector<uint32_t> t_bp(T, 0), t_rd(T, 0); std::vector<int> t_bad(T, 0);
+	auto work = [&](unsigned t) {
+		const uint32_t w0 = (uint32_t)((uint64_t)W * t / T), w1 = (uint32_t)((uint64_t)W * (t + 1) / T);
+		uint32_t mbp = 0, mrd = 0;
+		for (uint32_t w = w0; w < w1; ++w) {
+			const lb2_win_plan p = lb2_plan_one(b, w);
+			if (p.bad) { t_bad[t] = 1; return; }
+			uint32_t *rg = ctx->h_rng.data() + 4 * (size_t)w; rg[0] = p.rng[0]; rg[1] = p.rng[1]; rg[2] = p.rng[2]; rg[3] = p.rng[3];
+			if (p.bp > mbp) { mbp = (uint32_t)std::min<uint64_t>(p.bp, 1u << 30); }
+			mrd = std::max(mrd, p.nreads);
+		}
+		t_bp[t] = mbp; t_rd[t] = mrd;
+	};
+	if (T == 1) { work(0); }
+	else { std::vector<std::thread> th; for (unsigned t = 0; t < T; ++t) { th.emplace_back(work, t); } for (auto &x : th) { x.join(); } }
+	for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); }
+	ctx->plan_need_bp = std::min<uint32_t>((max_bp + 1023) & ~1023u, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
+	ctx->plan_max_reads = max_reads;
+	return LB2_OK;
+}
+
+static int lb2_prepare_static(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 {
 	if (!ctx || !b) { return LB2_ERR_ARG; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
@@ -291,70 +352,20 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	cudaStreamSynchronize(ctx->stream);      // (work of an earlier batch may still read the buffers re-planned below)
 	const uint32_t W = b->n_windows, R = b->n_reads;
 	if ((W && (!b->ref_off || !b->ref_start || !b->wr_off)) || (R && (!b->base_off || !b->flags || !b->name_rank)) || (b->n_wr && !b->wr_idx)) { return LB2_ERR_ARG; }
-	uint32_t max_bp = 0, max_reads = 0;
-	ctx->h_need.resize(W);
-	{
-		const unsigned hw = std::thread::hardware_concurrency();
-		// (several ranks on one host share its cores: each takes its part)
-		const unsigned share = std::max(1u, hw / (unsigned)std::max(1, ctx->comm_world));
-		const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(share, 16u), std::max(1u, env_u32("LB2_HOST_THREADS", 16))) : 1u;
-		std::vector<uint32_t> t_bp(T, 0), t_rd(T, 0); std::vector<int> t_bad(T, 0);
-		auto work = [&](unsigned t) {
-			const uint32_t w0 = (uint32_t)((uint64_t)W * t / T), w1 = (uint32_t)((uint64_t)W * (t + 1) / T);
-			uint32_t mbp = 0, mrd = 0;
-			for (uint32_t w = w0; w < w1; ++w) {
-				uint64_t bp = 0; uint32_t top = 0, prev = 0xFFFFFFFEu;
-				if (b->wr_off[w + 1] < b->wr_off[w] || b->wr_off[w + 1] > b->n_wr || b->ref_off[w + 1] < b->ref_off[w]) { t_bad[t] = 1; return; }
-				for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
-					const uint32_t r = b->wr_idx[x]; if (r >= R) { t_bad[t] = 1; return; }
-					bp += (uint64_t)lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]) * 16u;
-					if (r != prev + 1u) { bp += 14u * 16u; }
-					prev = r;
-					if (r >= top) { top = r + 1; }
-				}
-				ctx->h_need[w] = top;
-				bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; bp += 128;
-				if (bp > mbp) { mbp = (uint32_t)std::min<uint64_t>(bp, 1u << 30); }
-				mrd = std::max(mrd, b->wr_off[w + 1] - b->wr_off[w]);
-			}
-			t_bp[t] = mbp; t_rd[t] = mrd;
-		};
-		if (T == 1) { work(0); }
-		else { std::vector<std::thread> th; for (unsigned t = 0; t < T; ++t) { th.emplace_back(work, t); } for (auto &x : th) { x.join(); } }
-		for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); }
-		uint32_t need = 0; for (uint32_t w = 0; w < W; ++w) { need = std::max(need, ctx->h_need[w]); ctx->h_need[w] = need; }
-	}
-	{	// packed words before every block of LB2_PACK_BLOCK reads (the pre-pack kernel's blocks start from these)
-		const size_t nblk = (size_t)R / LB2_PACK_BLOCK + 2;
-		if (nblk > ctx->h_blk_cap) { if (ctx->h_blk) { cudaFreeHost(ctx->h_blk); ctx->h_blk = nullptr; } LB2_CK(cudaHostAlloc((void **)&ctx->h_blk, sizeof(uint32_t) * (nblk + nblk / 2), cudaHostAllocDefault)); ctx->h_blk_cap = nblk + nblk / 2; }
-		const size_t nb_ = ((size_t)R + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK;
-		auto block_words = [&](size_t blk0, size_t blk1) {      // h_blk[blk] := words of the block's own reads
-			for (size_t k = blk0; k < blk1; ++k) {
-				const uint32_t ra_ = (uint32_t)(k * LB2_PACK_BLOCK), rb_ = (uint32_t)std::min<size_t>(R, (k + 1) * LB2_PACK_BLOCK); uint32_t wsum = 0;
-				for (uint32_t r = ra_; r < rb_; ++r) { wsum += lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]); }
-				ctx->h_blk[k] = wsum;
-			}
-		};
-		const unsigned hw2 = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, ctx->comm_world)); const unsigned T2 = (nb_ >= 64 && hw2 > 1) ? std::min<unsigned>(std::min<unsigned>(hw2, 16u), std::max(1u, env_u32("LB2_HOST_THREADS", 16))) : 1u;
-		if (T2 == 1) { block_words(0, nb_); }
-		else { std::vector<std::thread> th; for (unsigned t = 0; t < T2; ++t) { th.emplace_back(block_words, nb_ * t / T2, nb_ * (t + 1) / T2); } for (auto &x : th) { x.join(); } }
-		uint64_t words = 0;
-		for (size_t k = 0; k < nb_; ++k) { const uint32_t c = ctx->h_blk[k]; ctx->h_blk[k] = (uint32_t)words; words += c; }
-		ctx->h_blk[nb_] = (uint32_t)words;
-		if (words > 0xFFFFFF00ull) { ctx->err = "read pool too large for 32-bit word offsets: split the batch"; return LB2_ERR_ARG; }
-	}
-	const uint32_t need_bp = std::min<uint32_t>((max_bp + 1023) & ~1023u, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
+	if (b->n_base_bytes / 16 + R > 0xFFFFFF00ull) { ctx->err = "read pool too large for 32-bit word offsets: split the batch"; return LB2_ERR_ARG; }
+	ctx->h_rng.resize(4 * (size_t)W);
 	const uint32_t smem_cap = (uint32_t)std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : (227u << 10), 227u << 10) - 2048u;      // (static shared memory of the kernel comes on top)
+	ctx->smem_cap = smem_cap;
 	lb2_cfg &C = ctx->C;
 	C.table_slots = std::min<uint32_t>(env_u32("LB2_TABLE_SLOTS", 4096), 16384u);      // (occurrence words hold 14-bit slot numbers)
-	// First pass: sized for the windows that still let LB2_MIN_CTAS_PER_SM CTAs share an SM; a window that needs more staging
-	// area than that goes to the escalation pass, which has the whole SM to itself (one outlier must not cost every window
-	// of the batch its occupancy)
-	// (never less than 72 K bases: the staging area doubles as the scratch of the graph stage -- parallel first compaction,
-	// alignment rows, BFS queue head -- and those want ~18 KB whatever the depth of the windows)
-	uint32_t bp1 = std::max(need_bp, env_u32("LB2_MIN_BP", 73728u));
+	// First pass: the same configuration for every batch -- the largest staging area that still lets LB2_MIN_CTAS_PER_SM CTAs
+	// share an SM (it doubles as the scratch of the graph stage: parallel first compaction, alignment rows, BFS queue head
+	// want 18-21 KB whatever the depth of the windows), room for 4096 reads.  A window that needs more goes to the
+	// escalation passes, which are sized from the plan (one outlier must not cost every window its occupancy).
+	uint32_t bp1 = env_u32("LB2_MIN_BP", 94208u);
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-	{
+	if (ctx->bp1_cached && ctx->bp1_slots == C.table_slots) { bp1 = ctx->bp1_cached; }
+	else {
 		const uint32_t want_occ = std::max(1u, env_u32("LB2_MIN_CTAS_PER_SM", 3));
 		while (bp1 > 32768u) {
 			int occ = 0; const size_t sm = lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes);
@@ -362,10 +373,11 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 			bp1 -= 1024;
 		}
 		cudaGetLastError();
+		while (C.table_slots > 1024 && lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes) > smem_cap) { C.table_slots >>= 1; }
+		ctx->bp1_cached = bp1; ctx->bp1_slots = C.table_slots;
 	}
-	while (C.table_slots > 1024 && lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes) > smem_cap) { C.table_slots >>= 1; }
 	C.max_nodes = C.table_slots - C.table_slots / 4;
-	C.max_bp = bp1; C.smem_bytes = (uint32_t)lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes); C.max_reads = std::max(max_reads + 2, 64u);
+	C.max_bp = bp1; C.smem_bytes = (uint32_t)lb2_smem_bytes(bp1, C.table_slots, C.graph_bytes); C.max_reads = env_u32("LB2_MAX_READS", 4096) + 2;
 	int occ = 0;
 	LB2_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lb2_window_kernel, (int)ctx->threads, C.smem_bytes));
 	if (occ < 1) { ctx->err = "kernel does not fit on an SM"; return LB2_ERR_CUDA; }
@@ -383,7 +395,7 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	LB2_RS(d_wr_idx, sizeof(uint32_t) * (size_t)b->n_wr + 4); LB2_RS(d_base_off, sizeof(uint64_t) * (size_t)(R + 1)); LB2_RS(d_flags, (size_t)R + 4);
 	LB2_RS(d_name_rank, sizeof(uint32_t) * (size_t)R + 4); LB2_RS(d_ref_seq, (size_t)b->n_ref_bytes + 4); LB2_RS(d_seq, (size_t)b->n_base_bytes + 64); LB2_RS(d_qual, (size_t)b->n_base_bytes + 64);
 	const size_t pk_words = (size_t)(b->n_base_bytes / 16) + R + 64;
-	LB2_RS(d_pk, sizeof(lb2_pkread) * ((size_t)R + 1)); LB2_RS(d_pk_bits, 4 * pk_words); LB2_RS(d_pk_lowq, 2 * pk_words); LB2_RS(d_blk, sizeof(uint32_t) * ((size_t)R / LB2_PACK_BLOCK + 4));
+	LB2_RS(d_pk, sizeof(lb2_pkread) * ((size_t)R + 1)); LB2_RS(d_pk_bits, 4 * pk_words); LB2_RS(d_pk_lowq, 2 * pk_words);
 	LB2_RS(d_info, sizeof(lb2_window_info) * (size_t)W + 16); LB2_RS(d_vars, sizeof(lb2_variant) * (size_t)W * C.max_var + 64); LB2_RS(d_strs, (size_t)W * C.str_bytes + 64);
 	LB2_RS(d_str_used, sizeof(uint32_t) * (size_t)W + 4); LB2_RS(d_var_off, sizeof(uint32_t) * (size_t)W + 4); LB2_RS(d_str_off, sizeof(uint32_t) * (size_t)W + 4);
 	const uint32_t nbig = ctx->escalate ? std::min<uint32_t>(ctx->big_cap, std::max(W, 1u)) : 0u;
@@ -408,9 +420,16 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 	L.retry_list = (uint32_t *)ctx->d_retry.p; L.retry_count = ctx->d_counters + LB2_CTR_RETRY;
 	L.var_off = (uint32_t *)ctx->d_var_off.p; L.str_off = (uint32_t *)ctx->d_str_off.p; L.totals = ctx->d_counters + LB2_CTR_TOTALS;
 	L.cvars = (lb2_variant *)ctx->d_cvars.p; L.cstr = (char *)ctx->d_cstr.p;
+	ctx->n_windows = W; ctx->n_reads = R;
+	return LB2_OK;
+}
+
+static int lb2_prepare_escalation(lb2_ctx *ctx)
+{
+	const lb2_cfg &C = ctx->C; const lb2_launch &L = ctx->L; const uint32_t smem_cap = ctx->smem_cap, bp1 = C.max_bp, need_bp = ctx->plan_need_bp;
 	if (ctx->escalate) {
 		// escalation pass: one CTA per SM, the largest staging area / table / graph region that fit, big arena / BFS queue
-		lb2_cfg &C2 = ctx->C2; C2 = C;
+		lb2_cfg &C2 = ctx->C2; C2 = C; C2.max_reads = std::max(C.max_reads, ctx->plan_max_reads + 2);
 		C2.table_slots = std::min<uint32_t>(env_u32("LB2_TABLE_SLOTS2", 16384), 16384u); C2.graph_bytes = env_u32("LB2_GRAPH_BYTES2", 184u << 10);
 		C2.max_bp = std::max(need_bp, bp1);
 		while (C2.graph_bytes > C.graph_bytes && lb2_smem_bytes(C2.max_bp, C2.table_slots, C2.graph_bytes) > smem_cap) { C2.graph_bytes -= 4096; }
@@ -439,7 +458,7 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 			}
 			cudaGetLastError();
 			Cm.max_nodes = Cm.table_slots - Cm.table_slots / 4; Cm.smem_bytes = (uint32_t)lb2_smem_bytes(Cm.max_bp, Cm.table_slots, Cm.graph_bytes);
-			Cm.arena_bytes = 2u << 20; Cm.deficit_bytes = 4u << 20; Cm.queue_cap = 1u << 20; Cm.max_inst = 1u << 19; Cm.max_special = 512;
+			Cm.arena_bytes = 2u << 20; Cm.deficit_bytes = 4u << 20; Cm.queue_cap = 1u << 20; Cm.max_inst = 1u << 19; Cm.max_special = 2048;
 			int occ_m = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, lb2_window_kernel, (int)ctx->threads, Cm.smem_bytes); cudaGetLastError();
 			Cm.n_slots = (uint32_t)ctx->sm_count * (uint32_t)std::max(1, std::min(occ_m, 2));
 			const size_t stridem = lb2_ws_layout(Cm, nullptr, nullptr);
@@ -448,7 +467,6 @@ static int lb2_prepare(lb2_ctx *ctx, const lb2_batch *b, bool two_sets)
 			Lm.ws_base = nullptr; Lm.ws_stride = stridem; Lm.counter = ctx->d_counters + LB2_MAX_SEG + 1;
 		}
 	}
-	ctx->n_windows = W; ctx->n_reads = R;
 	return LB2_OK;
 }
 
@@ -457,10 +475,9 @@ static int lb2_enqueue_pack(lb2_ctx *ctx, uint32_t r0, uint32_t r1, cudaStream_t
 {
 	if (r1 <= r0) { return LB2_OK; }
 	if (r0 % LB2_PACK_BLOCK) { return LB2_ERR_ARG; }
-	const uint32_t nblk = (r1 - r0 + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK, b0 = r0 / LB2_PACK_BLOCK; uint32_t *blk = (uint32_t *)ctx->d_blk.p;
+	const uint32_t nblk = (r1 - r0 + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK;
 	const uint32_t qt = (uint32_t)ctx->P.min_qual_trim & 0xFFu, qc = (uint32_t)ctx->P.min_qual_call & 0xFFu;
-	LB2_CK(cudaMemcpyAsync(blk + b0, ctx->h_blk + b0, sizeof(uint32_t) * nblk, cudaMemcpyHostToDevice, st));
-	lb2_pack_kernel<<<nblk, LB2_PACK_THREADS, 0, st>>>(ctx->L.B, (lb2_pkread *)ctx->d_pk.p, (uint32_t *)ctx->d_pk_bits.p, (uint16_t *)ctx->d_pk_lowq.p, qt * 0x01010101u, qc * 0x01010101u, r0, r1, blk + b0);
+	lb2_pack_kernel<<<nblk, LB2_PACK_THREADS, 0, st>>>(ctx->L.B, (lb2_pkread *)ctx->d_pk.p, (uint32_t *)ctx->d_pk_bits.p, (uint16_t *)ctx->d_pk_lowq.p, qt * 0x01010101u, qc * 0x01010101u, r0, r1);
 	ctx->launches += 1;
 	LB2_CK(cudaGetLastError());
 	return LB2_OK;
@@ -526,7 +543,9 @@ static int lb2_enqueue_reset(lb2_ctx *ctx, cudaStream_t st)
 
 extern "C" int lb2_upload(lb2_ctx *ctx, const lb2_batch *b)
 {
-	int rc = lb2_prepare(ctx, b, false); if (rc) { return rc; }
+	int rc = lb2_prepare_static(ctx, b, false); if (rc) { return rc; }
+	if ((rc = lb2_plan_windows(ctx, b))) { return rc; }
+	if ((rc = lb2_prepare_escalation(ctx))) { return rc; }
 	const uint32_t W = b->n_windows, R = b->n_reads; uint64_t h2d = 0;
 #define LB2_UP(buf, ptr, bytes) do { if (bytes) { LB2_CK(cudaMemcpyAsync(ctx->buf.p, (ptr), (bytes), cudaMemcpyHostToDevice, ctx->stream)); h2d += (bytes); } } while (0)
 	LB2_UP(d_ref_off, b->ref_off, sizeof(uint32_t) * (size_t)(W + 1)); LB2_UP(d_ref_start, b->ref_start, sizeof(int32_t) * (size_t)W); LB2_UP(d_wr_off, b->wr_off, sizeof(uint32_t) * (size_t)(W + 1));
@@ -546,7 +565,7 @@ extern "C" int lb2_run(lb2_ctx *ctx)
 	if (!ctx->resident) { return LB2_ERR_STATE; }
 	if (cudaSetDevice(ctx->device) != cudaSuccess) { return LB2_ERR_CUDA; }
 	const uint32_t W = ctx->n_windows; int rc;
-	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? std::max(ctx->C2.smem_bytes, ctx->mid ? ctx->Cm.smem_bytes : 0u) : 0u)));
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cap));
 	if ((rc = lb2_enqueue_reset(ctx, ctx->stream))) { return rc; }
 	LB2_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 	if (W) { if ((rc = lb2_enqueue_pack(ctx, 0, ctx->n_reads, ctx->stream))) { return rc; } }
@@ -604,57 +623,100 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 		}
 		cudaGetLastError();
 	}
-	int rc = lb2_prepare(ctx, batch, pinned); if (rc) { return rc; }
+	int rc = lb2_prepare_static(ctx, batch, pinned); if (rc) { return rc; }
 	const uint32_t W = ctx->n_windows, R = ctx->n_reads;
-	// segments: the first one small (the kernels start after it), then doubling; cut at window boundaries by pool bytes
-	std::vector<lb2_seg> segs;
-	{
-		const uint64_t nb = batch->n_base_bytes;
-		const uint64_t first = std::max<uint64_t>(env_u32("LB2_SEG_FIRST", 4u << 20), 1u << 16), min_w = std::max(1u, env_u32("LB2_SEG_MIN_WINDOWS", 512));
-		uint64_t lim = first, chunk = first; uint32_t wa = 0, ra = 0;
-		while (wa < W) {
-			uint32_t wb = W;
-			if (pinned && segs.size() + 1 < LB2_MAX_SEG && nb > 2 * first) {
-				wb = wa + 1;
-				while (wb < W && (batch->base_off[ctx->h_need[wb]] <= lim || wb - wa < min_w)) { ++wb; }
-				if (W - wb < min_w) { wb = W; }
-			}
-			lb2_seg sg; sg.w0 = wa; sg.w1 = wb; sg.r0 = ra;
-			sg.r1 = (wb == W) ? R : std::min<uint32_t>(R, (std::max(ra, ctx->h_need[wb - 1]) + LB2_PACK_BLOCK - 1) / LB2_PACK_BLOCK * LB2_PACK_BLOCK);      // (whole pack blocks)
-			segs.push_back(sg); wa = wb; ra = sg.r1; chunk *= 2; lim = batch->base_off[ra] + chunk;
-		}
-	}
+	// The pass over the windows' read lists runs on its own thread(s) beside the upload of the first segment, whose few
+	// hundred windows are planned right here; everything the first-pass launches need is fixed by lb2_prepare_static.
+	int plan_rc = LB2_OK; std::thread planner; struct lb2_joiner { std::thread &t; ~lb2_joiner() { if (t.joinable()) { t.join(); } } } joiner{ planner };
+	bool planning = false;
+	if (pinned && W >= 4096 && env_u32("LB2_PLAN_OVERLAP", 1)) { planner = std::thread([&]() { plan_rc = lb2_plan_windows(ctx, batch); }); planning = true; }
+	else { if ((rc = lb2_plan_windows(ctx, batch))) { return rc; } if ((rc = lb2_prepare_escalation(ctx))) { return rc; } }
 	const auto t1 = std::chrono::steady_clock::now();
-	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ctx->C.smem_bytes, ctx->escalate ? std::max(ctx->C2.smem_bytes, ctx->mid ? ctx->Cm.smem_bytes : 0u) : 0u)));
+	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cap));
 	if ((rc = lb2_enqueue_reset(ctx, ctx->stream))) { return rc; }
 	LB2_CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 	LB2_CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
-	LB2_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));      // (the pack carry is one of the counters just reset)
+	LB2_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
 	LB2_CK(cudaStreamWaitEvent(ctx->wstream[0], ctx->ev_ready, 0)); LB2_CK(cudaStreamWaitEvent(ctx->wstream[1], ctx->ev_ready, 0));
 	uint64_t h2d = 0;
 	// (LB2_TIMING=1: a device time line of the segments -- copy + pre-pack done, window launch begin / end)
-	std::vector<cudaEvent_t> tl; if (timing) { tl.resize(3 * segs.size()); for (auto &e : tl) { cudaEventCreate(&e); } }
+	std::vector<cudaEvent_t> tl; if (timing) { tl.resize(3 * LB2_MAX_SEG); for (auto &e : tl) { cudaEventCreate(&e); } }
 #define LB2_PIECE(buf, ptr, esz, from, to) do { if ((to) > (from)) { LB2_CK(cudaMemcpyAsync((char *)ctx->buf.p + (size_t)(from) * (esz), (const char *)(ptr) + (size_t)(from) * (esz), \
 		(size_t)((to) - (from)) * (esz), cudaMemcpyHostToDevice, ctx->copy_stream)); h2d += (uint64_t)((to) - (from)) * (esz); } } while (0)
 	LB2_PIECE(d_ref_off, batch->ref_off, 4, (size_t)0, (size_t)W + 1); LB2_PIECE(d_ref_start, batch->ref_start, 4, (size_t)0, (size_t)W); LB2_PIECE(d_wr_off, batch->wr_off, 4, (size_t)0, (size_t)W + 1);
-	for (size_t s = 0; s < segs.size(); ++s) {
-		const lb2_seg &sg = segs[s];
+	// segments: the first one small (the kernels start after it), then doubling; a segment = consecutive windows + the pack
+	// blocks of the pool they touch that no earlier segment has uploaded (a bitmap over the blocks)
+	std::vector<lb2_seg> segs;
+	const uint64_t nb = batch->n_base_bytes; const uint32_t PB = LB2_PACK_BLOCK, nblk = (R + PB - 1) / PB;
+	const uint64_t first = std::max<uint64_t>(env_u32("LB2_SEG_FIRST", 4u << 20), 1u << 16), min_w = std::max(1u, env_u32("LB2_SEG_MIN_WINDOWS", 512));
+	std::vector<uint8_t> up(nblk + 1, 0);
+	auto blk_bytes = [&](uint32_t k) -> uint64_t { const uint32_t ra_ = k * PB, rb_ = std::min(R, (k + 1) * PB); return batch->base_off[rb_] - batch->base_off[ra_]; };
+	uint64_t chunk = first; uint32_t wa = 0;
+	const bool split = pinned && nb > 2 * first;
+	while (wa < W) {
+		const size_t s = segs.size();
+		lb2_seg sg; sg.w0 = wa; sg.nr = 0;
+		{
+			uint32_t lo[2] = { 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[2] = { 0, 0 }; uint64_t fresh = 0; uint32_t wb = wa;      // block ranges of the two stretches
+			auto cover = [&](int which, uint32_t r0_, uint32_t r1_) {      // extend stretch `which` to cover reads [r0_, r1_); count the bytes of blocks not uploaded yet
+				if (r1_ <= r0_) { return; }
+				const uint32_t k0 = r0_ / PB, k1 = (r1_ + PB - 1) / PB;
+				if (lo[which] == 0xFFFFFFFFu) { lo[which] = k0; hi[which] = k0; }
+				for (uint32_t k = k0; k < lo[which]; ++k) { if (!up[k]) { fresh += blk_bytes(k); } }
+				for (uint32_t k = std::max(hi[which], k0); k < k1; ++k) { if (!up[k]) { fresh += blk_bytes(k); } }
+				lo[which] = std::min(lo[which], k0); hi[which] = std::max(hi[which], k1);
+			};
+			while (wb < W) {
+				if (split && s + 1 < LB2_MAX_SEG && wb - wa >= min_w && fresh > chunk && W - wb >= min_w) { break; }
+				if (planning) {      // (the plan is still being made: this window's stretches are worked out on the spot)
+					const lb2_win_plan wp = lb2_plan_one(batch, wb);
+					if (wp.bad) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->pack_stream); cudaStreamSynchronize(ctx->wstream[0]); cudaStreamSynchronize(ctx->wstream[1]); return LB2_ERR_ARG; }
+					cover(0, wp.rng[0], wp.rng[1]); cover(1, wp.rng[2], wp.rng[3]);
+				} else { const uint32_t *rg = ctx->h_rng.data() + 4 * (size_t)wb; cover(0, rg[0], rg[1]); cover(1, rg[2], rg[3]); }
+				++wb;
+			}
+			sg.w1 = wb;
+			if (lo[0] != 0xFFFFFFFFu && lo[1] != 0xFFFFFFFFu && !(hi[0] < lo[1] || hi[1] < lo[0])) { lo[0] = std::min(lo[0], lo[1]); hi[0] = std::max(hi[0], hi[1]); lo[1] = 0xFFFFFFFFu; }      // the two stretches met
+			for (int q = 0; q < 2; ++q) {      // blocks of each stretch that are not on the device yet: at most two runs per stretch are kept apart, more are bridged
+				if (lo[q] == 0xFFFFFFFFu) { continue; }
+				uint32_t k = lo[q]; int runs = 0;
+				while (k < hi[q]) {
+					while (k < hi[q] && up[k]) { ++k; }
+					if (k >= hi[q]) { break; }
+					uint32_t e = k; while (e < hi[q] && !up[e]) { ++e; }
+					if (runs == 1) { uint32_t last = hi[q]; while (last > e && up[last - 1]) { --last; } e = last; }      // (second run of this stretch: take the rest in one piece)
+					for (uint32_t z = k; z < e; ++z) { up[z] = 1; }
+					sg.r0[sg.nr] = k * PB; sg.r1[sg.nr] = std::min(R, e * PB); ++sg.nr; ++runs; k = e;
+				}
+			}
+			segs.push_back(sg); wa = wb; chunk *= 2;
+		}
 		LB2_PIECE(d_ref_seq, batch->ref_seq, 1, (size_t)batch->ref_off[sg.w0], (size_t)batch->ref_off[sg.w1]);
 		LB2_PIECE(d_wr_idx, batch->wr_idx, 4, (size_t)batch->wr_off[sg.w0], (size_t)batch->wr_off[sg.w1]);
-		if (sg.r1 > sg.r0) {
-			LB2_PIECE(d_base_off, batch->base_off, 8, (size_t)sg.r0, (size_t)sg.r1 + 1);
-			LB2_PIECE(d_flags, batch->flags, 1, (size_t)sg.r0, (size_t)sg.r1); LB2_PIECE(d_name_rank, batch->name_rank, 4, (size_t)sg.r0, (size_t)sg.r1);
-			LB2_PIECE(d_seq, batch->seq, 1, (size_t)batch->base_off[sg.r0], (size_t)batch->base_off[sg.r1]);
-			LB2_PIECE(d_qual, batch->qual, 1, (size_t)batch->base_off[sg.r0], (size_t)batch->base_off[sg.r1]);
-			if ((rc = lb2_enqueue_pack(ctx, sg.r0, sg.r1, ctx->copy_stream))) { return rc; }
+		for (uint32_t q = 0; q < sg.nr; ++q) {
+			const uint32_t r0 = sg.r0[q], r1 = sg.r1[q]; if (r1 <= r0) { continue; }
+			LB2_PIECE(d_base_off, batch->base_off, 8, (size_t)r0, (size_t)r1 + 1);
+			LB2_PIECE(d_flags, batch->flags, 1, (size_t)r0, (size_t)r1); LB2_PIECE(d_name_rank, batch->name_rank, 4, (size_t)r0, (size_t)r1);
+			LB2_PIECE(d_seq, batch->seq, 1, (size_t)batch->base_off[r0], (size_t)batch->base_off[r1]);
+			LB2_PIECE(d_qual, batch->qual, 1, (size_t)batch->base_off[r0], (size_t)batch->base_off[r1]);
 		}
-		LB2_CK(cudaEventRecord(ctx->ev_seg[s], ctx->copy_stream));
-		if (timing) { cudaEventRecord(tl[3 * s], ctx->copy_stream); }
+		// the pre-pack pass runs on its own stream: when its blocks have to wait for room beside the window CTAs, the copies of
+		// the next segment go on regardless
+		LB2_CK(cudaEventRecord(ctx->ev_cp[s], ctx->copy_stream));
+		LB2_CK(cudaStreamWaitEvent(ctx->pack_stream, ctx->ev_cp[s], 0));
+		for (uint32_t q = 0; q < sg.nr; ++q) { if (sg.r1[q] > sg.r0[q]) { if ((rc = lb2_enqueue_pack(ctx, sg.r0[q], sg.r1[q], ctx->pack_stream))) { return rc; } } }
+		LB2_CK(cudaEventRecord(ctx->ev_seg[s], ctx->pack_stream));
+		if (timing) { cudaEventRecord(tl[3 * s], ctx->pack_stream); }
 		cudaStream_t ws = ctx->wstream[s & 1];
 		LB2_CK(cudaStreamWaitEvent(ws, ctx->ev_seg[s], 0));
 		if (timing) { cudaEventRecord(tl[3 * s + 1], ws); }
 		if ((rc = lb2_enqueue_windows(ctx, sg.w0, sg.w1, pinned ? (uint32_t)(s & 1) : 0u, (uint32_t)s, ws))) { return rc; }
 		if (timing) { cudaEventRecord(tl[3 * s + 2], ws); }
+		if (planning) {      // the first segment is on its way: now the plan is needed (stretches of the other windows, sizes of the escalation passes)
+			planner.join(); planning = false;
+			if (plan_rc == LB2_OK) { plan_rc = lb2_prepare_escalation(ctx); }
+			if (plan_rc != LB2_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->pack_stream); cudaStreamSynchronize(ctx->wstream[0]); cudaStreamSynchronize(ctx->wstream[1]); return plan_rc; }
+		}
 	}
 #undef LB2_PIECE
 	ctx->h2d_bytes = h2d;
@@ -664,7 +726,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	LB2_CK(cudaEventRecord(ctx->ev[4], ctx->stream));
 	ctx->ran = true; ctx->resident = true;
 	const auto t2 = std::chrono::steady_clock::now();
-	LB2_CK(cudaStreamSynchronize(ctx->copy_stream));      // the caller's buffers are free again when the call returns
+	LB2_CK(cudaStreamSynchronize(ctx->copy_stream)); LB2_CK(cudaStreamSynchronize(ctx->pack_stream));      // the caller's buffers are free again when the call returns
 	const auto t3 = std::chrono::steady_clock::now();
 	rc = lb2_download(ctx, result);
 	if (timing) {
@@ -672,7 +734,7 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 		auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b_) { return std::chrono::duration<double, std::milli>(b_ - a).count(); };
 		for (size_t s_ = 0; s_ < segs.size() && !tl.empty(); ++s_) {
 			float a = 0, b_ = 0, c = 0; cudaEventElapsedTime(&a, ctx->ev[0], tl[3 * s_]); cudaEventElapsedTime(&b_, ctx->ev[0], tl[3 * s_ + 1]); cudaEventElapsedTime(&c, ctx->ev[0], tl[3 * s_ + 2]);
-			fprintf(stderr, "  segment %zu: windows [%u, %u) reads [%u, %u): copied+packed at %.2f ms, windows %.2f .. %.2f ms\n", s_, segs[s_].w0, segs[s_].w1, segs[s_].r0, segs[s_].r1, a, b_, c);
+			fprintf(stderr, "  segment %zu: windows [%u, %u) reads [%u, %u)%s: copied+packed at %.2f ms, windows %.2f .. %.2f ms\n", s_, segs[s_].w0, segs[s_].w1, segs[s_].nr ? segs[s_].r0[0] : 0u, segs[s_].nr ? segs[s_].r1[0] : 0u, segs[s_].nr > 1 ? " + more" : "", a, b_, c);
 		}
 		for (auto &e : tl) { cudaEventDestroy(e); }
 		fprintf(stderr, "lb2_process: %zu segment(s)%s, plan %.2f ms, enqueue %.2f ms, copies done +%.2f ms, kernels+download +%.2f ms, total %.2f ms (device span %.2f ms)\n",

@@ -935,8 +935,9 @@ LB2_DEVNI bool lb2_compress_par(lb2_win &W, int compid)
 #ifdef LB2_HOSTSIM
 	if (getenv("LB2_SIM_NOPAR")) { LB2_DBG(1); return false; }
 #endif
-	if ((size_t)NT * 5 + 16 > ws.px_words || (W.C->debug_flags & 1u)) { LB2_DBG(1); return false; }
-	uint32_t *J = ws.px, *SEED = J + 2 * NT, *INF = SEED + NT; float *RCP = (float *)(INF + NT);
+	if ((size_t)NT * 4 + 16 > ws.px_words || (W.C->debug_flags & 1u)) { LB2_DBG(1); return false; }
+	// (the reciprocals are written once and read once per chain slot: they live in the slab's scratch, not in shared memory)
+	uint32_t *J = ws.px, *SEED = J + 2 * NT, *INF = SEED + NT; float *RCP = (float *)ws.emu;
 	lb2_edge *etmp = ws.etmp; uint8_t *etn = (uint8_t *)(ws.etmp + (size_t)LB2_MAX_ROWS * LB2_ECAP);
 	lb2_job *jobs = (lb2_job *)ws.jobs;
 	// eligibility (d_color is idle between the cycle checks)
