@@ -636,6 +636,7 @@ int main(int argc, char **argv)
 	// itself and continues as rank 0; every rank assembles a contiguous range of the windows on its own GPU, the records are
 	// gathered on rank 0 over NCCL (lb2_comm_gather), rank 0 replays them into the variant store and writes the VCF
 	vector<pid_t> children;
+	if (o.gpus > 1 || o.world > 1) { setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); }      // stdout carries the VCF and nothing else
 	if (o.gpus > 1 && o.rank < 0) {
 		char id[LB2_COMM_ID_BYTES];
 		if (lb2_comm_unique_id(id) != LB2_OK) { std::cerr << "ERROR: cannot create the NCCL id (no GPU / no NCCL)" << std::endl; return 2; }
