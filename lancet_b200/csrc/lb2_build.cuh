@@ -241,7 +241,6 @@ LB2_DEVNI void lb2_stage_window(lb2_win &W, uint32_t w)
 //               ibase + offset * istride: transposed (offset-major) so that the lanes of a warp -- one read each, same
 //               offset -- store to consecutive words; read-major when the transposed array would not fit
 // ---------------------------------------------------------------------------------------------
-#define LB2_SEEN_WORDS 64         /* reads per window (x32) the mate replay can take its shortcut for */
 #define LB2_EM_NORMAL 0x100u
 #define LB2_EM_TUMOR  0x200u
 #define LB2_ID_BRANCH 0x8000u
@@ -755,17 +754,77 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	//      finds the read's name in the node's list of names of the OTHER mate order -- a list that is in push
 	//      order (unsorted) at that time.  Queries of one read only look at lists fed by reads of
 	//      the other mate order, so per node it suffices to replay its occurrences in read order.
-	if (sh->has_pairs) {
-		// The occurrences of every node in read order: a counting sort by node.  Every warp owns a contiguous stretch of
-		// reads (about the same number of occurrences each), counts its occurrences per node, the per-(warp, node) counts
-		// are turned into first positions (node's start + the counts of the warps before), and the warp then walks its
-		// reads again, 32 consecutive occurrences at a time, handing out positions in order (lanes holding the same node
-		// rank themselves by lane number: __match_any).  occ[pos] = read << 12 | offset.
+	// Which nodes need the replay at all?  A read's name can only be found in the other mate order's list if its mate
+	// (rd_mate, the window's other read of that name) has had an occurrence in the same node before -- binary_search on
+	// the unsorted list may miss a name that is there, it never finds one that is not.  So: the (node, read) pairs of every
+	// read whose mate comes later in the window go into an exact open-addressing set (global scratch), the occurrences of
+	// the later mates look their (node, mate) up, hits mark the node in a bitmap.  Mates that do not overlap mark nothing,
+	// and nothing below runs; otherwise only the marked nodes' occurrences are sorted and replayed, and inside the replay
+	// only the reads whose mate is in the set search the list (for everybody else the answer is known to be "not found").
+	uint32_t *const nbm = (uint32_t *)(W.treg + (size_t)TS * 6);      // (region T behind the table: idle until the graph stage)
+	const uint32_t nbm_words = (n + 31u) >> 5;
+	const bool nbm_fits = lb2_treg_bytes(TS, C->graph_bytes, C->max_bp) >= (size_t)TS * 6 + (size_t)nbm_words * 4 + 16;
+	uint32_t *const pset = (uint32_t *)ws.deficit;      // (the deficit counters come after the replay)
+	uint32_t smask = 0, hshift = 32; bool use_set = false;
+	if (tid == 0) { sh->flag_b = (sh->has_pairs == 2) ? 1u : 0u; }
+	if (sh->has_pairs && nbm_fits) { for (uint32_t i = tid; i < nbm_words; i += nt) { nbm[i] = 0; } }
+	lb2_sync();
+	if (sh->has_pairs == 1) {
+		const uint32_t total = ws.rd_kbase[R];
+		uint32_t cap = 1024; while (cap < total + 16u) { cap <<= 1; }
+		if ((size_t)cap * 4 > (size_t)C->deficit_bytes || R > 0x3FFFu || !nbm_fits) { if (tid == 0) { sh->flag_b = 1; } }      // no room: replay every node (exact either way)
+		else {
+			use_set = true; smask = cap - 1u; while ((1u << (32 - hshift)) < cap) { --hshift; }      // slot = top bits of key * odd constant
+			for (uint32_t i = tid; i < cap; i += nt) { pset[i] = 0; }
+			lb2_sync();
+			// one lane per read, its occurrences in offset order (offset-major storage: the lanes of a warp, on consecutive reads,
+			// load consecutive words), four loads in flight per lane; pass 0 inserts the reads whose mate comes later, pass 1
+			// looks the mates of the others up
+			const uint16_t *const INST = ws.inst; const uint16_t *const TID = W.t_id;
+			for (int pass = 0; pass < 2; ++pass) {
+				for (uint32_t r = tid; r < R; r += nt) {
+					const uint32_t q = ws.rd_mate[r]; if (q == LB2_NIL) { continue; }
+					if ((pass == 0) != (q > r)) { continue; }
+					const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb, who = ((pass == 0) ? r : q) & 0x3FFFu;
+					for (uint32_t o0 = 0; o0 < nk; o0 += 8) {      // eight occurrences at a time: their loads, then their first probes, are all in flight together
+						uint32_t iw[8], key[8], h[8], got[8];
+#pragma unroll
+						for (uint32_t u = 0; u < 8; ++u) { iw[u] = (o0 + u < nk) ? INST[ib + (o0 + u) * istr] : 0xFFFFFFFFu; }
+#pragma unroll
+						for (uint32_t u = 0; u < 8; ++u) {
+							if (iw[u] == 0xFFFFFFFFu) { key[u] = 0; h[u] = 0; got[u] = 0; continue; }
+							const uint32_t j = TID[iw[u] & 0x3FFFu] & 0x7FFFu; key[u] = ((j + 1u) << 14) | who; h[u] = ((key[u] * 2654435761u) >> hshift) & smask;
+							got[u] = (pass == 0) ? lb2x_cas32(&pset[h[u]], 0u, key[u]) : pset[h[u]];
+						}
+#pragma unroll
+						for (uint32_t u = 0; u < 8; ++u) {
+							if (!key[u]) { continue; }
+							if (pass == 0) { while (!(got[u] == 0u || got[u] == key[u])) { h[u] = (h[u] + 1u) & smask; got[u] = lb2x_cas32(&pset[h[u]], 0u, key[u]); } }
+							else {
+								while (got[u] != 0u && got[u] != key[u]) { h[u] = (h[u] + 1u) & smask; got[u] = pset[h[u]]; }
+								if (got[u] == key[u]) { const uint32_t j = (key[u] >> 14) - 1u; lb2_or32(&nbm[j >> 5], 1u << (j & 31u)); sh->flag_b = 1; }
+							}
+						}
+					}
+				}
+				lb2_sync();
+			}
+		}
+		lb2_sync();
+	}
+	if (sh->has_pairs && sh->flag_b) {
+		const bool all_nodes = !use_set;      // (complex names, or no room for the set / the bitmap)
+		auto marked = [&](uint32_t j) -> bool { return all_nodes || ((lb2_lds(&nbm[j >> 5]) >> (j & 31u)) & 1u); };
+		// The occurrences of every marked node in read order: a counting sort by node.  Every warp owns a contiguous stretch
+		// of reads (about the same number of occurrences each); counts per (warp, node) are turned into first positions
+		// (node's start + the counts of the warps before); the warp then walks its occurrences by occurrence number, 32 at
+		// a time, handing out positions in order (lanes holding the same node rank themselves by lane number:
+		// __match_any).  occ[pos] = read << 12 | offset.
 		const uint32_t total = ws.rd_kbase[R];
 		uint32_t *nstart = ws.b_row;                  // free until lb2_order_and_pack
 		uint32_t *occ = (uint32_t *)ws.sortk, *wcnt = ws.bseq;      // (bseq: 8 words per node, idle until the edges are built)
 		const uint32_t NW = nt / LB2_WARP, wid = tid / LB2_WARP, lane = lb2_lane();
-		lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return ws.b_cnt[j * 4] + ws.b_cnt[j * 4 + 1] + ws.b_cnt[j * 4 + 2] + ws.b_cnt[j * 4 + 3]; },
+		lb2_excl_scan(W, n, [&](uint32_t j) -> uint32_t { return marked(j) ? ws.b_cnt[j * 4] + ws.b_cnt[j * 4 + 1] + ws.b_cnt[j * 4 + 2] + ws.b_cnt[j * 4 + 3] : 0u; },
 		              [&](uint32_t j, uint32_t v) { nstart[j] = v; });
 		if (NW > 8) { if (tid == 0) { sh->err |= 1u << LB2_D_READS; } }
 		for (uint32_t i = tid; i < NW * n && NW <= 8; i += nt) { wcnt[i] = 0; }
@@ -777,18 +836,43 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		}
 		lb2_sync();
 		if (sh->err) { return; }
-		for (uint32_t r = ra; r < rb; ++r) {
-			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
-			for (uint32_t o = lane; o < nk; o += LB2_WARP) { lb2g_red_add(&wcnt[wid * n + W.t_id[ws.inst[ib + o * istr] & 0x3FFFu]], 1u); }
+		{	// pass 1: counts per (owning warp, node), one lane per read, four loads in flight
+			uint32_t *bounds = sh->scan;      // first read of every warp's stretch (scan[] is idle between the block scans)
+			if (lane == 0) { bounds[wid] = ra; if (wid + 1 == NW) { bounds[NW] = R; } }
+			lb2_sync();
+			const uint16_t *const INST = ws.inst; const uint16_t *const TID = W.t_id;
+			for (uint32_t r = tid; r < R; r += nt) {
+				uint32_t w = 0; while (w + 1 < NW && bounds[w + 1] <= r) { ++w; }
+				const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
+				for (uint32_t o0 = 0; o0 < nk; o0 += 4) {
+					uint32_t iw[4];
+#pragma unroll
+					for (uint32_t u = 0; u < 4; ++u) { iw[u] = (o0 + u < nk) ? INST[ib + (o0 + u) * istr] : 0xFFFFFFFFu; }
+#pragma unroll
+					for (uint32_t u = 0; u < 4; ++u) { if (iw[u] != 0xFFFFFFFFu) { const uint32_t j = TID[iw[u] & 0x3FFFu] & 0x7FFFu; if (marked(j)) { lb2g_red_add(&wcnt[w * n + j], 1u); } } }
+				}
+			}
 		}
 		lb2_sync();
 		for (uint32_t j = tid; j < n; j += nt) { uint32_t run = nstart[j]; for (uint32_t w = 0; w < NW; ++w) { const uint32_t c = wcnt[w * n + j]; wcnt[w * n + j] = run; run += c; } }
 		lb2_sync();
-		for (uint32_t r = ra; r < rb; ++r) {
-			const uint32_t kb = ws.rd_kbase[r], nk = ws.rd_kbase[r + 1] - kb, ib = sh->inst_stride ? r : kb;
-			for (uint32_t o0 = 0; o0 < nk; o0 += LB2_WARP) {
-				const uint32_t o = o0 + lane; const bool act = o < nk;
-				const uint32_t j = act ? (uint32_t)W.t_id[ws.inst[ib + o * istr] & 0x3FFFu] : 0xFFFFFFFFu;
+		{	// pass 3: the warp's occurrences by occurrence number, 32 at a time, the next tile's word on its way while this one is placed
+			const uint16_t *const INST = ws.inst; const uint16_t *const TID = W.t_id;
+			const uint32_t xa = (ra < R) ? ws.rd_kbase[ra] : total, xb = (rb < R) ? ws.rd_kbase[rb] : total;
+			uint32_t rr = ra;      // this lane's read cursor (occurrence numbers grow by LB2_WARP per tile)
+			auto fetch = [&](uint32_t x, uint32_t &r_, uint32_t &o_) -> uint32_t {
+				while (rr + 1 < R && x >= ws.rd_kbase[rr + 1]) { ++rr; }
+				r_ = rr; o_ = x - ws.rd_kbase[rr];
+				return INST[(sh->inst_stride ? rr : ws.rd_kbase[rr]) + o_ * istr];
+			};
+			uint32_t x = xa + lane, r_n = 0, o_n = 0, iw_n = 0; bool act_n = x < xb;
+			if (act_n) { iw_n = fetch(x, r_n, o_n); }
+			for (uint32_t t0 = xa; t0 < xb; t0 += LB2_WARP) {
+				bool act = act_n; const uint32_t iw = iw_n, r = r_n, o = o_n;
+				x += LB2_WARP; act_n = x < xb; if (act_n) { iw_n = fetch(x, r_n, o_n); }
+				uint32_t j = act ? (uint32_t)(TID[iw & 0x3FFFu] & 0x7FFFu) : 0xFFFFFFFFu;
+				if (act && !marked(j)) { act = false; j = 0xFFFFFFFFu; }
+				if (!lb2_ballot(act)) { continue; }      // (the same for every lane of the warp)
 				const uint32_t same = lb2_match_any(j), leader = (uint32_t)lb2_ctz32(same), below = same & ((1u << lane) - 1u);
 				uint32_t pos = 0;
 				if (act && lane == leader) { pos = wcnt[wid * n + j]; wcnt[wid * n + j] = pos + (uint32_t)lb2_popc32(same); }
@@ -799,38 +883,36 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		}
 		lb2_sync();
 		for (uint32_t j = tid; j < n; j += nt) {
+			if (!marked(j)) { continue; }      // no read of this node has its mate in it: nothing is suppressed here
 			uint32_t tot = 0; for (int c = 0; c < 4; ++c) { tot += ws.b_cnt[j * 4 + c]; }
 			if (!tot) { continue; }
 			uint32_t b0 = nstart[j];
-			if (sh->has_pairs == 1 && R <= 32u * LB2_SEEN_WORDS) {
-				// A name can only be found in the other mate order's list if the read's mate (rd_mate) has had an occurrence
-				// in this node before -- binary_search on the unsorted list may miss a name that is there, it never finds one
-				// that is not.  No such occurrence => nothing of this node is suppressed, and the lists need not be built.
-				uint32_t seen[LB2_SEEN_WORDS]; const uint32_t nwd = (R + 31u) >> 5; bool hit = false;
-				for (uint32_t i = 0; i < nwd; ++i) { seen[i] = 0; }
-				for (uint32_t x = b0; x < b0 + tot && !hit; ++x) {
-					const uint32_t r = occ[x] >> 12, q = ws.rd_mate[r];
-					if (q != LB2_NIL && ((seen[q >> 5] >> (q & 31u)) & 1u)) { hit = true; }
-					seen[r >> 5] |= 1u << (r & 31u);
-				}
-				if (!hit) { continue; }
-			}
 			uint32_t *L1 = ws.mates + 2 * (size_t)b0; uint32_t *L2top = ws.mates + 2 * (size_t)b0 + 2 * (size_t)tot - 1;   // list 2 grows downwards
 			uint32_t n1 = 0, n2_ = 0;
 			for (uint32_t x = b0; x < b0 + tot; ++x) {
 				const uint32_t s_ = occ[x], r = s_ >> 12, p = s_ & 0xFFFu;
 				uint32_t info = ws.rd_info[r], mate = (info >> 2) & 3u, cls = info & 3u, name = ws.rd_rank[r];
 				if (mate == 1 || mate == 2) {
-					// std::binary_search(first,last,val) = lower_bound + !(val < *it)   (libstdc++ stl_algo.h)
-					uint32_t len = (mate == 1) ? n2_ : n1, first = 0;
-					while (len > 0) {
-						uint32_t half = len >> 1, mid = first + half;
-						uint32_t v = (mate == 1) ? *(L2top - mid) : L1[mid];
-						if (v < name) { first = mid + 1; len = len - half - 1; } else { len = half; }
+					bool search = true;
+					if (use_set) {      // only a read whose mate has been in this node can be found
+						search = false; const uint32_t q = ws.rd_mate[r];
+						if (q != LB2_NIL && q < r) {
+							const uint32_t key = ((j + 1u) << 14) | (q & 0x3FFFu); uint32_t h = ((key * 2654435761u) >> hshift) & smask;
+							while (true) { const uint32_t v = pset[h]; if (v == key) { search = true; break; } if (v == 0u) { break; } h = (h + 1u) & smask; }
+						}
 					}
-					uint32_t cnt_other = (mate == 1) ? n2_ : n1;
 					bool ovl = false;
-					if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
+					if (search) {
+						// std::binary_search(first,last,val) = lower_bound + !(val < *it)   (libstdc++ stl_algo.h)
+						uint32_t len = (mate == 1) ? n2_ : n1, first = 0;
+						while (len > 0) {
+							uint32_t half = len >> 1, mid = first + half;
+							uint32_t v = (mate == 1) ? *(L2top - mid) : L1[mid];
+							if (v < name) { first = mid + 1; len = len - half - 1; } else { len = half; }
+						}
+						uint32_t cnt_other = (mate == 1) ? n2_ : n1;
+						if (first < cnt_other) { uint32_t v = (mate == 1) ? *(L2top - first) : L1[first]; ovl = !(name < v); }
+					}
 					if (ovl) { ws.inst[(sh->inst_stride ? r : ws.rd_kbase[r]) + p * istr] |= 0x4000u; ws.b_cnt[j * 4 + cls] -= 1; }
 					uint32_t last = ws.rd_len[r] - (uint32_t)K;
 					uint32_t pushes = (p == 0 || p == last) ? 1u : 2u;
@@ -849,20 +931,35 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 		if ((size_t)n * K * 8 > (size_t)C->deficit_bytes) { if (tid == 0) { sh->err |= 1u << LB2_D_ARENA; } }
 		else {
 			for (uint32_t i = tid; i < n * (uint32_t)K * 2; i += nt) { d32[i] = 0; }
+			// the low-quality bases of the kept stretches as a list (read << 12 | position): few per read, so one lane per read
+			// only collects them; the K k-mers covering each base are then handled by all lanes at once
+			uint32_t *lq = (uint32_t *)ws.sortk; const uint32_t lq_cap = C->max_inst;      // (sortk: >= max_inst 8-byte words)
+			if (tid == 0) { sh->n_jobs = 0; }
 			lb2_sync();
 			for (uint32_t r = tid; r < R; r += nt) {
-				uint32_t len = ws.rd_len[r]; if (len <= (uint32_t)K) { continue; }
-				uint32_t g0 = ws.rd_start[r]; uint32_t cls = ws.rd_info[r] & 3u; uint32_t kb = sh->inst_stride ? r : ws.rd_kbase[r];
-				for (uint32_t q = 0; q < len; ++q) {
-					if (!lb2_getbit(W.lowq, g0 + q)) { continue; }
-					uint32_t p0 = (q + 1 > (uint32_t)K) ? (q + 1 - K) : 0, p1 = (q < len - K) ? q : (len - K);
-					for (uint32_t p = p0; p <= p1; ++p) {
-						uint32_t iw = ws.inst[kb + p * istr];
-						if (iw & 0x4000u) { continue; }                   // suppressed (overlapping mate)
-						uint32_t id = W.t_id[iw & 0x3FFFu];
-						uint32_t i = (iw >> 15) ? ((uint32_t)K - 1 - (q - p)) : (q - p);   // qv string is reversed for ori R (src/Graph.cc:148-158)
-						lb2g_add32(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
-					}
+				const uint32_t len = ws.rd_len[r]; if (len <= (uint32_t)K) { continue; }
+				const uint32_t g0 = ws.rd_start[r];
+				for (uint32_t q0 = 0; q0 < len; ) {      // the mask words of the read, 32 - (g & 31) bases at a time
+					const uint32_t g = g0 + q0, sh_ = g & 31u; uint32_t m = lb2_lds(&W.lowq[g >> 5]) >> sh_; const uint32_t nb_ = (32u - sh_ < len - q0) ? 32u - sh_ : len - q0;
+					if (nb_ < 32u) { m &= (1u << nb_) - 1u; }
+					while (m) { const uint32_t bpos = (uint32_t)lb2_ctz32(m); m &= m - 1u; const uint32_t e = lb2_add32(&sh->n_jobs, 1u); if (e < lq_cap) { lq[e] = (r << 12) | (q0 + bpos); } }
+					q0 += nb_;
+				}
+			}
+			lb2_sync();
+			if (sh->n_jobs > lq_cap) { if (tid == 0) { sh->err |= 1u << LB2_D_ARENA; } }
+			else {
+				const uint32_t ne_ = sh->n_jobs;
+				for (uint32_t x = tid; x < ne_ * (uint32_t)K; x += nt) {
+					const uint32_t e = lq[x / (uint32_t)K], kk = x % (uint32_t)K, r = e >> 12, q = e & 0xFFFu;
+					const uint32_t len = ws.rd_len[r];
+					if (kk > q || q - kk > len - (uint32_t)K) { continue; }      // k-mer p = q - kk must exist: 0 <= p <= len - K
+					const uint32_t p_ = q - kk, kb = sh->inst_stride ? r : ws.rd_kbase[r], cls = ws.rd_info[r] & 3u;
+					const uint32_t iw = ws.inst[kb + p_ * istr];
+					if (iw & 0x4000u) { continue; }                   // suppressed (overlapping mate)
+					const uint32_t id = W.t_id[iw & 0x3FFFu] & 0x7FFFu;
+					const uint32_t i = (iw >> 15) ? ((uint32_t)K - 1u - kk) : kk;   // qv string is reversed for ori R (src/Graph.cc:148-158)
+					lb2g_red_add(&d32[((size_t)id * K + i) * 2 + (cls >> 1)], (cls & 1) ? 0x10000u : 1u);
 				}
 			}
 			lb2_sync();

@@ -18,6 +18,7 @@ CONFIGS = {
     "str": dict(desc="configs[3] STR-heavy 80x/80x, k 11..101: 1 Mb of the 10 Mb region", kw=dict(seed=2001, region_len=1_000_000, region_start=1_000_001, str_every=200, cov_t=80, cov_n=80, var_every=5000)),
     "wgs30": dict(desc="configs[4] WGS 30x/30x: 1 Mb sample of one GPU's share", kw=dict(seed=2002, region_len=1_000_000, region_start=1_000_001, cov_t=30, cov_n=30, var_every=5000)),
     "err": dict(desc="0.5 % substitution errors, 60x/60x, 1 Mb", kw=dict(seed=2003, region_len=1_000_000, region_start=1_000_001, err=0.005, var_every=5000)),
+    "realistic": dict(desc="true pairs + 4 % low-quality bases + 0.2 % errors, 60x/60x, 1 Mb (what a real BAM looks like to the kernels)", kw=dict(seed=2005, region_len=1_000_000, region_start=1_000_001, paired=True, low_qual_frac=0.04, err=0.002, var_every=5000)),
     "paired": dict(desc="true pairs (insert 300+-30, both mates in the window), 60x/60x, 1 Mb", kw=dict(seed=2004, region_len=1_000_000, region_start=1_000_001, paired=True, var_every=5000)),
 }
 
