@@ -636,10 +636,14 @@ int main(int argc, char **argv)
 	// itself and continues as rank 0; every rank assembles a contiguous range of the windows on its own GPU, the records are
 	// gathered on rank 0 over NCCL (lb2_comm_gather), rank 0 replays them into the variant store and writes the VCF
 	vector<pid_t> children;
-	if (o.gpus > 1 || o.world > 1) { setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); }      // stdout carries the VCF and nothing else
+	// stdout carries the VCF and nothing else: NCCL's diagnostics go to stderr (its version banner ignores NCCL_DEBUG_FILE,
+	// so stdout is pointed at stderr while the communicator is set up)
+	if (o.gpus > 1 || o.world > 1) { setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); }
+	struct StdoutToStderr { int saved = -1; void on() { fflush(stdout); saved = dup(1); dup2(2, 1); } void off() { if (saved >= 0) { fflush(stdout); dup2(saved, 1); close(saved); saved = -1; } } } quiet;
 	if (o.gpus > 1 && o.rank < 0) {
 		char id[LB2_COMM_ID_BYTES];
-		if (lb2_comm_unique_id(id) != LB2_OK) { std::cerr << "ERROR: cannot create the NCCL id (no GPU / no NCCL)" << std::endl; return 2; }
+		quiet.on(); const int id_rc = lb2_comm_unique_id(id); quiet.off();
+		if (id_rc != LB2_OK) { std::cerr << "ERROR: cannot create the NCCL id (no GPU / no NCCL)" << std::endl; return 2; }
 		o.nccl_id_file = "/tmp/lancet_b200_nccl_" + itos((int)getpid()) + ".id";
 		{ std::ofstream idf(o.nccl_id_file, std::ios::binary); idf.write(id, sizeof id); }
 		o.world = o.gpus; o.rank = 0;
@@ -687,7 +691,9 @@ int main(int argc, char **argv)
 	if (rc != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
 	if (o.world > 1) {
 		char id[LB2_COMM_ID_BYTES]; std::ifstream idf(o.nccl_id_file, std::ios::binary);
-		if (!idf.read(id, sizeof id) || (rc = lb2_comm_init(ctx, id, o.rank, o.world)) != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": NCCL set-up failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
+		bool id_ok = (bool)idf.read(id, sizeof id);
+		if (id_ok) { quiet.on(); rc = lb2_comm_init(ctx, id, o.rank, o.world); quiet.off(); }
+		if (!id_ok || rc != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": NCCL set-up failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
 	}
 
 	// ---- this rank's windows, in batches: fetch the reads of the batch's span once per sample (BAI), select per window ----
@@ -820,7 +826,7 @@ int main(int argc, char **argv)
 	const lb2_variant *all_v = vars.data(); const char *all_s = strs.data(); uint32_t all_n = (uint32_t)vars.size();
 	if (o.world > 1) {
 		uint64_t stats[2] = { (uint64_t)tot_skip, (uint64_t)n_failed }; lb2_result merged; memset(&merged, 0, sizeof merged);
-		rc = lb2_comm_gather(ctx, vars.data(), (uint32_t)vars.size(), strs.data(), (uint64_t)strs.size(), stats, 2, 0, &merged);
+		quiet.on(); rc = lb2_comm_gather(ctx, vars.data(), (uint32_t)vars.size(), strs.data(), (uint64_t)strs.size(), stats, 2, 0, &merged); quiet.off();
 		if (rc != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": record gather failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
 		if (!lead) { fflush(nullptr); _exit(n_failed ? 3 : 0); }      // (no communicator teardown here: rank 0 is still busy and tears its side down alone)
 		all_v = merged.variants; all_s = merged.strings; all_n = merged.n_variants; tot_skip = (int)stats[0]; n_failed = (uint32_t)stats[1];

@@ -290,17 +290,18 @@ extern "C" uint64_t lb2_kernel_launches(const lb2_ctx *ctx) { return ctx ? ctx->
 // split over host threads): the one or two stretches of the pool every window's reads lie in, the deepest window's staging
 // need and read count (sizes of the escalation passes).  lb2_prepare_escalation: the configurations of the middle and the
 // last pass.  lb2_process runs the window pass beside the upload of its first segment.
-struct lb2_win_plan { uint32_t rng[4]; uint64_t bp; uint32_t nreads; bool bad; };
+struct lb2_win_plan { uint32_t rng[4]; uint32_t runs; uint32_t nreads; bool bad; };
+// (only the index list is walked: the staging need of a window is bounded from its read count, its runs of pool-consecutive
+// reads and the longest read of the pool -- exact when all reads have the same length)
 static inline lb2_win_plan lb2_plan_one(const lb2_batch *b, uint32_t w)
 {
-	lb2_win_plan p; p.bad = false; p.bp = 0; p.nreads = 0; p.rng[0] = p.rng[1] = p.rng[2] = p.rng[3] = 0;
+	lb2_win_plan p; p.bad = false; p.runs = 0; p.nreads = 0; p.rng[0] = p.rng[1] = p.rng[2] = p.rng[3] = 0;
 	const uint32_t R = b->n_reads;
 	uint32_t top = 0, low = 0xFFFFFFFFu, prev = 0xFFFFFFFEu, gap = 0, gap_lo = 0, gap_hi = 0; bool ascending = true;
 	if (b->wr_off[w + 1] < b->wr_off[w] || b->wr_off[w + 1] > b->n_wr || b->ref_off[w + 1] < b->ref_off[w]) { p.bad = true; return p; }
 	for (uint32_t x = b->wr_off[w]; x < b->wr_off[w + 1]; ++x) {
 		const uint32_t r = b->wr_idx[x]; if (r >= R) { p.bad = true; return p; }
-		p.bp += (uint64_t)lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r]) * 16u;
-		if (r != prev + 1u) { p.bp += 14u * 16u; }
+		if (r != prev + 1u) { ++p.runs; }
 		if (prev != 0xFFFFFFFEu) { if (r < prev) { ascending = false; } else if (r - prev > gap) { gap = r - prev; gap_lo = prev + 1; gap_hi = r; } }
 		prev = r;
 		if (r >= top) { top = r + 1; } if (r < low) { low = r; }
@@ -311,7 +312,6 @@ static inline lb2_win_plan lb2_plan_one(const lb2_batch *b, uint32_t w)
 		if (ascending && gap > 8u * LB2_PACK_BLOCK) { p.rng[0] = low; p.rng[1] = gap_lo; p.rng[2] = gap_hi; p.rng[3] = top; }
 		else { p.rng[0] = low; p.rng[1] = top; }
 	}
-	p.bp += ((b->ref_off[w + 1] - b->ref_off[w]) + 31) & ~31u; p.bp += 128;
 	p.nreads = b->wr_off[w + 1] - b->wr_off[w];
 	return p;
 }
@@ -324,22 +324,27 @@ static int lb2_plan_windows(lb2_ctx *ctx, const lb2_batch *b)
 	const unsigned share = std::max(1u, hw / (unsigned)std::max(1, ctx->comm_world));      // (several ranks on one host share its cores)
 	const unsigned T = (W >= 2048 && hw > 1) ? std::min<unsigned>(std::min<unsigned>(share, 16u), std::max(1u, env_u32("LB2_HOST_THREADS", 16))) : 1u;
 	std::vector<uint32_t> t_bp(T, 0), t_rd(T, 0); std::vector<int> t_bad(T, 0);
+	std::vector<uint32_t> t_mw(T, 0);      // longest read of the pool, in 16-base words
 	auto work = [&](unsigned t) {
+		{ const uint32_t R_ = b->n_reads, r0 = (uint32_t)((uint64_t)R_ * t / T), r1 = (uint32_t)((uint64_t)R_ * (t + 1) / T); uint32_t mw = 0;
+		  for (uint32_t r = r0; r < r1; ++r) { mw = std::max(mw, lb2_pack_nwords(b->base_off[r + 1] - b->base_off[r])); } t_mw[t] = mw; }
 		const uint32_t w0 = (uint32_t)((uint64_t)W * t / T), w1 = (uint32_t)((uint64_t)W * (t + 1) / T);
-		uint32_t mbp = 0, mrd = 0;
+		uint32_t mbp = 0, mrd = 0;      // (mbp: reads + 14 pad words per run, still without the per-read words)
 		for (uint32_t w = w0; w < w1; ++w) {
 			const lb2_win_plan p = lb2_plan_one(b, w);
 			if (p.bad) { t_bad[t] = 1; return; }
 			uint32_t *rg = ctx->h_rng.data() + 4 * (size_t)w; rg[0] = p.rng[0]; rg[1] = p.rng[1]; rg[2] = p.rng[2]; rg[3] = p.rng[3];
-			if (p.bp > mbp) { mbp = (uint32_t)std::min<uint64_t>(p.bp, 1u << 30); }
+			mbp = std::max(mbp, (((b->ref_off[w + 1] - b->ref_off[w]) + 31u) & ~31u) + 128u + 224u * p.runs);
 			mrd = std::max(mrd, p.nreads);
 		}
 		t_bp[t] = mbp; t_rd[t] = mrd;
 	};
 	if (T == 1) { work(0); }
 	else { std::vector<std::thread> th; for (unsigned t = 0; t < T; ++t) { th.emplace_back(work, t); } for (auto &x : th) { x.join(); } }
-	for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); }
-	ctx->plan_need_bp = std::min<uint32_t>((max_bp + 1023) & ~1023u, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
+	uint32_t maxw = 0;
+	for (unsigned t = 0; t < T; ++t) { if (t_bad[t]) { return LB2_ERR_ARG; } max_bp = std::max(max_bp, t_bp[t]); max_reads = std::max(max_reads, t_rd[t]); maxw = std::max(maxw, t_mw[t]); }
+	const uint64_t bound = (uint64_t)max_bp + (uint64_t)max_reads * maxw * 16u;      // (deepest window x longest read: an upper bound of every window's need)
+	ctx->plan_need_bp = (uint32_t)std::min<uint64_t>((bound + 1023) & ~(uint64_t)1023, (1u << 20) - 1024);      // (the first-occurrence index in a table key has 20 bits)
 	ctx->plan_max_reads = max_reads;
 	return LB2_OK;
 }
