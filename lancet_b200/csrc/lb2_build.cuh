@@ -35,6 +35,11 @@ LB2_DEV void lb2_mark(lb2_win &W, int ph) {
 #else
 LB2_DEV void lb2_mark(lb2_win &, int) {}
 #endif
+#ifdef LB2_PROFILE_SEQ      // (debug builds only: the lane-0 sections of a component split over counters that are idle on unpaired, clean input)
+#define LB2_SEQMARK(ph) lb2_mark(W, ph)
+#else
+#define LB2_SEQMARK(ph) do { } while (0)
+#endif
 
 // CTA-wide exclusive prefix sum: set(i, sum_{j<i} get(j)); returns the total.  Each lane owns a contiguous chunk.
 template <class Get, class Set>
@@ -628,6 +633,7 @@ LB2_DEVNI void lb2_build_graph(lb2_win &W, int K)
 	while (true) {
 		const uint32_t it = lb2_batch_next(&sh->walk_next);
 		if (it >= ((nitems + 31u) & ~31u)) { break; }
+		if (lb2_ballot(lb2_ld32(&sh->err) != 0)) { break; }      // (table full: the window is redone with a larger one; filling this one to the brim only makes the probes longer)
 		// this lane's item (none: active = false; the one-word walks are called by all lanes of the warp together)
 		bool active = false, isref = false; uint32_t g0 = 0, n = 0, ob = 0, oe = 0, ib = 0, st = 1, cls = 0;
 		if (it < NP * R) {

@@ -117,7 +117,7 @@ LB2_DEV void lb2_oe_rehash(lb2_win &W, uint32_t nb) {   // _M_rehash_aux (unique
 	uint32_t p = sh->lhead; sh->lhead = LB2_NIL; uint32_t bbegin = 0;
 	while (p != LB2_NIL) {
 		uint32_t nx = ws.d_lnext[p];
-		uint32_t b = (uint32_t)(ws.d_hash[p] % nb); ws.d_bk[p] = b;
+		uint32_t b = (uint32_t)(ws.d_hash[p] % nb); ws.d_bk[p] = (uint16_t)b;
 		if (lb2_bget(W, b) == LB2_NIL) {
 			ws.d_lnext[p] = sh->lhead; sh->lhead = p; lb2_bset(W, b, LB2_SENT);
 			if (ws.d_lnext[p] != LB2_NIL) { lb2_bset(W, bbegin, p); }
@@ -144,7 +144,7 @@ LB2_DEV void lb2_oe_insert(lb2_win &W, uint32_t id) {   // _M_insert_unique_node
 			if (sh->err) { return; }
 		} else { sh->next_resize = sh->bkt_count; }
 	}
-	uint32_t b = (uint32_t)(ws.d_hash[id] % sh->bkt_count); ws.d_bk[id] = b;
+	uint32_t b = (uint32_t)(ws.d_hash[id] % sh->bkt_count); ws.d_bk[id] = (uint16_t)b;
 	if (lb2_bget(W, b) != LB2_NIL) {
 		uint32_t before = lb2_bget(W, b);
 		ws.d_lnext[id] = lb2_oe_next(W, before); lb2_oe_setnext(W, before, id);
@@ -218,10 +218,42 @@ LB2_DEV void lb2_remove_node(lb2_win &W, uint32_t id) {   // Graph_t::removeNode
 	lb2_edge *e = lb2_edges(ws, id); int ne = ws.d_ne[id];
 	for (int i = 0; i < ne; ++i) { if (e[i].to != id) { lb2_remove_edge(W, e[i].to, id, lb2_fliplink(e[i].dir)); } }
 }
-LB2_DEV void lb2_clean_dead(lb2_win &W) {                 // Graph_t::cleanDead
+// ---- the sweeps of one component (lane 0).  The reference walks the whole map and skips the nodes of other components;
+//      with many small components (large k, short reads) that is components x nodes dependent loads.  Once a component
+//      has been compacted for the first time its nodes are threaded on a list of their own, in map order (an erase keeps
+//      the relative order, and nothing is inserted while a component is being processed); nodes the map has dropped since
+//      are unlinked on the way.  f(p) returns false to stop the walk.
+LB2_DEV bool lb2_special(lb2_win &W, uint32_t id);
+template <class F> LB2_DEV void lb2_each_node(lb2_win &W, int compid, F f) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
+	if (!sh->cm_valid) {
+		uint32_t p = sh->lhead;
+		while (p != LB2_NIL) { const uint32_t nx = ws.d_lnext[p]; if (ws.d_comp[p] == compid && !lb2_special(W, p)) { if (!f(p)) { return; } } p = nx; }
+		return;
+	}
+	uint32_t prev = LB2_NIL, p = sh->chead;
+	while (p != LB2_NIL) {
+		const uint16_t v = ws.d_cnext[p]; const uint32_t nx = (v == 0xFFFFu) ? LB2_NIL : (uint32_t)v;
+		bool go = true;
+		if (!(ws.d_flags[p] & LB2_NF_GONE)) { go = f(p); }
+		if (ws.d_flags[p] & LB2_NF_GONE) { if (prev == LB2_NIL) { sh->chead = nx; } else { ws.d_cnext[prev] = v; } } else { prev = p; }
+		if (!go) { return; }
+		p = nx;
+	}
+}
+LB2_DEV void lb2_build_members(lb2_win &W, int compid) {
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; uint32_t last = LB2_NIL; sh->chead = LB2_NIL;
+	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
+		if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
+		if (last == LB2_NIL) { sh->chead = p; } else { ws.d_cnext[last] = (uint16_t)p; }
+		last = p;
+	}
+	if (last != LB2_NIL) { ws.d_cnext[last] = 0xFFFFu; }
+	sh->cm_valid = 1;
+}
+LB2_DEV void lb2_clean_dead(lb2_win &W, int compid) {     // Graph_t::cleanDead (every dead node belongs to the component being swept)
 	lb2_ws &ws = W.ws;
-	uint32_t p = W.sh->lhead;
-	while (p != LB2_NIL) { uint32_t nx = ws.d_lnext[p]; if (ws.d_flags[p] & LB2_NF_DEAD) { lb2_oe_erase(W, p); } p = nx; }
+	lb2_each_node(W, compid, [&](uint32_t p) -> bool { if (ws.d_flags[p] & LB2_NF_DEAD) { lb2_oe_erase(W, p); } return true; });
 }
 LB2_DEV bool lb2_is_tandem(lb2_win &W, uint32_t id) {     // Node_t::isTandem
 	lb2_edge *e = lb2_edges(W.ws, id); int ne = W.ws.d_ne[id];
@@ -381,7 +413,7 @@ LB2_DEVNI void lb2_order_and_pack(lb2_win &W)
 		bcap = Bfinal; if (NT > Bfinal) { bcap = lb2_level_bkt(NT); }      // a source/sink insert may still trigger a rehash
 		size_t off = 0;
 #define LB2_GT(field, type, count) do { off = (off + 7) & ~(size_t)7; if (tid == 0) { ws.field = (type *)(G + off); } off += sizeof(type) * (size_t)(count); } while (0)
-		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint32_t, NT); LB2_GT(buckets, uint16_t, bcap);
+		LB2_GT(d_lnext, uint32_t, NT); LB2_GT(d_bk, uint16_t, NT); LB2_GT(d_cnext, uint16_t, NT); LB2_GT(buckets, uint16_t, bcap);
 		LB2_GT(d_cov, float, NT * 4); LB2_GT(stack, uint32_t, NT + 8); LB2_GT(cpos, uint32_t, NT + 8);
 		LB2_GT(d_edge, lb2_edge, NT * LB2_EINL); LB2_GT(e_pool, lb2_edge, LB2_EOV_BLOCKS * LB2_ECAP);
 		LB2_GT(d_len, uint16_t, NT); LB2_GT(d_stn, uint16_t, NT); LB2_GT(d_stT, uint16_t, NT); LB2_GT(d_comp, int16_t, NT);
@@ -477,15 +509,14 @@ LB2_DEVNI void lb2_remove_lowcov(lb2_win &W, int compid) {
 	double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
 	double thr = W.P->min_cov_ratio * avgcov;
 	uint32_t removed = 0;
-	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
-		if (ws.d_comp[p] != compid) { continue; }
-		if (lb2_special(W, p)) { continue; }
+	lb2_each_node(W, compid, [&](uint32_t p) -> bool {
 		int mq = ws.d_mincovqv[p];
 		float tt = ws.d_cov[p * 4 + 0] + ws.d_cov[p * 4 + 1], tn = ws.d_cov[p * 4 + 2] + ws.d_cov[p * 4 + 3];
 		if (mq <= W.P->low_cov_threshold || (double)mq <= thr || (tt == 1 && tn == 1)) { lb2_remove_node(W, p); ++removed; }
-	}
+		return true;
+	});
 	sh->flag_b = removed; sh->n_changed = removed;      // (nothing removed: the graph is still fully compacted and the compaction that follows is a no-op)
-	if (removed) { lb2_clean_dead(W); }
+	if (removed) { lb2_clean_dead(W, compid); }
 }
 
 // Graph_t::markConnectedComponents (src/Graph.cc:2252-2336) by all lanes: the reference numbers a component when its
@@ -651,10 +682,11 @@ LB2_DEV bool lb2_cycle_from(lb2_win &W, uint32_t start, int ori) {
 	}
 	return ans;
 }
-LB2_DEVNI bool lb2_has_cycle(lb2_win &W) {
+LB2_DEVNI bool lb2_has_cycle(lb2_win &W, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh;
 	if (sh->source == LB2_NIL || sh->sink == LB2_NIL) { return false; }
-	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) { if (!lb2_special(W, p)) { ws.d_color[p] = 1; } }
+	// (the reference whitens every node of the map; the search from the source never leaves the source's component)
+	lb2_each_node(W, compid, [&](uint32_t p) -> bool { ws.d_color[p] = 1; return true; });
 	bool a1 = lb2_cycle_from(W, sh->source, 0);
 	bool a2 = lb2_cycle_from(W, sh->source, 1);
 	return a1 || a2;
@@ -732,20 +764,18 @@ LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
 	uint32_t cused = 0, njobs = 0; const uint32_t ccap = sh->n_rows + sh->spec_cap;
 	lb2_job *jobs = (lb2_job *)ws.jobs;
-	for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
-		if (ws.d_comp[p] != compid) { continue; }
-		if (ws.d_flags[p] & LB2_NF_DEAD) { continue; }
-		if (lb2_special(W, p)) { continue; }
+	lb2_each_node(W, compid, [&](uint32_t p) -> bool {
+		if (ws.d_flags[p] & LB2_NF_DEAD) { return true; }
 		uint32_t *chain = ws.chain + cused;
 		uint32_t len0 = ws.d_len[p], curlen = len0;
 		uint32_t nF = lb2_compress_dir(W, p, 0, chain, 0, curlen);
 		uint32_t nAll = lb2_compress_dir(W, p, 1, chain, nF, curlen);
-		if (sh->err) { break; }
-		if (nAll == 0) { continue; }
-		if (cused + nAll > ccap || njobs >= LB2_MAX_ROWS) { sh->err |= 1u << LB2_D_STACK; break; }
+		if (sh->err) { return false; }
+		if (nAll == 0) { return true; }
+		if (cused + nAll > ccap || njobs >= LB2_MAX_ROWS) { sh->err |= 1u << LB2_D_STACK; return false; }
 		lb2_job jb; jb.node = p; jb.cbeg = cused; jb.nF = nF; jb.nAll = nAll; jb.len0 = len0; jb.curlen = curlen; jb.pad = 0;
 		jb.so = lb2_arena_alloc(W, curlen); jb.co = lb2_arena_alloc(W, curlen * 2 * (uint32_t)sizeof(lb2_cov));
-		if (sh->err) { break; }
+		if (sh->err) { return false; }
 		// destination offsets: [R-chain, last absorbed first] seed [F-chain]; chain entries get their start position
 		uint32_t leftlen = 0;
 		for (uint32_t c = nF; c < nAll; ++c) { leftlen += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
@@ -756,7 +786,8 @@ LB2_DEVNI void lb2_compress_sweep(lb2_win &W, int compid) {
 		for (uint32_t c = 0; c < nAll; ++c) { ws.cpos[cused + c] = pos; pos += ws.d_len[chain[c] & 0x7FFFFFFFu] - K + 1; }
 		ws.d_mincov[p] = 10000000; ws.d_mincovqv[p] = 10000000;
 		jobs[njobs++] = jb; cused += nAll;
-	}
+		return true;
+	});
 	sh->n_jobs = njobs;
 }
 
@@ -1124,35 +1155,64 @@ LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {      // all lanes
 	while (true) {
 		if (lb2_tid() == 0) {
 			int tips = 0;
-			for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
-				if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
+			lb2_each_node(W, compid, [&](uint32_t p) -> bool {
 				int deg = ws.d_ne[p]; int len = (int)lb2_strlen(W, p) - K + 1;
 				if (deg <= 1 && len < W.P->max_tip_len) { lb2_remove_node(W, p); ++tips; }
-			}
+				return true;
+			});
 			sh->flag_b = (uint32_t)tips; sh->n_changed += (uint32_t)tips;
 		}
 		lb2_sync();
 		if (!sh->flag_b || sh->err) { break; }
+		LB2_SEQMARK(LB2_PH_LOWQ);
 		lb2_compress(W, compid);
 	}
 }
 
+// removeShortLinks (src/Graph.cc:3015-3062).  Whether a node's string holds a tandem repeat near its k-1'th base does not
+// change while the sweep runs (nor do its length and minimum coverage; only degrees drop as neighbours go), so the
+// findTandems calls -- the expensive part: every short low-coverage node of a large-k graph is a candidate -- are made
+// up front by all lanes, one candidate each from a private copy of the string, and lane 0 then applies the sweep in map
+// order with the degree test at its original place.
+#define LB2_LINK_BUF 320      /* >= 127 + 127 / 2 + slack; longer strings are read in place */
 LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {   // all lanes
-	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K;
-	if (lb2_tid() == 0) {
-		int links = 0;
+	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
+	uint32_t *cand = ws.stack;      // (idle between the cycle checks and the compactions: rows + 8 words)
+	if (tid == 0) {
+		uint32_t n = 0;
 		double avgcov = ((double)(int)sh->totalreadbp) / ((double)sh->L);
 		const int max_link = (int)floor((double)K / 2.0);
 		const double lim = floor(sqrt(avgcov));
-		for (uint32_t p = sh->lhead; p != LB2_NIL; p = ws.d_lnext[p]) {
-			if (ws.d_comp[p] != compid || lb2_special(W, p)) { continue; }
+		lb2_each_node(W, compid, [&](uint32_t p) -> bool {
 			int deg = ws.d_ne[p]; int len = (int)ws.d_len[p] - K + 1;
-			if (deg >= 2 && len < max_link && (double)ws.d_mincov[p] <= lim) {
-				int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false;
-				lb2_nview v; lb2_view(W, p, v);
-				lb2_find_tandems([&](uint32_t i) -> char { return lb2_vchar(W, v, i); }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov);
-				if (LEN == 0) { lb2_remove_node(W, p); ++links; }
-			}
+			if (deg >= 2 && len < max_link && (double)ws.d_mincov[p] <= lim) { cand[n++] = p; }
+			return true;
+		});
+		sh->n_jobs = n;
+	}
+	lb2_sync();
+	const uint32_t nc = sh->n_jobs;
+	for (uint32_t i = tid; i < nc; i += nt) {
+		const uint32_t p = cand[i];
+		int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false;
+		lb2_nview v; lb2_view(W, p, v);
+		if (v.len <= LB2_LINK_BUF) {
+			char buf[LB2_LINK_BUF];
+			for (uint32_t x = 0; x < v.len; ++x) { buf[x] = lb2_vchar(W, v, x); }
+			lb2_find_tandems([&](uint32_t x) -> char { return buf[x]; }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov);
+		} else {
+			lb2_find_tandems([&](uint32_t x) -> char { return lb2_vchar(W, v, x); }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov);
+		}
+		if (LEN != 0) { cand[i] = p | 0x80000000u; }
+	}
+	lb2_sync();
+	LB2_SEQMARK(LB2_PH_SCAN);
+	if (tid == 0) {
+		int links = 0;
+		for (uint32_t i = 0; i < nc; ++i) {
+			const uint32_t p = cand[i];
+			if (p & 0x80000000u) { continue; }
+			if (ws.d_ne[p] >= 2) { lb2_remove_node(W, p); ++links; }
 		}
 		sh->flag_b = (uint32_t)links; sh->n_changed += (uint32_t)links;
 	}

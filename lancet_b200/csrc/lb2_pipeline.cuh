@@ -120,7 +120,7 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 			const int numcomp = sh->numcomp;
 			for (int c = 1; c <= numcomp; ++c) {
 				lb2_find_anchors(W, c);
-				if (tid == 0) { lb2_mark_ref_ends(W, c); sh->flag_c = 0; lb2_mark(W, LB2_PH_ANCHOR); }
+				if (tid == 0) { lb2_mark_ref_ends(W, c); sh->flag_c = 0; sh->cm_valid = 0; lb2_mark(W, LB2_PH_ANCHOR); }
 				lb2_sync();
 				// A component without anchors is invisible from here on: both cycle checks, the path-repeat scan and the path
 				// enumeration return at once without a source (src/Graph.cc:602, :689, :2422), and the sweeps in between only
@@ -131,22 +131,26 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 					// compacted graph (a chain of links is always traversed whole), where it costs a handful of nodes
 					const bool par = lb2_compress_par(W, c);
 					if (!par) {
-						if (tid == 0) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+						if (tid == 0) { sh->flag_c = lb2_has_cycle(W, c) ? 1u : 0u; }
 						lb2_sync();
 						if (!sh->flag_c) { lb2_compress(W, c); }
 					} else {
-						if (tid == 0 && !sh->err) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+						// (from here on the sweeps walk the component's own node list, not the whole map)
+						if (tid == 0 && !sh->err) { lb2_build_members(W, c); sh->flag_c = lb2_has_cycle(W, c) ? 1u : 0u; }
 						lb2_sync();
 					}
 				}
+				LB2_SEQMARK(LB2_PH_PRESCAN);
 				if (!sh->flag_c && !sh->err) {
-					if (tid == 0 && !sh->err) { lb2_remove_lowcov(W, c); }      // removeLowCov(true,c): sweep, cleanDead, then compress
+					if (tid == 0 && !sh->err) { if (!sh->cm_valid) { lb2_build_members(W, c); } lb2_remove_lowcov(W, c); }      // removeLowCov(true,c): sweep, cleanDead, then compress
 					lb2_sync();
 					if (!sh->err && sh->flag_b) { lb2_compress(W, c); }          // (compaction is idempotent: skipped when the sweep removed nothing)
+					LB2_SEQMARK(LB2_PH_MATES);
 					if (!sh->err) { lb2_remove_tips(W, c); }
+					LB2_SEQMARK(LB2_PH_LOWQ);
 					if (!sh->err) { lb2_remove_short_links(W, c); }
 					// (the graph the first check called acyclic is only checked again if one of the three sweeps changed it)
-					if (tid == 0 && !sh->err && sh->n_changed) { sh->flag_c = lb2_has_cycle(W) ? 1u : 0u; }
+					if (tid == 0 && !sh->err && sh->n_changed) { sh->flag_c = lb2_has_cycle(W, c) ? 1u : 0u; }
 				}
 				lb2_mark(W, LB2_PH_COMP_SEQ);
 				lb2_sync();
@@ -184,9 +188,9 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 				}
 				if (sh->err) { break; }
 				if (tid == 0) {   // clear the edge flags again (all flags of this component were 0 before)
-					for (uint32_t p = sh->lhead; p != LB2_NIL; p = W.ws.d_lnext[p]) {
-						if (W.ws.d_comp[p] == c) { for (int e = 0; e < (int)W.ws.d_ne[p]; ++e) { lb2_edges(W.ws, p)[e].flag = 0; } }
-					}
+					auto unflag = [&](uint32_t p) -> bool { for (int e = 0; e < (int)W.ws.d_ne[p]; ++e) { lb2_edges(W.ws, p)[e].flag = 0; } return true; };
+					lb2_each_node(W, c, unflag);
+					unflag(sh->source); unflag(sh->sink);      // (the component's only source/sink nodes: the node walk leaves them out)
 				}
 				lb2_sync();
 				if (rpt) { retry = true; break; }
@@ -226,8 +230,11 @@ LB2_DEVNI void lb2_process_window(lb2_win &W, uint32_t w)
 	if (tid == 0) {
 		lb2_window_info wi; wi.status = (uint8_t)sh->status; wi.final_k = (uint8_t)sh->final_k; wi.n_k_tried = (uint16_t)sh->n_k_tried;
 		wi.n_variants = (sh->status == LB2_WIN_OK) ? sh->n_var : 0; wi.n_nodes = sh->last_nodes; wi.detail = sh->detail;
-		W.O->info[w] = wi; W.O->str_used[w] = sh->str_used;
 		lb2_mark(W, LB2_PH_OTHER);
+#ifdef LB2_PROFILE_SEQ      // (debug: this window's cycles / 256 in the detail word)
+		{ unsigned long long t = 0; for (int i = 0; i < LB2_PH_N; ++i) { t += sh->prof[i]; } wi.detail = (uint32_t)(t >> 8); }
+#endif
+		W.O->info[w] = wi; W.O->str_used[w] = sh->str_used;
 #if defined(LB2_PROFILE) && !defined(LB2_HOSTSIM)
 		if (W.O->prof) { for (int i = 0; i < LB2_PH_N; ++i) { if (sh->prof[i]) { atomicAdd(&W.O->prof[i], sh->prof[i]); } } }
 #endif

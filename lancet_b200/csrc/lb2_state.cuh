@@ -54,7 +54,7 @@ struct lb2_ws {
 	// --- reads ---
 	uint32_t *rd_start; uint32_t *rd_len; uint32_t *rd_t5; uint32_t *rd_info; uint32_t *rd_rank; uint32_t *rd_kbase; uint32_t *rd_mate; uint64_t *rd_src;      // rd_src: first word in the packed pool | words << 32
 	// --- graph stage, row space.  hot (shared memory): ---
-	uint32_t *d_lnext; uint32_t *d_bk; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
+	uint32_t *d_lnext; uint16_t *d_bk; uint16_t *d_cnext; uint16_t *buckets; uint8_t *d_ne; uint8_t *d_flags; uint8_t *d_color; uint8_t *d_eov; int16_t *d_comp;
 	uint16_t *d_pos; uint32_t *px; uint32_t px_words;   // (packed-read words, dead in the graph stage) list index of every row; scratch of the parallel compaction
 	lb2_edge *d_edge; lb2_edge *e_pool; float *d_cov; uint16_t *d_len; uint16_t *d_stn; uint16_t *d_stT; uint32_t *stack; uint32_t *chain; uint32_t *cpos;
 	// cold (global):
@@ -91,7 +91,7 @@ struct lb2_sh {
 	// reference trimming state (Ref_t::seq/trim5/trim3, persists across k: SURVEY B4)
 	uint32_t seq_off, seq_len; uint32_t trim5, trim3;
 	// order emulation
-	uint32_t bkt_count, bkt_cap, elem_count, next_resize, lhead;
+	uint32_t bkt_count, bkt_cap, elem_count, next_resize, lhead, chead, cm_valid;      // chead/cm_valid: the current component's own node list (d_cnext)
 	// anchors
 	uint32_t source, sink, anc_src, anc_snk, anc_amb, spec_cap;
 	uint32_t arena_used, tstr_used;

@@ -3,7 +3,7 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as _g
-os.environ["LB2_SO"] = _g.build_profile()      # the instrumented build (the product library has no counters)
+os.environ["LB2_SO"] = os.environ.get("LB2_PROFILE_SO") or _g.build_profile()      # the instrumented build (the product library has no counters)
 from lancet_b200.api import Context
 from lancet_b200.synth import make_batch
 
