@@ -19,7 +19,7 @@
 
 #include "lb2_pipeline.cuh"
 
-#define LB2_KERNEL_VERSION "r02-v2"
+#define LB2_KERNEL_VERSION "r02-v3"
 
 struct lb2_launch {
 	lb2_params P; lb2_cfg C; lb2_dev_batch B; lb2_dev_out O;

@@ -277,7 +277,8 @@ LB2_DEV int lb2_get_buddy(lb2_win &W, uint32_t id, int ori) {   // Node_t::getBu
 //      have no shorter period are the reference's candidate repeats, met in (i, m) order; those within `delta` of `pos`
 //      set LEN (the last one wins) and append their unit to the motif.
 template <class GetC>
-LB2_DEV bool lb2_find_tandems(GetC getc, uint32_t slen, const lb2_params *P, int pos, int &len, char *motif, uint32_t &mlen, uint32_t mcap, bool &movf)
+LB2_DEV bool lb2_find_tandems(GetC getc, uint32_t slen, const lb2_params *P, int pos, int &len, char *motif, uint32_t &mlen, uint32_t mcap, bool &movf,
+                              uint32_t i_first = 0, uint32_t i_step = 1)      // (i_first, i_step: this caller's share of the positions, for callers that only need "any")
 {
 	const uint32_t maxu = (uint32_t)P->max_unit_len < 16u ? (uint32_t)P->max_unit_len : 16u;
 	const int delta = P->dist_from_str;
@@ -289,7 +290,7 @@ LB2_DEV bool lb2_find_tandems(GetC getc, uint32_t slen, const lb2_params *P, int
 	};
 	auto closes = [&](uint32_t i, uint32_t m, uint32_t j) -> bool { return j != m || i + j + 1 == slen; };
 	bool found = false;
-	for (uint32_t i = 0; i < slen; ++i) {
+	for (uint32_t i = i_first; i < slen; i += i_step) {
 		for (uint32_t m = 1; m <= maxu; ++m) {
 			const uint32_t j = agree(i, m);
 			if (!closes(i, m, j)) { continue; }
@@ -1172,9 +1173,9 @@ LB2_DEVNI void lb2_remove_tips(lb2_win &W, int compid) {      // all lanes
 // removeShortLinks (src/Graph.cc:3015-3062).  Whether a node's string holds a tandem repeat near its k-1'th base does not
 // change while the sweep runs (nor do its length and minimum coverage; only degrees drop as neighbours go), so the
 // findTandems calls -- the expensive part: every short low-coverage node of a large-k graph is a candidate -- are made
-// up front by all lanes, one candidate each from a private copy of the string, and lane 0 then applies the sweep in map
-// order with the degree test at its original place.
-#define LB2_LINK_BUF 320      /* >= 127 + 127 / 2 + slack; longer strings are read in place */
+// up front by all lanes, one warp per candidate, and lane 0 then applies the sweep in map order with the degree test at
+// its original place.
+#define LB2_LINK_BUF 256      /* bytes per warp, >= 127 + 127 / 2; longer strings are read in place */
 LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {   // all lanes
 	lb2_ws &ws = W.ws; lb2_sh *sh = W.sh; const int K = sh->K; const unsigned tid = lb2_tid(), nt = lb2_nthr();
 	uint32_t *cand = ws.stack;      // (idle between the cycle checks and the compactions: rows + 8 words)
@@ -1191,19 +1192,24 @@ LB2_DEVNI void lb2_remove_short_links(lb2_win &W, int compid) {   // all lanes
 		sh->n_jobs = n;
 	}
 	lb2_sync();
-	const uint32_t nc = sh->n_jobs;
-	for (uint32_t i = tid; i < nc; i += nt) {
+	// one warp per candidate, the string in the warp's piece of the idle compaction scratch, the positions dealt to the
+	// lanes (a reported repeat always has a positive length: "LEN == 0" is "no position reports one")
+	const uint32_t nc = sh->n_jobs, nwarp = (nt / LB2_WARP) ? nt / LB2_WARP : 1u, wid = tid / LB2_WARP, lane = lb2_lane();
+	char *const wbuf = ((size_t)ws.px_words * 4 >= (size_t)nwarp * LB2_LINK_BUF) ? (char *)ws.px + (size_t)wid * LB2_LINK_BUF : nullptr;
+	for (uint32_t i = wid; i < nc; i += nwarp) {
 		const uint32_t p = cand[i];
-		int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false;
+		int LEN = 0; char motif[4]; uint32_t ml = 0; bool ov = false, found;
 		lb2_nview v; lb2_view(W, p, v);
-		if (v.len <= LB2_LINK_BUF) {
-			char buf[LB2_LINK_BUF];
-			for (uint32_t x = 0; x < v.len; ++x) { buf[x] = lb2_vchar(W, v, x); }
-			lb2_find_tandems([&](uint32_t x) -> char { return buf[x]; }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov);
+		if (wbuf && v.len <= LB2_LINK_BUF) {
+			for (uint32_t x = lane; x < v.len; x += LB2_WARP) { wbuf[x] = lb2_vchar(W, v, x); }
+			lb2_warp_sync();
+			found = lb2_find_tandems([&](uint32_t x) -> char { return wbuf[x]; }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov, lane, LB2_WARP);
 		} else {
-			lb2_find_tandems([&](uint32_t x) -> char { return lb2_vchar(W, v, x); }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov);
+			found = lb2_find_tandems([&](uint32_t x) -> char { return lb2_vchar(W, v, x); }, v.len, W.P, K - 1, LEN, motif, ml, 0, ov, lane, LB2_WARP);
 		}
-		if (LEN != 0) { cand[i] = p | 0x80000000u; }
+		const uint32_t any = lb2_ballot(found);
+		if (any && lane == 0) { cand[i] = p | 0x80000000u; }
+		lb2_warp_sync();
 	}
 	lb2_sync();
 	LB2_SEQMARK(LB2_PH_SCAN);
