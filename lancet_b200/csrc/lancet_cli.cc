@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <chrono>
 #include <mutex>
 #include <condition_variable>
 #include <deque>
@@ -58,7 +59,7 @@ struct Opts {
 	int max_indel_len = 500, max_mismatch = 2, max_unit_len = 4, min_report_units = 3, min_report_len = 7, dist_from_str = 1;
 	double cov_ratio = 0.01;
 	bool primary_only = false, xa_filter = false, active_regions = true, verbose = false;
-	int gpu = 0, gpus = 1, rank = -1, world = 1, batch_windows = 16384, io_threads = 0; string nccl_id_file;
+	int gpu = 0, gpus = 1, rank = -1, world = 1, batch_windows = 4096, io_threads = 0; string nccl_id_file;
 	Filters f;
 };
 
@@ -246,6 +247,7 @@ struct Aln {
 	float as = -1, xs = -1; bool has_md = false;
 };
 
+static double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 template <class F> static void parallel_for(size_t n, unsigned threads, F f)
 {
 	if (threads <= 1 || n < 2) { for (size_t i = 0; i < n; ++i) { f(i); } return; }
@@ -299,6 +301,7 @@ struct BamFile {
 	uint64_t first_voff = 0;                       // virtual offset of the first alignment record
 	bool has_index = false; vector<vector<uint64_t>> linear; vector<uint64_t> ref_first;      // BAI: linear index and smallest chunk start per reference
 	unsigned threads = 1;
+	double t_read = 0, t_inflate = 0, t_cut = 0, t_decode = 0; std::mutex t_mu;      // (LB2_CLI_TIMING)
 	~BamFile() { if (f) { fclose(f); } }
 
 	// compressed blocks [coff, ...) up to ~want bytes: (file offset, block size, inflated size) of every complete block read
@@ -308,7 +311,7 @@ struct BamFile {
 		if (coff >= file_size) { eof = true; return true; }
 		const size_t n = (size_t)std::min<uint64_t>(want + (1u << 16), file_size - coff);
 		in.resize(n);
-		if (fseeko(f, (off_t)coff, SEEK_SET) != 0 || fread(in.data(), 1, n, f) != n) { return false; }
+		{ size_t got = 0; while (got < n) { const ssize_t r_ = pread(fileno(f), in.data() + got, n - got, (off_t)(coff + got)); if (r_ <= 0) { return false; } got += (size_t)r_; } }      // (pread: several batch builders read the file at once)
 		size_t p = 0, out = 0;
 		while (p + 18 <= n) {
 			if (in[p] != 31 || in[p + 1] != 139) { return false; }
@@ -427,11 +430,21 @@ struct BamFile {
 		vector<uint8_t> in, d; vector<Blk> blks; bool eof = false; uint64_t coff = voff >> 16; size_t skip = (size_t)(voff & 0xFFFF);
 		vector<uint8_t> carry;
 		bool done = false; size_t want = 4u << 20;
+		// (the linear index also bounds the far end: the first block with an alignment in the 16 kb bin after `end` --
+		// read and inflate up to there, not a fixed 4 MiB; the loop below carries on if that was short)
+		if (has_index && refID < (int)linear.size() && !linear[refID].empty()) {
+			const vector<uint64_t> &li = linear[refID]; size_t j = ((size_t)std::max(end, 0) >> 14) + 1;
+			while (j < li.size() && li[j] == 0) { ++j; }
+			if (j < li.size() && (li[j] >> 16) >= (voff >> 16)) { want = (size_t)((li[j] >> 16) - (voff >> 16)) + (1u << 16); }
+		}
 		while (!done) {
+			const double f0 = wall();
 			if (!read_blocks(coff, want, in, blks, eof)) { return false; }
 			if (blks.empty()) { break; }
 			d = carry; const size_t keep = d.size();
+			const double f1 = wall();
 			if (!inflate_blocks(in, blks, d, keep)) { return false; }
+			const double f2 = wall();
 			coff = blks.back().coff + blks.back().bsize;
 			// cut into records (sequential: every record names its own size), remember the ones of this region
 			size_t q = skip; skip = 0; vector<std::pair<size_t, int32_t>> recs;
@@ -444,8 +457,10 @@ struct BamFile {
 				if (rid == refID && pos >= beg) { recs.push_back(std::make_pair(q + 4, bs)); }
 				q += 4 + (size_t)bs;
 			}
+			const double f3 = wall();
 			const size_t o0 = out.size(); out.resize(o0 + recs.size());
 			parallel_for((recs.size() + 255) / 256, threads, [&](size_t c) { for (size_t i = c * 256; i < std::min(recs.size(), (c + 1) * 256); ++i) { decode_record(d.data() + recs[i].first, recs[i].second, out[o0 + i]); } });
+			{ const double f4 = wall(); std::lock_guard<std::mutex> lk(t_mu); t_read += f1 - f0; t_inflate += f2 - f1; t_cut += f3 - f2; t_decode += f4 - f3; }
 			carry.assign(d.begin() + (done ? d.size() : q), d.end());
 			if (eof) { break; }
 			want = std::min<size_t>(want * 2, 64u << 20);
@@ -662,6 +677,10 @@ int main(int argc, char **argv)
 	if (o.rank < 0) { o.rank = 0; o.world = 1; }
 	const bool lead = o.rank == 0;
 
+	// LB2_CLI_TIMING=1: where the wall time of this run went (stderr)
+	const bool timing = getenv("LB2_CLI_TIMING") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t_start = now(); double t_fetch = 0, t_pool = 0, t_rank = 0, t_select = 0, t_process = 0, t_wait = 0; std::mutex t_mu;
 	BamFile T, N;
 	if (!T.open(o.tumor, (unsigned)o.io_threads)) { std::cerr << "Could not open tumor BAM file." << std::endl; return -1; }
 	if (!N.open(o.normal, (unsigned)o.io_threads)) { std::cerr << "Could not open normal BAM file." << std::endl; return -1; }
@@ -672,6 +691,7 @@ int main(int argc, char **argv)
 		}
 		o.active_regions = false;
 	}
+	const double t_open = now();
 	vector<Window> wins; int num_windows = 0, t = 0;
 	for (size_t r = 0; r < regions.size(); ++r) { t = load_refs(o, T, regions[r], wins, r < n_bed_regions ? t : 0, num_windows); }      // loadBed carries the thread counter, --reg restarts at 0
 	{	// reftable[T] is a std::map keyed by the header: a second window with the same header on the same thread is dropped
@@ -680,21 +700,17 @@ int main(int argc, char **argv)
 		wins.swap(uniq);
 	}
 	if (lead) { std::cerr << num_windows << " total windows to process" << std::endl; }
-
-	// ---- the GPU side ---------------------------------------------------------------------------------------------
+	const double t_refs = now();
+	// the CUDA context before the batch builders start, alone: created beside the batch builders (16 threads inflating, decoding, allocating) it
+	// took 3-4 s instead of 1 s on the B200 box -- the two contend for the process's address-space lock
 	lb2_params p; lb2_default_params(&p);
 	p.min_k = o.minK; p.max_k = o.maxK; p.min_qual_trim = o.min_qv_trim + o.qv_range; p.min_qual_call = o.min_qv_call + o.qv_range; p.cov_threshold = o.cov_thr;
 	p.low_cov_threshold = o.low_cov; p.max_tip_len = o.tip_len; p.dfs_limit = o.dfs_limit; p.max_indel_len = o.max_indel_len; p.max_mismatch = o.max_mismatch;
 	p.max_unit_len = o.max_unit_len; p.min_report_units = o.min_report_units; p.min_report_len = o.min_report_len; p.dist_from_str = o.dist_from_str; p.min_cov_ratio = o.cov_ratio;
-	lb2_ctx *ctx = nullptr;
-	int rc = lb2_create(&ctx, &p, o.gpu + o.rank);
-	if (rc != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
-	if (o.world > 1) {
-		char id[LB2_COMM_ID_BYTES]; std::ifstream idf(o.nccl_id_file, std::ios::binary);
-		bool id_ok = (bool)idf.read(id, sizeof id);
-		if (id_ok) { quiet.on(); rc = lb2_comm_init(ctx, id, o.rank, o.world); quiet.off(); }
-		if (!id_ok || rc != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": NCCL set-up failed: " << lb2_strerror(ctx, rc) << std::endl; return 2; }
-	}
+	lb2_ctx *ctx = nullptr; int rc_create = LB2_OK;
+	rc_create = lb2_create(&ctx, &p, o.gpu + o.rank);
+	if (rc_create != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc_create) << std::endl; return 2; }
+	const double t_ctx = now();
 
 	// ---- this rank's windows, in batches: fetch the reads of the batch's span once per sample (BAI), select per window ----
 	const size_t wlo = wins.size() * (size_t)o.rank / (size_t)o.world, whi = wins.size() * (size_t)(o.rank + 1) / (size_t)o.world;
@@ -723,7 +739,9 @@ int main(int argc, char **argv)
 		int left_all = INT32_MAX, right_all = 0; for (size_t wi = a; wi < b; ++wi) { left_all = std::min(left_all, wins[wi].refstart); right_all = std::max(right_all, wins[wi].refend); }
 		const string &chr = wins[a].chr;
 		vector<Aln> A[2];
+		double tb0 = now();
 		if (!T.fetch(ref_id(T, chr), left_all, right_all, A[0]) || !N.fetch(ref_id(N, chr), left_all, right_all, A[1])) { std::cerr << "ERROR: cannot read the BAM files (truncated or corrupt?)" << std::endl; exit(2); }
+		double tb1 = now();
 		// the pool: every usable alignment of the span once, tumour first
 		vector<int64_t> pool_of[2]; uint32_t n_reads = 0; uint64_t n_base = 0;
 		for (int s_ = 0; s_ < 2; ++s_) { pool_of[s_].assign(A[s_].size(), -1); for (size_t i = 0; i < A[s_].size(); ++i) { if (usable(A[s_][i], s_)) { pool_of[s_][i] = n_reads++; n_base += A[s_][i].seq.size(); } } }
@@ -742,9 +760,12 @@ int main(int argc, char **argv)
 				bo += al.seq.size(); base_off[r + 1] = bo;
 			}
 		}
+		double tb2 = now();
 		lb2_rank_names(names.data(), n_reads, rank);
+		double tb3 = now();
 		uint32_t *ref_off = (uint32_t *)hb.ref_off.need(4 * (b - a + 1)), *wr_off = (uint32_t *)hb.wr_off.need(4 * (b - a + 1)), *chr_id = (uint32_t *)hb.chr_id.need(4 * (b - a + 1));
 		int32_t *ref_start = (int32_t *)hb.ref_start.need(4 * (b - a + 1));
+		hb.wr_idx.need(4 * ((size_t)n_reads * 8 + 1024)); hb.ref_seq.need((b - a) * 640 + 64);      // (a read lies in ~6 windows: one page-locked allocation, not a series of growing ones)
 		uint32_t nw = 0; uint64_t n_wr = 0, n_ref = 0; ref_off[0] = 0; wr_off[0] = 0;
 		for (size_t wi = a; wi < b; ++wi) {
 			const Window &w = wins[wi];
@@ -782,23 +803,45 @@ int main(int argc, char **argv)
 		}
 		hb.wr_idx.need(4 * (n_wr + 1), 4 * n_wr); hb.ref_seq.need(n_ref + 64, n_ref);
 		hb.n_windows = nw; hb.n_reads = n_reads; hb.n_wr = n_wr; hb.n_ref = n_ref; hb.n_base = n_base;
+		{ const double tb4 = now(); std::lock_guard<std::mutex> lk(t_mu); t_fetch += tb1 - tb0; t_pool += tb2 - tb1; t_rank += tb3 - tb2; t_select += tb4 - tb3; }
 	};
-	// batches of consecutive windows on one chromosome; a producer thread reads and selects for batch i+1 while the GPU assembles batch i
+	// batches of consecutive windows on one chromosome.  The host side (BGZF inflate, record decode, filters, window
+	// selection) is what a run spends its time on -- the GPU needs ~2.5 ms per 1000 windows -- so several builder threads
+	// prepare different batches at once (builder p: batches p, p + P, ...; each with its share of the I/O threads) into a
+	// ring of page-locked slots, and the GPU consumes them in order.  Regions too small for --batch-windows are still cut
+	// into a few batches per builder.
+	const unsigned P = (unsigned)std::max(1, std::min(4, o.io_threads / 4)), NS = 2 * P;
+	T.threads = N.threads = std::max(1u, (unsigned)o.io_threads / P);
+	const size_t per_batch = std::min<size_t>((size_t)std::max(1, o.batch_windows), std::max<size_t>(256, (whi - wlo + 2 * P - 1) / (2 * P)));
 	vector<std::pair<size_t, size_t>> spans;
-	for (size_t a = wlo; a < whi; ) { size_t b = a; while (b < whi && b - a < (size_t)o.batch_windows && wins[b].chr == wins[a].chr) { ++b; } spans.push_back(std::make_pair(a, b)); a = b; }
-	HostBatch slots[2]; std::mutex mu; std::condition_variable cv; int filled[2] = { 0, 0 };      // 0 free, 1 ready
-	std::thread producer([&]() {
-		for (size_t i = 0; i < spans.size(); ++i) {
-			HostBatch &hb = slots[i & 1];
-			{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[i & 1] == 0; }); }
-			build_batch(spans[i].first, spans[i].second, hb);
-			{ std::lock_guard<std::mutex> lk(mu); filled[i & 1] = 1; } cv.notify_all();
-		}
-	});
+	for (size_t a = wlo; a < whi; ) { size_t b = a; while (b < whi && b - a < per_batch && wins[b].chr == wins[a].chr) { ++b; } spans.push_back(std::make_pair(a, b)); a = b; }
+	vector<HostBatch> slots(NS); std::mutex mu; std::condition_variable cv; vector<int> filled(NS, 0);      // 0 free, 1 ready
+	vector<std::thread> builders;
+	for (unsigned pr = 0; pr < P; ++pr) {
+		builders.emplace_back([&, pr]() {
+			for (size_t i = pr; i < spans.size(); i += P) {
+				HostBatch &hb = slots[i % NS];
+				{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[i % NS] == 0; }); }
+				build_batch(spans[i].first, spans[i].second, hb);
+				{ std::lock_guard<std::mutex> lk(mu); filled[i % NS] = 1; } cv.notify_all();
+			}
+		});
+	}
+	// ---- the communicator (one process per GPU) -------------------------------------------------------------------------
+	int rc = rc_create;
+	if (o.world > 1) {
+		char id[LB2_COMM_ID_BYTES]; std::ifstream idf(o.nccl_id_file, std::ios::binary);
+		bool id_ok = (bool)idf.read(id, sizeof id);
+		if (id_ok) { quiet.on(); rc = lb2_comm_init(ctx, id, o.rank, o.world); quiet.off(); }
+		if (!id_ok || rc != LB2_OK) { std::cerr << "ERROR: rank " << o.rank << ": NCCL set-up failed: " << lb2_strerror(ctx, rc) << std::endl; fflush(nullptr); _exit(2); }
+	}
+
 	vector<lb2_variant> vars; string strs; int tot_skip = 0; uint32_t n_failed = 0;      // this rank's records: window = index into wins, str_off into strs
 	for (size_t i = 0; i < spans.size(); ++i) {
-		HostBatch &hb = slots[i & 1];
-		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[i & 1] == 1; }); }
+		HostBatch &hb = slots[i % NS];
+		const double tw0 = now();
+		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[i % NS] == 1; }); }
+		t_wait += now() - tw0;
 		tot_skip += hb.skipped;
 		if (hb.n_windows) {
 			lb2_batch b; memset(&b, 0, sizeof b);
@@ -807,7 +850,9 @@ int main(int argc, char **argv)
 			b.wr_idx = (const uint32_t *)hb.wr_idx.p; b.base_off = (const uint64_t *)hb.base_off.p; b.flags = (const uint8_t *)hb.flags.p; b.name_rank = (const uint32_t *)hb.name_rank.p;
 			b.ref_seq = (const char *)hb.ref_seq.p; b.seq = (const char *)hb.seq.p; b.qual = (const char *)hb.qual.p;
 			lb2_result res; memset(&res, 0, sizeof res);
+			const double tp0 = now();
 			rc = lb2_process(ctx, &b, &res);
+			t_process += now() - tp0; if (timing) { std::cerr << "[timing] lb2_process of batch " << i << ": " << hb.n_windows << " windows, " << hb.n_reads << " reads, " << now() - tp0 << " s, at " << now() - t_start << " s" << std::endl; }
 			if (rc != LB2_OK) { std::cerr << "ERROR: " << lb2_strerror(ctx, rc) << std::endl; _exit(2); }
 			for (uint32_t w = 0; w < res.n_windows; ++w) {      // a window the device could not assemble would be missing from the VCF without a trace: an error, not a warning
 				if (res.windows[w].status >= LB2_WIN_OVERFLOW) {
@@ -818,9 +863,10 @@ int main(int argc, char **argv)
 			const size_t s0 = strs.size(); strs.append(res.strings, res.n_string_bytes);
 			for (uint32_t k = 0; k < res.n_variants; ++k) { lb2_variant v = res.variants[k]; v.window = hb.win_of_batch[v.window]; v.str_off += (uint32_t)s0; vars.push_back(v); }
 		}
-		{ std::lock_guard<std::mutex> lk(mu); filled[i & 1] = 0; } cv.notify_all();
+		{ std::lock_guard<std::mutex> lk(mu); filled[i % NS] = 0; } cv.notify_all();
 	}
-	producer.join();
+	for (auto &th_ : builders) { th_.join(); }
+	const double t_batches = now();
 
 	// ---- gather on rank 0 (several GPUs) ------------------------------------------------------------------------------
 	const lb2_variant *all_v = vars.data(); const char *all_s = strs.data(); uint32_t all_n = (uint32_t)vars.size();
@@ -860,6 +906,11 @@ int main(int argc, char **argv)
 	vector<std::pair<string, Variant>> vec(all.DB.begin(), all.DB.end());
 	std::sort(vec.begin(), vec.end(), byPos());
 	for (auto &kv : vec) { std::cout << kv.second.vcf(o.f); }
+	if (timing) {
+		std::cerr << "[timing] open+index " << t_open - t_start << " s, reference+tiling " << t_refs - t_open << " s, CUDA context " << t_ctx - t_refs << " s, batches " << t_batches - t_ctx << " s (" << spans.size() << " batches, " << P << " builders; consumer: waiting for a batch "
+		          << t_wait << " s, lb2_process " << t_process << " s; builders, summed: BAM fetch " << t_fetch << " s, pool " << t_pool << " s, name ranks " << t_rank << " s, window selection "
+		          << t_select << " s; inside the fetches: read " << T.t_read + N.t_read << " s, inflate " << T.t_inflate + N.t_inflate << " s, record cut " << T.t_cut + N.t_cut << " s, decode " << T.t_decode + N.t_decode << " s), gather+replay+VCF " << now() - t_batches << " s" << std::endl;
+	}
 	lb2_destroy(ctx);
 	return 0;
 }
