@@ -702,7 +702,7 @@ int main(int argc, char **argv)
 	if (lead) { std::cerr << num_windows << " total windows to process" << std::endl; }
 	const double t_refs = now();
 	// the CUDA context before the batch builders start, alone: created beside the batch builders (16 threads inflating, decoding, allocating) it
-	// took 3-4 s instead of 1 s on the B200 box -- the two contend for the process's address-space lock
+	// took 3-4 s instead of 1 s on the B200 box (presumably both want the process's address-space lock)
 	lb2_params p; lb2_default_params(&p);
 	p.min_k = o.minK; p.max_k = o.maxK; p.min_qual_trim = o.min_qv_trim + o.qv_range; p.min_qual_call = o.min_qv_call + o.qv_range; p.cov_threshold = o.cov_thr;
 	p.low_cov_threshold = o.low_cov; p.max_tip_len = o.tip_len; p.dfs_limit = o.dfs_limit; p.max_indel_len = o.max_indel_len; p.max_mismatch = o.max_mismatch;
