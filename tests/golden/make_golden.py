@@ -18,11 +18,21 @@ CASES = {
     "errors_s5": (dict(seed=5, region_len=1200, err=0.005), {}),
     "lowqual_s3": (dict(seed=3, region_len=1200, low_qual_frac=0.03), {}),
     "dense_s9": (dict(seed=9, region_len=1200, var_every=150), {}),
+    # round 2: overlapping mates (the unsorted binary_search quirk), and STR-rich windows that are only assembled at k = 83..99
+    # (at k = 99 one k-mer pair per 100 bp read: ~650 nodes in dozens of small components -- the per-component sweeps)
+    "paired_s62": (dict(seed=62, region_len=1200, paired=True, insert_mean=150, insert_sd=20), {}),
+    "str_k99": (dict(seed=1000, region_start=1_000_001, var_every=5000, region_len=100000, str_every=200, cov_t=80, cov_n=80, _windows=[289, 309, 337, 443, 715]), {}),
 }
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, (gk, hk) in CASES.items():
+        if only and name not in only:
+            continue
+        gk = dict(gk); pick = gk.pop("_windows", None)
         b = make_batch(**gk)
+        if pick is not None:
+            b = b.subset(pick)
         path = os.path.join(HERE, name + ".lb2b")
         b.save(path)
         recs, _ = run_ref.run(path=path, **hk)

@@ -59,6 +59,20 @@ def test_thread_count_changes_only_replay_order(sim_cli):
     assert outs[0] == outs[1]
 
 
+def test_batch_builders_do_not_change_the_vcf(sim_cli):
+    """many small batches prepared by four builder threads at once (out of order, consumed in order) == one batch, one builder"""
+    d = os.path.join(GOLD, "e2e_basic")
+    base = [sim_cli, "--tumor", os.path.join(d, "tumor.bam"), "--normal", os.path.join(d, "normal.bam"), "--ref", os.path.join(d, "ref.fa"), "--reg", "chr22:1-6000", "--num-threads", "2"]
+    outs = []
+    for extra in (["--batch-windows", "100000", "--io-threads", "1"], ["--batch-windows", "3", "--io-threads", "16"]):
+        r = subprocess.run(base + extra, capture_output=True, text=True, timeout=600, env=dict(os.environ, LB2_CLI_TIMING="1"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(_normalise(r.stdout))
+        timing = [l for l in r.stderr.splitlines() if l.startswith("[timing] open")]
+        assert timing and ("4 builders" in timing[0]) == (extra[-1] == "16")
+    assert outs[0] == outs[1] and sum(1 for l in outs[0].splitlines() if not l.startswith("#")) > 3
+
+
 def test_known_answers(sim_cli):
     out = subprocess.run([sim_cli, "--self-test"], capture_output=True, text=True, check=True).stdout.splitlines()
     kv = dict(l.split("=", 1) for l in out if l.startswith("sha256"))

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-CASES = {"config1_k25": dict(min_k=25, max_k=25), "small_s7": {}, "errors_s5": {}, "lowqual_s3": {}, "dense_s9": {}}
+CASES = {"config1_k25": dict(min_k=25, max_k=25), "small_s7": {}, "errors_s5": {}, "lowqual_s3": {}, "dense_s9": {}, "paired_s62": {}, "str_k99": {}}
 
 
 def _load_gz(name, tmp_path):
