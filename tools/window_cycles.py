@@ -1,9 +1,10 @@
-"""DEBUG TOOLING: per-window cycle counts (needs the -DLB2_PROFILE -DLB2_PROFILE_SEQ build, lancet_b200/_lb2_profseq.so):
+"""DEBUG TOOLING: per-window cycle counts (the -DLB2_PROFILE -DLB2_PROFILE_SEQ build, lancet_b200/_lb2_profseq.so):
 the slowest windows of a synthetic workload, the distribution, and the phase shares of the slowest ones alone."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["LB2_SO"] = os.path.join(ROOT, "lancet_b200", "_lb2_profseq.so")
+import __graft_entry__ as _g
+os.environ["LB2_SO"] = _g.build_profile(per_window=True)
 from lancet_b200.api import Context
 from lancet_b200.synth import make_batch
 import numpy as np
