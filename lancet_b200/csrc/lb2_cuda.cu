@@ -14,6 +14,7 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <atomic>
 #include <thread>
 #include <chrono>
 
@@ -634,7 +635,8 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 	// hundred windows are planned right here; everything the first-pass launches need is fixed by lb2_prepare_static.
 	int plan_rc = LB2_OK; std::thread planner; struct lb2_joiner { std::thread &t; ~lb2_joiner() { if (t.joinable()) { t.join(); } } } joiner{ planner };
 	bool planning = false;
-	if (pinned && W >= 4096 && env_u32("LB2_PLAN_OVERLAP", 1)) { planner = std::thread([&]() { plan_rc = lb2_plan_windows(ctx, batch); }); planning = true; }
+	std::atomic<bool> plan_done(false);
+	if (pinned && W >= 4096 && env_u32("LB2_PLAN_OVERLAP", 1)) { planner = std::thread([&]() { plan_rc = lb2_plan_windows(ctx, batch); plan_done.store(true, std::memory_order_release); }); planning = true; }
 	else { if ((rc = lb2_plan_windows(ctx, batch))) { return rc; } if ((rc = lb2_prepare_escalation(ctx))) { return rc; } }
 	const auto t1 = std::chrono::steady_clock::now();
 	LB2_CK(cudaFuncSetAttribute(lb2_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_cap));
@@ -717,7 +719,9 @@ extern "C" int lb2_process(lb2_ctx *ctx, const lb2_batch *batch, lb2_result *res
 		if (timing) { cudaEventRecord(tl[3 * s + 1], ws); }
 		if ((rc = lb2_enqueue_windows(ctx, sg.w0, sg.w1, pinned ? (uint32_t)(s & 1) : 0u, (uint32_t)s, ws))) { return rc; }
 		if (timing) { cudaEventRecord(tl[3 * s + 2], ws); }
-		if (planning) {      // the first segment is on its way: now the plan is needed (stretches of the other windows, sizes of the escalation passes)
+		// the plan is taken over as soon as it is there (until then the segments work their windows' stretches out themselves,
+		// which keeps the copy and compute streams fed); it is only NEEDED for the sizes of the escalation passes, below
+		if (planning && (plan_done.load(std::memory_order_acquire) || wa >= W)) {
 			planner.join(); planning = false;
 			if (plan_rc == LB2_OK) { plan_rc = lb2_prepare_escalation(ctx); }
 			if (plan_rc != LB2_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->pack_stream); cudaStreamSynchronize(ctx->wstream[0]); cudaStreamSynchronize(ctx->wstream[1]); return plan_rc; }
