@@ -245,6 +245,7 @@ struct Aln {
 	string name, seq, qual, md, xt, xa;
 	vector<uint32_t> cigar;                // BAM encoding: len << 4 | op
 	float as = -1, xs = -1; bool has_md = false;
+	mutable vector<int32_t> ev; mutable bool ev_done = false;      // isActiveRegion evidence of this read, (position << 2 | kind), made on first use (a read lies in ~6 windows)
 };
 
 static double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -528,7 +529,11 @@ static int load_refs(const Opts &o, const BamFile &bam, const string &region, ve
 // ------------------------------------------------------------------------------------------------------------
 // isActiveRegion (src/Microassembler.cc:255-432) and parseMD (src/util.cc:432-483) on decoded records
 // ------------------------------------------------------------------------------------------------------------
-static void parse_md(const string &md, std::map<int, int> &M, int start, const string &qual, int min_qv)
+// The reference counts, per window, the reads that show a mismatch (MD tag, base quality permitting, or an X operation),
+// an insertion, a deletion or a soft clip at each position (four std::map<int,int>) and calls the window active when some
+// count reaches MIN_EVIDENCE.  What one read contributes does not depend on the window: it is listed once per read
+// (kind 0 mismatch, 1 insertion, 2 deletion, 3 soft clip), the window then only merges the lists of its reads.
+static void parse_md(const string &md, vector<int32_t> &ev, int start, const string &qual, int min_qv)
 {
 	const string valid = "acgtumrwsykvhdbxnACGTUMRWSYKVHDBXN^";
 	size_t p = md.find_first_of(valid), p_old = (size_t)-1, p2; int pos = start; size_t rpos = 0;
@@ -541,38 +546,47 @@ static void parse_md(const string &md, std::map<int, int> &M, int start, const s
 		} else {
 			++pos; ++rpos;
 			char q = (rpos < qual.length()) ? qual[rpos] : (char)0;          // qual[len] is the terminating NUL of the reference's std::string
-			if (q >= min_qv) { ++M[pos]; }
+			if (q >= min_qv) { ev.push_back(pos * 4 + 0); }
 			p_old = p; p = md.find_first_of(valid, p_old + 1);
 		}
 	}
 }
+static void read_evidence(const Aln &al, int min_qv)
+{
+	al.ev.clear(); al.ev_done = true;
+	if (al.has_md) { parse_md(al.md, al.ev, al.pos, al.qual, min_qv); }
+	int pos = al.pos;
+	for (uint32_t c : al.cigar) {
+		int op = c & 15; int len = (int)(c >> 4);
+		if (op != 1) { pos += len; }                 // every operation except 'I' advances (literal, src/Microassembler.cc:321)
+		if (op == 8) { al.ev.push_back(pos * 4 + 0); } if (op == 1) { al.ev.push_back(pos * 4 + 1); } if (op == 2) { al.ev.push_back(pos * 4 + 2); }
+	}
+	int refp = al.pos;                               // BamAlignment::GetSoftClips genome positions
+	for (uint32_t c : al.cigar) {
+		int op = c & 15; int len = (int)(c >> 4);
+		if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) { refp += len; }
+		else if (op == 4) { al.ev.push_back(refp * 4 + 3); }
+	}
+}
 
-static bool is_active(const vector<Aln> &alns, size_t lo, size_t hi, int left, int right, bool normal, const Opts &o)
+static bool is_active(const vector<Aln> &alns, size_t lo, size_t hi, int left, int right, bool normal, const Opts &o, vector<int32_t> &scratch)
 {
 	int MQ = normal ? 0 : o.min_map_qual; const int MIN_EVIDENCE = o.f.minAltCntTumor;
-	std::map<int, int> mX, mI, mD, mSC;
+	scratch.clear();
 	for (size_t i = lo; i < hi; ++i) {
 		const Aln &al = alns[i];
 		if (al.pos < left || al.end > right) { continue; }
 		if (!(al.mapq >= MQ && !(al.flag & 0x400))) { continue; }
 		if (al.seq.empty() || al.qual.empty()) { continue; }
-		if (al.has_md) { parse_md(al.md, mX, al.pos, al.qual, o.min_qv_call + o.qv_range); }
-		int pos = al.pos;
-		for (uint32_t c : al.cigar) {
-			int op = c & 15; int len = (int)(c >> 4);
-			if (op != 1) { pos += len; }                 // every operation except 'I' advances (literal, src/Microassembler.cc:321)
-			if (op == 8) { ++mX[pos]; } if (op == 1) { ++mI[pos]; } if (op == 2) { ++mD[pos]; }
-		}
-		int refp = al.pos; bool firstop = true;          // BamAlignment::GetSoftClips genome positions
-		for (uint32_t c : al.cigar) {
-			int op = c & 15; int len = (int)(c >> 4);
-			if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) { refp += len; }
-			else if (op == 4) { ++mSC[refp]; }
-			(void)firstop; firstop = false;
-		}
+		if (!al.ev_done) { read_evidence(al, o.min_qv_call + o.qv_range); }
+		scratch.insert(scratch.end(), al.ev.begin(), al.ev.end());
 	}
-	auto any = [&](const std::map<int, int> &m) { for (auto &kv : m) { if (kv.second >= MIN_EVIDENCE) { return true; } } return false; };
-	return any(mX) || any(mI) || any(mD) || any(mSC);
+	std::sort(scratch.begin(), scratch.end());       // equal (position, kind) next to each other: a run of MIN_EVIDENCE is a map entry that reached it
+	for (size_t i = 0, j = 0; i < scratch.size(); i = j) {
+		while (j < scratch.size() && scratch[j] == scratch[i]) { ++j; }
+		if ((long)(j - i) >= (long)MIN_EVIDENCE) { return true; }
+	}
+	return false;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -767,6 +781,7 @@ int main(int argc, char **argv)
 		int32_t *ref_start = (int32_t *)hb.ref_start.need(4 * (b - a + 1));
 		hb.wr_idx.need(4 * ((size_t)n_reads * 8 + 1024)); hb.ref_seq.need((b - a) * 640 + 64);      // (a read lies in ~6 windows: one page-locked allocation, not a series of growing ones)
 		uint32_t nw = 0; uint64_t n_wr = 0, n_ref = 0; ref_off[0] = 0; wr_off[0] = 0;
+		vector<int32_t> ev_scratch;
 		for (size_t wi = a; wi < b; ++wi) {
 			const Window &w = wins[wi];
 			if (w.raw.empty()) { continue; }
@@ -777,7 +792,7 @@ int main(int argc, char **argv)
 				hi[s_] = std::lower_bound(A[s_].begin(), A[s_].end(), right, [](const Aln &x, int v) { return x.pos < v; }) - A[s_].begin();
 			}
 			bool activeT = true, activeN = true;
-			if (o.active_regions) { activeT = is_active(A[0], lo[0], hi[0], left, right, false, o); activeN = is_active(A[1], lo[1], hi[1], left, right, true, o); }
+			if (o.active_regions) { activeT = is_active(A[0], lo[0], hi[0], left, right, false, o, ev_scratch); activeN = is_active(A[1], lo[1], hi[1], left, right, true, o, ev_scratch); }
 			if (!(activeT || activeN)) { ++hb.skipped; continue; }
 			const uint64_t wr0 = n_wr; bool skip = false;
 			uint32_t *wr_idx = (uint32_t *)hb.wr_idx.need(4 * (n_wr + (hi[0] - lo[0]) + (hi[1] - lo[1]) + 1), 4 * n_wr);
